@@ -1,0 +1,258 @@
+"""Batch entry point over the C ABI (``include/bsqgpu.h``).
+
+The reference API is one ``Aligner`` per pair; a GPU needs whole batches, so
+this module takes packed numpy buffers (all letters in one uint8 array plus
+per-pair offsets/lengths) and returns arrays.  ``biseqt_b200.pw.Aligner`` is a
+batch of one on top of this.
+"""
+import numpy as np
+
+from . import _ffi
+from ._ffi import ffi, CONST, BsqError
+
+STATUS_NAMES = {
+    CONST['BSQ_OK']: 'OK', CONST['BSQ_NO_ALIGNMENT']: 'NO_ALIGNMENT',
+    CONST['BSQ_EMPTY']: 'EMPTY', CONST['BSQ_INIT_FAIL']: 'INIT_FAIL',
+    CONST['BSQ_REF_WOULD_ABORT']: 'REF_WOULD_ABORT', CONST['BSQ_UNSUPPORTED']: 'UNSUPPORTED',
+}
+OK, NO_ALIGNMENT, EMPTY, INIT_FAIL, REF_WOULD_ABORT, UNSUPPORTED = 0, 1, 2, 3, 4, 5
+DTYPE_F64, DTYPE_I32, DTYPE_AUTO = 0, 1, -1
+DTYPE_NAMES = {0: 'f64', 1: 'i32'}
+
+
+def _ptr(a, ctype):
+    return ffi.NULL if a is None else ffi.cast(ctype, a.ctypes.data)
+
+
+def _c(a, dt):
+    if a is None:
+        return None
+    a = np.asarray(a)
+    if a.dtype != dt or not a.flags['C_CONTIGUOUS']:
+        a = np.ascontiguousarray(a, dtype=dt)
+    return a
+
+
+class BatchResult(object):
+    """Arrays of a finished batch; transcripts are packed in ``tx_buf``."""
+
+    def __init__(self, score, end_x, end_y, start_x, start_y, status, tx_off, tx_buf):
+        self.score, self.end_x, self.end_y = score, end_x, end_y
+        self.start_x, self.start_y, self.status = start_x, start_y, status
+        self.tx_off, self.tx_buf = tx_off, tx_buf
+
+    def __len__(self):
+        return len(self.score)
+
+    def transcript(self, i):
+        if self.tx_off is None:
+            return None
+        return bytes(self.tx_buf[self.tx_off[i]:self.tx_off[i + 1]]).decode()
+
+    def transcripts(self):
+        return [self.transcript(i) for i in range(len(self))]
+
+    @property
+    def tx_len(self):
+        return np.diff(self.tx_off).astype(np.int32)
+
+
+class Engine(object):
+    """One GPU context (``bsq_ctx``).  Single-owner, not thread-safe."""
+
+    def __init__(self, device=0, lib=None):
+        self.lib = lib if lib is not None else _ffi.load()
+        self.ctx = self.lib.bsq_create(int(device))
+        if self.ctx == ffi.NULL:
+            raise BsqError('bsq_create(%d) failed: %s' % (
+                device, ffi.string(self.lib.bsq_last_error(ffi.NULL)).decode()))
+        self.device = device
+        self._keep = None
+
+    def close(self):
+        if self.ctx is not None and self.ctx != ffi.NULL:
+            self.lib.bsq_destroy(self.ctx)
+        self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _err(self):
+        return ffi.string(self.lib.bsq_last_error(self.ctx)).decode()
+
+    def pinned_empty(self, n, dtype):
+        """1-D numpy array in page-locked host memory (full-speed H2D/D2H)."""
+        dtype = np.dtype(dtype)
+        nbytes = int(n) * dtype.itemsize
+        p = self.lib.bsq_host_alloc(max(nbytes, 1))
+        if p == ffi.NULL:
+            raise BsqError('bsq_host_alloc(%d) failed' % nbytes)
+        p = ffi.gc(p, self.lib.bsq_host_free, size=nbytes)
+        arr = np.frombuffer(ffi.buffer(p, max(nbytes, 1)), dtype=dtype, count=int(n))
+        arr._bsq_pin = p if False else None  # numpy keeps the buffer (and so `p`) alive
+        return arr
+
+    def _params(self, mode, type, subst, go, ge, dtype=DTYPE_AUTO, max_new_mins=-1):
+        S = np.ascontiguousarray(np.asarray(subst, dtype=np.float64))
+        assert S.ndim == 2 and S.shape[0] == S.shape[1], 'subst must be L x L'
+        prm = ffi.new('bsq_params*')
+        prm.mode, prm.type = int(mode), int(type)
+        prm.alphabet_len = S.shape[0]
+        prm.max_new_mins = int(max_new_mins)
+        prm.go, prm.ge = float(go), float(ge)
+        prm.subst = ffi.cast('double*', S.ctypes.data)
+        prm.dtype = int(dtype)
+        return prm, S
+
+    def align(self, codes, o_off, o_len, m_off, m_len, mode, type, subst, go, ge,
+              dmin=None, dmax=None, dtype=DTYPE_AUTO, transcripts=True, out=None,
+              max_new_mins=-1):
+        """dptable_init + solve + traceback + free for a whole batch
+        (``bsq_align_batch``).  Returns :class:`BatchResult`.  ``out`` may hold
+        preallocated (e.g. pinned) arrays under the result's field names."""
+        codes = _c(codes, np.uint8)
+        o_off, m_off = _c(o_off, np.int64), _c(m_off, np.int64)
+        o_len, m_len = _c(o_len, np.int32), _c(m_len, np.int32)
+        dmin, dmax = _c(dmin, np.int32), _c(dmax, np.int32)
+        N = len(o_len)
+        prm, S = self._params(mode, type, subst, go, ge, dtype, max_new_mins)
+        out = out or {}
+
+        def arr(name, dt, n):
+            a = out.get(name)
+            if a is None:
+                a = np.empty(n, dtype=dt)
+            assert a.dtype == dt and len(a) >= n
+            return a
+        score = arr('score', np.float64, N)
+        end_x, end_y = arr('end_x', np.int32, N), arr('end_y', np.int32, N)
+        start_x, start_y = arr('start_x', np.int32, N), arr('start_y', np.int32, N)
+        status = arr('status', np.int32, N)
+        tx_off = tx_buf = None
+        cap = 0
+        if transcripts:
+            cap = int(o_len.astype(np.int64).sum() + m_len.astype(np.int64).sum())
+            tx_off = arr('tx_off', np.int64, N + 1)
+            tx_buf = out.get('tx_buf')
+            if tx_buf is None or len(tx_buf) < cap:
+                tx_buf = np.empty(max(cap, 1), dtype=np.uint8)
+        total = ffi.new('int64_t*')
+        rc = self.lib.bsq_align_batch(
+            self.ctx, prm, N, _ptr(codes, 'uint8_t*'), len(codes),
+            _ptr(o_off, 'int64_t*'), _ptr(o_len, 'int32_t*'),
+            _ptr(m_off, 'int64_t*'), _ptr(m_len, 'int32_t*'),
+            _ptr(dmin, 'int32_t*'), _ptr(dmax, 'int32_t*'),
+            _ptr(score, 'double*'), _ptr(end_x, 'int32_t*'), _ptr(end_y, 'int32_t*'),
+            _ptr(start_x, 'int32_t*'), _ptr(start_y, 'int32_t*'), _ptr(status, 'int32_t*'),
+            _ptr(tx_off, 'int64_t*'), _ptr(tx_buf, 'char*'), cap, total)
+        if rc != 0:
+            raise BsqError('bsq_align_batch failed (%d): %s' % (rc, self._err()))
+        return BatchResult(score[:N], end_x[:N], end_y[:N], start_x[:N], start_y[:N],
+                           status[:N], None if tx_off is None else tx_off[:N + 1], tx_buf)
+
+    def solve(self, codes, o_off, o_len, m_off, m_len, mode, type, subst, go, ge,
+              dmin=None, dmax=None, dtype=DTYPE_AUTO, max_new_mins=-1):
+        """dptable_init + dptable_solve; tables stay in HBM (``bsq_solve_batch``)."""
+        codes = _c(codes, np.uint8)
+        o_off, m_off = _c(o_off, np.int64), _c(m_off, np.int64)
+        o_len, m_len = _c(o_len, np.int32), _c(m_len, np.int32)
+        dmin, dmax = _c(dmin, np.int32), _c(dmax, np.int32)
+        N = len(o_len)
+        prm, S = self._params(mode, type, subst, go, ge, dtype, max_new_mins)
+        score = np.empty(N, np.float64)
+        end_x, end_y = np.empty(N, np.int32), np.empty(N, np.int32)
+        status = np.empty(N, np.int32)
+        hb = ffi.new('bsq_batch**')
+        rc = self.lib.bsq_solve_batch(
+            self.ctx, prm, N, _ptr(codes, 'uint8_t*'), len(codes),
+            _ptr(o_off, 'int64_t*'), _ptr(o_len, 'int32_t*'),
+            _ptr(m_off, 'int64_t*'), _ptr(m_len, 'int32_t*'),
+            _ptr(dmin, 'int32_t*'), _ptr(dmax, 'int32_t*'),
+            _ptr(score, 'double*'), _ptr(end_x, 'int32_t*'), _ptr(end_y, 'int32_t*'),
+            _ptr(status, 'int32_t*'), hb)
+        if rc != 0:
+            raise BsqError('bsq_solve_batch failed (%d): %s' % (rc, self._err()))
+        cap = int(o_len.astype(np.int64).sum() + m_len.astype(np.int64).sum())
+        return SolvedBatch(self, hb[0], score, end_x, end_y, status, cap)
+
+    def table_scores(self, origin, mutant, type, subst, go, ge):
+        """H of every STD cell, (n+1) x (m+1) (``bsq_table_scores``)."""
+        o, t = _c(origin, np.uint8), _c(mutant, np.uint8)
+        prm, S = self._params(0, type, subst, go, ge)
+        out = np.empty((len(o) + 1, len(t) + 1), dtype=np.float64)
+        rc = self.lib.bsq_table_scores(self.ctx, prm, _ptr(o, 'uint8_t*'), len(o),
+                                       _ptr(t, 'uint8_t*'), len(t), _ptr(out, 'double*'))
+        if rc != 0:
+            raise BsqError('bsq_table_scores failed (%d): %s' % (rc, self._err()))
+        return out
+
+    def timing(self):
+        t = ffi.new('bsq_timing*')
+        self.lib.bsq_get_timing(self.ctx, t)
+        return {k: getattr(t, k) for k in ('fill_ms', 'traceback_ms', 'total_ms', 'cells',
+                                           'fill_launches', 'h2d_bytes', 'd2h_bytes',
+                                           'ptr_bytes', 'dtype', 'chunks')}
+
+
+class SolvedBatch(object):
+    """A solved batch whose pointer tables are still resident (``bsq_batch``)."""
+
+    def __init__(self, engine, handle, score, end_x, end_y, status, cap):
+        self.engine, self.handle = engine, handle
+        self.score, self.end_x, self.end_y, self.status = score, end_x, end_y, status
+        self._cap = cap
+
+    def traceback(self):
+        N = len(self.score)
+        start_x, start_y = np.empty(N, np.int32), np.empty(N, np.int32)
+        status = np.empty(N, np.int32)
+        tx_off = np.empty(N + 1, np.int64)
+        tx_buf = np.empty(max(self._cap, 1), np.uint8)
+        total = ffi.new('int64_t*')
+        rc = self.engine.lib.bsq_traceback_batch(
+            self.handle, _ptr(start_x, 'int32_t*'), _ptr(start_y, 'int32_t*'),
+            _ptr(status, 'int32_t*'), _ptr(tx_off, 'int64_t*'), _ptr(tx_buf, 'char*'),
+            self._cap, total)
+        if rc != 0:
+            raise BsqError('bsq_traceback_batch failed (%d): %s' % (rc, self.engine._err()))
+        return BatchResult(self.score, self.end_x, self.end_y, start_x, start_y, status,
+                           tx_off, tx_buf)
+
+    def release(self):
+        if self.handle is not None:
+            self.engine.lib.bsq_release(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+def pack_pairs(pairs):
+    """[(origin_codes, mutant_codes), ...] -> (codes, o_off, o_len, m_off, m_len)."""
+    o_len = np.array([len(p[0]) for p in pairs], dtype=np.int32)
+    m_len = np.array([len(p[1]) for p in pairs], dtype=np.int32)
+    tot = int(o_len.sum() + m_len.sum())
+    codes = np.zeros(max(tot, 1), dtype=np.uint8)
+    o_off = np.zeros(len(pairs), dtype=np.int64)
+    m_off = np.zeros(len(pairs), dtype=np.int64)
+    pos = 0
+    for i, (o, t) in enumerate(pairs):
+        o_off[i] = pos
+        codes[pos:pos + len(o)] = o
+        pos += len(o)
+        m_off[i] = pos
+        codes[pos:pos + len(t)] = t
+        pos += len(t)
+    return codes, o_off, o_len, m_off, m_len

@@ -1,0 +1,82 @@
+// bsq_common.h -- shared host/device declarations of libbsqgpu.
+#pragma once
+#include <stdint.h>
+
+#ifdef BSQ_SIMT_EMU
+// tests/simt_emu: the same sources compiled for a CPU fiber emulator so that
+// kernel logic can be checked without a GPU.  Never part of the product .so.
+#include "simt_emu.h"
+#define BSQ_LAUNCH(kern, grid, block, smem, stream, ...) \
+  emu::launch(kern, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__)
+#define BSQ_HD
+#else
+#include <cuda_runtime.h>
+#define BSQ_LAUNCH(kern, grid, block, smem, stream, ...) \
+  kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define BSQ_HD __host__ __device__
+#endif
+
+// tied-max mask bits, in the reference's candidate order (pw.c:77-80)
+#define BSQ_MB 1u
+#define BSQ_MD 2u
+#define BSQ_MI 4u
+#define BSQ_MM 8u
+
+#define BSQ_MAX_L 32  // largest alphabet the kernels stage in shared memory
+
+// where B (start of alignment) is allowed: _alnchoice_B, _pw_internals.c:161-209
+enum { BSQ_B_ORIGIN = 0, BSQ_B_EDGE = 1, BSQ_B_ALL = 2 };
+// where an alignment may end: _std_find_optimal / _banded_find_optimal, :303-414
+enum { BSQ_E_CORNER = 0, BSQ_E_EDGE = 1, BSQ_E_ALL = 2 };
+// sign of gap_open_score decides the D/I tie rules (_pw_internals.c:266-278)
+enum { BSQ_GO_NEG = -1, BSQ_GO_ZERO = 0, BSQ_GO_POS = 1 };
+
+struct BsqPair {         // one problem of a chunk, device resident
+  long long o_off;       // frame start of origin in codes[]
+  long long m_off;       // frame start of mutant in codes[]
+  long long ptr_off;     // first uint32 word of this pair's pointer table
+  long long tx_slot;     // first byte of this pair's transcript slot (cap n+m)
+  int n, m;              // frame lengths
+  int dmin, dmax;        // clipped band (BANDED)
+  int s0;                // first anti-diagonal x+y the banded kernel visits
+  int pad;
+};
+
+struct BsqFillArgs {
+  const uint8_t* codes;
+  const BsqPair* pairs;
+  int npairs;
+  int L;
+  const void* subst;     // L*L scores already converted to the kernel's type
+  double go_d, ge_d;
+  int go_i, ge_i;
+  int bmode, emode;      // STD: BSQ_B_* / BSQ_E_* of the alignment type
+  int btype;             // BANDED: banded_alntype
+  uint32_t* ptr;         // pointer-table arena
+  double* out_score;
+  int* out_ex;
+  int* out_ey;
+  int* out_status;
+  int* counter;          // dynamic work queue head
+  // STD multi-pass boundary column scratch, one slab per resident group
+  double* col_h;         // (also used for int scores, stored as double-sized slots)
+  uint8_t* col_f;
+  long long col_stride;  // entries per group
+};
+
+struct BsqTraceArgs {
+  const uint8_t* codes;
+  const BsqPair* pairs;
+  int npairs;
+  int mode;              // BSQ_STD_MODE / BSQ_BANDED_MODE
+  int G, K;              // geometry of the fill kernel that wrote the tables
+  int gosign;
+  const uint32_t* ptr;
+  const int* ex;
+  const int* ey;
+  int* status;           // in: OK / NO_ALIGNMENT from the fill; out: final class
+  int* sx;
+  int* sy;
+  int* txlen;
+  char* slots;           // transcripts, right-aligned in [tx_slot, tx_slot+n+m)
+};

@@ -1,0 +1,855 @@
+// bsq_host.cu -- C ABI of libbsqgpu (include/bsqgpu.h) and the host-side
+// batch scheduler: classifies every pair the way dptable_init would
+// (_pw_internals.c:22-62), picks the kernel geometry, orders pairs by size,
+// cuts the batch into chunks whose pointer tables fit the HBM arena, and
+// drives fill -> traceback -> pack on the context's stream.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bsqgpu.h"
+#include "bsq_post.cuh"
+#include "bsq_launch.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  bool ensure(size_t n) {
+    if (n <= cap && p) return true;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = n + n / 16 + 256;
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+      p = nullptr;
+      cudaGetLastError();
+      want = n ? n : 256;
+      if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; cudaGetLastError(); return false; }
+    }
+    cap = want;
+    return true;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  bool ensure(size_t n) {
+    if (n <= cap && p) return true;
+    if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+    size_t want = n + n / 16 + 256;
+    if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { p = nullptr; cudaGetLastError(); return false; }
+    cap = want;
+    return true;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+struct BufSet {  // everything one batch needs in HBM
+  DevBuf codes, pairs, ptr, slots, packed, score, ex, ey, sx, sy, status, txlen, txoff, tiles,
+      subst, counters, colh, colf, total;
+  PinBuf hpairs, hsmall;
+  void release() {
+    DevBuf* all[] = {&codes, &pairs, &ptr, &slots, &packed, &score, &ex, &ey, &sx, &sy, &status,
+                     &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total};
+    for (DevBuf* b : all) b->release();
+    hpairs.release();
+    hsmall.release();
+  }
+};
+
+struct Chunk {
+  int64_t first, count;  // range in processing order
+  int family;            // 1 = K1 (STD), 2 = K2 (BANDED)
+  int cfg;
+  int64_t ptr_words;
+  int max_n_multipass;   // K1: longest origin among pairs needing > 1 pass (0 if none)
+};
+
+struct Override { int64_t idx; int status; };
+
+struct Plan {
+  bsq_params prm;
+  std::vector<double> subst;
+  int64_t N = 0;
+  int dtype = BSQ_DTYPE_F64;
+  int gosign = 0;
+  int bmode = 0, emode = 0;
+  std::vector<BsqPair> pairs;      // processing order
+  std::vector<Chunk> chunks;
+  std::vector<Override> overrides; // pairs never sent to the GPU
+  int64_t cells = 0;
+  int64_t slot_bytes = 0;
+  int64_t max_chunk_words = 0;
+  int64_t total_words = 0;
+};
+
+}  // namespace
+
+struct bsq_ctx {
+  int device = 0;
+  int sms = 1;
+  cudaStream_t st = nullptr;
+  std::string err;
+  bsq_timing tm;
+  BufSet bufs;
+  std::vector<cudaEvent_t> events;
+  size_t arena_cap_bytes = 0;  // test hook / safety: upper bound for the pointer arena
+};
+
+struct bsq_batch {
+  bsq_ctx* ctx = nullptr;
+  Plan plan;
+  BufSet bufs;
+  bool have_codes = false;
+};
+
+namespace {
+
+#define BSQ_CK(ctx, call)                                                          \
+  do {                                                                             \
+    cudaError_t e_ = (call);                                                       \
+    if (e_ != cudaSuccess) {                                                       \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);             \
+      return BSQ_ERR_CUDA;                                                         \
+    }                                                                              \
+  } while (0)
+
+int fail(bsq_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  g_err = msg;
+  return code;
+}
+
+// ---- geometry helpers (pure host) ---------------------------------------
+
+// cells of one diagonal d of an (n+1)x(m+1) table: row_lens[], _pw_internals.c:56
+inline int64_t diag_len(int n, int m, int d) {
+  return 1 + (int64_t)(d > 0 ? 0 : d) + (int64_t)((int64_t)n - d > m ? m : n - d);
+}
+
+int64_t count_cells(int mode, int n, int m, int dmin, int dmax) {
+  if (mode == BSQ_STD_MODE) return (int64_t)(n + 1) * (m + 1);
+  if (dmax > n) dmax = n;
+  if (dmin < -m) dmin = -m;
+  if (dmax < dmin) return 0;
+  // sum of diag_len over [dmin,dmax], closed form over the three linear pieces
+  auto sum_range = [&](int64_t a, int64_t b, auto f) -> int64_t {  // f linear in d
+    if (b < a) return 0;
+    return (f(a) + f(b)) * (b - a + 1) / 2;
+  };
+  const int64_t lo = std::min(0, n - m), hi = std::max(0, n - m);
+  int64_t acc = 0;
+  {  // d in [dmin, min(dmax, lo-1)]: len rises with slope 1
+    int64_t a = dmin, b = std::min<int64_t>(dmax, lo - 1);
+    acc += sum_range(a, b, [&](int64_t d) { return diag_len(n, m, (int)d); });
+  }
+  {  // d in [max(dmin,lo), min(dmax,hi)]: plateau (constant)
+    int64_t a = std::max<int64_t>(dmin, lo), b = std::min<int64_t>(dmax, hi);
+    acc += sum_range(a, b, [&](int64_t d) { return diag_len(n, m, (int)d); });
+  }
+  {  // d in [max(dmin,hi+1), dmax]: falls with slope -1
+    int64_t a = std::max<int64_t>(dmin, hi + 1), b = dmax;
+    acc += sum_range(a, b, [&](int64_t d) { return diag_len(n, m, (int)d); });
+  }
+  return acc;
+}
+
+inline bool is_integer(double v) { return std::isfinite(v) && v == std::floor(v); }
+
+// Bound on |any partial score|: every path has at most n+m ops, each adding at
+// most maxabs (a gap op adds ge and possibly go).
+bool scores_int32_exact(const bsq_params* p, int64_t max_n, int64_t max_m) {
+  const int L = p->alphabet_len;
+  double maxabs = std::fabs(p->go) + std::fabs(p->ge);
+  if (!is_integer(p->go) || !is_integer(p->ge)) return false;
+  for (int i = 0; i < L * L; i++) {
+    if (!is_integer(p->subst[i])) return false;
+    maxabs = std::max(maxabs, std::fabs(p->subst[i]));
+  }
+  const double R = (double)(max_n + max_m + 4) * maxabs;
+  return R < (double)(1 << 29);
+}
+
+void std_modes(int type, int* bmode, int* emode) {
+  // _alnchoice_B (_pw_internals.c:165-181) and _std_find_optimal (:309-355)
+  switch (type) {
+    case BSQ_GLOBAL: *bmode = BSQ_B_ORIGIN; *emode = BSQ_E_CORNER; break;
+    case BSQ_LOCAL: *bmode = BSQ_B_ALL; *emode = BSQ_E_ALL; break;
+    case BSQ_START_ANCHORED: *bmode = BSQ_B_ORIGIN; *emode = BSQ_E_ALL; break;
+    case BSQ_END_ANCHORED: *bmode = BSQ_B_ALL; *emode = BSQ_E_CORNER; break;
+    case BSQ_OVERLAP: *bmode = BSQ_B_EDGE; *emode = BSQ_E_EDGE; break;
+    case BSQ_START_ANCHORED_OVERLAP: *bmode = BSQ_B_ORIGIN; *emode = BSQ_E_EDGE; break;
+    default: *bmode = BSQ_B_EDGE; *emode = BSQ_E_CORNER; break;  // END_ANCHORED_OVERLAP
+  }
+}
+
+int pick_k1_cfg(int n, int m) {
+  int best = 0;
+  double bestc = 1e300;
+  for (int c = 0; c < BSQ_K1_NCFG; c++) {
+    const int G = BSQ_K1_CFGS[c].G, K = BSQ_K1_CFGS[c].K, BW = G * K;
+    const double passes = (double)((m + BW) / BW);
+    const double cost = passes * ((double)n + G) * BW / (G == 32 ? 1.0 : 1.0);
+    if (cost < bestc) { bestc = cost; best = c; }
+  }
+  return best;
+}
+
+int pick_k2_cfg(int W) {
+  for (int c = 0; c < BSQ_K2_NCFG; c++)
+    if (BSQ_K2_CFGS[c].G * BSQ_K2_CFGS[c].C >= W) return c;
+  return -1;
+}
+
+int k1_op(int dtype, int cfg, int ball, int eall, int gos, int op, int grid, cudaStream_t st, const BsqFillArgs* A) {
+  return dtype == BSQ_DTYPE_I32 ? bsq_k1_i32_op(cfg, ball, eall, gos, op, grid, st, A)
+                                : bsq_k1_f64_op(cfg, ball, eall, gos, op, grid, st, A);
+}
+int k2_op(int dtype, int cfg, int blocal, int gos, int op, int grid, cudaStream_t st, const BsqFillArgs* A) {
+  return dtype == BSQ_DTYPE_I32 ? bsq_k2_i32_op(cfg, blocal, gos, op, grid, st, A)
+                                : bsq_k2_f64_op(cfg, blocal, gos, op, grid, st, A);
+}
+
+// ---- planning -------------------------------------------------------------
+
+int make_plan(bsq_ctx* ctx, Plan& P, const bsq_params* prm, int64_t N, int64_t ncodes,
+              const int64_t* o_off, const int32_t* o_len, const int64_t* m_off,
+              const int32_t* m_len, const int32_t* dmin, const int32_t* dmax,
+              int64_t arena_words, bool single_chunk) {
+  if (!prm || !prm->subst) return fail(ctx, BSQ_ERR_ARG, "params/subst is NULL");
+  const int L = prm->alphabet_len;
+  if (L < 1 || L > BSQ_MAX_L) return fail(ctx, BSQ_ERR_ARG, "alphabet_len must be in [1,32]");
+  if (prm->mode != BSQ_STD_MODE && prm->mode != BSQ_BANDED_MODE) return fail(ctx, BSQ_ERR_ARG, "bad alnmode");
+  if (prm->mode == BSQ_STD_MODE && (prm->type < 0 || prm->type > 6)) return fail(ctx, BSQ_ERR_ARG, "bad std_alntype");
+  if (prm->mode == BSQ_BANDED_MODE && (prm->type < 0 || prm->type > 2)) return fail(ctx, BSQ_ERR_ARG, "bad banded_alntype");
+  if (prm->mode == BSQ_BANDED_MODE && (!dmin || !dmax)) return fail(ctx, BSQ_ERR_ARG, "BANDED needs dmin/dmax");
+  if (prm->max_new_mins > 0)
+    return fail(ctx, BSQ_ERR_ARG, "max_new_mins > 0 is undefined behaviour in the reference (_pw_internals.c:236-243); not supported");
+  if (!std::isfinite(prm->go) || !std::isfinite(prm->ge)) return fail(ctx, BSQ_ERR_ARG, "go/ge must be finite");
+  P.prm = *prm;
+  P.subst.assign(prm->subst, prm->subst + L * L);
+  for (double& v : P.subst) {
+    if (!std::isfinite(v)) return fail(ctx, BSQ_ERR_ARG, "subst scores must be finite");
+    if (v == 0.0) v = 0.0;  // canonicalise -0.0
+  }
+  P.prm.subst = nullptr;
+  P.N = N;
+  P.gosign = prm->go < 0 ? -1 : (prm->go > 0 ? 1 : 0);
+  if (prm->mode == BSQ_STD_MODE) std_modes(prm->type, &P.bmode, &P.emode);
+
+  int64_t max_n = 0, max_m = 0;
+  for (int64_t i = 0; i < N; i++) {
+    const int n = o_len[i], m = m_len[i];
+    if (n < 0 || m < 0) return fail(ctx, BSQ_ERR_ARG, "negative sequence length");
+    if (o_off[i] < 0 || m_off[i] < 0 || o_off[i] + n > ncodes || m_off[i] + m > ncodes)
+      return fail(ctx, BSQ_ERR_ARG, "sequence range outside codes[]");
+    max_n = std::max<int64_t>(max_n, n);
+    max_m = std::max<int64_t>(max_m, m);
+  }
+  bsq_params tmp = *prm;
+  tmp.subst = P.subst.data();
+  const bool i32ok = scores_int32_exact(&tmp, max_n, max_m);
+  if (prm->dtype == BSQ_DTYPE_I32 && !i32ok)
+    return fail(ctx, BSQ_ERR_ARG, "dtype I32 forced but scores are not int32-exact for these lengths");
+  P.dtype = (prm->dtype == BSQ_DTYPE_F64) ? BSQ_DTYPE_F64 : (i32ok ? BSQ_DTYPE_I32 : BSQ_DTYPE_F64);
+  bool range_ok = true;
+  if (P.dtype == BSQ_DTYPE_F64) {
+    // pwlib clamps gap candidates at -INT_MAX (_pw_internals.c:267); the kernels
+    // do not, so refuse score ranges in which the clamp could ever bind.
+    double maxabs = std::fabs(prm->go) + std::fabs(prm->ge);
+    for (double v : P.subst) maxabs = std::max(maxabs, std::fabs(v));
+    range_ok = (double)(max_n + max_m + 4) * maxabs < 2147483647.0;
+  }
+
+  struct Item { int64_t idx; int64_t words; int cfg; int multipass_n; };
+  std::vector<Item> items;
+  items.reserve((size_t)N);
+  P.overrides.clear();
+  P.cells = 0;
+  const int family = prm->mode == BSQ_STD_MODE ? 1 : 2;
+  std::vector<int32_t> cdmin, cdmax;
+  if (family == 2) { cdmin.resize((size_t)N); cdmax.resize((size_t)N); }
+  bool uniform = true;
+  int64_t first_words = -1;
+  int first_cfg = -1;
+  for (int64_t i = 0; i < N; i++) {
+    const int n = o_len[i], m = m_len[i];
+    if (!range_ok) { P.overrides.push_back({i, BSQ_UNSUPPORTED}); continue; }
+    Item it;
+    it.idx = i;
+    it.multipass_n = 0;
+    if (family == 1) {
+      it.cfg = pick_k1_cfg(n, m);
+      const int G = BSQ_K1_CFGS[it.cfg].G, K = BSQ_K1_CFGS[it.cfg].K, BW = G * K, WPL = (K + 7) / 8;
+      const int64_t passes = (m + BW) / BW;
+      it.words = passes * (int64_t)(n + 1) * G * WPL;
+      if (passes > 1) it.multipass_n = n;
+      P.cells += (int64_t)(n + 1) * (m + 1);
+    } else {
+      int lo = dmin[i], hi = dmax[i];
+      if (hi > n) hi = n;   // _pw_internals.c:29-36
+      if (lo < -m) lo = -m;
+      const int dend = n - m;
+      if (prm->type == BSQ_B_GLOBAL && (dend > hi || dend < lo || (int64_t)hi * lo > 0)) {
+        P.overrides.push_back({i, BSQ_INIT_FAIL});
+        continue;
+      }
+      const int64_t W = (int64_t)hi - lo + 1;
+      if (W < 0) { P.overrides.push_back({i, BSQ_INIT_FAIL}); continue; }
+      if (W == 0) { P.overrides.push_back({i, BSQ_NO_ALIGNMENT}); continue; }
+      it.cfg = pick_k2_cfg((int)std::min<int64_t>(W, 1 << 30));
+      if (it.cfg < 0) { P.overrides.push_back({i, BSQ_UNSUPPORTED}); continue; }
+      cdmin[i] = lo; cdmax[i] = hi;
+      const int G = BSQ_K2_CFGS[it.cfg].G, C = BSQ_K2_CFGS[it.cfg].C, WPS = (C / 2 + 7) / 8;
+      const int smin = (lo <= 0 && hi >= 0) ? 0 : std::min(std::abs(lo), std::abs(hi));
+      const int sbase = smin - ((smin - lo) & 1);
+      int dstar = std::max(lo, std::min(hi, dend));
+      const int s_end = 2 * std::min(n, m + dstar) - dstar;
+      const int64_t steps = (int64_t)(s_end - sbase + 1 + 1) / 2 * 2 + 2;
+      it.words = steps * G * WPS;
+      it.multipass_n = sbase;  // reused: first step
+      P.cells += count_cells(BSQ_BANDED_MODE, n, m, lo, hi);
+    }
+    if (first_words < 0) { first_words = it.words; first_cfg = it.cfg; }
+    else if (it.words != first_words || it.cfg != first_cfg) uniform = false;
+    items.push_back(it);
+  }
+  // processing order: by kernel geometry, heaviest first inside a geometry
+  if (!uniform)
+    std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) {
+      if (a.cfg != b.cfg) return a.cfg < b.cfg;
+      return a.words > b.words;
+    });
+
+  P.pairs.resize(items.size());
+  P.chunks.clear();
+  P.slot_bytes = 0;
+  P.max_chunk_words = 0;
+  P.total_words = 0;
+  Chunk cur{0, 0, family, -1, 0, 0};
+  int64_t global_words = 0;
+  for (size_t e = 0; e < items.size(); e++) {
+    const Item& it = items[e];
+    const int64_t i = it.idx;
+    if (it.words > arena_words) {
+      return fail(ctx, BSQ_ERR_NOMEM, "a single pair's traceback table exceeds the device arena");
+    }
+    const bool new_chunk = cur.count > 0 && (it.cfg != cur.cfg || (!single_chunk && cur.ptr_words + it.words > arena_words));
+    if (single_chunk && global_words + it.words > arena_words)
+      return fail(ctx, BSQ_ERR_NOMEM, "batch does not fit the device arena in two-phase mode; use bsq_align_batch");
+    if (new_chunk) {
+      P.chunks.push_back(cur);
+      cur = Chunk{(int64_t)e, 0, family, -1, 0, 0};
+    }
+    if (cur.count == 0) cur.cfg = it.cfg;
+    BsqPair& bp = P.pairs[e];
+    bp.o_off = o_off[i];
+    bp.m_off = m_off[i];
+    bp.n = o_len[i];
+    bp.m = m_len[i];
+    bp.ptr_off = single_chunk ? global_words : cur.ptr_words;
+    bp.tx_slot = P.slot_bytes;
+    bp.pad = (int)i;  // original index (N < 2^31 enforced by caller)
+    if (family == 2) { bp.dmin = cdmin[i]; bp.dmax = cdmax[i]; bp.s0 = it.multipass_n; }
+    else { bp.dmin = 0; bp.dmax = 0; bp.s0 = 0; cur.max_n_multipass = std::max(cur.max_n_multipass, it.multipass_n); }
+    P.slot_bytes += (int64_t)bp.n + bp.m;
+    cur.ptr_words += it.words;
+    global_words += it.words;
+    cur.count++;
+    P.max_chunk_words = std::max(P.max_chunk_words, cur.ptr_words);
+  }
+  if (cur.count > 0) P.chunks.push_back(cur);
+  P.total_words = global_words;
+  return BSQ_SUCCESS;
+}
+
+cudaEvent_t get_event(bsq_ctx* ctx, size_t i) {
+  while (ctx->events.size() <= i) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    ctx->events.push_back(e);
+  }
+  return ctx->events[i];
+}
+
+int64_t arena_budget_words(bsq_ctx* ctx, int64_t other_bytes) {
+  size_t fr = 0, tot = 0;
+  if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { fr = (size_t)1 << 30; cudaGetLastError(); }
+  fr += ctx->bufs.ptr.cap;  // our own cached arena counts as available
+  double budget = (double)fr * 0.85 - (double)other_bytes;
+  if (ctx->arena_cap_bytes && budget > (double)ctx->arena_cap_bytes) budget = (double)ctx->arena_cap_bytes;
+  if (budget < (double)(1 << 20)) budget = (double)(1 << 20);
+  return (int64_t)(budget / 4.0);
+}
+
+// upload everything the kernels read; size the output arrays
+int stage_inputs(bsq_ctx* ctx, BufSet& B, Plan& P, const uint8_t* codes, int64_t ncodes, bool single_chunk) {
+  const int64_t N = P.N, E = (int64_t)P.pairs.size();
+  const int L = P.prm.alphabet_len;
+  bool ok = B.codes.ensure((size_t)ncodes + 16) && B.pairs.ensure(sizeof(BsqPair) * (size_t)std::max<int64_t>(E, 1)) &&
+            B.score.ensure(8 * (size_t)N) && B.ex.ensure(4 * (size_t)N) && B.ey.ensure(4 * (size_t)N) &&
+            B.sx.ensure(4 * (size_t)N) && B.sy.ensure(4 * (size_t)N) && B.status.ensure(4 * (size_t)N) &&
+            B.txlen.ensure(4 * (size_t)N) && B.subst.ensure(8 * (size_t)L * L) &&
+            B.counters.ensure(4 * (P.chunks.size() + 1)) && B.total.ensure(16) &&
+            B.ptr.ensure(4 * (size_t)(single_chunk ? P.total_words : P.max_chunk_words) + 64);
+  if (!ok) return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed");
+  cudaStream_t st = ctx->st;
+  if (ncodes > 0) BSQ_CK(ctx, cudaMemcpyAsync(B.codes.p, codes, (size_t)ncodes, cudaMemcpyHostToDevice, st));
+  ctx->tm.h2d_bytes += ncodes;
+  if (E > 0) {
+    BSQ_CK(ctx, cudaMemcpyAsync(B.pairs.p, P.pairs.data(), sizeof(BsqPair) * (size_t)E, cudaMemcpyHostToDevice, st));
+    ctx->tm.h2d_bytes += (int64_t)sizeof(BsqPair) * E;
+  }
+  if (P.dtype == BSQ_DTYPE_I32) {
+    std::vector<int> si((size_t)L * L);
+    for (int i = 0; i < L * L; i++) si[i] = (int)P.subst[i];
+    BSQ_CK(ctx, cudaMemcpyAsync(B.subst.p, si.data(), 4 * (size_t)L * L, cudaMemcpyHostToDevice, st));
+    BSQ_CK(ctx, cudaStreamSynchronize(st));  // si is a temporary
+  } else {
+    BSQ_CK(ctx, cudaMemcpyAsync(B.subst.p, P.subst.data(), 8 * (size_t)L * L, cudaMemcpyHostToDevice, st));
+  }
+  BSQ_CK(ctx, cudaMemsetAsync(B.counters.p, 0, 4 * (P.chunks.size() + 1), st));
+  BSQ_CK(ctx, cudaMemsetAsync(B.txlen.p, 0, 4 * (size_t)N, st));
+  return BSQ_SUCCESS;
+}
+
+int launch_fill(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, size_t* evi) {
+  const Chunk& ch = P.chunks[ci];
+  BsqFillArgs A;
+  memset(&A, 0, sizeof A);
+  A.codes = B.codes.as<uint8_t>();
+  A.pairs = B.pairs.as<BsqPair>() + ch.first;
+  A.npairs = (int)ch.count;
+  A.L = P.prm.alphabet_len;
+  A.subst = B.subst.p;
+  A.go_d = P.prm.go; A.ge_d = P.prm.ge;
+  A.go_i = (int)P.prm.go; A.ge_i = (int)P.prm.ge;
+  A.bmode = P.bmode; A.emode = P.emode; A.btype = P.prm.type;
+  A.ptr = B.ptr.as<uint32_t>();
+  A.out_score = B.score.as<double>();
+  A.out_ex = B.ex.as<int>();
+  A.out_ey = B.ey.as<int>();
+  A.out_status = B.status.as<int>();
+  A.counter = B.counters.as<int>() + ci;
+  const int G = ch.family == 1 ? BSQ_K1_CFGS[ch.cfg].G : BSQ_K2_CFGS[ch.cfg].G;
+  const int ball = P.bmode == BSQ_B_ALL, eall = P.emode == BSQ_E_ALL;
+  const int blocal = P.prm.type == BSQ_B_LOCAL;
+  int occ = ch.family == 1 ? k1_op(P.dtype, ch.cfg, ball, eall, P.gosign, BSQ_OP_OCCUPANCY, 0, 0, nullptr)
+                           : k2_op(P.dtype, ch.cfg, blocal, P.gosign, BSQ_OP_OCCUPANCY, 0, 0, nullptr);
+  if (occ < 0) return fail(ctx, BSQ_ERR_ARG, "no kernel variant for this configuration");
+  const int groups_per_block = BSQ_FILL_THREADS / G;
+  int64_t want_blocks = (ch.count + groups_per_block - 1) / groups_per_block;
+  int grid = (int)std::min<int64_t>(want_blocks, (int64_t)ctx->sms * occ);
+  if (grid < 1) grid = 1;
+  if (ch.family == 1 && ch.max_n_multipass > 0) {
+    const int64_t stride = (int64_t)ch.max_n_multipass + 2;
+    const int64_t groups = (int64_t)grid * groups_per_block;
+    if (!B.colh.ensure(8 * (size_t)(stride * groups)) || !B.colf.ensure((size_t)(stride * groups)))
+      return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (boundary columns)");
+    A.col_h = B.colh.as<double>();
+    A.col_f = B.colf.as<uint8_t>();
+    A.col_stride = stride;
+  }
+  cudaEvent_t e0 = get_event(ctx, (*evi)++), e1 = get_event(ctx, (*evi)++);
+  BSQ_CK(ctx, cudaEventRecord(e0, ctx->st));
+  int rc = ch.family == 1 ? k1_op(P.dtype, ch.cfg, ball, eall, P.gosign, BSQ_OP_LAUNCH, grid, ctx->st, &A)
+                          : k2_op(P.dtype, ch.cfg, blocal, P.gosign, BSQ_OP_LAUNCH, grid, ctx->st, &A);
+  if (rc < 0) return fail(ctx, BSQ_ERR_ARG, "no kernel variant for this configuration");
+  BSQ_CK(ctx, cudaGetLastError());
+  BSQ_CK(ctx, cudaEventRecord(e1, ctx->st));
+  ctx->tm.fill_launches++;
+  ctx->tm.ptr_bytes += 4 * ch.ptr_words;
+  return BSQ_SUCCESS;
+}
+
+int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci) {
+  const Chunk& ch = P.chunks[ci];
+  BsqTraceArgs T;
+  memset(&T, 0, sizeof T);
+  T.codes = B.codes.as<uint8_t>();
+  T.pairs = B.pairs.as<BsqPair>() + ch.first;
+  T.npairs = (int)ch.count;
+  T.mode = P.prm.mode;
+  T.G = ch.family == 1 ? BSQ_K1_CFGS[ch.cfg].G : BSQ_K2_CFGS[ch.cfg].G;
+  T.K = ch.family == 1 ? BSQ_K1_CFGS[ch.cfg].K : BSQ_K2_CFGS[ch.cfg].C;
+  T.gosign = P.gosign;
+  T.ptr = B.ptr.as<uint32_t>();
+  T.ex = B.ex.as<int>();
+  T.ey = B.ey.as<int>();
+  T.status = B.status.as<int>();
+  T.sx = B.sx.as<int>();
+  T.sy = B.sy.as<int>();
+  T.txlen = B.txlen.as<int>();
+  T.slots = B.slots.as<char>();
+  const int grid = (int)((ch.count + 127) / 128);
+  BSQ_LAUNCH(bsq_k4_traceback, grid, 128, 0, ctx->st, T);
+  BSQ_CK(ctx, cudaGetLastError());
+  ctx->tm.fill_launches++;
+  return BSQ_SUCCESS;
+}
+
+// scan txlen (original order) -> txoff, pack slots -> packed, D2H
+int pack_and_fetch_transcripts(bsq_ctx* ctx, BufSet& B, const Plan& P, int64_t* tx_off, char* tx_buf,
+                               int64_t tx_cap, int64_t* tx_total) {
+  const int64_t N = P.N, E = (int64_t)P.pairs.size();
+  const int ntiles = (int)((N + BSQ_SCAN_TILE - 1) / BSQ_SCAN_TILE);
+  if (!B.txoff.ensure(8 * (size_t)(N + 1)) || !B.tiles.ensure(8 * (size_t)std::max(ntiles, 1)) ||
+      !B.packed.ensure((size_t)std::max<int64_t>(P.slot_bytes, 1)))
+    return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (transcripts)");
+  cudaStream_t st = ctx->st;
+  BSQ_LAUNCH(bsq_scan_tile_sums, ntiles, 256, 0, st, (const int*)B.txlen.as<int>(), (int)N, B.tiles.as<long long>());
+  BSQ_LAUNCH(bsq_scan_tiles, 1, 256, 0, st, B.tiles.as<long long>(), ntiles, B.total.as<long long>());
+  BSQ_LAUNCH(bsq_scan_apply, ntiles, 256, 0, st, (const int*)B.txlen.as<int>(), (int)N,
+             (const long long*)B.tiles.as<long long>(), B.txoff.as<long long>());
+  ctx->tm.fill_launches += 3;
+  if (E > 0) {
+    const int grid = (int)((E * 32 + 255) / 256);
+    BSQ_LAUNCH(bsq_pack_transcripts, grid, 256, 0, st, (const BsqPair*)B.pairs.as<BsqPair>(), (int)E,
+               (const int*)B.txlen.as<int>(), (const long long*)B.txoff.as<long long>(),
+               (const char*)B.slots.as<char>(), B.packed.as<char>());
+    ctx->tm.fill_launches++;
+  }
+  BSQ_CK(ctx, cudaGetLastError());
+  long long total = 0;
+  BSQ_CK(ctx, cudaMemcpyAsync(&total, B.total.p, 8, cudaMemcpyDeviceToHost, st));
+  BSQ_CK(ctx, cudaMemcpyAsync(tx_off, B.txoff.p, 8 * (size_t)N, cudaMemcpyDeviceToHost, st));
+  BSQ_CK(ctx, cudaStreamSynchronize(st));
+  tx_off[N] = total;
+  if (tx_total) *tx_total = total;
+  ctx->tm.d2h_bytes += 8 * N + 8;
+  if (total > tx_cap) return fail(ctx, BSQ_ERR_CAPACITY, "tx_buf too small for the batch's transcripts");
+  if (total > 0) {
+    BSQ_CK(ctx, cudaMemcpyAsync(tx_buf, B.packed.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+    ctx->tm.d2h_bytes += total;
+  }
+  return BSQ_SUCCESS;
+}
+
+void apply_overrides(const Plan& P, double* score, int32_t* ex, int32_t* ey, int32_t* sx, int32_t* sy,
+                     int32_t* status) {
+  for (const Override& o : P.overrides) {
+    if (score) score[o.idx] = 0.0;
+    if (ex) ex[o.idx] = -1;
+    if (ey) ey[o.idx] = -1;
+    if (sx) sx[o.idx] = -1;
+    if (sy) sy[o.idx] = -1;
+    if (status) status[o.idx] = o.status;
+  }
+}
+
+int collect_timing(bsq_ctx* ctx, size_t nev, cudaEvent_t t0, cudaEvent_t t1) {
+  double fill = 0;
+  for (size_t i = 2; i + 1 < nev; i += 2) {  // events 0/1 bracket the whole call
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->events[i], ctx->events[i + 1]) == cudaSuccess) fill += ms;
+  }
+  float tot = 0;
+  cudaEventElapsedTime(&tot, t0, t1);
+  ctx->tm.fill_ms = fill;
+  ctx->tm.total_ms = tot;
+  ctx->tm.traceback_ms = 0;
+  return 0;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+const char* bsq_version(void) {
+#ifdef BSQ_SIMT_EMU
+  return "bsqgpu 0.1 (simt-emu test build)";
+#else
+  return "bsqgpu 0.1 (sm_100a)";
+#endif
+}
+
+int bsq_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* bsq_last_error(const bsq_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+bsq_ctx* bsq_create(int device) {
+  int n = bsq_device_count();
+  if (n <= 0) { g_err = "no CUDA device available (libbsqgpu has no CPU fallback)"; return nullptr; }
+  if (device < 0 || device >= n) { g_err = "device ordinal out of range"; return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { g_err = "cudaSetDevice failed"; return nullptr; }
+  bsq_ctx* ctx = new bsq_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { g_err = "cudaGetDeviceProperties failed"; delete ctx; return nullptr; }
+  ctx->sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) { g_err = "cudaStreamCreate failed"; delete ctx; return nullptr; }
+  memset(&ctx->tm, 0, sizeof ctx->tm);
+  const char* cap = getenv("BSQ_ARENA_CAP_BYTES");
+  if (cap) ctx->arena_cap_bytes = (size_t)atoll(cap);
+  return ctx;
+}
+
+void bsq_destroy(bsq_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->st);
+  ctx->bufs.release();
+  for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+  cudaStreamDestroy(ctx->st);
+  delete ctx;
+}
+
+void* bsq_host_alloc(int64_t bytes) {
+  void* p = nullptr;
+  if (bytes < 0) return nullptr;
+  if (cudaHostAlloc(&p, (size_t)(bytes ? bytes : 1), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void bsq_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int bsq_get_timing(const bsq_ctx* ctx, bsq_timing* out) {
+  if (!ctx || !out) return BSQ_ERR_ARG;
+  *out = ctx->tm;
+  return BSQ_SUCCESS;
+}
+
+int64_t bsq_count_cells(int32_t mode, int32_t n, int32_t m, int32_t dmin, int32_t dmax) {
+  return count_cells(mode, n, m, dmin, dmax);
+}
+
+int bsq_scores_are_int32_exact(const bsq_params* params, int32_t max_n, int32_t max_m) {
+  if (!params || !params->subst) return 0;
+  return scores_int32_exact(params, max_n, max_m) ? 1 : 0;
+}
+
+int bsq_partition_pairs(int32_t mode, int64_t npairs, const int32_t* o_len, const int32_t* m_len,
+                        const int32_t* dmin, const int32_t* dmax, int32_t nshards, int32_t* shard_of,
+                        int64_t* load) {
+  if (npairs < 0 || nshards < 1 || !o_len || !m_len || !shard_of) return BSQ_ERR_ARG;
+  if (mode == BSQ_BANDED_MODE && (!dmin || !dmax)) return BSQ_ERR_ARG;
+  std::vector<int64_t> w((size_t)npairs), order((size_t)npairs);
+  for (int64_t i = 0; i < npairs; i++) {
+    w[i] = count_cells(mode, o_len[i], m_len[i], dmin ? dmin[i] : 0, dmax ? dmax[i] : 0);
+    order[i] = i;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return w[a] > w[b]; });
+  std::vector<int64_t> ld((size_t)nshards, 0);
+  for (int64_t r = 0; r < npairs; r++) {
+    const int64_t i = order[r];
+    int bestk = 0;
+    for (int k = 1; k < nshards; k++) if (ld[k] < ld[bestk]) bestk = k;
+    shard_of[i] = bestk;
+    ld[bestk] += w[i];
+  }
+  if (load) for (int k = 0; k < nshards; k++) load[k] = ld[k];
+  return BSQ_SUCCESS;
+}
+
+static int run_one_shot(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, const uint8_t* codes,
+                        int64_t ncodes, const int64_t* o_off, const int32_t* o_len, const int64_t* m_off,
+                        const int32_t* m_len, const int32_t* dmin, const int32_t* dmax, double* score,
+                        int32_t* end_x, int32_t* end_y, int32_t* start_x, int32_t* start_y,
+                        int32_t* status, int64_t* tx_off, char* tx_buf, int64_t tx_cap, int64_t* tx_total) {
+  if (!ctx) return BSQ_ERR_ARG;
+  ctx->err.clear();
+  if (npairs < 0 || npairs >= ((int64_t)1 << 31)) return fail(ctx, BSQ_ERR_ARG, "npairs out of range");
+  if (npairs > 0 && (!codes || !o_off || !o_len || !m_off || !m_len)) return fail(ctx, BSQ_ERR_ARG, "NULL input array");
+  if (!score || !status) return fail(ctx, BSQ_ERR_ARG, "score/status must not be NULL");
+  const bool want_tx = (tx_off != nullptr && tx_buf != nullptr);
+  const bool want_trace = want_tx || start_x || start_y;
+  BSQ_CK(ctx, cudaSetDevice(ctx->device));
+  memset(&ctx->tm, 0, sizeof ctx->tm);
+  if (tx_total) *tx_total = 0;
+  if (npairs == 0) { if (tx_off) tx_off[0] = 0; return BSQ_SUCCESS; }
+
+  Plan P;
+  int64_t slot_guess = 0;
+  for (int64_t i = 0; i < npairs; i++) slot_guess += (int64_t)o_len[i] + m_len[i];
+  const int64_t other = ncodes + 2 * slot_guess + npairs * (int64_t)(sizeof(BsqPair) + 48) + (64 << 20);
+  const int64_t arena_words = arena_budget_words(ctx, other);
+  int rc = make_plan(ctx, P, params, npairs, ncodes, o_off, o_len, m_off, m_len, dmin, dmax, arena_words, false);
+  if (rc != BSQ_SUCCESS) return rc;
+  BufSet& B = ctx->bufs;
+  cudaEvent_t t0 = get_event(ctx, 0), t1 = get_event(ctx, 1);
+  size_t evi = 2;
+  BSQ_CK(ctx, cudaEventRecord(t0, ctx->st));
+  rc = stage_inputs(ctx, B, P, codes, ncodes, false);
+  if (rc != BSQ_SUCCESS) return rc;
+  if (want_trace && !B.slots.ensure((size_t)std::max<int64_t>(P.slot_bytes, 1)))
+    return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (transcript slots)");
+  for (size_t ci = 0; ci < P.chunks.size(); ci++) {
+    rc = launch_fill(ctx, B, P, ci, &evi);
+    if (rc != BSQ_SUCCESS) return rc;
+    if (want_trace) {
+      rc = launch_trace(ctx, B, P, ci);
+      if (rc != BSQ_SUCCESS) return rc;
+    }
+  }
+  cudaStream_t st = ctx->st;
+  const size_t N = (size_t)npairs;
+  BSQ_CK(ctx, cudaMemcpyAsync(score, B.score.p, 8 * N, cudaMemcpyDeviceToHost, st));
+  if (end_x) BSQ_CK(ctx, cudaMemcpyAsync(end_x, B.ex.p, 4 * N, cudaMemcpyDeviceToHost, st));
+  if (end_y) BSQ_CK(ctx, cudaMemcpyAsync(end_y, B.ey.p, 4 * N, cudaMemcpyDeviceToHost, st));
+  if (want_trace && start_x) BSQ_CK(ctx, cudaMemcpyAsync(start_x, B.sx.p, 4 * N, cudaMemcpyDeviceToHost, st));
+  if (want_trace && start_y) BSQ_CK(ctx, cudaMemcpyAsync(start_y, B.sy.p, 4 * N, cudaMemcpyDeviceToHost, st));
+  BSQ_CK(ctx, cudaMemcpyAsync(status, B.status.p, 4 * N, cudaMemcpyDeviceToHost, st));
+  ctx->tm.d2h_bytes += (int64_t)N * (8 + 4 * (1 + (end_x != 0) + (end_y != 0) + (start_x != 0) + (start_y != 0)));
+  if (want_tx) {
+    rc = pack_and_fetch_transcripts(ctx, B, P, tx_off, tx_buf, tx_cap, tx_total);
+    if (rc != BSQ_SUCCESS && rc != BSQ_ERR_CAPACITY) return rc;
+  }
+  BSQ_CK(ctx, cudaEventRecord(t1, st));
+  BSQ_CK(ctx, cudaStreamSynchronize(st));
+  collect_timing(ctx, evi, t0, t1);
+  ctx->tm.cells = P.cells;
+  ctx->tm.dtype = P.dtype;
+  ctx->tm.chunks = (int32_t)P.chunks.size();
+  apply_overrides(P, score, end_x, end_y, start_x, start_y, status);
+  return rc;
+}
+
+int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, const uint8_t* codes,
+                    int64_t ncodes, const int64_t* o_off, const int32_t* o_len, const int64_t* m_off,
+                    const int32_t* m_len, const int32_t* dmin, const int32_t* dmax, double* score,
+                    int32_t* end_x, int32_t* end_y, int32_t* start_x, int32_t* start_y, int32_t* status,
+                    int64_t* tx_off, char* tx_buf, int64_t tx_cap, int64_t* tx_total) {
+  return run_one_shot(ctx, params, npairs, codes, ncodes, o_off, o_len, m_off, m_len, dmin, dmax, score,
+                      end_x, end_y, start_x, start_y, status, tx_off, tx_buf, tx_cap, tx_total);
+}
+
+int bsq_solve_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, const uint8_t* codes,
+                    int64_t ncodes, const int64_t* o_off, const int32_t* o_len, const int64_t* m_off,
+                    const int32_t* m_len, const int32_t* dmin, const int32_t* dmax, double* score,
+                    int32_t* end_x, int32_t* end_y, int32_t* status, bsq_batch** batch) {
+  if (!ctx) return BSQ_ERR_ARG;
+  ctx->err.clear();
+  if (!batch) return fail(ctx, BSQ_ERR_ARG, "batch out-pointer is NULL");
+  *batch = nullptr;
+  if (npairs < 0 || npairs >= ((int64_t)1 << 31)) return fail(ctx, BSQ_ERR_ARG, "npairs out of range");
+  if (npairs > 0 && (!codes || !o_off || !o_len || !m_off || !m_len)) return fail(ctx, BSQ_ERR_ARG, "NULL input array");
+  if (!score || !status) return fail(ctx, BSQ_ERR_ARG, "score/status must not be NULL");
+  BSQ_CK(ctx, cudaSetDevice(ctx->device));
+  memset(&ctx->tm, 0, sizeof ctx->tm);
+  bsq_batch* b = new bsq_batch();
+  b->ctx = ctx;
+  if (npairs == 0) { *batch = b; return BSQ_SUCCESS; }
+  int64_t slot_guess = 0;
+  for (int64_t i = 0; i < npairs; i++) slot_guess += (int64_t)o_len[i] + m_len[i];
+  const int64_t other = ncodes + 2 * slot_guess + npairs * (int64_t)(sizeof(BsqPair) + 48) + (64 << 20);
+  const int64_t arena_words = arena_budget_words(ctx, other);
+  int rc = make_plan(ctx, b->plan, params, npairs, ncodes, o_off, o_len, m_off, m_len, dmin, dmax, arena_words, true);
+  if (rc != BSQ_SUCCESS) { delete b; return rc; }
+  cudaEvent_t t0 = get_event(ctx, 0), t1 = get_event(ctx, 1);
+  size_t evi = 2;
+  cudaEventRecord(t0, ctx->st);
+  rc = stage_inputs(ctx, b->bufs, b->plan, codes, ncodes, true);
+  for (size_t ci = 0; rc == BSQ_SUCCESS && ci < b->plan.chunks.size(); ci++) rc = launch_fill(ctx, b->bufs, b->plan, ci, &evi);
+  if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(ctx->st); b->bufs.release(); delete b; return rc; }
+  cudaStream_t st = ctx->st;
+  const size_t N = (size_t)npairs;
+  cudaMemcpyAsync(score, b->bufs.score.p, 8 * N, cudaMemcpyDeviceToHost, st);
+  if (end_x) cudaMemcpyAsync(end_x, b->bufs.ex.p, 4 * N, cudaMemcpyDeviceToHost, st);
+  if (end_y) cudaMemcpyAsync(end_y, b->bufs.ey.p, 4 * N, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(status, b->bufs.status.p, 4 * N, cudaMemcpyDeviceToHost, st);
+  cudaEventRecord(t1, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    ctx->err = std::string("solve: ") + cudaGetErrorString(e);
+    b->bufs.release(); delete b; return BSQ_ERR_CUDA;
+  }
+  collect_timing(ctx, evi, t0, t1);
+  ctx->tm.cells = b->plan.cells;
+  ctx->tm.dtype = b->plan.dtype;
+  ctx->tm.chunks = (int32_t)b->plan.chunks.size();
+  apply_overrides(b->plan, score, end_x, end_y, nullptr, nullptr, status);
+  *batch = b;
+  return BSQ_SUCCESS;
+}
+
+int bsq_traceback_batch(bsq_batch* b, int32_t* start_x, int32_t* start_y, int32_t* status, int64_t* tx_off,
+                        char* tx_buf, int64_t tx_cap, int64_t* tx_total) {
+  if (!b || !b->ctx) return BSQ_ERR_ARG;
+  bsq_ctx* ctx = b->ctx;
+  ctx->err.clear();
+  if (tx_total) *tx_total = 0;
+  const int64_t N = b->plan.N;
+  if (N == 0) { if (tx_off) tx_off[0] = 0; return BSQ_SUCCESS; }
+  if (!tx_off || !tx_buf) return fail(ctx, BSQ_ERR_ARG, "tx_off/tx_buf must not be NULL");
+  BSQ_CK(ctx, cudaSetDevice(ctx->device));
+  if (!b->bufs.slots.ensure((size_t)std::max<int64_t>(b->plan.slot_bytes, 1)))
+    return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (transcript slots)");
+  int rc = BSQ_SUCCESS;
+  for (size_t ci = 0; rc == BSQ_SUCCESS && ci < b->plan.chunks.size(); ci++) rc = launch_trace(ctx, b->bufs, b->plan, ci);
+  if (rc != BSQ_SUCCESS) return rc;
+  cudaStream_t st = ctx->st;
+  if (start_x) BSQ_CK(ctx, cudaMemcpyAsync(start_x, b->bufs.sx.p, 4 * (size_t)N, cudaMemcpyDeviceToHost, st));
+  if (start_y) BSQ_CK(ctx, cudaMemcpyAsync(start_y, b->bufs.sy.p, 4 * (size_t)N, cudaMemcpyDeviceToHost, st));
+  if (status) BSQ_CK(ctx, cudaMemcpyAsync(status, b->bufs.status.p, 4 * (size_t)N, cudaMemcpyDeviceToHost, st));
+  rc = pack_and_fetch_transcripts(ctx, b->bufs, b->plan, tx_off, tx_buf, tx_cap, tx_total);
+  BSQ_CK(ctx, cudaStreamSynchronize(st));
+  apply_overrides(b->plan, nullptr, nullptr, nullptr, start_x, start_y, status);
+  return rc;
+}
+
+void bsq_release(bsq_batch* b) {
+  if (!b) return;
+  if (b->ctx) { cudaSetDevice(b->ctx->device); cudaStreamSynchronize(b->ctx->st); }
+  b->bufs.release();
+  delete b;
+}
+
+int bsq_table_scores(bsq_ctx* ctx, const bsq_params* params, const uint8_t* origin, int32_t n,
+                     const uint8_t* mutant, int32_t m, double* out) {
+  if (!ctx) return BSQ_ERR_ARG;
+  ctx->err.clear();
+  if (!params || !params->subst || !out || n < 0 || m < 0) return fail(ctx, BSQ_ERR_ARG, "bad argument");
+  if (params->mode != BSQ_STD_MODE) return fail(ctx, BSQ_ERR_ARG, "table_scores is STD mode only (pw.py:280-281)");
+  const int L = params->alphabet_len;
+  if (L < 1 || L > BSQ_MAX_L) return fail(ctx, BSQ_ERR_ARG, "alphabet_len must be in [1,32]");
+  BSQ_CK(ctx, cudaSetDevice(ctx->device));
+  int bmode, emode;
+  std_modes(params->type, &bmode, &emode);
+  const size_t cells = (size_t)(n + 1) * (size_t)(m + 1);
+  DevBuf dH, dM, dO, dT, dS;
+  if (!dH.ensure(8 * cells) || !dM.ensure(cells) || !dO.ensure((size_t)n + 1) || !dT.ensure((size_t)m + 1) ||
+      !dS.ensure(8 * (size_t)L * L)) {
+    dH.release(); dM.release(); dO.release(); dT.release(); dS.release();
+    return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (table_scores)");
+  }
+  cudaStream_t st = ctx->st;
+  if (n) cudaMemcpyAsync(dO.p, origin, (size_t)n, cudaMemcpyHostToDevice, st);
+  if (m) cudaMemcpyAsync(dT.p, mutant, (size_t)m, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dS.p, params->subst, 8 * (size_t)L * L, cudaMemcpyHostToDevice, st);
+  const int gos = params->go < 0 ? -1 : (params->go > 0 ? 1 : 0);
+  if (gos < 0)
+    BSQ_LAUNCH(bsq_table_scores_kernel<-1>, 1, 256, 0, st, (const uint8_t*)dO.as<uint8_t>(), (int)n,
+               (const uint8_t*)dT.as<uint8_t>(), (int)m, (const double*)dS.as<double>(), L, params->go,
+               params->ge, bmode, dH.as<double>(), dM.as<uint8_t>());
+  else if (gos == 0)
+    BSQ_LAUNCH(bsq_table_scores_kernel<0>, 1, 256, 0, st, (const uint8_t*)dO.as<uint8_t>(), (int)n,
+               (const uint8_t*)dT.as<uint8_t>(), (int)m, (const double*)dS.as<double>(), L, params->go,
+               params->ge, bmode, dH.as<double>(), dM.as<uint8_t>());
+  else
+    BSQ_LAUNCH(bsq_table_scores_kernel<1>, 1, 256, 0, st, (const uint8_t*)dO.as<uint8_t>(), (int)n,
+               (const uint8_t*)dT.as<uint8_t>(), (int)m, (const double*)dS.as<double>(), L, params->go,
+               params->ge, bmode, dH.as<double>(), dM.as<uint8_t>());
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dH.p, 8 * cells, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  dH.release(); dM.release(); dO.release(); dT.release(); dS.release();
+  if (e != cudaSuccess) { ctx->err = std::string("table_scores: ") + cudaGetErrorString(e); return BSQ_ERR_CUDA; }
+  return BSQ_SUCCESS;
+}
+
+}  // extern "C"

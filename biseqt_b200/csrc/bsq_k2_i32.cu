@@ -1,0 +1,5 @@
+// k2 fill kernels, i32 arithmetic (see bsq_kernels.cuh)
+#include "bsq_dispatch.cuh"
+int bsq_k2_i32_op(int cfg, int blocal, int gos, int op, int grid, cudaStream_t st, const BsqFillArgs* A) {
+  return bsq_k2_op_t<ScI32>(cfg, blocal, gos, op, grid, st, A);
+}

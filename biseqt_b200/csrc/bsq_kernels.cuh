@@ -1,0 +1,471 @@
+// bsq_kernels.cuh -- sm_100a DP fill + traceback kernels of libbsqgpu.
+//
+// What is computed is pwlib's recurrence, not textbook Gotoh: per cell the
+// candidates B, D, I, M are formed in that order (pw.c:77-80), EVERY candidate
+// tying for the maximum is kept (pw.c:89-108) and a gap candidate extends for
+// free only out of a source cell whose tied-max set already contains the same
+// gap op (_pw_internals.c:266-278).  All choices of a cell carry the same
+// score, so a cell is (H, 4-bit mask); the kernels keep H in registers and
+// write only the masks (4 bit/cell) to HBM for the traceback kernel.
+//
+// Arithmetic (template parameter S):
+//   ScF64  IEEE double, the reference's own type.  Adds are issued in the
+//          reference's association -- (H + ge) then (+ go) as in
+//          _pw_internals.c:269-273, H + subst as in :234 -- with __dadd_rn so
+//          that nothing is contracted or re-associated; ties are detected with
+//          == on doubles exactly like pw.c:94.
+//   ScI32  exact integer path, selected by the host only when every score is an
+//          integer and no partial sum can leave 30 bits; then double arithmetic
+//          in the reference is exact too and the results are identical.
+//
+// "Does not exist" (outside the table / band) is encoded as -inf (F64) or
+// -2^30 (I32): such a neighbour yields a candidate that can never tie with a
+// real one, which removes every boundary branch from the inner loops.
+#pragma once
+#include "bsq_common.h"
+#include "../../include/bsqgpu.h"
+
+#define BSQ_INT_MAX 0x7fffffff
+
+struct ScF64 {
+  typedef double T;
+  static __device__ __forceinline__ T ninf() {
+    return __longlong_as_double((long long)0xFFF0000000000000ULL);
+  }
+  static __device__ __forceinline__ T add(T a, T b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double to_f64(T v) { return v; }
+  static __device__ __forceinline__ T go(const BsqFillArgs& A) { return A.go_d; }
+  static __device__ __forceinline__ T ge(const BsqFillArgs& A) { return A.ge_d; }
+};
+
+struct ScI32 {
+  typedef int T;
+  static __device__ __forceinline__ T ninf() { return -(1 << 30); }
+  static __device__ __forceinline__ T add(T a, T b) { return a + b; }
+  static __device__ __forceinline__ double to_f64(T v) { return (double)v; }
+  static __device__ __forceinline__ T go(const BsqFillArgs& A) { return A.go_i; }
+  static __device__ __forceinline__ T ge(const BsqFillArgs& A) { return A.ge_i; }
+};
+
+// Decides whether a gap candidate out of a source cell with tied-max set `nib`
+// extends (score H+ge) or opens (score (H+ge)+go); `own` is the gap's own bit.
+//   go < 0 : extends iff own is in the set           (max over k picks k==own)
+//   go > 0 : extends iff nothing but own is in the set
+//   go = 0 : both give H+ge; the second add is skipped altogether
+template <int GOS>
+__device__ __forceinline__ bool bsq_extends(uint32_t nib, uint32_t own) {
+  if (GOS < 0) return (nib & own) != 0u;
+  if (GOS > 0) return (nib & (0xFu ^ own)) == 0u;
+  return true;
+}
+
+// One DP cell.  up/left/diag are H of (x-1,y), (x,y-1), (x-1,y-1); fD / fI say
+// whether the D / I candidate extends; bval is 0 where B is allowed, else -inf.
+template <class S, int GOS, bool HASB>
+__device__ __forceinline__ void bsq_cell(typename S::T up, bool fD, typename S::T left,
+                                         bool fI, typename S::T diag, typename S::T sig,
+                                         typename S::T bval, typename S::T go,
+                                         typename S::T ge, typename S::T& H,
+                                         uint32_t& mask) {
+  typedef typename S::T T;
+  T D = S::add(up, ge);      // _pw_internals.c:269-270
+  T I = S::add(left, ge);
+  if (GOS != 0) {            // :271-273
+    if (!fD) D = S::add(D, go);
+    if (!fI) I = S::add(I, go);
+  }
+  const T M = S::add(diag, sig);  // :234
+  T h = D > I ? D : I;
+  h = M > h ? M : h;
+  if (HASB) h = bval > h ? bval : h;
+  uint32_t mk = (D == h ? BSQ_MD : 0u) | (I == h ? BSQ_MI : 0u) | (M == h ? BSQ_MM : 0u);
+  if (HASB) mk |= (bval == h ? BSQ_MB : 0u);
+  H = h;
+  mask = mk;
+}
+
+// lexicographic "better end cell": higher score, then earlier scan position
+template <class T>
+__device__ __forceinline__ bool bsq_better(T s, int k1, int k2, T bs, int b1, int b2) {
+  return s > bs || (s == bs && (k1 < b1 || (k1 == b1 && k2 < b2)));
+}
+
+// group-wide argmax with the reference's scan-order tie-break
+template <class T, int G>
+__device__ __forceinline__ void bsq_group_best(unsigned gmask, T& s, int& k1, int& k2) {
+#pragma unroll
+  for (int off = 1; off < G; off <<= 1) {
+    T os = __shfl_xor_sync(gmask, s, off, G);
+    int o1 = __shfl_xor_sync(gmask, k1, off, G);
+    int o2 = __shfl_xor_sync(gmask, k2, off, G);
+    if (bsq_better<T>(os, o1, o2, s, k1, k2)) { s = os; k1 = o1; k2 = o2; }
+  }
+}
+
+// ===========================================================================
+// K1: STD frame.  A group of G lanes owns one pair; lane l owns K consecutive
+// columns (y), walks the rows (x) and lags its left neighbour by one row, so
+// the (x, y-1) dependency arrives by one shuffle per row.  Tables wider than
+// G*K columns are swept in passes, the boundary column going through a small
+// per-group scratch slab.  Pointer layout: [pass][x][lane][word], 8 cells/word.
+//   replaces: dptable_solve's fill loop pw.c:59-110 + _std_find_optimal
+// ===========================================================================
+template <class S, int K, int GOS, bool ALLB, bool EALL>
+__device__ __forceinline__ void bsq_k1_row(
+    typename S::T (&Hup)[K], uint32_t (&pw)[(K + 7) / 8], const int (&mlet)[K],
+    const typename S::T* srow, typename S::T inH, uint32_t inNib, typename S::T diag_in,
+    typename S::T bfirst, typename S::T brest, typename S::T go, typename S::T ge, int x,
+    int y0, int kv, typename S::T& best, int& bx, int& by, typename S::T& outH,
+    uint32_t& outNib) {
+  typedef typename S::T T;
+  constexpr int WPL = (K + 7) / 8;
+  T left = inH;
+  bool fI = bsq_extends<GOS>(inNib, BSQ_MI);
+  T diag = diag_in;
+  uint32_t cw[WPL];
+#pragma unroll
+  for (int w = 0; w < WPL; w++) cw[w] = 0u;
+  uint32_t mk = 0u;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const T up = Hup[k];
+    const uint32_t upnib = (pw[k >> 3] >> (4 * (k & 7))) & 0xFu;
+    const bool fD = bsq_extends<GOS>(upnib, BSQ_MD);
+    const T sig = srow[mlet[k]];
+    T H;
+    if (ALLB || k == 0)
+      bsq_cell<S, GOS, true>(up, fD, left, fI, diag, sig, k == 0 ? bfirst : brest, go, ge, H, mk);
+    else
+      bsq_cell<S, GOS, false>(up, fD, left, fI, diag, sig, bfirst, go, ge, H, mk);
+    cw[k >> 3] |= mk << (4 * (k & 7));
+    diag = up;
+    left = H;
+    fI = bsq_extends<GOS>(mk, BSQ_MI);
+    Hup[k] = H;
+    if (EALL) {  // _std_find_optimal :343-353, row-major first strict max
+      if (H > best && k < kv) { best = H; bx = x; by = y0 + k; }
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < WPL; w++) pw[w] = cw[w];
+  outH = left;
+  outNib = mk;
+}
+
+template <class S, int G, int K, bool BALL, bool EALL, int GOS>
+__global__ void __launch_bounds__(128) bsq_k1_fill(const BsqFillArgs A) {
+  typedef typename S::T T;
+  constexpr int WPL = (K + 7) / 8;
+  constexpr int BW = G * K;
+  __shared__ T s_sub[BSQ_MAX_L * BSQ_MAX_L];
+  const int L = A.L;
+  for (int i = threadIdx.x; i < L * L; i += blockDim.x) s_sub[i] = ((const T*)A.subst)[i];
+  __syncthreads();
+
+  const int tid = threadIdx.x;
+  const int l = tid % G;
+  const unsigned lane = (unsigned)tid & 31u;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(unsigned)(G - 1)));
+  const long long group = ((long long)blockIdx.x * blockDim.x + tid) / G;
+  const T NINF = S::ninf();
+  const T ZERO = (T)0;
+  const T go = S::go(A), ge = S::ge(A);
+  const int bmode = A.bmode, emode = A.emode;  // EDGE/ORIGIN and EDGE/CORNER are runtime
+  T* colh = (T*)(A.col_h + group * A.col_stride);
+  uint8_t* colf = A.col_f + group * A.col_stride;
+
+  for (;;) {
+    int p = 0;
+    if (l == 0) p = atomicAdd(A.counter, 1);
+    p = __shfl_sync(gmask, p, 0, G);
+    if (p >= A.npairs) break;
+    const BsqPair P = A.pairs[p];
+    const int n = P.n, m = P.m;
+    const int npass = (m + BW) / BW;  // ceil((m+1)/BW)
+
+    // running end-cell record: E_ALL -> (x, y); E_EDGE -> (scan key, 0); E_CORNER -> none
+    T best = EALL ? ZERO : NINF;
+    int bk1 = BSQ_INT_MAX, bk2 = BSQ_INT_MAX;
+
+    for (int pass = 0; pass < npass; pass++) {
+      const int y0 = pass * BW + l * K;
+      int mlet[K];
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const int y = y0 + k;
+        mlet[k] = (y >= 1 && y <= m) ? (int)A.codes[P.m_off + y - 1] : 0;
+      }
+      int kv = m - y0 + 1;
+      kv = kv < 0 ? 0 : (kv > K ? K : kv);
+      const int km = m - y0;  // which of my columns is column m (if in [0,K))
+      T Hup[K];
+      uint32_t pw[WPL];
+#pragma unroll
+      for (int k = 0; k < K; k++) Hup[k] = NINF;
+#pragma unroll
+      for (int w = 0; w < WPL; w++) pw[w] = 0u;
+      T lastH = NINF;
+      uint32_t lastNib = 0u;
+      T prev_in = NINF;
+      T pbest = ZERO;  // per-pass record for E_ALL (merged lexicographically below)
+      int pbx = BSQ_INT_MAX, pby = BSQ_INT_MAX;
+      uint32_t* prow = A.ptr + P.ptr_off + ((long long)pass * (n + 1) * G + l) * WPL;
+      const bool more = (pass + 1 < npass);
+
+      for (int t = 0; t <= n + G - 1; t++) {
+        const int x = t - l;
+        T inH = __shfl_up_sync(gmask, lastH, 1, G);
+        uint32_t inNib = __shfl_up_sync(gmask, lastNib, 1, G);
+        const bool active = (x >= 0 && x <= n);
+        if (l == 0) {
+          inH = NINF;
+          inNib = 0u;
+          if (pass > 0 && active) { inH = colh[x]; inNib = colf[x]; }
+        }
+        if (active) {
+          const int o = (x >= 1) ? (int)A.codes[P.o_off + x - 1] : 0;
+          const T* srow = s_sub + o * L;
+          T outH;
+          uint32_t outNib;
+          if (BALL || x == 0) {
+            T bfirst, brest;
+            if (BALL) { bfirst = ZERO; brest = ZERO; }
+            else {
+              brest = (bmode >= BSQ_B_EDGE) ? ZERO : NINF;
+              bfirst = (bmode >= BSQ_B_EDGE || y0 == 0) ? ZERO : NINF;
+            }
+            bsq_k1_row<S, K, GOS, true, EALL>(Hup, pw, mlet, srow, inH, inNib, prev_in,
+                                                          bfirst, brest, go, ge, x, y0, kv, pbest,
+                                                          pbx, pby, outH, outNib);
+          } else {
+            const T bfirst = (bmode == BSQ_B_EDGE && y0 == 0) ? ZERO : NINF;
+            bsq_k1_row<S, K, GOS, false, EALL>(Hup, pw, mlet, srow, inH, inNib, prev_in,
+                                                           bfirst, NINF, go, ge, x, y0, kv, pbest,
+                                                           pbx, pby, outH, outNib);
+          }
+          lastH = outH;
+          lastNib = outNib;
+          uint32_t* pr = prow + (long long)x * (G * WPL);
+#pragma unroll
+          for (int w = 0; w < WPL; w++) pr[w] = pw[w];
+          if (more && l == G - 1) { colh[x] = outH; colf[x] = (uint8_t)outNib; }
+          if (!EALL) {
+            if (km >= 0 && km < K) {  // I own column m
+              T Hm = NINF;
+#pragma unroll
+              for (int k = 0; k < K; k++) if (k == km) Hm = Hup[k];
+              if (emode == BSQ_E_CORNER) {
+                if (x == n) { best = Hm; bk1 = 0; bk2 = 0; }
+              } else if (x < n) {  // right column, rows above the last: key = x (:321-326)
+                if (bsq_better<T>(Hm, x, 0, best, bk1, bk2)) { best = Hm; bk1 = x; bk2 = 0; }
+              }
+            }
+            if (emode == BSQ_E_EDGE && x == n) {  // bottom row, left to right: key = n + y
+#pragma unroll
+              for (int k = 0; k < K; k++) {
+                if (k < kv && bsq_better<T>(Hup[k], n + y0 + k, 0, best, bk1, bk2)) {
+                  best = Hup[k]; bk1 = n + y0 + k; bk2 = 0;
+                }
+              }
+            }
+          }
+        }
+        prev_in = (x >= 0) ? inH : NINF;
+      }
+      if (EALL) {
+        if (bsq_better<T>(pbest, pbx, pby, best, bk1, bk2)) { best = pbest; bk1 = pbx; bk2 = pby; }
+      }
+      if (more) __syncwarp(gmask);  // boundary column visible to lane 0 of the next pass
+    }
+
+    bsq_group_best<T, G>(gmask, best, bk1, bk2);
+    if (l == 0) {
+      int ex, ey, st = BSQ_OK;
+      if (EALL) {
+        ex = bk1; ey = bk2;
+        if (bk1 == BSQ_INT_MAX) { st = BSQ_NO_ALIGNMENT; ex = -1; ey = -1; }
+      } else if (emode == BSQ_E_EDGE) {
+        if (bk1 < n) { ex = bk1; ey = m; } else { ex = n; ey = bk1 - n; }
+      } else { ex = n; ey = m; }
+      const int oi = P.pad;  // index of this pair in the caller's arrays
+      A.out_score[oi] = S::to_f64(best);
+      A.out_ex[oi] = ex;
+      A.out_ey[oi] = ey;
+      A.out_status[oi] = st;
+    }
+  }
+}
+
+// ===========================================================================
+// K2: BANDED frame.  A group of G lanes owns one pair; lane l owns C (even)
+// consecutive diagonals d = x - y and the group sweeps anti-diagonals s = x+y
+// in lockstep: a cell on diagonal d at step s needs d-1 and d+1 from step s-1
+// and d from step s-2, so every lane updates C/2 cells per step and only the
+// strip edges cross lanes (one shuffle up on even steps, one down on odd).
+// Pointer layout: [step s - s0][lane][word], C/2 nibbles per lane per step.
+//   replaces: dptable_solve's fill loop pw.c:59-110 in (d,a) coordinates
+//   (_pw_internals.c:87-153) + _banded_find_optimal (:364-414)
+// ===========================================================================
+template <class S, int C, bool BLOCAL, int GOS, int Q>
+__device__ __forceinline__ void bsq_k2_step(
+    int btype, typename S::T (&H)[C], typename S::T (&best)[BLOCAL ? C : 1],
+    int (&besta)[BLOCAL ? C : 1], uint32_t (&pwprev)[(C / 2 + 7) / 8],
+    typename S::T edgeH, uint32_t edgeNib, const typename S::T* s_sub, int L,
+    const uint8_t* oseq, const uint8_t* mseq, int n, int m, int s, int d0, int nreal,
+    typename S::T go, typename S::T ge, uint32_t* pout) {
+  typedef typename S::T T;
+  constexpr int HC = C / 2;
+  constexpr int WPS = (HC + 7) / 8;
+  const T NINF = S::ninf();
+  uint32_t cur[WPS];
+#pragma unroll
+  for (int w = 0; w < WPS; w++) cur[w] = 0u;
+  // Q == 0: cells c = 0,2,..; c = 0 takes (x-1,y) from the lane below (edge*)
+  // Q == 1: cells c = 1,3,..; c = C-1 takes (x,y-1) from the lane above (edge*)
+  T newH[HC];
+  bool commit[HC];
+#pragma unroll
+  for (int hc = 0; hc < HC; hc++) {
+    const int c = 2 * hc + Q;
+    const int d = d0 + c;
+    const int x = (s + d) >> 1, y = (s - d) >> 1;
+    const bool intab = (c < nreal) && x >= 0 && y >= 0 && x <= n && y <= m;
+    T up, left;
+    uint32_t upnib, leftnib;
+    if (c == 0) { up = edgeH; upnib = edgeNib; }
+    else { up = H[c - 1]; upnib = (pwprev[((c - 1) >> 1) >> 3] >> (4 * (((c - 1) >> 1) & 7))) & 0xFu; }
+    if (c == C - 1) { left = edgeH; leftnib = edgeNib; }
+    else { left = H[c + 1]; leftnib = (pwprev[((c + 1) >> 1) >> 3] >> (4 * (((c + 1) >> 1) & 7))) & 0xFu; }
+    const T diag = H[c];
+    const int o = (x >= 1 && x <= n) ? (int)oseq[x - 1] : 0;
+    const int mm = (y >= 1 && y <= m) ? (int)mseq[y - 1] : 0;
+    const T sig = s_sub[o * L + mm];
+    bool ballow;  // _alnchoice_B, _pw_internals.c:182-197
+    if (BLOCAL) ballow = true;
+    else if (btype == BSQ_B_OVERLAP) ballow = (x == 0 || y == 0);
+    else ballow = (x == 0 && y == 0);
+    const T bval = (intab && ballow) ? (T)0 : NINF;
+    T h;
+    uint32_t mk;
+    bsq_cell<S, GOS, true>(up, bsq_extends<GOS>(upnib, BSQ_MD), left,
+                           bsq_extends<GOS>(leftnib, BSQ_MI), diag, sig, bval, go, ge, h, mk);
+    newH[hc] = h;
+    commit[hc] = intab;
+    cur[hc >> 3] |= mk << (4 * (hc & 7));
+    if (BLOCAL) {  // :397-406 restricted to one diagonal (a ascends with s)
+      if (intab && h > best[c]) { best[c] = h; besta[c] = x < y ? x : y; }
+    }
+  }
+  // commit after all reads of this step (cells of one step never read each other)
+#pragma unroll
+  for (int hc = 0; hc < HC; hc++)
+    if (commit[hc]) H[2 * hc + Q] = newH[hc];
+#pragma unroll
+  for (int w = 0; w < WPS; w++) { pout[w] = cur[w]; pwprev[w] = cur[w]; }
+}
+
+template <class S, int G, int C, bool BLOCAL, int GOS>
+__global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
+  typedef typename S::T T;
+  static_assert(C % 2 == 0, "lanes own an even number of diagonals");
+  constexpr int HC = C / 2;
+  constexpr int WPS = (HC + 7) / 8;
+  constexpr int NB = BLOCAL ? C : 1;
+  __shared__ T s_sub[BSQ_MAX_L * BSQ_MAX_L];
+  const int L = A.L;
+  for (int i = threadIdx.x; i < L * L; i += blockDim.x) s_sub[i] = ((const T*)A.subst)[i];
+  __syncthreads();
+
+  const int tid = threadIdx.x;
+  const int l = tid % G;
+  const unsigned lane = (unsigned)tid & 31u;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(unsigned)(G - 1)));
+  const T NINF = S::ninf();
+  const T go = S::go(A), ge = S::ge(A);
+  const int btype = A.btype;
+
+  for (;;) {
+    int p = 0;
+    if (l == 0) p = atomicAdd(A.counter, 1);
+    p = __shfl_sync(gmask, p, 0, G);
+    if (p >= A.npairs) break;
+    const BsqPair P = A.pairs[p];
+    const int n = P.n, m = P.m, dmin = P.dmin, dmax = P.dmax;
+    const int W = dmax - dmin + 1;
+    const uint8_t* oseq = A.codes + P.o_off;
+    const uint8_t* mseq = A.codes + P.m_off;
+    const int d0 = dmin + l * C;       // my first diagonal
+    int nreal = W - l * C;             // how many of my diagonals are inside the band
+    nreal = nreal < 0 ? 0 : (nreal > C ? C : nreal);
+    // last anti-diagonal holding a cell: max over d of 2*min(n, m+d) - d, at d* = clamp(n-m)
+    int dstar = n - m;
+    dstar = dstar < dmin ? dmin : (dstar > dmax ? dmax : dstar);
+    const int s_end = 2 * (n < m + dstar ? n : m + dstar) - dstar;
+    const int s0 = P.s0;               // (s0 - dmin) is even: step parity == loop parity
+
+    T H[C];
+    T best[NB];
+    int besta[NB];
+    uint32_t pwprev[WPS];
+#pragma unroll
+    for (int c = 0; c < C; c++) H[c] = NINF;
+#pragma unroll
+    for (int c = 0; c < NB; c++) { best[c] = NINF; besta[c] = -1; }
+#pragma unroll
+    for (int w = 0; w < WPS; w++) pwprev[w] = 0u;
+    uint32_t* prow = A.ptr + P.ptr_off + (long long)l * WPS;
+
+    for (int s = s0; s <= s_end; s += 2) {
+      {  // even parity: c = 0 needs diagonal d0-1 (lane below, its C-1) from step s-1
+        T eH = __shfl_up_sync(gmask, H[C - 1], 1, G);
+        uint32_t eW = __shfl_up_sync(gmask, pwprev[WPS - 1], 1, G);
+        uint32_t eNib = (eW >> (4 * ((HC - 1) & 7))) & 0xFu;
+        if (l == 0) { eH = NINF; eNib = 0u; }
+        bsq_k2_step<S, C, BLOCAL, GOS, 0>(btype, H, best, besta, pwprev, eH, eNib, s_sub, L, oseq, mseq, n, m,
+                                      s, d0, nreal, go, ge, prow + (long long)(s - s0) * (G * WPS));
+      }
+      {  // odd parity: c = C-1 needs diagonal d0+C (lane above, its 0) from step s
+        T eH = __shfl_down_sync(gmask, H[0], 1, G);
+        uint32_t eW = __shfl_down_sync(gmask, pwprev[0], 1, G);
+        uint32_t eNib = eW & 0xFu;
+        if (l == G - 1) { eH = NINF; eNib = 0u; }
+        bsq_k2_step<S, C, BLOCAL, GOS, 1>(btype, H, best, besta, pwprev, eH, eNib, s_sub, L, oseq, mseq, n, m,
+                                      s + 1, d0, nreal, go, ge,
+                                      prow + (long long)(s + 1 - s0) * (G * WPS));
+      }
+    }
+
+    // end cell, _banded_find_optimal (:364-414): diagonals ascending, strict >
+    T bs = NINF;
+    int bdi = BSQ_INT_MAX, ba = 0;
+    if (!BLOCAL && btype == BSQ_B_GLOBAL) {
+      const int dg = (n - m) - dmin - l * C;  // my local index of the diagonal of (n,m)
+#pragma unroll
+      for (int c = 0; c < C; c++) if (c == dg) { bs = H[c]; bdi = l * C + c; }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        if (c < nreal) {
+          const T cand = BLOCAL ? best[c < NB ? c : 0] : H[c];
+          if (cand > bs) { bs = cand; bdi = l * C + c; ba = BLOCAL ? besta[c < NB ? c : 0] : 0; }
+        }
+      }
+    }
+    bsq_group_best<T, G>(gmask, bs, bdi, ba);
+    if (l == 0) {
+      int ex = -1, ey = -1, st = BSQ_OK;
+      if (bdi == BSQ_INT_MAX) st = BSQ_NO_ALIGNMENT;
+      else {
+        const int d = dmin + bdi;
+        if (BLOCAL) { ex = ba + (d > 0 ? d : 0); ey = ba - (d > 0 ? 0 : d); }
+        else { ex = n < m + d ? n : m + d; ey = ex - d; }  // last cell of the diagonal (:383)
+      }
+      const int oi = P.pad;
+      A.out_score[oi] = S::to_f64(bs);
+      A.out_ex[oi] = ex;
+      A.out_ey[oi] = ey;
+      A.out_status[oi] = st;
+    }
+  }
+}
+

@@ -1,0 +1,26 @@
+// bsq_launch.h -- kernel-family tables and the per-translation-unit launchers.
+// The fill kernels are instantiated over (arithmetic, lane geometry, B rule,
+// end rule, sign of go); each family/arithmetic lives in its own .cu so the
+// build parallelises.
+#pragma once
+#include "bsq_common.h"
+
+#define BSQ_FILL_THREADS 128
+
+struct BsqK1Cfg { int G, K; };   // STD: G lanes x K columns per pass
+struct BsqK2Cfg { int G, C; };   // BANDED: G lanes x C diagonals
+
+#define BSQ_K1_NCFG 3
+#define BSQ_K2_NCFG 5
+static const BsqK1Cfg BSQ_K1_CFGS[BSQ_K1_NCFG] = {{8, 19}, {16, 16}, {32, 16}};
+static const BsqK2Cfg BSQ_K2_CFGS[BSQ_K2_NCFG] = {{8, 8}, {8, 18}, {16, 16}, {32, 16}, {32, 32}};
+
+enum { BSQ_OP_OCCUPANCY = 0, BSQ_OP_LAUNCH = 1 };
+
+// op == BSQ_OP_OCCUPANCY: returns resident blocks per SM (>= 1) for the kernel
+// op == BSQ_OP_LAUNCH   : launches it on `grid` blocks, returns 0 or a negative
+//                         error (unknown variant)
+int bsq_k1_f64_op(int cfg, int ball, int eall, int gos, int op, int grid, cudaStream_t st, const BsqFillArgs* A);
+int bsq_k1_i32_op(int cfg, int ball, int eall, int gos, int op, int grid, cudaStream_t st, const BsqFillArgs* A);
+int bsq_k2_f64_op(int cfg, int blocal, int gos, int op, int grid, cudaStream_t st, const BsqFillArgs* A);
+int bsq_k2_i32_op(int cfg, int blocal, int gos, int op, int grid, cudaStream_t st, const BsqFillArgs* A);

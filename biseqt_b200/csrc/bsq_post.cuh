@@ -1,0 +1,184 @@
+// bsq_post.cuh -- traceback, transcript packing and the table_scores debug
+// kernel.  Included by exactly one translation unit (bsq_host.cu).
+#pragma once
+#include "bsq_kernels.cuh"
+
+// ===========================================================================
+// K4: traceback (pw.c:116-151).  One thread per pair walks the 4-bit masks
+// from the end cell: the current op is the lowest set bit on arrival by M or at
+// the end cell (base = choices[0], _pw_internals.c:235) and the first maximiser
+// of _pw_internals.c:266-278 on arrival by a gap.  Ops are written backwards
+// into the right end of the pair's slot; a second kernel packs them.
+// ===========================================================================
+__device__ __forceinline__ uint32_t bsq_lowest(uint32_t mk) { return mk & (0u - mk); }
+
+__device__ __forceinline__ uint32_t bsq_gap_base(uint32_t mk, uint32_t own, int gosign) {
+  if (gosign < 0) return (mk & own) ? own : bsq_lowest(mk);
+  if (gosign > 0) return (mk & (0xFu ^ own)) ? bsq_lowest(mk & (0xFu ^ own)) : own;
+  return bsq_lowest(mk);
+}
+
+__device__ __forceinline__ uint32_t bsq_get_mask(const BsqTraceArgs& A, const BsqPair& P, int x, int y) {
+  long long idx;
+  int sh;
+  if (A.mode == BSQ_STD_MODE) {
+    const int G = A.G, K = A.K, BW = G * K, WPL = (K + 7) / 8;
+    const int pass = y / BW, r = y - pass * BW, l = r / K, k = r - l * K;
+    idx = P.ptr_off + (((long long)pass * (P.n + 1) + x) * G + l) * WPL + (k >> 3);
+    sh = 4 * (k & 7);
+  } else {
+    const int G = A.G, C = A.K, WPS = (C / 2 + 7) / 8;
+    const int s = x + y, di = (x - y) - P.dmin, l = di / C, c = di - l * C, hc = c >> 1;
+    idx = P.ptr_off + ((long long)(s - P.s0) * G + l) * WPS + (hc >> 3);
+    sh = 4 * (hc & 7);
+  }
+  return (A.ptr[idx] >> sh) & 0xFu;
+}
+
+__global__ void __launch_bounds__(128) bsq_k4_traceback(const BsqTraceArgs A) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= A.npairs) return;
+  const BsqPair P = A.pairs[p];
+  const int oi = P.pad;  // index of this pair in the caller's arrays
+  if (A.status[oi] != BSQ_OK) { A.txlen[oi] = 0; A.sx[oi] = -1; A.sy[oi] = -1; return; }
+  const int ex = A.ex[oi], ey = A.ey[oi];
+  int x = ex, y = ey, len = 0;
+  const uint8_t* oseq = A.codes + P.o_off;
+  const uint8_t* mseq = A.codes + P.m_off;
+  char* wr = A.slots + P.tx_slot + (long long)P.n + P.m;  // one past the slot end
+  uint32_t op = bsq_lowest(bsq_get_mask(A, P, x, y));
+  while (op != BSQ_MB && op != 0u && len < P.n + P.m) {
+    char ch;
+    if (op == BSQ_MM) {
+      ch = (oseq[x - 1] == mseq[y - 1]) ? 'M' : 'S';  // _pw_internals.c:232
+      x--; y--;
+      op = bsq_lowest(bsq_get_mask(A, P, x, y));
+    } else if (op == BSQ_MD) {
+      ch = 'D'; x--;
+      op = bsq_gap_base(bsq_get_mask(A, P, x, y), BSQ_MD, A.gosign);
+    } else {
+      ch = 'I'; y--;
+      op = bsq_gap_base(bsq_get_mask(A, P, x, y), BSQ_MI, A.gosign);
+    }
+    len++;
+    wr[-len] = ch;
+  }
+  A.txlen[oi] = len;
+  A.sx[oi] = x;
+  A.sy[oi] = y;
+  // pw.c:121-138: pos = (ex+ey) - len; pos <= 0 -> PANICK; no ops -> NULL
+  A.status[oi] = (ex + ey - len <= 0) ? BSQ_REF_WOULD_ABORT : (len == 0 ? BSQ_EMPTY : BSQ_OK);
+}
+
+// exclusive scan of txlen (int32) into int64 offsets, three small kernels
+#define BSQ_SCAN_TILE 2048
+__global__ void __launch_bounds__(256) bsq_scan_tile_sums(const int* in, int n, long long* tile_sums) {
+  __shared__ long long sh[256];
+  const int base = blockIdx.x * BSQ_SCAN_TILE;
+  long long acc = 0;
+  for (int i = threadIdx.x; i < BSQ_SCAN_TILE; i += 256)
+    if (base + i < n) acc += in[base + i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = sh[0];
+}
+// single block: tile_sums -> exclusive prefix (+ *base), writes grand total back to *base_total
+__global__ void __launch_bounds__(256) bsq_scan_tiles(long long* tile_sums, int ntiles, long long* total_out) {
+  __shared__ long long carry;
+  __shared__ long long sh[256];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < ntiles; base += 256) {
+    const int i = base + threadIdx.x;
+    long long v = (i < ntiles) ? tile_sums[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) {  // Hillis-Steele inclusive
+      long long t = ((int)threadIdx.x >= off) ? sh[threadIdx.x - off] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < ntiles) tile_sums[i] = carry + sh[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 255) carry += sh[255];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_out = carry;
+}
+__global__ void __launch_bounds__(256) bsq_scan_apply(const int* in, int n, const long long* tile_sums,
+                                                      long long* out) {
+  __shared__ long long sh[256];
+  __shared__ long long carry;
+  const int base = blockIdx.x * BSQ_SCAN_TILE;
+  if (threadIdx.x == 0) carry = tile_sums[blockIdx.x];
+  __syncthreads();
+  for (int j = 0; j < BSQ_SCAN_TILE; j += 256) {
+    const int i = base + j + threadIdx.x;
+    long long v = (i < n) ? in[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) {
+      long long t = ((int)threadIdx.x >= off) ? sh[threadIdx.x - off] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < n) out[i] = carry + sh[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 255) carry += sh[255];
+    __syncthreads();
+  }
+}
+
+// pack transcripts: one warp per pair copies slot tail -> packed[off]
+__global__ void __launch_bounds__(256) bsq_pack_transcripts(const BsqPair* pairs, int npairs,
+                                                            const int* txlen, const long long* off,
+                                                            const char* slots, char* packed) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= npairs) return;
+  const int oi = pairs[warp].pad;
+  const int len = txlen[oi];
+  const char* src = slots + pairs[warp].tx_slot + (long long)pairs[warp].n + pairs[warp].m - len;
+  char* dst = packed + off[oi];
+  for (int i = lane; i < len; i += 32) dst[i] = src[i];
+}
+
+// ===========================================================================
+// table_scores(): H of every cell of one STD problem (pw.py:278-285).  A
+// debug/teaching path: one thread block, anti-diagonal sweep over global
+// memory, F64 only.
+// ===========================================================================
+template <int GOS>
+__global__ void __launch_bounds__(256) bsq_table_scores_kernel(const uint8_t* o, int n, const uint8_t* t,
+                                                               int m, const double* subst, int L, double go,
+                                                               double ge, int bmode, double* Hout,
+                                                               uint8_t* mask) {
+  const double NINF = ScF64::ninf();
+  const long long Wd = (long long)m + 1;
+  for (int s = 0; s <= n + m; s++) {
+    const int xlo = s - m > 0 ? s - m : 0, xhi = s < n ? s : n;
+    for (int x = xlo + (int)threadIdx.x; x <= xhi; x += (int)blockDim.x) {
+      const int y = s - x;
+      const double up = x > 0 ? Hout[(x - 1) * Wd + y] : NINF;
+      const double left = y > 0 ? Hout[x * Wd + y - 1] : NINF;
+      const double diag = (x > 0 && y > 0) ? Hout[(x - 1) * Wd + y - 1] : NINF;
+      const uint32_t upn = x > 0 ? mask[(x - 1) * Wd + y] : 0u;
+      const uint32_t leftn = y > 0 ? mask[x * Wd + y - 1] : 0u;
+      const double sig = (x > 0 && y > 0) ? subst[(int)o[x - 1] * L + (int)t[y - 1]] : 0.0;
+      bool ballow = (x == 0 && y == 0) || bmode == BSQ_B_ALL || (bmode == BSQ_B_EDGE && (x == 0 || y == 0));
+      double h;
+      uint32_t mk;
+      bsq_cell<ScF64, GOS, true>(up, bsq_extends<GOS>(upn, BSQ_MD), left, bsq_extends<GOS>(leftn, BSQ_MI),
+                                 diag, sig, ballow ? 0.0 : NINF, go, ge, h, mk);
+      Hout[x * Wd + y] = h;
+      mask[x * Wd + y] = (uint8_t)mk;
+    }
+    __syncthreads();
+  }
+}

@@ -1,0 +1,320 @@
+// simt_emu.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// A tiny single-OS-thread SIMT emulator: every CUDA thread of a block is a
+// ucontext fiber, scheduled round-robin; warp collectives (__shfl_*_sync,
+// __syncwarp, __ballot_sync) and __syncthreads are rendezvous points.  Plus a
+// fake of the handful of CUDA runtime calls the host side of libbsqgpu uses.
+//
+// Purpose: the authoring container has no GPU.  Compiling the *same* kernel
+// and scheduler sources (biseqt_b200/csrc/*.cu) with -DBSQ_SIMT_EMU against
+// this header yields tests/simt_emu/_build/libbsqgpu_emu.so, which the
+// `-m "not gpu"` tests drive through the real C ABI to check kernel logic
+// (lane skew, shuffles, pointer-table layout, traceback, chunking) against the
+// oracle before any GPU minute is spent.  It is never shipped, never loaded by
+// the biseqt_b200 package on its own, and is ~10^4x slower than a GPU.
+#pragma once
+#include <ucontext.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <functional>
+#include <chrono>
+#include <algorithm>
+
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+
+namespace emu {
+
+struct Coll {            // one rendezvous per distinct participation mask
+  unsigned mask = 0;
+  uint64_t vals[2][32];
+  int arrived = 0;
+  unsigned gen = 0;
+};
+struct Warp {
+  std::vector<Coll> colls;
+  int nlanes = 0;
+};
+
+struct Lane {
+  ucontext_t ctx;
+  char* stack = nullptr;
+  bool done = false;
+};
+
+struct Block {
+  std::vector<Lane> lanes;
+  std::vector<Warp> warps;
+  ucontext_t sched;
+  int cur = 0;
+  int nthreads = 0;
+  dim3 bidx, bdim, gdim;
+  int bar_arrived = 0;
+  unsigned bar_gen = 0;
+  uint64_t progress = 0;
+  std::vector<char> dyn_smem;
+  std::function<void()> body;
+};
+
+inline Block*& cur_block() { static Block* b = nullptr; return b; }
+
+inline void yield() {
+  Block* b = cur_block();
+  swapcontext(&b->lanes[b->cur].ctx, &b->sched);
+}
+
+inline void trampoline() {
+  Block* b = cur_block();
+  b->body();
+  b->lanes[b->cur].done = true;
+  b->progress++;
+  swapcontext(&b->lanes[b->cur].ctx, &b->sched);
+}
+
+// the lanes named in `mask` deposit v and rendezvous; returns the 32 slots
+inline const uint64_t* warp_exchange(unsigned mask, uint64_t v) {
+  Block* b = cur_block();
+  int tid = b->cur;
+  Warp& w = b->warps[tid / 32];
+  if (w.nlanes < 32) mask &= (1u << w.nlanes) - 1u;
+  if (!(mask & (1u << (tid % 32)))) {
+    fprintf(stderr, "simt_emu: lane %d not in its own collective mask %08x\n", tid, mask);
+    abort();
+  }
+  int ci = -1;
+  for (int i = 0; i < (int)w.colls.size(); i++) if (w.colls[i].mask == mask) { ci = i; break; }
+  if (ci < 0) { w.colls.emplace_back(); ci = (int)w.colls.size() - 1; w.colls[ci].mask = mask; }
+  // NOTE: w.colls may reallocate while we are parked -> re-index after yield
+  unsigned g = w.colls[ci].gen;
+  int par = g & 1;
+  w.colls[ci].vals[par][tid % 32] = v;
+  w.colls[ci].arrived++;
+  if (w.colls[ci].arrived == __builtin_popcount(mask)) {
+    w.colls[ci].arrived = 0;
+    w.colls[ci].gen++;
+    b->progress++;
+  } else {
+    while (b->warps[tid / 32].colls[ci].gen == g) yield();
+  }
+  return b->warps[tid / 32].colls[ci].vals[par];
+}
+
+inline void block_barrier() {
+  Block* b = cur_block();
+  unsigned g = b->bar_gen;
+  b->bar_arrived++;
+  if (b->bar_arrived == b->nthreads) {
+    b->bar_arrived = 0;
+    b->bar_gen++;
+    b->progress++;
+  } else {
+    while (b->bar_gen == g) yield();
+  }
+}
+
+inline void run_block(Block& B) {
+  const size_t STK = 256 * 1024;
+  cur_block() = &B;
+  B.lanes.assign(B.nthreads, Lane());
+  B.warps.assign((B.nthreads + 31) / 32, Warp());
+  for (int w = 0; w < (int)B.warps.size(); w++)
+    B.warps[w].nlanes = std::min(32, B.nthreads - 32 * w);
+  for (int i = 0; i < B.nthreads; i++) {
+    Lane& L = B.lanes[i];
+    L.stack = (char*)malloc(STK);
+    getcontext(&L.ctx);
+    L.ctx.uc_stack.ss_sp = L.stack;
+    L.ctx.uc_stack.ss_size = STK;
+    L.ctx.uc_link = nullptr;
+    makecontext(&L.ctx, (void (*)())trampoline, 0);
+  }
+  int ndone = 0;
+  while (ndone < B.nthreads) {
+    uint64_t before = B.progress;
+    ndone = 0;
+    for (int i = 0; i < B.nthreads; i++) {
+      if (B.lanes[i].done) { ndone++; continue; }
+      B.cur = i;
+      swapcontext(&B.sched, &B.lanes[i].ctx);
+      if (B.lanes[i].done) ndone++;
+    }
+    if (ndone < B.nthreads && B.progress == before) {
+      fprintf(stderr, "simt_emu: deadlock in block (%u): %d/%d lanes done, no progress "
+              "(divergent collective or exited lane inside a full-mask shuffle)\n",
+              B.bidx.x, ndone, B.nthreads);
+      abort();
+    }
+  }
+  for (auto& L : B.lanes) free(L.stack);
+  cur_block() = nullptr;
+}
+
+template <class F, class... A>
+inline void launch(F kernel, dim3 grid, dim3 block, size_t smem, A... args) {
+  for (unsigned by = 0; by < grid.y; by++)
+    for (unsigned bx = 0; bx < grid.x; bx++) {
+      Block B;
+      B.nthreads = (int)(block.x * block.y * block.z);
+      B.bidx = dim3(bx, by, 0);
+      B.bdim = block;
+      B.gdim = grid;
+      B.dyn_smem.assign(smem + 16, 0);
+      B.body = [=]() { kernel(args...); };
+      run_block(B);
+    }
+}
+
+inline dim3 tid3() {
+  Block* b = cur_block();
+  unsigned t = (unsigned)b->cur;
+  return dim3(t % b->bdim.x, (t / b->bdim.x) % b->bdim.y, t / (b->bdim.x * b->bdim.y));
+}
+inline char* dyn_smem() { return cur_block()->dyn_smem.data(); }
+
+template <class T> inline uint64_t to_bits(T v) {
+  uint64_t u = 0; static_assert(sizeof(T) <= 8, "shuffle payload"); memcpy(&u, &v, sizeof(T)); return u;
+}
+template <class T> inline T from_bits(uint64_t u) { T v; memcpy(&v, &u, sizeof(T)); return v; }
+
+}  // namespace emu
+
+// ---- CUDA language surface used by the kernels --------------------------
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __restrict__
+#define __shared__ static
+#define __constant__ static
+#define threadIdx (emu::tid3())
+#define blockIdx (emu::cur_block()->bidx)
+#define blockDim (emu::cur_block()->bdim)
+#define gridDim (emu::cur_block()->gdim)
+#define warpSize 32
+
+inline void __syncthreads() { emu::block_barrier(); }
+inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::warp_exchange(mask, 0); }
+inline void __threadfence() {}
+inline void __threadfence_block() {}
+
+template <class T> inline T __shfl_sync(unsigned mask_, T v, int src, int width = 32) {
+  int lane = emu::cur_block()->cur % 32;
+  const uint64_t* all = emu::warp_exchange(mask_, emu::to_bits(v));
+  int base = lane & ~(width - 1);
+  return emu::from_bits<T>(all[base + (src & (width - 1))]);
+}
+template <class T> inline T __shfl_up_sync(unsigned mask_, T v, unsigned delta, int width = 32) {
+  int lane = emu::cur_block()->cur % 32;
+  const uint64_t* all = emu::warp_exchange(mask_, emu::to_bits(v));
+  int base = lane & ~(width - 1);
+  int src = lane - (int)delta;
+  return src < base ? v : emu::from_bits<T>(all[src]);
+}
+template <class T> inline T __shfl_down_sync(unsigned mask_, T v, unsigned delta, int width = 32) {
+  int lane = emu::cur_block()->cur % 32;
+  const uint64_t* all = emu::warp_exchange(mask_, emu::to_bits(v));
+  int base = lane & ~(width - 1);
+  int src = lane + (int)delta;
+  return src >= base + width ? v : emu::from_bits<T>(all[src]);
+}
+template <class T> inline T __shfl_xor_sync(unsigned mask_, T v, int m, int width = 32) {
+  int lane = emu::cur_block()->cur % 32;
+  const uint64_t* all = emu::warp_exchange(mask_, emu::to_bits(v));
+  int base = lane & ~(width - 1);
+  int src = lane ^ m;
+  return (src < base || src >= base + width) ? v : emu::from_bits<T>(all[src]);
+}
+inline unsigned __ballot_sync(unsigned mask_, int pred) {
+  emu::Block* b = emu::cur_block();
+  int nl = b->warps[b->cur / 32].nlanes;
+  const uint64_t* all = emu::warp_exchange(mask_, (uint64_t)(pred != 0));
+  unsigned r = 0;
+  for (int i = 0; i < nl; i++) if (mask_ & (1u << i)) r |= (unsigned)(all[i] & 1) << i;
+  return r;
+}
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline long long __double_as_longlong(double d) { long long v; memcpy(&v, &d, 8); return v; }
+inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+inline int __double2hiint(double d) { return (int)(__double_as_longlong(d) >> 32); }
+inline int __double2loint(double d) { return (int)(__double_as_longlong(d) & 0xffffffffLL); }
+inline double __hiloint2double(int hi, int lo) {
+  return __longlong_as_double(((long long)hi << 32) | (unsigned)lo);
+}
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __vimax3_s32(int a, int b, int c) { return std::max(a, std::max(b, c)); }
+inline int __vimax3_s32_relu(int a, int b, int c) { return std::max(0, std::max(a, std::max(b, c))); }
+inline int __viaddmax_s32(int a, int b, int c) { return std::max(a + b, c); }
+template <class T> inline T __ldg(const T* p) { return *p; }
+
+template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
+template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
+template <class T> inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
+
+// ---- CUDA runtime surface used by the host scheduler -------------------
+typedef int cudaError_t;
+typedef struct emuStream_* cudaStream_t;
+struct emuEvent_ { std::chrono::steady_clock::time_point t; };
+typedef emuEvent_* cudaEvent_t;
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
+enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaEventDefault = 0, cudaEventDisableTiming = 2 };
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type; };
+struct cudaDeviceProp { char name[256]; int multiProcessorCount; size_t totalGlobalMem; int major, minor; };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+
+inline const char* cudaGetErrorString(cudaError_t e) { return e == 0 ? "no error" : "emulated error"; }
+inline cudaError_t cudaGetLastError() { return 0; }
+inline cudaError_t cudaPeekAtLastError() { return 0; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
+inline cudaError_t cudaSetDevice(int) { return 0; }
+inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
+  memset(p, 0, sizeof *p); strcpy(p->name, "simt_emu");
+  const char* sm = getenv("BSQ_EMU_SMS");
+  p->multiProcessorCount = sm ? atoi(sm) : 2; p->totalGlobalMem = (size_t)1 << 30; p->major = 10; p->minor = 0; return 0;
+}
+inline cudaError_t cudaMemGetInfo(size_t* fr, size_t* tot) {
+  const char* e = getenv("BSQ_EMU_FREE_BYTES");
+  size_t v = e ? (size_t)atoll(e) : ((size_t)1 << 30);
+  *fr = v; *tot = v; return 0;
+}
+inline cudaError_t cudaMalloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
+template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
+inline cudaError_t cudaFree(void* p) { free(p); return 0; }
+inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
+template <class T> inline cudaError_t cudaHostAlloc(T** p, size_t n, unsigned f) { return cudaHostAlloc((void**)p, n, f); }
+inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaHostAlloc(p, n, 0); }
+inline cudaError_t cudaFreeHost(void* p) { free(p); return 0; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { if (n) memcpy(d, s, n); return 0; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) memcpy(d, s, n); return 0; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) { if (n) memset(d, v, n); return 0; }
+inline cudaError_t cudaMemset(void* d, int v, size_t n) { if (n) memset(d, v, n); return 0; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }
+inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return 0; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+inline cudaError_t cudaDeviceSynchronize() { return 0; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emuEvent_(); return 0; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new emuEvent_(); return 0; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = 0) { e->t = std::chrono::steady_clock::now(); return 0; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+  *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(); return 0;
+}
+inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) { a->type = cudaMemoryTypeUnregistered; return 0; }
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
+template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 1; return 0; }

@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py -- GCUPS of the pwlib DP path (fill + traceback) on B200.
+
+A "step" is one pass of the hot path over one batch of synthetic pairs of
+BASELINE.json's configs[1] (1M read pairs of 150 bp, STD LOCAL, affine gaps;
+integer IgBlast-like scores).  Three numbers:
+
+  value   GCUPS with inputs already resident in HBM (bsq_batch_run), timed with
+          CUDA events inside the library on its own stream
+  e2e     the same metric through the public batch call (bsq_align_batch) with
+          pinned HOST buffers, H2D + D2H inside the timed region
+  cpu_baseline / --impl reference
+          the reference's own C library (oracle/_ref/pwlib.so, compiled from the
+          untouched sources) on the host cores, bounded sample of the same pairs
+
+One process per GPU (torchrun); pairs are sharded by rank, no collective on
+the data path (weak scaling: every rank aligns its own 1M pairs).  torch is
+imported only for the barrier / max-over-ranks of a multi-GPU run.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import bench_workloads as bw  # noqa: E402
+
+WORKLOAD_PAIRS = {'c2_int': 1000000, 'c2_logodds': 1000000, 'c3_int': 4096, 'c3_logodds': 4096,
+                  'c4_int': 512, 'c1': 1}
+
+
+def ops_per_cell(go):
+    """Algorithmic ALU ops per cell: 5 adds + 3 max + 4 equality
+    tests; the two '+go' adds vanish when go == 0."""
+    return 12 if go != 0 else 10
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for k, nme in enumerate(names):
+                if r[5 + k].lower().startswith('active'):
+                    reasons.add(nme)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': float(max(mx)) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# CPU reference: the unmodified pwlib through oracle/pwref.py, one process per core
+# ---------------------------------------------------------------------------
+def _cpu_worker(task):
+    kind, w, idx = task
+    from oracle import pwref, lean
+    use_ref = (kind == 'reference')
+    subst = w['subst'].tolist()
+    cells, busy = 0, 0.0
+    for i in idx:
+        o = w['codes'][w['o_off'][i]:w['o_off'][i] + w['o_len'][i]]
+        t = w['codes'][w['m_off'][i]:w['m_off'][i] + w['m_len'][i]]
+        dr = None if w['mode'] == 0 else (int(w['dmin'][i]), int(w['dmax'][i]))
+        if use_ref:
+            P = pwref.Problem(o, t, subst, w['go'], w['ge'], w['mode'], w['type'], dr)
+            t0 = time.perf_counter()     # init + solve + traceback + free
+            if P.init() == 0:
+                if P.solve() is not None:
+                    P.traceback()
+                P.free()
+            busy += time.perf_counter() - t0
+        else:
+            t0 = time.perf_counter()
+            lean.align(o, t, w['subst'], w['go'], w['ge'], w['mode'], w['type'], dr)
+            busy += time.perf_counter() - t0
+        cells += bw_cells_one(w, i)
+    return cells, busy, len(idx)
+
+
+def bw_cells_one(w, i):
+    n, m = int(w['o_len'][i]), int(w['m_len'][i])
+    if w['mode'] == 0:
+        return (n + 1) * (m + 1)
+    from oracle import lean
+    return lean.count_cells(1, n, m, int(w['dmin'][i]), int(w['dmax'][i]))
+
+
+def cpu_reference_run(w, pairs_per_core, cores=None, pool=None):
+    """Aligns a bounded sample on all host cores; returns dict(value GCUPS, ...)."""
+    from oracle import pwref
+    import multiprocessing as mp
+    kind = 'reference' if pwref.available() else 'port'
+    cores = cores or (os.cpu_count() or 1)
+    N = len(w['o_len'])
+    total = min(N, pairs_per_core * cores)
+    idx = np.arange(total)
+    slim = {k: w[k] for k in ('codes', 'o_off', 'o_len', 'm_off', 'm_len', 'mode', 'type', 'subst', 'go', 'ge')}
+    if w['mode'] == 1:
+        slim['dmin'], slim['dmax'] = w['dmin'], w['dmax']
+    hi = int(max(w['o_off'][total - 1] + w['o_len'][total - 1], w['m_off'][total - 1] + w['m_len'][total - 1]))
+    slim['codes'] = w['codes'][:hi]
+    tasks = [(kind, slim, idx[c::cores]) for c in range(cores)]
+    own = pool is None
+    if own:
+        pool = mp.get_context('fork').Pool(cores)
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_worker, tasks)
+    wall = time.perf_counter() - t0
+    if own:
+        pool.close()
+    cells = sum(r[0] for r in res)
+    # every worker ran concurrently; aggregate rate = sum of per-worker rates over
+    # the timed regions (struct construction in Python is excluded)
+    rate = sum(r[0] / r[1] for r in res if r[1] > 0)
+    return {'value': rate / 1e9, 'unit': 'GCUPS', 'cores': cores, 'kind': kind,
+            'sample': '%d of the workload\'s pairs (%d per core), init+solve+traceback+free per pair, -O2 build'
+                      % (total, pairs_per_core),
+            'pairs_per_s': sum(r[2] / r[1] for r in res if r[1] > 0), 'wall_s': wall, 'cells': cells}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    kind = args.workload
+    per_core = {'c2_int': 300, 'c2_logodds': 300}.get(kind, 1)
+    cores = os.cpu_count() or 1
+    npairs = max(per_core * cores, 64)
+    w = bw.make(kind, min(npairs, WORKLOAD_PAIRS[kind]), seed=2)
+    import multiprocessing as mp
+    pool = mp.get_context('fork').Pool(cores)
+    times, last = [], None
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        last = cpu_reference_run(w, per_core, cores, pool)
+        if s >= args.warmup:
+            times.append((time.perf_counter() - t0, last))
+    pool.close()
+    val = float(np.mean([r['value'] for _, r in times]))
+    line = {
+        'impl': 'reference', 'metric': 'GCUPS', 'value': val, 'unit': 'GCUPS', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * float(np.mean([t for t, _ in times])), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': w['desc'], 'sample_pairs_per_step': int(len(w['o_len']))},
+        'cpu_baseline': {'value': val, 'unit': 'GCUPS', 'cores': last['cores'], 'kind': last['kind'],
+                         'sample': last['sample']},
+        'pairs_per_s': last['pairs_per_s'],
+        'e2e': {'value': val, 'unit': 'GCUPS', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def pinned_copy(eng, a):
+    p = eng.pinned_empty(len(a), a.dtype)
+    p[:] = a
+    return p
+
+
+def measure(eng, w, steps, warmup, sampler_gpu, do_e2e=True):
+    """Returns dict with resident + e2e timings for workload w on this rank."""
+    from biseqt_b200 import batch
+    N = len(w['o_len'])
+    kw = dict(dmin=w.get('dmin'), dmax=w.get('dmax'))
+    args = (w['mode'], w['type'], w['subst'], w['go'], w['ge'])
+    # ---- device-resident: upload once, run W + K times -----------------
+    rb = eng.upload(w['codes'], w['o_off'], w['o_len'], w['m_off'], w['m_len'], *args, **kw)
+    for _ in range(warmup):
+        rb.run()
+    barrier()
+    sampler = ClockSampler(sampler_gpu).start()
+    res_ms, fill_ms, launches = [], [], 0
+    t = None
+    for _ in range(steps):
+        t = rb.run()
+        res_ms.append(t['total_ms'])
+        fill_ms.append(t['fill_ms'])
+        launches += t['fill_launches']
+    clocks = sampler.stop()
+    barrier()
+    cells = t['cells']
+    out = {'cells': cells, 'pairs': N, 'resident_ms': float(np.sum(res_ms)), 'fill_ms': float(np.sum(fill_ms)),
+           'launches': launches, 'clocks': clocks, 'dtype': batch.DTYPE_NAMES[t['dtype']],
+           'ptr_bytes': t['ptr_bytes'], 'chunks': t['chunks']}
+    rb.release()
+    # ---- end to end: pinned host buffers in, pinned host buffers out ------
+    if do_e2e:
+        pin = {k: pinned_copy(eng, np.ascontiguousarray(w[k])) for k in ('codes', 'o_off', 'o_len', 'm_off', 'm_len')}
+        if w['mode'] == 1:
+            kw = dict(dmin=pinned_copy(eng, w['dmin']), dmax=pinned_copy(eng, w['dmax']))
+        cap = int(w['o_len'].astype(np.int64).sum() + w['m_len'].astype(np.int64).sum())
+        outb = {'score': eng.pinned_empty(N, np.float64), 'tx_off': eng.pinned_empty(N + 1, np.int64),
+                'tx_buf': eng.pinned_empty(cap, np.uint8)}
+        for k in ('end_x', 'end_y', 'start_x', 'start_y', 'status'):
+            outb[k] = eng.pinned_empty(N, np.int32)
+        for _ in range(max(1, warmup - 1)):
+            eng.align(pin['codes'], pin['o_off'], pin['o_len'], pin['m_off'], pin['m_len'], *args, out=outb, **kw)
+        barrier()
+        t0 = time.perf_counter()
+        h2d = d2h = 0
+        for _ in range(steps):
+            r = eng.align(pin['codes'], pin['o_off'], pin['o_len'], pin['m_off'], pin['m_len'], *args, out=outb, **kw)
+            tt = eng.timing()
+            h2d, d2h = tt['h2d_bytes'], tt['d2h_bytes']
+            launches += tt['fill_launches']
+        out['e2e_s'] = time.perf_counter() - t0
+        out['h2d'], out['d2h'] = h2d, d2h
+        out['ok_frac'] = float((r.status == 0).mean())
+        out['launches'] = launches
+        barrier()
+    return out
+
+
+_dist = None
+
+
+def barrier():
+    if _dist is not None:
+        import torch
+        torch.cuda.synchronize()
+        _dist.barrier()
+
+
+def allreduce(val, op):
+    if _dist is None:
+        return val
+    import torch
+    t = torch.tensor([float(val)], dtype=torch.float64, device='cuda')
+    _dist.all_reduce(t, op=getattr(_dist.ReduceOp, op))
+    return float(t.item())
+
+
+def main():
+    global _dist
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c2_int', choices=sorted(WORKLOAD_PAIRS))
+    ap.add_argument('--pairs', type=int, default=0, help='pairs per GPU (default: the config\'s size)')
+    ap.add_argument('--no-extras', action='store_true', help='skip the secondary workloads')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+
+    if args.impl == 'reference':
+        run_reference_arm(args, rank, world)
+        return
+
+    from biseqt_b200 import batch
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl')
+        _dist = dist
+    eng = batch.Engine(local)
+
+    kind = args.workload
+    npairs = args.pairs or WORKLOAD_PAIRS[kind]
+    w = bw.make(kind, npairs, seed=2 + 1000 * rank)     # every rank aligns its own shard
+    m = measure(eng, w, args.steps, args.warmup, local)
+
+    # whole-job numbers: all ranks' cells over the slowest rank's time
+    cells_all = allreduce(m['cells'], 'SUM')
+    pairs_all = allreduce(m['pairs'], 'SUM')
+    res_ms = allreduce(m['resident_ms'], 'MAX')
+    e2e_s = allreduce(m['e2e_s'], 'MAX')
+    launches = allreduce(m['launches'], 'SUM')
+    value = cells_all * args.steps / (res_ms * 1e-3) / 1e9
+    e2e = cells_all * args.steps / e2e_s / 1e9
+
+    line = None
+    if rank == 0:
+        # roofline of the dominant kernel (DP fill): ALU-pipe bound, SURVEY.md section 8(d)
+        opc = ops_per_cell(w['go'])
+        which = 'IADD' if m['dtype'] == 'i32' else 'DADD'
+        try:
+            pipe = {k: eng.microbench(k) for k in ('DADD', 'DMAX', 'DSETP', 'IADD', 'VIMAX3', 'VIADDMAX', 'SHFL', 'LDS64')}
+        except Exception as e:   # never hide the bench line behind a microbenchmark problem
+            pipe = {'error': str(e)}
+        fill_s = m['fill_ms'] * 1e-3
+        achieved = m['cells'] * args.steps * opc / fill_s / 1e9
+        peak = pipe.get(which, 0.0) / 1e9 if 'error' not in pipe else None
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        hbm_peak = peaks.get('hbm_gbs', 6650.0)
+        roofline = {
+            'bound': 'alu', 'achieved': achieved, 'peak': peak, 'unit': 'Gop/s',
+            'frac': (achieved / peak) if peak else None, 'traffic': None,
+            'ops_per_cell': opc, 'pipe': which,
+            'note': 'achieved = cells x algorithmic ops/cell / fill-kernel time (CUDA events on the library stream); '
+                    'peak = add.%s issue rate measured in this run (bsq_microbench)' % ('s32' if which == 'IADD' else 'f64'),
+            'pipe_rates_gops': {k: v / 1e9 for k, v in pipe.items()} if 'error' not in pipe else pipe,
+            'hbm': {'achieved': m['ptr_bytes'] * args.steps / fill_s / 1e9, 'peak': hbm_peak,
+                    'unit': 'GB/s', 'frac': m['ptr_bytes'] * args.steps / fill_s / 1e9 / hbm_peak,
+                    'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback',
+                    'note': 'traceback-pointer bytes written by the fill kernel / fill time'},
+        }
+        line = {
+            'metric': 'GCUPS', 'value': value, 'unit': 'GCUPS', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': res_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': m['dtype'], 'data': 'synthetic',
+            'config': {'workload': w['desc'], 'pairs_per_gpu': npairs, 'seed': 2,
+                       'l2': 'inputs larger than L2 (%.0f MB of sequences + %.1f GB of pointer tables per step)'
+                             % (len(w['codes']) / 1e6, m['ptr_bytes'] / 1e9),
+                       'timed': 'fill + traceback + transcript packing, inputs/outputs resident in HBM'},
+            'pairs_per_s': pairs_all * args.steps / (res_ms * 1e-3),
+            'fill_only_gcups': cells_all * args.steps / (allreduce(m['fill_ms'], 'MAX') * 1e-3) / 1e9 if world == 1 else None,
+            'clocks': m['clocks'],
+            'e2e': {'value': e2e, 'unit': 'GCUPS', 'h2d_bytes_per_step': m['h2d'], 'd2h_bytes_per_step': m['d2h'],
+                    'pairs_per_s': pairs_all * args.steps / e2e_s,
+                    'note': 'bsq_align_batch from pinned host arrays: plan + H2D + fill + traceback + pack + D2H'},
+            'gpu_launches': int(launches),
+            'roofline': roofline,
+            'parity_spotcheck': {'status_ok_fraction': m['ok_frac']},
+        }
+
+    # secondary workloads (rank 0, single GPU): f64 path and the banded kernels
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = {}
+        for k2 in ('c2_logodds', 'c3_int', 'c3_logodds'):
+            n2 = WORKLOAD_PAIRS[k2] if k2 != 'c2_logodds' else min(npairs, 250000)
+            try:
+                w2 = bw.make(k2, n2, seed=3)
+                m2 = measure(eng, w2, max(2, args.steps // 2), 3, local, do_e2e=True)
+                st2 = max(2, args.steps // 2)
+                opc2 = ops_per_cell(w2['go'])
+                which2 = 'IADD' if m2['dtype'] == 'i32' else 'DADD'
+                pk = roofline['pipe_rates_gops'].get(which2) if isinstance(roofline['pipe_rates_gops'], dict) else None
+                ach = m2['cells'] * st2 * opc2 / (m2['fill_ms'] * 1e-3) / 1e9
+                extras[k2] = {'workload': w2['desc'], 'dtype': m2['dtype'],
+                              'gcups': m2['cells'] * st2 / (m2['resident_ms'] * 1e-3) / 1e9,
+                              'fill_only_gcups': m2['cells'] * st2 / (m2['fill_ms'] * 1e-3) / 1e9,
+                              'e2e_gcups': m2['cells'] * st2 / m2['e2e_s'] / 1e9,
+                              'roofline_frac': ach / pk if pk else None, 'ops_per_cell': opc2,
+                              'status_ok_fraction': m2['ok_frac'], 'chunks': m2['chunks']}
+            except Exception as e:
+                extras[k2] = {'error': str(e)}
+        line['other_workloads'] = extras
+
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            per_core = 300 if kind.startswith('c2') else 1
+            line['cpu_baseline'] = {k: v for k, v in cpu_reference_run(w, per_core).items()
+                                    if k in ('value', 'unit', 'cores', 'kind', 'sample', 'pairs_per_s')}
+        except Exception as e:
+            line['cpu_baseline'] = {'error': str(e)}
+    if rank == 0:
+        print(json.dumps(line))
+    eng.close()
+    if _dist is not None:
+        _dist.barrier()
+        _dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

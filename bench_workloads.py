@@ -1,0 +1,113 @@
+"""Synthetic workloads of BASELINE.json's configs:
+Alphabet('ACGT'), uniform random origin (rand_seq), mutant with
+MutationProcess.mutate semantics, numpy Generator(PCG64(seed)).  Shared by
+bench.py and the GPU parity tests."""
+import numpy as np
+
+from biseqt_b200 import stochastics as st
+from biseqt_b200 import band
+
+STD_MODE, BANDED_MODE = 0, 1
+LOCAL, GLOBAL = 1, 0
+B_GLOBAL, B_LOCAL, B_OVERLAP = 0, 1, 2
+
+
+def _pack_rows(o_rows, o_lens, m_rows, m_lens):
+    """[origin_i | mutant_i] back to back in one uint8 array + offsets."""
+    N = len(o_lens)
+    o_lens = np.asarray(o_lens, dtype=np.int64)
+    m_lens = np.asarray(m_lens, dtype=np.int64)
+    tot = o_lens + m_lens
+    base = np.zeros(N + 1, dtype=np.int64)
+    np.cumsum(tot, out=base[1:])
+    codes = np.zeros(int(base[-1]) + 16, dtype=np.uint8)
+    o_off = base[:-1].copy()
+    m_off = o_off + o_lens
+    if N and (o_lens == o_lens[0]).all() and (m_lens == m_lens[0]).all():
+        no, nm = int(o_lens[0]), int(m_lens[0])
+        view = codes[:N * (no + nm)].reshape(N, no + nm)
+        view[:, :no] = o_rows[:, :no]
+        view[:, no:] = m_rows[:, :nm]
+    else:
+        for i in range(N):
+            codes[o_off[i]:o_off[i] + o_lens[i]] = o_rows[i][:o_lens[i]]
+            codes[m_off[i]:m_off[i] + m_lens[i]] = m_rows[i][:m_lens[i]]
+    return codes, o_off, o_lens.astype(np.int32), m_off, m_lens.astype(np.int32)
+
+
+def int_scores(match, mismatch, L=4):
+    return np.where(np.eye(L, dtype=bool), float(match), float(mismatch))
+
+
+def make(kind, npairs, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    L = 4
+    if kind in ('c2_int', 'c2_logodds'):
+        # configs[1]: 150 bp read pairs, STD LOCAL, affine gaps
+        n = 150
+        o = st.rand_seqs(rng, npairs, n, L)
+        mut, mlen = st.mutate_batch(rng, o, L, 0.02, 0.005, 0.01)
+        m = np.empty((npairs, n), dtype=np.uint8)
+        pad = st.rand_seqs(rng, npairs, n, L)
+        w = min(mut.shape[1], n)
+        m[:, :w] = mut[:, :w]
+        if w < n:
+            m[:, w:] = pad[:, w:]
+        short = np.arange(n)[None, :] >= np.minimum(mlen, n)[:, None]   # trimmed / padded to 150
+        m[short] = pad[short]
+        codes, o_off, o_len, m_off, m_len = _pack_rows(o, np.full(npairs, n), m, np.full(npairs, n))
+        if kind == 'c2_int':   # IgBlast-like, experiments/blot_ig_genotyping.py:351-355
+            S, go, ge = int_scores(1, -3), -5.0, -2.0
+        else:
+            S, go, ge = st.log_odds_scores(L, 0.05, 0.05, 0.1)
+        return dict(kind=kind, mode=STD_MODE, type=LOCAL, subst=S, go=go, ge=ge, codes=codes,
+                    o_off=o_off, o_len=o_len, m_off=m_off, m_len=m_len,
+                    desc='%d pairs 150x150 bp, STD LOCAL, %s' % (npairs, 'int +1/-3 go-5 ge-2' if kind == 'c2_int' else 'log-odds'))
+    if kind in ('c3_int', 'c3_logodds', 'c4_int'):
+        # configs[2] / [3]: long noisy reads, banded overlap alignment
+        if kind == 'c4_int':
+            n, maxoff, gmax, sens = 50000, 25000, 0.15, 0.99
+        else:
+            n, maxoff = 10000, 5000
+        chunk = st.rand_seqs(rng, npairs, n + maxoff, L)
+        off = rng.integers(0, maxoff + 1, size=npairs)
+        o = chunk[:, :n]
+        src = np.stack([chunk[i, off[i]:off[i] + n] for i in range(npairs)])
+        mut, mlen = st.mutate_batch(rng, src, L, 0.03, 0.06, 0.12)
+        codes, o_off, o_len, m_off, m_len = _pack_rows(o, np.full(npairs, n), mut, mlen)
+        if kind == 'c4_int':
+            K = band.expected_overlap_len(n, mlen, off, gmax)
+            r = band.band_radii(K, gmax, sens)
+        else:
+            r = np.full(npairs, 64)
+        dmin = np.maximum(off - r, -mlen).astype(np.int32)
+        dmax = np.minimum(off + r, n).astype(np.int32)
+        if kind == 'c3_logodds':
+            S, go, ge = st.log_odds_scores(L, 0.03, 0.06, 0.12)
+        else:
+            S, go, ge = int_scores(2, -3), 0.0, -2.0
+        return dict(kind=kind, mode=BANDED_MODE, type=B_OVERLAP, subst=S, go=go, ge=ge, codes=codes,
+                    o_off=o_off, o_len=o_len, m_off=m_off, m_len=m_len, dmin=dmin, dmax=dmax,
+                    desc='%d pairs ~%d bp, B_OVERLAP, radius %s' % (npairs, n, '64' if kind != 'c4_int' else 'band_radius(K,.15,.99)~%d' % int(np.median(r))))
+    if kind == 'c1':
+        # configs[0]: one 1 kb x 1 kb STD GLOBAL pair, log-odds scores (go_score = 0)
+        n = 1000
+        o = st.rand_seqs(rng, 1, n, L)
+        mut, mlen = st.mutate_batch(rng, o, L, 0.1, 0.1, 0.1)
+        codes, o_off, o_len, m_off, m_len = _pack_rows(o, [n], mut, mlen)
+        S, go, ge = st.log_odds_scores(L, 0.1, 0.1, 0.1)
+        return dict(kind=kind, mode=STD_MODE, type=GLOBAL, subst=S, go=go, ge=ge, codes=codes,
+                    o_off=o_off, o_len=o_len, m_off=m_off, m_len=m_len, desc='1 pair 1 kb x ~1 kb STD GLOBAL log-odds')
+    raise ValueError(kind)
+
+
+def count_cells(w):
+    """DP cells the reference would fill (pw.c:59-61), vectorised closed form."""
+    n = w['o_len'].astype(np.int64)
+    m = w['m_len'].astype(np.int64)
+    if w['mode'] == STD_MODE:
+        return int(((n + 1) * (m + 1)).sum())
+    from biseqt_b200 import _ffi
+    lib = _ffi.load()
+    return int(sum(lib.bsq_count_cells(1, int(n[i]), int(m[i]), int(w['dmin'][i]), int(w['dmax'][i]))
+                   for i in range(len(n))))

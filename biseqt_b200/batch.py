@@ -184,6 +184,36 @@ class Engine(object):
         cap = int(o_len.astype(np.int64).sum() + m_len.astype(np.int64).sum())
         return SolvedBatch(self, hb[0], score, end_x, end_y, status, cap)
 
+    def upload(self, codes, o_off, o_len, m_off, m_len, mode, type, subst, go, ge,
+               dmin=None, dmax=None, dtype=DTYPE_AUTO, keep_tables=False, max_new_mins=-1):
+        """Plan + H2D once (``bsq_batch_upload``); returns a :class:`ResidentBatch`
+        whose ``run()`` executes with inputs and outputs resident in HBM."""
+        codes = _c(codes, np.uint8)
+        o_off, m_off = _c(o_off, np.int64), _c(m_off, np.int64)
+        o_len, m_len = _c(o_len, np.int32), _c(m_len, np.int32)
+        dmin, dmax = _c(dmin, np.int32), _c(dmax, np.int32)
+        N = len(o_len)
+        prm, S = self._params(mode, type, subst, go, ge, dtype, max_new_mins)
+        hb = ffi.new('bsq_batch**')
+        rc = self.lib.bsq_batch_upload(
+            self.ctx, prm, N, _ptr(codes, 'uint8_t*'), len(codes),
+            _ptr(o_off, 'int64_t*'), _ptr(o_len, 'int32_t*'),
+            _ptr(m_off, 'int64_t*'), _ptr(m_len, 'int32_t*'),
+            _ptr(dmin, 'int32_t*'), _ptr(dmax, 'int32_t*'), int(bool(keep_tables)), hb)
+        if rc != 0:
+            raise BsqError('bsq_batch_upload failed (%d): %s' % (rc, self._err()))
+        cap = int(o_len.astype(np.int64).sum() + m_len.astype(np.int64).sum())
+        return ResidentBatch(self, hb[0], N, cap)
+
+    def microbench(self, which):
+        """Measured issue rate (thread-ops/s, whole GPU) of one pipe; ``which`` is a
+        BSQ_MB_* name such as ``'DADD'``."""
+        out = ffi.new('double*')
+        rc = self.lib.bsq_microbench(self.ctx, CONST['BSQ_MB_' + which], out)
+        if rc != 0:
+            raise BsqError('bsq_microbench failed (%d): %s' % (rc, self._err()))
+        return out[0]
+
     def table_scores(self, origin, mutant, type, subst, go, ge):
         """H of every STD cell, (n+1) x (m+1) (``bsq_table_scores``)."""
         o, t = _c(origin, np.uint8), _c(mutant, np.uint8)
@@ -226,6 +256,44 @@ class SolvedBatch(object):
             raise BsqError('bsq_traceback_batch failed (%d): %s' % (rc, self.engine._err()))
         return BatchResult(self.score, self.end_x, self.end_y, start_x, start_y, status,
                            tx_off, tx_buf)
+
+    def release(self):
+        if self.handle is not None:
+            self.engine.lib.bsq_release(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class ResidentBatch(object):
+    """Inputs uploaded once; ``run()`` = fill + traceback + packing on the device."""
+
+    def __init__(self, engine, handle, n, cap):
+        self.engine, self.handle, self.n, self._cap = engine, handle, n, cap
+
+    def run(self, traceback=True):
+        rc = self.engine.lib.bsq_batch_run(self.handle, int(bool(traceback)))
+        if rc != 0:
+            raise BsqError('bsq_batch_run failed (%d): %s' % (rc, self.engine._err()))
+        return self.engine.timing()
+
+    def fetch(self, transcripts=True):
+        N = self.n
+        score = np.empty(N, np.float64)
+        ints = [np.empty(N, np.int32) for _ in range(5)]
+        tx_off = np.empty(N + 1, np.int64) if transcripts else None
+        tx_buf = np.empty(max(self._cap, 1), np.uint8) if transcripts else None
+        total = ffi.new('int64_t*')
+        rc = self.engine.lib.bsq_batch_fetch(
+            self.handle, _ptr(score, 'double*'), *[_ptr(a, 'int32_t*') for a in ints],
+            _ptr(tx_off, 'int64_t*'), _ptr(tx_buf, 'char*'), self._cap, total)
+        if rc != 0:
+            raise BsqError('bsq_batch_fetch failed (%d): %s' % (rc, self.engine._err()))
+        return BatchResult(score, ints[0], ints[1], ints[2], ints[3], ints[4], tx_off, tx_buf)
 
     def release(self):
         if self.handle is not None:

@@ -14,6 +14,8 @@
 #include "bsq_post.cuh"
 #include "bsq_launch.h"
 
+int bsq_microbench_impl(int sms, cudaStream_t st, int which, double* out, std::string* err);
+
 namespace {
 
 thread_local std::string g_err;
@@ -108,8 +110,11 @@ struct bsq_ctx {
 struct bsq_batch {
   bsq_ctx* ctx = nullptr;
   Plan plan;
-  BufSet bufs;
-  bool have_codes = false;
+  BufSet bufs;          // used when own_bufs
+  BufSet* B = nullptr;  // the buffers in use (own or the context's cached set)
+  bool own_bufs = false;
+  bool single_chunk = false;  // all pointer tables resident at once
+  bool filled = false, traced = false;
 };
 
 namespace {
@@ -387,7 +392,7 @@ int64_t arena_budget_words(bsq_ctx* ctx, int64_t other_bytes) {
   fr += ctx->bufs.ptr.cap;  // our own cached arena counts as available
   double budget = (double)fr * 0.85 - (double)other_bytes;
   if (ctx->arena_cap_bytes && budget > (double)ctx->arena_cap_bytes) budget = (double)ctx->arena_cap_bytes;
-  if (budget < (double)(1 << 20)) budget = (double)(1 << 20);
+  if (budget < (double)(1 << 16)) budget = (double)(1 << 16);
   return (int64_t)(budget / 4.0);
 }
 
@@ -497,9 +502,8 @@ int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci) {
   return BSQ_SUCCESS;
 }
 
-// scan txlen (original order) -> txoff, pack slots -> packed, D2H
-int pack_and_fetch_transcripts(bsq_ctx* ctx, BufSet& B, const Plan& P, int64_t* tx_off, char* tx_buf,
-                               int64_t tx_cap, int64_t* tx_total) {
+// scan txlen (original order) -> txoff, pack slots -> packed; all on device
+int pack_transcripts(bsq_ctx* ctx, BufSet& B, const Plan& P) {
   const int64_t N = P.N, E = (int64_t)P.pairs.size();
   const int ntiles = (int)((N + BSQ_SCAN_TILE - 1) / BSQ_SCAN_TILE);
   if (!B.txoff.ensure(8 * (size_t)(N + 1)) || !B.tiles.ensure(8 * (size_t)std::max(ntiles, 1)) ||
@@ -519,6 +523,13 @@ int pack_and_fetch_transcripts(bsq_ctx* ctx, BufSet& B, const Plan& P, int64_t* 
     ctx->tm.fill_launches++;
   }
   BSQ_CK(ctx, cudaGetLastError());
+  return BSQ_SUCCESS;
+}
+
+int fetch_transcripts(bsq_ctx* ctx, BufSet& B, const Plan& P, int64_t* tx_off, char* tx_buf,
+                      int64_t tx_cap, int64_t* tx_total) {
+  const int64_t N = P.N;
+  cudaStream_t st = ctx->st;
   long long total = 0;
   BSQ_CK(ctx, cudaMemcpyAsync(&total, B.total.p, 8, cudaMemcpyDeviceToHost, st));
   BSQ_CK(ctx, cudaMemcpyAsync(tx_off, B.txoff.p, 8 * (size_t)N, cudaMemcpyDeviceToHost, st));
@@ -529,6 +540,7 @@ int pack_and_fetch_transcripts(bsq_ctx* ctx, BufSet& B, const Plan& P, int64_t* 
   if (total > tx_cap) return fail(ctx, BSQ_ERR_CAPACITY, "tx_buf too small for the batch's transcripts");
   if (total > 0) {
     BSQ_CK(ctx, cudaMemcpyAsync(tx_buf, B.packed.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+    BSQ_CK(ctx, cudaStreamSynchronize(st));
     ctx->tm.d2h_bytes += total;
   }
   return BSQ_SUCCESS;
@@ -656,66 +668,98 @@ int bsq_partition_pairs(int32_t mode, int64_t npairs, const int32_t* o_len, cons
   return BSQ_SUCCESS;
 }
 
-static int run_one_shot(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, const uint8_t* codes,
-                        int64_t ncodes, const int64_t* o_off, const int32_t* o_len, const int64_t* m_off,
-                        const int32_t* m_len, const int32_t* dmin, const int32_t* dmax, double* score,
-                        int32_t* end_x, int32_t* end_y, int32_t* start_x, int32_t* start_y,
-                        int32_t* status, int64_t* tx_off, char* tx_buf, int64_t tx_cap, int64_t* tx_total) {
-  if (!ctx) return BSQ_ERR_ARG;
-  ctx->err.clear();
+static int check_inputs(bsq_ctx* ctx, int64_t npairs, const uint8_t* codes, const int64_t* o_off,
+                        const int32_t* o_len, const int64_t* m_off, const int32_t* m_len) {
   if (npairs < 0 || npairs >= ((int64_t)1 << 31)) return fail(ctx, BSQ_ERR_ARG, "npairs out of range");
   if (npairs > 0 && (!codes || !o_off || !o_len || !m_off || !m_len)) return fail(ctx, BSQ_ERR_ARG, "NULL input array");
-  if (!score || !status) return fail(ctx, BSQ_ERR_ARG, "score/status must not be NULL");
-  const bool want_tx = (tx_off != nullptr && tx_buf != nullptr);
-  const bool want_trace = want_tx || start_x || start_y;
-  BSQ_CK(ctx, cudaSetDevice(ctx->device));
-  memset(&ctx->tm, 0, sizeof ctx->tm);
-  if (tx_total) *tx_total = 0;
-  if (npairs == 0) { if (tx_off) tx_off[0] = 0; return BSQ_SUCCESS; }
+  return BSQ_SUCCESS;
+}
 
-  Plan P;
+// plan + H2D.  own_bufs: the batch gets its own HBM buffers (two-phase / resident
+// use); otherwise the context's cached buffers are borrowed (one-shot).
+static int batch_upload(bsq_ctx* ctx, bsq_batch* b, bool own_bufs, bool single_chunk, const bsq_params* params,
+                        int64_t npairs, const uint8_t* codes, int64_t ncodes, const int64_t* o_off,
+                        const int32_t* o_len, const int64_t* m_off, const int32_t* m_len,
+                        const int32_t* dmin, const int32_t* dmax) {
+  b->ctx = ctx;
+  b->own_bufs = own_bufs;
+  b->B = own_bufs ? &b->bufs : &ctx->bufs;
+  b->plan.N = npairs;
+  if (npairs == 0) return BSQ_SUCCESS;
   int64_t slot_guess = 0;
   for (int64_t i = 0; i < npairs; i++) slot_guess += (int64_t)o_len[i] + m_len[i];
   const int64_t other = ncodes + 2 * slot_guess + npairs * (int64_t)(sizeof(BsqPair) + 48) + (64 << 20);
   const int64_t arena_words = arena_budget_words(ctx, other);
-  int rc = make_plan(ctx, P, params, npairs, ncodes, o_off, o_len, m_off, m_len, dmin, dmax, arena_words, false);
+  int rc = make_plan(ctx, b->plan, params, npairs, ncodes, o_off, o_len, m_off, m_len, dmin, dmax, arena_words, single_chunk);
   if (rc != BSQ_SUCCESS) return rc;
-  BufSet& B = ctx->bufs;
+  b->single_chunk = single_chunk;
+  return stage_inputs(ctx, *b->B, b->plan, codes, ncodes, single_chunk);
+}
+
+// fill (+ traceback + pack) entirely on the device; returns after the stream drained
+static int batch_run(bsq_batch* b, bool do_fill, bool do_trace) {
+  bsq_ctx* ctx = b->ctx;
+  Plan& P = b->plan;
+  BufSet& B = *b->B;
+  if (P.N == 0) return BSQ_SUCCESS;
+  if (!do_fill && !b->single_chunk)
+    return fail(ctx, BSQ_ERR_ARG, "traceback-only run needs resident tables (two-phase batch)");
   cudaEvent_t t0 = get_event(ctx, 0), t1 = get_event(ctx, 1);
   size_t evi = 2;
-  BSQ_CK(ctx, cudaEventRecord(t0, ctx->st));
-  rc = stage_inputs(ctx, B, P, codes, ncodes, false);
-  if (rc != BSQ_SUCCESS) return rc;
-  if (want_trace && !B.slots.ensure((size_t)std::max<int64_t>(P.slot_bytes, 1)))
+  int rc = BSQ_SUCCESS;
+  if (do_trace && !B.slots.ensure((size_t)std::max<int64_t>(P.slot_bytes, 1)))
     return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (transcript slots)");
+  BSQ_CK(ctx, cudaEventRecord(t0, ctx->st));
+  if (do_fill) BSQ_CK(ctx, cudaMemsetAsync(B.counters.p, 0, 4 * (P.chunks.size() + 1), ctx->st));
+  cudaEvent_t tr0 = nullptr, tr1 = nullptr;
   for (size_t ci = 0; ci < P.chunks.size(); ci++) {
-    rc = launch_fill(ctx, B, P, ci, &evi);
-    if (rc != BSQ_SUCCESS) return rc;
-    if (want_trace) {
+    if (do_fill) {
+      rc = launch_fill(ctx, B, P, ci, &evi);
+      if (rc != BSQ_SUCCESS) return rc;
+    }
+    if (do_trace) {
       rc = launch_trace(ctx, B, P, ci);
       if (rc != BSQ_SUCCESS) return rc;
     }
   }
-  cudaStream_t st = ctx->st;
-  const size_t N = (size_t)npairs;
-  BSQ_CK(ctx, cudaMemcpyAsync(score, B.score.p, 8 * N, cudaMemcpyDeviceToHost, st));
-  if (end_x) BSQ_CK(ctx, cudaMemcpyAsync(end_x, B.ex.p, 4 * N, cudaMemcpyDeviceToHost, st));
-  if (end_y) BSQ_CK(ctx, cudaMemcpyAsync(end_y, B.ey.p, 4 * N, cudaMemcpyDeviceToHost, st));
-  if (want_trace && start_x) BSQ_CK(ctx, cudaMemcpyAsync(start_x, B.sx.p, 4 * N, cudaMemcpyDeviceToHost, st));
-  if (want_trace && start_y) BSQ_CK(ctx, cudaMemcpyAsync(start_y, B.sy.p, 4 * N, cudaMemcpyDeviceToHost, st));
-  BSQ_CK(ctx, cudaMemcpyAsync(status, B.status.p, 4 * N, cudaMemcpyDeviceToHost, st));
-  ctx->tm.d2h_bytes += (int64_t)N * (8 + 4 * (1 + (end_x != 0) + (end_y != 0) + (start_x != 0) + (start_y != 0)));
-  if (want_tx) {
-    rc = pack_and_fetch_transcripts(ctx, B, P, tx_off, tx_buf, tx_cap, tx_total);
-    if (rc != BSQ_SUCCESS && rc != BSQ_ERR_CAPACITY) return rc;
+  if (do_trace) {
+    rc = pack_transcripts(ctx, B, P);
+    if (rc != BSQ_SUCCESS) return rc;
+    b->traced = true;
   }
-  BSQ_CK(ctx, cudaEventRecord(t1, st));
-  BSQ_CK(ctx, cudaStreamSynchronize(st));
+  (void)tr0; (void)tr1;
+  BSQ_CK(ctx, cudaEventRecord(t1, ctx->st));
+  BSQ_CK(ctx, cudaStreamSynchronize(ctx->st));
   collect_timing(ctx, evi, t0, t1);
   ctx->tm.cells = P.cells;
   ctx->tm.dtype = P.dtype;
   ctx->tm.chunks = (int32_t)P.chunks.size();
-  apply_overrides(P, score, end_x, end_y, start_x, start_y, status);
+  if (do_fill) b->filled = true;
+  return BSQ_SUCCESS;
+}
+
+static int batch_fetch(bsq_batch* b, double* score, int32_t* end_x, int32_t* end_y, int32_t* start_x,
+                       int32_t* start_y, int32_t* status, int64_t* tx_off, char* tx_buf, int64_t tx_cap,
+                       int64_t* tx_total) {
+  bsq_ctx* ctx = b->ctx;
+  Plan& P = b->plan;
+  BufSet& B = *b->B;
+  if (tx_total) *tx_total = 0;
+  if (P.N == 0) { if (tx_off) tx_off[0] = 0; return BSQ_SUCCESS; }
+  cudaStream_t st = ctx->st;
+  const size_t N = (size_t)P.N;
+  if (score) BSQ_CK(ctx, cudaMemcpyAsync(score, B.score.p, 8 * N, cudaMemcpyDeviceToHost, st));
+  if (end_x) BSQ_CK(ctx, cudaMemcpyAsync(end_x, B.ex.p, 4 * N, cudaMemcpyDeviceToHost, st));
+  if (end_y) BSQ_CK(ctx, cudaMemcpyAsync(end_y, B.ey.p, 4 * N, cudaMemcpyDeviceToHost, st));
+  if (b->traced && start_x) BSQ_CK(ctx, cudaMemcpyAsync(start_x, B.sx.p, 4 * N, cudaMemcpyDeviceToHost, st));
+  if (b->traced && start_y) BSQ_CK(ctx, cudaMemcpyAsync(start_y, B.sy.p, 4 * N, cudaMemcpyDeviceToHost, st));
+  if (status) BSQ_CK(ctx, cudaMemcpyAsync(status, B.status.p, 4 * N, cudaMemcpyDeviceToHost, st));
+  ctx->tm.d2h_bytes += (int64_t)N * (8 * (score != 0) + 4 * ((status != 0) + (end_x != 0) + (end_y != 0) +
+                                                             (start_x != 0) + (start_y != 0)));
+  int rc = BSQ_SUCCESS;
+  if (b->traced && tx_off && tx_buf) rc = fetch_transcripts(ctx, B, P, tx_off, tx_buf, tx_cap, tx_total);
+  BSQ_CK(ctx, cudaStreamSynchronize(st));
+  apply_overrides(P, score, end_x, end_y, b->traced ? start_x : nullptr, b->traced ? start_y : nullptr, status);
   return rc;
 }
 
@@ -724,8 +768,65 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
                     const int32_t* m_len, const int32_t* dmin, const int32_t* dmax, double* score,
                     int32_t* end_x, int32_t* end_y, int32_t* start_x, int32_t* start_y, int32_t* status,
                     int64_t* tx_off, char* tx_buf, int64_t tx_cap, int64_t* tx_total) {
-  return run_one_shot(ctx, params, npairs, codes, ncodes, o_off, o_len, m_off, m_len, dmin, dmax, score,
-                      end_x, end_y, start_x, start_y, status, tx_off, tx_buf, tx_cap, tx_total);
+  if (!ctx) return BSQ_ERR_ARG;
+  ctx->err.clear();
+  int rc = check_inputs(ctx, npairs, codes, o_off, o_len, m_off, m_len);
+  if (rc != BSQ_SUCCESS) return rc;
+  if (!score || !status) return fail(ctx, BSQ_ERR_ARG, "score/status must not be NULL");
+  BSQ_CK(ctx, cudaSetDevice(ctx->device));
+  memset(&ctx->tm, 0, sizeof ctx->tm);
+  const bool want_trace = (tx_off && tx_buf) || start_x || start_y;
+  bsq_batch b;
+  rc = batch_upload(ctx, &b, false, false, params, npairs, codes, ncodes, o_off, o_len, m_off, m_len, dmin, dmax);
+  if (rc == BSQ_SUCCESS) rc = batch_run(&b, true, want_trace);
+  const bsq_timing run_tm = ctx->tm;
+  if (rc == BSQ_SUCCESS) rc = batch_fetch(&b, score, end_x, end_y, start_x, start_y, status, tx_off, tx_buf, tx_cap, tx_total);
+  (void)run_tm;
+  if (rc != BSQ_SUCCESS) cudaStreamSynchronize(ctx->st);
+  return rc;
+}
+
+int bsq_batch_upload(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, const uint8_t* codes,
+                     int64_t ncodes, const int64_t* o_off, const int32_t* o_len, const int64_t* m_off,
+                     const int32_t* m_len, const int32_t* dmin, const int32_t* dmax, int32_t keep_tables,
+                     bsq_batch** batch) {
+  if (!ctx) return BSQ_ERR_ARG;
+  ctx->err.clear();
+  if (!batch) return fail(ctx, BSQ_ERR_ARG, "batch out-pointer is NULL");
+  *batch = nullptr;
+  int rc = check_inputs(ctx, npairs, codes, o_off, o_len, m_off, m_len);
+  if (rc != BSQ_SUCCESS) return rc;
+  BSQ_CK(ctx, cudaSetDevice(ctx->device));
+  memset(&ctx->tm, 0, sizeof ctx->tm);
+  bsq_batch* b = new bsq_batch();
+  rc = batch_upload(ctx, b, true, keep_tables != 0, params, npairs, codes, ncodes, o_off, o_len, m_off, m_len, dmin, dmax);
+  if (rc == BSQ_SUCCESS) {
+    cudaError_t e = cudaStreamSynchronize(ctx->st);
+    if (e != cudaSuccess) { ctx->err = std::string("upload: ") + cudaGetErrorString(e); rc = BSQ_ERR_CUDA; }
+  }
+  if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(ctx->st); b->bufs.release(); delete b; return rc; }
+  *batch = b;
+  return BSQ_SUCCESS;
+}
+
+int bsq_batch_run(bsq_batch* b, int32_t with_traceback) {
+  if (!b || !b->ctx) return BSQ_ERR_ARG;
+  b->ctx->err.clear();
+  BSQ_CK(b->ctx, cudaSetDevice(b->ctx->device));
+  const int64_t h2d = b->ctx->tm.h2d_bytes;
+  memset(&b->ctx->tm, 0, sizeof b->ctx->tm);
+  b->ctx->tm.h2d_bytes = h2d;
+  return batch_run(b, true, with_traceback != 0);
+}
+
+int bsq_batch_fetch(bsq_batch* b, double* score, int32_t* end_x, int32_t* end_y, int32_t* start_x,
+                    int32_t* start_y, int32_t* status, int64_t* tx_off, char* tx_buf, int64_t tx_cap,
+                    int64_t* tx_total) {
+  if (!b || !b->ctx) return BSQ_ERR_ARG;
+  b->ctx->err.clear();
+  if (!b->filled) return fail(b->ctx, BSQ_ERR_ARG, "bsq_batch_fetch before bsq_batch_run");
+  BSQ_CK(b->ctx, cudaSetDevice(b->ctx->device));
+  return batch_fetch(b, score, end_x, end_y, start_x, start_y, status, tx_off, tx_buf, tx_cap, tx_total);
 }
 
 int bsq_solve_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, const uint8_t* codes,
@@ -733,48 +834,13 @@ int bsq_solve_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
                     const int32_t* m_len, const int32_t* dmin, const int32_t* dmax, double* score,
                     int32_t* end_x, int32_t* end_y, int32_t* status, bsq_batch** batch) {
   if (!ctx) return BSQ_ERR_ARG;
-  ctx->err.clear();
-  if (!batch) return fail(ctx, BSQ_ERR_ARG, "batch out-pointer is NULL");
-  *batch = nullptr;
-  if (npairs < 0 || npairs >= ((int64_t)1 << 31)) return fail(ctx, BSQ_ERR_ARG, "npairs out of range");
-  if (npairs > 0 && (!codes || !o_off || !o_len || !m_off || !m_len)) return fail(ctx, BSQ_ERR_ARG, "NULL input array");
   if (!score || !status) return fail(ctx, BSQ_ERR_ARG, "score/status must not be NULL");
-  BSQ_CK(ctx, cudaSetDevice(ctx->device));
-  memset(&ctx->tm, 0, sizeof ctx->tm);
-  bsq_batch* b = new bsq_batch();
-  b->ctx = ctx;
-  if (npairs == 0) { *batch = b; return BSQ_SUCCESS; }
-  int64_t slot_guess = 0;
-  for (int64_t i = 0; i < npairs; i++) slot_guess += (int64_t)o_len[i] + m_len[i];
-  const int64_t other = ncodes + 2 * slot_guess + npairs * (int64_t)(sizeof(BsqPair) + 48) + (64 << 20);
-  const int64_t arena_words = arena_budget_words(ctx, other);
-  int rc = make_plan(ctx, b->plan, params, npairs, ncodes, o_off, o_len, m_off, m_len, dmin, dmax, arena_words, true);
-  if (rc != BSQ_SUCCESS) { delete b; return rc; }
-  cudaEvent_t t0 = get_event(ctx, 0), t1 = get_event(ctx, 1);
-  size_t evi = 2;
-  cudaEventRecord(t0, ctx->st);
-  rc = stage_inputs(ctx, b->bufs, b->plan, codes, ncodes, true);
-  for (size_t ci = 0; rc == BSQ_SUCCESS && ci < b->plan.chunks.size(); ci++) rc = launch_fill(ctx, b->bufs, b->plan, ci, &evi);
-  if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(ctx->st); b->bufs.release(); delete b; return rc; }
-  cudaStream_t st = ctx->st;
-  const size_t N = (size_t)npairs;
-  cudaMemcpyAsync(score, b->bufs.score.p, 8 * N, cudaMemcpyDeviceToHost, st);
-  if (end_x) cudaMemcpyAsync(end_x, b->bufs.ex.p, 4 * N, cudaMemcpyDeviceToHost, st);
-  if (end_y) cudaMemcpyAsync(end_y, b->bufs.ey.p, 4 * N, cudaMemcpyDeviceToHost, st);
-  cudaMemcpyAsync(status, b->bufs.status.p, 4 * N, cudaMemcpyDeviceToHost, st);
-  cudaEventRecord(t1, st);
-  cudaError_t e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) {
-    ctx->err = std::string("solve: ") + cudaGetErrorString(e);
-    b->bufs.release(); delete b; return BSQ_ERR_CUDA;
-  }
-  collect_timing(ctx, evi, t0, t1);
-  ctx->tm.cells = b->plan.cells;
-  ctx->tm.dtype = b->plan.dtype;
-  ctx->tm.chunks = (int32_t)b->plan.chunks.size();
-  apply_overrides(b->plan, score, end_x, end_y, nullptr, nullptr, status);
-  *batch = b;
-  return BSQ_SUCCESS;
+  int rc = bsq_batch_upload(ctx, params, npairs, codes, ncodes, o_off, o_len, m_off, m_len, dmin, dmax, 1, batch);
+  if (rc != BSQ_SUCCESS) return rc;
+  rc = batch_run(*batch, true, false);
+  if (rc == BSQ_SUCCESS) rc = batch_fetch(*batch, score, end_x, end_y, nullptr, nullptr, status, nullptr, nullptr, 0, nullptr);
+  if (rc != BSQ_SUCCESS) { bsq_release(*batch); *batch = nullptr; }
+  return rc;
 }
 
 int bsq_traceback_batch(bsq_batch* b, int32_t* start_x, int32_t* start_y, int32_t* status, int64_t* tx_off,
@@ -782,31 +848,27 @@ int bsq_traceback_batch(bsq_batch* b, int32_t* start_x, int32_t* start_y, int32_
   if (!b || !b->ctx) return BSQ_ERR_ARG;
   bsq_ctx* ctx = b->ctx;
   ctx->err.clear();
-  if (tx_total) *tx_total = 0;
-  const int64_t N = b->plan.N;
-  if (N == 0) { if (tx_off) tx_off[0] = 0; return BSQ_SUCCESS; }
   if (!tx_off || !tx_buf) return fail(ctx, BSQ_ERR_ARG, "tx_off/tx_buf must not be NULL");
+  if (!b->filled && b->plan.N > 0) return fail(ctx, BSQ_ERR_ARG, "bsq_traceback_batch before solve");
   BSQ_CK(ctx, cudaSetDevice(ctx->device));
-  if (!b->bufs.slots.ensure((size_t)std::max<int64_t>(b->plan.slot_bytes, 1)))
-    return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (transcript slots)");
   int rc = BSQ_SUCCESS;
-  for (size_t ci = 0; rc == BSQ_SUCCESS && ci < b->plan.chunks.size(); ci++) rc = launch_trace(ctx, b->bufs, b->plan, ci);
+  if (!b->traced) rc = batch_run(b, false, true);
   if (rc != BSQ_SUCCESS) return rc;
-  cudaStream_t st = ctx->st;
-  if (start_x) BSQ_CK(ctx, cudaMemcpyAsync(start_x, b->bufs.sx.p, 4 * (size_t)N, cudaMemcpyDeviceToHost, st));
-  if (start_y) BSQ_CK(ctx, cudaMemcpyAsync(start_y, b->bufs.sy.p, 4 * (size_t)N, cudaMemcpyDeviceToHost, st));
-  if (status) BSQ_CK(ctx, cudaMemcpyAsync(status, b->bufs.status.p, 4 * (size_t)N, cudaMemcpyDeviceToHost, st));
-  rc = pack_and_fetch_transcripts(ctx, b->bufs, b->plan, tx_off, tx_buf, tx_cap, tx_total);
-  BSQ_CK(ctx, cudaStreamSynchronize(st));
-  apply_overrides(b->plan, nullptr, nullptr, nullptr, start_x, start_y, status);
-  return rc;
+  return batch_fetch(b, nullptr, nullptr, nullptr, start_x, start_y, status, tx_off, tx_buf, tx_cap, tx_total);
 }
 
 void bsq_release(bsq_batch* b) {
   if (!b) return;
   if (b->ctx) { cudaSetDevice(b->ctx->device); cudaStreamSynchronize(b->ctx->st); }
-  b->bufs.release();
+  if (b->own_bufs) b->bufs.release();
   delete b;
+}
+
+int bsq_microbench(bsq_ctx* ctx, int32_t which, double* ops_per_sec) {
+  if (!ctx || !ops_per_sec) return BSQ_ERR_ARG;
+  ctx->err.clear();
+  BSQ_CK(ctx, cudaSetDevice(ctx->device));
+  return bsq_microbench_impl(ctx->sms, ctx->st, which, ops_per_sec, &ctx->err);
 }
 
 int bsq_table_scores(bsq_ctx* ctx, const bsq_params* params, const uint8_t* origin, int32_t n,

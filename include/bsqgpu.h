@@ -160,6 +160,27 @@ int bsq_traceback_batch(bsq_batch* batch, int32_t* start_x, int32_t* start_y,
                         int64_t tx_cap, int64_t* tx_total);
 void bsq_release(bsq_batch* batch);
 
+/*
+ * Device-resident form of the same path, for pipelines and for measurement:
+ * bsq_batch_upload plans the batch and copies the inputs to HBM once;
+ * bsq_batch_run executes fill (+ traceback + transcript packing when
+ * with_traceback != 0) with every input and output resident in HBM and returns
+ * when the device is done (bsq_get_timing then holds the CUDA-event times);
+ * bsq_batch_fetch copies the results to host buffers (any pointer may be NULL).
+ * keep_tables != 0 keeps all pointer tables resident (needed for a later
+ * bsq_traceback_batch); 0 lets the scheduler reuse one arena chunk by chunk.
+ */
+int bsq_batch_upload(bsq_ctx* ctx, const bsq_params* params, int64_t npairs,
+                     const uint8_t* codes, int64_t ncodes,
+                     const int64_t* o_off, const int32_t* o_len,
+                     const int64_t* m_off, const int32_t* m_len,
+                     const int32_t* dmin, const int32_t* dmax,
+                     int32_t keep_tables, bsq_batch** batch);
+int bsq_batch_run(bsq_batch* batch, int32_t with_traceback);
+int bsq_batch_fetch(bsq_batch* batch, double* score, int32_t* end_x, int32_t* end_y,
+                    int32_t* start_x, int32_t* start_y, int32_t* status,
+                    int64_t* tx_off, char* tx_buf, int64_t tx_cap, int64_t* tx_total);
+
 /* Aligner.table_scores() (pw.py:278-285): H of every cell of ONE STD problem,
  * (n+1)*(m+1) doubles row-major. Debug/teaching path, not a hot path. */
 int bsq_table_scores(bsq_ctx* ctx, const bsq_params* params,
@@ -167,6 +188,23 @@ int bsq_table_scores(bsq_ctx* ctx, const bsq_params* params,
                      const uint8_t* mutant, int32_t m, double* out);
 
 int bsq_get_timing(const bsq_ctx* ctx, bsq_timing* out);
+
+/*
+ * Pipe-rate microbenchmarks: the measured denominators of the ALU roofline
+ * (P_pipe = peak issue rate of the score datatype's ALU
+ * op).  *ops_per_sec receives thread-level operations per second for the whole
+ * GPU, measured with CUDA events over a dependent-free instruction stream.
+ */
+#define BSQ_MB_DADD 0      /* add.rn.f64                                   */
+#define BSQ_MB_DMAX 1      /* setp.gt.f64 + selp.f64 (one "max" of doubles) */
+#define BSQ_MB_DSETP 2     /* setp.eq.f64 feeding a predicated integer op   */
+#define BSQ_MB_IADD 3      /* add.s32                                       */
+#define BSQ_MB_VIMAX3 4    /* DPX three-way max (VIMNMX3)                   */
+#define BSQ_MB_VIADDMAX 5  /* DPX add+max (VIADDMNMX)                       */
+#define BSQ_MB_SHFL 6      /* shfl.sync.up.b32                              */
+#define BSQ_MB_LDS64 7     /* ld.shared.b64, conflict free                  */
+#define BSQ_MB_COUNT 8
+int bsq_microbench(bsq_ctx* ctx, int32_t which, double* ops_per_sec);
 
 /* pure host helpers (usable without a GPU) ------------------------------- */
 

@@ -1,0 +1,202 @@
+"""Parity test bodies shared by the CPU-emulator run (-m "not gpu") and the
+real B200 run (-m gpu).  Every function takes an Engine; sizes are passed in."""
+import os
+
+import numpy as np
+
+from biseqt_b200 import batch
+from oracle import lean
+from tests.gen import random_problem, score_family, mutate
+from tests.util import (oracle_one, engine_batch, same_as, check_problems, golden_problem,
+                        golden_expected)
+
+
+def run_golden(eng, golden, limit_random=None, limit_large=None):
+    nr = nl = 0
+    for g in golden:
+        if g['name'].startswith('random-'):
+            nr += 1
+            if limit_random is not None and nr > limit_random:
+                continue
+        if g['name'].startswith('large-'):
+            nl += 1
+            if limit_large is not None and nl > limit_large:
+                continue
+        r = engine_batch(eng, [golden_problem(g)])
+        same_as(golden_expected(g), r, 0, what=g['name'])
+
+
+def run_random_singles(eng, seed, count, max_len=13):
+    rng = np.random.default_rng(seed)
+    check_problems(eng, [random_problem(rng, max_len=max_len) for _ in range(count)])
+
+
+def make_batch(rng, npairs, mode, typ, lo, hi, L=4, family=None, gomode=None, band=None):
+    """npairs problems sharing scores/mode/type, heterogeneous lengths."""
+    S, go, ge = score_family(rng, L, int(rng.integers(0, 4)) if family is None else family,
+                             int(rng.integers(-1, 2)) if gomode is None else gomode)
+    probs = []
+    for _ in range(npairs):
+        n = int(rng.integers(lo, hi + 1))
+        o = rng.integers(0, L, size=n).astype(np.uint8)
+        if rng.random() < 0.7:
+            t, _ = mutate(rng, o, L, subst=0.1, go=0.05, ge=0.3)
+        else:
+            t = rng.integers(0, L, size=int(rng.integers(lo, hi + 1))).astype(np.uint8)
+        m = len(t)
+        dr = None
+        if mode == 1:
+            if band is not None:
+                c = int(rng.integers(-3, 4))
+                dr = (c - band, c + band)
+            else:
+                a, b = sorted(int(v) for v in rng.integers(-m - 2, n + 3, size=2))
+                dr = (a, b)
+            if typ == 0 and rng.random() < 0.8:
+                dr = (min(dr[0], 0, n - m), max(dr[1], 0, n - m))
+        probs.append(dict(origin=o, mutant=t, subst=S, go=go, ge=ge, mode=mode, type=typ,
+                          diag_range=dr, L=L))
+    return probs
+
+
+def check_batch(eng, probs, **kw):
+    r = engine_batch(eng, probs, **kw)
+    for i, pr in enumerate(probs):
+        same_as(oracle_one(pr), r, i, what='pair %d of batch (mode %d type %d)' % (i, pr['mode'], pr['type']))
+    return r
+
+
+def run_batches(eng, seed, npairs, lo, hi):
+    rng = np.random.default_rng(seed)
+    for mode, types in ((0, range(7)), (1, range(3))):
+        for typ in types:
+            check_batch(eng, make_batch(rng, npairs, mode, typ, lo, hi))
+
+
+def run_multipass_std(eng, seed, n_hi=40, widths=(520, 700, 1100)):
+    """Tables wider than the widest single-pass geometry (32x16 columns)."""
+    rng = np.random.default_rng(seed)
+    for w in widths:
+        for typ in (0, 1, 4):
+            S, go, ge = score_family(rng, 4, 1, -1)
+            o = rng.integers(0, 4, size=int(rng.integers(n_hi // 2, n_hi))).astype(np.uint8)
+            t = rng.integers(0, 4, size=w).astype(np.uint8)
+            pos = int(rng.integers(0, w - len(o)))
+            t[pos:pos + len(o)] = o   # plant the origin so local/overlap find something
+            pr = dict(origin=o, mutant=t, subst=S, go=go, ge=ge, mode=0, type=typ, diag_range=None)
+            check_batch(eng, [pr])
+
+
+def run_wide_bands(eng, seed, length=300, radii=(40, 100, 200, 500)):
+    rng = np.random.default_rng(seed)
+    for r in radii:
+        for typ in (0, 1, 2):
+            probs = make_batch(rng, 2, 1, typ, length, length + 20, family=2, gomode=-1, band=r)
+            check_batch(eng, probs)
+
+
+def run_unsupported_band(eng):
+    o = np.zeros(1500, np.uint8)
+    pr = dict(origin=o, mutant=o, subst=np.eye(4), go=0.0, ge=-1.0, mode=1, type=2,
+              diag_range=(-600, 600))
+    r = engine_batch(eng, [pr])
+    assert int(r.status[0]) == batch.UNSUPPORTED
+
+
+def run_dtype_equivalence(eng, seed, npairs=12, lo=5, hi=60):
+    """Integer scores: the I32 fast path and the F64 path give identical results."""
+    rng = np.random.default_rng(seed)
+    for mode, typ in ((0, 0), (0, 1), (0, 4), (1, 0), (1, 1), (1, 2)):
+        for gomode in (-1, 0, 1):
+            probs = make_batch(rng, npairs, mode, typ, lo, hi, family=1, gomode=gomode)
+            a = check_batch(eng, probs, dtype=batch.DTYPE_F64)
+            assert eng.timing()['dtype'] == batch.DTYPE_F64
+            b = check_batch(eng, probs, dtype=batch.DTYPE_AUTO)
+            assert eng.timing()['dtype'] == batch.DTYPE_I32
+            assert np.array_equal(a.status, b.status) and np.array_equal(a.tx_buf[:a.tx_off[-1]], b.tx_buf[:b.tx_off[-1]])
+
+
+def run_two_phase(eng, seed):
+    rng = np.random.default_rng(seed)
+    for mode, typ in ((0, 1), (1, 2)):
+        probs = make_batch(rng, 9, mode, typ, 10, 50)
+        p0 = probs[0]
+        codes, o_off, o_len, m_off, m_len = batch.pack_pairs([(p['origin'], p['mutant']) for p in probs])
+        kw = {}
+        if mode == 1:
+            kw = dict(dmin=[p['diag_range'][0] for p in probs], dmax=[p['diag_range'][1] for p in probs])
+        sb = eng.solve(codes, o_off, o_len, m_off, m_len, mode, typ, p0['subst'], p0['go'], p0['ge'], **kw)
+        for i, pr in enumerate(probs):
+            e = oracle_one(pr)
+            if e['status'] in (0, 2, 4):
+                assert sb.score[i] == e['score'] and (sb.end_x[i], sb.end_y[i]) == tuple(e['end'])
+        r = sb.traceback()
+        for i, pr in enumerate(probs):
+            same_as(oracle_one(pr), r, i, what='two-phase %d' % i)
+        sb.release()
+
+
+def run_resident(eng, seed):
+    """upload once, run twice, fetch: same results as the one-shot call."""
+    rng = np.random.default_rng(seed)
+    for mode, typ in ((0, 1), (1, 2), (1, 0)):
+        probs = make_batch(rng, 11, mode, typ, 10, 60)
+        p0 = probs[0]
+        codes, o_off, o_len, m_off, m_len = batch.pack_pairs([(p['origin'], p['mutant']) for p in probs])
+        kw = {}
+        if mode == 1:
+            kw = dict(dmin=[p['diag_range'][0] for p in probs], dmax=[p['diag_range'][1] for p in probs])
+        rb = eng.upload(codes, o_off, o_len, m_off, m_len, mode, typ, p0['subst'], p0['go'], p0['ge'], **kw)
+        rb.run()
+        t = rb.run()
+        assert t['cells'] == sum(oracle_one(p)['ncells'] for p in probs if oracle_one(p)['status'] != 3)
+        r = rb.fetch()
+        for i, pr in enumerate(probs):
+            same_as(oracle_one(pr), r, i, what='resident %d' % i)
+        rb.release()
+
+
+def run_edge_cases(eng):
+    E = np.zeros(0, np.uint8)
+    A4 = np.array([0, 1, 2, 3, 0, 1], np.uint8)
+    for mode, typ, dr in ((0, 0, None), (0, 1, None), (0, 4, None), (1, 0, (0, 0)), (1, 2, (-2, 2)), (1, 1, (-1, 3))):
+        for o, t in ((E, E), (A4, E), (E, A4), (A4[:1], A4[:1])):
+            pr = dict(origin=o, mutant=t, subst=np.eye(4), go=-1.0, ge=-1.0, mode=mode, type=typ, diag_range=dr)
+            check_batch(eng, [pr])
+    # empty batch
+    r = eng.align(np.zeros(1, np.uint8), np.zeros(0, np.int64), np.zeros(0, np.int32),
+                  np.zeros(0, np.int64), np.zeros(0, np.int32), 0, 0, np.eye(4), 0, 0)
+    assert len(r) == 0
+    # alphabets of 1 and 20 letters
+    rng = np.random.default_rng(3)
+    for L in (1, 20):
+        for mode, typ in ((0, 1), (1, 2)):
+            check_batch(eng, make_batch(rng, 5, mode, typ, 5, 40, L=L))
+
+
+def run_table_scores(eng, seed):
+    rng = np.random.default_rng(seed)
+    for typ in range(7):
+        pr = random_problem(rng, max_len=30, L=4, min_len=3)
+        e = lean.align(pr['origin'], pr['mutant'], pr['subst'], pr['go'], pr['ge'], 0, typ, None, want_table=True)
+        H = eng.table_scores(pr['origin'], pr['mutant'], typ, pr['subst'], pr['go'], pr['ge'])
+        assert np.array_equal(H, e['table'])
+
+
+def run_chunked(make_engine, seed):
+    """Arena cap so small that the batch is cut into several chunks."""
+    os.environ['BSQ_ARENA_CAP_BYTES'] = str(1 << 18)
+    try:
+        eng = make_engine()
+    finally:
+        del os.environ['BSQ_ARENA_CAP_BYTES']
+    try:
+        rng = np.random.default_rng(seed)
+        probs = make_batch(rng, 40, 0, 1, 100, 140, family=1, gomode=-1)
+        check_batch(eng, probs)
+        assert eng.timing()['chunks'] > 1
+        probs = make_batch(rng, 30, 1, 2, 300, 400, family=2, gomode=0, band=30)
+        check_batch(eng, probs)
+        assert eng.timing()['chunks'] > 1
+    finally:
+        eng.close()

@@ -1,0 +1,55 @@
+"""Kernel + scheduler logic on CPU: the product's CUDA sources compiled
+against tests/simt_emu (fiber SIMT emulator) and driven through the real C ABI,
+checked against the oracle.  These are NOT the parity tests proper (those are
+tests/test_gpu_parity.py, -m gpu); they exist so that kernel bugs are found
+without spending GPU minutes."""
+from biseqt_b200 import batch
+from tests import parity_cases as pc
+
+
+def test_emu_golden(emu_engine, golden):
+    pc.run_golden(emu_engine, golden, limit_random=150, limit_large=3)
+
+
+def test_emu_random_singles(emu_engine):
+    pc.run_random_singles(emu_engine, seed=11, count=250)
+
+
+def test_emu_batches(emu_engine):
+    pc.run_batches(emu_engine, seed=21, npairs=12, lo=0, hi=40)
+
+
+def test_emu_multipass_std(emu_engine):
+    pc.run_multipass_std(emu_engine, seed=31, n_hi=24, widths=(520, 1100))
+
+
+def test_emu_wide_bands(emu_engine):
+    pc.run_wide_bands(emu_engine, seed=41, length=120, radii=(40, 100, 300))
+
+
+def test_emu_unsupported_band(emu_engine):
+    pc.run_unsupported_band(emu_engine)
+
+
+def test_emu_dtype_equivalence(emu_engine):
+    pc.run_dtype_equivalence(emu_engine, seed=51, npairs=5, lo=5, hi=30)
+
+
+def test_emu_two_phase(emu_engine):
+    pc.run_two_phase(emu_engine, seed=61)
+
+
+def test_emu_resident(emu_engine):
+    pc.run_resident(emu_engine, seed=65)
+
+
+def test_emu_edge_cases(emu_engine):
+    pc.run_edge_cases(emu_engine)
+
+
+def test_emu_table_scores(emu_engine):
+    pc.run_table_scores(emu_engine, seed=71)
+
+
+def test_emu_chunked(emu_lib):
+    pc.run_chunked(lambda: batch.Engine(0, lib=emu_lib), seed=81)

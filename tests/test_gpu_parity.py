@@ -1,0 +1,146 @@
+"""The parity tests proper: biseqt_b200/libbsqgpu.so on a real B200, through
+the C ABI, against the oracle / golden vectors (bit-exact scores, transcripts,
+start/end) plus size-independent properties at BASELINE.json-like sizes.
+Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+
+from biseqt_b200 import batch
+from oracle import lean
+from tests import parity_cases as pc
+from tests.gen import score_family
+from tests.util import same_as
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gpu_library_is_the_cuda_build(gpu_engine):
+    from biseqt_b200._ffi import ffi
+    v = ffi.string(gpu_engine.lib.bsq_version()).decode()
+    assert 'sm_100a' in v and 'emu' not in v
+
+
+def test_gpu_golden(gpu_engine, golden):
+    pc.run_golden(gpu_engine, golden)
+
+
+def test_gpu_random_singles(gpu_engine):
+    pc.run_random_singles(gpu_engine, seed=11, count=1500)
+    pc.run_random_singles(gpu_engine, seed=12, count=300, max_len=80)
+
+
+def test_gpu_batches(gpu_engine):
+    pc.run_batches(gpu_engine, seed=21, npairs=64, lo=0, hi=40)
+    pc.run_batches(gpu_engine, seed=22, npairs=200, lo=100, hi=400)
+
+
+def test_gpu_multipass_std(gpu_engine):
+    pc.run_multipass_std(gpu_engine, seed=31, n_hi=300, widths=(520, 700, 1100, 2100))
+
+
+def test_gpu_wide_bands(gpu_engine):
+    pc.run_wide_bands(gpu_engine, seed=41, length=1200, radii=(40, 64, 100, 200, 232, 500))
+
+
+def test_gpu_unsupported_band(gpu_engine):
+    pc.run_unsupported_band(gpu_engine)
+
+
+def test_gpu_dtype_equivalence(gpu_engine):
+    pc.run_dtype_equivalence(gpu_engine, seed=51, npairs=40, lo=5, hi=200)
+
+
+def test_gpu_two_phase(gpu_engine):
+    pc.run_two_phase(gpu_engine, seed=61)
+
+
+def test_gpu_resident(gpu_engine):
+    pc.run_resident(gpu_engine, seed=65)
+
+
+def test_gpu_edge_cases(gpu_engine):
+    pc.run_edge_cases(gpu_engine)
+
+
+def test_gpu_table_scores(gpu_engine):
+    pc.run_table_scores(gpu_engine, seed=71)
+
+
+def test_gpu_chunked():
+    pc.run_chunked(lambda: batch.Engine(0), seed=81)
+
+
+def _workload(kind, npairs, seed):
+    import bench_workloads as bw
+    return bw.make(kind, npairs, seed)
+
+
+@pytest.mark.parametrize('kind', ['c2_int', 'c2_logodds', 'c3_int', 'c3_logodds'])
+def test_gpu_bench_shapes_vs_oracle(gpu_engine, kind):
+    """The bench's own workload generators (BASELINE.json configs[1] and [2]) at
+    a size the oracle finishes in seconds, every pair compared."""
+    npairs = 4000 if kind.startswith('c2') else 24
+    w = _workload(kind, npairs, seed=5)
+    r = gpu_engine.align(w['codes'], w['o_off'], w['o_len'], w['m_off'], w['m_len'], w['mode'],
+                         w['type'], w['subst'], w['go'], w['ge'], dmin=w.get('dmin'), dmax=w.get('dmax'))
+    e = lean.align_batch(w['mode'], w['type'], w['subst'], w['go'], w['ge'], w['codes'], w['o_off'],
+                         w['o_len'], w['m_off'], w['m_len'], w.get('dmin'), w.get('dmax'))
+    assert np.array_equal(r.status, e['status'])
+    ok = (e['status'] == 0) | (e['status'] == 4)
+    assert np.array_equal(r.score[ok], e['score'][ok])
+    assert np.array_equal(r.end_x[ok], e['end_x'][ok]) and np.array_equal(r.end_y[ok], e['end_y'][ok])
+    assert np.array_equal(r.start_x[ok], e['start_x'][ok]) and np.array_equal(r.start_y[ok], e['start_y'][ok])
+    assert np.array_equal(r.tx_len, e['tx_len'])
+    etx = lean.transcripts(e)
+    for i in range(npairs):
+        assert r.transcript(i) == etx[i], 'pair %d' % i
+
+
+def _rescore(w, r, i):
+    """Alignment.calculate_score (pw.py:391-428) of pair i's transcript."""
+    tx = r.transcript(i)
+    o = w['codes'][w['o_off'][i]:w['o_off'][i] + w['o_len'][i]]
+    t = w['codes'][w['m_off'][i]:w['m_off'][i] + w['m_len'][i]]
+    x, y, s, prev = int(r.start_x[i]), int(r.start_y[i]), 0.0, ''
+    for op in tx:
+        if op in 'MS':
+            s += w['subst'][o[x]][t[y]]
+            assert (o[x] == t[y]) == (op == 'M')
+            x += 1; y += 1
+        else:
+            s += w['ge'] + (w['go'] if op != prev else 0.0)
+            if op == 'D':
+                x += 1
+            else:
+                y += 1
+        prev = op
+    return s, x, y
+
+
+@pytest.mark.parametrize('kind,npairs', [('c2_int', 200000), ('c2_logodds', 200000), ('c3_int', 2000), ('c4_int', 200)])
+def test_gpu_full_size_properties(gpu_engine, kind, npairs):
+    """At sizes the CPU oracle cannot cover: every transcript re-scores to the
+    reported score, ends at the reported end cell, and determinism across runs."""
+    w = _workload(kind, npairs, seed=9)
+    args = (w['codes'], w['o_off'], w['o_len'], w['m_off'], w['m_len'], w['mode'], w['type'],
+            w['subst'], w['go'], w['ge'])
+    r = gpu_engine.align(*args, dmin=w.get('dmin'), dmax=w.get('dmax'))
+    assert (r.status == 0).mean() > 0.99
+    rng = np.random.default_rng(1)
+    for i in rng.choice(npairs, size=300, replace=False):
+        if r.status[i] != 0:
+            continue
+        s, x, y = _rescore(w, r, int(i))
+        assert (x, y) == (int(r.end_x[i]), int(r.end_y[i]))
+        assert abs(s - r.score[i]) <= 1e-9 * max(1.0, abs(r.score[i]))
+    r2 = gpu_engine.align(*args, dmin=w.get('dmin'), dmax=w.get('dmax'))
+    assert np.array_equal(r.score, r2.score) and np.array_equal(r.tx_off, r2.tx_off)
+    assert np.array_equal(r.tx_buf[:r.tx_off[-1]], r2.tx_buf[:r2.tx_off[-1]])
+
+
+def test_gpu_banded_memory_1e6(gpu_engine):
+    """tests/test_pw.py:95-103 of the reference: two 1e6-long sequences, band (0,0)."""
+    Ln = 1000000
+    codes = np.concatenate([np.zeros(Ln, np.uint8), np.ones(Ln, np.uint8)])
+    r = gpu_engine.align(codes, [0], [Ln], [Ln], [Ln], 1, 0, np.eye(4), 0, 0, dmin=[0], dmax=[0])
+    assert int(r.status[0]) == 0 and r.transcript(0) == 'S' * Ln

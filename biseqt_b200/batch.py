@@ -98,7 +98,6 @@ class Engine(object):
             raise BsqError('bsq_host_alloc(%d) failed' % nbytes)
         p = ffi.gc(p, self.lib.bsq_host_free, size=nbytes)
         arr = np.frombuffer(ffi.buffer(p, max(nbytes, 1)), dtype=dtype, count=int(n))
-        arr._bsq_pin = p if False else None  # numpy keeps the buffer (and so `p`) alive
         return arr
 
     def _params(self, mode, type, subst, go, ge, dtype=DTYPE_AUTO, max_new_mins=-1):

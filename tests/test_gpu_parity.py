@@ -127,7 +127,7 @@ def test_gpu_full_size_properties(gpu_engine, kind, npairs):
     r = gpu_engine.align(*args, dmin=w.get('dmin'), dmax=w.get('dmax'))
     assert (r.status == 0).mean() > 0.99
     rng = np.random.default_rng(1)
-    for i in rng.choice(npairs, size=300, replace=False):
+    for i in rng.choice(npairs, size=min(300, npairs), replace=False):
         if r.status[i] != 0:
             continue
         s, x, y = _rescore(w, r, int(i))

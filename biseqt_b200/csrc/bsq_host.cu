@@ -495,8 +495,21 @@ int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci) {
   T.sy = B.sy.as<int>();
   T.txlen = B.txlen.as<int>();
   T.slots = B.slots.as<char>();
-  const int grid = (int)((ch.count + 127) / 128);
-  BSQ_LAUNCH(bsq_k4_traceback, grid, 128, 0, ctx->st, T);
+  // long pairs: one warp per pair walking shared-memory tiles; short pairs: one
+  // thread per pair (there are enough of them to hide the load latency)
+  const long long avg_path = P.slot_bytes / std::max<long long>((long long)P.pairs.size(), 1);
+  const char* force = getenv("BSQ_TRACE_KERNEL");  // test hook: "thread" / "warp"
+  bool warp_walk = avg_path >= 1024;
+  if (force && force[0] == 't') warp_walk = false;
+  if (force && force[0] == 'w') warp_walk = true;
+  if (warp_walk) {
+    const int grid = (int)((ch.count + BSQ_WALK_WARPS - 1) / BSQ_WALK_WARPS);
+    if (ch.family == 1) BSQ_LAUNCH(bsq_k4_walk<1>, grid, 32 * BSQ_WALK_WARPS, 0, ctx->st, T);
+    else BSQ_LAUNCH(bsq_k4_walk<2>, grid, 32 * BSQ_WALK_WARPS, 0, ctx->st, T);
+  } else {
+    const int grid = (int)((ch.count + 127) / 128);
+    BSQ_LAUNCH(bsq_k4_traceback, grid, 128, 0, ctx->st, T);
+  }
   BSQ_CK(ctx, cudaGetLastError());
   ctx->tm.fill_launches++;
   return BSQ_SUCCESS;

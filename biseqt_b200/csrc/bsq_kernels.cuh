@@ -303,13 +303,29 @@ __global__ void __launch_bounds__(128) bsq_k1_fill(const BsqFillArgs A) {
 // and d from step s-2, so every lane updates C/2 cells per step and only the
 // strip edges cross lanes (one shuffle up on even steps, one down on odd).
 // Pointer layout: [step s - s0][lane][word], C/2 nibbles per lane per step.
+//
+// The sweep runs in three phases.  While some band cell can still lie on a
+// table edge, outside the table, or past the end of its diagonal ("careful"
+// steps) every cell is gated individually.  In between ("interior" steps: every
+// band diagonal has a cell with x >= 1 and y >= 1) nothing is gated, B is
+// either impossible (B_GLOBAL, B_OVERLAP) or always 0 (B_LOCAL), and for DNA-
+// sized alphabets the letters come from two nibble-packed shift registers (the
+// origin window slides one way, the mutant window the other, like a systolic
+// array) so that a cell's substitution score is one shared-memory load indexed
+// by a nibble of their OR.
 //   replaces: dptable_solve's fill loop pw.c:59-110 in (d,a) coordinates
 //   (_pw_internals.c:87-153) + _banded_find_optimal (:364-414)
 // ===========================================================================
+template <int C>
+__device__ __forceinline__ uint32_t bsq_k2_nib(const uint32_t (&pw)[(C / 2 + 7) / 8], int c) {
+  return (pw[(c >> 1) >> 3] >> (4 * ((c >> 1) & 7))) & 0xFu;  // c is a compile-time constant
+}
+
+// careful step: any cell may be off-table, on an edge, or a padding diagonal
 template <class S, int C, bool BLOCAL, int GOS, int Q>
-__device__ __forceinline__ void bsq_k2_step(
+__device__ __forceinline__ void bsq_k2_step_careful(
     int btype, typename S::T (&H)[C], typename S::T (&best)[BLOCAL ? C : 1],
-    int (&besta)[BLOCAL ? C : 1], uint32_t (&pwprev)[(C / 2 + 7) / 8],
+    int (&bests)[BLOCAL ? C : 1], uint32_t (&pwprev)[(C / 2 + 7) / 8],
     typename S::T edgeH, uint32_t edgeNib, const typename S::T* s_sub, int L,
     const uint8_t* oseq, const uint8_t* mseq, int n, int m, int s, int d0, int nreal,
     typename S::T go, typename S::T ge, uint32_t* pout) {
@@ -333,9 +349,9 @@ __device__ __forceinline__ void bsq_k2_step(
     T up, left;
     uint32_t upnib, leftnib;
     if (c == 0) { up = edgeH; upnib = edgeNib; }
-    else { up = H[c - 1]; upnib = (pwprev[((c - 1) >> 1) >> 3] >> (4 * (((c - 1) >> 1) & 7))) & 0xFu; }
+    else { up = H[c - 1]; upnib = bsq_k2_nib<C>(pwprev, c - 1); }
     if (c == C - 1) { left = edgeH; leftnib = edgeNib; }
-    else { left = H[c + 1]; leftnib = (pwprev[((c + 1) >> 1) >> 3] >> (4 * (((c + 1) >> 1) & 7))) & 0xFu; }
+    else { left = H[c + 1]; leftnib = bsq_k2_nib<C>(pwprev, c + 1); }
     const T diag = H[c];
     const int o = (x >= 1 && x <= n) ? (int)oseq[x - 1] : 0;
     const int mm = (y >= 1 && y <= m) ? (int)mseq[y - 1] : 0;
@@ -353,10 +369,9 @@ __device__ __forceinline__ void bsq_k2_step(
     commit[hc] = intab;
     cur[hc >> 3] |= mk << (4 * (hc & 7));
     if (BLOCAL) {  // :397-406 restricted to one diagonal (a ascends with s)
-      if (intab && h > best[c]) { best[c] = h; besta[c] = x < y ? x : y; }
+      if (intab && h > best[c]) { best[c] = h; bests[c] = s; }
     }
   }
-  // commit after all reads of this step (cells of one step never read each other)
 #pragma unroll
   for (int hc = 0; hc < HC; hc++)
     if (commit[hc]) H[2 * hc + Q] = newH[hc];
@@ -364,17 +379,92 @@ __device__ __forceinline__ void bsq_k2_step(
   for (int w = 0; w < WPS; w++) { pout[w] = cur[w]; pwprev[w] = cur[w]; }
 }
 
+// interior step: every band cell is a regular cell (x >= 1, y >= 1, in table).
+// comb: nibble hc = 4*origin letter + mutant letter of cell hc (PACKED), else
+// the letters are read per cell.  fixc: local index of the first diagonal past
+// the band in this lane (or -1): it is reset to -inf so the band edge stays shut.
+template <class S, int C, bool BLOCAL, int GOS, int Q, bool PACKED>
+__device__ __forceinline__ void bsq_k2_step_fast(
+    typename S::T (&H)[C], typename S::T (&best)[BLOCAL ? C : 1], int (&bests)[BLOCAL ? C : 1],
+    uint32_t (&pwprev)[(C / 2 + 7) / 8], typename S::T edgeH, uint32_t edgeNib,
+    const typename S::T* s_sub, int L, unsigned long long comb, const uint8_t* oseq,
+    const uint8_t* mseq, int s, int d0, int fixc, typename S::T go, typename S::T ge,
+    uint32_t* pout) {
+  typedef typename S::T T;
+  constexpr int HC = C / 2;
+  constexpr int WPS = (HC + 7) / 8;
+  constexpr int SH = (sizeof(T) == 8) ? 3 : 2;  // log2 of the table entry size
+  uint32_t cur[WPS];
+#pragma unroll
+  for (int w = 0; w < WPS; w++) cur[w] = 0u;
+  const uint32_t comb_lo = (uint32_t)comb, comb_hi = (uint32_t)(comb >> 32);
+  T newH[HC];
+#pragma unroll
+  for (int hc = 0; hc < HC; hc++) {
+    const int c = 2 * hc + Q;
+    T up, left;
+    uint32_t upnib, leftnib;
+    if (c == 0) { up = edgeH; upnib = edgeNib; }
+    else { up = H[c - 1]; upnib = bsq_k2_nib<C>(pwprev, c - 1); }
+    if (c == C - 1) { left = edgeH; leftnib = edgeNib; }
+    else { left = H[c + 1]; leftnib = bsq_k2_nib<C>(pwprev, c + 1); }
+    const T diag = H[c];
+    T sig;
+    if (PACKED) {
+      const uint32_t cw = (hc < 8) ? comb_lo : comb_hi;
+      const int sh = 4 * (hc & 7) - SH;  // nibble -> byte offset into the 16-entry table
+      const uint32_t off = (sh >= 0 ? (cw >> (sh >= 0 ? sh : 0)) : (cw << (sh < 0 ? -sh : 0))) & (0xFu << SH);
+      sig = *(const T*)((const char*)s_sub + off);
+    } else {
+      const int d = d0 + c;
+      const int x = (s + d) >> 1, y = (s - d) >> 1;
+      sig = s_sub[(int)oseq[x - 1] * L + (int)mseq[y - 1]];
+    }
+    T h;
+    uint32_t mk;
+    bsq_cell<S, GOS, BLOCAL>(up, bsq_extends<GOS>(upnib, BSQ_MD), left,
+                             bsq_extends<GOS>(leftnib, BSQ_MI), diag, sig, (T)0, go, ge, h, mk);
+    newH[hc] = h;
+    cur[hc >> 3] |= mk << (4 * (hc & 7));
+    if (BLOCAL) {
+      if (h > best[c]) { best[c] = h; bests[c] = s; }
+    }
+  }
+#pragma unroll
+  for (int hc = 0; hc < HC; hc++) H[2 * hc + Q] = newH[hc];
+  if (fixc >= 0 && (fixc & 1) == Q) {  // one lane per group, every other step
+    const T NINF = S::ninf();
+    switch (fixc >> 1) {
+#define BSQ_FIX(J) case J: if (J < HC) H[(2 * J + Q) < C ? (2 * J + Q) : 0] = NINF; break;
+      BSQ_FIX(0) BSQ_FIX(1) BSQ_FIX(2) BSQ_FIX(3) BSQ_FIX(4) BSQ_FIX(5) BSQ_FIX(6) BSQ_FIX(7)
+      BSQ_FIX(8) BSQ_FIX(9) BSQ_FIX(10) BSQ_FIX(11) BSQ_FIX(12) BSQ_FIX(13) BSQ_FIX(14) BSQ_FIX(15)
+#undef BSQ_FIX
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < WPS; w++) { pout[w] = cur[w]; pwprev[w] = cur[w]; }
+}
+
 template <class S, int G, int C, bool BLOCAL, int GOS>
 __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
   typedef typename S::T T;
-  static_assert(C % 2 == 0, "lanes own an even number of diagonals");
+  static_assert(C % 2 == 0 && C <= 32, "lanes own an even number of diagonals, at most 32");
   constexpr int HC = C / 2;
   constexpr int WPS = (HC + 7) / 8;
   constexpr int NB = BLOCAL ? C : 1;
   __shared__ T s_sub[BSQ_MAX_L * BSQ_MAX_L];
   const int L = A.L;
-  for (int i = threadIdx.x; i < L * L; i += blockDim.x) s_sub[i] = ((const T*)A.subst)[i];
+  // DNA-sized alphabets: the table is re-laid out 4 x 4 so that a nibble
+  // (4*o + m) indexes it directly
+  const bool packed = (L <= 4);
+  for (int i = threadIdx.x; i < BSQ_MAX_L * BSQ_MAX_L; i += blockDim.x) s_sub[i] = (T)0;
   __syncthreads();
+  for (int i = threadIdx.x; i < L * L; i += blockDim.x) {
+    const int o = i / L, mm = i - o * L;
+    s_sub[packed ? (o * 4 + mm) : i] = ((const T*)A.subst)[i];
+  }
+  __syncthreads();
+  const int Lt = packed ? 4 : L;  // row stride of s_sub
 
   const int tid = threadIdx.x;
   const int l = tid % G;
@@ -397,43 +487,123 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
     const int d0 = dmin + l * C;       // my first diagonal
     int nreal = W - l * C;             // how many of my diagonals are inside the band
     nreal = nreal < 0 ? 0 : (nreal > C ? C : nreal);
+    const int fixc = (nreal < C && W - l * C >= 0) ? nreal : -1;  // first diagonal past the band, if mine
     // last anti-diagonal holding a cell: max over d of 2*min(n, m+d) - d, at d* = clamp(n-m)
     int dstar = n - m;
     dstar = dstar < dmin ? dmin : (dstar > dmax ? dmax : dstar);
     const int s_end = 2 * (n < m + dstar ? n : m + dstar) - dstar;
     const int s0 = P.s0;               // (s0 - dmin) is even: step parity == loop parity
+    // interior steps: all band diagonals have x >= 1, y >= 1 and have not ended
+    const int admin = dmin < 0 ? -dmin : dmin, admax = dmax < 0 ? -dmax : dmax;
+    const int si_lo = (admin > admax ? admin : admax) + 2;
+    const int e_lo = 2 * (n < m + dmin ? n : m + dmin) - dmin, e_hi = 2 * (n < m + dmax ? n : m + dmax) - dmax;
+    const int si_hi = e_lo < e_hi ? e_lo : e_hi;
+    int sA = s0;
+    if (si_lo > s0) sA = s0 + 2 * ((si_lo - s0 + 1) / 2);
+    // last pair start s with s + 1 <= si_hi and s == s0 (mod 2)
+    int sB = si_hi - 1;
+    if (((sB - s0) & 1) != 0) sB -= 1;
 
     T H[C];
     T best[NB];
-    int besta[NB];
+    int bests[NB];
     uint32_t pwprev[WPS];
 #pragma unroll
     for (int c = 0; c < C; c++) H[c] = NINF;
 #pragma unroll
-    for (int c = 0; c < NB; c++) { best[c] = NINF; besta[c] = -1; }
+    for (int c = 0; c < NB; c++) { best[c] = NINF; bests[c] = 0; }
 #pragma unroll
     for (int w = 0; w < WPS; w++) pwprev[w] = 0u;
     uint32_t* prow = A.ptr + P.ptr_off + (long long)l * WPS;
 
-    for (int s = s0; s <= s_end; s += 2) {
-      {  // even parity: c = 0 needs diagonal d0-1 (lane below, its C-1) from step s-1
+    int s = s0;
+#define BSQ_K2_CAREFUL_PAIR()                                                                         \
+    {                                                                                                 \
+      T eH = __shfl_up_sync(gmask, H[C - 1], 1, G);                                                   \
+      uint32_t eW = __shfl_up_sync(gmask, pwprev[WPS - 1], 1, G);                                     \
+      uint32_t eNib = (eW >> (4 * ((HC - 1) & 7))) & 0xFu;                                            \
+      if (l == 0) { eH = NINF; eNib = 0u; }                                                           \
+      bsq_k2_step_careful<S, C, BLOCAL, GOS, 0>(btype, H, best, bests, pwprev, eH, eNib, s_sub, Lt,   \
+                                                oseq, mseq, n, m, s, d0, nreal, go, ge,               \
+                                                prow + (long long)(s - s0) * (G * WPS));              \
+      eH = __shfl_down_sync(gmask, H[0], 1, G);                                                       \
+      eW = __shfl_down_sync(gmask, pwprev[0], 1, G);                                                  \
+      eNib = eW & 0xFu;                                                                               \
+      if (l == G - 1) { eH = NINF; eNib = 0u; }                                                       \
+      bsq_k2_step_careful<S, C, BLOCAL, GOS, 1>(btype, H, best, bests, pwprev, eH, eNib, s_sub, Lt,   \
+                                                oseq, mseq, n, m, s + 1, d0, nreal, go, ge,           \
+                                                prow + (long long)(s + 1 - s0) * (G * WPS));          \
+    }
+    for (; s < sA && s <= s_end; s += 2) BSQ_K2_CAREFUL_PAIR()
+
+    if (s <= sB) {
+      // letter windows for the pair of steps (s, s+1); cell hc of the even step is
+      // (x0 + hc, y0 - hc), of the odd step (x0 + 1 + hc, y0 - hc)
+      int x0 = (s + d0) >> 1, y0 = (s - d0) >> 1;
+      // nibble j of ow: 4*o[x0+j-1], of mw: m[y0-j-1] (j < HC); onx: 4*o[x0+HC-1],
+      // the nibble that slides into ow for the odd step
+      unsigned long long ow = 0ull, mw = 0ull;
+      unsigned onx = 0u;
+      if (packed) {
+#pragma unroll
+        for (int j = 0; j < HC; j++) {
+          const int xi = x0 + j - 1;
+          const unsigned v = ((unsigned)xi < (unsigned)n) ? (unsigned)oseq[xi] : 0u;
+          ow |= (unsigned long long)(v << 2) << (4 * j);
+        }
+        {
+          const int xi = x0 + HC - 1;
+          onx = ((unsigned)xi < (unsigned)n) ? ((unsigned)oseq[xi] << 2) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < HC; j++) {
+          const int yi = y0 - j - 1;
+          const unsigned v = ((unsigned)yi < (unsigned)m) ? (unsigned)mseq[yi] : 0u;
+          mw |= (unsigned long long)v << (4 * j);
+        }
+      }
+      for (; s <= sB; s += 2) {
+        unsigned no = 0u, nm = 0u;  // letters entering the windows after this pair
+        if (packed) {
+          const int xi = x0 + HC, yi = y0;
+          if ((unsigned)xi < (unsigned)n) no = oseq[xi];
+          if ((unsigned)yi < (unsigned)m) nm = mseq[yi];
+        }
+        const unsigned long long ow_odd = (ow >> 4) | ((unsigned long long)onx << (4 * (HC - 1)));
         T eH = __shfl_up_sync(gmask, H[C - 1], 1, G);
         uint32_t eW = __shfl_up_sync(gmask, pwprev[WPS - 1], 1, G);
         uint32_t eNib = (eW >> (4 * ((HC - 1) & 7))) & 0xFu;
         if (l == 0) { eH = NINF; eNib = 0u; }
-        bsq_k2_step<S, C, BLOCAL, GOS, 0>(btype, H, best, besta, pwprev, eH, eNib, s_sub, L, oseq, mseq, n, m,
-                                      s, d0, nreal, go, ge, prow + (long long)(s - s0) * (G * WPS));
-      }
-      {  // odd parity: c = C-1 needs diagonal d0+C (lane above, its 0) from step s
-        T eH = __shfl_down_sync(gmask, H[0], 1, G);
-        uint32_t eW = __shfl_down_sync(gmask, pwprev[0], 1, G);
-        uint32_t eNib = eW & 0xFu;
+        if (packed)
+          bsq_k2_step_fast<S, C, BLOCAL, GOS, 0, true>(H, best, bests, pwprev, eH, eNib, s_sub, Lt, ow | mw, oseq,
+                                                       mseq, s, d0, fixc, go, ge,
+                                                       prow + (long long)(s - s0) * (G * WPS));
+        else
+          bsq_k2_step_fast<S, C, BLOCAL, GOS, 0, false>(H, best, bests, pwprev, eH, eNib, s_sub, Lt, 0ull, oseq,
+                                                        mseq, s, d0, fixc, go, ge,
+                                                        prow + (long long)(s - s0) * (G * WPS));
+        eH = __shfl_down_sync(gmask, H[0], 1, G);
+        eW = __shfl_down_sync(gmask, pwprev[0], 1, G);
+        eNib = eW & 0xFu;
         if (l == G - 1) { eH = NINF; eNib = 0u; }
-        bsq_k2_step<S, C, BLOCAL, GOS, 1>(btype, H, best, besta, pwprev, eH, eNib, s_sub, L, oseq, mseq, n, m,
-                                      s + 1, d0, nreal, go, ge,
-                                      prow + (long long)(s + 1 - s0) * (G * WPS));
+        if (packed)
+          bsq_k2_step_fast<S, C, BLOCAL, GOS, 1, true>(H, best, bests, pwprev, eH, eNib, s_sub, Lt, ow_odd | mw,
+                                                       oseq, mseq, s + 1, d0, fixc, go, ge,
+                                                       prow + (long long)(s + 1 - s0) * (G * WPS));
+        else
+          bsq_k2_step_fast<S, C, BLOCAL, GOS, 1, false>(H, best, bests, pwprev, eH, eNib, s_sub, Lt, 0ull, oseq,
+                                                        mseq, s + 1, d0, fixc, go, ge,
+                                                        prow + (long long)(s + 1 - s0) * (G * WPS));
+        if (packed) {
+          ow = ow_odd;
+          onx = no << 2;
+          mw = (mw << 4) | (unsigned long long)nm;
+          x0++; y0++;
+        }
       }
     }
+    for (; s <= s_end; s += 2) BSQ_K2_CAREFUL_PAIR()
+#undef BSQ_K2_CAREFUL_PAIR
 
     // end cell, _banded_find_optimal (:364-414): diagonals ascending, strict >
     T bs = NINF;
@@ -447,7 +617,7 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
       for (int c = 0; c < C; c++) {
         if (c < nreal) {
           const T cand = BLOCAL ? best[c < NB ? c : 0] : H[c];
-          if (cand > bs) { bs = cand; bdi = l * C + c; ba = BLOCAL ? besta[c < NB ? c : 0] : 0; }
+          if (cand > bs) { bs = cand; bdi = l * C + c; ba = BLOCAL ? bests[c < NB ? c : 0] : 0; }
         }
       }
     }
@@ -457,8 +627,8 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
       if (bdi == BSQ_INT_MAX) st = BSQ_NO_ALIGNMENT;
       else {
         const int d = dmin + bdi;
-        if (BLOCAL) { ex = ba + (d > 0 ? d : 0); ey = ba - (d > 0 ? 0 : d); }
-        else { ex = n < m + d ? n : m + d; ey = ex - d; }  // last cell of the diagonal (:383)
+        if (BLOCAL) { ex = (ba + d) >> 1; ey = (ba - d) >> 1; }  // ba = step s of the best cell
+        else { ex = n < m + d ? n : m + d; ey = ex - d; }        // last cell of the diagonal (:383)
       }
       const int oi = P.pad;
       A.out_score[oi] = S::to_f64(bs);
@@ -468,4 +638,3 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
     }
   }
 }
-

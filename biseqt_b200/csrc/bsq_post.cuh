@@ -70,6 +70,107 @@ __global__ void __launch_bounds__(128) bsq_k4_traceback(const BsqTraceArgs A) {
   A.status[oi] = (ex + ey - len <= 0) ? BSQ_REF_WOULD_ABORT : (len == 0 ? BSQ_EMPTY : BSQ_OK);
 }
 
+// ---------------------------------------------------------------------------
+// K4w: the same walk for LONG pairs, one warp per pair.  A thread-per-pair walk
+// is a chain of dependent HBM loads (~1 us each); here the warp stages the
+// next BSQ_TILE_WORDS of pointer rows below the current position into shared
+// memory with coalesced 16-byte loads and every lane then performs the same
+// walk out of shared memory (lane 0 emits).  The position inside a row is kept
+// incrementally (lane, column) so the walk needs no divisions.
+//   FAMILY 1: K1 layout [pass][x][lane][word]   row id = pass*(n+1) + x
+//   FAMILY 2: K2 layout [s - s0][lane][word]    row id = s - s0
+// ---------------------------------------------------------------------------
+#define BSQ_TILE_WORDS 2048
+#define BSQ_WALK_WARPS 4
+
+template <int FAMILY>
+__global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTraceArgs A) {
+  __shared__ uint32_t s_tile[BSQ_WALK_WARPS][BSQ_TILE_WORDS];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = blockIdx.x * BSQ_WALK_WARPS + wib;
+  if (p >= A.npairs) return;  // whole warp
+  const BsqPair P = A.pairs[p];
+  const int oi = P.pad;
+  if (A.status[oi] != BSQ_OK) {
+    if (lane == 0) { A.txlen[oi] = 0; A.sx[oi] = -1; A.sy[oi] = -1; }
+    return;
+  }
+  uint32_t* tile = s_tile[wib];
+  const int G = A.G, K = A.K;
+  const int WP = (FAMILY == 1) ? (K + 7) / 8 : (K / 2 + 7) / 8;  // words per lane per row
+  const int RB = G * WP;                                        // words per row
+  const int R = BSQ_TILE_WORDS / RB;                            // rows per tile
+  const int ex = A.ex[oi], ey = A.ey[oi];
+  int x = ex, y = ey, len = 0;
+  int l, k;            // lane / column (K1) or lane / local diagonal (K2) of (x,y)
+  long long rid;       // row id of (x,y)
+  if (FAMILY == 1) {
+    const int BW = G * K, pass = y / BW, r = y - pass * BW;
+    l = r / K; k = r - l * K;
+    rid = (long long)pass * (P.n + 1) + x;
+  } else {
+    const int di = (x - y) - P.dmin;
+    l = di / K; k = di - l * K;
+    rid = (long long)(x + y) - P.s0;
+  }
+  const uint32_t* table = A.ptr + P.ptr_off;
+  const uint8_t* oseq = A.codes + P.o_off;
+  const uint8_t* mseq = A.codes + P.m_off;
+  char* wr = A.slots + P.tx_slot + (long long)P.n + P.m;
+  long long tlo = 1, thi = 0;  // rows [tlo, thi] are staged; empty
+  uint32_t arrive = BSQ_MM;    // how we got here: M (or the end cell) -> lowest bit
+  const int maxlen = P.n + P.m;
+  for (;;) {
+    if (rid < tlo || rid > thi) {
+      thi = rid;
+      tlo = rid - R + 1;
+      if (tlo < 0) tlo = 0;
+      const int nw = (int)(thi - tlo + 1) * RB;   // multiple of 4 words
+      const uint4* src = (const uint4*)(table + tlo * RB);
+      __syncwarp();
+      for (int i = lane; i < nw / 4; i += 32) ((uint4*)tile)[i] = src[i];
+      __syncwarp();
+    }
+    const int kk = (FAMILY == 1) ? k : (k >> 1);
+    const uint32_t word = tile[(int)(rid - tlo) * RB + l * WP + (kk >> 3)];
+    const uint32_t mk = (word >> (4 * (kk & 7))) & 0xFu;
+    const uint32_t op = (arrive == BSQ_MM) ? bsq_lowest(mk) : bsq_gap_base(mk, arrive, A.gosign);
+    if (op == BSQ_MB || op == 0u || len >= maxlen) break;
+    char ch;
+    if (op == BSQ_MM) {
+      ch = (oseq[x - 1] == mseq[y - 1]) ? 'M' : 'S';
+      x--; y--;
+      if (FAMILY == 1) {
+        rid -= 1;
+        if (--k < 0) { k = K - 1; if (--l < 0) { l = G - 1; rid -= (P.n + 1); } }
+      } else {
+        rid -= 2;
+      }
+    } else if (op == BSQ_MD) {
+      ch = 'D'; x--;
+      rid -= 1;
+      if (FAMILY == 2) { if (--k < 0) { k = K - 1; l--; } }
+    } else {
+      ch = 'I'; y--;
+      if (FAMILY == 1) {
+        if (--k < 0) { k = K - 1; if (--l < 0) { l = G - 1; rid -= (P.n + 1); } }
+      } else {
+        rid -= 1;
+        if (++k == K) { k = 0; l++; }
+      }
+    }
+    arrive = op;
+    len++;
+    if (lane == 0) wr[-len] = ch;
+  }
+  if (lane == 0) {
+    A.txlen[oi] = len;
+    A.sx[oi] = x;
+    A.sy[oi] = y;
+    A.status[oi] = (ex + ey - len <= 0) ? BSQ_REF_WOULD_ABORT : (len == 0 ? BSQ_EMPTY : BSQ_OK);
+  }
+}
+
 // exclusive scan of txlen (int32) into int64 offsets, three small kernels
 #define BSQ_SCAN_TILE 2048
 __global__ void __launch_bounds__(256) bsq_scan_tile_sums(const int* in, int n, long long* tile_sums) {

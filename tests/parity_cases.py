@@ -95,6 +95,32 @@ def run_wide_bands(eng, seed, length=300, radii=(40, 100, 200, 500)):
             check_batch(eng, probs)
 
 
+def run_banded_interior(eng, seed, length=260, npairs=4):
+    """Banded problems long enough to reach the ungated interior phase, with
+    shifted bands (overlap offsets), odd/even widths, all types and go signs."""
+    rng = np.random.default_rng(seed)
+    for typ in (0, 1, 2):
+        for gomode in (-1, 0, 1):
+            for L in (4, 7):
+                S, go, ge = score_family(rng, L, int(rng.integers(1, 4)), gomode)
+                probs = []
+                for _ in range(npairs):
+                    n = int(rng.integers(length // 2, length))
+                    off = 0 if typ == 0 else int(rng.integers(-length // 3, length // 3))
+                    chunk = rng.integers(0, L, size=2 * length).astype(np.uint8)
+                    o = chunk[max(0, -off):max(0, -off) + n]
+                    src = chunk[max(0, off):max(0, off) + n]
+                    t, _ = mutate(rng, src, L, subst=0.05, go=0.03, ge=0.3)
+                    m = len(t)
+                    r1, r2 = int(rng.integers(1, 45)), int(rng.integers(1, 45))
+                    dr = (off - r1, off + r2)
+                    if typ == 0:
+                        dr = (min(dr[0], 0, n - m), max(dr[1], 0, n - m))
+                    probs.append(dict(origin=o, mutant=t, subst=S, go=go, ge=ge, mode=1, type=typ,
+                                      diag_range=dr, L=L))
+                check_batch(eng, probs)
+
+
 def run_unsupported_band(eng):
     o = np.zeros(1500, np.uint8)
     pr = dict(origin=o, mutant=o, subst=np.eye(4), go=0.0, ge=-1.0, mode=1, type=2,

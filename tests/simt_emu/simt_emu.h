@@ -29,6 +29,9 @@ struct dim3 {
   dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 
+struct uint4 { unsigned x, y, z, w; };
+struct uint2 { unsigned x, y; };
+
 namespace emu {
 
 struct Coll {            // one rendezvous per distinct participation mask

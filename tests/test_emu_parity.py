@@ -27,6 +27,27 @@ def test_emu_wide_bands(emu_engine):
     pc.run_wide_bands(emu_engine, seed=41, length=120, radii=(40, 100, 300))
 
 
+def test_emu_banded_interior(emu_engine):
+    pc.run_banded_interior(emu_engine, seed=43, length=200, npairs=3)
+
+
+def test_emu_wide_band_interior(emu_engine):
+    pc.run_wide_bands(emu_engine, seed=45, length=520, radii=(460,))
+
+
+def test_emu_warp_traceback(emu_lib, monkeypatch):
+    """Force the warp-per-pair tile walker (normally only used for long pairs)."""
+    monkeypatch.setenv('BSQ_TRACE_KERNEL', 'warp')
+    eng = batch.Engine(0, lib=emu_lib)
+    try:
+        pc.run_batches(eng, seed=23, npairs=6, lo=0, hi=60)
+        pc.run_multipass_std(eng, seed=33, n_hi=24, widths=(700,))
+        pc.run_banded_interior(eng, seed=47, length=200, npairs=2)
+        pc.run_wide_bands(eng, seed=49, length=300, radii=(100, 200))
+    finally:
+        eng.close()
+
+
 def test_emu_unsupported_band(emu_engine):
     pc.run_unsupported_band(emu_engine)
 

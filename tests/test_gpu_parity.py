@@ -42,6 +42,23 @@ def test_gpu_wide_bands(gpu_engine):
     pc.run_wide_bands(gpu_engine, seed=41, length=1200, radii=(40, 64, 100, 200, 232, 500))
 
 
+def test_gpu_banded_interior(gpu_engine):
+    pc.run_banded_interior(gpu_engine, seed=43, length=1500, npairs=12)
+    pc.run_banded_interior(gpu_engine, seed=44, length=300, npairs=30)
+
+
+def test_gpu_both_traceback_kernels(monkeypatch):
+    for which in ('warp', 'thread'):
+        monkeypatch.setenv('BSQ_TRACE_KERNEL', which)
+        eng = batch.Engine(0)
+        try:
+            pc.run_batches(eng, seed=23, npairs=40, lo=0, hi=300)
+            pc.run_multipass_std(eng, seed=33, n_hi=200, widths=(700, 1500))
+            pc.run_banded_interior(eng, seed=47, length=2500, npairs=6)
+        finally:
+            eng.close()
+
+
 def test_gpu_unsupported_band(gpu_engine):
     pc.run_unsupported_band(gpu_engine)
 

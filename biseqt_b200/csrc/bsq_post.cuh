@@ -82,10 +82,12 @@ __global__ void __launch_bounds__(128) bsq_k4_traceback(const BsqTraceArgs A) {
 // ---------------------------------------------------------------------------
 #define BSQ_TILE_WORDS 2048
 #define BSQ_WALK_WARPS 4
+#define BSQ_LET_WIN 256
 
 template <int FAMILY>
 __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTraceArgs A) {
   __shared__ uint32_t s_tile[BSQ_WALK_WARPS][BSQ_TILE_WORDS];
+  __shared__ uint8_t s_let[BSQ_WALK_WARPS][2][BSQ_LET_WIN];  // staged letters: origin, mutant
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p = blockIdx.x * BSQ_WALK_WARPS + wib;
   if (p >= A.npairs) return;  // whole warp
@@ -120,7 +122,22 @@ __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTrac
   long long tlo = 1, thi = 0;  // rows [tlo, thi] are staged; empty
   uint32_t arrive = BSQ_MM;    // how we got here: M (or the end cell) -> lowest bit
   const int maxlen = P.n + P.m;
+  uint8_t* obuf = s_let[wib][0];
+  uint8_t* mbuf = s_let[wib][1];
+  int xb = x, yb = y;          // obuf holds o[xb .. xb+WIN), mbuf m[yb .. yb+WIN); empty
   for (;;) {
+    if (x - 1 < xb && x >= 1) {  // the walk only moves towards smaller x and y
+      xb = x - BSQ_LET_WIN; if (xb < 0) xb = 0;
+      __syncwarp();
+      for (int i = lane; i < BSQ_LET_WIN; i += 32) if (xb + i < P.n) obuf[i] = oseq[xb + i];
+      __syncwarp();
+    }
+    if (y - 1 < yb && y >= 1) {
+      yb = y - BSQ_LET_WIN; if (yb < 0) yb = 0;
+      __syncwarp();
+      for (int i = lane; i < BSQ_LET_WIN; i += 32) if (yb + i < P.m) mbuf[i] = mseq[yb + i];
+      __syncwarp();
+    }
     if (rid < tlo || rid > thi) {
       thi = rid;
       tlo = rid - R + 1;
@@ -138,7 +155,7 @@ __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTrac
     if (op == BSQ_MB || op == 0u || len >= maxlen) break;
     char ch;
     if (op == BSQ_MM) {
-      ch = (oseq[x - 1] == mseq[y - 1]) ? 'M' : 'S';
+      ch = (obuf[x - 1 - xb] == mbuf[y - 1 - yb]) ? 'M' : 'S';
       x--; y--;
       if (FAMILY == 1) {
         rid -= 1;

@@ -18,11 +18,13 @@ static int bsq_do_op(KernelT kern, int op, int grid, cudaStream_t st, const BsqF
 template <class S, int G, int K>
 static int bsq_k1_variant(int ball, int eall, int gos, int op, int grid, cudaStream_t st, const BsqFillArgs* A) {
 #define BSQ_K1_CASE(B, E, GS) \
-  if (ball == B && eall == E && gos == GS) return bsq_do_op(bsq_k1_fill<S, G, K, B != 0, E != 0, GS>, op, grid, st, A);
+  if (ball == B && eall == E && gos == GS) return bsq_do_op(bsq_k1_fill<S, G, K, B != 0, E, GS>, op, grid, st, A);
   BSQ_K1_CASE(0, 0, -1) BSQ_K1_CASE(0, 0, 0) BSQ_K1_CASE(0, 0, 1)
   BSQ_K1_CASE(0, 1, -1) BSQ_K1_CASE(0, 1, 0) BSQ_K1_CASE(0, 1, 1)
+  BSQ_K1_CASE(0, 2, -1) BSQ_K1_CASE(0, 2, 0) BSQ_K1_CASE(0, 2, 1)
   BSQ_K1_CASE(1, 0, -1) BSQ_K1_CASE(1, 0, 0) BSQ_K1_CASE(1, 0, 1)
   BSQ_K1_CASE(1, 1, -1) BSQ_K1_CASE(1, 1, 0) BSQ_K1_CASE(1, 1, 1)
+  BSQ_K1_CASE(1, 2, -1) BSQ_K1_CASE(1, 2, 0) BSQ_K1_CASE(1, 2, 1)
 #undef BSQ_K1_CASE
   return -1;
 }

@@ -446,7 +446,10 @@ int launch_fill(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, size_t* evi) 
   A.out_status = B.status.as<int>();
   A.counter = B.counters.as<int>() + ci;
   const int G = ch.family == 1 ? BSQ_K1_CFGS[ch.cfg].G : BSQ_K2_CFGS[ch.cfg].G;
-  const int ball = P.bmode == BSQ_B_ALL, eall = P.emode == BSQ_E_ALL;
+  // per-cell end search: ungated when every gap move lowers (or keeps) the score, so that
+  // the -inf padding columns can never beat a real cell; explicitly gated otherwise
+  const bool monotone = (P.prm.ge <= 0.0) && (P.prm.ge + P.prm.go <= 0.0);
+  const int ball = P.bmode == BSQ_B_ALL, eall = (P.emode == BSQ_E_ALL) ? (monotone ? 1 : 2) : 0;
   const int blocal = P.prm.type == BSQ_B_LOCAL;
   int occ = ch.family == 1 ? k1_op(P.dtype, ch.cfg, ball, eall, P.gosign, BSQ_OP_OCCUPANCY, 0, 0, nullptr)
                            : k2_op(P.dtype, ch.cfg, blocal, P.gosign, BSQ_OP_OCCUPANCY, 0, 0, nullptr);

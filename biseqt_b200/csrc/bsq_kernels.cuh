@@ -33,6 +33,12 @@ struct ScF64 {
     return __longlong_as_double((long long)0xFFF0000000000000ULL);
   }
   static __device__ __forceinline__ T add(T a, T b) { return __dadd_rn(a, b); }
+  // (a) + go when the gap opens, (a) when it extends.  The "opens" flag travels as the
+  // high word of the double 1.0 / 0.0 and is applied with one DFMA: fma(1,go,a) is the
+  // correctly rounded a+go (the same value as the reference's second add,
+  // _pw_internals.c:272) and fma(0,go,a) == a, so no select is needed.
+  static __device__ __forceinline__ T open(T a, int g, T go) { return __fma_rn(__hiloint2double(g, 0), go, a); }
+  static __device__ __forceinline__ int flag(bool extends) { return extends ? 0 : 0x3FF00000; }
   static __device__ __forceinline__ double to_f64(T v) { return v; }
   static __device__ __forceinline__ T go(const BsqFillArgs& A) { return A.go_d; }
   static __device__ __forceinline__ T ge(const BsqFillArgs& A) { return A.ge_d; }
@@ -42,6 +48,8 @@ struct ScI32 {
   typedef int T;
   static __device__ __forceinline__ T ninf() { return -(1 << 30); }
   static __device__ __forceinline__ T add(T a, T b) { return a + b; }
+  static __device__ __forceinline__ T open(T a, int g, T go) { return g * go + a; }  // one IMAD
+  static __device__ __forceinline__ int flag(bool extends) { return extends ? 0 : 1; }
   static __device__ __forceinline__ double to_f64(T v) { return (double)v; }
   static __device__ __forceinline__ T go(const BsqFillArgs& A) { return A.go_i; }
   static __device__ __forceinline__ T ge(const BsqFillArgs& A) { return A.ge_i; }
@@ -84,6 +92,40 @@ __device__ __forceinline__ void bsq_cell(typename S::T up, bool fD, typename S::
   mask = mk;
 }
 
+// The same cell with the open/extend decision carried as S::flag() words (see
+// ScF64::open) and the tie set returned as four predicates, which keeps the
+// ALU-pipe work per cell minimal (the pipe that bounds these kernels).
+template <class S, int GOS, bool HASB>
+__device__ __forceinline__ void bsq_cell2(typename S::T up, int gD, typename S::T left, int gI,
+                                          typename S::T diag, typename S::T sig, typename S::T bval,
+                                          typename S::T go, typename S::T ge, typename S::T& H,
+                                          bool& eB, bool& eD, bool& eI, bool& eM) {
+  typedef typename S::T T;
+  T D = S::add(up, ge);      // _pw_internals.c:269-270
+  T I = S::add(left, ge);
+  if (GOS != 0) {            // :271-273
+    D = S::open(D, gD, go);
+    I = S::open(I, gI, go);
+  }
+  const T M = S::add(diag, sig);  // :234
+  T h = D > I ? D : I;
+  h = M > h ? M : h;
+  if (HASB) h = bval > h ? bval : h;
+  eD = (D == h);
+  eI = (I == h);
+  eM = (M == h);
+  eB = HASB ? (bval == h) : false;
+  H = h;
+}
+
+// open/extend flag of a gap out of a cell with tie set (eB,eD,eI,eM); own = the gap's op
+template <class S, int GOS>
+__device__ __forceinline__ int bsq_gapflag(bool eOwn, bool eO1, bool eO2, bool eO3) {
+  if (GOS < 0) return S::flag(eOwn);                           // extends iff own op in the set
+  if (GOS > 0) return S::flag(eOwn && !(eO1 || eO2 || eO3));   // extends iff nothing else is
+  return 0;
+}
+
 // lexicographic "better end cell": higher score, then earlier scan position
 template <class T>
 __device__ __forceinline__ bool bsq_better(T s, int k1, int k2, T bs, int b1, int b2) {
@@ -110,56 +152,67 @@ __device__ __forceinline__ void bsq_group_best(unsigned gmask, T& s, int& k1, in
 // per-group scratch slab.  Pointer layout: [pass][x][lane][word], 8 cells/word.
 //   replaces: dptable_solve's fill loop pw.c:59-110 + _std_find_optimal
 // ===========================================================================
-template <class S, int K, int GOS, bool ALLB, bool EALL>
+// EALL: 0 = end cell not searched per cell, 1 = every cell may end the alignment
+// (LOCAL / START_ANCHORED), 2 = same but padding columns must be masked out
+// explicitly (only needed for score sets where a gap does not lower the score).
+template <class S, int K, int GOS, bool ALLB, int EALL>
 __device__ __forceinline__ void bsq_k1_row(
-    typename S::T (&Hup)[K], uint32_t (&pw)[(K + 7) / 8], const int (&mlet)[K],
-    const typename S::T* srow, typename S::T inH, uint32_t inNib, typename S::T diag_in,
-    typename S::T bfirst, typename S::T brest, typename S::T go, typename S::T ge, int x,
-    int y0, int kv, typename S::T& best, int& bx, int& by, typename S::T& outH,
-    uint32_t& outNib) {
+    typename S::T (&Hup)[K], int (&gD)[K], uint32_t (&cw)[(K + 7) / 8], const int (&moff)[K],
+    const char* srow, typename S::T inH, int inG, typename S::T diag_in,
+    typename S::T bfirst, typename S::T brest, typename S::T go, typename S::T ge, int xk,
+    int kv, typename S::T& best, int& bpos, typename S::T& outH, int& outG) {
   typedef typename S::T T;
   constexpr int WPL = (K + 7) / 8;
   T left = inH;
-  bool fI = bsq_extends<GOS>(inNib, BSQ_MI);
+  int gI = inG;
   T diag = diag_in;
-  uint32_t cw[WPL];
 #pragma unroll
   for (int w = 0; w < WPL; w++) cw[w] = 0u;
-  uint32_t mk = 0u;
 #pragma unroll
   for (int k = 0; k < K; k++) {
     const T up = Hup[k];
-    const uint32_t upnib = (pw[k >> 3] >> (4 * (k & 7))) & 0xFu;
-    const bool fD = bsq_extends<GOS>(upnib, BSQ_MD);
-    const T sig = srow[mlet[k]];
+    const T sig = *(const T*)(srow + moff[k]);
     T H;
+    bool eB, eD, eI, eM;
     if (ALLB || k == 0)
-      bsq_cell<S, GOS, true>(up, fD, left, fI, diag, sig, k == 0 ? bfirst : brest, go, ge, H, mk);
+      bsq_cell2<S, GOS, true>(up, gD[k], left, gI, diag, sig, k == 0 ? bfirst : brest, go, ge, H, eB, eD, eI, eM);
     else
-      bsq_cell<S, GOS, false>(up, fD, left, fI, diag, sig, bfirst, go, ge, H, mk);
-    cw[k >> 3] |= mk << (4 * (k & 7));
+      bsq_cell2<S, GOS, false>(up, gD[k], left, gI, diag, sig, bfirst, go, ge, H, eB, eD, eI, eM);
+    uint32_t w = cw[k >> 3];
+    if (eB) w += BSQ_MB << (4 * (k & 7));
+    if (eD) w += BSQ_MD << (4 * (k & 7));
+    if (eI) w += BSQ_MI << (4 * (k & 7));
+    if (eM) w += BSQ_MM << (4 * (k & 7));
+    cw[k >> 3] = w;
+    gD[k] = bsq_gapflag<S, GOS>(eD, eB, eI, eM);
+    gI = bsq_gapflag<S, GOS>(eI, eB, eD, eM);
     diag = up;
     left = H;
-    fI = bsq_extends<GOS>(mk, BSQ_MI);
     Hup[k] = H;
-    if (EALL) {  // _std_find_optimal :343-353, row-major first strict max
-      if (H > best && k < kv) { best = H; bx = x; by = y0 + k; }
+    if (EALL == 1) {  // _std_find_optimal :343-353, row-major first strict max
+      if (H > best) { best = H; bpos = xk + k; }
+    } else if (EALL == 2) {
+      if (H > best && k < kv) { best = H; bpos = xk + k; }
     }
   }
-#pragma unroll
-  for (int w = 0; w < WPL; w++) pw[w] = cw[w];
   outH = left;
-  outNib = mk;
+  outG = gI;
 }
 
-template <class S, int G, int K, bool BALL, bool EALL, int GOS>
+template <class S, int G, int K, bool BALL, int EALL, int GOS>
 __global__ void __launch_bounds__(128) bsq_k1_fill(const BsqFillArgs A) {
   typedef typename S::T T;
+  static_assert(K <= 32, "end-cell positions are packed as x*32 + k");
   constexpr int WPL = (K + 7) / 8;
   constexpr int BW = G * K;
-  __shared__ T s_sub[BSQ_MAX_L * BSQ_MAX_L];
-  const int L = A.L;
-  for (int i = threadIdx.x; i < L * L; i += blockDim.x) s_sub[i] = ((const T*)A.subst)[i];
+  // substitution table with one extra column (letter L = "padding column") holding
+  // -inf, so cells right of the table can never win or tie anything
+  __shared__ T s_sub[BSQ_MAX_L * (BSQ_MAX_L + 1)];
+  const int L = A.L, Ls = L + 1;
+  for (int i = threadIdx.x; i < L * Ls; i += blockDim.x) {
+    const int o = i / Ls, mm = i - o * Ls;
+    s_sub[i] = (mm < L) ? ((const T*)A.subst)[o * L + mm] : S::ninf();
+  }
   __syncthreads();
 
   const int tid = threadIdx.x;
@@ -189,44 +242,44 @@ __global__ void __launch_bounds__(128) bsq_k1_fill(const BsqFillArgs A) {
 
     for (int pass = 0; pass < npass; pass++) {
       const int y0 = pass * BW + l * K;
-      int mlet[K];
+      int moff[K];  // byte offset of my column's letter inside a table row
 #pragma unroll
       for (int k = 0; k < K; k++) {
         const int y = y0 + k;
-        mlet[k] = (y >= 1 && y <= m) ? (int)A.codes[P.m_off + y - 1] : 0;
+        const int let = (y >= 1 && y <= m) ? (int)A.codes[P.m_off + y - 1] : (y > m ? L : 0);
+        moff[k] = let * (int)sizeof(T);
       }
       int kv = m - y0 + 1;
       kv = kv < 0 ? 0 : (kv > K ? K : kv);
       const int km = m - y0;  // which of my columns is column m (if in [0,K))
       T Hup[K];
-      uint32_t pw[WPL];
+      int gD[K];
+      uint32_t cw[WPL];
 #pragma unroll
-      for (int k = 0; k < K; k++) Hup[k] = NINF;
-#pragma unroll
-      for (int w = 0; w < WPL; w++) pw[w] = 0u;
+      for (int k = 0; k < K; k++) { Hup[k] = NINF; gD[k] = 0; }
       T lastH = NINF;
-      uint32_t lastNib = 0u;
+      int lastG = 0;
       T prev_in = NINF;
       T pbest = ZERO;  // per-pass record for E_ALL (merged lexicographically below)
-      int pbx = BSQ_INT_MAX, pby = BSQ_INT_MAX;
+      int pbpos = BSQ_INT_MAX;
       uint32_t* prow = A.ptr + P.ptr_off + ((long long)pass * (n + 1) * G + l) * WPL;
       const bool more = (pass + 1 < npass);
 
       for (int t = 0; t <= n + G - 1; t++) {
         const int x = t - l;
         T inH = __shfl_up_sync(gmask, lastH, 1, G);
-        uint32_t inNib = __shfl_up_sync(gmask, lastNib, 1, G);
+        int inG = __shfl_up_sync(gmask, lastG, 1, G);
         const bool active = (x >= 0 && x <= n);
         if (l == 0) {
           inH = NINF;
-          inNib = 0u;
-          if (pass > 0 && active) { inH = colh[x]; inNib = colf[x]; }
+          inG = 0;
+          if (pass > 0 && active) { inH = colh[x]; inG = S::flag(colf[x] == 0); }
         }
         if (active) {
           const int o = (x >= 1) ? (int)A.codes[P.o_off + x - 1] : 0;
-          const T* srow = s_sub + o * L;
+          const char* srow = (const char*)s_sub + o * Ls * (int)sizeof(T);
           T outH;
-          uint32_t outNib;
+          int outG;
           if (BALL || x == 0) {
             T bfirst, brest;
             if (BALL) { bfirst = ZERO; brest = ZERO; }
@@ -234,21 +287,19 @@ __global__ void __launch_bounds__(128) bsq_k1_fill(const BsqFillArgs A) {
               brest = (bmode >= BSQ_B_EDGE) ? ZERO : NINF;
               bfirst = (bmode >= BSQ_B_EDGE || y0 == 0) ? ZERO : NINF;
             }
-            bsq_k1_row<S, K, GOS, true, EALL>(Hup, pw, mlet, srow, inH, inNib, prev_in,
-                                                          bfirst, brest, go, ge, x, y0, kv, pbest,
-                                                          pbx, pby, outH, outNib);
+            bsq_k1_row<S, K, GOS, true, EALL>(Hup, gD, cw, moff, srow, inH, inG, prev_in, bfirst, brest, go, ge,
+                                              x * 32, kv, pbest, pbpos, outH, outG);
           } else {
             const T bfirst = (bmode == BSQ_B_EDGE && y0 == 0) ? ZERO : NINF;
-            bsq_k1_row<S, K, GOS, false, EALL>(Hup, pw, mlet, srow, inH, inNib, prev_in,
-                                                           bfirst, NINF, go, ge, x, y0, kv, pbest,
-                                                           pbx, pby, outH, outNib);
+            bsq_k1_row<S, K, GOS, false, EALL>(Hup, gD, cw, moff, srow, inH, inG, prev_in, bfirst, NINF, go, ge,
+                                               x * 32, kv, pbest, pbpos, outH, outG);
           }
           lastH = outH;
-          lastNib = outNib;
+          lastG = outG;
           uint32_t* pr = prow + (long long)x * (G * WPL);
 #pragma unroll
-          for (int w = 0; w < WPL; w++) pr[w] = pw[w];
-          if (more && l == G - 1) { colh[x] = outH; colf[x] = (uint8_t)outNib; }
+          for (int w = 0; w < WPL; w++) pr[w] = cw[w];
+          if (more && l == G - 1) { colh[x] = outH; colf[x] = (uint8_t)(outG != 0); }
           if (!EALL) {
             if (km >= 0 && km < K) {  // I own column m
               T Hm = NINF;
@@ -273,6 +324,8 @@ __global__ void __launch_bounds__(128) bsq_k1_fill(const BsqFillArgs A) {
         prev_in = (x >= 0) ? inH : NINF;
       }
       if (EALL) {
+        const int pbx = (pbpos == BSQ_INT_MAX) ? BSQ_INT_MAX : (pbpos >> 5);
+        const int pby = (pbpos == BSQ_INT_MAX) ? BSQ_INT_MAX : (y0 + (pbpos & 31));
         if (bsq_better<T>(pbest, pbx, pby, best, bk1, bk2)) { best = pbest; bk1 = pbx; bk2 = pby; }
       }
       if (more) __syncwarp(gmask);  // boundary column visible to lane 0 of the next pass

@@ -245,6 +245,7 @@ inline unsigned __ballot_sync(unsigned mask_, int pred) {
 inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 
 inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline long long __double_as_longlong(double d) { long long v; memcpy(&v, &d, 8); return v; }
 inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 inline int __double2hiint(double d) { return (int)(__double_as_longlong(d) >> 32); }

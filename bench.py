@@ -246,12 +246,18 @@ def measure(eng, w, steps, warmup, sampler_gpu, do_e2e=True):
         barrier()
         t0 = time.perf_counter()
         h2d = d2h = 0
+        plan_ms, call_ms = [], []
         for _ in range(steps):
             r = eng.align(pin['codes'], pin['o_off'], pin['o_len'], pin['m_off'], pin['m_len'], *args, out=outb, **kw)
             tt = eng.timing()
             h2d, d2h = tt['h2d_bytes'], tt['d2h_bytes']
             launches += tt['fill_launches']
+            plan_ms.append(tt['plan_ms'])
+            call_ms.append(tt['call_ms'])
         out['e2e_s'] = time.perf_counter() - t0
+        out['e2e_breakdown_ms'] = {'python_call': 1e3 * out['e2e_s'] / steps, 'c_call': float(np.mean(call_ms)),
+                                   'host_plan': float(np.mean(plan_ms)), 'device_span': tt['total_ms'],
+                                   'fill_kernels': tt['fill_ms'], 'chunks': tt['chunks']}
         out['h2d'], out['d2h'] = h2d, d2h
         out['ok_frac'] = float((r.status == 0).mean())
         out['launches'] = launches
@@ -364,7 +370,7 @@ def main():
             'fill_only_gcups': cells_all * args.steps / (allreduce(m['fill_ms'], 'MAX') * 1e-3) / 1e9 if world == 1 else None,
             'clocks': m['clocks'],
             'e2e': {'value': e2e, 'unit': 'GCUPS', 'h2d_bytes_per_step': m['h2d'], 'd2h_bytes_per_step': m['d2h'],
-                    'pairs_per_s': pairs_all * args.steps / e2e_s,
+                    'pairs_per_s': pairs_all * args.steps / e2e_s, 'breakdown_ms': m.get('e2e_breakdown_ms'),
                     'note': 'bsq_align_batch from pinned host arrays: plan + H2D + fill + traceback + pack + D2H'},
             'gpu_launches': int(launches),
             'roofline': roofline,

@@ -229,7 +229,7 @@ class Engine(object):
         self.lib.bsq_get_timing(self.ctx, t)
         return {k: getattr(t, k) for k in ('fill_ms', 'traceback_ms', 'total_ms', 'cells',
                                            'fill_launches', 'h2d_bytes', 'd2h_bytes',
-                                           'ptr_bytes', 'dtype', 'chunks')}
+                                           'ptr_bytes', 'dtype', 'chunks', 'plan_ms', 'call_ms')}
 
 
 class SolvedBatch(object):

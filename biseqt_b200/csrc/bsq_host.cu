@@ -4,10 +4,12 @@
 // cuts the batch into chunks whose pointer tables fit the HBM arena, and
 // drives fill -> traceback -> pack on the context's stream.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/bsqgpu.h"
@@ -74,9 +76,20 @@ struct Chunk {
   int cfg;
   int64_t ptr_words;
   int max_n_multipass;   // K1: longest origin among pairs needing > 1 pass (0 if none)
+  int64_t idx_lo, idx_hi; // caller indices [idx_lo, idx_hi) covered (identity order only)
+  int64_t code_end;      // one past the last byte of codes[] this chunk reads
 };
 
 struct Override { int64_t idx; int status; };
+
+struct PlanItem {  // per-pair classification, filled in parallel
+  int64_t words;   // pointer-table words
+  int64_t cells;
+  int32_t cfg;     // kernel geometry, or -1 - status for pairs that never reach the GPU
+  int32_t aux;     // K1: n if multi-pass else 0; K2: first step s0
+  int32_t lo, hi;  // clipped band
+};
+
 
 struct Plan {
   bsq_params prm;
@@ -85,13 +98,15 @@ struct Plan {
   int dtype = BSQ_DTYPE_F64;
   int gosign = 0;
   int bmode = 0, emode = 0;
-  std::vector<BsqPair> pairs;      // processing order
+  BsqPair* pairs = nullptr;        // processing order; lives in pinned host memory (BufSet.hpairs)
+  int64_t E = 0;                   // number of pair records
   std::vector<Chunk> chunks;
   std::vector<Override> overrides; // pairs never sent to the GPU
   int64_t cells = 0;
   int64_t slot_bytes = 0;
   int64_t max_chunk_words = 0;
   int64_t total_words = 0;
+  bool identity = false;  // processing order == caller order (no sort was needed)
 };
 
 }  // namespace
@@ -99,7 +114,11 @@ struct Plan {
 struct bsq_ctx {
   int device = 0;
   int sms = 1;
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr;       // compute
+  cudaStream_t st_copy = nullptr;  // H2D / D2H, so copies overlap kernels
+  PinBuf htotals;                  // pinned: running transcript totals per chunk
+  std::vector<PlanItem> plan_items;  // planner scratch, kept across calls (no page faults)
+  std::vector<int64_t> plan_order, plan_ptr_off, plan_slot_off;
   std::string err;
   bsq_timing tm;
   BufSet bufs;
@@ -226,10 +245,20 @@ int k2_op(int dtype, int cfg, int blocal, int gos, int op, int grid, cudaStream_
 
 // ---- planning -------------------------------------------------------------
 
-int make_plan(bsq_ctx* ctx, Plan& P, const bsq_params* prm, int64_t N, int64_t ncodes,
+template <class F>
+void parallel_for(int64_t n, F f) {
+  unsigned hw = std::thread::hardware_concurrency();
+  int T = (int)std::min<int64_t>(std::max(1u, std::min(hw, 8u)), std::max<int64_t>(n / 32768, 1));
+  if (T <= 1) { f(0, (int64_t)0, n); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < T; t++) th.emplace_back([=]() { f(t, n * t / T, n * (t + 1) / T); });
+  for (auto& x : th) x.join();
+}
+
+int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int64_t N, int64_t ncodes,
               const int64_t* o_off, const int32_t* o_len, const int64_t* m_off,
               const int32_t* m_len, const int32_t* dmin, const int32_t* dmax,
-              int64_t arena_words, bool single_chunk) {
+              int64_t arena_words, bool single_chunk, int target_chunks = 0) {
   if (!prm || !prm->subst) return fail(ctx, BSQ_ERR_ARG, "params/subst is NULL");
   const int L = prm->alphabet_len;
   if (L < 1 || L > BSQ_MAX_L) return fail(ctx, BSQ_ERR_ARG, "alphabet_len must be in [1,32]");
@@ -250,16 +279,76 @@ int make_plan(bsq_ctx* ctx, Plan& P, const bsq_params* prm, int64_t N, int64_t n
   P.N = N;
   P.gosign = prm->go < 0 ? -1 : (prm->go > 0 ? 1 : 0);
   if (prm->mode == BSQ_STD_MODE) std_modes(prm->type, &P.bmode, &P.emode);
+  const int family = prm->mode == BSQ_STD_MODE ? 1 : 2;
+  const int btype = prm->type;
 
+  // ---- phase 1 (parallel): classify every pair like dptable_init would ----------
+  std::vector<PlanItem>& items = ctx->plan_items;
+  if ((int64_t)items.size() < N) items.resize((size_t)N);
+  struct Part { int64_t max_n = 0, max_m = 0, cells = 0; int bad = 0; };
+  std::vector<Part> parts(16);
+  parallel_for(N, [&](int t, int64_t i0, int64_t i1) {
+    Part pt;
+    int pn = -1, pm = -1, plo = 0, phi = 0;
+    PlanItem prev{};
+    for (int64_t i = i0; i < i1; i++) {
+      const int n = o_len[i], m = m_len[i];
+      if (n < 0 || m < 0 || o_off[i] < 0 || m_off[i] < 0 || o_off[i] + n > ncodes || m_off[i] + m > ncodes) { pt.bad = 1; continue; }
+      pt.max_n = std::max<int64_t>(pt.max_n, n);
+      pt.max_m = std::max<int64_t>(pt.max_m, m);
+      const int dlo = family == 2 ? dmin[i] : 0, dhi = family == 2 ? dmax[i] : 0;
+      if (n == pn && m == pm && dlo == plo && dhi == phi) {  // same shape as the previous pair
+        items[i] = prev;
+        if (prev.cfg >= 0) pt.cells += prev.cells;
+        continue;
+      }
+      PlanItem it{};
+      if (family == 1) {
+        it.cfg = pick_k1_cfg(n, m);
+        const int G = BSQ_K1_CFGS[it.cfg].G, K = BSQ_K1_CFGS[it.cfg].K, BW = G * K, WPL = (K + 7) / 8;
+        const int64_t passes = (m + BW) / BW;
+        it.words = passes * (int64_t)(n + 1) * G * WPL;
+        it.aux = passes > 1 ? n : 0;
+        it.cells = (int64_t)(n + 1) * (m + 1);
+      } else {
+        int lo = dlo, hi = dhi;
+        if (hi > n) hi = n;   // _pw_internals.c:29-36
+        if (lo < -m) lo = -m;
+        const int dend = n - m;
+        const int64_t W = (int64_t)hi - lo + 1;
+        if (btype == BSQ_B_GLOBAL && (dend > hi || dend < lo || (int64_t)hi * lo > 0)) it.cfg = -1 - BSQ_INIT_FAIL;
+        else if (W < 0) it.cfg = -1 - BSQ_INIT_FAIL;
+        else if (W == 0) it.cfg = -1 - BSQ_NO_ALIGNMENT;
+        else {
+          it.cfg = pick_k2_cfg((int)std::min<int64_t>(W, 1 << 30));
+          if (it.cfg < 0) it.cfg = -1 - BSQ_UNSUPPORTED;
+        }
+        if (it.cfg >= 0) {
+          it.lo = lo; it.hi = hi;
+          const int G = BSQ_K2_CFGS[it.cfg].G, C = BSQ_K2_CFGS[it.cfg].C, WPS = (C / 2 + 7) / 8;
+          const int smin = (lo <= 0 && hi >= 0) ? 0 : std::min(std::abs(lo), std::abs(hi));
+          const int sbase = smin - ((smin - lo) & 1);
+          const int dstar = std::max(lo, std::min(hi, dend));
+          const int s_end = 2 * std::min(n, m + dstar) - dstar;
+          const int64_t steps = (int64_t)(s_end - sbase + 1 + 1) / 2 * 2 + 2;
+          it.words = steps * G * WPS;
+          it.aux = sbase;
+          it.cells = count_cells(BSQ_BANDED_MODE, n, m, lo, hi);
+        }
+      }
+      items[i] = it;
+      if (it.cfg >= 0) pt.cells += it.cells;
+      prev = it; pn = n; pm = m; plo = dlo; phi = dhi;
+    }
+    parts[t] = pt;
+  });
   int64_t max_n = 0, max_m = 0;
-  for (int64_t i = 0; i < N; i++) {
-    const int n = o_len[i], m = m_len[i];
-    if (n < 0 || m < 0) return fail(ctx, BSQ_ERR_ARG, "negative sequence length");
-    if (o_off[i] < 0 || m_off[i] < 0 || o_off[i] + n > ncodes || m_off[i] + m > ncodes)
-      return fail(ctx, BSQ_ERR_ARG, "sequence range outside codes[]");
-    max_n = std::max<int64_t>(max_n, n);
-    max_m = std::max<int64_t>(max_m, m);
+  P.cells = 0;
+  for (const Part& pt : parts) {
+    if (pt.bad) return fail(ctx, BSQ_ERR_ARG, "negative length or sequence range outside codes[]");
+    max_n = std::max(max_n, pt.max_n); max_m = std::max(max_m, pt.max_m); P.cells += pt.cells;
   }
+
   bsq_params tmp = *prm;
   tmp.subst = P.subst.data();
   const bool i32ok = scores_int32_exact(&tmp, max_n, max_m);
@@ -275,105 +364,98 @@ int make_plan(bsq_ctx* ctx, Plan& P, const bsq_params* prm, int64_t N, int64_t n
     range_ok = (double)(max_n + max_m + 4) * maxabs < 2147483647.0;
   }
 
-  struct Item { int64_t idx; int64_t words; int cfg; int multipass_n; };
-  std::vector<Item> items;
-  items.reserve((size_t)N);
+  // ---- phase 2 (serial, O(N) light): order, chunk boundaries, prefix sums -----------
   P.overrides.clear();
-  P.cells = 0;
-  const int family = prm->mode == BSQ_STD_MODE ? 1 : 2;
-  std::vector<int32_t> cdmin, cdmax;
-  if (family == 2) { cdmin.resize((size_t)N); cdmax.resize((size_t)N); }
+  std::vector<int64_t>& order = ctx->plan_order;  // processing order -> caller index
+  order.clear();
+  order.reserve((size_t)N);
   bool uniform = true;
-  int64_t first_words = -1;
+  int64_t first_words = -1, tot_words = 0, maxw = 0;
   int first_cfg = -1;
   for (int64_t i = 0; i < N; i++) {
-    const int n = o_len[i], m = m_len[i];
+    const PlanItem& it = items[i];
     if (!range_ok) { P.overrides.push_back({i, BSQ_UNSUPPORTED}); continue; }
-    Item it;
-    it.idx = i;
-    it.multipass_n = 0;
-    if (family == 1) {
-      it.cfg = pick_k1_cfg(n, m);
-      const int G = BSQ_K1_CFGS[it.cfg].G, K = BSQ_K1_CFGS[it.cfg].K, BW = G * K, WPL = (K + 7) / 8;
-      const int64_t passes = (m + BW) / BW;
-      it.words = passes * (int64_t)(n + 1) * G * WPL;
-      if (passes > 1) it.multipass_n = n;
-      P.cells += (int64_t)(n + 1) * (m + 1);
-    } else {
-      int lo = dmin[i], hi = dmax[i];
-      if (hi > n) hi = n;   // _pw_internals.c:29-36
-      if (lo < -m) lo = -m;
-      const int dend = n - m;
-      if (prm->type == BSQ_B_GLOBAL && (dend > hi || dend < lo || (int64_t)hi * lo > 0)) {
-        P.overrides.push_back({i, BSQ_INIT_FAIL});
-        continue;
-      }
-      const int64_t W = (int64_t)hi - lo + 1;
-      if (W < 0) { P.overrides.push_back({i, BSQ_INIT_FAIL}); continue; }
-      if (W == 0) { P.overrides.push_back({i, BSQ_NO_ALIGNMENT}); continue; }
-      it.cfg = pick_k2_cfg((int)std::min<int64_t>(W, 1 << 30));
-      if (it.cfg < 0) { P.overrides.push_back({i, BSQ_UNSUPPORTED}); continue; }
-      cdmin[i] = lo; cdmax[i] = hi;
-      const int G = BSQ_K2_CFGS[it.cfg].G, C = BSQ_K2_CFGS[it.cfg].C, WPS = (C / 2 + 7) / 8;
-      const int smin = (lo <= 0 && hi >= 0) ? 0 : std::min(std::abs(lo), std::abs(hi));
-      const int sbase = smin - ((smin - lo) & 1);
-      int dstar = std::max(lo, std::min(hi, dend));
-      const int s_end = 2 * std::min(n, m + dstar) - dstar;
-      const int64_t steps = (int64_t)(s_end - sbase + 1 + 1) / 2 * 2 + 2;
-      it.words = steps * G * WPS;
-      it.multipass_n = sbase;  // reused: first step
-      P.cells += count_cells(BSQ_BANDED_MODE, n, m, lo, hi);
-    }
+    if (it.cfg < 0) { P.overrides.push_back({i, -1 - it.cfg}); continue; }
     if (first_words < 0) { first_words = it.words; first_cfg = it.cfg; }
     else if (it.words != first_words || it.cfg != first_cfg) uniform = false;
-    items.push_back(it);
+    tot_words += it.words;
+    maxw = std::max(maxw, it.words);
+    order.push_back(i);
+  }
+  if (!range_ok) P.cells = 0;
+  P.identity = uniform;
+  if (target_chunks > 1 && !single_chunk) {  // cut evenly so that copies overlap compute
+    int64_t per = std::max<int64_t>((tot_words + target_chunks - 1) / target_chunks, (int64_t)8 << 20);
+    per = std::max(per, maxw);
+    arena_words = std::min(arena_words, per);
   }
   // processing order: by kernel geometry, heaviest first inside a geometry
   if (!uniform)
-    std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) {
-      if (a.cfg != b.cfg) return a.cfg < b.cfg;
-      return a.words > b.words;
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+      if (items[a].cfg != items[b].cfg) return items[a].cfg < items[b].cfg;
+      return items[a].words > items[b].words;
     });
+  if (maxw > arena_words) return fail(ctx, BSQ_ERR_NOMEM, "a single pair's traceback table exceeds the device arena");
+  if (single_chunk && tot_words > arena_words)
+    return fail(ctx, BSQ_ERR_NOMEM, "batch does not fit the device arena in two-phase mode; use bsq_align_batch");
 
-  P.pairs.resize(items.size());
+  const int64_t E = (int64_t)order.size();
+  P.E = E;
+  if (!hpairs.ensure(sizeof(BsqPair) * (size_t)std::max<int64_t>(E, 1))) return fail(ctx, BSQ_ERR_NOMEM, "pinned host allocation failed");
+  P.pairs = hpairs.as<BsqPair>();
+  std::vector<int64_t>& ptr_off = ctx->plan_ptr_off;   // per processing slot
+  std::vector<int64_t>& slot_off = ctx->plan_slot_off;
+  if ((int64_t)ptr_off.size() < E + 1) { ptr_off.resize((size_t)E + 1); slot_off.resize((size_t)E + 1); }
   P.chunks.clear();
-  P.slot_bytes = 0;
   P.max_chunk_words = 0;
-  P.total_words = 0;
-  Chunk cur{0, 0, family, -1, 0, 0};
-  int64_t global_words = 0;
-  for (size_t e = 0; e < items.size(); e++) {
-    const Item& it = items[e];
-    const int64_t i = it.idx;
-    if (it.words > arena_words) {
-      return fail(ctx, BSQ_ERR_NOMEM, "a single pair's traceback table exceeds the device arena");
-    }
+  Chunk cur{0, 0, family, -1, 0, 0, 0, 0, 0};
+  int64_t global_words = 0, slot = 0;
+  for (int64_t e = 0; e < E; e++) {
+    const int64_t i = order[e];
+    const PlanItem& it = items[i];
     const bool new_chunk = cur.count > 0 && (it.cfg != cur.cfg || (!single_chunk && cur.ptr_words + it.words > arena_words));
-    if (single_chunk && global_words + it.words > arena_words)
-      return fail(ctx, BSQ_ERR_NOMEM, "batch does not fit the device arena in two-phase mode; use bsq_align_batch");
     if (new_chunk) {
+      cur.idx_hi = i;
       P.chunks.push_back(cur);
-      cur = Chunk{(int64_t)e, 0, family, -1, 0, 0};
+      cur = Chunk{e, 0, family, -1, 0, 0, i, 0, 0};
     }
     if (cur.count == 0) cur.cfg = it.cfg;
-    BsqPair& bp = P.pairs[e];
-    bp.o_off = o_off[i];
-    bp.m_off = m_off[i];
-    bp.n = o_len[i];
-    bp.m = m_len[i];
-    bp.ptr_off = single_chunk ? global_words : cur.ptr_words;
-    bp.tx_slot = P.slot_bytes;
-    bp.pad = (int)i;  // original index (N < 2^31 enforced by caller)
-    if (family == 2) { bp.dmin = cdmin[i]; bp.dmax = cdmax[i]; bp.s0 = it.multipass_n; }
-    else { bp.dmin = 0; bp.dmax = 0; bp.s0 = 0; cur.max_n_multipass = std::max(cur.max_n_multipass, it.multipass_n); }
-    P.slot_bytes += (int64_t)bp.n + bp.m;
+    ptr_off[e] = single_chunk ? global_words : cur.ptr_words;
+    slot_off[e] = slot;
+    slot += (int64_t)o_len[i] + m_len[i];
+    if (family == 1) cur.max_n_multipass = std::max(cur.max_n_multipass, it.aux);
+    cur.code_end = std::max<int64_t>(cur.code_end, std::max(o_off[i] + o_len[i], m_off[i] + m_len[i]));
     cur.ptr_words += it.words;
     global_words += it.words;
     cur.count++;
     P.max_chunk_words = std::max(P.max_chunk_words, cur.ptr_words);
   }
+  cur.idx_hi = N;
   if (cur.count > 0) P.chunks.push_back(cur);
+  if (!P.chunks.empty()) P.chunks.front().idx_lo = 0;
   P.total_words = global_words;
+  P.slot_bytes = slot;
+
+  // ---- phase 3 (parallel): the pair records, straight into pinned memory ------------
+  BsqPair* out = P.pairs;
+  parallel_for(E, [&](int, int64_t e0, int64_t e1) {
+    for (int64_t e = e0; e < e1; e++) {
+      const int64_t i = order[e];
+      const PlanItem& it = items[i];
+      BsqPair bp;
+      bp.o_off = o_off[i];
+      bp.m_off = m_off[i];
+      bp.ptr_off = ptr_off[e];
+      bp.tx_slot = slot_off[e];
+      bp.n = o_len[i];
+      bp.m = m_len[i];
+      bp.dmin = family == 2 ? it.lo : 0;
+      bp.dmax = family == 2 ? it.hi : 0;
+      bp.s0 = family == 2 ? it.aux : 0;
+      bp.pad = (int)i;  // original index (N < 2^31 enforced by caller)
+      out[e] = bp;
+    }
+  });
   return BSQ_SUCCESS;
 }
 
@@ -398,7 +480,7 @@ int64_t arena_budget_words(bsq_ctx* ctx, int64_t other_bytes) {
 
 // upload everything the kernels read; size the output arrays
 int stage_inputs(bsq_ctx* ctx, BufSet& B, Plan& P, const uint8_t* codes, int64_t ncodes, bool single_chunk) {
-  const int64_t N = P.N, E = (int64_t)P.pairs.size();
+  const int64_t N = P.N, E = (int64_t)P.E;
   const int L = P.prm.alphabet_len;
   bool ok = B.codes.ensure((size_t)ncodes + 16) && B.pairs.ensure(sizeof(BsqPair) * (size_t)std::max<int64_t>(E, 1)) &&
             B.score.ensure(8 * (size_t)N) && B.ex.ensure(4 * (size_t)N) && B.ey.ensure(4 * (size_t)N) &&
@@ -411,7 +493,7 @@ int stage_inputs(bsq_ctx* ctx, BufSet& B, Plan& P, const uint8_t* codes, int64_t
   if (ncodes > 0) BSQ_CK(ctx, cudaMemcpyAsync(B.codes.p, codes, (size_t)ncodes, cudaMemcpyHostToDevice, st));
   ctx->tm.h2d_bytes += ncodes;
   if (E > 0) {
-    BSQ_CK(ctx, cudaMemcpyAsync(B.pairs.p, P.pairs.data(), sizeof(BsqPair) * (size_t)E, cudaMemcpyHostToDevice, st));
+    BSQ_CK(ctx, cudaMemcpyAsync(B.pairs.p, P.pairs, sizeof(BsqPair) * (size_t)E, cudaMemcpyHostToDevice, st));
     ctx->tm.h2d_bytes += (int64_t)sizeof(BsqPair) * E;
   }
   if (P.dtype == BSQ_DTYPE_I32) {
@@ -500,7 +582,7 @@ int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci) {
   T.slots = B.slots.as<char>();
   // long pairs: one warp per pair walking shared-memory tiles; short pairs: one
   // thread per pair (there are enough of them to hide the load latency)
-  const long long avg_path = P.slot_bytes / std::max<long long>((long long)P.pairs.size(), 1);
+  const long long avg_path = P.slot_bytes / std::max<long long>((long long)P.E, 1);
   const char* force = getenv("BSQ_TRACE_KERNEL");  // test hook: "thread" / "warp"
   bool warp_walk = avg_path >= 1024;
   if (force && force[0] == 't') warp_walk = false;
@@ -520,14 +602,15 @@ int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci) {
 
 // scan txlen (original order) -> txoff, pack slots -> packed; all on device
 int pack_transcripts(bsq_ctx* ctx, BufSet& B, const Plan& P) {
-  const int64_t N = P.N, E = (int64_t)P.pairs.size();
+  const int64_t N = P.N, E = (int64_t)P.E;
   const int ntiles = (int)((N + BSQ_SCAN_TILE - 1) / BSQ_SCAN_TILE);
   if (!B.txoff.ensure(8 * (size_t)(N + 1)) || !B.tiles.ensure(8 * (size_t)std::max(ntiles, 1)) ||
       !B.packed.ensure((size_t)std::max<int64_t>(P.slot_bytes, 1)))
     return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (transcripts)");
   cudaStream_t st = ctx->st;
   BSQ_LAUNCH(bsq_scan_tile_sums, ntiles, 256, 0, st, (const int*)B.txlen.as<int>(), (int)N, B.tiles.as<long long>());
-  BSQ_LAUNCH(bsq_scan_tiles, 1, 256, 0, st, B.tiles.as<long long>(), ntiles, B.total.as<long long>());
+  BSQ_LAUNCH(bsq_scan_tiles, 1, 256, 0, st, B.tiles.as<long long>(), ntiles, (const long long*)nullptr,
+             B.total.as<long long>());
   BSQ_LAUNCH(bsq_scan_apply, ntiles, 256, 0, st, (const int*)B.txlen.as<int>(), (int)N,
              (const long long*)B.tiles.as<long long>(), B.txoff.as<long long>());
   ctx->tm.fill_launches += 3;
@@ -621,7 +704,10 @@ bsq_ctx* bsq_create(int device) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { g_err = "cudaGetDeviceProperties failed"; delete ctx; return nullptr; }
   ctx->sms = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) { g_err = "cudaStreamCreate failed"; delete ctx; return nullptr; }
+  if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking) != cudaSuccess) {
+    g_err = "cudaStreamCreate failed"; delete ctx; return nullptr;
+  }
   memset(&ctx->tm, 0, sizeof ctx->tm);
   const char* cap = getenv("BSQ_ARENA_CAP_BYTES");
   if (cap) ctx->arena_cap_bytes = (size_t)atoll(cap);
@@ -633,8 +719,10 @@ void bsq_destroy(bsq_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->st);
   ctx->bufs.release();
+  ctx->htotals.release();
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->st);
+  cudaStreamDestroy(ctx->st_copy);
   delete ctx;
 }
 
@@ -706,7 +794,7 @@ static int batch_upload(bsq_ctx* ctx, bsq_batch* b, bool own_bufs, bool single_c
   for (int64_t i = 0; i < npairs; i++) slot_guess += (int64_t)o_len[i] + m_len[i];
   const int64_t other = ncodes + 2 * slot_guess + npairs * (int64_t)(sizeof(BsqPair) + 48) + (64 << 20);
   const int64_t arena_words = arena_budget_words(ctx, other);
-  int rc = make_plan(ctx, b->plan, params, npairs, ncodes, o_off, o_len, m_off, m_len, dmin, dmax, arena_words, single_chunk);
+  int rc = make_plan(ctx, b->plan, b->B->hpairs, params, npairs, ncodes, o_off, o_len, m_off, m_len, dmin, dmax, arena_words, single_chunk);
   if (rc != BSQ_SUCCESS) return rc;
   b->single_chunk = single_chunk;
   return stage_inputs(ctx, *b->B, b->plan, codes, ncodes, single_chunk);
@@ -779,27 +867,207 @@ static int batch_fetch(bsq_batch* b, double* score, int32_t* end_x, int32_t* end
   return rc;
 }
 
+// One-shot path, pipelined: the sequence bytes start moving on the copy stream
+// before the host has planned anything; the batch is cut into ~8 chunks; the
+// compute stream runs fill -> traceback -> pack chunk after chunk while the copy
+// stream ships finished chunks back, so H2D, kernels and D2H overlap.
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, const uint8_t* codes,
                     int64_t ncodes, const int64_t* o_off, const int32_t* o_len, const int64_t* m_off,
                     const int32_t* m_len, const int32_t* dmin, const int32_t* dmax, double* score,
                     int32_t* end_x, int32_t* end_y, int32_t* start_x, int32_t* start_y, int32_t* status,
                     int64_t* tx_off, char* tx_buf, int64_t tx_cap, int64_t* tx_total) {
   if (!ctx) return BSQ_ERR_ARG;
+  const double t_call = now_ms();
   ctx->err.clear();
   int rc = check_inputs(ctx, npairs, codes, o_off, o_len, m_off, m_len);
   if (rc != BSQ_SUCCESS) return rc;
   if (!score || !status) return fail(ctx, BSQ_ERR_ARG, "score/status must not be NULL");
   BSQ_CK(ctx, cudaSetDevice(ctx->device));
   memset(&ctx->tm, 0, sizeof ctx->tm);
-  const bool want_trace = (tx_off && tx_buf) || start_x || start_y;
+  if (tx_total) *tx_total = 0;
+  if (npairs == 0) { if (tx_off) tx_off[0] = 0; return BSQ_SUCCESS; }
+  const bool want_tx = (tx_off && tx_buf);
+  const bool want_trace = want_tx || start_x || start_y;
+  BufSet& B = ctx->bufs;
+  cudaStream_t sc = ctx->st, sx = ctx->st_copy;
+  const size_t N = (size_t)npairs;
+
+  // ---- 0. sequence bytes: H2D in slices on the copy stream, one event per slice
+  const int NSL = 8;
+  size_t evi = 2;  // events 0/1 bracket the call on the compute stream
+  if (!B.codes.ensure((size_t)ncodes + 16)) return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (codes)");
+  cudaEvent_t ev_code[NSL];
+  int64_t slice_end[NSL];
+  const int64_t slice = ((ncodes + NSL - 1) / NSL + 255) / 256 * 256;
+  int nsl = 0;
+  for (int64_t off = 0; off < ncodes && nsl < NSL; off += slice, nsl++) {
+    const int64_t len = std::min<int64_t>(slice, ncodes - off);
+    BSQ_CK(ctx, cudaMemcpyAsync((char*)B.codes.p + off, codes + off, (size_t)len, cudaMemcpyHostToDevice, sx));
+    ev_code[nsl] = get_event(ctx, evi++);
+    BSQ_CK(ctx, cudaEventRecord(ev_code[nsl], sx));
+    slice_end[nsl] = off + len;
+  }
+  ctx->tm.h2d_bytes += ncodes;
+
+  // ---- 1. plan on the host while the bytes fly
+  const double t_plan = now_ms();
   bsq_batch b;
-  rc = batch_upload(ctx, &b, false, false, params, npairs, codes, ncodes, o_off, o_len, m_off, m_len, dmin, dmax);
-  if (rc == BSQ_SUCCESS) rc = batch_run(&b, true, want_trace);
-  const bsq_timing run_tm = ctx->tm;
-  if (rc == BSQ_SUCCESS) rc = batch_fetch(&b, score, end_x, end_y, start_x, start_y, status, tx_off, tx_buf, tx_cap, tx_total);
-  (void)run_tm;
-  if (rc != BSQ_SUCCESS) cudaStreamSynchronize(ctx->st);
-  return rc;
+  b.ctx = ctx; b.own_bufs = false; b.B = &B;
+  Plan& P = b.plan;
+  int64_t slot_guess = 0;
+  for (int64_t i = 0; i < npairs; i++) slot_guess += (int64_t)o_len[i] + m_len[i];
+  const int64_t other = ncodes + 2 * slot_guess + npairs * (int64_t)(sizeof(BsqPair) + 48) + (64 << 20);
+  rc = make_plan(ctx, P, B.hpairs, params, npairs, ncodes, o_off, o_len, m_off, m_len, dmin, dmax,
+                 arena_budget_words(ctx, other), false, (int)std::min<int64_t>(8, std::max<int64_t>(npairs / 16384, 1)));
+  if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(sx); return rc; }
+  ctx->tm.plan_ms = now_ms() - t_plan;
+  const int64_t E = (int64_t)P.E;
+  const int L = P.prm.alphabet_len;
+  const size_t NC = P.chunks.size();
+  const int ntiles_max = (int)((N + BSQ_SCAN_TILE - 1) / BSQ_SCAN_TILE) + (int)NC + 1;
+  bool ok = B.pairs.ensure(sizeof(BsqPair) * (size_t)std::max<int64_t>(E, 1)) && B.score.ensure(8 * N) &&
+            B.ex.ensure(4 * N) && B.ey.ensure(4 * N) && B.sx.ensure(4 * N) && B.sy.ensure(4 * N) &&
+            B.status.ensure(4 * N) && B.txlen.ensure(4 * N) && B.subst.ensure(8 * (size_t)L * L + 64) &&
+            B.counters.ensure(4 * (NC + 1)) && B.total.ensure(8 * (NC + 2)) &&
+            B.ptr.ensure(4 * (size_t)P.max_chunk_words + 64) && ctx->htotals.ensure(8 * (NC + 2));
+  if (ok && want_trace) ok = B.slots.ensure((size_t)std::max<int64_t>(P.slot_bytes, 1));
+  if (ok && want_tx) ok = B.txoff.ensure(8 * (N + 1)) && B.tiles.ensure(8 * (size_t)ntiles_max) &&
+                          B.packed.ensure((size_t)std::max<int64_t>(P.slot_bytes, 1));
+  if (!ok) { cudaStreamSynchronize(sx); return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed"); }
+
+  // ---- 2. pair records + score table on the copy stream
+  std::vector<int> subst_i;
+  if (E > 0) BSQ_CK(ctx, cudaMemcpyAsync(B.pairs.p, P.pairs, sizeof(BsqPair) * (size_t)E, cudaMemcpyHostToDevice, sx));
+  ctx->tm.h2d_bytes += (int64_t)sizeof(BsqPair) * E;
+  if (P.dtype == BSQ_DTYPE_I32) {
+    subst_i.resize((size_t)L * L);
+    for (int i = 0; i < L * L; i++) subst_i[i] = (int)P.subst[i];
+    BSQ_CK(ctx, cudaMemcpyAsync(B.subst.p, subst_i.data(), 4 * (size_t)L * L, cudaMemcpyHostToDevice, sx));
+  } else {
+    BSQ_CK(ctx, cudaMemcpyAsync(B.subst.p, P.subst.data(), 8 * (size_t)L * L, cudaMemcpyHostToDevice, sx));
+  }
+  cudaEvent_t ev_pairs = get_event(ctx, evi++);
+  BSQ_CK(ctx, cudaEventRecord(ev_pairs, sx));
+
+  // ---- 3. compute stream: chunk after chunk
+  cudaEvent_t t0 = get_event(ctx, 0), t1 = get_event(ctx, 1);
+  BSQ_CK(ctx, cudaEventRecord(t0, sc));
+  BSQ_CK(ctx, cudaMemsetAsync(B.counters.p, 0, 4 * (NC + 1), sc));
+  BSQ_CK(ctx, cudaMemsetAsync(B.txlen.p, 0, 4 * N, sc));
+  BSQ_CK(ctx, cudaMemsetAsync(B.total.p, 0, 8 * (NC + 2), sc));
+  BSQ_CK(ctx, cudaStreamWaitEvent(sc, ev_pairs, 0));
+  const bool per_chunk_out = P.identity;  // chunk c covers caller indices [idx_lo, idx_hi)
+  std::vector<cudaEvent_t> ev_done(NC);
+  std::vector<size_t> fill_ev0(NC);
+  int waited_slice = -1;
+  long long* totals = B.total.as<long long>();  // totals[c] = transcript bytes before chunk c
+  for (size_t ci = 0; ci < NC; ci++) {
+    const Chunk& ch = P.chunks[ci];
+    int need = 0;
+    while (need < nsl - 1 && slice_end[need] < ch.code_end) need++;
+    for (int sidx = waited_slice + 1; sidx <= need && sidx < nsl; sidx++) BSQ_CK(ctx, cudaStreamWaitEvent(sc, ev_code[sidx], 0));
+    waited_slice = std::max(waited_slice, need);
+    fill_ev0[ci] = evi;
+    rc = launch_fill(ctx, B, P, ci, &evi);
+    if (rc == BSQ_SUCCESS && want_trace) rc = launch_trace(ctx, B, P, ci);
+    if (rc == BSQ_SUCCESS && want_tx && per_chunk_out) {
+      const int64_t lo = ch.idx_lo, cnt = ch.idx_hi - ch.idx_lo;
+      const int nt = (int)((cnt + BSQ_SCAN_TILE - 1) / BSQ_SCAN_TILE);
+      long long* tiles = B.tiles.as<long long>() + (lo / BSQ_SCAN_TILE) + ci;  // disjoint scratch per chunk
+      BSQ_LAUNCH(bsq_scan_tile_sums, nt, 256, 0, sc, (const int*)(B.txlen.as<int>() + lo), (int)cnt, tiles);
+      BSQ_LAUNCH(bsq_scan_tiles, 1, 256, 0, sc, tiles, nt, (const long long*)(totals + ci), totals + ci + 1);
+      BSQ_LAUNCH(bsq_scan_apply, nt, 256, 0, sc, (const int*)(B.txlen.as<int>() + lo), (int)cnt,
+                 (const long long*)tiles, B.txoff.as<long long>() + lo);
+      const int grid = (int)((ch.count * 32 + 255) / 256);
+      BSQ_LAUNCH(bsq_pack_transcripts, grid, 256, 0, sc, (const BsqPair*)(B.pairs.as<BsqPair>() + ch.first),
+                 (int)ch.count, (const int*)B.txlen.as<int>(), (const long long*)B.txoff.as<long long>(),
+                 (const char*)B.slots.as<char>(), B.packed.as<char>());
+      ctx->tm.fill_launches += 4;
+      if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, BSQ_ERR_CUDA, "scan/pack launch failed");
+    }
+    if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(sc); cudaStreamSynchronize(sx); return rc; }
+    ev_done[ci] = get_event(ctx, evi++);
+    BSQ_CK(ctx, cudaEventRecord(ev_done[ci], sc));
+  }
+  if (want_tx && !per_chunk_out) {
+    rc = pack_transcripts(ctx, B, P);  // whole batch, caller order
+    if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(sc); cudaStreamSynchronize(sx); return rc; }
+  }
+  BSQ_CK(ctx, cudaEventRecord(t1, sc));
+
+  // ---- 4. copy stream: ship results back as chunks finish
+  long long* htot = ctx->htotals.as<long long>();
+  int rc_cap = BSQ_SUCCESS;
+  auto d2h_range = [&](int64_t lo, int64_t cnt) -> int {
+    const size_t n4 = 4 * (size_t)cnt, o4 = 4 * (size_t)lo;
+    BSQ_CK(ctx, cudaMemcpyAsync(score + lo, (char*)B.score.p + 8 * (size_t)lo, 8 * (size_t)cnt, cudaMemcpyDeviceToHost, sx));
+    if (end_x) BSQ_CK(ctx, cudaMemcpyAsync(end_x + lo, (char*)B.ex.p + o4, n4, cudaMemcpyDeviceToHost, sx));
+    if (end_y) BSQ_CK(ctx, cudaMemcpyAsync(end_y + lo, (char*)B.ey.p + o4, n4, cudaMemcpyDeviceToHost, sx));
+    if (want_trace && start_x) BSQ_CK(ctx, cudaMemcpyAsync(start_x + lo, (char*)B.sx.p + o4, n4, cudaMemcpyDeviceToHost, sx));
+    if (want_trace && start_y) BSQ_CK(ctx, cudaMemcpyAsync(start_y + lo, (char*)B.sy.p + o4, n4, cudaMemcpyDeviceToHost, sx));
+    BSQ_CK(ctx, cudaMemcpyAsync(status + lo, (char*)B.status.p + o4, n4, cudaMemcpyDeviceToHost, sx));
+    ctx->tm.d2h_bytes += cnt * (8 + 4 * (1 + (end_x != 0) + (end_y != 0) + (start_x != 0) + (start_y != 0)));
+    return BSQ_SUCCESS;
+  };
+  if (per_chunk_out) {
+    long long shipped = 0;
+    for (size_t ci = 0; ci < NC; ci++) {
+      const Chunk& ch = P.chunks[ci];
+      const int64_t lo = ch.idx_lo, cnt = ch.idx_hi - ch.idx_lo;
+      BSQ_CK(ctx, cudaStreamWaitEvent(sx, ev_done[ci], 0));
+      rc = d2h_range(lo, cnt);
+      if (rc != BSQ_SUCCESS) return rc;
+      if (want_tx) {
+        BSQ_CK(ctx, cudaMemcpyAsync(tx_off + lo, B.txoff.as<long long>() + lo, 8 * (size_t)cnt, cudaMemcpyDeviceToHost, sx));
+        BSQ_CK(ctx, cudaMemcpyAsync(htot + ci + 1, totals + ci + 1, 8, cudaMemcpyDeviceToHost, sx));
+        BSQ_CK(ctx, cudaStreamSynchronize(sx));  // later chunks are already queued on the compute stream
+        const long long upto = htot[ci + 1];
+        ctx->tm.d2h_bytes += 8 * cnt + 8;
+        if (upto > tx_cap) { rc_cap = BSQ_ERR_CAPACITY; }
+        else if (upto > shipped) {
+          BSQ_CK(ctx, cudaMemcpyAsync(tx_buf + shipped, B.packed.as<char>() + shipped, (size_t)(upto - shipped), cudaMemcpyDeviceToHost, sx));
+          ctx->tm.d2h_bytes += upto - shipped;
+        }
+        shipped = upto;
+      }
+    }
+    if (want_tx) { tx_off[N] = shipped; if (tx_total) *tx_total = shipped; }
+  } else {
+    BSQ_CK(ctx, cudaStreamWaitEvent(sx, t1, 0));
+    rc = d2h_range(0, npairs);
+    if (rc != BSQ_SUCCESS) return rc;
+    if (want_tx) {
+      BSQ_CK(ctx, cudaStreamSynchronize(sx));
+      cudaStream_t keep = ctx->st;
+      ctx->st = sx;  // fetch_transcripts issues on ctx->st
+      rc_cap = fetch_transcripts(ctx, B, P, tx_off, tx_buf, tx_cap, tx_total);
+      ctx->st = keep;
+      if (rc_cap != BSQ_SUCCESS && rc_cap != BSQ_ERR_CAPACITY) return rc_cap;
+    }
+  }
+  BSQ_CK(ctx, cudaStreamSynchronize(sx));
+  BSQ_CK(ctx, cudaStreamSynchronize(sc));
+  collect_timing(ctx, 2, t0, t1);
+  // only the (fill start, fill end) event pairs count as fill time
+  {
+    double fill = 0;
+    for (size_t ci = 0; ci < NC; ci++) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, ctx->events[fill_ev0[ci]], ctx->events[fill_ev0[ci] + 1]) == cudaSuccess) fill += ms;
+    }
+    ctx->tm.fill_ms = fill;
+  }
+  ctx->tm.cells = P.cells;
+  ctx->tm.dtype = P.dtype;
+  ctx->tm.chunks = (int32_t)NC;
+  apply_overrides(P, score, end_x, end_y, want_trace ? start_x : nullptr, want_trace ? start_y : nullptr, status);
+  if (rc_cap == BSQ_ERR_CAPACITY) return fail(ctx, BSQ_ERR_CAPACITY, "tx_buf too small for the batch's transcripts");
+  ctx->tm.call_ms = now_ms() - t_call;
+  return BSQ_SUCCESS;
 }
 
 int bsq_batch_upload(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, const uint8_t* codes,

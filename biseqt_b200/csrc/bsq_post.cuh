@@ -205,10 +205,11 @@ __global__ void __launch_bounds__(256) bsq_scan_tile_sums(const int* in, int n, 
   if (threadIdx.x == 0) tile_sums[blockIdx.x] = sh[0];
 }
 // single block: tile_sums -> exclusive prefix (+ *base), writes grand total back to *base_total
-__global__ void __launch_bounds__(256) bsq_scan_tiles(long long* tile_sums, int ntiles, long long* total_out) {
+__global__ void __launch_bounds__(256) bsq_scan_tiles(long long* tile_sums, int ntiles, const long long* base_in,
+                                                      long long* total_out) {
   __shared__ long long carry;
   __shared__ long long sh[256];
-  if (threadIdx.x == 0) carry = 0;
+  if (threadIdx.x == 0) carry = base_in ? *base_in : 0;
   __syncthreads();
   for (int base = 0; base < ntiles; base += 256) {
     const int i = base + threadIdx.x;

@@ -99,6 +99,8 @@ typedef struct {
   int64_t ptr_bytes;     /* bytes of traceback-pointer tables written to HBM     */
   int32_t dtype;         /* BSQ_DTYPE_* actually used                            */
   int32_t chunks;
+  double plan_ms;        /* host: classification + ordering + chunking (wall clock) */
+  double call_ms;        /* host: whole call, wall clock                            */
 } bsq_timing;
 
 int bsq_device_count(void);

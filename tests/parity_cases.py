@@ -224,5 +224,17 @@ def run_chunked(make_engine, seed):
         probs = make_batch(rng, 30, 1, 2, 300, 400, family=2, gomode=0, band=30)
         check_batch(eng, probs)
         assert eng.timing()['chunks'] > 1
+        # equal-sized pairs keep the caller's order: results leave chunk by chunk
+        S, go, ge = score_family(rng, 4, 1, -1)
+        probs = []
+        for i in range(70):
+            o = rng.integers(0, 4, size=120).astype(np.uint8)
+            t = o.copy()
+            t[rng.integers(0, 120, size=12)] = rng.integers(0, 4, size=12)
+            if i % 9 == 0:
+                t = rng.integers(0, 4, size=120).astype(np.uint8)
+            probs.append(dict(origin=o, mutant=t, subst=S, go=go, ge=ge, mode=0, type=1, diag_range=None))
+        check_batch(eng, probs)
+        assert eng.timing()['chunks'] > 2
     finally:
         eng.close()

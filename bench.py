@@ -33,7 +33,7 @@ if ROOT not in sys.path:
 
 import bench_workloads as bw  # noqa: E402
 
-WORKLOAD_PAIRS = {'c2_int': 1000000, 'c2_logodds': 1000000, 'c3_int': 4096, 'c3_logodds': 4096,
+WORKLOAD_PAIRS = {'c2_int': 1000000, 'c2_logodds': 1000000, 'c3_int': 16384, 'c3_logodds': 16384,
                   'c4_int': 512, 'c1': 1}
 
 
@@ -164,7 +164,7 @@ def cpu_reference_run(w, pairs_per_core, cores=None, pool=None):
             'pairs_per_s': sum(r[2] / r[1] for r in res if r[1] > 0), 'wall_s': wall, 'cells': cells}
 
 
-def run_reference_arm(args, rank, world):
+def run_reference_arm(args, rank, world, emit):
     if rank != 0:
         return
     kind = args.workload
@@ -193,7 +193,7 @@ def run_reference_arm(args, rank, world):
         'pairs_per_s': last['pairs_per_s'],
         'e2e': {'value': val, 'unit': 'GCUPS', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------
@@ -300,9 +300,21 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    # exactly ONE line goes to stdout (the JSON); libraries that print there
+    # (NCCL's version banner, pwlib's printf) are routed to stderr meanwhile
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj))
+        sys.stdout.flush()
+        os.dup2(2, 1)
 
     if args.impl == 'reference':
-        run_reference_arm(args, rank, world)
+        run_reference_arm(args, rank, world, emit)
         return
 
     from biseqt_b200 import batch
@@ -395,7 +407,8 @@ def main():
                               'fill_only_gcups': m2['cells'] * st2 / (m2['fill_ms'] * 1e-3) / 1e9,
                               'e2e_gcups': m2['cells'] * st2 / m2['e2e_s'] / 1e9,
                               'roofline_frac': ach / pk if pk else None, 'ops_per_cell': opc2,
-                              'status_ok_fraction': m2['ok_frac'], 'chunks': m2['chunks']}
+                              'status_ok_fraction': m2['ok_frac'], 'chunks': m2['chunks'],
+                              'e2e_breakdown_ms': m2.get('e2e_breakdown_ms')}
             except Exception as e:
                 extras[k2] = {'error': str(e)}
         line['other_workloads'] = extras
@@ -408,7 +421,7 @@ def main():
         except Exception as e:
             line['cpu_baseline'] = {'error': str(e)}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     eng.close()
     if _dist is not None:
         _dist.barrier()

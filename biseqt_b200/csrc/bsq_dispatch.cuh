@@ -54,9 +54,10 @@ static int bsq_k2_op_t(int cfg, int blocal, int gos, int op, int grid, cudaStrea
   switch (cfg) {
     case 0: return bsq_k2_variant<S, 8, 8>(blocal, gos, op, grid, st, A);
     case 1: return bsq_k2_variant<S, 8, 18>(blocal, gos, op, grid, st, A);
-    case 2: return bsq_k2_variant<S, 16, 16>(blocal, gos, op, grid, st, A);
-    case 3: return bsq_k2_variant<S, 32, 16>(blocal, gos, op, grid, st, A);
-    case 4: return bsq_k2_variant<S, 32, 32>(blocal, gos, op, grid, st, A);
+    case 2: return bsq_k2_variant<S, 16, 10>(blocal, gos, op, grid, st, A);
+    case 3: return bsq_k2_variant<S, 16, 16>(blocal, gos, op, grid, st, A);
+    case 4: return bsq_k2_variant<S, 32, 16>(blocal, gos, op, grid, st, A);
+    case 5: return bsq_k2_variant<S, 32, 32>(blocal, gos, op, grid, st, A);
   }
   return -1;
 }

@@ -228,10 +228,25 @@ int pick_k1_cfg(int n, int m) {
   return best;
 }
 
-int pick_k2_cfg(int W) {
-  for (int c = 0; c < BSQ_K2_NCFG; c++)
-    if (BSQ_K2_CFGS[c].G * BSQ_K2_CFGS[c].C >= W) return c;
-  return -1;
+// Geometry for a band of W diagonals: least estimated time = lane-cells / relative
+// speed.  Measured on B200 (profiles/r01_k2_geometry.txt): for doubles the
+// register footprint of C >= 16 diagonals per lane costs occupancy, so lanes with
+// fewer diagonals win even at lower lane efficiency; int32 prefers tight fits.
+int pick_k2_cfg(int W, bool f64) {
+  static const int forced = getenv("BSQ_K2_CFG") ? atoi(getenv("BSQ_K2_CFG")) : -1;  // tuning hook
+  if (forced >= 0 && forced < BSQ_K2_NCFG && BSQ_K2_CFGS[forced].G * BSQ_K2_CFGS[forced].C >= W) return forced;
+  int best = -1;
+  double bestc = 1e300;
+  for (int c = 0; c < BSQ_K2_NCFG; c++) {
+    const int G = BSQ_K2_CFGS[c].G, C = BSQ_K2_CFGS[c].C, cap = G * C;
+    if (cap < W) continue;
+    double speed = 1.0;
+    if (f64) speed = C <= 10 ? 1.0 : (C <= 16 ? 0.85 : 0.78);
+    else speed = C <= 10 ? 0.97 : 1.0;
+    const double cost = cap / speed;
+    if (cost < bestc) { bestc = cost; best = c; }
+  }
+  return best;
 }
 
 int k1_op(int dtype, int cfg, int ball, int eall, int gos, int op, int grid, cudaStream_t st, const BsqFillArgs* A) {
@@ -282,6 +297,16 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   const int family = prm->mode == BSQ_STD_MODE ? 1 : 2;
   const int btype = prm->type;
 
+  // geometry depends on the arithmetic; decide it up front from the scores alone (lengths
+  // only matter for the overflow bound, checked again below with the real maxima)
+  bool f64_geom = true;
+  {
+    bsq_params t0 = *prm;
+    t0.subst = P.subst.data();
+    int64_t mn = 0, mm = 0;
+    for (int64_t i = 0; i < N; i++) { mn = std::max<int64_t>(mn, o_len[i]); mm = std::max<int64_t>(mm, m_len[i]); }
+    f64_geom = (prm->dtype == BSQ_DTYPE_F64) || !(prm->dtype == BSQ_DTYPE_I32 || scores_int32_exact(&t0, mn, mm));
+  }
   // ---- phase 1 (parallel): classify every pair like dptable_init would ----------
   std::vector<PlanItem>& items = ctx->plan_items;
   if ((int64_t)items.size() < N) items.resize((size_t)N);
@@ -320,7 +345,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
         else if (W < 0) it.cfg = -1 - BSQ_INIT_FAIL;
         else if (W == 0) it.cfg = -1 - BSQ_NO_ALIGNMENT;
         else {
-          it.cfg = pick_k2_cfg((int)std::min<int64_t>(W, 1 << 30));
+          it.cfg = pick_k2_cfg((int)std::min<int64_t>(W, 1 << 30), f64_geom);
           if (it.cfg < 0) it.cfg = -1 - BSQ_UNSUPPORTED;
         }
         if (it.cfg >= 0) {

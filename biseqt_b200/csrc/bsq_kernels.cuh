@@ -369,17 +369,15 @@ __global__ void __launch_bounds__(128) bsq_k1_fill(const BsqFillArgs A) {
 //   replaces: dptable_solve's fill loop pw.c:59-110 in (d,a) coordinates
 //   (_pw_internals.c:87-153) + _banded_find_optimal (:364-414)
 // ===========================================================================
-template <int C>
-__device__ __forceinline__ uint32_t bsq_k2_nib(const uint32_t (&pw)[(C / 2 + 7) / 8], int c) {
-  return (pw[(c >> 1) >> 3] >> (4 * ((c >> 1) & 7))) & 0xFu;  // c is a compile-time constant
-}
+// State per owned diagonal c: H[c] (latest cell), fD[c] / fI[c] = open/extend flag
+// words (S::flag) of the D candidate of the cell below it / the I candidate of the
+// cell right of it -- i.e. what diagonals c+1 and c-1 will need one step later.
 
 // careful step: any cell may be off-table, on an edge, or a padding diagonal
 template <class S, int C, bool BLOCAL, int GOS, int Q>
 __device__ __forceinline__ void bsq_k2_step_careful(
-    int btype, typename S::T (&H)[C], typename S::T (&best)[BLOCAL ? C : 1],
-    int (&bests)[BLOCAL ? C : 1], uint32_t (&pwprev)[(C / 2 + 7) / 8],
-    typename S::T edgeH, uint32_t edgeNib, const typename S::T* s_sub, int L,
+    int btype, typename S::T (&H)[C], int (&fD)[C], int (&fI)[C], typename S::T (&best)[BLOCAL ? C : 1],
+    int (&bests)[BLOCAL ? C : 1], typename S::T edgeH, int edgeF, const typename S::T* s_sub, int L,
     const uint8_t* oseq, const uint8_t* mseq, int n, int m, int s, int d0, int nreal,
     typename S::T go, typename S::T ge, uint32_t* pout) {
   typedef typename S::T T;
@@ -391,8 +389,6 @@ __device__ __forceinline__ void bsq_k2_step_careful(
   for (int w = 0; w < WPS; w++) cur[w] = 0u;
   // Q == 0: cells c = 0,2,..; c = 0 takes (x-1,y) from the lane below (edge*)
   // Q == 1: cells c = 1,3,..; c = C-1 takes (x,y-1) from the lane above (edge*)
-  T newH[HC];
-  bool commit[HC];
 #pragma unroll
   for (int hc = 0; hc < HC; hc++) {
     const int c = 2 * hc + Q;
@@ -400,11 +396,11 @@ __device__ __forceinline__ void bsq_k2_step_careful(
     const int x = (s + d) >> 1, y = (s - d) >> 1;
     const bool intab = (c < nreal) && x >= 0 && y >= 0 && x <= n && y <= m;
     T up, left;
-    uint32_t upnib, leftnib;
-    if (c == 0) { up = edgeH; upnib = edgeNib; }
-    else { up = H[c - 1]; upnib = bsq_k2_nib<C>(pwprev, c - 1); }
-    if (c == C - 1) { left = edgeH; leftnib = edgeNib; }
-    else { left = H[c + 1]; leftnib = bsq_k2_nib<C>(pwprev, c + 1); }
+    int gD, gI;
+    if (c == 0) { up = edgeH; gD = edgeF; }
+    else { up = H[c - 1]; gD = fD[c - 1]; }
+    if (c == C - 1) { left = edgeH; gI = edgeF; }
+    else { left = H[c + 1]; gI = fI[c + 1]; }
     const T diag = H[c];
     const int o = (x >= 1 && x <= n) ? (int)oseq[x - 1] : 0;
     const int mm = (y >= 1 && y <= m) ? (int)mseq[y - 1] : 0;
@@ -415,21 +411,21 @@ __device__ __forceinline__ void bsq_k2_step_careful(
     else ballow = (x == 0 && y == 0);
     const T bval = (intab && ballow) ? (T)0 : NINF;
     T h;
-    uint32_t mk;
-    bsq_cell<S, GOS, true>(up, bsq_extends<GOS>(upnib, BSQ_MD), left,
-                           bsq_extends<GOS>(leftnib, BSQ_MI), diag, sig, bval, go, ge, h, mk);
-    newH[hc] = h;
-    commit[hc] = intab;
+    bool eB, eD, eI, eM;
+    bsq_cell2<S, GOS, true>(up, gD, left, gI, diag, sig, bval, go, ge, h, eB, eD, eI, eM);
+    const uint32_t mk = (eB ? BSQ_MB : 0u) | (eD ? BSQ_MD : 0u) | (eI ? BSQ_MI : 0u) | (eM ? BSQ_MM : 0u);
     cur[hc >> 3] |= mk << (4 * (hc & 7));
-    if (BLOCAL) {  // :397-406 restricted to one diagonal (a ascends with s)
-      if (intab && h > best[c]) { best[c] = h; bests[c] = s; }
+    if (intab) {  // cells of one step never read each other, so commit in place
+      H[c] = h;
+      fD[c] = bsq_gapflag<S, GOS>(eD, eB, eI, eM);
+      fI[c] = bsq_gapflag<S, GOS>(eI, eB, eD, eM);
+      if (BLOCAL) {  // :397-406 restricted to one diagonal (a ascends with s)
+        if (h > best[c]) { best[c] = h; bests[c] = s; }
+      }
     }
   }
 #pragma unroll
-  for (int hc = 0; hc < HC; hc++)
-    if (commit[hc]) H[2 * hc + Q] = newH[hc];
-#pragma unroll
-  for (int w = 0; w < WPS; w++) { pout[w] = cur[w]; pwprev[w] = cur[w]; }
+  for (int w = 0; w < WPS; w++) pout[w] = cur[w];
 }
 
 // interior step: every band cell is a regular cell (x >= 1, y >= 1, in table).
@@ -438,8 +434,8 @@ __device__ __forceinline__ void bsq_k2_step_careful(
 // the band in this lane (or -1): it is reset to -inf so the band edge stays shut.
 template <class S, int C, bool BLOCAL, int GOS, int Q, bool PACKED>
 __device__ __forceinline__ void bsq_k2_step_fast(
-    typename S::T (&H)[C], typename S::T (&best)[BLOCAL ? C : 1], int (&bests)[BLOCAL ? C : 1],
-    uint32_t (&pwprev)[(C / 2 + 7) / 8], typename S::T edgeH, uint32_t edgeNib,
+    typename S::T (&H)[C], int (&fD)[C], int (&fI)[C], typename S::T (&best)[BLOCAL ? C : 1],
+    int (&bests)[BLOCAL ? C : 1], typename S::T edgeH, int edgeF,
     const typename S::T* s_sub, int L, unsigned long long comb, const uint8_t* oseq,
     const uint8_t* mseq, int s, int d0, int fixc, typename S::T go, typename S::T ge,
     uint32_t* pout) {
@@ -451,16 +447,15 @@ __device__ __forceinline__ void bsq_k2_step_fast(
 #pragma unroll
   for (int w = 0; w < WPS; w++) cur[w] = 0u;
   const uint32_t comb_lo = (uint32_t)comb, comb_hi = (uint32_t)(comb >> 32);
-  T newH[HC];
 #pragma unroll
   for (int hc = 0; hc < HC; hc++) {
     const int c = 2 * hc + Q;
     T up, left;
-    uint32_t upnib, leftnib;
-    if (c == 0) { up = edgeH; upnib = edgeNib; }
-    else { up = H[c - 1]; upnib = bsq_k2_nib<C>(pwprev, c - 1); }
-    if (c == C - 1) { left = edgeH; leftnib = edgeNib; }
-    else { left = H[c + 1]; leftnib = bsq_k2_nib<C>(pwprev, c + 1); }
+    int gD, gI;
+    if (c == 0) { up = edgeH; gD = edgeF; }
+    else { up = H[c - 1]; gD = fD[c - 1]; }
+    if (c == C - 1) { left = edgeH; gI = edgeF; }
+    else { left = H[c + 1]; gI = fI[c + 1]; }
     const T diag = H[c];
     T sig;
     if (PACKED) {
@@ -474,17 +469,21 @@ __device__ __forceinline__ void bsq_k2_step_fast(
       sig = s_sub[(int)oseq[x - 1] * L + (int)mseq[y - 1]];
     }
     T h;
-    uint32_t mk;
-    bsq_cell<S, GOS, BLOCAL>(up, bsq_extends<GOS>(upnib, BSQ_MD), left,
-                             bsq_extends<GOS>(leftnib, BSQ_MI), diag, sig, (T)0, go, ge, h, mk);
-    newH[hc] = h;
-    cur[hc >> 3] |= mk << (4 * (hc & 7));
+    bool eB, eD, eI, eM;
+    bsq_cell2<S, GOS, BLOCAL>(up, gD, left, gI, diag, sig, (T)0, go, ge, h, eB, eD, eI, eM);
+    uint32_t w = cur[hc >> 3];
+    if (BLOCAL) { if (eB) w += BSQ_MB << (4 * (hc & 7)); }
+    if (eD) w += BSQ_MD << (4 * (hc & 7));
+    if (eI) w += BSQ_MI << (4 * (hc & 7));
+    if (eM) w += BSQ_MM << (4 * (hc & 7));
+    cur[hc >> 3] = w;
+    H[c] = h;
+    fD[c] = bsq_gapflag<S, GOS>(eD, eB, eI, eM);
+    fI[c] = bsq_gapflag<S, GOS>(eI, eB, eD, eM);
     if (BLOCAL) {
       if (h > best[c]) { best[c] = h; bests[c] = s; }
     }
   }
-#pragma unroll
-  for (int hc = 0; hc < HC; hc++) H[2 * hc + Q] = newH[hc];
   if (fixc >= 0 && (fixc & 1) == Q) {  // one lane per group, every other step
     const T NINF = S::ninf();
     switch (fixc >> 1) {
@@ -495,7 +494,7 @@ __device__ __forceinline__ void bsq_k2_step_fast(
     }
   }
 #pragma unroll
-  for (int w = 0; w < WPS; w++) { pout[w] = cur[w]; pwprev[w] = cur[w]; }
+  for (int w = 0; w < WPS; w++) pout[w] = cur[w];
 }
 
 template <class S, int G, int C, bool BLOCAL, int GOS>
@@ -527,6 +526,9 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
   const T go = S::go(A), ge = S::ge(A);
   const int btype = A.btype;
 
+  // Each group runs its own loop over pairs (group-mask shuffles only).  A
+  // warp-synchronous variant that votes on careful/interior per warp was measured
+  // slower on B200 (more gated steps, more live state), so groups are independent.
   for (;;) {
     int p = 0;
     if (l == 0) p = atomicAdd(A.counter, 1);
@@ -553,37 +555,32 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
     const int si_hi = e_lo < e_hi ? e_lo : e_hi;
     int sA = s0;
     if (si_lo > s0) sA = s0 + 2 * ((si_lo - s0 + 1) / 2);
-    // last pair start s with s + 1 <= si_hi and s == s0 (mod 2)
-    int sB = si_hi - 1;
+    int sB = si_hi - 1;                // last pair start s with s + 1 <= si_hi, s == s0 (mod 2)
     if (((sB - s0) & 1) != 0) sB -= 1;
 
     T H[C];
+    int fD[C], fI[C];
     T best[NB];
     int bests[NB];
-    uint32_t pwprev[WPS];
 #pragma unroll
-    for (int c = 0; c < C; c++) H[c] = NINF;
+    for (int c = 0; c < C; c++) { H[c] = NINF; fD[c] = 0; fI[c] = 0; }
 #pragma unroll
     for (int c = 0; c < NB; c++) { best[c] = NINF; bests[c] = 0; }
-#pragma unroll
-    for (int w = 0; w < WPS; w++) pwprev[w] = 0u;
     uint32_t* prow = A.ptr + P.ptr_off + (long long)l * WPS;
 
     int s = s0;
 #define BSQ_K2_CAREFUL_PAIR()                                                                         \
     {                                                                                                 \
       T eH = __shfl_up_sync(gmask, H[C - 1], 1, G);                                                   \
-      uint32_t eW = __shfl_up_sync(gmask, pwprev[WPS - 1], 1, G);                                     \
-      uint32_t eNib = (eW >> (4 * ((HC - 1) & 7))) & 0xFu;                                            \
-      if (l == 0) { eH = NINF; eNib = 0u; }                                                           \
-      bsq_k2_step_careful<S, C, BLOCAL, GOS, 0>(btype, H, best, bests, pwprev, eH, eNib, s_sub, Lt,   \
+      int eF = __shfl_up_sync(gmask, fD[C - 1], 1, G);                                                \
+      if (l == 0) { eH = NINF; eF = 0; }                                                              \
+      bsq_k2_step_careful<S, C, BLOCAL, GOS, 0>(btype, H, fD, fI, best, bests, eH, eF, s_sub, Lt,     \
                                                 oseq, mseq, n, m, s, d0, nreal, go, ge,               \
                                                 prow + (long long)(s - s0) * (G * WPS));              \
       eH = __shfl_down_sync(gmask, H[0], 1, G);                                                       \
-      eW = __shfl_down_sync(gmask, pwprev[0], 1, G);                                                  \
-      eNib = eW & 0xFu;                                                                               \
-      if (l == G - 1) { eH = NINF; eNib = 0u; }                                                       \
-      bsq_k2_step_careful<S, C, BLOCAL, GOS, 1>(btype, H, best, bests, pwprev, eH, eNib, s_sub, Lt,   \
+      eF = __shfl_down_sync(gmask, fI[0], 1, G);                                                      \
+      if (l == G - 1) { eH = NINF; eF = 0; }                                                          \
+      bsq_k2_step_careful<S, C, BLOCAL, GOS, 1>(btype, H, fD, fI, best, bests, eH, eF, s_sub, Lt,     \
                                                 oseq, mseq, n, m, s + 1, d0, nreal, go, ge,           \
                                                 prow + (long long)(s + 1 - s0) * (G * WPS));          \
     }
@@ -591,10 +588,10 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
 
     if (s <= sB) {
       // letter windows for the pair of steps (s, s+1); cell hc of the even step is
-      // (x0 + hc, y0 - hc), of the odd step (x0 + 1 + hc, y0 - hc)
-      int x0 = (s + d0) >> 1, y0 = (s - d0) >> 1;
+      // (x0 + hc, y0 - hc), of the odd step (x0 + 1 + hc, y0 - hc).
       // nibble j of ow: 4*o[x0+j-1], of mw: m[y0-j-1] (j < HC); onx: 4*o[x0+HC-1],
       // the nibble that slides into ow for the odd step
+      int x0 = (s + d0) >> 1, y0 = (s - d0) >> 1;
       unsigned long long ow = 0ull, mw = 0ull;
       unsigned onx = 0u;
       if (packed) {
@@ -623,30 +620,26 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
           if ((unsigned)yi < (unsigned)m) nm = mseq[yi];
         }
         const unsigned long long ow_odd = (ow >> 4) | ((unsigned long long)onx << (4 * (HC - 1)));
+        uint32_t* pe = prow + (long long)(s - s0) * (G * WPS);
+        uint32_t* po = pe + G * WPS;
         T eH = __shfl_up_sync(gmask, H[C - 1], 1, G);
-        uint32_t eW = __shfl_up_sync(gmask, pwprev[WPS - 1], 1, G);
-        uint32_t eNib = (eW >> (4 * ((HC - 1) & 7))) & 0xFu;
-        if (l == 0) { eH = NINF; eNib = 0u; }
+        int eF = __shfl_up_sync(gmask, fD[C - 1], 1, G);
+        if (l == 0) { eH = NINF; eF = 0; }
         if (packed)
-          bsq_k2_step_fast<S, C, BLOCAL, GOS, 0, true>(H, best, bests, pwprev, eH, eNib, s_sub, Lt, ow | mw, oseq,
-                                                       mseq, s, d0, fixc, go, ge,
-                                                       prow + (long long)(s - s0) * (G * WPS));
+          bsq_k2_step_fast<S, C, BLOCAL, GOS, 0, true>(H, fD, fI, best, bests, eH, eF, s_sub, Lt, ow | mw, oseq,
+                                                       mseq, s, d0, fixc, go, ge, pe);
         else
-          bsq_k2_step_fast<S, C, BLOCAL, GOS, 0, false>(H, best, bests, pwprev, eH, eNib, s_sub, Lt, 0ull, oseq,
-                                                        mseq, s, d0, fixc, go, ge,
-                                                        prow + (long long)(s - s0) * (G * WPS));
+          bsq_k2_step_fast<S, C, BLOCAL, GOS, 0, false>(H, fD, fI, best, bests, eH, eF, s_sub, Lt, 0ull, oseq,
+                                                        mseq, s, d0, fixc, go, ge, pe);
         eH = __shfl_down_sync(gmask, H[0], 1, G);
-        eW = __shfl_down_sync(gmask, pwprev[0], 1, G);
-        eNib = eW & 0xFu;
-        if (l == G - 1) { eH = NINF; eNib = 0u; }
+        eF = __shfl_down_sync(gmask, fI[0], 1, G);
+        if (l == G - 1) { eH = NINF; eF = 0; }
         if (packed)
-          bsq_k2_step_fast<S, C, BLOCAL, GOS, 1, true>(H, best, bests, pwprev, eH, eNib, s_sub, Lt, ow_odd | mw,
-                                                       oseq, mseq, s + 1, d0, fixc, go, ge,
-                                                       prow + (long long)(s + 1 - s0) * (G * WPS));
+          bsq_k2_step_fast<S, C, BLOCAL, GOS, 1, true>(H, fD, fI, best, bests, eH, eF, s_sub, Lt, ow_odd | mw,
+                                                       oseq, mseq, s + 1, d0, fixc, go, ge, po);
         else
-          bsq_k2_step_fast<S, C, BLOCAL, GOS, 1, false>(H, best, bests, pwprev, eH, eNib, s_sub, Lt, 0ull, oseq,
-                                                        mseq, s + 1, d0, fixc, go, ge,
-                                                        prow + (long long)(s + 1 - s0) * (G * WPS));
+          bsq_k2_step_fast<S, C, BLOCAL, GOS, 1, false>(H, fD, fI, best, bests, eH, eF, s_sub, Lt, 0ull, oseq,
+                                                        mseq, s + 1, d0, fixc, go, ge, po);
         if (packed) {
           ow = ow_odd;
           onx = no << 2;

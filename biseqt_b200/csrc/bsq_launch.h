@@ -11,9 +11,9 @@ struct BsqK1Cfg { int G, K; };   // STD: G lanes x K columns per pass
 struct BsqK2Cfg { int G, C; };   // BANDED: G lanes x C diagonals
 
 #define BSQ_K1_NCFG 3
-#define BSQ_K2_NCFG 5
+#define BSQ_K2_NCFG 6
 static const BsqK1Cfg BSQ_K1_CFGS[BSQ_K1_NCFG] = {{8, 19}, {16, 16}, {32, 16}};
-static const BsqK2Cfg BSQ_K2_CFGS[BSQ_K2_NCFG] = {{8, 8}, {8, 18}, {16, 16}, {32, 16}, {32, 32}};
+static const BsqK2Cfg BSQ_K2_CFGS[BSQ_K2_NCFG] = {{8, 8}, {8, 18}, {16, 10}, {16, 16}, {32, 16}, {32, 32}};
 
 enum { BSQ_OP_OCCUPANCY = 0, BSQ_OP_LAUNCH = 1 };
 

@@ -107,6 +107,7 @@ struct Plan {
   int64_t max_chunk_words = 0;
   int64_t total_words = 0;
   bool identity = false;  // processing order == caller order (no sort was needed)
+  int64_t half_words = 0; // > 0: two arena halves, chunk c uses half (c & 1) so trace(c) overlaps fill(c+1)
 };
 
 }  // namespace
@@ -116,6 +117,7 @@ struct bsq_ctx {
   int sms = 1;
   cudaStream_t st = nullptr;       // compute
   cudaStream_t st_copy = nullptr;  // H2D / D2H, so copies overlap kernels
+  cudaStream_t st_trace = nullptr; // traceback + packing of chunk c while chunk c+1 fills
   PinBuf htotals;                  // pinned: running transcript totals per chunk
   std::vector<PlanItem> plan_items;  // planner scratch, kept across calls (no page faults)
   std::vector<int64_t> plan_order, plan_ptr_off, plan_slot_off;
@@ -135,6 +137,19 @@ struct bsq_batch {
   bool single_chunk = false;  // all pointer tables resident at once
   bool filled = false, traced = false;
 };
+
+// How many chunks to cut a batch into so that traceback/copies of one chunk overlap the
+// fill of the next.  Only short pairs profit: their chunks still hold many waves of work,
+// and their thread-per-pair walk fits beside the fill; long pairs are cut by capacity only.
+static int overlap_chunks(int64_t npairs, const int32_t* o_len, const int32_t* m_len) {
+  if (npairs < 32768) return 1;
+  int64_t tot = 0;
+  const int64_t step = std::max<int64_t>(npairs / 1024, 1);
+  int64_t cnt = 0;
+  for (int64_t i = 0; i < npairs; i += step) { tot += (int64_t)o_len[i] + m_len[i]; cnt++; }
+  if (tot / std::max<int64_t>(cnt, 1) >= 1024) return 1;
+  return (int)std::min<int64_t>(8, npairs / 16384);
+}
 
 namespace {
 
@@ -200,7 +215,7 @@ bool scores_int32_exact(const bsq_params* p, int64_t max_n, int64_t max_m) {
     maxabs = std::max(maxabs, std::fabs(p->subst[i]));
   }
   const double R = (double)(max_n + max_m + 4) * maxabs;
-  return R < (double)(1 << 29);
+  return R < (double)(1 << 25);  // H * 32 + column must fit an int (packed end-cell key)
 }
 
 void std_modes(int type, int* bmode, int* emode) {
@@ -460,6 +475,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   if (!P.chunks.empty()) P.chunks.front().idx_lo = 0;
   P.total_words = global_words;
   P.slot_bytes = slot;
+  P.half_words = (!single_chunk && P.chunks.size() >= 2) ? P.max_chunk_words : 0;
 
   // ---- phase 3 (parallel): the pair records, straight into pinned memory ------------
   BsqPair* out = P.pairs;
@@ -512,7 +528,7 @@ int stage_inputs(bsq_ctx* ctx, BufSet& B, Plan& P, const uint8_t* codes, int64_t
             B.sx.ensure(4 * (size_t)N) && B.sy.ensure(4 * (size_t)N) && B.status.ensure(4 * (size_t)N) &&
             B.txlen.ensure(4 * (size_t)N) && B.subst.ensure(8 * (size_t)L * L) &&
             B.counters.ensure(4 * (P.chunks.size() + 1)) && B.total.ensure(16) &&
-            B.ptr.ensure(4 * (size_t)(single_chunk ? P.total_words : P.max_chunk_words) + 64);
+            B.ptr.ensure(4 * (size_t)(single_chunk ? P.total_words : (P.half_words > 0 ? 2 * P.half_words : P.max_chunk_words)) + 64);
   if (!ok) return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed");
   cudaStream_t st = ctx->st;
   if (ncodes > 0) BSQ_CK(ctx, cudaMemcpyAsync(B.codes.p, codes, (size_t)ncodes, cudaMemcpyHostToDevice, st));
@@ -534,7 +550,7 @@ int stage_inputs(bsq_ctx* ctx, BufSet& B, Plan& P, const uint8_t* codes, int64_t
   return BSQ_SUCCESS;
 }
 
-int launch_fill(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, size_t* evi) {
+int launch_fill(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, size_t* evi, cudaStream_t stream, bool leave_room) {
   const Chunk& ch = P.chunks[ci];
   BsqFillArgs A;
   memset(&A, 0, sizeof A);
@@ -546,7 +562,7 @@ int launch_fill(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, size_t* evi) 
   A.go_d = P.prm.go; A.ge_d = P.prm.ge;
   A.go_i = (int)P.prm.go; A.ge_i = (int)P.prm.ge;
   A.bmode = P.bmode; A.emode = P.emode; A.btype = P.prm.type;
-  A.ptr = B.ptr.as<uint32_t>();
+  A.ptr = B.ptr.as<uint32_t>() + (P.half_words > 0 ? (int64_t)(ci & 1) * P.half_words : 0);
   A.out_score = B.score.as<double>();
   A.out_ex = B.ex.as<int>();
   A.out_ey = B.ey.as<int>();
@@ -563,7 +579,10 @@ int launch_fill(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, size_t* evi) 
   if (occ < 0) return fail(ctx, BSQ_ERR_ARG, "no kernel variant for this configuration");
   const int groups_per_block = BSQ_FILL_THREADS / G;
   int64_t want_blocks = (ch.count + groups_per_block - 1) / groups_per_block;
-  int grid = (int)std::min<int64_t>(want_blocks, (int64_t)ctx->sms * occ);
+  // when a traceback kernel is to run beside this fill, leave one block's worth of
+  // registers per SM free (the fill is ALU-bound well below full occupancy)
+  const int occ_use = (leave_room && occ >= 4) ? occ - 1 : occ;
+  int grid = (int)std::min<int64_t>(want_blocks, (int64_t)ctx->sms * occ_use);
   if (grid < 1) grid = 1;
   if (ch.family == 1 && ch.max_n_multipass > 0) {
     const int64_t stride = (int64_t)ch.max_n_multipass + 2;
@@ -575,18 +594,18 @@ int launch_fill(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, size_t* evi) 
     A.col_stride = stride;
   }
   cudaEvent_t e0 = get_event(ctx, (*evi)++), e1 = get_event(ctx, (*evi)++);
-  BSQ_CK(ctx, cudaEventRecord(e0, ctx->st));
-  int rc = ch.family == 1 ? k1_op(P.dtype, ch.cfg, ball, eall, P.gosign, BSQ_OP_LAUNCH, grid, ctx->st, &A)
-                          : k2_op(P.dtype, ch.cfg, blocal, P.gosign, BSQ_OP_LAUNCH, grid, ctx->st, &A);
+  BSQ_CK(ctx, cudaEventRecord(e0, stream));
+  int rc = ch.family == 1 ? k1_op(P.dtype, ch.cfg, ball, eall, P.gosign, BSQ_OP_LAUNCH, grid, stream, &A)
+                          : k2_op(P.dtype, ch.cfg, blocal, P.gosign, BSQ_OP_LAUNCH, grid, stream, &A);
   if (rc < 0) return fail(ctx, BSQ_ERR_ARG, "no kernel variant for this configuration");
   BSQ_CK(ctx, cudaGetLastError());
-  BSQ_CK(ctx, cudaEventRecord(e1, ctx->st));
+  BSQ_CK(ctx, cudaEventRecord(e1, stream));
   ctx->tm.fill_launches++;
   ctx->tm.ptr_bytes += 4 * ch.ptr_words;
   return BSQ_SUCCESS;
 }
 
-int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci) {
+int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, cudaStream_t stream) {
   const Chunk& ch = P.chunks[ci];
   BsqTraceArgs T;
   memset(&T, 0, sizeof T);
@@ -597,7 +616,7 @@ int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci) {
   T.G = ch.family == 1 ? BSQ_K1_CFGS[ch.cfg].G : BSQ_K2_CFGS[ch.cfg].G;
   T.K = ch.family == 1 ? BSQ_K1_CFGS[ch.cfg].K : BSQ_K2_CFGS[ch.cfg].C;
   T.gosign = P.gosign;
-  T.ptr = B.ptr.as<uint32_t>();
+  T.ptr = B.ptr.as<uint32_t>() + (P.half_words > 0 ? (int64_t)(ci & 1) * P.half_words : 0);
   T.ex = B.ex.as<int>();
   T.ey = B.ey.as<int>();
   T.status = B.status.as<int>();
@@ -614,11 +633,14 @@ int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci) {
   if (force && force[0] == 'w') warp_walk = true;
   if (warp_walk) {
     const int grid = (int)((ch.count + BSQ_WALK_WARPS - 1) / BSQ_WALK_WARPS);
-    if (ch.family == 1) BSQ_LAUNCH(bsq_k4_walk<1>, grid, 32 * BSQ_WALK_WARPS, 0, ctx->st, T);
-    else BSQ_LAUNCH(bsq_k4_walk<2>, grid, 32 * BSQ_WALK_WARPS, 0, ctx->st, T);
+#define BSQ_WALK(F, GS) BSQ_LAUNCH((bsq_k4_walk<F, GS>), grid, 32 * BSQ_WALK_WARPS, 0, stream, T)
+    if (ch.family == 1) { if (P.gosign < 0) BSQ_WALK(1, -1); else if (P.gosign == 0) BSQ_WALK(1, 0); else BSQ_WALK(1, 1); }
+    else { if (P.gosign < 0) BSQ_WALK(2, -1); else if (P.gosign == 0) BSQ_WALK(2, 0); else BSQ_WALK(2, 1); }
+#undef BSQ_WALK
   } else {
-    const int grid = (int)((ch.count + 127) / 128);
-    BSQ_LAUNCH(bsq_k4_traceback, grid, 128, 0, ctx->st, T);
+    // small blocks so they fit beside a resident fill kernel's register allocation
+    const int grid = (int)((ch.count + 63) / 64);
+    BSQ_LAUNCH(bsq_k4_traceback, grid, 64, 0, stream, T);
   }
   BSQ_CK(ctx, cudaGetLastError());
   ctx->tm.fill_launches++;
@@ -730,7 +752,8 @@ bsq_ctx* bsq_create(int device) {
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { g_err = "cudaGetDeviceProperties failed"; delete ctx; return nullptr; }
   ctx->sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&ctx->st_trace, cudaStreamNonBlocking, -1) != cudaSuccess) {
     g_err = "cudaStreamCreate failed"; delete ctx; return nullptr;
   }
   memset(&ctx->tm, 0, sizeof ctx->tm);
@@ -748,6 +771,7 @@ void bsq_destroy(bsq_ctx* ctx) {
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->st);
   cudaStreamDestroy(ctx->st_copy);
+  cudaStreamDestroy(ctx->st_trace);
   delete ctx;
 }
 
@@ -819,11 +843,62 @@ static int batch_upload(bsq_ctx* ctx, bsq_batch* b, bool own_bufs, bool single_c
   for (int64_t i = 0; i < npairs; i++) slot_guess += (int64_t)o_len[i] + m_len[i];
   const int64_t other = ncodes + 2 * slot_guess + npairs * (int64_t)(sizeof(BsqPair) + 48) + (64 << 20);
   const int64_t arena_words = arena_budget_words(ctx, other);
-  int rc = make_plan(ctx, b->plan, b->B->hpairs, params, npairs, ncodes, o_off, o_len, m_off, m_len, dmin, dmax, arena_words, single_chunk);
+  int rc = make_plan(ctx, b->plan, b->B->hpairs, params, npairs, ncodes, o_off, o_len, m_off, m_len, dmin, dmax,
+                     single_chunk ? arena_words : arena_words / 2, single_chunk,
+                     single_chunk ? 0 : overlap_chunks(npairs, o_len, m_len));
   if (rc != BSQ_SUCCESS) return rc;
   b->single_chunk = single_chunk;
   return stage_inputs(ctx, *b->B, b->plan, codes, ncodes, single_chunk);
 }
+
+// Enqueues fill (compute stream) and traceback (+ optional per-chunk work, trace
+// stream) for every chunk.  With two arena halves the traceback of chunk c runs
+// beside the fill of chunk c+1: the fill is ALU-bound, the walk latency-bound.
+// done[ci] is recorded after the chunk's last kernel.
+extern "C++" {
+template <class BeforeFill, class AfterTrace>
+static int run_chunks(bsq_ctx* ctx, BufSet& B, const Plan& P, bool do_fill, bool do_trace, size_t* evi,
+                      std::vector<size_t>* fill_ev0, std::vector<cudaEvent_t>* done, BeforeFill before_fill,
+                      AfterTrace after_trace) {
+  const size_t NC = P.chunks.size();
+  cudaStream_t sc = ctx->st, stt = ctx->st_trace;
+  const bool overlap = do_fill && do_trace && P.half_words > 0;
+  std::vector<cudaEvent_t> efill(NC), etrace(NC);
+  if (fill_ev0) fill_ev0->assign(NC, 0);
+  if (done) done->assign(NC, nullptr);
+  cudaEvent_t estart = get_event(ctx, (*evi)++);
+  BSQ_CK(ctx, cudaEventRecord(estart, sc));
+  if (do_trace) BSQ_CK(ctx, cudaStreamWaitEvent(stt, estart, 0));  // the trace stream joins the timeline
+  for (size_t ci = 0; ci < NC; ci++) {
+    int rc = before_fill(ci);
+    if (rc != BSQ_SUCCESS) return rc;
+    if (do_fill) {
+      if (overlap && ci >= 2) BSQ_CK(ctx, cudaStreamWaitEvent(sc, etrace[ci - 2], 0));  // arena half is free again
+      if (fill_ev0) (*fill_ev0)[ci] = *evi;
+      rc = launch_fill(ctx, B, P, ci, evi, sc, overlap);
+      if (rc != BSQ_SUCCESS) return rc;
+      efill[ci] = get_event(ctx, (*evi)++);
+      BSQ_CK(ctx, cudaEventRecord(efill[ci], sc));
+    }
+    if (do_trace) {
+      cudaStream_t ts = overlap ? stt : sc;
+      if (overlap) BSQ_CK(ctx, cudaStreamWaitEvent(ts, efill[ci], 0));
+      rc = launch_trace(ctx, B, P, ci, ts);
+      if (rc == BSQ_SUCCESS) rc = after_trace(ci, ts);
+      if (rc != BSQ_SUCCESS) return rc;
+      etrace[ci] = get_event(ctx, (*evi)++);
+      BSQ_CK(ctx, cudaEventRecord(etrace[ci], ts));
+      if (done) (*done)[ci] = etrace[ci];
+    } else if (done) {
+      (*done)[ci] = efill[ci];
+    }
+  }
+  if (overlap) {  // the compute stream rejoins: everything after this sees all traces done
+    for (size_t ci = (NC >= 2 ? NC - 2 : 0); ci < NC; ci++) BSQ_CK(ctx, cudaStreamWaitEvent(sc, etrace[ci], 0));
+  }
+  return BSQ_SUCCESS;
+}
+}  // extern "C++"
 
 // fill (+ traceback + pack) entirely on the device; returns after the stream drained
 static int batch_run(bsq_batch* b, bool do_fill, bool do_trace) {
@@ -840,26 +915,27 @@ static int batch_run(bsq_batch* b, bool do_fill, bool do_trace) {
     return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (transcript slots)");
   BSQ_CK(ctx, cudaEventRecord(t0, ctx->st));
   if (do_fill) BSQ_CK(ctx, cudaMemsetAsync(B.counters.p, 0, 4 * (P.chunks.size() + 1), ctx->st));
-  cudaEvent_t tr0 = nullptr, tr1 = nullptr;
-  for (size_t ci = 0; ci < P.chunks.size(); ci++) {
-    if (do_fill) {
-      rc = launch_fill(ctx, B, P, ci, &evi);
-      if (rc != BSQ_SUCCESS) return rc;
-    }
-    if (do_trace) {
-      rc = launch_trace(ctx, B, P, ci);
-      if (rc != BSQ_SUCCESS) return rc;
-    }
-  }
+  std::vector<size_t> fill_ev0;
+  rc = run_chunks(ctx, B, P, do_fill, do_trace, &evi, &fill_ev0, nullptr, [](size_t) { return BSQ_SUCCESS; },
+                  [](size_t, cudaStream_t) { return BSQ_SUCCESS; });
+  if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(ctx->st); cudaStreamSynchronize(ctx->st_trace); return rc; }
   if (do_trace) {
     rc = pack_transcripts(ctx, B, P);
     if (rc != BSQ_SUCCESS) return rc;
     b->traced = true;
   }
-  (void)tr0; (void)tr1;
   BSQ_CK(ctx, cudaEventRecord(t1, ctx->st));
   BSQ_CK(ctx, cudaStreamSynchronize(ctx->st));
-  collect_timing(ctx, evi, t0, t1);
+  BSQ_CK(ctx, cudaStreamSynchronize(ctx->st_trace));
+  collect_timing(ctx, 2, t0, t1);
+  if (do_fill) {
+    double fill = 0;
+    for (size_t ci = 0; ci < fill_ev0.size(); ci++) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, ctx->events[fill_ev0[ci]], ctx->events[fill_ev0[ci] + 1]) == cudaSuccess) fill += ms;
+    }
+    ctx->tm.fill_ms = fill;
+  }
   ctx->tm.cells = P.cells;
   ctx->tm.dtype = P.dtype;
   ctx->tm.chunks = (int32_t)P.chunks.size();
@@ -947,7 +1023,7 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
   for (int64_t i = 0; i < npairs; i++) slot_guess += (int64_t)o_len[i] + m_len[i];
   const int64_t other = ncodes + 2 * slot_guess + npairs * (int64_t)(sizeof(BsqPair) + 48) + (64 << 20);
   rc = make_plan(ctx, P, B.hpairs, params, npairs, ncodes, o_off, o_len, m_off, m_len, dmin, dmax,
-                 arena_budget_words(ctx, other), false, (int)std::min<int64_t>(8, std::max<int64_t>(npairs / 16384, 1)));
+                 arena_budget_words(ctx, other) / 2, false, overlap_chunks(npairs, o_len, m_len));
   if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(sx); return rc; }
   ctx->tm.plan_ms = now_ms() - t_plan;
   const int64_t E = (int64_t)P.E;
@@ -958,7 +1034,8 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
             B.ex.ensure(4 * N) && B.ey.ensure(4 * N) && B.sx.ensure(4 * N) && B.sy.ensure(4 * N) &&
             B.status.ensure(4 * N) && B.txlen.ensure(4 * N) && B.subst.ensure(8 * (size_t)L * L + 64) &&
             B.counters.ensure(4 * (NC + 1)) && B.total.ensure(8 * (NC + 2)) &&
-            B.ptr.ensure(4 * (size_t)P.max_chunk_words + 64) && ctx->htotals.ensure(8 * (NC + 2));
+            B.ptr.ensure(4 * (size_t)(P.half_words > 0 ? 2 * P.half_words : P.max_chunk_words) + 64) &&
+            ctx->htotals.ensure(8 * (NC + 2));
   if (ok && want_trace) ok = B.slots.ensure((size_t)std::max<int64_t>(P.slot_bytes, 1));
   if (ok && want_tx) ok = B.txoff.ensure(8 * (N + 1)) && B.tiles.ensure(8 * (size_t)ntiles_max) &&
                           B.packed.ensure((size_t)std::max<int64_t>(P.slot_bytes, 1));
@@ -986,38 +1063,39 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
   BSQ_CK(ctx, cudaMemsetAsync(B.total.p, 0, 8 * (NC + 2), sc));
   BSQ_CK(ctx, cudaStreamWaitEvent(sc, ev_pairs, 0));
   const bool per_chunk_out = P.identity;  // chunk c covers caller indices [idx_lo, idx_hi)
-  std::vector<cudaEvent_t> ev_done(NC);
-  std::vector<size_t> fill_ev0(NC);
+  std::vector<cudaEvent_t> ev_done;
+  std::vector<size_t> fill_ev0;
   int waited_slice = -1;
   long long* totals = B.total.as<long long>();  // totals[c] = transcript bytes before chunk c
-  for (size_t ci = 0; ci < NC; ci++) {
-    const Chunk& ch = P.chunks[ci];
-    int need = 0;
-    while (need < nsl - 1 && slice_end[need] < ch.code_end) need++;
-    for (int sidx = waited_slice + 1; sidx <= need && sidx < nsl; sidx++) BSQ_CK(ctx, cudaStreamWaitEvent(sc, ev_code[sidx], 0));
-    waited_slice = std::max(waited_slice, need);
-    fill_ev0[ci] = evi;
-    rc = launch_fill(ctx, B, P, ci, &evi);
-    if (rc == BSQ_SUCCESS && want_trace) rc = launch_trace(ctx, B, P, ci);
-    if (rc == BSQ_SUCCESS && want_tx && per_chunk_out) {
-      const int64_t lo = ch.idx_lo, cnt = ch.idx_hi - ch.idx_lo;
-      const int nt = (int)((cnt + BSQ_SCAN_TILE - 1) / BSQ_SCAN_TILE);
-      long long* tiles = B.tiles.as<long long>() + (lo / BSQ_SCAN_TILE) + ci;  // disjoint scratch per chunk
-      BSQ_LAUNCH(bsq_scan_tile_sums, nt, 256, 0, sc, (const int*)(B.txlen.as<int>() + lo), (int)cnt, tiles);
-      BSQ_LAUNCH(bsq_scan_tiles, 1, 256, 0, sc, tiles, nt, (const long long*)(totals + ci), totals + ci + 1);
-      BSQ_LAUNCH(bsq_scan_apply, nt, 256, 0, sc, (const int*)(B.txlen.as<int>() + lo), (int)cnt,
-                 (const long long*)tiles, B.txoff.as<long long>() + lo);
-      const int grid = (int)((ch.count * 32 + 255) / 256);
-      BSQ_LAUNCH(bsq_pack_transcripts, grid, 256, 0, sc, (const BsqPair*)(B.pairs.as<BsqPair>() + ch.first),
-                 (int)ch.count, (const int*)B.txlen.as<int>(), (const long long*)B.txoff.as<long long>(),
-                 (const char*)B.slots.as<char>(), B.packed.as<char>());
-      ctx->tm.fill_launches += 4;
-      if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, BSQ_ERR_CUDA, "scan/pack launch failed");
-    }
-    if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(sc); cudaStreamSynchronize(sx); return rc; }
-    ev_done[ci] = get_event(ctx, evi++);
-    BSQ_CK(ctx, cudaEventRecord(ev_done[ci], sc));
-  }
+  rc = run_chunks(
+      ctx, B, P, true, want_trace, &evi, &fill_ev0, &ev_done,
+      [&](size_t ci) -> int {  // the fill of chunk ci needs its slice of sequence bytes on the device
+        const Chunk& ch = P.chunks[ci];
+        int need = 0;
+        while (need < nsl - 1 && slice_end[need] < ch.code_end) need++;
+        for (int sidx = waited_slice + 1; sidx <= need && sidx < nsl; sidx++) BSQ_CK(ctx, cudaStreamWaitEvent(sc, ev_code[sidx], 0));
+        waited_slice = std::max(waited_slice, need);
+        return BSQ_SUCCESS;
+      },
+      [&](size_t ci, cudaStream_t ts) -> int {  // pack this chunk's transcripts behind its traceback
+        if (!(want_tx && per_chunk_out)) return BSQ_SUCCESS;
+        const Chunk& ch = P.chunks[ci];
+        const int64_t lo = ch.idx_lo, cnt = ch.idx_hi - ch.idx_lo;
+        const int nt = (int)((cnt + BSQ_SCAN_TILE - 1) / BSQ_SCAN_TILE);
+        long long* tiles = B.tiles.as<long long>() + (lo / BSQ_SCAN_TILE) + ci;  // disjoint scratch per chunk
+        BSQ_LAUNCH(bsq_scan_tile_sums, nt, 256, 0, ts, (const int*)(B.txlen.as<int>() + lo), (int)cnt, tiles);
+        BSQ_LAUNCH(bsq_scan_tiles, 1, 256, 0, ts, tiles, nt, (const long long*)(totals + ci), totals + ci + 1);
+        BSQ_LAUNCH(bsq_scan_apply, nt, 256, 0, ts, (const int*)(B.txlen.as<int>() + lo), (int)cnt,
+                   (const long long*)tiles, B.txoff.as<long long>() + lo);
+        const int grid = (int)((ch.count * 32 + 255) / 256);
+        BSQ_LAUNCH(bsq_pack_transcripts, grid, 256, 0, ts, (const BsqPair*)(B.pairs.as<BsqPair>() + ch.first),
+                   (int)ch.count, (const int*)B.txlen.as<int>(), (const long long*)B.txoff.as<long long>(),
+                   (const char*)B.slots.as<char>(), B.packed.as<char>());
+        ctx->tm.fill_launches += 4;
+        if (cudaGetLastError() != cudaSuccess) return fail(ctx, BSQ_ERR_CUDA, "scan/pack launch failed");
+        return BSQ_SUCCESS;
+      });
+  if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(sc); cudaStreamSynchronize(ctx->st_trace); cudaStreamSynchronize(sx); return rc; }
   if (want_tx && !per_chunk_out) {
     rc = pack_transcripts(ctx, B, P);  // whole batch, caller order
     if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(sc); cudaStreamSynchronize(sx); return rc; }
@@ -1075,6 +1153,7 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
     }
   }
   BSQ_CK(ctx, cudaStreamSynchronize(sx));
+  BSQ_CK(ctx, cudaStreamSynchronize(ctx->st_trace));
   BSQ_CK(ctx, cudaStreamSynchronize(sc));
   collect_timing(ctx, 2, t0, t1);
   // only the (fill start, fill end) event pairs count as fill time

@@ -29,6 +29,7 @@
 
 struct ScF64 {
   typedef double T;
+  static constexpr bool IS_INT = false;
   static __device__ __forceinline__ T ninf() {
     return __longlong_as_double((long long)0xFFF0000000000000ULL);
   }
@@ -46,6 +47,7 @@ struct ScF64 {
 
 struct ScI32 {
   typedef int T;
+  static constexpr bool IS_INT = true;
   static __device__ __forceinline__ T ninf() { return -(1 << 30); }
   static __device__ __forceinline__ T add(T a, T b) { return a + b; }
   static __device__ __forceinline__ T open(T a, int g, T go) { return g * go + a; }  // one IMAD
@@ -118,6 +120,56 @@ __device__ __forceinline__ void bsq_cell2(typename S::T up, int gD, typename S::
   H = h;
 }
 
+// 0 if h == x, else 1 (h >= x).  Written in PTX on the device: left to the compiler,
+// nvcc 12.9 folds "h - x == 0" into the predicate output of the VIMNMX that produced
+// h, which is wrong when the two max operands tie (found by the GPU parity tests).
+__device__ __forceinline__ int bsq_nz(int h, int x) {
+#ifdef BSQ_SIMT_EMU
+  return (unsigned)h - (unsigned)x != 0u;
+#else
+  unsigned r;
+  asm("{\n\t.reg .u32 t;\n\tsub.u32 t, %1, %2;\n\tmin.u32 %0, t, 1;\n\t}" : "=r"(r) : "r"(h), "r"(x));
+  return (int)r;
+#endif
+}
+
+// Integer cell without predicates: nX = min(h - X, 1) is 0 iff candidate X ties
+// for the maximum (h >= X always), so the tie set, the open/extend flags and the
+// pointer nibble are plain integer arithmetic -- subtractions and multiply-adds
+// that ptxas places on the FMA pipe (IMAD) -- and the ALU pipe, which bounds
+// these kernels, is left with the DPX max (VIMNMX3) and the four min() ops.
+template <int GOS, bool HASB, bool BZERO>
+__device__ __forceinline__ void bsq_cell_i32(int up, int gD, int left, int gI, int diag, int sig, int bval,
+                                             int go, int ge, int& H, int& nB, int& nD, int& nI, int& nM) {
+  int D = up + ge;
+  int I = left + ge;
+  if (GOS != 0) {
+    D = gD * go + D;
+    I = gI * go + I;
+  }
+  const int M = diag + sig;
+  int h;
+  if (HASB && BZERO) h = __vimax3_s32_relu(D, I, M);
+  else {
+    h = __vimax3_s32(D, I, M);
+    if (HASB) h = max(h, bval);
+  }
+  // differences in unsigned arithmetic: a -2^30 sentinel candidate may sit 2^31 below h
+  nD = bsq_nz(h, D);
+  nI = bsq_nz(h, I);
+  nM = bsq_nz(h, M);
+  nB = HASB ? bsq_nz(h, BZERO ? 0 : bval) : 1;
+  H = h;
+}
+
+// "the gap must open" flag out of a cell whose NOT-in-tie-set indicators are given
+template <int GOS>
+__device__ __forceinline__ int bsq_gapflag_i32(int nOwn, int nO1, int nO2, int nO3) {
+  if (GOS < 0) return nOwn;                                              // extends iff own op in the set
+  if (GOS > 0) return (int)min((unsigned)(nOwn + 3 - nO1 - nO2 - nO3), 1u);  // extends iff nothing else is
+  return 0;
+}
+
 // open/extend flag of a gap out of a cell with tie set (eB,eD,eI,eM); own = the gap's op
 template <class S, int GOS>
 __device__ __forceinline__ int bsq_gapflag(bool eOwn, bool eO1, bool eO2, bool eO3) {
@@ -155,7 +207,7 @@ __device__ __forceinline__ void bsq_group_best(unsigned gmask, T& s, int& k1, in
 // EALL: 0 = end cell not searched per cell, 1 = every cell may end the alignment
 // (LOCAL / START_ANCHORED), 2 = same but padding columns must be masked out
 // explicitly (only needed for score sets where a gap does not lower the score).
-template <class S, int K, int GOS, bool ALLB, int EALL>
+template <class S, int K, int GOS, bool ALLB, int EALL, bool BZ>
 __device__ __forceinline__ void bsq_k1_row(
     typename S::T (&Hup)[K], int (&gD)[K], uint32_t (&cw)[(K + 7) / 8], const int (&moff)[K],
     const char* srow, typename S::T inH, int inG, typename S::T diag_in,
@@ -168,6 +220,35 @@ __device__ __forceinline__ void bsq_k1_row(
   T diag = diag_in;
 #pragma unroll
   for (int w = 0; w < WPL; w++) cw[w] = 0u;
+  if constexpr (S::IS_INT) {
+    // end-cell search by packed key: (H << 5 | 31 - k) is maximal at the row's first
+    // maximum, so one IMAD + one max per cell and one compare per row do the job
+    int rowkey = -2147483647 - 1;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const int up = Hup[k];
+      const int sig = *(const int*)(srow + moff[k]);
+      int H, nB, nD, nI, nM;
+      if (ALLB || k == 0) {
+        if (ALLB && BZ) bsq_cell_i32<GOS, true, true>(up, gD[k], left, gI, diag, sig, 0, go, ge, H, nB, nD, nI, nM);
+        else bsq_cell_i32<GOS, true, false>(up, gD[k], left, gI, diag, sig, k == 0 ? bfirst : brest, go, ge, H, nB, nD, nI, nM);
+      } else {
+        bsq_cell_i32<GOS, false, false>(up, gD[k], left, gI, diag, sig, 0, go, ge, H, nB, nD, nI, nM);
+      }
+      const int notmask = nB + 2 * nD + 4 * nI + 8 * nM;
+      cw[k >> 3] += (uint32_t)(15 - notmask) << (4 * (k & 7));
+      gD[k] = bsq_gapflag_i32<GOS>(nD, nB, nI, nM);
+      gI = bsq_gapflag_i32<GOS>(nI, nB, nD, nM);
+      diag = up;
+      left = H;
+      Hup[k] = H;
+      if (EALL == 1) rowkey = max(rowkey, H * 32 + (31 - k));
+      else if (EALL == 2) { if (k < kv) rowkey = max(rowkey, H * 32 + (31 - k)); }
+    }
+    if (EALL != 0) {
+      if ((rowkey >> 5) > best) { best = rowkey >> 5; bpos = xk + (31 - (rowkey & 31)); }
+    }
+  } else {
 #pragma unroll
   for (int k = 0; k < K; k++) {
     const T up = Hup[k];
@@ -194,6 +275,7 @@ __device__ __forceinline__ void bsq_k1_row(
     } else if (EALL == 2) {
       if (H > best && k < kv) { best = H; bpos = xk + k; }
     }
+  }
   }
   outH = left;
   outG = gI;
@@ -287,11 +369,11 @@ __global__ void __launch_bounds__(128) bsq_k1_fill(const BsqFillArgs A) {
               brest = (bmode >= BSQ_B_EDGE) ? ZERO : NINF;
               bfirst = (bmode >= BSQ_B_EDGE || y0 == 0) ? ZERO : NINF;
             }
-            bsq_k1_row<S, K, GOS, true, EALL>(Hup, gD, cw, moff, srow, inH, inG, prev_in, bfirst, brest, go, ge,
+            bsq_k1_row<S, K, GOS, true, EALL, BALL>(Hup, gD, cw, moff, srow, inH, inG, prev_in, bfirst, brest, go, ge,
                                               x * 32, kv, pbest, pbpos, outH, outG);
           } else {
             const T bfirst = (bmode == BSQ_B_EDGE && y0 == 0) ? ZERO : NINF;
-            bsq_k1_row<S, K, GOS, false, EALL>(Hup, gD, cw, moff, srow, inH, inG, prev_in, bfirst, NINF, go, ge,
+            bsq_k1_row<S, K, GOS, false, EALL, false>(Hup, gD, cw, moff, srow, inH, inG, prev_in, bfirst, NINF, go, ge,
                                                x * 32, kv, pbest, pbpos, outH, outG);
           }
           lastH = outH;

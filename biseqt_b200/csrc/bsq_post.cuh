@@ -80,11 +80,18 @@ __global__ void __launch_bounds__(128) bsq_k4_traceback(const BsqTraceArgs A) {
 //   FAMILY 1: K1 layout [pass][x][lane][word]   row id = pass*(n+1) + x
 //   FAMILY 2: K2 layout [s - s0][lane][word]    row id = s - s0
 // ---------------------------------------------------------------------------
-#define BSQ_TILE_WORDS 2048
+#define BSQ_TILE_WORDS 1024
 #define BSQ_WALK_WARPS 4
-#define BSQ_LET_WIN 256
+#define BSQ_LET_WIN 128
 
-template <int FAMILY>
+template <int GOS>
+__device__ __forceinline__ uint32_t bsq_gap_base_t(uint32_t mk, uint32_t own) {
+  if (GOS < 0) return (mk & own) ? own : bsq_lowest(mk);
+  if (GOS > 0) return (mk & (0xFu ^ own)) ? bsq_lowest(mk & (0xFu ^ own)) : own;
+  return bsq_lowest(mk);
+}
+
+template <int FAMILY, int GOS>
 __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTraceArgs A) {
   __shared__ uint32_t s_tile[BSQ_WALK_WARPS][BSQ_TILE_WORDS];
   __shared__ uint8_t s_let[BSQ_WALK_WARPS][2][BSQ_LET_WIN];  // staged letters: origin, mutant
@@ -119,67 +126,75 @@ __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTrac
   const uint8_t* oseq = A.codes + P.o_off;
   const uint8_t* mseq = A.codes + P.m_off;
   char* wr = A.slots + P.tx_slot + (long long)P.n + P.m;
-  long long tlo = 1, thi = 0;  // rows [tlo, thi] are staged; empty
-  uint32_t arrive = BSQ_MM;    // how we got here: M (or the end cell) -> lowest bit
+  long long tlo = 1;            // first staged row; the tile holds rows [tlo, tlo + rows)
+  int roff = -1;                // word offset of row `rid` inside the tile (< 0: not staged)
+  int rows = 0;
+  int colw, sh;                 // word inside the row and bit position of my nibble
+#define BSQ_RECOL() { const int kk_ = (FAMILY == 1) ? k : (k >> 1); colw = l * WP + (kk_ >> 3); sh = 4 * (kk_ & 7); }
+  BSQ_RECOL();
+  uint32_t arrive = BSQ_MM;     // how we got here: M (or the end cell) -> lowest bit
   const int maxlen = P.n + P.m;
   uint8_t* obuf = s_let[wib][0];
   uint8_t* mbuf = s_let[wib][1];
-  int xb = x, yb = y;          // obuf holds o[xb .. xb+WIN), mbuf m[yb .. yb+WIN); empty
+  int xb = x, yb = y;           // obuf holds o[xb .. xb+WIN), mbuf m[yb .. yb+WIN); empty
   for (;;) {
-    if (x - 1 < xb && x >= 1) {  // the walk only moves towards smaller x and y
-      xb = x - BSQ_LET_WIN; if (xb < 0) xb = 0;
-      __syncwarp();
-      for (int i = lane; i < BSQ_LET_WIN; i += 32) if (xb + i < P.n) obuf[i] = oseq[xb + i];
-      __syncwarp();
-    }
-    if (y - 1 < yb && y >= 1) {
-      yb = y - BSQ_LET_WIN; if (yb < 0) yb = 0;
-      __syncwarp();
-      for (int i = lane; i < BSQ_LET_WIN; i += 32) if (yb + i < P.m) mbuf[i] = mseq[yb + i];
-      __syncwarp();
-    }
-    if (rid < tlo || rid > thi) {
-      thi = rid;
-      tlo = rid - R + 1;
-      if (tlo < 0) tlo = 0;
-      const int nw = (int)(thi - tlo + 1) * RB;   // multiple of 4 words
+    if (roff < 0 || roff >= rows * RB) {  // stage the rows at and below `rid`
+      long long lo = rid - R + 1;
+      if (lo < 0) lo = 0;
+      tlo = lo;
+      rows = (int)(rid - lo + 1);
+      const int nw = rows * RB;            // multiple of 4 words
       const uint4* src = (const uint4*)(table + tlo * RB);
       __syncwarp();
       for (int i = lane; i < nw / 4; i += 32) ((uint4*)tile)[i] = src[i];
       __syncwarp();
+      roff = (int)(rid - tlo) * RB;
     }
-    const int kk = (FAMILY == 1) ? k : (k >> 1);
-    const uint32_t word = tile[(int)(rid - tlo) * RB + l * WP + (kk >> 3)];
-    const uint32_t mk = (word >> (4 * (kk & 7))) & 0xFu;
-    const uint32_t op = (arrive == BSQ_MM) ? bsq_lowest(mk) : bsq_gap_base(mk, arrive, A.gosign);
+    const uint32_t mk = (tile[roff + colw] >> sh) & 0xFu;
+    const uint32_t op = (arrive == BSQ_MM) ? bsq_lowest(mk) : bsq_gap_base_t<GOS>(mk, arrive);
     if (op == BSQ_MB || op == 0u || len >= maxlen) break;
     char ch;
     if (op == BSQ_MM) {
+      if (x - 1 < xb) {  // the walk only moves towards smaller x and y
+        xb = x - BSQ_LET_WIN; if (xb < 0) xb = 0;
+        __syncwarp();
+        for (int i = lane; i < BSQ_LET_WIN; i += 32) if (xb + i < P.n) obuf[i] = oseq[xb + i];
+        __syncwarp();
+      }
+      if (y - 1 < yb) {
+        yb = y - BSQ_LET_WIN; if (yb < 0) yb = 0;
+        __syncwarp();
+        for (int i = lane; i < BSQ_LET_WIN; i += 32) if (yb + i < P.m) mbuf[i] = mseq[yb + i];
+        __syncwarp();
+      }
       ch = (obuf[x - 1 - xb] == mbuf[y - 1 - yb]) ? 'M' : 'S';
       x--; y--;
       if (FAMILY == 1) {
-        rid -= 1;
-        if (--k < 0) { k = K - 1; if (--l < 0) { l = G - 1; rid -= (P.n + 1); } }
+        rid -= 1; roff -= RB;
+        if (--k < 0) { k = K - 1; if (--l < 0) { l = G - 1; rid -= (P.n + 1); roff = -1; } }
+        BSQ_RECOL();
       } else {
-        rid -= 2;
+        rid -= 2; roff -= 2 * RB;
       }
     } else if (op == BSQ_MD) {
       ch = 'D'; x--;
-      rid -= 1;
-      if (FAMILY == 2) { if (--k < 0) { k = K - 1; l--; } }
+      rid -= 1; roff -= RB;
+      if (FAMILY == 2) { if (--k < 0) { k = K - 1; l--; } BSQ_RECOL(); }
     } else {
       ch = 'I'; y--;
       if (FAMILY == 1) {
-        if (--k < 0) { k = K - 1; if (--l < 0) { l = G - 1; rid -= (P.n + 1); } }
+        if (--k < 0) { k = K - 1; if (--l < 0) { l = G - 1; rid -= (P.n + 1); roff = -1; } }
       } else {
-        rid -= 1;
+        rid -= 1; roff -= RB;
         if (++k == K) { k = 0; l++; }
       }
+      BSQ_RECOL();
     }
     arrive = op;
     len++;
     if (lane == 0) wr[-len] = ch;
   }
+#undef BSQ_RECOL
   if (lane == 0) {
     A.txlen[oi] = len;
     A.sx[oi] = x;

@@ -259,6 +259,10 @@ inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __vimax3_s32(int a, int b, int c) { return std::max(a, std::max(b, c)); }
 inline int __vimax3_s32_relu(int a, int b, int c) { return std::max(0, std::max(a, std::max(b, c))); }
 inline int __viaddmax_s32(int a, int b, int c) { return std::max(a + b, c); }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline int min(int a, int b) { return a < b ? a : b; }
+inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 
 template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
@@ -307,6 +311,7 @@ inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) {
 inline cudaError_t cudaMemset(void* d, int v, size_t n) { if (n) memset(d, v, n); return 0; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }
 inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return 0; }
+inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = nullptr; return 0; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 inline cudaError_t cudaDeviceSynchronize() { return 0; }

@@ -550,6 +550,18 @@ __device__ __forceinline__ void bsq_k2_step_fast(
       const int x = (s + d) >> 1, y = (s - d) >> 1;
       sig = s_sub[(int)oseq[x - 1] * L + (int)mseq[y - 1]];
     }
+    if constexpr (S::IS_INT) {
+      int h, nB, nD, nI, nM;
+      bsq_cell_i32<GOS, BLOCAL, true>(up, gD, left, gI, diag, sig, 0, go, ge, h, nB, nD, nI, nM);
+      const int notmask = nB + 2 * nD + 4 * nI + 8 * nM;
+      cur[hc >> 3] += (uint32_t)(15 - notmask) << (4 * (hc & 7));
+      H[c] = h;
+      fD[c] = bsq_gapflag_i32<GOS>(nD, nB, nI, nM);
+      fI[c] = bsq_gapflag_i32<GOS>(nI, nB, nD, nM);
+      if (BLOCAL) {
+        if (h > best[c]) { best[c] = h; bests[c] = s; }
+      }
+    } else {
     T h;
     bool eB, eD, eI, eM;
     bsq_cell2<S, GOS, BLOCAL>(up, gD, left, gI, diag, sig, (T)0, go, ge, h, eB, eD, eI, eM);
@@ -564,6 +576,7 @@ __device__ __forceinline__ void bsq_k2_step_fast(
     fI[c] = bsq_gapflag<S, GOS>(eI, eB, eD, eM);
     if (BLOCAL) {
       if (h > best[c]) { best[c] = h; bests[c] = s; }
+    }
     }
   }
   if (fixc >= 0 && (fixc & 1) == Q) {  // one lane per group, every other step

@@ -136,8 +136,11 @@ __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTrac
   const int maxlen = P.n + P.m;
   uint8_t* obuf = s_let[wib][0];
   uint8_t* mbuf = s_let[wib][1];
-  int xb = x, yb = y;           // obuf holds o[xb .. xb+WIN), mbuf m[yb .. yb+WIN); empty
-  for (;;) {
+  int xb = x + 1, yb = y + 1;   // obuf holds o[xb .. xb+WIN), mbuf m[yb .. yb+WIN); empty (forces a load)
+  constexpr int BATCH = 8;       // M/S steps examined per round out of preloaded words
+  const int mstep = (FAMILY == 1) ? RB : 2 * RB;   // a diagonal move goes back 1 row (K1) / 2 rows (K2)
+  bool finished = false;
+  while (!finished) {
     if (roff < 0 || roff >= rows * RB) {  // stage the rows at and below `rid`
       long long lo = rid - R + 1;
       if (lo < 0) lo = 0;
@@ -150,33 +153,61 @@ __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTrac
       __syncwarp();
       roff = (int)(rid - tlo) * RB;
     }
-    const uint32_t mk = (tile[roff + colw] >> sh) & 0xFu;
-    const uint32_t op = (arrive == BSQ_MM) ? bsq_lowest(mk) : bsq_gap_base_t<GOS>(mk, arrive);
-    if (op == BSQ_MB || op == 0u || len >= maxlen) break;
-    char ch;
-    if (op == BSQ_MM) {
-      if (x - 1 < xb) {  // the walk only moves towards smaller x and y
-        xb = x - BSQ_LET_WIN; if (xb < 0) xb = 0;
-        __syncwarp();
-        for (int i = lane; i < BSQ_LET_WIN; i += 32) if (xb + i < P.n) obuf[i] = oseq[xb + i];
-        __syncwarp();
-      }
-      if (y - 1 < yb) {
-        yb = y - BSQ_LET_WIN; if (yb < 0) yb = 0;
-        __syncwarp();
-        for (int i = lane; i < BSQ_LET_WIN; i += 32) if (yb + i < P.m) mbuf[i] = mseq[yb + i];
-        __syncwarp();
-      }
-      ch = (obuf[x - 1 - xb] == mbuf[y - 1 - yb]) ? 'M' : 'S';
-      x--; y--;
-      if (FAMILY == 1) {
-        rid -= 1; roff -= RB;
-        if (--k < 0) { k = K - 1; if (--l < 0) { l = G - 1; rid -= (P.n + 1); roff = -1; } }
-        BSQ_RECOL();
+    if (x - BATCH < xb && xb > 0) {  // the walk only moves towards smaller x and y
+      xb = x - BSQ_LET_WIN; if (xb < 0) xb = 0;
+      __syncwarp();
+      for (int i = lane; i < BSQ_LET_WIN; i += 32) if (xb + i < P.n) obuf[i] = oseq[xb + i];
+      __syncwarp();
+    }
+    if (y - BATCH < yb && yb > 0) {
+      yb = y - BSQ_LET_WIN; if (yb < 0) yb = 0;
+      __syncwarp();
+      for (int i = lane; i < BSQ_LET_WIN; i += 32) if (yb + i < P.m) mbuf[i] = mseq[yb + i];
+      __syncwarp();
+    }
+    // preload the nibbles a run of up to BATCH diagonal moves would visit: the loads are
+    // independent of each other, so the chain per move is a few ALU ops, not a memory access
+    int jmax = roff / mstep + 1;
+    if (jmax > BATCH) jmax = BATCH;
+    if (FAMILY == 1 && jmax > k + 1) jmax = k + 1;   // stay inside my lane's columns
+    uint32_t nib[BATCH];
+#pragma unroll
+    for (int j = 0; j < BATCH; j++) {
+      if (j < jmax) {
+        int cwj = colw, shj = sh;
+        if (FAMILY == 1) { cwj = l * WP + ((k - j) >> 3); shj = 4 * ((k - j) & 7); }
+        nib[j] = (tile[roff - j * mstep + cwj] >> shj) & 0xFu;
       } else {
-        rid -= 2; roff -= 2 * RB;
+        nib[j] = 0u;
       }
-    } else if (op == BSQ_MD) {
+    }
+    int taken = 0;           // diagonal moves taken in this round
+    uint32_t op = 0u;
+#pragma unroll
+    for (int j = 0; j < BATCH; j++) {
+      if (j < jmax && taken == j) {
+        const uint32_t mk = nib[j];
+        op = (j == 0 && arrive != BSQ_MM) ? bsq_gap_base_t<GOS>(mk, arrive) : bsq_lowest(mk);
+        if (op == BSQ_MM && len < maxlen) {
+          const char ch = (obuf[x - 1 - xb] == mbuf[y - 1 - yb]) ? 'M' : 'S';
+          x--; y--; len++;
+          if (lane == 0) wr[-len] = ch;
+          arrive = BSQ_MM;
+          taken = j + 1;
+        }
+      }
+    }
+    if (taken > 0) {  // account for the diagonal moves
+      rid -= (FAMILY == 1) ? taken : 2 * taken;
+      roff -= taken * mstep;
+      if (FAMILY == 1) { k -= taken; if (k < 0) { k = K - 1; if (--l < 0) { l = G - 1; rid -= (P.n + 1); roff = -1; } } BSQ_RECOL(); }
+      if (taken == jmax) continue;  // the run may go on: next round
+    }
+    // here `op` is the op found at the current cell and it is not a diagonal move
+    if (taken == 0 && jmax <= 0) continue;   // nothing staged (cannot happen, defensive)
+    if (op == BSQ_MB || op == 0u || len >= maxlen || op == BSQ_MM) { finished = true; break; }
+    char ch;
+    if (op == BSQ_MD) {
       ch = 'D'; x--;
       rid -= 1; roff -= RB;
       if (FAMILY == 2) { if (--k < 0) { k = K - 1; l--; } BSQ_RECOL(); }

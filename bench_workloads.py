@@ -23,7 +23,7 @@ def _pack_rows(o_rows, o_lens, m_rows, m_lens):
     codes = np.zeros(int(base[-1]) + 16, dtype=np.uint8)
     o_off = base[:-1].copy()
     m_off = o_off + o_lens
-    if N and (o_lens == o_lens[0]).all() and (m_lens == m_lens[0]).all():
+    if N and hasattr(o_rows, 'shape') and (o_lens == o_lens[0]).all() and (m_lens == m_lens[0]).all():
         no, nm = int(o_lens[0]), int(m_lens[0])
         view = codes[:N * (no + nm)].reshape(N, no + nm)
         view[:, :no] = o_rows[:, :no]
@@ -89,6 +89,30 @@ def make(kind, npairs, seed):
         return dict(kind=kind, mode=BANDED_MODE, type=B_OVERLAP, subst=S, go=go, ge=ge, codes=codes,
                     o_off=o_off, o_len=o_len, m_off=m_off, m_len=m_len, dmin=dmin, dmax=dmax,
                     desc='%d pairs ~%d bp, B_OVERLAP, radius %s' % (npairs, n, '64' if kind != 'c4_int' else 'band_radius(K,.15,.99)~%d' % int(np.median(r))))
+    if kind in ('c5_int', 'c5_logodds', 'c5s_int', 'c5s_logodds'):
+        # configs[4]: `npairs` pairs of 1 Mb x ~1 Mb, B_GLOBAL, radius 2048 (c5s_*: 64 kb, the
+        # size the CPU oracle finishes in seconds).  The mutant is made piecewise (1000-letter
+        # pieces mutated in lock step) because the mutation state machine is per letter.
+        n = 1000000 if kind.startswith('c5_') else 65000
+        piece = 1000
+        rows = []
+        for _ in range(npairs):
+            o = st.rand_seqs(rng, n // piece, piece, L)
+            mut, mlen = st.mutate_batch(rng, o, L, 0.05, 0.01, 0.02)
+            rows.append((o.reshape(-1), np.concatenate([mut[i, :mlen[i]] for i in range(len(mlen))])))
+        o_lens = [len(r[0]) for r in rows]
+        m_lens = [len(r[1]) for r in rows]
+        codes, o_off, o_len, m_off, m_len = _pack_rows([r[0] for r in rows], o_lens, [r[1] for r in rows], m_lens)
+        if kind.endswith('logodds'):
+            S, go, ge = st.log_odds_scores(L, 0.05, 0.01, 0.02)
+        else:
+            S, go, ge = int_scores(2, -3), -4.0, -2.0
+        dmin = np.full(npairs, -2048, dtype=np.int32)
+        dmax = np.full(npairs, 2048, dtype=np.int32)
+        return dict(kind=kind, mode=BANDED_MODE, type=B_GLOBAL, subst=S, go=go, ge=ge, codes=codes,
+                    o_off=o_off, o_len=o_len, m_off=m_off, m_len=m_len, dmin=dmin, dmax=dmax,
+                    desc='%d pair(s) %d x ~%d bp, B_GLOBAL, radius 2048, %s' % (
+                        npairs, n, n, 'log-odds' if kind.endswith('logodds') else 'int +2/-3 go-4 ge-2'))
     if kind == 'c1':
         # configs[0]: one 1 kb x 1 kb STD GLOBAL pair, log-odds scores (go_score = 0)
         n = 1000

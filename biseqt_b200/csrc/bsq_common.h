@@ -38,8 +38,24 @@ struct BsqPair {         // one problem of a chunk, device resident
   long long tx_slot;     // first byte of this pair's transcript slot (cap n+m)
   int n, m;              // frame lengths
   int dmin, dmax;        // clipped band (BANDED)
-  int s0;                // first anti-diagonal x+y the banded kernel visits
+  int s0;                // K2: first anti-diagonal x+y the kernel visits; K3: time steps per strip
   int pad;
+};
+
+// K3 (strip-pipelined wide bands): what a pair needs beyond BsqPair
+struct BsqK3Pair {
+  long long slab_off;    // first entry of this pair's boundary-column slab (n+1 entries)
+  int strip_base;        // index of this pair's strip 0 in the chunk's strip list
+  int nstrips;           // ceil((m+1) / (32*K))
+};
+struct BsqK3Res {        // best end-cell candidate found inside one strip
+  double score;
+  int k1, k2;            // scan keys (diagonal, x); k1 == INT_MAX: none
+#ifdef BSQ_K3_PROFILE       // tuning builds only: when the strip was claimed / could start / ended
+  long long t_claim, t_ready, t_end;   // %globaltimer, ns
+  long long wait_clk;                  // SM clocks spent waiting for boundary batches
+  int polls, sm;
+#endif
 };
 
 struct BsqFillArgs {
@@ -62,6 +78,13 @@ struct BsqFillArgs {
   double* col_h;         // (also used for int scores, stored as double-sized slots)
   uint8_t* col_f;
   long long col_stride;  // entries per group
+  // K3: strips of all pairs of the chunk form one ordered work list; col_h holds one
+  // boundary-column slab per pair (BsqK3Pair.slab_off rows of 1 (I32) / 2 (F64) 64-bit
+  // self-validating entries), zeroed before the launch
+  const BsqK3Pair* k3;
+  int k3_total;          // strips in the chunk
+  int* k3_done;          // [npairs] strips finished per pair, zeroed before the launch
+  BsqK3Res* k3_res;      // [k3_total]
 };
 
 struct BsqTraceArgs {
@@ -79,4 +102,5 @@ struct BsqTraceArgs {
   int* sy;
   int* txlen;
   char* slots;           // transcripts, right-aligned in [tx_slot, tx_slot+n+m)
+  int family;            // 1 = K1, 2 = K2, 3 = K3 table layout
 };

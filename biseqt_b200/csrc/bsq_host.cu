@@ -59,11 +59,11 @@ struct PinBuf {
 
 struct BufSet {  // everything one batch needs in HBM
   DevBuf codes, pairs, ptr, slots, packed, score, ex, ey, sx, sy, status, txlen, txoff, tiles,
-      subst, counters, colh, colf, total;
+      subst, counters, colh, colf, total, k3pairs, k3sync, k3res;
   PinBuf hpairs, hsmall;
   void release() {
     DevBuf* all[] = {&codes, &pairs, &ptr, &slots, &packed, &score, &ex, &ey, &sx, &sy, &status,
-                     &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total};
+                     &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res};
     for (DevBuf* b : all) b->release();
     hpairs.release();
     hsmall.release();
@@ -78,7 +78,12 @@ struct Chunk {
   int max_n_multipass;   // K1: longest origin among pairs needing > 1 pass (0 if none)
   int64_t idx_lo, idx_hi; // caller indices [idx_lo, idx_hi) covered (identity order only)
   int64_t code_end;      // one past the last byte of codes[] this chunk reads
+  int64_t k3_strips = 0; // K3: strips in the chunk's work list
+  int64_t k3_slab = 0;   // K3: boundary-column slab entries (sum of n+1)
+  int64_t k3_active = 0; // K3: strips in flight when every pair's pipeline is full
 };
+
+inline bool chunk_is_k3(const Chunk& ch) { return ch.family == 2 && ch.cfg >= BSQ_K2_NCFG; }
 
 struct Override { int64_t idx; int status; };
 
@@ -108,6 +113,8 @@ struct Plan {
   int64_t total_words = 0;
   bool identity = false;  // processing order == caller order (no sort was needed)
   int64_t half_words = 0; // > 0: two arena halves, chunk c uses half (c & 1) so trace(c) overlaps fill(c+1)
+  std::vector<BsqK3Pair> k3;  // per pair record (processing order); empty when no pair uses K3
+  int64_t k3_max_strips = 0, k3_max_slab = 0, k3_max_pairs = 0;  // maxima over chunks
 };
 
 }  // namespace
@@ -273,6 +280,18 @@ int k2_op(int dtype, int cfg, int blocal, int gos, int op, int grid, cudaStream_
                                 : bsq_k2_f64_op(cfg, blocal, gos, op, grid, st, A);
 }
 
+int k3_op(int dtype, int cfg, int btype, int gos, int grid, cudaStream_t st, const BsqFillArgs* A) {
+  return dtype == BSQ_DTYPE_I32 ? bsq_k3_i32_op(cfg, btype, gos, grid, st, A)
+                                : bsq_k3_f64_op(cfg, btype, gos, grid, st, A);
+}
+
+// K3 geometry for bands no K2 geometry holds (or for every band: BSQ_FORCE_K3, a test hook)
+int pick_k3_cfg() {
+  const char* e = getenv("BSQ_K3_CFG");  // tuning hook
+  const int forced = e ? atoi(e) : -1;
+  return (forced >= 0 && forced < BSQ_K3_NCFG) ? forced : 1;
+}
+
 // ---- planning -------------------------------------------------------------
 
 template <class F>
@@ -322,6 +341,8 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
     for (int64_t i = 0; i < N; i++) { mn = std::max<int64_t>(mn, o_len[i]); mm = std::max<int64_t>(mm, m_len[i]); }
     f64_geom = (prm->dtype == BSQ_DTYPE_F64) || !(prm->dtype == BSQ_DTYPE_I32 || scores_int32_exact(&t0, mn, mm));
   }
+  const bool force_k3 = getenv("BSQ_FORCE_K3") != nullptr;  // test hook: K3 for every band
+  const int k3_cfg = pick_k3_cfg();
   // ---- phase 1 (parallel): classify every pair like dptable_init would ----------
   std::vector<PlanItem>& items = ctx->plan_items;
   if ((int64_t)items.size() < N) items.resize((size_t)N);
@@ -360,10 +381,18 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
         else if (W < 0) it.cfg = -1 - BSQ_INIT_FAIL;
         else if (W == 0) it.cfg = -1 - BSQ_NO_ALIGNMENT;
         else {
-          it.cfg = pick_k2_cfg((int)std::min<int64_t>(W, 1 << 30), f64_geom);
-          if (it.cfg < 0) it.cfg = -1 - BSQ_UNSUPPORTED;
+          it.cfg = force_k3 ? -1 : pick_k2_cfg((int)std::min<int64_t>(W, 1 << 30), f64_geom);
+          if (it.cfg < 0) it.cfg = BSQ_K2_NCFG + k3_cfg;
         }
-        if (it.cfg >= 0) {
+        if (it.cfg >= BSQ_K2_NCFG) {  // K3: strips of G*K columns, tstride time steps each
+          it.lo = lo; it.hi = hi;
+          const int K = BSQ_K3_CFGS[it.cfg - BSQ_K2_NCFG].K, G = 32, BW = G * K;
+          const int64_t nstrips = ((int64_t)m + BW) / BW;
+          const int64_t tstride = std::min<int64_t>((int64_t)n + 1, W + BW - 1) + G - 1;
+          it.words = nstrips * tstride * G * (K / 2) / 4;
+          it.aux = (int32_t)tstride;
+          it.cells = count_cells(BSQ_BANDED_MODE, n, m, lo, hi);
+        } else if (it.cfg >= 0) {
           it.lo = lo; it.hi = hi;
           const int G = BSQ_K2_CFGS[it.cfg].G, C = BSQ_K2_CFGS[it.cfg].C, WPS = (C / 2 + 7) / 8;
           const int smin = (lo <= 0 && hi >= 0) ? 0 : std::min(std::abs(lo), std::abs(hi));
@@ -450,13 +479,24 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   P.max_chunk_words = 0;
   Chunk cur{0, 0, family, -1, 0, 0, 0, 0, 0};
   int64_t global_words = 0, slot = 0;
+  bool any_k3 = false;
+  for (int64_t e = 0; e < E && !any_k3; e++) any_k3 = items[order[e]].cfg >= BSQ_K2_NCFG && family == 2;
+  P.k3.clear();
+  if (any_k3) P.k3.assign((size_t)E, BsqK3Pair{0, 0, 0});
+  P.k3_max_strips = P.k3_max_slab = P.k3_max_pairs = 0;
+  auto close_chunk = [&](Chunk& c) {
+    P.k3_max_strips = std::max(P.k3_max_strips, c.k3_strips);
+    P.k3_max_slab = std::max(P.k3_max_slab, c.k3_slab);
+    if (chunk_is_k3(c)) P.k3_max_pairs = std::max(P.k3_max_pairs, c.count);
+    P.chunks.push_back(c);
+  };
   for (int64_t e = 0; e < E; e++) {
     const int64_t i = order[e];
     const PlanItem& it = items[i];
     const bool new_chunk = cur.count > 0 && (it.cfg != cur.cfg || (!single_chunk && cur.ptr_words + it.words > arena_words));
     if (new_chunk) {
       cur.idx_hi = i;
-      P.chunks.push_back(cur);
+      close_chunk(cur);
       cur = Chunk{e, 0, family, -1, 0, 0, i, 0, 0};
     }
     if (cur.count == 0) cur.cfg = it.cfg;
@@ -465,13 +505,23 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
     slot += (int64_t)o_len[i] + m_len[i];
     if (family == 1) cur.max_n_multipass = std::max(cur.max_n_multipass, it.aux);
     cur.code_end = std::max<int64_t>(cur.code_end, std::max(o_off[i] + o_len[i], m_off[i] + m_len[i]));
+    if (family == 2 && it.cfg >= BSQ_K2_NCFG) {
+      const int BW = 32 * BSQ_K3_CFGS[it.cfg - BSQ_K2_NCFG].K;
+      const int64_t nstrips = ((int64_t)m_len[i] + BW) / BW;
+      if (cur.k3_strips + nstrips >= ((int64_t)1 << 30))
+        return fail(ctx, BSQ_ERR_ARG, "too many wide-band strips in one chunk");
+      P.k3[(size_t)e] = BsqK3Pair{cur.k3_slab, (int)cur.k3_strips, (int)nstrips};
+      cur.k3_strips += nstrips;
+      cur.k3_slab += (int64_t)o_len[i] + 1;
+      cur.k3_active += std::min<int64_t>(nstrips, ((int64_t)it.hi - it.lo + 1 + BW + 32) / BW + 2);
+    }
     cur.ptr_words += it.words;
     global_words += it.words;
     cur.count++;
     P.max_chunk_words = std::max(P.max_chunk_words, cur.ptr_words);
   }
   cur.idx_hi = N;
-  if (cur.count > 0) P.chunks.push_back(cur);
+  if (cur.count > 0) close_chunk(cur);
   if (!P.chunks.empty()) P.chunks.front().idx_lo = 0;
   P.total_words = global_words;
   P.slot_bytes = slot;
@@ -519,6 +569,19 @@ int64_t arena_budget_words(bsq_ctx* ctx, int64_t other_bytes) {
   return (int64_t)(budget / 4.0);
 }
 
+// K3 chunks: per-pair strip records, progress/done words, per-strip results, slabs
+int stage_k3(bsq_ctx* ctx, BufSet& B, const Plan& P, cudaStream_t st) {
+  if (P.k3.empty()) return BSQ_SUCCESS;
+  const bool ok = B.k3pairs.ensure(sizeof(BsqK3Pair) * P.k3.size()) &&
+                  B.k3sync.ensure(4 * (size_t)(P.k3_max_pairs + 1)) &&
+                  B.k3res.ensure(sizeof(BsqK3Res) * (size_t)(P.k3_max_strips + 1)) &&
+                  B.colh.ensure(16 * (size_t)(P.k3_max_slab + 1));
+  if (!ok) return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (wide-band strips)");
+  BSQ_CK(ctx, cudaMemcpyAsync(B.k3pairs.p, P.k3.data(), sizeof(BsqK3Pair) * P.k3.size(), cudaMemcpyHostToDevice, st));
+  ctx->tm.h2d_bytes += (int64_t)(sizeof(BsqK3Pair) * P.k3.size());
+  return BSQ_SUCCESS;
+}
+
 // upload everything the kernels read; size the output arrays
 int stage_inputs(bsq_ctx* ctx, BufSet& B, Plan& P, const uint8_t* codes, int64_t ncodes, bool single_chunk) {
   const int64_t N = P.N, E = (int64_t)P.E;
@@ -547,7 +610,7 @@ int stage_inputs(bsq_ctx* ctx, BufSet& B, Plan& P, const uint8_t* codes, int64_t
   }
   BSQ_CK(ctx, cudaMemsetAsync(B.counters.p, 0, 4 * (P.chunks.size() + 1), st));
   BSQ_CK(ctx, cudaMemsetAsync(B.txlen.p, 0, 4 * (size_t)N, st));
-  return BSQ_SUCCESS;
+  return stage_k3(ctx, B, P, st);
 }
 
 int launch_fill(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, size_t* evi, cudaStream_t stream, bool leave_room) {
@@ -568,6 +631,30 @@ int launch_fill(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, size_t* evi, 
   A.out_ey = B.ey.as<int>();
   A.out_status = B.status.as<int>();
   A.counter = B.counters.as<int>() + ci;
+  if (chunk_is_k3(ch)) {
+    A.k3 = B.k3pairs.as<BsqK3Pair>() + ch.first;
+    A.k3_total = (int)ch.k3_strips;
+    A.k3_done = B.k3sync.as<int>();
+    A.k3_res = B.k3res.as<BsqK3Res>();
+    A.col_h = B.colh.as<double>();
+    BSQ_CK(ctx, cudaMemsetAsync(B.k3sync.p, 0, 4 * (size_t)ch.count, stream));
+    BSQ_CK(ctx, cudaMemsetAsync(B.colh.p, 0, (P.dtype == BSQ_DTYPE_I32 ? 8 : 16) * (size_t)ch.k3_slab, stream));
+    // workers: twice the strips in flight with full pipelines (the rest would only poll), at
+    // most 16 warps per SM; any number is deadlock-free because strips are claimed in order
+    const int wpb = BSQ_K3_THREADS / 32;
+    int64_t workers = std::min<int64_t>(ch.k3_strips, std::max<int64_t>(2 * ch.k3_active, 64));
+    workers = std::min<int64_t>(workers, (int64_t)ctx->sms * 16);
+    const int grid = (int)std::max<int64_t>((workers + wpb - 1) / wpb, 1);
+    cudaEvent_t e0 = get_event(ctx, (*evi)++), e1 = get_event(ctx, (*evi)++);
+    BSQ_CK(ctx, cudaEventRecord(e0, stream));
+    if (k3_op(P.dtype, ch.cfg - BSQ_K2_NCFG, P.prm.type, P.gosign, grid, stream, &A) < 0)
+      return fail(ctx, BSQ_ERR_ARG, "no kernel variant for this configuration");
+    BSQ_CK(ctx, cudaGetLastError());
+    BSQ_CK(ctx, cudaEventRecord(e1, stream));
+    ctx->tm.fill_launches++;
+    ctx->tm.ptr_bytes += 4 * ch.ptr_words;
+    return BSQ_SUCCESS;
+  }
   const int G = ch.family == 1 ? BSQ_K1_CFGS[ch.cfg].G : BSQ_K2_CFGS[ch.cfg].G;
   // per-cell end search: ungated when every gap move lowers (or keeps) the score, so that
   // the -inf padding columns can never beat a real cell; explicitly gated otherwise
@@ -613,8 +700,10 @@ int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, cudaStream_t
   T.pairs = B.pairs.as<BsqPair>() + ch.first;
   T.npairs = (int)ch.count;
   T.mode = P.prm.mode;
-  T.G = ch.family == 1 ? BSQ_K1_CFGS[ch.cfg].G : BSQ_K2_CFGS[ch.cfg].G;
-  T.K = ch.family == 1 ? BSQ_K1_CFGS[ch.cfg].K : BSQ_K2_CFGS[ch.cfg].C;
+  const bool k3 = chunk_is_k3(ch);
+  T.family = k3 ? 3 : ch.family;
+  T.G = k3 ? 32 : (ch.family == 1 ? BSQ_K1_CFGS[ch.cfg].G : BSQ_K2_CFGS[ch.cfg].G);
+  T.K = k3 ? BSQ_K3_CFGS[ch.cfg - BSQ_K2_NCFG].K : (ch.family == 1 ? BSQ_K1_CFGS[ch.cfg].K : BSQ_K2_CFGS[ch.cfg].C);
   T.gosign = P.gosign;
   T.ptr = B.ptr.as<uint32_t>() + (P.half_words > 0 ? (int64_t)(ci & 1) * P.half_words : 0);
   T.ex = B.ex.as<int>();
@@ -631,7 +720,14 @@ int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, cudaStream_t
   bool warp_walk = avg_path >= 1024;
   if (force && force[0] == 't') warp_walk = false;
   if (force && force[0] == 'w') warp_walk = true;
-  if (warp_walk) {
+  if (k3) {  // one warp per pair over the [strip][t][lane] table
+    const int grid = (int)ch.count;
+#define BSQ_WALK3(KK) { if (P.gosign < 0) BSQ_LAUNCH((bsq_k3_walk<KK, -1>), grid, 32, 0, stream, T); \
+                        else if (P.gosign == 0) BSQ_LAUNCH((bsq_k3_walk<KK, 0>), grid, 32, 0, stream, T); \
+                        else BSQ_LAUNCH((bsq_k3_walk<KK, 1>), grid, 32, 0, stream, T); }
+    if (T.K == 2) BSQ_WALK3(2) else if (T.K == 4) BSQ_WALK3(4) else BSQ_WALK3(8)
+#undef BSQ_WALK3
+  } else if (warp_walk) {
     const int grid = (int)((ch.count + BSQ_WALK_WARPS - 1) / BSQ_WALK_WARPS);
 #define BSQ_WALK(F, GS) BSQ_LAUNCH((bsq_k4_walk<F, GS>), grid, 32 * BSQ_WALK_WARPS, 0, stream, T)
     if (ch.family == 1) { if (P.gosign < 0) BSQ_WALK(1, -1); else if (P.gosign == 0) BSQ_WALK(1, 0); else BSQ_WALK(1, 1); }
@@ -1052,6 +1148,8 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
   } else {
     BSQ_CK(ctx, cudaMemcpyAsync(B.subst.p, P.subst.data(), 8 * (size_t)L * L, cudaMemcpyHostToDevice, sx));
   }
+  rc = stage_k3(ctx, B, P, sx);
+  if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(sx); return rc; }
   cudaEvent_t ev_pairs = get_event(ctx, evi++);
   BSQ_CK(ctx, cudaEventRecord(ev_pairs, sx));
 
@@ -1251,6 +1349,15 @@ void bsq_release(bsq_batch* b) {
   if (b->own_bufs) b->bufs.release();
   delete b;
 }
+
+#ifdef BSQ_K3_PROFILE
+// tuning builds only (not declared in bsqgpu.h): raw per-strip records of the last K3 launch
+int bsq_debug_k3_res(bsq_batch* b, void* out, int64_t bytes) {
+  if (!b || !b->ctx || !b->B->k3res.p) return BSQ_ERR_ARG;
+  if ((size_t)bytes > b->B->k3res.cap) bytes = (int64_t)b->B->k3res.cap;
+  return cudaMemcpy(out, b->B->k3res.p, (size_t)bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? (int)sizeof(BsqK3Res) : BSQ_ERR_CUDA;
+}
+#endif
 
 int bsq_microbench(bsq_ctx* ctx, int32_t which, double* ops_per_sec) {
   if (!ctx || !ops_per_sec) return BSQ_ERR_ARG;

@@ -1,0 +1,382 @@
+// bsq_k3.cuh -- K3: BANDED frame with a band of ANY width (config 5: one
+// 1 Mb x 1 Mb pair, 4097 diagonals), intra-task wavefront.
+//
+// The band is cut into column strips of 32*K mutant positions.  One warp owns
+// a strip and walks it like K1 walks a table: lane l owns K consecutive columns
+// and lags its left neighbour by one row, so (x, y-1) arrives by one shuffle per
+// row.  A strip only visits the rows its columns have inside the band
+// (x in [Y+dmin, Y+32K-1+dmax]); cells outside band or table are forced to
+// "does not exist" (-inf).  Strip j+1 consumes the right boundary column of strip
+// j through a per-pair slab in global memory whose 8-byte entries validate
+// themselves (each carries the producing strip's number, so no fence and no flag
+// word is needed: an entry is either the old one or completely the new one), and
+// fetches them 32 rows at a time, one batch ahead.  Successive strips thus run as
+// a software pipeline across the SMs: about (W + 32K) / 32K strips are in flight.  Strips of all pairs of a
+// chunk form ONE ordered work list claimed with an atomic counter -- a strip's
+// predecessor is therefore always held by a resident warp (no deadlock) and
+// several wide pairs overlap without a drain in between.
+//
+// The single-pair case is bound by the dependency chain, not by ALU issue: the
+// last strip cannot finish before ~m * (1 + 1/K) row steps have elapsed.
+//
+// Pointer layout (4 bit/cell): [strip][t][lane], one PU (K nibbles) per lane and
+// time step t = x - x_lo(strip) + lane, i.e. skewed so that a warp writes one
+// contiguous 32*sizeof(PU) segment per step.
+//   replaces: dptable_solve's fill loop pw.c:59-110 over _xlim/_ylim
+//   (_pw_internals.c:116-153) + _banded_find_optimal (:364-414)
+#pragma once
+#include "bsq_kernels.cuh"
+#include "bsq_launch.h"
+
+#ifdef BSQ_SIMT_EMU
+#define BSQ_LD_CG(p) (*(p))
+#define BSQ_ST_CG(p, v) (*(p) = (v))
+#define BSQ_BACKOFF(ns) emu::yield()
+#else
+#define BSQ_LD_CG(p) __ldcg(p)
+#define BSQ_ST_CG(p, v) __stcg((p), (v))
+#define BSQ_BACKOFF(ns) __nanosleep(ns)
+#endif
+
+template <int K> struct BsqK3Unit;
+template <> struct BsqK3Unit<2> { typedef uint8_t type; };
+template <> struct BsqK3Unit<4> { typedef uint16_t type; };
+template <> struct BsqK3Unit<8> { typedef uint32_t type; };
+
+// one cell, band-gated: H = -inf when the cell is outside band/table
+template <class S, int GOS, bool HASB>
+__device__ __forceinline__ void bsq_k3_cell(typename S::T up, int gD, typename S::T left, int gI,
+                                            typename S::T diag, typename S::T sig, typename S::T bval,
+                                            typename S::T go, typename S::T ge, bool inb, typename S::T& H,
+                                            int& fD, int& fI, uint32_t& nib) {
+  typedef typename S::T T;
+  T h;
+  if constexpr (S::IS_INT) {
+    int nB, nD, nI, nM;
+    bsq_cell_i32<GOS, HASB, false>(up, gD, left, gI, diag, sig, bval, go, ge, h, nB, nD, nI, nM);
+    nib = (uint32_t)(15 - (nB + 2 * nD + 4 * nI + 8 * nM));
+    fD = bsq_gapflag_i32<GOS>(nD, nB, nI, nM);
+    fI = bsq_gapflag_i32<GOS>(nI, nB, nD, nM);
+  } else {
+    bool eB, eD, eI, eM;
+    bsq_cell2<S, GOS, HASB>(up, gD, left, gI, diag, sig, bval, go, ge, h, eB, eD, eI, eM);
+    nib = (eB ? BSQ_MB : 0u) | (eD ? BSQ_MD : 0u) | (eI ? BSQ_MI : 0u) | (eM ? BSQ_MM : 0u);
+    fD = bsq_gapflag<S, GOS>(eD, eB, eI, eM);
+    fI = bsq_gapflag<S, GOS>(eI, eB, eD, eM);
+  }
+  H = inb ? h : S::ninf();
+}
+
+// Boundary-column slab entries: 64-bit words that are written and read whole.
+//   I32: one word per row   = H (32) | opens (1) | tag (31)
+//   F64: two words per row  = lo32(H) | tag (32)   and   hi32(H) | opens (1) | tag (31)
+// tag = 1 + index of the strip that wrote the entry; a reader of strip j accepts tag == j.
+template <class S> struct BsqK3Slab;
+template <> struct BsqK3Slab<ScI32> {
+  static constexpr int EPR = 1;
+  struct Raw { unsigned long long e0; };
+  static __device__ __forceinline__ void put(unsigned long long* row, int H, int opens, unsigned tag) {
+    BSQ_ST_CG(row, (unsigned long long)(unsigned)H | ((unsigned long long)(opens ? 1u : 0u) << 32) |
+                       ((unsigned long long)tag << 33));
+  }
+  static __device__ __forceinline__ Raw load(const unsigned long long* row) { Raw r; r.e0 = BSQ_LD_CG(row); return r; }
+  static __device__ __forceinline__ bool decode(const Raw& r, unsigned tag, int& H, int& opens) {
+    H = (int)(unsigned)r.e0;
+    opens = (int)((r.e0 >> 32) & 1ull);
+    return (unsigned)(r.e0 >> 33) == tag;
+  }
+};
+template <> struct BsqK3Slab<ScF64> {
+  static constexpr int EPR = 2;
+  struct Raw { unsigned long long e0, e1; };
+  static __device__ __forceinline__ void put(unsigned long long* row, double H, int opens, unsigned tag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(H);
+    BSQ_ST_CG(row, (b & 0xffffffffull) | ((unsigned long long)tag << 32));
+    BSQ_ST_CG(row + 1, (b >> 32) | ((unsigned long long)(2u * tag + (opens ? 1u : 0u)) << 32));
+  }
+  static __device__ __forceinline__ Raw load(const unsigned long long* row) {
+    Raw r; r.e0 = BSQ_LD_CG(row); r.e1 = BSQ_LD_CG(row + 1); return r;
+  }
+  static __device__ __forceinline__ bool decode(const Raw& r, unsigned tag, double& H, int& opens) {
+    H = __longlong_as_double((long long)((r.e1 << 32) | (r.e0 & 0xffffffffull)));
+    opens = (int)((r.e1 >> 32) & 1ull);
+    return (unsigned)(r.e0 >> 32) == tag && (unsigned)(r.e1 >> 33) == tag;
+  }
+};
+
+// BT = banded_alntype (BSQ_B_GLOBAL 0 / BSQ_B_LOCAL 1 / BSQ_B_OVERLAP 2)
+template <class S, int K, int BT, int GOS>
+__global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3_fill(const BsqFillArgs A) {
+  typedef typename S::T T;
+  typedef typename BsqK3Unit<K>::type PU;
+  typedef BsqK3Slab<S> Slab;
+  constexpr int G = 32, BW = G * K;
+  constexpr int NB = (BT == BSQ_B_LOCAL) ? K : 1;
+  __shared__ T s_sub[BSQ_MAX_L * BSQ_MAX_L];
+  __shared__ T s_inH[BSQ_K3_THREADS / 32][32];    // the batch of boundary values lane 0 consumes
+  __shared__ int s_inG[BSQ_K3_THREADS / 32][32];
+  const int L = A.L;
+  for (int i = threadIdx.x; i < L * L; i += blockDim.x) s_sub[i] = ((const T*)A.subst)[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const unsigned FULL = 0xffffffffu;
+  const T NINF = S::ninf();
+  const T ZERO = (T)0;
+  const T go = S::go(A), ge = S::ge(A);
+  unsigned long long* slab_all = (unsigned long long*)A.col_h;
+  int p = 0;
+
+  for (;;) {
+    int g = 0;
+    if (lane == 0) g = atomicAdd(A.counter, 1);
+    g = __shfl_sync(FULL, g, 0);
+    if (g >= A.k3_total) break;
+#ifdef BSQ_K3_PROFILE
+    long long pf_claim, pf_ready = 0, pf_wait = 0;
+    int pf_polls = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pf_claim));
+#endif
+    while (g >= A.k3[p].strip_base + A.k3[p].nstrips) p++;  // claims only grow
+    const BsqPair P = A.pairs[p];
+    const BsqK3Pair Q = A.k3[p];
+    const int j = g - Q.strip_base;
+    const int n = P.n, m = P.m, dmin = P.dmin, dmax = P.dmax;
+    const int Wm1 = dmax - dmin;
+    const int Y = j * BW;
+    const int ylast = (Y + BW - 1 < m) ? (Y + BW - 1) : m;
+    int x_lo = Y + dmin;
+    x_lo = x_lo < 0 ? 0 : x_lo;
+    int x_hi = ylast + dmax;
+    x_hi = x_hi > n ? n : x_hi;
+    const bool has_succ = (j + 1 < Q.nstrips);
+    // rows whose (x, Y-1) lies inside the band, i.e. the rows the predecessor strip wrote to
+    // the slab: [pred_lo, pred_hi] (empty for strip 0)
+    int pred_hi = -1;
+    if (j > 0) { pred_hi = Y - 1 + dmax; pred_hi = pred_hi > n ? n : pred_hi; }
+    int pred_lo = Y - BW + dmin;
+    pred_lo = pred_lo < 0 ? 0 : pred_lo;
+    unsigned long long* slab = slab_all + Q.slab_off * Slab::EPR;
+    const unsigned tag_in = (unsigned)j, tag_out = (unsigned)j + 1u;
+
+    T bs = NINF;                     // lane's best end-cell candidate of this strip
+    int bk1 = BSQ_INT_MAX, bk2 = BSQ_INT_MAX;
+
+    if (x_lo <= x_hi) {
+      const int y0 = Y + lane * K;
+      int moff[K];
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const int y = y0 + k;
+        moff[k] = (y >= 1 && y <= m) ? (int)A.codes[P.m_off + y - 1] : 0;
+      }
+      int kv = m - y0 + 1;           // my columns inside the table
+      kv = kv < 0 ? 0 : (kv > K ? K : kv);
+      const int km = m - y0;         // which of my columns is column m (if in [0,K))
+      T Hup[K];
+      int gD[K];
+      T best[NB];
+      int bestx[NB];
+#pragma unroll
+      for (int k = 0; k < K; k++) { Hup[k] = NINF; gD[k] = 0; }
+#pragma unroll
+      for (int k = 0; k < NB; k++) { best[k] = NINF; bestx[k] = 0; }
+      T lastH = NINF;
+      int lastG = 0;
+      T prev_in = NINF;
+      if (lane == 0 && j > 0) {      // (x_lo - 1, Y - 1): the diagonal neighbour of my first cell
+        const int xd = x_lo - 1;
+        if (xd >= pred_lo && xd <= pred_hi) {
+          unsigned ns = 32;
+          int f;
+          while (!Slab::decode(Slab::load(slab + (long long)xd * Slab::EPR), tag_in, prev_in, f)) { BSQ_BACKOFF(ns); if (ns < 1024) ns *= 2; }
+        }
+      }
+      const int nsteps = (x_hi - x_lo + 1) + G - 1;
+      PU* prow = (PU*)(A.ptr + P.ptr_off) + (long long)j * P.s0 * G + lane;
+      const uint8_t* oseq = A.codes + P.o_off;
+      // software pipeline of the letter / score loads: row x uses o[x-1]
+      auto letter = [&](int xr) -> int { return (xr >= 1 && xr <= n) ? (int)oseq[xr - 1] : 0; };
+      int o1 = letter(x_lo - lane + 1);  // letter of the row after the one being computed
+      T sig[K];
+      {
+        const int ob = letter(x_lo - lane) * L;
+#pragma unroll
+        for (int k = 0; k < K; k++) sig[k] = s_sub[ob + moff[k]];
+      }
+      typename Slab::Raw nx = {};    // prefetched (raw) boundary entry of row x_lo + (next batch) + lane
+      bool nx_have = false;
+
+      for (int t = 0; t < nsteps; t++) {
+        const int x = x_lo + t - lane;
+        if ((t & 31) == 0 && j > 0) {
+          // boundary values of rows x_lo + t .. x_lo + t + 31: mine is row xr (fetched one batch
+          // ahead); rows past pred_hi lie outside the band
+          const int xr = x_lo + t + lane;
+          const bool need = (xr <= pred_hi);
+          T bH = NINF;
+          int bF = 0;
+          bool ok = !need || (nx_have && Slab::decode(nx, tag_in, bH, bF));
+          unsigned ns = 32;
+#ifdef BSQ_K3_PROFILE
+          const long long pf_c0 = clock64();
+#endif
+          while (!__all_sync(FULL, ok)) {
+            if (!ok) {
+              ok = Slab::decode(Slab::load(slab + (long long)xr * Slab::EPR), tag_in, bH, bF);
+              if (!ok) { BSQ_BACKOFF(ns); if (ns < 1024) ns *= 2; }
+            }
+#ifdef BSQ_K3_PROFILE
+            pf_polls++;
+#endif
+          }
+#ifdef BSQ_K3_PROFILE
+          pf_wait += clock64() - pf_c0;
+          if (t == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pf_ready));
+#endif
+          s_inH[wib][lane] = need ? bH : NINF;
+          s_inG[wib][lane] = need ? S::flag(bF == 0) : 0;
+          __syncwarp();
+          const int xn = xr + 32;
+          nx_have = (xn <= pred_hi);
+          if (nx_have) nx = Slab::load(slab + (long long)xn * Slab::EPR);
+        }
+        T inH = __shfl_up_sync(FULL, lastH, 1);
+        int inG = __shfl_up_sync(FULL, lastG, 1);
+        const bool active = (t >= lane) && (x <= x_hi);
+        if (lane == 0) {
+          inH = NINF;
+          inG = 0;
+          if (j > 0) { inH = s_inH[wib][t & 31]; inG = s_inG[wib][t & 31]; }
+        }
+        // loads for the next two rows, off the dependency chain
+        const int o2 = letter(x + 2);
+        T sign[K];
+        {
+          const int ob = o1 * L;
+#pragma unroll
+          for (int k = 0; k < K; k++) sign[k] = s_sub[ob + moff[k]];
+        }
+        if (active) {
+          const int e = x - y0 - dmin;   // cell k is inside the band iff 0 <= e - k <= W - 1
+          // B (_alnchoice_B, _pw_internals.c:182-197): B_LOCAL anywhere, B_OVERLAP on x==0 or y==0,
+          // B_GLOBAL at (0,0) only
+          const bool rowb = (BT == BSQ_B_LOCAL) || (BT == BSQ_B_OVERLAP && x == 0);
+          const T brest = rowb ? ZERO : NINF;
+          const T bfirst = (rowb || (y0 == 0 && (BT == BSQ_B_OVERLAP || x == 0))) ? ZERO : NINF;
+          T left = inH;
+          int gI = inG;
+          T diag = prev_in;
+          uint32_t cw = 0u;
+          if (rowb) {
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+              const bool inb = ((unsigned)(e - k) <= (unsigned)Wm1) && (k < kv);
+              const T up = Hup[k];
+              T H;
+              int fD, fI;
+              uint32_t nib;
+              bsq_k3_cell<S, GOS, true>(up, gD[k], left, gI, diag, sig[k], k == 0 ? bfirst : brest, go, ge, inb,
+                                        H, fD, fI, nib);
+              cw |= nib << (4 * k);
+              gD[k] = fD; gI = fI; diag = up; left = H; Hup[k] = H;
+              if (BT == BSQ_B_LOCAL) { if (H > best[k < NB ? k : 0]) { best[k < NB ? k : 0] = H; bestx[k < NB ? k : 0] = x; } }
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+              const bool inb = ((unsigned)(e - k) <= (unsigned)Wm1) && (k < kv);
+              const T up = Hup[k];
+              T H;
+              int fD, fI;
+              uint32_t nib;
+              if (k == 0) bsq_k3_cell<S, GOS, true>(up, gD[k], left, gI, diag, sig[k], bfirst, go, ge, inb, H, fD, fI, nib);
+              else bsq_k3_cell<S, GOS, false>(up, gD[k], left, gI, diag, sig[k], ZERO, go, ge, inb, H, fD, fI, nib);
+              cw |= nib << (4 * k);
+              gD[k] = fD; gI = fI; diag = up; left = H; Hup[k] = H;
+            }
+          }
+          lastH = left;
+          lastG = gI;
+          prow[(long long)t * G] = (PU)cw;
+          if (lane == G - 1 && has_succ) Slab::put(slab + (long long)x * Slab::EPR, left, gI != 0, tag_out);
+          // end cell, _banded_find_optimal (_pw_internals.c:364-414)
+          if (BT == BSQ_B_GLOBAL) {
+            if (x == n && km >= 0 && km < K) {
+#pragma unroll
+              for (int k = 0; k < K; k++) if (k == km) { bs = Hup[k]; bk1 = n - m; bk2 = n; }
+            }
+          } else if (BT == BSQ_B_OVERLAP) {  // last cell of every diagonal, diagonals ascending, strict >
+            if (x == n) {
+#pragma unroll
+              for (int k = 0; k < K; k++) {
+                const T c = Hup[k];
+                if (c > NINF && bsq_better<T>(c, n - (y0 + k), 0, bs, bk1, bk2)) { bs = c; bk1 = n - (y0 + k); bk2 = 0; }
+              }
+            } else if (km >= 0 && km < K) {
+              T c = NINF;
+#pragma unroll
+              for (int k = 0; k < K; k++) if (k == km) c = Hup[k];
+              if (c > NINF && bsq_better<T>(c, x - m, 0, bs, bk1, bk2)) { bs = c; bk1 = x - m; bk2 = 0; }
+            }
+          }
+        }
+        if (t >= lane) prev_in = inH;
+        o1 = o2;
+#pragma unroll
+        for (int k = 0; k < K; k++) sig[k] = sign[k];
+      }
+      if (BT == BSQ_B_LOCAL) {  // every cell, (d, a) ascending; per column d ascends with x
+#pragma unroll
+        for (int k = 0; k < NB; k++) {
+          const T c = best[k];
+          const int d = bestx[k] - (y0 + k);
+          if (c > NINF && bsq_better<T>(c, d, bestx[k], bs, bk1, bk2)) { bs = c; bk1 = d; bk2 = bestx[k]; }
+        }
+      }
+    }
+
+    bsq_group_best<T, 32>(FULL, bs, bk1, bk2);
+    int last = 0;
+    if (lane == 0) {
+      BsqK3Res r;
+      r.score = S::to_f64(bs);
+      r.k1 = bk1;
+      r.k2 = bk2;
+#ifdef BSQ_K3_PROFILE
+      r.t_claim = pf_claim; r.t_ready = pf_ready; r.wait_clk = pf_wait; r.polls = pf_polls;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(r.t_end));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(r.sm));
+#endif
+      A.k3_res[g] = r;
+      __threadfence();
+      last = (atomicAdd(A.k3_done + p, 1) == Q.nstrips - 1);
+    }
+    last = __shfl_sync(FULL, last, 0);
+    if (last) {  // this warp finished the pair's last open strip: pick the end cell
+      __threadfence();
+      double fs = ScF64::ninf();
+      int f1 = BSQ_INT_MAX, f2 = BSQ_INT_MAX;
+      for (int i = lane; i < Q.nstrips; i += 32) {
+        const BsqK3Res* rp = A.k3_res + Q.strip_base + i;
+        const double sc = BSQ_LD_CG(&rp->score);
+        const int k1 = BSQ_LD_CG(&rp->k1), k2 = BSQ_LD_CG(&rp->k2);
+        if (k1 != BSQ_INT_MAX && (f1 == BSQ_INT_MAX || bsq_better<double>(sc, k1, k2, fs, f1, f2))) { fs = sc; f1 = k1; f2 = k2; }
+      }
+      bsq_group_best<double, 32>(FULL, fs, f1, f2);
+      if (lane == 0) {
+        int ex = -1, ey = -1, st = BSQ_OK;
+        if (f1 == BSQ_INT_MAX) { st = BSQ_NO_ALIGNMENT; fs = 0.0; }
+        else if (BT == BSQ_B_LOCAL) { ex = f2; ey = f2 - f1; }
+        else if (BT == BSQ_B_GLOBAL) { ex = n; ey = m; }
+        else { ex = n < m + f1 ? n : m + f1; ey = ex - f1; }
+        const int oi = P.pad;
+        A.out_score[oi] = fs;
+        A.out_ex[oi] = ex;
+        A.out_ey[oi] = ey;
+        A.out_status[oi] = st;
+      }
+    }
+  }
+}
+

@@ -10,10 +10,16 @@
 struct BsqK1Cfg { int G, K; };   // STD: G lanes x K columns per pass
 struct BsqK2Cfg { int G, C; };   // BANDED: G lanes x C diagonals
 
+struct BsqK3Cfg { int G, K; };   // BANDED, any width: strips of G*K columns, one warp each
+
 #define BSQ_K1_NCFG 3
 #define BSQ_K2_NCFG 6
 static const BsqK1Cfg BSQ_K1_CFGS[BSQ_K1_NCFG] = {{8, 19}, {16, 16}, {32, 16}};
 static const BsqK2Cfg BSQ_K2_CFGS[BSQ_K2_NCFG] = {{8, 8}, {8, 18}, {16, 10}, {16, 16}, {32, 16}, {32, 32}};
+
+#define BSQ_K3_NCFG 3
+static const BsqK3Cfg BSQ_K3_CFGS[BSQ_K3_NCFG] = {{32, 2}, {32, 4}, {32, 8}};
+#define BSQ_K3_THREADS 64     // two independent strip workers per block
 
 enum { BSQ_OP_OCCUPANCY = 0, BSQ_OP_LAUNCH = 1 };
 
@@ -24,3 +30,6 @@ int bsq_k1_f64_op(int cfg, int ball, int eall, int gos, int op, int grid, cudaSt
 int bsq_k1_i32_op(int cfg, int ball, int eall, int gos, int op, int grid, cudaStream_t st, const BsqFillArgs* A);
 int bsq_k2_f64_op(int cfg, int blocal, int gos, int op, int grid, cudaStream_t st, const BsqFillArgs* A);
 int bsq_k2_i32_op(int cfg, int blocal, int gos, int op, int grid, cudaStream_t st, const BsqFillArgs* A);
+// K3 (cfg = index into BSQ_K3_CFGS): launches on `grid` blocks of BSQ_K3_THREADS
+int bsq_k3_f64_op(int cfg, int btype, int gos, int grid, cudaStream_t st, const BsqFillArgs* A);
+int bsq_k3_i32_op(int cfg, int btype, int gos, int grid, cudaStream_t st, const BsqFillArgs* A);

@@ -2,6 +2,7 @@
 // kernel.  Included by exactly one translation unit (bsq_host.cu).
 #pragma once
 #include "bsq_kernels.cuh"
+#include "bsq_k3.cuh"
 
 // ===========================================================================
 // K4: traceback (pw.c:116-151).  One thread per pair walks the 4-bit masks
@@ -226,6 +227,110 @@ __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTrac
     if (lane == 0) wr[-len] = ch;
   }
 #undef BSQ_RECOL
+  if (lane == 0) {
+    A.txlen[oi] = len;
+    A.sx[oi] = x;
+    A.sy[oi] = y;
+    A.status[oi] = (ex + ey - len <= 0) ? BSQ_REF_WOULD_ABORT : (len == 0 ? BSQ_EMPTY : BSQ_OK);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K3 traceback (pw.c:116-151): one warp per pair walks the [strip][t][lane]
+// table out of shared-memory tiles (the rows at and below the current step of
+// the current strip), like bsq_k4_walk.
+// ---------------------------------------------------------------------------
+#define BSQ_K3_TILE_BYTES 8192
+#define BSQ_K3_LET_WIN 128
+
+template <int K, int GOS>
+__global__ void __launch_bounds__(32) bsq_k3_walk(const BsqTraceArgs A) {
+  typedef typename BsqK3Unit<K>::type PU;
+  constexpr int G = 32, BW = G * K;
+  constexpr int TSTEPS = BSQ_K3_TILE_BYTES / (G * (int)sizeof(PU));
+  __shared__ uint4 s_tile4[BSQ_K3_TILE_BYTES / 16];
+  __shared__ uint8_t s_let[2][BSQ_K3_LET_WIN];
+  PU* tile = (PU*)s_tile4;
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x;
+  if (p >= A.npairs) return;
+  const BsqPair P = A.pairs[p];
+  const int oi = P.pad;
+  if (A.status[oi] != BSQ_OK) {
+    if (lane == 0) { A.txlen[oi] = 0; A.sx[oi] = -1; A.sy[oi] = -1; }
+    return;
+  }
+  const int ex = A.ex[oi], ey = A.ey[oi];
+  int x = ex, y = ey, len = 0;
+  int j = y / BW, l = (y - j * BW) / K, k = y - j * BW - l * K;
+  int xlo = j * BW + P.dmin;
+  xlo = xlo < 0 ? 0 : xlo;
+  int t = x - xlo + l;
+  const long long tstride = P.s0;
+  const PU* table = (const PU*)(A.ptr + P.ptr_off);
+  const uint8_t* oseq = A.codes + P.o_off;
+  const uint8_t* mseq = A.codes + P.m_off;
+  char* wr = A.slots + P.tx_slot + (long long)P.n + P.m;
+  const int maxlen = P.n + P.m;
+  int tlo = 1, thi = 0;          // staged steps [tlo, thi] of strip j (empty)
+  uint8_t* obuf = s_let[0];
+  uint8_t* mbuf = s_let[1];
+  int xb = x + 1, yb = y + 1;    // obuf holds o[xb .. xb+WIN), mbuf m[yb .. yb+WIN); empty
+  uint32_t arrive = BSQ_MM;
+  for (;;) {
+    if (t < tlo || t > thi) {    // stage the steps at and below t
+      thi = t;
+      tlo = t - TSTEPS + 1;
+      tlo = tlo < 0 ? 0 : tlo;
+      const uint4* src = (const uint4*)(table + ((long long)j * tstride + tlo) * G);
+      const int n16 = (thi - tlo + 1) * G * (int)sizeof(PU) / 16;
+      __syncwarp();
+      for (int i = lane; i < n16; i += 32) s_tile4[i] = src[i];
+      __syncwarp();
+    }
+    const uint32_t mk = ((uint32_t)tile[(t - tlo) * G + l] >> (4 * k)) & 0xFu;
+    const uint32_t op = (arrive == BSQ_MM) ? bsq_lowest(mk) : bsq_gap_base_t<GOS>(mk, arrive);
+    if (op == BSQ_MB || op == 0u || len >= maxlen) break;
+    char ch;
+    bool left_col = false;       // the move leaves column y
+    if (op == BSQ_MM) {
+      if (x - 1 < xb) {          // the walk only moves towards smaller x and y
+        xb = x - BSQ_K3_LET_WIN; if (xb < 0) xb = 0;
+        __syncwarp();
+        for (int i = lane; i < BSQ_K3_LET_WIN; i += 32) if (xb + i < P.n) obuf[i] = oseq[xb + i];
+        __syncwarp();
+      }
+      if (y - 1 < yb) {
+        yb = y - BSQ_K3_LET_WIN; if (yb < 0) yb = 0;
+        __syncwarp();
+        for (int i = lane; i < BSQ_K3_LET_WIN; i += 32) if (yb + i < P.m) mbuf[i] = mseq[yb + i];
+        __syncwarp();
+      }
+      ch = (obuf[x - 1 - xb] == mbuf[y - 1 - yb]) ? 'M' : 'S';
+      x--; y--; t--;
+      left_col = true;
+    } else if (op == BSQ_MD) {
+      ch = 'D'; x--; t--;
+    } else {
+      ch = 'I'; y--;
+      left_col = true;
+    }
+    if (left_col && --k < 0) {
+      k = K - 1;
+      t--;
+      if (--l < 0) {             // into the previous strip
+        l = G - 1;
+        j--;
+        xlo = j * BW + P.dmin;
+        xlo = xlo < 0 ? 0 : xlo;
+        t = x - xlo + l;
+        tlo = 1; thi = 0;
+      }
+    }
+    arrive = op;
+    len++;
+    if (lane == 0) wr[-len] = ch;
+  }
   if (lane == 0) {
     A.txlen[oi] = len;
     A.sx[oi] = x;

@@ -121,12 +121,38 @@ def run_banded_interior(eng, seed, length=260, npairs=4):
                 check_batch(eng, probs)
 
 
-def run_unsupported_band(eng):
-    o = np.zeros(1500, np.uint8)
-    pr = dict(origin=o, mutant=o, subst=np.eye(4), go=0.0, ge=-1.0, mode=1, type=2,
-              diag_range=(-600, 600))
-    r = engine_batch(eng, [pr])
-    assert int(r.status[0]) == batch.UNSUPPORTED
+def run_very_wide_bands(eng, seed, length=1300, radius=560, npairs=1):
+    """Bands wider than the 1024 diagonals of the widest K2 geometry go to K3 (strips)."""
+    rng = np.random.default_rng(seed)
+    for typ in (0, 1, 2):
+        probs = make_batch(rng, npairs, 1, typ, length, length + 40, family=int(rng.integers(1, 3)),
+                           gomode=int(rng.integers(-1, 2)), band=radius)
+        check_batch(eng, probs)
+
+
+def run_forced_k3(make_engine, seed, count=150, cfgs=(0, 1, 2)):
+    """The strip kernel on every banded problem, all three strip geometries."""
+    os.environ['BSQ_FORCE_K3'] = '1'
+    try:
+        for cfg in cfgs:
+            os.environ['BSQ_K3_CFG'] = str(cfg)
+            eng = make_engine()
+            try:
+                rng = np.random.default_rng(seed + cfg)
+                probs = []
+                while len(probs) < count:
+                    pr = random_problem(rng, max_len=40)
+                    if pr['mode'] == 1:
+                        probs.append(pr)
+                check_problems(eng, probs)
+                for typ in (0, 1, 2):
+                    check_batch(eng, make_batch(rng, 9, 1, typ, 0, 150))
+                run_banded_interior(eng, seed=seed + 7 + cfg, length=330, npairs=2)
+            finally:
+                eng.close()
+    finally:
+        del os.environ['BSQ_FORCE_K3']
+        os.environ.pop('BSQ_K3_CFG', None)
 
 
 def run_dtype_equivalence(eng, seed, npairs=12, lo=5, hi=60):

@@ -243,6 +243,13 @@ inline unsigned __ballot_sync(unsigned mask_, int pred) {
   return r;
 }
 inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+inline int __all_sync(unsigned m, int pred) {
+  emu::Block* b = emu::cur_block();
+  int nl = b->warps[b->cur / 32].nlanes;
+  unsigned want = m;
+  if (nl < 32) want &= (1u << nl) - 1u;
+  return __ballot_sync(m, pred) == want;
+}
 
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }

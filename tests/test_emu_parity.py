@@ -48,8 +48,12 @@ def test_emu_warp_traceback(emu_lib, monkeypatch):
         eng.close()
 
 
-def test_emu_unsupported_band(emu_engine):
-    pc.run_unsupported_band(emu_engine)
+def test_emu_very_wide_band(emu_engine):
+    pc.run_very_wide_bands(emu_engine, seed=91, length=1100, radius=530)
+
+
+def test_emu_forced_k3(emu_lib):
+    pc.run_forced_k3(lambda: batch.Engine(0, lib=emu_lib), seed=95, count=120)
 
 
 def test_emu_dtype_equivalence(emu_engine):

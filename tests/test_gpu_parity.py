@@ -59,8 +59,13 @@ def test_gpu_both_traceback_kernels(monkeypatch):
             eng.close()
 
 
-def test_gpu_unsupported_band(gpu_engine):
-    pc.run_unsupported_band(gpu_engine)
+def test_gpu_very_wide_bands(gpu_engine):
+    pc.run_very_wide_bands(gpu_engine, seed=91, length=1300, radius=560, npairs=3)
+    pc.run_very_wide_bands(gpu_engine, seed=92, length=5000, radius=1500, npairs=2)
+
+
+def test_gpu_forced_k3():
+    pc.run_forced_k3(lambda: batch.Engine(0), seed=95, count=400)
 
 
 def test_gpu_dtype_equivalence(gpu_engine):
@@ -161,3 +166,41 @@ def test_gpu_banded_memory_1e6(gpu_engine):
     codes = np.concatenate([np.zeros(Ln, np.uint8), np.ones(Ln, np.uint8)])
     r = gpu_engine.align(codes, [0], [Ln], [Ln], [Ln], 1, 0, np.eye(4), 0, 0, dmin=[0], dmax=[0])
     assert int(r.status[0]) == 0 and r.transcript(0) == 'S' * Ln
+
+
+@pytest.mark.parametrize('kind', ['c5s_int', 'c5s_logodds'])
+def test_gpu_c5_scaled_vs_oracle(gpu_engine, kind):
+    """configs[4] scaled to 65 kb x 65 kb (radius 2048 -> K3, the strip-pipelined kernel):
+    the size the CPU oracle finishes in seconds."""
+    w = _workload(kind, 2, seed=6)
+    r = gpu_engine.align(w['codes'], w['o_off'], w['o_len'], w['m_off'], w['m_len'], w['mode'],
+                         w['type'], w['subst'], w['go'], w['ge'], dmin=w.get('dmin'), dmax=w.get('dmax'))
+    e = lean.align_batch(w['mode'], w['type'], w['subst'], w['go'], w['ge'], w['codes'], w['o_off'],
+                         w['o_len'], w['m_off'], w['m_len'], w.get('dmin'), w.get('dmax'))
+    assert np.array_equal(r.status, e['status']) and (r.status == 0).all()
+    assert np.array_equal(r.score, e['score'])
+    assert np.array_equal(r.end_x, e['end_x']) and np.array_equal(r.end_y, e['end_y'])
+    assert np.array_equal(r.start_x, e['start_x']) and np.array_equal(r.start_y, e['start_y'])
+    assert r.transcripts() == lean.transcripts(e)
+
+
+@pytest.mark.parametrize('kind', ['c5_int', 'c5_logodds'])
+def test_gpu_c5_full_size_vs_golden(gpu_engine, kind):
+    """configs[4] at full size: one 1 Mb x 1 Mb B_GLOBAL pair, radius 2048 (4.1e9 cells),
+    against the oracle's answer recorded by tests/golden/make_c5_golden.py."""
+    import hashlib
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'c5_golden.json')) as f:
+        g = json.load(f)[kind]
+    w = _workload(kind, 1, seed=g['seed'])
+    assert (int(w['o_len'][0]), int(w['m_len'][0])) == (g['n'], g['m'])
+    r = gpu_engine.align(w['codes'], w['o_off'], w['o_len'], w['m_off'], w['m_len'], w['mode'],
+                         w['type'], w['subst'], w['go'], w['ge'], dmin=w.get('dmin'), dmax=w.get('dmax'))
+    assert int(r.status[0]) == g['status']
+    assert float(r.score[0]).hex() == g['score_hex']
+    assert [int(r.end_x[0]), int(r.end_y[0])] == g['end']
+    assert [int(r.start_x[0]), int(r.start_y[0])] == g['start']
+    tx = r.transcript(0)
+    assert len(tx) == g['tx_len'] and {c: tx.count(c) for c in 'MSID'} == g['ops']
+    assert hashlib.sha256(tx.encode()).hexdigest() == g['tx_sha256']

@@ -17,7 +17,8 @@ STATUS_NAMES = {
 }
 OK, NO_ALIGNMENT, EMPTY, INIT_FAIL, REF_WOULD_ABORT, UNSUPPORTED = 0, 1, 2, 3, 4, 5
 DTYPE_F64, DTYPE_I32, DTYPE_AUTO = 0, 1, -1
-DTYPE_NAMES = {0: 'f64', 1: 'i32'}
+DTYPE_I16X2 = 2
+DTYPE_NAMES = {0: 'f64', 1: 'i32', 2: 'i16x2'}
 
 
 def _ptr(a, ctype):

@@ -22,6 +22,12 @@
 #define BSQ_MI 4u
 #define BSQ_MM 8u
 
+// Words per lane per row of the K1 pointer layout, rounded up to a power of two: a lane then
+// writes its row with ONE aligned vector store and a group's row is a whole number of full 32-byte
+// sectors.  (Three separate 4-byte stores per lane put 8x the bytes on the L1->L2 path as partial
+// sectors and cost more than the fill's arithmetic: profiles/r01_k1h_store_experiment.txt.)
+#define BSQ_K1_WPL(K) ((((K) + 7) / 8) == 3 ? 4 : (((K) + 7) / 8))
+
 #define BSQ_MAX_L 32  // largest alphabet the kernels stage in shared memory
 
 // where B (start of alignment) is allowed: _alnchoice_B, _pw_internals.c:161-209
@@ -40,6 +46,13 @@ struct BsqPair {         // one problem of a chunk, device resident
   int dmin, dmax;        // clipped band (BANDED)
   int s0;                // K2: first anti-diagonal x+y the kernel visits; K3: time steps per strip
   int pad;
+};
+
+// every pair of the batch has this shape (uniform batches: records are built on the device)
+struct BsqUniform {
+  int n, m, dmin, dmax, s0;
+  long long words;       // pointer-table words per pair
+  long long ppc;         // pairs per chunk (ptr_off restarts at every chunk)
 };
 
 // K3 (strip-pipelined wide bands): what a pair needs beyond BsqPair

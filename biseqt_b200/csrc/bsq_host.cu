@@ -59,11 +59,11 @@ struct PinBuf {
 
 struct BufSet {  // everything one batch needs in HBM
   DevBuf codes, pairs, ptr, slots, packed, score, ex, ey, sx, sy, status, txlen, txoff, tiles,
-      subst, counters, colh, colf, total, k3pairs, k3sync, k3res;
+      subst, counters, colh, colf, total, k3pairs, k3sync, k3res, ooff, moff;
   PinBuf hpairs, hsmall;
   void release() {
     DevBuf* all[] = {&codes, &pairs, &ptr, &slots, &packed, &score, &ex, &ey, &sx, &sy, &status,
-                     &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res};
+                     &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff};
     for (DevBuf* b : all) b->release();
     hpairs.release();
     hsmall.release();
@@ -78,6 +78,7 @@ struct Chunk {
   int max_n_multipass;   // K1: longest origin among pairs needing > 1 pass (0 if none)
   int64_t idx_lo, idx_hi; // caller indices [idx_lo, idx_hi) covered (identity order only)
   int64_t code_end;      // one past the last byte of codes[] this chunk reads
+  bool duo = false;      // K1h: pairs (2q, 2q+1) share a lane group, packed 16-bit arithmetic
   int64_t k3_strips = 0; // K3: strips in the chunk's work list
   int64_t k3_slab = 0;   // K3: boundary-column slab entries (sum of n+1)
   int64_t k3_active = 0; // K3: strips in flight when every pair's pipeline is full
@@ -113,6 +114,12 @@ struct Plan {
   int64_t total_words = 0;
   bool identity = false;  // processing order == caller order (no sort was needed)
   int64_t half_words = 0; // > 0: two arena halves, chunk c uses half (c & 1) so trace(c) overlaps fill(c+1)
+  // uniform batches (every pair the same shape, e.g. fixed-length reads): the pair records are
+  // built ON THE DEVICE from the caller's offset arrays (bsq_make_pairs_uniform); pairs == nullptr
+  bool uniform_dev = false;
+  BsqUniform uni;
+  const int64_t* src_o_off = nullptr;
+  const int64_t* src_m_off = nullptr;
   std::vector<BsqK3Pair> k3;  // per pair record (processing order); empty when no pair uses K3
   int64_t k3_max_strips = 0, k3_max_slab = 0, k3_max_pairs = 0;  // maxima over chunks
 };
@@ -124,6 +131,7 @@ struct bsq_ctx {
   int sms = 1;
   cudaStream_t st = nullptr;       // compute
   cudaStream_t st_copy = nullptr;  // H2D / D2H, so copies overlap kernels
+  cudaStream_t st_copy2 = nullptr; // pair records / score table: must not queue behind the sequence bytes
   cudaStream_t st_trace = nullptr; // traceback + packing of chunk c while chunk c+1 fills
   PinBuf htotals;                  // pinned: running transcript totals per chunk
   std::vector<PlanItem> plan_items;  // planner scratch, kept across calls (no page faults)
@@ -331,18 +339,175 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   const int family = prm->mode == BSQ_STD_MODE ? 1 : 2;
   const int btype = prm->type;
 
-  // geometry depends on the arithmetic; decide it up front from the scores alone (lengths
-  // only matter for the overflow bound, checked again below with the real maxima)
+  // one parallel pass over the lengths: maxima (for the arithmetic / overflow decisions), input
+  // validation, and whether every pair has the same shape
+  struct Scan { int64_t max_n = 0, max_m = 0; int bad = 0, uniform = 1; };
+  std::vector<Scan> scans(16);
+  {
+    const int n0 = N ? o_len[0] : 0, m0 = N ? m_len[0] : 0;
+    const int lo0 = (N && family == 2) ? dmin[0] : 0, hi0 = (N && family == 2) ? dmax[0] : 0;
+    parallel_for(N, [&](int t, int64_t i0, int64_t i1) {
+      Scan sc;
+      for (int64_t i = i0; i < i1; i++) {
+        const int n = o_len[i], m = m_len[i];
+        if (n < 0 || m < 0 || o_off[i] < 0 || m_off[i] < 0 || o_off[i] + n > ncodes || m_off[i] + m > ncodes) { sc.bad = 1; continue; }
+        sc.max_n = std::max<int64_t>(sc.max_n, n);
+        sc.max_m = std::max<int64_t>(sc.max_m, m);
+        if (n != n0 || m != m0 || (family == 2 && (dmin[i] != lo0 || dmax[i] != hi0))) sc.uniform = 0;
+      }
+      scans[t] = sc;
+    });
+  }
+  int64_t scan_n = 0, scan_m = 0;
+  bool all_uniform = N > 0;
+  for (const Scan& sc : scans) {
+    if (sc.bad) return fail(ctx, BSQ_ERR_ARG, "negative length or sequence range outside codes[]");
+    scan_n = std::max(scan_n, sc.max_n); scan_m = std::max(scan_m, sc.max_m);
+    if (!sc.uniform) all_uniform = false;
+  }
+  // geometry depends on the arithmetic; decide it up front from the scores and maxima
   bool f64_geom = true;
   {
     bsq_params t0 = *prm;
     t0.subst = P.subst.data();
-    int64_t mn = 0, mm = 0;
-    for (int64_t i = 0; i < N; i++) { mn = std::max<int64_t>(mn, o_len[i]); mm = std::max<int64_t>(mm, m_len[i]); }
-    f64_geom = (prm->dtype == BSQ_DTYPE_F64) || !(prm->dtype == BSQ_DTYPE_I32 || scores_int32_exact(&t0, mn, mm));
+    f64_geom = (prm->dtype == BSQ_DTYPE_F64) || !(prm->dtype == BSQ_DTYPE_I32 || scores_int32_exact(&t0, scan_n, scan_m));
   }
+  P.uniform_dev = false;
+  P.pairs = nullptr;
   const bool force_k3 = getenv("BSQ_FORCE_K3") != nullptr;  // test hook: K3 for every band
   const int k3_cfg = pick_k3_cfg();
+  // what dptable_init would make of one problem shape, the kernel geometry, table size, cells
+  auto classify = [&](int n, int m, int dlo, int dhi) -> PlanItem {
+    PlanItem it{};
+    if (family == 1) {
+      it.cfg = pick_k1_cfg(n, m);
+      const int G = BSQ_K1_CFGS[it.cfg].G, K = BSQ_K1_CFGS[it.cfg].K, BW = G * K, WPL = BSQ_K1_WPL(K);
+      const int64_t passes = (m + BW) / BW;
+      it.words = passes * (int64_t)(n + G) * G * WPL;  // rows t = x + lane, see bsq_kernels.cuh
+      it.aux = passes > 1 ? n : 0;
+      it.cells = (int64_t)(n + 1) * (m + 1);
+    } else {
+      int lo = dlo, hi = dhi;
+      if (hi > n) hi = n;   // _pw_internals.c:29-36
+      if (lo < -m) lo = -m;
+      const int dend = n - m;
+      const int64_t W = (int64_t)hi - lo + 1;
+      if (btype == BSQ_B_GLOBAL && (dend > hi || dend < lo || (int64_t)hi * lo > 0)) it.cfg = -1 - BSQ_INIT_FAIL;
+      else if (W < 0) it.cfg = -1 - BSQ_INIT_FAIL;
+      else if (W == 0) it.cfg = -1 - BSQ_NO_ALIGNMENT;
+      else {
+        it.cfg = force_k3 ? -1 : pick_k2_cfg((int)std::min<int64_t>(W, 1 << 30), f64_geom);
+        if (it.cfg < 0) it.cfg = BSQ_K2_NCFG + k3_cfg;
+      }
+      if (it.cfg >= BSQ_K2_NCFG) {  // K3: strips of G*K columns, tstride time steps each
+        it.lo = lo; it.hi = hi;
+        const int K = BSQ_K3_CFGS[it.cfg - BSQ_K2_NCFG].K, G = 32, BW = G * K;
+        const int64_t nstrips = ((int64_t)m + BW) / BW;
+        const int64_t tstride = std::min<int64_t>((int64_t)n + 1, W + BW - 1) + G - 1;
+        it.words = nstrips * tstride * G * (K / 2) / 4;
+        it.aux = (int32_t)tstride;
+        it.cells = count_cells(BSQ_BANDED_MODE, n, m, lo, hi);
+      } else if (it.cfg >= 0) {
+        it.lo = lo; it.hi = hi;
+        const int G = BSQ_K2_CFGS[it.cfg].G, C = BSQ_K2_CFGS[it.cfg].C, WPS = (C / 2 + 7) / 8;
+        const int smin = (lo <= 0 && hi >= 0) ? 0 : std::min(std::abs(lo), std::abs(hi));
+        const int sbase = smin - ((smin - lo) & 1);
+        const int dstar = std::max(lo, std::min(hi, dend));
+        const int s_end = 2 * std::min(n, m + dstar) - dstar;
+        const int64_t steps = (int64_t)(s_end - sbase + 1 + 1) / 2 * 2 + 2;
+        it.words = steps * G * WPS;
+        it.aux = sbase;
+        it.cells = count_cells(BSQ_BANDED_MODE, n, m, lo, hi);
+      }
+    }
+    return it;
+  };
+
+  // ---- fast path: one shape for the whole batch (fixed-length reads).  No per-pair host work:
+  // chunk boundaries are arithmetic and the pair records are generated on the device.
+  const char* umin_env = getenv("BSQ_UNIFORM_MIN");  // test hook
+  const int64_t uniform_min = umin_env ? atoll(umin_env) : 4096;
+  if (all_uniform && N >= uniform_min && N < ((int64_t)1 << 31)) {
+    const PlanItem it = classify(o_len[0], m_len[0], family == 2 ? dmin[0] : 0, family == 2 ? dmax[0] : 0);
+    bsq_params tmp = *prm;
+    tmp.subst = P.subst.data();
+    const bool i32ok = scores_int32_exact(&tmp, scan_n, scan_m);
+    if (prm->dtype == BSQ_DTYPE_I32 && !i32ok)
+      return fail(ctx, BSQ_ERR_ARG, "dtype I32 forced but scores are not int32-exact for these lengths");
+    const int dtype = (prm->dtype == BSQ_DTYPE_F64) ? BSQ_DTYPE_F64 : (i32ok ? BSQ_DTYPE_I32 : BSQ_DTYPE_F64);
+    bool range_ok = true;
+    if (dtype == BSQ_DTYPE_F64) {
+      double maxabs = std::fabs(prm->go) + std::fabs(prm->ge);
+      for (double v : P.subst) maxabs = std::max(maxabs, std::fabs(v));
+      range_ok = (double)(scan_n + scan_m + 4) * maxabs < 2147483647.0;
+    }
+    const bool k3 = family == 2 && it.cfg >= BSQ_K2_NCFG;
+    if (it.cfg >= 0 && !k3 && range_ok && it.words > 0) {
+      P.dtype = dtype;
+      P.overrides.clear();
+      P.k3.clear();
+      P.k3_max_strips = P.k3_max_slab = P.k3_max_pairs = 0;
+      P.identity = true;
+      P.E = N;
+      P.cells = it.cells * N;
+      const int64_t tot_words = it.words * N;
+      if (target_chunks > 1 && !single_chunk) {
+        const int64_t per = std::max<int64_t>(std::max<int64_t>((tot_words + target_chunks - 1) / target_chunks, (int64_t)8 << 20), it.words);
+        arena_words = std::min(arena_words, per);
+      }
+      if (it.words > arena_words) return fail(ctx, BSQ_ERR_NOMEM, "a single pair's traceback table exceeds the device arena");
+      if (single_chunk && tot_words > arena_words)
+        return fail(ctx, BSQ_ERR_NOMEM, "batch does not fit the device arena in two-phase mode; use bsq_align_batch");
+      const int64_t ppc = single_chunk ? N : std::max<int64_t>(1, std::min<int64_t>(N, arena_words / it.words));
+      const int64_t NC = (N + ppc - 1) / ppc;
+      P.chunks.assign((size_t)NC, Chunk{});
+      for (int64_t c = 0; c < NC; c++) {
+        Chunk& ch = P.chunks[(size_t)c];
+        ch.first = c * ppc;
+        ch.count = std::min<int64_t>(ppc, N - ch.first);
+        ch.family = family;
+        ch.cfg = it.cfg;
+        ch.ptr_words = ch.count * it.words;
+        ch.max_n_multipass = family == 1 ? it.aux : 0;
+        ch.idx_lo = ch.first;
+        ch.idx_hi = ch.first + ch.count;
+        ch.code_end = 0;
+      }
+      {  // last byte of codes[] each chunk reads (pairs need not be laid out in order)
+        std::vector<int64_t> ends((size_t)NC * 16, 0);
+        const int n = o_len[0], m = m_len[0];
+        parallel_for(N, [&](int t, int64_t i0, int64_t i1) {
+          for (int64_t i = i0; i < i1; i++) {
+            int64_t& e = ends[(size_t)(i / ppc) * 16 + t];
+            e = std::max(e, std::max(o_off[i] + n, m_off[i] + m));
+          }
+        });
+        for (int64_t c = 0; c < NC; c++)
+          for (int t = 0; t < 16; t++) P.chunks[(size_t)c].code_end = std::max(P.chunks[(size_t)c].code_end, ends[(size_t)c * 16 + t]);
+      }
+      {  // K1h: short reads, small integer scores, STD LOCAL -> two problems per lane
+        double maxabs = std::fabs(prm->go) + std::fabs(prm->ge);
+        for (double v : P.subst) maxabs = std::max(maxabs, std::fabs(v));
+        const bool duo = family == 1 && it.cfg == 0 && dtype == BSQ_DTYPE_I32 && P.bmode == BSQ_B_ALL &&
+                         P.emode == BSQ_E_ALL && prm->go <= 0.0 && prm->ge <= 0.0 && L <= 4 && m_len[0] <= 151 &&
+                         (double)(scan_n + scan_m + 4) * maxabs < 4000.0 && getenv("BSQ_NO_DUO") == nullptr;
+        for (Chunk& ch : P.chunks) ch.duo = duo;
+      }
+      P.max_chunk_words = std::min(ppc, N) * it.words;
+      P.total_words = tot_words;
+      P.slot_bytes = N * ((int64_t)o_len[0] + m_len[0]);
+      P.half_words = (!single_chunk && NC >= 2) ? P.max_chunk_words : 0;
+      P.uniform_dev = true;
+      P.src_o_off = o_off;
+      P.src_m_off = m_off;
+      P.uni.n = o_len[0]; P.uni.m = m_len[0];
+      P.uni.dmin = family == 2 ? it.lo : 0; P.uni.dmax = family == 2 ? it.hi : 0;
+      P.uni.s0 = family == 2 ? it.aux : 0;
+      P.uni.words = it.words;
+      P.uni.ppc = single_chunk ? ((int64_t)1 << 62) : ppc;
+      return BSQ_SUCCESS;
+    }
+  }
   // ---- phase 1 (parallel): classify every pair like dptable_init would ----------
   std::vector<PlanItem>& items = ctx->plan_items;
   if ((int64_t)items.size() < N) items.resize((size_t)N);
@@ -363,48 +528,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
         if (prev.cfg >= 0) pt.cells += prev.cells;
         continue;
       }
-      PlanItem it{};
-      if (family == 1) {
-        it.cfg = pick_k1_cfg(n, m);
-        const int G = BSQ_K1_CFGS[it.cfg].G, K = BSQ_K1_CFGS[it.cfg].K, BW = G * K, WPL = (K + 7) / 8;
-        const int64_t passes = (m + BW) / BW;
-        it.words = passes * (int64_t)(n + 1) * G * WPL;
-        it.aux = passes > 1 ? n : 0;
-        it.cells = (int64_t)(n + 1) * (m + 1);
-      } else {
-        int lo = dlo, hi = dhi;
-        if (hi > n) hi = n;   // _pw_internals.c:29-36
-        if (lo < -m) lo = -m;
-        const int dend = n - m;
-        const int64_t W = (int64_t)hi - lo + 1;
-        if (btype == BSQ_B_GLOBAL && (dend > hi || dend < lo || (int64_t)hi * lo > 0)) it.cfg = -1 - BSQ_INIT_FAIL;
-        else if (W < 0) it.cfg = -1 - BSQ_INIT_FAIL;
-        else if (W == 0) it.cfg = -1 - BSQ_NO_ALIGNMENT;
-        else {
-          it.cfg = force_k3 ? -1 : pick_k2_cfg((int)std::min<int64_t>(W, 1 << 30), f64_geom);
-          if (it.cfg < 0) it.cfg = BSQ_K2_NCFG + k3_cfg;
-        }
-        if (it.cfg >= BSQ_K2_NCFG) {  // K3: strips of G*K columns, tstride time steps each
-          it.lo = lo; it.hi = hi;
-          const int K = BSQ_K3_CFGS[it.cfg - BSQ_K2_NCFG].K, G = 32, BW = G * K;
-          const int64_t nstrips = ((int64_t)m + BW) / BW;
-          const int64_t tstride = std::min<int64_t>((int64_t)n + 1, W + BW - 1) + G - 1;
-          it.words = nstrips * tstride * G * (K / 2) / 4;
-          it.aux = (int32_t)tstride;
-          it.cells = count_cells(BSQ_BANDED_MODE, n, m, lo, hi);
-        } else if (it.cfg >= 0) {
-          it.lo = lo; it.hi = hi;
-          const int G = BSQ_K2_CFGS[it.cfg].G, C = BSQ_K2_CFGS[it.cfg].C, WPS = (C / 2 + 7) / 8;
-          const int smin = (lo <= 0 && hi >= 0) ? 0 : std::min(std::abs(lo), std::abs(hi));
-          const int sbase = smin - ((smin - lo) & 1);
-          const int dstar = std::max(lo, std::min(hi, dend));
-          const int s_end = 2 * std::min(n, m + dstar) - dstar;
-          const int64_t steps = (int64_t)(s_end - sbase + 1 + 1) / 2 * 2 + 2;
-          it.words = steps * G * WPS;
-          it.aux = sbase;
-          it.cells = count_cells(BSQ_BANDED_MODE, n, m, lo, hi);
-        }
-      }
+      const PlanItem it = classify(n, m, dlo, dhi);
       items[i] = it;
       if (it.cfg >= 0) pt.cells += it.cells;
       prev = it; pn = n; pm = m; plo = dlo; phi = dhi;
@@ -569,6 +693,28 @@ int64_t arena_budget_words(bsq_ctx* ctx, int64_t other_bytes) {
   return (int64_t)(budget / 4.0);
 }
 
+// pair records: a plain H2D copy, or (uniform batches) generated on the device from the
+// caller's offset arrays
+int upload_pairs(bsq_ctx* ctx, BufSet& B, const Plan& P, cudaStream_t st) {
+  const int64_t E = P.E;
+  if (E <= 0) return BSQ_SUCCESS;
+  if (!P.uniform_dev) {
+    BSQ_CK(ctx, cudaMemcpyAsync(B.pairs.p, P.pairs, sizeof(BsqPair) * (size_t)E, cudaMemcpyHostToDevice, st));
+    ctx->tm.h2d_bytes += (int64_t)sizeof(BsqPair) * E;
+    return BSQ_SUCCESS;
+  }
+  if (!B.ooff.ensure(8 * (size_t)E) || !B.moff.ensure(8 * (size_t)E)) return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (offsets)");
+  BSQ_CK(ctx, cudaMemcpyAsync(B.ooff.p, P.src_o_off, 8 * (size_t)E, cudaMemcpyHostToDevice, st));
+  BSQ_CK(ctx, cudaMemcpyAsync(B.moff.p, P.src_m_off, 8 * (size_t)E, cudaMemcpyHostToDevice, st));
+  ctx->tm.h2d_bytes += 16 * E;
+  const int grid = (int)((E + 255) / 256);
+  BSQ_LAUNCH(bsq_make_pairs_uniform, grid, 256, 0, st, (const long long*)B.ooff.as<long long>(),
+             (const long long*)B.moff.as<long long>(), (long long)E, P.uni, B.pairs.as<BsqPair>());
+  BSQ_CK(ctx, cudaGetLastError());
+  ctx->tm.fill_launches++;
+  return BSQ_SUCCESS;
+}
+
 // K3 chunks: per-pair strip records, progress/done words, per-strip results, slabs
 int stage_k3(bsq_ctx* ctx, BufSet& B, const Plan& P, cudaStream_t st) {
   if (P.k3.empty()) return BSQ_SUCCESS;
@@ -596,9 +742,9 @@ int stage_inputs(bsq_ctx* ctx, BufSet& B, Plan& P, const uint8_t* codes, int64_t
   cudaStream_t st = ctx->st;
   if (ncodes > 0) BSQ_CK(ctx, cudaMemcpyAsync(B.codes.p, codes, (size_t)ncodes, cudaMemcpyHostToDevice, st));
   ctx->tm.h2d_bytes += ncodes;
-  if (E > 0) {
-    BSQ_CK(ctx, cudaMemcpyAsync(B.pairs.p, P.pairs, sizeof(BsqPair) * (size_t)E, cudaMemcpyHostToDevice, st));
-    ctx->tm.h2d_bytes += (int64_t)sizeof(BsqPair) * E;
+  {
+    const int rcp = upload_pairs(ctx, B, P, st);
+    if (rcp != BSQ_SUCCESS) return rcp;
   }
   if (P.dtype == BSQ_DTYPE_I32) {
     std::vector<int> si((size_t)L * L);
@@ -653,6 +799,25 @@ int launch_fill(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, size_t* evi, 
     BSQ_CK(ctx, cudaEventRecord(e1, stream));
     ctx->tm.fill_launches++;
     ctx->tm.ptr_bytes += 4 * ch.ptr_words;
+    return BSQ_SUCCESS;
+  }
+  if (ch.duo) {
+    int occ = bsq_k1h_op(P.gosign, BSQ_OP_OCCUPANCY, 0, 0, nullptr);
+    if (occ < 0) return fail(ctx, BSQ_ERR_ARG, "no kernel variant for this configuration");
+    const int gpb = BSQ_FILL_THREADS / 8;
+    const int64_t duos = (ch.count + 1) / 2;
+    const int occ_use = (leave_room && occ >= 4) ? occ - 1 : occ;
+    int grid = (int)std::min<int64_t>((duos + gpb - 1) / gpb, (int64_t)ctx->sms * occ_use);
+    if (grid < 1) grid = 1;
+    cudaEvent_t e0 = get_event(ctx, (*evi)++), e1 = get_event(ctx, (*evi)++);
+    BSQ_CK(ctx, cudaEventRecord(e0, stream));
+    if (bsq_k1h_op(P.gosign, BSQ_OP_LAUNCH, grid, stream, &A) < 0)
+      return fail(ctx, BSQ_ERR_ARG, "no kernel variant for this configuration");
+    BSQ_CK(ctx, cudaGetLastError());
+    BSQ_CK(ctx, cudaEventRecord(e1, stream));
+    ctx->tm.fill_launches++;
+    ctx->tm.ptr_bytes += 4 * ch.ptr_words;
+    ctx->tm.dtype = BSQ_DTYPE_I16X2;
     return BSQ_SUCCESS;
   }
   const int G = ch.family == 1 ? BSQ_K1_CFGS[ch.cfg].G : BSQ_K2_CFGS[ch.cfg].G;
@@ -849,6 +1014,7 @@ bsq_ctx* bsq_create(int device) {
   ctx->sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->st_copy2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithPriority(&ctx->st_trace, cudaStreamNonBlocking, -1) != cudaSuccess) {
     g_err = "cudaStreamCreate failed"; delete ctx; return nullptr;
   }
@@ -867,6 +1033,7 @@ void bsq_destroy(bsq_ctx* ctx) {
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->st);
   cudaStreamDestroy(ctx->st_copy);
+  cudaStreamDestroy(ctx->st_copy2);
   cudaStreamDestroy(ctx->st_trace);
   delete ctx;
 }
@@ -1033,7 +1200,7 @@ static int batch_run(bsq_batch* b, bool do_fill, bool do_trace) {
     ctx->tm.fill_ms = fill;
   }
   ctx->tm.cells = P.cells;
-  ctx->tm.dtype = P.dtype;
+  ctx->tm.dtype = (!P.chunks.empty() && P.chunks[0].duo) ? BSQ_DTYPE_I16X2 : P.dtype;
   ctx->tm.chunks = (int32_t)P.chunks.size();
   if (do_fill) b->filled = true;
   return BSQ_SUCCESS;
@@ -1137,21 +1304,22 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
                           B.packed.ensure((size_t)std::max<int64_t>(P.slot_bytes, 1));
   if (!ok) { cudaStreamSynchronize(sx); return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed"); }
 
-  // ---- 2. pair records + score table on the copy stream
+  // ---- 2. pair records + score table on their own copy stream (the sequence bytes are still in flight on the other)
+  cudaStream_t sp = ctx->st_copy2;
   std::vector<int> subst_i;
-  if (E > 0) BSQ_CK(ctx, cudaMemcpyAsync(B.pairs.p, P.pairs, sizeof(BsqPair) * (size_t)E, cudaMemcpyHostToDevice, sx));
-  ctx->tm.h2d_bytes += (int64_t)sizeof(BsqPair) * E;
+  rc = upload_pairs(ctx, B, P, sp);
+  if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(sx); cudaStreamSynchronize(sp); return rc; }
   if (P.dtype == BSQ_DTYPE_I32) {
     subst_i.resize((size_t)L * L);
     for (int i = 0; i < L * L; i++) subst_i[i] = (int)P.subst[i];
-    BSQ_CK(ctx, cudaMemcpyAsync(B.subst.p, subst_i.data(), 4 * (size_t)L * L, cudaMemcpyHostToDevice, sx));
+    BSQ_CK(ctx, cudaMemcpyAsync(B.subst.p, subst_i.data(), 4 * (size_t)L * L, cudaMemcpyHostToDevice, sp));
   } else {
-    BSQ_CK(ctx, cudaMemcpyAsync(B.subst.p, P.subst.data(), 8 * (size_t)L * L, cudaMemcpyHostToDevice, sx));
+    BSQ_CK(ctx, cudaMemcpyAsync(B.subst.p, P.subst.data(), 8 * (size_t)L * L, cudaMemcpyHostToDevice, sp));
   }
-  rc = stage_k3(ctx, B, P, sx);
-  if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(sx); return rc; }
+  rc = stage_k3(ctx, B, P, sp);
+  if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(sx); cudaStreamSynchronize(sp); return rc; }
   cudaEvent_t ev_pairs = get_event(ctx, evi++);
-  BSQ_CK(ctx, cudaEventRecord(ev_pairs, sx));
+  BSQ_CK(ctx, cudaEventRecord(ev_pairs, sp));
 
   // ---- 3. compute stream: chunk after chunk
   cudaEvent_t t0 = get_event(ctx, 0), t1 = get_event(ctx, 1);
@@ -1251,6 +1419,7 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
     }
   }
   BSQ_CK(ctx, cudaStreamSynchronize(sx));
+  BSQ_CK(ctx, cudaStreamSynchronize(ctx->st_copy2));
   BSQ_CK(ctx, cudaStreamSynchronize(ctx->st_trace));
   BSQ_CK(ctx, cudaStreamSynchronize(sc));
   collect_timing(ctx, 2, t0, t1);
@@ -1264,7 +1433,7 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
     ctx->tm.fill_ms = fill;
   }
   ctx->tm.cells = P.cells;
-  ctx->tm.dtype = P.dtype;
+  ctx->tm.dtype = (!P.chunks.empty() && P.chunks[0].duo) ? BSQ_DTYPE_I16X2 : P.dtype;
   ctx->tm.chunks = (int32_t)NC;
   apply_overrides(P, score, end_x, end_y, want_trace ? start_x : nullptr, want_trace ? start_y : nullptr, status);
   if (rc_cap == BSQ_ERR_CAPACITY) return fail(ctx, BSQ_ERR_CAPACITY, "tx_buf too small for the batch's transcripts");

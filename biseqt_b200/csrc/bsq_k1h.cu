@@ -1,0 +1,20 @@
+// k1h fill kernels: two short problems per lane, packed 16-bit arithmetic (see bsq_k1h.cuh)
+#include "bsq_k1h.cuh"
+
+template <class KernelT>
+static int bsq_k1h_do(KernelT kern, int op, int grid, cudaStream_t st, const BsqFillArgs* A) {
+  if (op == BSQ_OP_OCCUPANCY) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, BSQ_FILL_THREADS, 0) != cudaSuccess) nb = 1;
+    return nb < 1 ? 1 : nb;
+  }
+  BSQ_LAUNCH(kern, grid, BSQ_FILL_THREADS, 0, st, *A);
+  (void)st;
+  return 0;
+}
+
+int bsq_k1h_op(int gos, int op, int grid, cudaStream_t st, const BsqFillArgs* A) {
+  if (gos < 0) return bsq_k1h_do(bsq_k1h_fill<-1>, op, grid, st, A);
+  if (gos == 0) return bsq_k1h_do(bsq_k1h_fill<0>, op, grid, st, A);
+  return -1;
+}

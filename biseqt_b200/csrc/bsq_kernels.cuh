@@ -27,6 +27,28 @@
 
 #define BSQ_INT_MAX 0x7fffffff
 
+// a lane's NW pointer words of one row / step -> ONE aligned vector store of STRIDE words
+template <int NW, int STRIDE>
+__device__ __forceinline__ void bsq_store_words(uint32_t* dst, const uint32_t (&w)[NW]) {
+  static_assert(STRIDE == 1 || STRIDE == 2 || STRIDE == 4, "power-of-two words per lane");
+  static_assert(NW <= STRIDE, "more words than the slot holds");
+  if (STRIDE == 1) {
+    dst[0] = w[0];
+  } else if (STRIDE == 2) {
+    uint2 v;
+    v.x = w[0];
+    v.y = NW > 1 ? w[NW > 1 ? 1 : 0] : 0u;
+    *(uint2*)dst = v;
+  } else {
+    uint4 v;
+    v.x = w[0];
+    v.y = NW > 1 ? w[NW > 1 ? 1 : 0] : 0u;
+    v.z = NW > 2 ? w[NW > 2 ? 2 : 0] : 0u;
+    v.w = NW > 3 ? w[NW > 3 ? 3 : 0] : 0u;
+    *(uint4*)dst = v;
+  }
+}
+
 struct ScF64 {
   typedef double T;
   static constexpr bool IS_INT = false;
@@ -201,7 +223,11 @@ __device__ __forceinline__ void bsq_group_best(unsigned gmask, T& s, int& k1, in
 // columns (y), walks the rows (x) and lags its left neighbour by one row, so
 // the (x, y-1) dependency arrives by one shuffle per row.  Tables wider than
 // G*K columns are swept in passes, the boundary column going through a small
-// per-group scratch slab.  Pointer layout: [pass][x][lane][word], 8 cells/word.
+// per-group scratch slab.  Pointer layout: [pass][t = x + lane][lane][word], 8
+// cells/word: skewed by the lane index like the computation itself, so that at
+// every step the G lanes of a group write ONE contiguous run of full sectors
+// (unskewed, each lane would write 16 bytes of a different row: 8x the L2 write
+// requests, half-written sectors, read-modify-write in DRAM).
 //   replaces: dptable_solve's fill loop pw.c:59-110 + _std_find_optimal
 // ===========================================================================
 // EALL: 0 = end cell not searched per cell, 1 = every cell may end the alignment
@@ -285,7 +311,8 @@ template <class S, int G, int K, bool BALL, int EALL, int GOS>
 __global__ void __launch_bounds__(128) bsq_k1_fill(const BsqFillArgs A) {
   typedef typename S::T T;
   static_assert(K <= 32, "end-cell positions are packed as x*32 + k");
-  constexpr int WPL = (K + 7) / 8;
+  constexpr int WPL = (K + 7) / 8;          // words holding a lane's K nibbles
+  constexpr int WST = BSQ_K1_WPL(K);        // words a lane's row occupies in the table
   constexpr int BW = G * K;
   // substitution table with one extra column (letter L = "padding column") holding
   // -inf, so cells right of the table can never win or tie anything
@@ -344,7 +371,7 @@ __global__ void __launch_bounds__(128) bsq_k1_fill(const BsqFillArgs A) {
       T prev_in = NINF;
       T pbest = ZERO;  // per-pass record for E_ALL (merged lexicographically below)
       int pbpos = BSQ_INT_MAX;
-      uint32_t* prow = A.ptr + P.ptr_off + ((long long)pass * (n + 1) * G + l) * WPL;
+      uint32_t* prow = A.ptr + P.ptr_off + ((long long)pass * (n + G) * G + l) * WST;
       const bool more = (pass + 1 < npass);
 
       for (int t = 0; t <= n + G - 1; t++) {
@@ -378,9 +405,7 @@ __global__ void __launch_bounds__(128) bsq_k1_fill(const BsqFillArgs A) {
           }
           lastH = outH;
           lastG = outG;
-          uint32_t* pr = prow + (long long)x * (G * WPL);
-#pragma unroll
-          for (int w = 0; w < WPL; w++) pr[w] = cw[w];
+          bsq_store_words<WPL, WST>(prow + (long long)t * (G * WST), cw);  // skewed: row t = x + l
           if (more && l == G - 1) { colh[x] = outH; colf[x] = (uint8_t)(outG != 0); }
           if (!EALL) {
             if (km >= 0 && km < K) {  // I own column m
@@ -506,8 +531,7 @@ __device__ __forceinline__ void bsq_k2_step_careful(
       }
     }
   }
-#pragma unroll
-  for (int w = 0; w < WPS; w++) pout[w] = cur[w];
+  bsq_store_words<WPS, WPS>(pout, cur);
 }
 
 // interior step: every band cell is a regular cell (x >= 1, y >= 1, in table).
@@ -588,8 +612,7 @@ __device__ __forceinline__ void bsq_k2_step_fast(
 #undef BSQ_FIX
     }
   }
-#pragma unroll
-  for (int w = 0; w < WPS; w++) pout[w] = cur[w];
+  bsq_store_words<WPS, WPS>(pout, cur);
 }
 
 template <class S, int G, int C, bool BLOCAL, int GOS>

@@ -39,6 +39,9 @@ __global__ void __launch_bounds__(256) bsq_mb_kernel(double* sink, int iters, do
           v[k] = __vimax3_s32(v[k], w[k], v[(k + 1) & 7] + it);
         } else if (WHICH == BSQ_MB_VIADDMAX) {
           v[k] = __viaddmax_s32(v[k], w[k], v[(k + 3) & 7]);
+        } else if (WHICH == BSQ_MB_VADD2) {
+          v[k] = (int)__vadd2((unsigned)v[k], (unsigned)w[k]);
+          w[k] = (int)__vadd2((unsigned)w[k], (unsigned)v[k]);
         } else if (WHICH == BSQ_MB_SHFL) {
           v[k] = __shfl_up_sync(0xffffffffu, v[k], 1);
         } else if (WHICH == BSQ_MB_LDS64) {
@@ -79,6 +82,7 @@ static int run_mb(int sms, cudaStream_t st, double* ops_per_sec, std::string* er
   if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BSQ_ERR_CUDA; }
   double per_thread = (double)MB_ITERS * MB_UNROLL * 8;
   if (WHICH == BSQ_MB_IADD) per_thread *= 2;
+  if (WHICH == BSQ_MB_VADD2) per_thread *= 4;  // two instructions, two halfword adds each
   *ops_per_sec = per_thread * grid * block / (best * 1e-3);
   return BSQ_SUCCESS;
 }
@@ -91,6 +95,7 @@ int bsq_microbench_impl(int sms, cudaStream_t st, int which, double* out, std::s
     case BSQ_MB_IADD: return run_mb<BSQ_MB_IADD>(sms, st, out, err);
     case BSQ_MB_VIMAX3: return run_mb<BSQ_MB_VIMAX3>(sms, st, out, err);
     case BSQ_MB_VIADDMAX: return run_mb<BSQ_MB_VIADDMAX>(sms, st, out, err);
+    case BSQ_MB_VADD2: return run_mb<BSQ_MB_VADD2>(sms, st, out, err);
     case BSQ_MB_SHFL: return run_mb<BSQ_MB_SHFL>(sms, st, out, err);
     case BSQ_MB_LDS64: return run_mb<BSQ_MB_LDS64>(sms, st, out, err);
   }

@@ -23,9 +23,9 @@ __device__ __forceinline__ uint32_t bsq_get_mask(const BsqTraceArgs& A, const Bs
   long long idx;
   int sh;
   if (A.mode == BSQ_STD_MODE) {
-    const int G = A.G, K = A.K, BW = G * K, WPL = (K + 7) / 8;
+    const int G = A.G, K = A.K, BW = G * K, WPL = BSQ_K1_WPL(K);
     const int pass = y / BW, r = y - pass * BW, l = r / K, k = r - l * K;
-    idx = P.ptr_off + (((long long)pass * (P.n + 1) + x) * G + l) * WPL + (k >> 3);
+    idx = P.ptr_off + (((long long)pass * (P.n + G) + x + l) * G + l) * WPL + (k >> 3);
     sh = 4 * (k & 7);
   } else {
     const int G = A.G, C = A.K, WPS = (C / 2 + 7) / 8;
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(128) bsq_k4_traceback(const BsqTraceArgs A) {
 // memory with coalesced 16-byte loads and every lane then performs the same
 // walk out of shared memory (lane 0 emits).  The position inside a row is kept
 // incrementally (lane, column) so the walk needs no divisions.
-//   FAMILY 1: K1 layout [pass][x][lane][word]   row id = pass*(n+1) + x
+//   FAMILY 1: K1 layout [pass][x+lane][lane][word]   row id = pass*(n+G) + x + lane
 //   FAMILY 2: K2 layout [s - s0][lane][word]    row id = s - s0
 // ---------------------------------------------------------------------------
 #define BSQ_TILE_WORDS 1024
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTrac
   }
   uint32_t* tile = s_tile[wib];
   const int G = A.G, K = A.K;
-  const int WP = (FAMILY == 1) ? (K + 7) / 8 : (K / 2 + 7) / 8;  // words per lane per row
+  const int WP = (FAMILY == 1) ? BSQ_K1_WPL(K) : (K / 2 + 7) / 8;  // words per lane per row
   const int RB = G * WP;                                        // words per row
   const int R = BSQ_TILE_WORDS / RB;                            // rows per tile
   const int ex = A.ex[oi], ey = A.ey[oi];
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTrac
   if (FAMILY == 1) {
     const int BW = G * K, pass = y / BW, r = y - pass * BW;
     l = r / K; k = r - l * K;
-    rid = (long long)pass * (P.n + 1) + x;
+    rid = (long long)pass * (P.n + G) + x + l;
   } else {
     const int di = (x - y) - P.dmin;
     l = di / K; k = di - l * K;
@@ -201,7 +201,15 @@ __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTrac
     if (taken > 0) {  // account for the diagonal moves
       rid -= (FAMILY == 1) ? taken : 2 * taken;
       roff -= taken * mstep;
-      if (FAMILY == 1) { k -= taken; if (k < 0) { k = K - 1; if (--l < 0) { l = G - 1; rid -= (P.n + 1); roff = -1; } } BSQ_RECOL(); }
+      if (FAMILY == 1) {
+        k -= taken;
+        if (k < 0) {  // into the previous lane: its rows are skewed by one more
+          k = K - 1;
+          if (--l < 0) { l = G - 1; rid -= (P.n + 1); roff = -1; }  // (pass-1)*(n+G) + x + G-1
+          else { rid -= 1; roff -= RB; }
+        }
+        BSQ_RECOL();
+      }
       if (taken == jmax) continue;  // the run may go on: next round
     }
     // here `op` is the op found at the current cell and it is not a diagonal move
@@ -215,7 +223,11 @@ __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTrac
     } else {
       ch = 'I'; y--;
       if (FAMILY == 1) {
-        if (--k < 0) { k = K - 1; if (--l < 0) { l = G - 1; rid -= (P.n + 1); roff = -1; } }
+        if (--k < 0) {
+          k = K - 1;
+          if (--l < 0) { l = G - 1; rid -= (P.n + 1); roff = -1; }
+          else { rid -= 1; roff -= RB; }
+        }
       } else {
         rid -= 1; roff -= RB;
         if (++k == K) { k = 0; l++; }
@@ -403,6 +415,23 @@ __global__ void __launch_bounds__(256) bsq_scan_apply(const int* in, int n, cons
     if (threadIdx.x == 255) carry += sh[255];
     __syncthreads();
   }
+}
+
+// uniform batches: pair record e from the caller's offset arrays (processing order == caller order)
+__global__ void __launch_bounds__(256) bsq_make_pairs_uniform(const long long* o_off, const long long* m_off,
+                                                              long long E, const BsqUniform U, BsqPair* out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  BsqPair bp;
+  bp.o_off = o_off[e];
+  bp.m_off = m_off[e];
+  bp.ptr_off = (e % U.ppc) * U.words;
+  bp.tx_slot = e * ((long long)U.n + U.m);
+  bp.n = U.n; bp.m = U.m;
+  bp.dmin = U.dmin; bp.dmax = U.dmax;
+  bp.s0 = U.s0;
+  bp.pad = (int)e;
+  out[e] = bp;
 }
 
 // pack transcripts: one warp per pair copies slot tail -> packed[off]

@@ -68,6 +68,8 @@ extern "C" {
 /* arithmetic the fill kernels ran in */
 #define BSQ_DTYPE_F64 0       /* general path: IEEE double, same association as pwlib */
 #define BSQ_DTYPE_I32 1       /* exact fast path: every score an integer, no overflow */
+#define BSQ_DTYPE_I16X2 2     /* reported only: the I32 path's short-read form, two problems per  *
+                               * register in packed 16-bit arithmetic (same exact results)        */
 #define BSQ_DTYPE_AUTO -1
 
 typedef struct bsq_ctx bsq_ctx;     /* one per GPU; single-owner                    */
@@ -205,7 +207,8 @@ int bsq_get_timing(const bsq_ctx* ctx, bsq_timing* out);
 #define BSQ_MB_VIADDMAX 5  /* DPX add+max (VIADDMNMX)                       */
 #define BSQ_MB_SHFL 6      /* shfl.sync.up.b32                              */
 #define BSQ_MB_LDS64 7     /* ld.shared.b64, conflict free                  */
-#define BSQ_MB_COUNT 8
+#define BSQ_MB_VADD2 8     /* VIADD.16x2, counted as two halfword adds            */
+#define BSQ_MB_COUNT 9
 int bsq_microbench(bsq_ctx* ctx, int32_t which, double* ops_per_sec);
 
 /* pure host helpers (usable without a GPU) ------------------------------- */

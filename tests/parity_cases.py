@@ -155,6 +155,89 @@ def run_forced_k3(make_engine, seed, count=150, cfgs=(0, 1, 2)):
         os.environ.pop('BSQ_K3_CFG', None)
 
 
+def run_uniform_batches(make_engine, seed):
+    """Batches in which every pair has the same shape take the planner's fast path (pair
+    records generated on the device); forced here for small batches, with and without chunking."""
+    os.environ['BSQ_UNIFORM_MIN'] = '2'
+    os.environ['BSQ_ARENA_CAP_BYTES'] = str(1 << 17)
+    try:
+        eng = make_engine()
+    finally:
+        del os.environ['BSQ_ARENA_CAP_BYTES']
+    eng2 = make_engine()    # no arena cap: the two-phase form keeps every table resident
+    try:
+        rng = np.random.default_rng(seed)
+        for mode, typ, n, m, dr in ((0, 1, 60, 60, None), (0, 0, 33, 47, None), (0, 4, 200, 170, None),
+                                    (1, 2, 150, 140, (-12, 20)), (1, 0, 90, 95, (-9, 7)), (1, 1, 80, 80, (3, 30))):
+            S, go, ge = score_family(rng, 4, int(rng.integers(1, 3)), int(rng.integers(-1, 2)))
+            probs = []
+            for i in range(37):
+                o = rng.integers(0, 4, size=n).astype(np.uint8)
+                t = rng.integers(0, 4, size=m).astype(np.uint8)
+                k = min(n, m)
+                if i % 5:
+                    t[:k] = o[:k]
+                    t[rng.integers(0, m, size=m // 10)] = rng.integers(0, 4, size=m // 10)
+                probs.append(dict(origin=o, mutant=t, subst=S, go=go, ge=ge, mode=mode, type=typ, diag_range=dr))
+            check_batch(eng, probs)
+            # resident + two-phase forms of the same batch
+            codes, o_off, o_len, m_off, m_len = batch.pack_pairs([(p['origin'], p['mutant']) for p in probs])
+            kw = dict(dmin=[dr[0]] * len(probs), dmax=[dr[1]] * len(probs)) if dr else {}
+            sb = eng2.solve(codes, o_off, o_len, m_off, m_len, mode, typ, S, go, ge, **kw)
+            r = sb.traceback()
+            for i, pr in enumerate(probs):
+                same_as(oracle_one(pr), r, i, what='uniform two-phase %d' % i)
+            sb.release()
+    finally:
+        eng.close()
+        eng2.close()
+        del os.environ['BSQ_UNIFORM_MIN']
+
+
+def run_duo_short_reads(make_engine, seed, npairs=37):
+    """STD LOCAL, small integer scores, one shape for the whole batch: the packed 16-bit
+    kernel (two problems per lane, K1h).  Odd pair counts, edge shapes, go == 0 and go < 0,
+    alphabets of 2..4 letters; the scalar I32 kernel (BSQ_NO_DUO) must give the same bytes."""
+    os.environ['BSQ_UNIFORM_MIN'] = '2'
+    try:
+        eng = make_engine()
+        try:
+            rng = np.random.default_rng(seed)
+            shapes = [(150, 150), (151, 151), (40, 151), (97, 33), (1, 1), (5, 0), (0, 7), (64, 152 - 1), (150, 120)]
+            for (n, m) in shapes:
+                for gomode in (-1, 0):
+                    L = int(rng.choice([2, 3, 4, 4]))
+                    ma, mi = int(rng.integers(1, 4)), -int(rng.integers(0, 4))
+                    S = np.where(np.eye(L, dtype=bool), float(ma), float(mi))
+                    ge = -float(rng.integers(0, 3))
+                    go = 0.0 if gomode == 0 else -float(rng.integers(1, 6))
+                    probs = []
+                    for i in range(npairs):
+                        o = rng.integers(0, L, size=n).astype(np.uint8)
+                        t = rng.integers(0, L, size=m).astype(np.uint8)
+                        k = min(n, m)
+                        if i % 4 and k:
+                            sh = int(rng.integers(0, max(1, k // 3)))
+                            t[sh:k] = o[:k - sh]
+                            if m >= 10:
+                                t[rng.integers(0, m, size=m // 10)] = rng.integers(0, L, size=m // 10)
+                        probs.append(dict(origin=o, mutant=t, subst=S, go=go, ge=ge, mode=0, type=1, diag_range=None))
+                    r = check_batch(eng, probs)
+                    assert eng.timing()['dtype'] == batch.DTYPE_I16X2, (n, m, gomode)
+                    os.environ['BSQ_NO_DUO'] = '1'
+                    try:
+                        r1 = engine_batch(eng, probs)
+                    finally:
+                        del os.environ['BSQ_NO_DUO']
+                    assert eng.timing()['dtype'] == batch.DTYPE_I32
+                    assert np.array_equal(r.score, r1.score) and np.array_equal(r.tx_off, r1.tx_off)
+                    assert np.array_equal(r.tx_buf[:r.tx_off[-1]], r1.tx_buf[:r1.tx_off[-1]])
+        finally:
+            eng.close()
+    finally:
+        del os.environ['BSQ_UNIFORM_MIN']
+
+
 def run_dtype_equivalence(eng, seed, npairs=12, lo=5, hi=60):
     """Integer scores: the I32 fast path and the F64 path give identical results."""
     rng = np.random.default_rng(seed)

@@ -78,3 +78,11 @@ def test_emu_table_scores(emu_engine):
 
 def test_emu_chunked(emu_lib):
     pc.run_chunked(lambda: batch.Engine(0, lib=emu_lib), seed=81)
+
+
+def test_emu_uniform_batches(emu_lib):
+    pc.run_uniform_batches(lambda: batch.Engine(0, lib=emu_lib), seed=83)
+
+
+def test_emu_duo_short_reads(emu_lib):
+    pc.run_duo_short_reads(lambda: batch.Engine(0, lib=emu_lib), seed=87, npairs=11)

@@ -92,6 +92,14 @@ def test_gpu_chunked():
     pc.run_chunked(lambda: batch.Engine(0), seed=81)
 
 
+def test_gpu_uniform_batches():
+    pc.run_uniform_batches(lambda: batch.Engine(0), seed=83)
+
+
+def test_gpu_duo_short_reads():
+    pc.run_duo_short_reads(lambda: batch.Engine(0), seed=87, npairs=301)
+
+
 def _workload(kind, npairs, seed):
     import bench_workloads as bw
     return bw.make(kind, npairs, seed)

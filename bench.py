@@ -344,9 +344,9 @@ def main():
     if rank == 0:
         # roofline of the dominant kernel (DP fill): ALU-pipe bound, SURVEY.md section 8(d)
         opc = ops_per_cell(w['go'])
-        which = 'IADD' if m['dtype'] == 'i32' else 'DADD'
+        which = {'i32': 'IADD', 'i16x2': 'VADD2'}.get(m['dtype'], 'DADD')
         try:
-            pipe = {k: eng.microbench(k) for k in ('DADD', 'DMAX', 'DSETP', 'IADD', 'VIMAX3', 'VIADDMAX', 'SHFL', 'LDS64')}
+            pipe = {k: eng.microbench(k) for k in ('DADD', 'DMAX', 'DSETP', 'IADD', 'VADD2', 'VIMAX3', 'VIADDMAX', 'SHFL', 'LDS64')}
         except Exception as e:   # never hide the bench line behind a microbenchmark problem
             pipe = {'error': str(e)}
         fill_s = m['fill_ms'] * 1e-3
@@ -363,7 +363,7 @@ def main():
             'frac': (achieved / peak) if peak else None, 'traffic': None,
             'ops_per_cell': opc, 'pipe': which,
             'note': 'achieved = cells x algorithmic ops/cell / fill-kernel time (CUDA events on the library stream); '
-                    'peak = add.%s issue rate measured in this run (bsq_microbench)' % ('s32' if which == 'IADD' else 'f64'),
+                    'peak = %s issue rate measured in this run (bsq_microbench)' % {'IADD': 'add.s32', 'VADD2': 'packed 16-bit add (VIADD.16x2, two adds per instruction)', 'DADD': 'add.f64'}[which],
             'pipe_rates_gops': {k: v / 1e9 for k, v in pipe.items()} if 'error' not in pipe else pipe,
             'hbm': {'achieved': m['ptr_bytes'] * args.steps / fill_s / 1e9, 'peak': hbm_peak,
                     'unit': 'GB/s', 'frac': m['ptr_bytes'] * args.steps / fill_s / 1e9 / hbm_peak,
@@ -399,7 +399,7 @@ def main():
                 m2 = measure(eng, w2, max(2, args.steps // 2), 3, local, do_e2e=True)
                 st2 = max(2, args.steps // 2)
                 opc2 = ops_per_cell(w2['go'])
-                which2 = 'IADD' if m2['dtype'] == 'i32' else 'DADD'
+                which2 = {'i32': 'IADD', 'i16x2': 'VADD2'}.get(m2['dtype'], 'DADD')
                 pk = roofline['pipe_rates_gops'].get(which2) if isinstance(roofline['pipe_rates_gops'], dict) else None
                 ach = m2['cells'] * st2 * opc2 / (m2['fill_ms'] * 1e-3) / 1e9
                 extras[k2] = {'workload': w2['desc'], 'dtype': m2['dtype'],

@@ -233,6 +233,21 @@ class Engine(object):
                                            'ptr_bytes', 'dtype', 'chunks', 'plan_ms', 'call_ms')}
 
 
+STATS_DTYPE = np.dtype([('n_match', 'i4'), ('n_subst', 'i4'), ('n_ins', 'i4'), ('n_del', 'i4'),
+                        ('trunc_lo', 'i4'), ('trunc_hi', 'i4'), ('trunc_start_x', 'i4'),
+                        ('trunc_start_y', 'i4'), ('rescore', 'f8')])
+
+
+def _batch_stats(engine, handle, n):
+    """``bsq_batch_stats``: op counts, Alignment.calculate_score and truncate_to_match for
+    every pair of a traced resident batch, computed on the device (pw.py:367-448)."""
+    out = np.zeros(n, dtype=STATS_DTYPE)
+    rc = engine.lib.bsq_batch_stats(handle, ffi.cast('bsq_aln_stats*', out.ctypes.data))
+    if rc != 0:
+        raise BsqError('bsq_batch_stats failed (%d): %s' % (rc, engine._err()))
+    return out
+
+
 class SolvedBatch(object):
     """A solved batch whose pointer tables are still resident (``bsq_batch``)."""
 
@@ -256,6 +271,10 @@ class SolvedBatch(object):
             raise BsqError('bsq_traceback_batch failed (%d): %s' % (rc, self.engine._err()))
         return BatchResult(self.score, self.end_x, self.end_y, start_x, start_y, status,
                            tx_off, tx_buf)
+
+    def stats(self):
+        """Device-side Alignment post-processing (after :meth:`traceback`)."""
+        return _batch_stats(self.engine, self.handle, len(self.score))
 
     def release(self):
         if self.handle is not None:
@@ -294,6 +313,10 @@ class ResidentBatch(object):
         if rc != 0:
             raise BsqError('bsq_batch_fetch failed (%d): %s' % (rc, self.engine._err()))
         return BatchResult(score, ints[0], ints[1], ints[2], ints[3], ints[4], tx_off, tx_buf)
+
+    def stats(self):
+        """Device-side Alignment post-processing (after ``run(traceback=True)``)."""
+        return _batch_stats(self.engine, self.handle, self.n)
 
     def release(self):
         if self.handle is not None:

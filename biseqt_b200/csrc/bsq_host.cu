@@ -9,6 +9,9 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -302,14 +305,72 @@ int pick_k3_cfg() {
 
 // ---- planning -------------------------------------------------------------
 
+// A small persistent worker pool: the planner's passes over a million pairs take well under a
+// millisecond each, less than spawning threads for them would.
+class WorkerPool {
+ public:
+  static WorkerPool& get() { static WorkerPool p; return p; }
+  int size() const { return (int)th_.size() + 1; }
+  // runs job(t) for t in [0, T) -- t = 0 on the caller -- and returns when all are done
+  void run(int T, const std::function<void(int)>& job) {
+    if (T <= 1) { job(0); return; }
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      job_ = &job;
+      want_ = T;
+      pending_ = T - 1;
+      gen_++;
+    }
+    cv_.notify_all();
+    job(0);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [&] { return pending_ == 0; });
+    job_ = nullptr;
+  }
+  ~WorkerPool() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; gen_++; }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+ private:
+  WorkerPool() {
+    unsigned hw = std::thread::hardware_concurrency();
+    const int n = (int)std::max(1u, std::min(hw, 8u)) - 1;
+    for (int i = 0; i < n; i++) th_.emplace_back([this, i] { loop(i + 1); });
+  }
+  void loop(int id) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(int)>* job = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        if (id < want_) job = job_;
+      }
+      if (job) {
+        (*job)(id);
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* job_ = nullptr;
+  int want_ = 0, pending_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
 template <class F>
 void parallel_for(int64_t n, F f) {
-  unsigned hw = std::thread::hardware_concurrency();
-  int T = (int)std::min<int64_t>(std::max(1u, std::min(hw, 8u)), std::max<int64_t>(n / 32768, 1));
+  WorkerPool& pool = WorkerPool::get();
+  const int T = (int)std::min<int64_t>(pool.size(), std::max<int64_t>(n / 32768, 1));
   if (T <= 1) { f(0, (int64_t)0, n); return; }
-  std::vector<std::thread> th;
-  for (int t = 0; t < T; t++) th.emplace_back([=]() { f(t, n * t / T, n * (t + 1) / T); });
-  for (auto& x : th) x.join();
+  pool.run(T, [&](int t) { f(t, n * t / T, n * (t + 1) / T); });
 }
 
 int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int64_t N, int64_t ncodes,
@@ -1283,12 +1344,26 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
   b.ctx = ctx; b.own_bufs = false; b.B = &B;
   Plan& P = b.plan;
   int64_t slot_guess = 0;
-  for (int64_t i = 0; i < npairs; i++) slot_guess += (int64_t)o_len[i] + m_len[i];
+  {
+    std::vector<int64_t> part(16, 0);
+    parallel_for(npairs, [&](int t, int64_t i0, int64_t i1) {
+      int64_t a = 0;
+      for (int64_t i = i0; i < i1; i++) a += (int64_t)o_len[i] + m_len[i];
+      part[t] = a;
+    });
+    for (int64_t v : part) slot_guess += v;
+  }
   const int64_t other = ncodes + 2 * slot_guess + npairs * (int64_t)(sizeof(BsqPair) + 48) + (64 << 20);
+  const double t_p1 = now_ms();
+  const int64_t budget = arena_budget_words(ctx, other);
+  const double t_p2 = now_ms();
   rc = make_plan(ctx, P, B.hpairs, params, npairs, ncodes, o_off, o_len, m_off, m_len, dmin, dmax,
-                 arena_budget_words(ctx, other) / 2, false, overlap_chunks(npairs, o_len, m_len));
+                 budget / 2, false, overlap_chunks(npairs, o_len, m_len));
   if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(sx); return rc; }
   ctx->tm.plan_ms = now_ms() - t_plan;
+  if (getenv("BSQ_PLAN_DEBUG"))
+    fprintf(stderr, "[bsq] plan: memgetinfo %.3f ms, make_plan %.3f ms, h2d enqueue before plan %.3f ms\n",
+            t_p2 - t_p1, now_ms() - t_p2, t_plan - t_call);
   const int64_t E = (int64_t)P.E;
   const int L = P.prm.alphabet_len;
   const size_t NC = P.chunks.size();
@@ -1533,6 +1608,48 @@ int bsq_microbench(bsq_ctx* ctx, int32_t which, double* ops_per_sec) {
   ctx->err.clear();
   BSQ_CK(ctx, cudaSetDevice(ctx->device));
   return bsq_microbench_impl(ctx->sms, ctx->st, which, ops_per_sec, &ctx->err);
+}
+
+int bsq_batch_stats(bsq_batch* b, bsq_aln_stats* out) {
+  if (!b || !b->ctx) return BSQ_ERR_ARG;
+  bsq_ctx* ctx = b->ctx;
+  ctx->err.clear();
+  if (!out) return fail(ctx, BSQ_ERR_ARG, "out must not be NULL");
+  const Plan& P = b->plan;
+  if (P.N == 0) return BSQ_SUCCESS;
+  if (!b->traced) return fail(ctx, BSQ_ERR_ARG, "bsq_batch_stats needs a traced batch (run with traceback first)");
+  BSQ_CK(ctx, cudaSetDevice(ctx->device));
+  BufSet& B = *b->B;
+  const int L = P.prm.alphabet_len;
+  const size_t N = (size_t)P.N;
+  DevBuf dS, dOut;
+  if (!dS.ensure(8 * (size_t)L * L) || !dOut.ensure(sizeof(bsq_aln_stats) * N)) {
+    dS.release(); dOut.release();
+    return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (stats)");
+  }
+  cudaStream_t st = ctx->st;
+  cudaError_t e = cudaMemcpyAsync(dS.p, P.subst.data(), 8 * (size_t)L * L, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dOut.p, 0, sizeof(bsq_aln_stats) * N, st);
+  if (e == cudaSuccess && P.E > 0) {
+    const int grid = (int)((P.E + 127) / 128);
+    BSQ_LAUNCH(bsq_k5_stats, grid, 128, 0, st, (const BsqPair*)B.pairs.as<BsqPair>(), (int)P.E,
+               (const uint8_t*)B.codes.as<uint8_t>(), (const long long*)B.txoff.as<long long>(),
+               (const int*)B.txlen.as<int>(), (const char*)B.packed.as<char>(), (const int*)B.sx.as<int>(),
+               (const int*)B.sy.as<int>(), (const int*)B.status.as<int>(), (const double*)dS.as<double>(), L,
+               P.prm.go, P.prm.ge, dOut.as<bsq_aln_stats>());
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dOut.p, sizeof(bsq_aln_stats) * N, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  dS.release(); dOut.release();
+  if (e != cudaSuccess) { ctx->err = std::string("stats: ") + cudaGetErrorString(e); return BSQ_ERR_CUDA; }
+  for (const Override& o : P.overrides) {  // pairs that never reached the device
+    bsq_aln_stats z;
+    memset(&z, 0, sizeof z);
+    z.trunc_lo = z.trunc_hi = z.trunc_start_x = z.trunc_start_y = -1;
+    out[o.idx] = z;
+  }
+  return BSQ_SUCCESS;
 }
 
 int bsq_table_scores(bsq_ctx* ctx, const bsq_params* params, const uint8_t* origin, int32_t n,

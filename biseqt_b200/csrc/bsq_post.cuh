@@ -449,6 +449,63 @@ __global__ void __launch_bounds__(256) bsq_pack_transcripts(const BsqPair* pairs
 }
 
 // ===========================================================================
+// K5: Alignment post-processing (pw.py:367-448) of a traced batch, one thread per
+// pair over the packed transcripts.  calculate_score adds in the reference's order:
+// every run of M/S is summed on its own (Python's sum() starts from 0) and then added
+// to the score; a gap run adds go + ge * len.
+// ===========================================================================
+__global__ void __launch_bounds__(128) bsq_k5_stats(const BsqPair* pairs, int npairs, const uint8_t* codes,
+                                                    const long long* txoff, const int* txlen, const char* packed,
+                                                    const int* sx, const int* sy, const int* status,
+                                                    const double* subst, int L, double go, double ge,
+                                                    bsq_aln_stats* out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= npairs) return;
+  const BsqPair P = pairs[e];
+  const int oi = P.pad;
+  bsq_aln_stats r;
+  r.n_match = r.n_subst = r.n_ins = r.n_del = 0;
+  r.trunc_lo = -1; r.trunc_hi = -1; r.trunc_start_x = -1; r.trunc_start_y = -1;
+  r.rescore = 0.0;
+  const int st = status[oi];
+  const int len = txlen[oi];
+  if ((st == BSQ_OK || st == BSQ_REF_WOULD_ABORT) && len > 0) {
+    const char* tx = packed + txoff[oi];
+    const uint8_t* o = codes + P.o_off;
+    const uint8_t* m = codes + P.m_off;
+    int i = sx[oi], j = sy[oi];
+    double score = 0.0;
+    int t = 0;
+    int first_m = -1, last_m = -1, fx = 0, fy = 0;
+    while (t < len) {
+      const char op = tx[t];
+      int run = 1;
+      while (t + run < len && tx[t + run] == op) run++;
+      if (op == 'M' || op == 'S') {
+        double acc = 0.0;
+        for (int k = 0; k < run; k++) acc = __dadd_rn(acc, subst[(int)o[i + k] * L + (int)m[j + k]]);
+        score = __dadd_rn(score, acc);
+        if (op == 'M') {
+          r.n_match += run;
+          if (first_m < 0) { first_m = t; fx = i; fy = j; }
+          last_m = t + run - 1;
+        } else {
+          r.n_subst += run;
+        }
+        i += run; j += run;
+      } else {
+        score = __dadd_rn(score, __dadd_rn(go, __dmul_rn(ge, (double)run)));
+        if (op == 'I') { r.n_ins += run; j += run; } else { r.n_del += run; i += run; }
+      }
+      t += run;
+    }
+    r.rescore = score;
+    if (first_m >= 0 && first_m < last_m) { r.trunc_lo = first_m; r.trunc_hi = last_m; r.trunc_start_x = fx; r.trunc_start_y = fy; }
+  }
+  out[oi] = r;
+}
+
+// ===========================================================================
 // table_scores(): H of every cell of one STD problem (pw.py:278-285).  A
 // debug/teaching path: one thread block, anti-diagonal sweep over global
 // memory, F64 only.

@@ -185,6 +185,26 @@ int bsq_batch_fetch(bsq_batch* batch, double* score, int32_t* end_x, int32_t* en
                     int32_t* start_x, int32_t* start_y, int32_t* status,
                     int64_t* tx_off, char* tx_buf, int64_t tx_cap, int64_t* tx_total);
 
+/*
+ * Alignment post-processing for every pair of a traced, resident batch, on the device
+ * (the step right after the DP in every caller, e.g. experiments/blot_stats.py:460-470):
+ *   n_match/n_subst/n_ins/n_del   op counts; Alignment.projected_len (pw.py:367-389) is
+ *                                 n_match+n_subst+n_del on the origin, +n_ins on the mutant
+ *   rescore                       Alignment.calculate_score (pw.py:391-428) of the transcript with
+ *                                 the batch's own scores, summed in the reference's order
+ *   trunc_*                       Alignment.truncate_to_match (pw.py:430-448): transcript range
+ *                                 [trunc_lo, trunc_hi] and the new frame-relative start, or
+ *                                 trunc_lo = -1 where the reference returns None
+ * Pairs without a transcript (status != BSQ_OK / BSQ_REF_WOULD_ABORT) get zeros and trunc_lo = -1.
+ */
+typedef struct {
+  int32_t n_match, n_subst, n_ins, n_del;
+  int32_t trunc_lo, trunc_hi;
+  int32_t trunc_start_x, trunc_start_y;
+  double rescore;
+} bsq_aln_stats;
+int bsq_batch_stats(bsq_batch* batch, bsq_aln_stats* out);
+
 /* Aligner.table_scores() (pw.py:278-285): H of every cell of ONE STD problem,
  * (n+1)*(m+1) doubles row-major. Debug/teaching path, not a hot path. */
 int bsq_table_scores(bsq_ctx* ctx, const bsq_params* params,

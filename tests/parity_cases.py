@@ -238,6 +238,64 @@ def run_duo_short_reads(make_engine, seed, npairs=37):
         del os.environ['BSQ_UNIFORM_MIN']
 
 
+def _py_stats(pr, tx, sx, sy):
+    """Alignment.projected_len / calculate_score / truncate_to_match (pw.py:367-448) in plain
+    Python, the way biseqt_b200.pw.Alignment (and the reference) compute them."""
+    import re
+    S, go, ge = pr['subst'], pr['go'], pr['ge']
+    o, m = pr['origin'], pr['mutant']
+    score, i, j = 0., sx, sy
+    for match in re.finditer(r'(.)\1*', tx):
+        run = match.group(0)
+        op, num = run[0], len(run)
+        if op in 'MS':
+            score += sum(S[o[i + k]][m[j + k]] for k in range(num))
+            i, j = i + num, j + num
+        else:
+            score += go + ge * num
+            if op == 'I':
+                j += num
+            else:
+                i += num
+    trunc = None
+    if 'M' in tx:
+        a, b = tx.index('M'), tx.rindex('M')
+        if a < b:
+            ox = sx + sum(c in 'DS' for c in tx[:a])
+            oy = sy + sum(c in 'IS' for c in tx[:a])
+            trunc = (a, b, ox, oy)
+    return {c: tx.count(c) for c in 'MSID'}, score, trunc
+
+
+def run_stats(eng, seed, npairs=14, hi=70):
+    """Device-side Alignment post-processing against the Python definitions."""
+    rng = np.random.default_rng(seed)
+    for mode, typ in ((0, 1), (0, 0), (0, 4), (1, 2), (1, 1)):
+        probs = make_batch(rng, npairs, mode, typ, 5, hi)
+        p0 = probs[0]
+        codes, o_off, o_len, m_off, m_len = batch.pack_pairs([(p['origin'], p['mutant']) for p in probs])
+        kw = {}
+        if mode == 1:
+            kw = dict(dmin=[p['diag_range'][0] for p in probs], dmax=[p['diag_range'][1] for p in probs])
+        rb = eng.upload(codes, o_off, o_len, m_off, m_len, mode, typ, p0['subst'], p0['go'], p0['ge'], **kw)
+        rb.run()
+        r = rb.fetch()
+        st = rb.stats()
+        for i, pr in enumerate(probs):
+            if int(r.status[i]) not in (0, 4) or not r.transcript(i):
+                assert st['trunc_lo'][i] == -1 and st['n_match'][i] == 0
+                continue
+            cnt, score, trunc = _py_stats(pr, r.transcript(i), int(r.start_x[i]), int(r.start_y[i]))
+            assert (st['n_match'][i], st['n_subst'][i], st['n_ins'][i], st['n_del'][i]) == \
+                (cnt['M'], cnt['S'], cnt['I'], cnt['D']), i
+            assert st['rescore'][i] == score, (i, st['rescore'][i], score)
+            if trunc is None:
+                assert st['trunc_lo'][i] == -1
+            else:
+                assert (st['trunc_lo'][i], st['trunc_hi'][i], st['trunc_start_x'][i], st['trunc_start_y'][i]) == trunc
+        rb.release()
+
+
 def run_dtype_equivalence(eng, seed, npairs=12, lo=5, hi=60):
     """Integer scores: the I32 fast path and the F64 path give identical results."""
     rng = np.random.default_rng(seed)

@@ -252,6 +252,7 @@ inline int __all_sync(unsigned m, int pred) {
 }
 
 inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline long long __double_as_longlong(double d) { long long v; memcpy(&v, &d, 8); return v; }
 inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }

@@ -86,3 +86,7 @@ def test_emu_uniform_batches(emu_lib):
 
 def test_emu_duo_short_reads(emu_lib):
     pc.run_duo_short_reads(lambda: batch.Engine(0, lib=emu_lib), seed=87, npairs=11)
+
+
+def test_emu_stats(emu_engine):
+    pc.run_stats(emu_engine, seed=97)

@@ -92,6 +92,10 @@ def test_gpu_chunked():
     pc.run_chunked(lambda: batch.Engine(0), seed=81)
 
 
+def test_gpu_stats(gpu_engine):
+    pc.run_stats(gpu_engine, seed=97, npairs=200, hi=300)
+
+
 def test_gpu_uniform_batches():
     pc.run_uniform_batches(lambda: batch.Engine(0), seed=83)
 

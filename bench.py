@@ -392,12 +392,12 @@ def main():
     # secondary workloads (rank 0, single GPU): f64 path and the banded kernels
     if rank == 0 and world == 1 and not args.no_extras:
         extras = {}
-        for k2 in ('c2_logodds', 'c3_int', 'c3_logodds'):
+        for k2 in ('c2_logodds', 'c3_int', 'c3_logodds', 'c4_int', 'c5_int', 'c1'):
             n2 = WORKLOAD_PAIRS[k2] if k2 != 'c2_logodds' else min(npairs, 250000)
             try:
                 w2 = bw.make(k2, n2, seed=3)
-                m2 = measure(eng, w2, max(2, args.steps // 2), 3, local, do_e2e=True)
                 st2 = max(2, args.steps // 2)
+                m2 = measure(eng, w2, st2, 3 if not k2.startswith('c5') else 1, local, do_e2e=True)
                 opc2 = ops_per_cell(w2['go'])
                 which2 = {'i32': 'IADD', 'i16x2': 'VADD2'}.get(m2['dtype'], 'DADD')
                 pk = roofline['pipe_rates_gops'].get(which2) if isinstance(roofline['pipe_rates_gops'], dict) else None

@@ -942,10 +942,10 @@ int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, cudaStream_t
   // long pairs: one warp per pair walking shared-memory tiles; short pairs: one
   // thread per pair (there are enough of them to hide the load latency)
   const long long avg_path = P.slot_bytes / std::max<long long>((long long)P.E, 1);
-  const char* force = getenv("BSQ_TRACE_KERNEL");  // test hook: "thread" / "warp"
+  const char* force = getenv("BSQ_TRACE_KERNEL");  // test hook: "thread" / "warp" / "narrow"
   bool warp_walk = avg_path >= 1024;
   if (force && force[0] == 't') warp_walk = false;
-  if (force && force[0] == 'w') warp_walk = true;
+  if (force && (force[0] == 'w' || force[0] == 'n')) warp_walk = true;  // "narrow": 8 lanes per pair
   if (k3) {  // one warp per pair over the [strip][t][lane] table
     const int grid = (int)ch.count;
 #define BSQ_WALK3(KK) { if (P.gosign < 0) BSQ_LAUNCH((bsq_k3_walk<KK, -1>), grid, 32, 0, stream, T); \
@@ -954,10 +954,14 @@ int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, cudaStream_t
     if (T.K == 2) BSQ_WALK3(2) else if (T.K == 4) BSQ_WALK3(4) else BSQ_WALK3(8)
 #undef BSQ_WALK3
   } else if (warp_walk) {
-    const int grid = (int)((ch.count + BSQ_WALK_WARPS - 1) / BSQ_WALK_WARPS);
-#define BSQ_WALK(F, GS) BSQ_LAUNCH((bsq_k4_walk<F, GS>), grid, 32 * BSQ_WALK_WARPS, 0, stream, T)
-    if (ch.family == 1) { if (P.gosign < 0) BSQ_WALK(1, -1); else if (P.gosign == 0) BSQ_WALK(1, 0); else BSQ_WALK(1, 1); }
-    else { if (P.gosign < 0) BSQ_WALK(2, -1); else if (P.gosign == 0) BSQ_WALK(2, 0); else BSQ_WALK(2, 1); }
+    // lanes per pair: 8 when there are enough pairs to fill the GPU four times over, else a warp
+    const bool narrow = (ch.count >= (int64_t)ctx->sms * 16 * 4 || (force && force[0] == 'n')) && !(force && force[0] == 'w');
+    const int ppb = BSQ_WALK_WARPS * (narrow ? 4 : 1);  // pairs per block
+    const int grid = (int)((ch.count + ppb - 1) / ppb);
+#define BSQ_WALK(F, GS) { if (narrow) BSQ_LAUNCH((bsq_k4_walk<F, GS, 8>), grid, 32 * BSQ_WALK_WARPS, 0, stream, T); \
+                          else BSQ_LAUNCH((bsq_k4_walk<F, GS, 32>), grid, 32 * BSQ_WALK_WARPS, 0, stream, T); }
+    if (ch.family == 1) { if (P.gosign < 0) BSQ_WALK(1, -1) else if (P.gosign == 0) BSQ_WALK(1, 0) else BSQ_WALK(1, 1) }
+    else { if (P.gosign < 0) BSQ_WALK(2, -1) else if (P.gosign == 0) BSQ_WALK(2, 0) else BSQ_WALK(2, 1) }
 #undef BSQ_WALK
   } else {
     // small blocks so they fit beside a resident fill kernel's register allocation

@@ -72,16 +72,18 @@ __global__ void __launch_bounds__(128) bsq_k4_traceback(const BsqTraceArgs A) {
 }
 
 // ---------------------------------------------------------------------------
-// K4w: the same walk for LONG pairs, one warp per pair.  A thread-per-pair walk
-// is a chain of dependent HBM loads (~1 us each); here the warp stages the
-// next BSQ_TILE_WORDS of pointer rows below the current position into shared
-// memory with coalesced 16-byte loads and every lane then performs the same
-// walk out of shared memory (lane 0 emits).  The position inside a row is kept
+// K4w: the same walk for LONG pairs, a group of GW = 8 or 32 lanes per pair (4 or 1 pairs per warp).
+// A thread-per-pair walk is a chain of dependent HBM loads (~1 us each); here the
+// group stages the next BSQ_TILE_WORDS of pointer rows below the current position
+// into shared memory with coalesced 16-byte loads and every lane of the group then
+// performs the same walk out of shared memory (lane 0 emits); the rows below the tile are
+// prefetched into L2 meanwhile.  Big batches use 8 lanes per pair (more walks in flight per
+// issue slot), small ones 32 (groups of one warp diverge and would slow each other down).  The position inside a row is kept
 // incrementally (lane, column) so the walk needs no divisions.
 //   FAMILY 1: K1 layout [pass][x+lane][lane][word]   row id = pass*(n+G) + x + lane
 //   FAMILY 2: K2 layout [s - s0][lane][word]    row id = s - s0
 // ---------------------------------------------------------------------------
-#define BSQ_TILE_WORDS 1024
+#define BSQ_TILE_WORDS 512     // per pair
 #define BSQ_WALK_WARPS 4
 #define BSQ_LET_WIN 128
 
@@ -92,20 +94,25 @@ __device__ __forceinline__ uint32_t bsq_gap_base_t(uint32_t mk, uint32_t own) {
   return bsq_lowest(mk);
 }
 
-template <int FAMILY, int GOS>
+template <int FAMILY, int GOS, int BSQ_WALK_GW>
 __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTraceArgs A) {
-  __shared__ uint32_t s_tile[BSQ_WALK_WARPS][BSQ_TILE_WORDS];
-  __shared__ uint8_t s_let[BSQ_WALK_WARPS][2][BSQ_LET_WIN];  // staged letters: origin, mutant
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p = blockIdx.x * BSQ_WALK_WARPS + wib;
-  if (p >= A.npairs) return;  // whole warp
+  constexpr int BSQ_WALK_PPW = 32 / BSQ_WALK_GW;
+  __shared__ uint32_t s_tile[BSQ_WALK_WARPS * BSQ_WALK_PPW][BSQ_TILE_WORDS];
+  __shared__ uint8_t s_let[BSQ_WALK_WARPS * BSQ_WALK_PPW][2][BSQ_LET_WIN];  // staged letters: origin, mutant
+  const int wib = threadIdx.x >> 5;
+  const int lane = threadIdx.x & (BSQ_WALK_GW - 1);              // lane inside my group of GW
+  const int grp = (threadIdx.x & 31) / BSQ_WALK_GW;              // my pair's slot inside the warp
+  const unsigned gmask = (BSQ_WALK_GW == 32) ? 0xffffffffu : (((1u << BSQ_WALK_GW) - 1u) << (grp * BSQ_WALK_GW));
+  const int slot = wib * BSQ_WALK_PPW + grp;
+  const int p = blockIdx.x * (BSQ_WALK_WARPS * BSQ_WALK_PPW) + slot;
+  if (p >= A.npairs) return;  // the whole group
   const BsqPair P = A.pairs[p];
   const int oi = P.pad;
   if (A.status[oi] != BSQ_OK) {
     if (lane == 0) { A.txlen[oi] = 0; A.sx[oi] = -1; A.sy[oi] = -1; }
     return;
   }
-  uint32_t* tile = s_tile[wib];
+  uint32_t* tile = s_tile[slot];
   const int G = A.G, K = A.K;
   const int WP = (FAMILY == 1) ? BSQ_K1_WPL(K) : (K / 2 + 7) / 8;  // words per lane per row
   const int RB = G * WP;                                        // words per row
@@ -135,8 +142,8 @@ __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTrac
   BSQ_RECOL();
   uint32_t arrive = BSQ_MM;     // how we got here: M (or the end cell) -> lowest bit
   const int maxlen = P.n + P.m;
-  uint8_t* obuf = s_let[wib][0];
-  uint8_t* mbuf = s_let[wib][1];
+  uint8_t* obuf = s_let[slot][0];
+  uint8_t* mbuf = s_let[slot][1];
   int xb = x + 1, yb = y + 1;   // obuf holds o[xb .. xb+WIN), mbuf m[yb .. yb+WIN); empty (forces a load)
   constexpr int BATCH = 8;       // M/S steps examined per round out of preloaded words
   const int mstep = (FAMILY == 1) ? RB : 2 * RB;   // a diagonal move goes back 1 row (K1) / 2 rows (K2)
@@ -149,22 +156,31 @@ __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTrac
       rows = (int)(rid - lo + 1);
       const int nw = rows * RB;            // multiple of 4 words
       const uint4* src = (const uint4*)(table + tlo * RB);
-      __syncwarp();
-      for (int i = lane; i < nw / 4; i += 32) ((uint4*)tile)[i] = src[i];
-      __syncwarp();
+      __syncwarp(gmask);
+      for (int i = lane; i < nw / 4; i += BSQ_WALK_GW) ((uint4*)tile)[i] = src[i];
+#ifndef BSQ_SIMT_EMU
+      {  // the walk goes on below this tile: pull those rows into L2 while this tile is walked
+        const long long plo = tlo - R > 0 ? tlo - R : 0;
+        const char* pf = (const char*)(table + plo * RB) + 128 * lane;
+        if (tlo > 0 && 128 * lane < (int)(tlo - plo) * RB * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+        if (BSQ_WALK_GW < 16 && tlo > 0 && 128 * (lane + BSQ_WALK_GW) < (int)(tlo - plo) * RB * 4)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 128 * BSQ_WALK_GW));
+      }
+#endif
+      __syncwarp(gmask);
       roff = (int)(rid - tlo) * RB;
     }
     if (x - BATCH < xb && xb > 0) {  // the walk only moves towards smaller x and y
       xb = x - BSQ_LET_WIN; if (xb < 0) xb = 0;
-      __syncwarp();
-      for (int i = lane; i < BSQ_LET_WIN; i += 32) if (xb + i < P.n) obuf[i] = oseq[xb + i];
-      __syncwarp();
+      __syncwarp(gmask);
+      for (int i = lane; i < BSQ_LET_WIN; i += BSQ_WALK_GW) if (xb + i < P.n) obuf[i] = oseq[xb + i];
+      __syncwarp(gmask);
     }
     if (y - BATCH < yb && yb > 0) {
       yb = y - BSQ_LET_WIN; if (yb < 0) yb = 0;
-      __syncwarp();
-      for (int i = lane; i < BSQ_LET_WIN; i += 32) if (yb + i < P.m) mbuf[i] = mseq[yb + i];
-      __syncwarp();
+      __syncwarp(gmask);
+      for (int i = lane; i < BSQ_LET_WIN; i += BSQ_WALK_GW) if (yb + i < P.m) mbuf[i] = mseq[yb + i];
+      __syncwarp(gmask);
     }
     // preload the nibbles a run of up to BATCH diagonal moves would visit: the loads are
     // independent of each other, so the chain per move is a few ALU ops, not a memory access
@@ -259,7 +275,9 @@ template <int K, int GOS>
 __global__ void __launch_bounds__(32) bsq_k3_walk(const BsqTraceArgs A) {
   typedef typename BsqK3Unit<K>::type PU;
   constexpr int G = 32, BW = G * K;
+  constexpr int LOGK = (K == 2) ? 1 : (K == 4 ? 2 : 3);
   constexpr int TSTEPS = BSQ_K3_TILE_BYTES / (G * (int)sizeof(PU));
+  constexpr int BATCH = 8;       // diagonal moves examined per round out of preloaded nibbles
   __shared__ uint4 s_tile4[BSQ_K3_TILE_BYTES / 16];
   __shared__ uint8_t s_let[2][BSQ_K3_LET_WIN];
   PU* tile = (PU*)s_tile4;
@@ -274,10 +292,10 @@ __global__ void __launch_bounds__(32) bsq_k3_walk(const BsqTraceArgs A) {
   }
   const int ex = A.ex[oi], ey = A.ey[oi];
   int x = ex, y = ey, len = 0;
-  int j = y / BW, l = (y - j * BW) / K, k = y - j * BW - l * K;
+  int j = y / BW;                // strip
+  int c = y - j * BW;            // column inside the strip: lane = c >> LOGK, nibble = c & (K-1)
   int xlo = j * BW + P.dmin;
   xlo = xlo < 0 ? 0 : xlo;
-  int t = x - xlo + l;
   const long long tstride = P.s0;
   const PU* table = (const PU*)(A.ptr + P.ptr_off);
   const uint8_t* oseq = A.codes + P.o_off;
@@ -290,6 +308,7 @@ __global__ void __launch_bounds__(32) bsq_k3_walk(const BsqTraceArgs A) {
   int xb = x + 1, yb = y + 1;    // obuf holds o[xb .. xb+WIN), mbuf m[yb .. yb+WIN); empty
   uint32_t arrive = BSQ_MM;
   for (;;) {
+    const int t = x - xlo + (c >> LOGK);
     if (t < tlo || t > thi) {    // stage the steps at and below t
       thi = t;
       tlo = t - TSTEPS + 1;
@@ -300,42 +319,73 @@ __global__ void __launch_bounds__(32) bsq_k3_walk(const BsqTraceArgs A) {
       for (int i = lane; i < n16; i += 32) s_tile4[i] = src[i];
       __syncwarp();
     }
-    const uint32_t mk = ((uint32_t)tile[(t - tlo) * G + l] >> (4 * k)) & 0xFu;
-    const uint32_t op = (arrive == BSQ_MM) ? bsq_lowest(mk) : bsq_gap_base_t<GOS>(mk, arrive);
-    if (op == BSQ_MB || op == 0u || len >= maxlen) break;
-    char ch;
-    bool left_col = false;       // the move leaves column y
-    if (op == BSQ_MM) {
-      if (x - 1 < xb) {          // the walk only moves towards smaller x and y
-        xb = x - BSQ_K3_LET_WIN; if (xb < 0) xb = 0;
-        __syncwarp();
-        for (int i = lane; i < BSQ_K3_LET_WIN; i += 32) if (xb + i < P.n) obuf[i] = oseq[xb + i];
-        __syncwarp();
-      }
-      if (y - 1 < yb) {
-        yb = y - BSQ_K3_LET_WIN; if (yb < 0) yb = 0;
-        __syncwarp();
-        for (int i = lane; i < BSQ_K3_LET_WIN; i += 32) if (yb + i < P.m) mbuf[i] = mseq[yb + i];
-        __syncwarp();
-      }
-      ch = (obuf[x - 1 - xb] == mbuf[y - 1 - yb]) ? 'M' : 'S';
-      x--; y--; t--;
-      left_col = true;
-    } else if (op == BSQ_MD) {
-      ch = 'D'; x--; t--;
-    } else {
-      ch = 'I'; y--;
-      left_col = true;
+    if (x - BATCH < xb && xb > 0) {  // the walk only moves towards smaller x and y
+      xb = x - BSQ_K3_LET_WIN; if (xb < 0) xb = 0;
+      __syncwarp();
+      for (int i = lane; i < BSQ_K3_LET_WIN; i += 32) if (xb + i < P.n) obuf[i] = oseq[xb + i];
+      __syncwarp();
     }
-    if (left_col && --k < 0) {
-      k = K - 1;
-      t--;
-      if (--l < 0) {             // into the previous strip
-        l = G - 1;
+    if (y - BATCH < yb && yb > 0) {
+      yb = y - BSQ_K3_LET_WIN; if (yb < 0) yb = 0;
+      __syncwarp();
+      for (int i = lane; i < BSQ_K3_LET_WIN; i += 32) if (yb + i < P.m) mbuf[i] = mseq[yb + i];
+      __syncwarp();
+    }
+    // the q-th diagonal move from here visits (x-q, y-q): column c-q, step t-q-(lanes crossed).
+    // Those nibbles are loaded up front (independent loads), as far as strip and tile reach.
+    int jmax = c + 1;                                  // stay inside the strip
+    jmax = jmax > BATCH ? BATCH : jmax;
+    const int room = ((t - tlo) >> 1) + 1;             // a move lowers the step by at most 2
+    jmax = jmax > room ? room : jmax;
+    uint32_t nib[BATCH];
+#pragma unroll
+    for (int q = 0; q < BATCH; q++) {
+      nib[q] = 0u;
+      if (q < jmax) {
+        const int cq = c - q, lq = cq >> LOGK;
+        const int tq = x - q - xlo + lq;
+        nib[q] = ((uint32_t)tile[(tq - tlo) * G + lq] >> (4 * (cq & (K - 1)))) & 0xFu;
+      }
+    }
+    int taken = 0;
+    uint32_t op = 0u;
+#pragma unroll
+    for (int q = 0; q < BATCH; q++) {
+      if (q < jmax && taken == q) {
+        const uint32_t mk = nib[q];
+        op = (q == 0 && arrive != BSQ_MM) ? bsq_gap_base_t<GOS>(mk, arrive) : bsq_lowest(mk);
+        if (op == BSQ_MM && len < maxlen) {
+          const char ch = (obuf[x - 1 - xb] == mbuf[y - 1 - yb]) ? 'M' : 'S';
+          x--; y--; len++;
+          if (lane == 0) wr[-len] = ch;
+          arrive = BSQ_MM;
+          taken = q + 1;
+        }
+      }
+    }
+    if (taken > 0) {
+      c -= taken;
+      if (c < 0) {               // into the previous strip
         j--;
+        c += BW;
         xlo = j * BW + P.dmin;
         xlo = xlo < 0 ? 0 : xlo;
-        t = x - xlo + l;
+        tlo = 1; thi = 0;
+      }
+      if (taken == jmax) continue;   // the run may go on
+    }
+    // `op` is the op at the current cell and it is not a (possible) diagonal move
+    if (op == BSQ_MB || op == 0u || len >= maxlen || op == BSQ_MM) break;
+    char ch;
+    if (op == BSQ_MD) {
+      ch = 'D'; x--;
+    } else {
+      ch = 'I'; y--;
+      if (--c < 0) {
+        j--;
+        c += BW;
+        xlo = j * BW + P.dmin;
+        xlo = xlo < 0 ? 0 : xlo;
         tlo = 1; thi = 0;
       }
     }

@@ -3,6 +3,8 @@ against tests/simt_emu (fiber SIMT emulator) and driven through the real C ABI,
 checked against the oracle.  These are NOT the parity tests proper (those are
 tests/test_gpu_parity.py, -m gpu); they exist so that kernel bugs are found
 without spending GPU minutes."""
+import pytest
+
 from biseqt_b200 import batch
 from tests import parity_cases as pc
 
@@ -35,9 +37,10 @@ def test_emu_wide_band_interior(emu_engine):
     pc.run_wide_bands(emu_engine, seed=45, length=520, radii=(460,))
 
 
-def test_emu_warp_traceback(emu_lib, monkeypatch):
-    """Force the warp-per-pair tile walker (normally only used for long pairs)."""
-    monkeypatch.setenv('BSQ_TRACE_KERNEL', 'warp')
+@pytest.mark.parametrize('which', ['warp', 'narrow'])
+def test_emu_warp_traceback(emu_lib, monkeypatch, which):
+    """Force the tile walker (normally only used for long pairs): a warp, or 8 lanes, per pair."""
+    monkeypatch.setenv('BSQ_TRACE_KERNEL', which)
     eng = batch.Engine(0, lib=emu_lib)
     try:
         pc.run_batches(eng, seed=23, npairs=6, lo=0, hi=60)

@@ -48,7 +48,7 @@ def test_gpu_banded_interior(gpu_engine):
 
 
 def test_gpu_both_traceback_kernels(monkeypatch):
-    for which in ('warp', 'thread'):
+    for which in ('warp', 'narrow', 'thread'):
         monkeypatch.setenv('BSQ_TRACE_KERNEL', which)
         eng = batch.Engine(0)
         try:

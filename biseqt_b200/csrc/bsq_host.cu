@@ -309,7 +309,9 @@ int pick_k3_cfg() {
 // millisecond each, less than spawning threads for them would.
 class WorkerPool {
  public:
-  static WorkerPool& get() { static WorkerPool p; return p; }
+  // never destroyed: a forked child (or exit() from foreign code) must not try to join threads
+  // that do not exist there
+  static WorkerPool& get() { static WorkerPool* p = new WorkerPool(); return *p; }
   int size() const { return (int)th_.size() + 1; }
   // runs job(t) for t in [0, T) -- t = 0 on the caller -- and returns when all are done
   void run(int T, const std::function<void(int)>& job) {
@@ -327,16 +329,11 @@ class WorkerPool {
     done_.wait(lk, [&] { return pending_ == 0; });
     job_ = nullptr;
   }
-  ~WorkerPool() {
-    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; gen_++; }
-    cv_.notify_all();
-    for (auto& t : th_) t.join();
-  }
  private:
   WorkerPool() {
     unsigned hw = std::thread::hardware_concurrency();
     const int n = (int)std::max(1u, std::min(hw, 8u)) - 1;
-    for (int i = 0; i < n; i++) th_.emplace_back([this, i] { loop(i + 1); });
+    for (int i = 0; i < n; i++) { th_.emplace_back([this, i] { loop(i + 1); }); th_.back().detach(); }
   }
   void loop(int id) {
     uint64_t seen = 0;

@@ -178,8 +178,7 @@ class Aligner(object):
             raise Exception('Failed to initialize the DP table.')
         if st == _batch.UNSUPPORTED:
             raise NotImplementedError(
-                'problem outside what this build supports (band wider than '
-                'the banded kernels or score range beyond +/-2^31)')
+                'problem outside what this build supports (score range beyond +/-2^31)')
         if st != _batch.OK:
             self.opt = None
             return None

@@ -300,7 +300,7 @@ int k3_op(int dtype, int cfg, int btype, int gos, int grid, cudaStream_t st, con
 int pick_k3_cfg() {
   const char* e = getenv("BSQ_K3_CFG");  // tuning hook
   const int forced = e ? atoi(e) : -1;
-  return (forced >= 0 && forced < BSQ_K3_NCFG) ? forced : 1;
+  return (forced >= 0 && forced < BSQ_K3_NCFG) ? forced : 2;  // K = 8: measured best on C5
 }
 
 // ---- planning -------------------------------------------------------------

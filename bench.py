@@ -55,7 +55,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                ['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '20'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -360,7 +360,11 @@ def main():
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
         roofline = {
             'bound': 'alu', 'achieved': achieved, 'peak': peak, 'unit': 'Gop/s',
-            'frac': (achieved / peak) if peak else None, 'traffic': None,
+            'frac': (achieved / peak) if peak else None,
+            # DRAM bytes (read + write) of ONE fill launch, from the ncu --set full capture of this
+            # kernel on this workload (profiles/r01_k1h_final_ncu.txt); algorithmic pointer bytes of
+            # a launch (125k pairs x 0.5 B/cell) are 1.43e9
+            'traffic': 2.474e9 if (kind == 'c2_int' and npairs == 1000000 and m['dtype'] == 'i16x2') else None,
             'ops_per_cell': opc, 'pipe': which,
             'note': 'achieved = cells x algorithmic ops/cell / fill-kernel time (CUDA events on the library stream); '
                     'peak = %s issue rate measured in this run (bsq_microbench)' % {'IADD': 'add.s32', 'VADD2': 'packed 16-bit add (VIADD.16x2, two adds per instruction)', 'DADD': 'add.f64'}[which],

@@ -33,8 +33,8 @@ if ROOT not in sys.path:
 
 import bench_workloads as bw  # noqa: E402
 
-WORKLOAD_PAIRS = {'c2_int': 1000000, 'c2_logodds': 1000000, 'c3_int': 16384, 'c3_logodds': 16384,
-                  'c4_int': 512, 'c1': 1, 'c5_int': 1, 'c5_logodds': 1, 'c5s_int': 1, 'c5s_logodds': 1}
+WORKLOAD_PAIRS = {'c2_int': 1000000, 'c2_logodds': 1000000, 'c3_int': 32768, 'c3_logodds': 32768,
+                  'c4_int': 1024, 'c1': 1, 'c5_int': 1, 'c5_logodds': 1, 'c5s_int': 1, 'c5s_logodds': 1}
 
 
 def ops_per_cell(go):
@@ -396,10 +396,17 @@ def main():
     # secondary workloads (rank 0, single GPU): f64 path and the banded kernels
     if rank == 0 and world == 1 and not args.no_extras:
         extras = {}
+        made = {}
         for k2 in ('c2_logodds', 'c3_int', 'c3_logodds', 'c4_int', 'c5_int', 'c1'):
             n2 = WORKLOAD_PAIRS[k2] if k2 != 'c2_logodds' else min(npairs, 250000)
             try:
-                w2 = bw.make(k2, n2, seed=3)
+                if k2 == 'c3_logodds' and 'c3_int' in made:   # same pairs, log-odds scores
+                    w2 = dict(made['c3_int'])
+                    S3, go3, ge3 = bw.st.log_odds_scores(4, 0.03, 0.06, 0.12)
+                    w2.update(kind=k2, subst=S3, go=go3, ge=ge3, desc=w2['desc'] + ' (log-odds scores)')
+                else:
+                    w2 = bw.make(k2, n2, seed=3)
+                    made[k2] = w2
                 st2 = max(2, args.steps // 2)
                 m2 = measure(eng, w2, st2, 3 if not k2.startswith('c5') else 1, local, do_e2e=True)
                 opc2 = ops_per_cell(w2['go'])

@@ -140,7 +140,7 @@ class Engine(object):
         tx_off = tx_buf = None
         cap = 0
         if transcripts:
-            cap = int(o_len.astype(np.int64).sum() + m_len.astype(np.int64).sum())
+            cap = int(o_len.sum(dtype=np.int64) + m_len.sum(dtype=np.int64))
             tx_off = arr('tx_off', np.int64, N + 1)
             tx_buf = out.get('tx_buf')
             if tx_buf is None or len(tx_buf) < cap:
@@ -181,7 +181,7 @@ class Engine(object):
             _ptr(status, 'int32_t*'), hb)
         if rc != 0:
             raise BsqError('bsq_solve_batch failed (%d): %s' % (rc, self._err()))
-        cap = int(o_len.astype(np.int64).sum() + m_len.astype(np.int64).sum())
+        cap = int(o_len.sum(dtype=np.int64) + m_len.sum(dtype=np.int64))
         return SolvedBatch(self, hb[0], score, end_x, end_y, status, cap)
 
     def upload(self, codes, o_off, o_len, m_off, m_len, mode, type, subst, go, ge,
@@ -202,7 +202,7 @@ class Engine(object):
             _ptr(dmin, 'int32_t*'), _ptr(dmax, 'int32_t*'), int(bool(keep_tables)), hb)
         if rc != 0:
             raise BsqError('bsq_batch_upload failed (%d): %s' % (rc, self._err()))
-        cap = int(o_len.astype(np.int64).sum() + m_len.astype(np.int64).sum())
+        cap = int(o_len.sum(dtype=np.int64) + m_len.sum(dtype=np.int64))
         return ResidentBatch(self, hb[0], N, cap)
 
     def microbench(self, which):

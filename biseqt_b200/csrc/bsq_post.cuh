@@ -145,6 +145,9 @@ __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTrac
   uint8_t* obuf = s_let[slot][0];
   uint8_t* mbuf = s_let[slot][1];
   int xb = x + 1, yb = y + 1;   // obuf holds o[xb .. xb+WIN), mbuf m[yb .. yb+WIN); empty (forces a load)
+  if constexpr (BSQ_WALK_GW == 32) {
+  // ---- one pair per warp (small batches): latency bound, so runs of diagonal moves are examined
+  // out of preloaded nibbles
   constexpr int BATCH = 8;       // M/S steps examined per round out of preloaded words
   const int mstep = (FAMILY == 1) ? RB : 2 * RB;   // a diagonal move goes back 1 row (K1) / 2 rows (K2)
   bool finished = false;
@@ -253,6 +256,75 @@ __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTrac
     arrive = op;
     len++;
     if (lane == 0) wr[-len] = ch;
+  }
+  } else {
+  // One move per iteration, written without data-dependent branches: the groups of a warp walk
+  // different pairs and would otherwise serialise each other on every gap.
+  for (;;) {
+    if (roff < 0 || roff >= rows * RB) {  // stage the rows at and below `rid`
+      long long lo = rid - R + 1;
+      if (lo < 0) lo = 0;
+      tlo = lo;
+      rows = (int)(rid - lo + 1);
+      const int nw = rows * RB;            // multiple of 4 words
+      const uint4* src = (const uint4*)(table + tlo * RB);
+      __syncwarp(gmask);
+      for (int i = lane; i < nw / 4; i += BSQ_WALK_GW) ((uint4*)tile)[i] = src[i];
+#ifndef BSQ_SIMT_EMU
+      {  // the walk goes on below this tile: pull those rows into L2 while this tile is walked
+        const long long plo = tlo - R > 0 ? tlo - R : 0;
+        const char* pf = (const char*)(table + plo * RB) + 128 * lane;
+        if (tlo > 0 && 128 * lane < (int)(tlo - plo) * RB * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+        if (BSQ_WALK_GW < 16 && tlo > 0 && 128 * (lane + BSQ_WALK_GW) < (int)(tlo - plo) * RB * 4)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 128 * BSQ_WALK_GW));
+      }
+#endif
+      __syncwarp(gmask);
+      roff = (int)(rid - tlo) * RB;
+    }
+    if (x - 1 < xb && xb > 0) {  // the walk only moves towards smaller x and y
+      xb = x - BSQ_LET_WIN; if (xb < 0) xb = 0;
+      __syncwarp(gmask);
+      for (int i = lane; i < BSQ_LET_WIN; i += BSQ_WALK_GW) if (xb + i < P.n) obuf[i] = oseq[xb + i];
+      __syncwarp(gmask);
+    }
+    if (y - 1 < yb && yb > 0) {
+      yb = y - BSQ_LET_WIN; if (yb < 0) yb = 0;
+      __syncwarp(gmask);
+      for (int i = lane; i < BSQ_LET_WIN; i += BSQ_WALK_GW) if (yb + i < P.m) mbuf[i] = mseq[yb + i];
+      __syncwarp(gmask);
+    }
+    const uint32_t mk = (tile[roff + colw] >> sh) & 0xFu;
+    const uint32_t op = (arrive == BSQ_MM) ? bsq_lowest(mk) : bsq_gap_base_t<GOS>(mk, arrive);
+    if (op == BSQ_MB || op == 0u || len >= maxlen) break;
+    const bool isM = (op == BSQ_MM), isD = (op == BSQ_MD), isI = !(isM || isD);
+    const int xi = x - 1 - xb, yi = y - 1 - yb;   // clamped: only meaningful for a diagonal move
+    const char ms = (obuf[xi < 0 ? 0 : xi] == mbuf[yi < 0 ? 0 : yi]) ? 'M' : 'S';
+    const char ch = isM ? ms : (isD ? 'D' : 'I');
+    len++;
+    if (lane == 0) wr[-len] = ch;
+    arrive = op;
+    x -= isI ? 0 : 1;
+    y -= isD ? 0 : 1;
+    if (FAMILY == 2) {   // [s][lane][word]: s = x + y, local diagonal k moves with x - y
+      const int dr = isM ? 2 : 1;
+      rid -= dr;
+      roff -= dr * RB;
+      k += isI ? 1 : (isD ? -1 : 0);
+      if (k < 0) { k = K - 1; l--; }
+      if (k == K) { k = 0; l++; }
+    } else {             // [pass][x + lane][lane][word]
+      int dr = isI ? 0 : 1;
+      if (!isD && --k < 0) {                 // M and I leave the column: maybe the lane, maybe the pass
+        k = K - 1;
+        if (--l < 0) { l = G - 1; rid -= (P.n + 1); roff = -1 - (1 << 28); }  // (pass-1)*(n+G) + x + G-1: restage
+        else dr += 1;                        // the previous lane's rows are skewed by one more
+      }
+      rid -= dr;
+      roff -= dr * RB;
+    }
+    BSQ_RECOL();
+  }
   }
 #undef BSQ_RECOL
   if (lane == 0) {

@@ -316,6 +316,7 @@ class WorkerPool {
   // runs job(t) for t in [0, T) -- t = 0 on the caller -- and returns when all are done
   void run(int T, const std::function<void(int)>& job) {
     if (T <= 1) { job(0); return; }
+    std::lock_guard<std::mutex> one_caller(run_mu_);  // contexts on different host threads share the pool
     {
       std::lock_guard<std::mutex> lk(mu_);
       job_ = &job;
@@ -354,7 +355,7 @@ class WorkerPool {
     }
   }
   std::vector<std::thread> th_;
-  std::mutex mu_;
+  std::mutex mu_, run_mu_;
   std::condition_variable cv_, done_;
   const std::function<void(int)>* job_ = nullptr;
   int want_ = 0, pending_ = 0;

@@ -160,6 +160,7 @@ struct bsq_batch {
 // fill of the next.  Only short pairs profit: their chunks still hold many waves of work,
 // and their thread-per-pair walk fits beside the fill; long pairs are cut by capacity only.
 static int overlap_chunks(int64_t npairs, const int32_t* o_len, const int32_t* m_len) {
+  if (const char* e = getenv("BSQ_TARGET_CHUNKS")) return atoi(e);  // tuning hook
   if (npairs < 32768) return 1;
   int64_t tot = 0;
   const int64_t step = std::max<int64_t>(npairs / 1024, 1);

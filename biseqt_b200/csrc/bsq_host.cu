@@ -135,6 +135,7 @@ struct bsq_ctx {
   cudaStream_t st = nullptr;       // compute
   cudaStream_t st_copy = nullptr;  // H2D / D2H, so copies overlap kernels
   cudaStream_t st_copy2 = nullptr; // pair records / score table: must not queue behind the sequence bytes
+  cudaStream_t st_d2h = nullptr;   // results back to the host while sequence bytes still travel the other way
   cudaStream_t st_trace = nullptr; // traceback + packing of chunk c while chunk c+1 fills
   PinBuf htotals;                  // pinned: running transcript totals per chunk
   std::vector<PlanItem> plan_items;  // planner scratch, kept across calls (no page faults)
@@ -144,6 +145,10 @@ struct bsq_ctx {
   BufSet bufs;
   std::vector<cudaEvent_t> events;
   size_t arena_cap_bytes = 0;  // test hook / safety: upper bound for the pointer arena
+  // cudaMemGetInfo costs 0.1 - 50 ms (measured on the bench box): the one-shot path remembers
+  // "free bytes + our cached arena" and only asks again after a resident batch came or went or
+  // an allocation failed
+  double mem_avail = -1.0;
 };
 
 struct bsq_batch {
@@ -743,11 +748,13 @@ cudaEvent_t get_event(bsq_ctx* ctx, size_t i) {
   return ctx->events[i];
 }
 
-int64_t arena_budget_words(bsq_ctx* ctx, int64_t other_bytes) {
-  size_t fr = 0, tot = 0;
-  if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { fr = (size_t)1 << 30; cudaGetLastError(); }
-  fr += ctx->bufs.ptr.cap;  // our own cached arena counts as available
-  double budget = (double)fr * 0.85 - (double)other_bytes;
+int64_t arena_budget_words(bsq_ctx* ctx, int64_t other_bytes, bool may_use_cached = false) {
+  if (!(may_use_cached && ctx->mem_avail >= 0.0)) {
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { fr = (size_t)1 << 30; cudaGetLastError(); }
+    ctx->mem_avail = (double)fr + (double)ctx->bufs.ptr.cap;  // our own cached arena counts as available
+  }
+  double budget = ctx->mem_avail * 0.85 - (double)other_bytes;
   if (ctx->arena_cap_bytes && budget > (double)ctx->arena_cap_bytes) budget = (double)ctx->arena_cap_bytes;
   if (budget < (double)(1 << 16)) budget = (double)(1 << 16);
   return (int64_t)(budget / 4.0);
@@ -1079,6 +1086,7 @@ bsq_ctx* bsq_create(int device) {
   if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->st_copy2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->st_d2h, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithPriority(&ctx->st_trace, cudaStreamNonBlocking, -1) != cudaSuccess) {
     g_err = "cudaStreamCreate failed"; delete ctx; return nullptr;
   }
@@ -1098,6 +1106,7 @@ void bsq_destroy(bsq_ctx* ctx) {
   cudaStreamDestroy(ctx->st);
   cudaStreamDestroy(ctx->st_copy);
   cudaStreamDestroy(ctx->st_copy2);
+  cudaStreamDestroy(ctx->st_d2h);
   cudaStreamDestroy(ctx->st_trace);
   delete ctx;
 }
@@ -1324,7 +1333,10 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
   cudaStream_t sc = ctx->st, sx = ctx->st_copy;
   const size_t N = (size_t)npairs;
 
-  // ---- 0. sequence bytes: H2D in slices on the copy stream, one event per slice
+  // ---- 0. sequence bytes: H2D in slices on the copy stream, one event per slice.  Only the first
+  // slice is enqueued before the plan exists: the H2D engine serves its queue in order, and the
+  // (small) pair records must not wait behind all the sequence bytes (measured: the first fill
+  // started 7 ms late).  The other slices follow the pair records.
   const int NSL = 8;
   size_t evi = 2;  // events 0/1 bracket the call on the compute stream
   if (!B.codes.ensure((size_t)ncodes + 16)) return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (codes)");
@@ -1334,11 +1346,19 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
   int nsl = 0;
   for (int64_t off = 0; off < ncodes && nsl < NSL; off += slice, nsl++) {
     const int64_t len = std::min<int64_t>(slice, ncodes - off);
-    BSQ_CK(ctx, cudaMemcpyAsync((char*)B.codes.p + off, codes + off, (size_t)len, cudaMemcpyHostToDevice, sx));
     ev_code[nsl] = get_event(ctx, evi++);
-    BSQ_CK(ctx, cudaEventRecord(ev_code[nsl], sx));
     slice_end[nsl] = off + len;
   }
+  auto enqueue_slices = [&](int from, int to) -> int {
+    for (int i = from; i < to && i < nsl; i++) {
+      const int64_t off = (int64_t)i * slice, len = slice_end[i] - off;
+      BSQ_CK(ctx, cudaMemcpyAsync((char*)B.codes.p + off, codes + off, (size_t)len, cudaMemcpyHostToDevice, sx));
+      BSQ_CK(ctx, cudaEventRecord(ev_code[i], sx));
+    }
+    return BSQ_SUCCESS;
+  };
+  rc = enqueue_slices(0, 1);
+  if (rc != BSQ_SUCCESS) return rc;
   ctx->tm.h2d_bytes += ncodes;
 
   // ---- 1. plan on the host while the bytes fly
@@ -1358,7 +1378,7 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
   }
   const int64_t other = ncodes + 2 * slot_guess + npairs * (int64_t)(sizeof(BsqPair) + 48) + (64 << 20);
   const double t_p1 = now_ms();
-  const int64_t budget = arena_budget_words(ctx, other);
+  const int64_t budget = arena_budget_words(ctx, other, true);
   const double t_p2 = now_ms();
   rc = make_plan(ctx, P, B.hpairs, params, npairs, ncodes, o_off, o_len, m_off, m_len, dmin, dmax,
                  budget / 2, false, overlap_chunks(npairs, o_len, m_len));
@@ -1380,10 +1400,11 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
   if (ok && want_trace) ok = B.slots.ensure((size_t)std::max<int64_t>(P.slot_bytes, 1));
   if (ok && want_tx) ok = B.txoff.ensure(8 * (N + 1)) && B.tiles.ensure(8 * (size_t)ntiles_max) &&
                           B.packed.ensure((size_t)std::max<int64_t>(P.slot_bytes, 1));
-  if (!ok) { cudaStreamSynchronize(sx); return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed"); }
+  if (!ok) { ctx->mem_avail = -1.0; cudaStreamSynchronize(sx); return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed"); }
 
-  // ---- 2. pair records + score table on their own copy stream (the sequence bytes are still in flight on the other)
-  cudaStream_t sp = ctx->st_copy2;
+  // ---- 2. pair records + score table right behind the first slice of sequence bytes, the rest of
+  // the sequence bytes behind them
+  cudaStream_t sp = sx;
   std::vector<int> subst_i;
   rc = upload_pairs(ctx, B, P, sp);
   if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(sx); cudaStreamSynchronize(sp); return rc; }
@@ -1398,6 +1419,8 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
   if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(sx); cudaStreamSynchronize(sp); return rc; }
   cudaEvent_t ev_pairs = get_event(ctx, evi++);
   BSQ_CK(ctx, cudaEventRecord(ev_pairs, sp));
+  rc = enqueue_slices(1, nsl);
+  if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(sx); return rc; }
 
   // ---- 3. compute stream: chunk after chunk
   cudaEvent_t t0 = get_event(ctx, 0), t1 = get_event(ctx, 1);
@@ -1446,17 +1469,19 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
   }
   BSQ_CK(ctx, cudaEventRecord(t1, sc));
 
-  // ---- 4. copy stream: ship results back as chunks finish
+  // ---- 4. D2H stream: ship results back as chunks finish (PCIe is full duplex: the sequence bytes
+  // of later chunks are still arriving on the H2D stream)
+  cudaStream_t sd = ctx->st_d2h;
   long long* htot = ctx->htotals.as<long long>();
   int rc_cap = BSQ_SUCCESS;
   auto d2h_range = [&](int64_t lo, int64_t cnt) -> int {
     const size_t n4 = 4 * (size_t)cnt, o4 = 4 * (size_t)lo;
-    BSQ_CK(ctx, cudaMemcpyAsync(score + lo, (char*)B.score.p + 8 * (size_t)lo, 8 * (size_t)cnt, cudaMemcpyDeviceToHost, sx));
-    if (end_x) BSQ_CK(ctx, cudaMemcpyAsync(end_x + lo, (char*)B.ex.p + o4, n4, cudaMemcpyDeviceToHost, sx));
-    if (end_y) BSQ_CK(ctx, cudaMemcpyAsync(end_y + lo, (char*)B.ey.p + o4, n4, cudaMemcpyDeviceToHost, sx));
-    if (want_trace && start_x) BSQ_CK(ctx, cudaMemcpyAsync(start_x + lo, (char*)B.sx.p + o4, n4, cudaMemcpyDeviceToHost, sx));
-    if (want_trace && start_y) BSQ_CK(ctx, cudaMemcpyAsync(start_y + lo, (char*)B.sy.p + o4, n4, cudaMemcpyDeviceToHost, sx));
-    BSQ_CK(ctx, cudaMemcpyAsync(status + lo, (char*)B.status.p + o4, n4, cudaMemcpyDeviceToHost, sx));
+    BSQ_CK(ctx, cudaMemcpyAsync(score + lo, (char*)B.score.p + 8 * (size_t)lo, 8 * (size_t)cnt, cudaMemcpyDeviceToHost, sd));
+    if (end_x) BSQ_CK(ctx, cudaMemcpyAsync(end_x + lo, (char*)B.ex.p + o4, n4, cudaMemcpyDeviceToHost, sd));
+    if (end_y) BSQ_CK(ctx, cudaMemcpyAsync(end_y + lo, (char*)B.ey.p + o4, n4, cudaMemcpyDeviceToHost, sd));
+    if (want_trace && start_x) BSQ_CK(ctx, cudaMemcpyAsync(start_x + lo, (char*)B.sx.p + o4, n4, cudaMemcpyDeviceToHost, sd));
+    if (want_trace && start_y) BSQ_CK(ctx, cudaMemcpyAsync(start_y + lo, (char*)B.sy.p + o4, n4, cudaMemcpyDeviceToHost, sd));
+    BSQ_CK(ctx, cudaMemcpyAsync(status + lo, (char*)B.status.p + o4, n4, cudaMemcpyDeviceToHost, sd));
     ctx->tm.d2h_bytes += cnt * (8 + 4 * (1 + (end_x != 0) + (end_y != 0) + (start_x != 0) + (start_y != 0)));
     return BSQ_SUCCESS;
   };
@@ -1465,18 +1490,18 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
     for (size_t ci = 0; ci < NC; ci++) {
       const Chunk& ch = P.chunks[ci];
       const int64_t lo = ch.idx_lo, cnt = ch.idx_hi - ch.idx_lo;
-      BSQ_CK(ctx, cudaStreamWaitEvent(sx, ev_done[ci], 0));
+      BSQ_CK(ctx, cudaStreamWaitEvent(sd, ev_done[ci], 0));
       rc = d2h_range(lo, cnt);
       if (rc != BSQ_SUCCESS) return rc;
       if (want_tx) {
-        BSQ_CK(ctx, cudaMemcpyAsync(tx_off + lo, B.txoff.as<long long>() + lo, 8 * (size_t)cnt, cudaMemcpyDeviceToHost, sx));
-        BSQ_CK(ctx, cudaMemcpyAsync(htot + ci + 1, totals + ci + 1, 8, cudaMemcpyDeviceToHost, sx));
-        BSQ_CK(ctx, cudaStreamSynchronize(sx));  // later chunks are already queued on the compute stream
+        BSQ_CK(ctx, cudaMemcpyAsync(tx_off + lo, B.txoff.as<long long>() + lo, 8 * (size_t)cnt, cudaMemcpyDeviceToHost, sd));
+        BSQ_CK(ctx, cudaMemcpyAsync(htot + ci + 1, totals + ci + 1, 8, cudaMemcpyDeviceToHost, sd));
+        BSQ_CK(ctx, cudaStreamSynchronize(sd));  // later chunks are already queued on the compute stream
         const long long upto = htot[ci + 1];
         ctx->tm.d2h_bytes += 8 * cnt + 8;
         if (upto > tx_cap) { rc_cap = BSQ_ERR_CAPACITY; }
         else if (upto > shipped) {
-          BSQ_CK(ctx, cudaMemcpyAsync(tx_buf + shipped, B.packed.as<char>() + shipped, (size_t)(upto - shipped), cudaMemcpyDeviceToHost, sx));
+          BSQ_CK(ctx, cudaMemcpyAsync(tx_buf + shipped, B.packed.as<char>() + shipped, (size_t)(upto - shipped), cudaMemcpyDeviceToHost, sd));
           ctx->tm.d2h_bytes += upto - shipped;
         }
         shipped = upto;
@@ -1484,18 +1509,19 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
     }
     if (want_tx) { tx_off[N] = shipped; if (tx_total) *tx_total = shipped; }
   } else {
-    BSQ_CK(ctx, cudaStreamWaitEvent(sx, t1, 0));
+    BSQ_CK(ctx, cudaStreamWaitEvent(sd, t1, 0));
     rc = d2h_range(0, npairs);
     if (rc != BSQ_SUCCESS) return rc;
     if (want_tx) {
-      BSQ_CK(ctx, cudaStreamSynchronize(sx));
+      BSQ_CK(ctx, cudaStreamSynchronize(sd));
       cudaStream_t keep = ctx->st;
-      ctx->st = sx;  // fetch_transcripts issues on ctx->st
+      ctx->st = sd;  // fetch_transcripts issues on ctx->st
       rc_cap = fetch_transcripts(ctx, B, P, tx_off, tx_buf, tx_cap, tx_total);
       ctx->st = keep;
       if (rc_cap != BSQ_SUCCESS && rc_cap != BSQ_ERR_CAPACITY) return rc_cap;
     }
   }
+  BSQ_CK(ctx, cudaStreamSynchronize(sd));
   BSQ_CK(ctx, cudaStreamSynchronize(sx));
   BSQ_CK(ctx, cudaStreamSynchronize(ctx->st_copy2));
   BSQ_CK(ctx, cudaStreamSynchronize(ctx->st_trace));
@@ -1509,6 +1535,15 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
       if (cudaEventElapsedTime(&ms, ctx->events[fill_ev0[ci]], ctx->events[fill_ev0[ci] + 1]) == cudaSuccess) fill += ms;
     }
     ctx->tm.fill_ms = fill;
+    if (getenv("BSQ_PLAN_DEBUG")) {  // device timeline of the call, relative to its first event
+      for (size_t ci = 0; ci < NC; ci++) {
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, t0, ctx->events[fill_ev0[ci]]);
+        cudaEventElapsedTime(&b, t0, ctx->events[fill_ev0[ci] + 1]);
+        if (ev_done.size() > ci && ev_done[ci]) cudaEventElapsedTime(&c, t0, ev_done[ci]);
+        fprintf(stderr, "[bsq] chunk %zu: fill %.3f .. %.3f ms, done %.3f ms\n", ci, a, b, c);
+      }
+    }
   }
   ctx->tm.cells = P.cells;
   ctx->tm.dtype = (!P.chunks.empty() && P.chunks[0].duo) ? BSQ_DTYPE_I16X2 : P.dtype;
@@ -1532,6 +1567,7 @@ int bsq_batch_upload(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, con
   BSQ_CK(ctx, cudaSetDevice(ctx->device));
   memset(&ctx->tm, 0, sizeof ctx->tm);
   bsq_batch* b = new bsq_batch();
+  ctx->mem_avail = -1.0;  // a resident batch takes HBM of its own
   rc = batch_upload(ctx, b, true, keep_tables != 0, params, npairs, codes, ncodes, o_off, o_len, m_off, m_len, dmin, dmax);
   if (rc == BSQ_SUCCESS) {
     cudaError_t e = cudaStreamSynchronize(ctx->st);
@@ -1592,7 +1628,7 @@ int bsq_traceback_batch(bsq_batch* b, int32_t* start_x, int32_t* start_y, int32_
 
 void bsq_release(bsq_batch* b) {
   if (!b) return;
-  if (b->ctx) { cudaSetDevice(b->ctx->device); cudaStreamSynchronize(b->ctx->st); }
+  if (b->ctx) { cudaSetDevice(b->ctx->device); cudaStreamSynchronize(b->ctx->st); b->ctx->mem_avail = -1.0; }
   if (b->own_bufs) b->bufs.release();
   delete b;
 }

@@ -87,6 +87,10 @@ struct Chunk {
   int64_t k3_active = 0; // K3: strips in flight when every pair's pipeline is full
 };
 
+// three slots: the fill of chunk c+2 need not wait for the traceback of chunk c, which shares
+// the SMs with fill c+1 and often takes longer than a fill
+#define BSQ_ARENA_SLOTS 3
+
 inline bool chunk_is_k3(const Chunk& ch) { return ch.family == 2 && ch.cfg >= BSQ_K2_NCFG; }
 
 struct Override { int64_t idx; int status; };
@@ -116,7 +120,8 @@ struct Plan {
   int64_t max_chunk_words = 0;
   int64_t total_words = 0;
   bool identity = false;  // processing order == caller order (no sort was needed)
-  int64_t half_words = 0; // > 0: two arena halves, chunk c uses half (c & 1) so trace(c) overlaps fill(c+1)
+  int64_t half_words = 0; // > 0: BSQ_ARENA_SLOTS arena slots of this size, chunk c uses slot c % SLOTS so that
+                          // trace(c) overlaps the fills of the following chunks
   // uniform batches (every pair the same shape, e.g. fixed-length reads): the pair records are
   // built ON THE DEVICE from the caller's offset arrays (bsq_make_pairs_uniform); pairs == nullptr
   bool uniform_dev = false;
@@ -804,7 +809,7 @@ int stage_inputs(bsq_ctx* ctx, BufSet& B, Plan& P, const uint8_t* codes, int64_t
             B.sx.ensure(4 * (size_t)N) && B.sy.ensure(4 * (size_t)N) && B.status.ensure(4 * (size_t)N) &&
             B.txlen.ensure(4 * (size_t)N) && B.subst.ensure(8 * (size_t)L * L) &&
             B.counters.ensure(4 * (P.chunks.size() + 1)) && B.total.ensure(16) &&
-            B.ptr.ensure(4 * (size_t)(single_chunk ? P.total_words : (P.half_words > 0 ? 2 * P.half_words : P.max_chunk_words)) + 64);
+            B.ptr.ensure(4 * (size_t)(single_chunk ? P.total_words : (P.half_words > 0 ? BSQ_ARENA_SLOTS * P.half_words : P.max_chunk_words)) + 64);
   if (!ok) return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed");
   cudaStream_t st = ctx->st;
   if (ncodes > 0) BSQ_CK(ctx, cudaMemcpyAsync(B.codes.p, codes, (size_t)ncodes, cudaMemcpyHostToDevice, st));
@@ -838,7 +843,7 @@ int launch_fill(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, size_t* evi, 
   A.go_d = P.prm.go; A.ge_d = P.prm.ge;
   A.go_i = (int)P.prm.go; A.ge_i = (int)P.prm.ge;
   A.bmode = P.bmode; A.emode = P.emode; A.btype = P.prm.type;
-  A.ptr = B.ptr.as<uint32_t>() + (P.half_words > 0 ? (int64_t)(ci & 1) * P.half_words : 0);
+  A.ptr = B.ptr.as<uint32_t>() + (P.half_words > 0 ? (int64_t)(ci % BSQ_ARENA_SLOTS) * P.half_words : 0);
   A.out_score = B.score.as<double>();
   A.out_ex = B.ex.as<int>();
   A.out_ey = B.ey.as<int>();
@@ -937,7 +942,7 @@ int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, cudaStream_t
   T.G = k3 ? 32 : (ch.family == 1 ? BSQ_K1_CFGS[ch.cfg].G : BSQ_K2_CFGS[ch.cfg].G);
   T.K = k3 ? BSQ_K3_CFGS[ch.cfg - BSQ_K2_NCFG].K : (ch.family == 1 ? BSQ_K1_CFGS[ch.cfg].K : BSQ_K2_CFGS[ch.cfg].C);
   T.gosign = P.gosign;
-  T.ptr = B.ptr.as<uint32_t>() + (P.half_words > 0 ? (int64_t)(ci & 1) * P.half_words : 0);
+  T.ptr = B.ptr.as<uint32_t>() + (P.half_words > 0 ? (int64_t)(ci % BSQ_ARENA_SLOTS) * P.half_words : 0);
   T.ex = B.ex.as<int>();
   T.ey = B.ey.as<int>();
   T.status = B.status.as<int>();
@@ -1180,7 +1185,7 @@ static int batch_upload(bsq_ctx* ctx, bsq_batch* b, bool own_bufs, bool single_c
   const int64_t other = ncodes + 2 * slot_guess + npairs * (int64_t)(sizeof(BsqPair) + 48) + (64 << 20);
   const int64_t arena_words = arena_budget_words(ctx, other);
   int rc = make_plan(ctx, b->plan, b->B->hpairs, params, npairs, ncodes, o_off, o_len, m_off, m_len, dmin, dmax,
-                     single_chunk ? arena_words : arena_words / 2, single_chunk,
+                     single_chunk ? arena_words : arena_words / BSQ_ARENA_SLOTS, single_chunk,
                      single_chunk ? 0 : overlap_chunks(npairs, o_len, m_len));
   if (rc != BSQ_SUCCESS) return rc;
   b->single_chunk = single_chunk;
@@ -1209,7 +1214,7 @@ static int run_chunks(bsq_ctx* ctx, BufSet& B, const Plan& P, bool do_fill, bool
     int rc = before_fill(ci);
     if (rc != BSQ_SUCCESS) return rc;
     if (do_fill) {
-      if (overlap && ci >= 2) BSQ_CK(ctx, cudaStreamWaitEvent(sc, etrace[ci - 2], 0));  // arena half is free again
+      if (overlap && ci >= BSQ_ARENA_SLOTS) BSQ_CK(ctx, cudaStreamWaitEvent(sc, etrace[ci - BSQ_ARENA_SLOTS], 0));  // that arena slot is free again
       if (fill_ev0) (*fill_ev0)[ci] = *evi;
       rc = launch_fill(ctx, B, P, ci, evi, sc, overlap);
       if (rc != BSQ_SUCCESS) return rc;
@@ -1230,7 +1235,7 @@ static int run_chunks(bsq_ctx* ctx, BufSet& B, const Plan& P, bool do_fill, bool
     }
   }
   if (overlap) {  // the compute stream rejoins: everything after this sees all traces done
-    for (size_t ci = (NC >= 2 ? NC - 2 : 0); ci < NC; ci++) BSQ_CK(ctx, cudaStreamWaitEvent(sc, etrace[ci], 0));
+    for (size_t ci = (NC >= BSQ_ARENA_SLOTS ? NC - BSQ_ARENA_SLOTS : 0); ci < NC; ci++) BSQ_CK(ctx, cudaStreamWaitEvent(sc, etrace[ci], 0));
   }
   return BSQ_SUCCESS;
 }
@@ -1381,7 +1386,7 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
   const int64_t budget = arena_budget_words(ctx, other, true);
   const double t_p2 = now_ms();
   rc = make_plan(ctx, P, B.hpairs, params, npairs, ncodes, o_off, o_len, m_off, m_len, dmin, dmax,
-                 budget / 2, false, overlap_chunks(npairs, o_len, m_len));
+                 budget / BSQ_ARENA_SLOTS, false, overlap_chunks(npairs, o_len, m_len));
   if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(sx); return rc; }
   ctx->tm.plan_ms = now_ms() - t_plan;
   if (getenv("BSQ_PLAN_DEBUG"))
@@ -1395,7 +1400,7 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
             B.ex.ensure(4 * N) && B.ey.ensure(4 * N) && B.sx.ensure(4 * N) && B.sy.ensure(4 * N) &&
             B.status.ensure(4 * N) && B.txlen.ensure(4 * N) && B.subst.ensure(8 * (size_t)L * L + 64) &&
             B.counters.ensure(4 * (NC + 1)) && B.total.ensure(8 * (NC + 2)) &&
-            B.ptr.ensure(4 * (size_t)(P.half_words > 0 ? 2 * P.half_words : P.max_chunk_words) + 64) &&
+            B.ptr.ensure(4 * (size_t)(P.half_words > 0 ? BSQ_ARENA_SLOTS * P.half_words : P.max_chunk_words) + 64) &&
             ctx->htotals.ensure(8 * (NC + 2));
   if (ok && want_trace) ok = B.slots.ensure((size_t)std::max<int64_t>(P.slot_bytes, 1));
   if (ok && want_tx) ok = B.txoff.ensure(8 * (N + 1)) && B.tiles.ensure(8 * (size_t)ntiles_max) &&

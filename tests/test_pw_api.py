@@ -264,3 +264,26 @@ def test_init_failure_and_unsupported(backend):
         Aligner(S, T, max_new_mins=3)
     with pytest.raises(AssertionError):
         Aligner(S, T, alnmode=BANDED_MODE, alntype=OVERLAP, diag_range=(0, 0))   # type not in ALN_TYPES[mode]
+
+
+def test_very_wide_band_through_aligner(backend):
+    """A band wider than 1024 diagonals (the strip-pipelined kernel) through the drop-in API,
+    against the oracle: the shape of BASELINE.json's config 5, scaled down."""
+    rng = np.random.default_rng(17)
+    A = Alphabet('ACGT')
+    n = 1250
+    o = rng.integers(0, 4, size=(1, n), dtype=np.uint8)
+    mut, mlen = mutate_batch(rng, o, 4, 0.05, 0.02, 0.1)
+    S = Sequence(A, [int(c) for c in o[0]])
+    T = Sequence(A, [int(c) for c in mut[0, :mlen[0]]])
+    subst, go, ge = log_odds_scores(4, 0.05, 0.02, 0.1)
+    dr = (-560, 560)
+    with Aligner(S, T, alnmode=BANDED_MODE, alntype=B_GLOBAL, subst_scores=subst.tolist(),
+                 go_score=go, ge_score=ge, diag_range=dr) as al:
+        score = al.solve()
+        aln = al.traceback()
+    e = lean.align(o[0], mut[0, :mlen[0]], subst, go, ge, 1, 0, dr)
+    assert e['status'] == 0
+    assert score == e['score']
+    assert aln.transcript == e['transcript']
+    assert (aln.origin_start, aln.mutant_start) == tuple(e['start'])

@@ -42,9 +42,9 @@ def int_scores(match, mismatch, L=4):
 def make(kind, npairs, seed):
     rng = np.random.Generator(np.random.PCG64(seed))
     L = 4
-    if kind in ('c2_int', 'c2_logodds'):
-        # configs[1]: 150 bp read pairs, STD LOCAL, affine gaps
-        n = 150
+    if kind in ('c2_int', 'c2_logodds', 'c2w_int'):
+        # configs[1]: 150 bp read pairs, STD LOCAL, affine gaps (c2w_*: the same with 250 bp reads)
+        n = 250 if kind == 'c2w_int' else 150
         o = st.rand_seqs(rng, npairs, n, L)
         mut, mlen = st.mutate_batch(rng, o, L, 0.02, 0.005, 0.01)
         m = np.empty((npairs, n), dtype=np.uint8)
@@ -53,16 +53,16 @@ def make(kind, npairs, seed):
         m[:, :w] = mut[:, :w]
         if w < n:
             m[:, w:] = pad[:, w:]
-        short = np.arange(n)[None, :] >= np.minimum(mlen, n)[:, None]   # trimmed / padded to 150
+        short = np.arange(n)[None, :] >= np.minimum(mlen, n)[:, None]   # trimmed / padded to n
         m[short] = pad[short]
         codes, o_off, o_len, m_off, m_len = _pack_rows(o, np.full(npairs, n), m, np.full(npairs, n))
-        if kind == 'c2_int':   # IgBlast-like, experiments/blot_ig_genotyping.py:351-355
+        if kind in ('c2_int', 'c2w_int'):   # IgBlast-like, experiments/blot_ig_genotyping.py:351-355
             S, go, ge = int_scores(1, -3), -5.0, -2.0
         else:
             S, go, ge = st.log_odds_scores(L, 0.05, 0.05, 0.1)
         return dict(kind=kind, mode=STD_MODE, type=LOCAL, subst=S, go=go, ge=ge, codes=codes,
                     o_off=o_off, o_len=o_len, m_off=m_off, m_len=m_len,
-                    desc='%d pairs 150x150 bp, STD LOCAL, %s' % (npairs, 'int +1/-3 go-5 ge-2' if kind == 'c2_int' else 'log-odds'))
+                    desc='%d pairs %dx%d bp, STD LOCAL, %s' % (npairs, n, n, 'int +1/-3 go-5 ge-2' if kind != 'c2_logodds' else 'log-odds'))
     if kind in ('c3_int', 'c3_logodds', 'c4_int'):
         # configs[2] / [3]: long noisy reads, banded overlap alignment
         if kind == 'c4_int':

@@ -558,8 +558,9 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
       {  // K1h: short reads, small integer scores, STD LOCAL -> two problems per lane
         double maxabs = std::fabs(prm->go) + std::fabs(prm->ge);
         for (double v : P.subst) maxabs = std::max(maxabs, std::fabs(v));
-        const bool duo = family == 1 && it.cfg == 0 && dtype == BSQ_DTYPE_I32 && P.bmode == BSQ_B_ALL &&
-                         P.emode == BSQ_E_ALL && prm->go <= 0.0 && prm->ge <= 0.0 && L <= 4 && m_len[0] <= 151 &&
+        const bool duo = family == 1 && (it.cfg == 0 || it.cfg == 1) && it.aux == 0 /* single pass */ &&
+                         dtype == BSQ_DTYPE_I32 && P.bmode == BSQ_B_ALL &&
+                         P.emode == BSQ_E_ALL && prm->go <= 0.0 && prm->ge <= 0.0 && L <= 4 &&
                          (double)(scan_n + scan_m + 4) * maxabs < 4000.0 && getenv("BSQ_NO_DUO") == nullptr;
         for (Chunk& ch : P.chunks) ch.duo = duo;
       }
@@ -874,16 +875,16 @@ int launch_fill(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, size_t* evi, 
     return BSQ_SUCCESS;
   }
   if (ch.duo) {
-    int occ = bsq_k1h_op(P.gosign, BSQ_OP_OCCUPANCY, 0, 0, nullptr);
+    int occ = bsq_k1h_op(ch.cfg, P.gosign, BSQ_OP_OCCUPANCY, 0, 0, nullptr);
     if (occ < 0) return fail(ctx, BSQ_ERR_ARG, "no kernel variant for this configuration");
-    const int gpb = BSQ_FILL_THREADS / 8;
+    const int gpb = BSQ_FILL_THREADS / BSQ_K1_CFGS[ch.cfg].G;
     const int64_t duos = (ch.count + 1) / 2;
     const int occ_use = (leave_room && occ >= 4) ? occ - 1 : occ;
     int grid = (int)std::min<int64_t>((duos + gpb - 1) / gpb, (int64_t)ctx->sms * occ_use);
     if (grid < 1) grid = 1;
     cudaEvent_t e0 = get_event(ctx, (*evi)++), e1 = get_event(ctx, (*evi)++);
     BSQ_CK(ctx, cudaEventRecord(e0, stream));
-    if (bsq_k1h_op(P.gosign, BSQ_OP_LAUNCH, grid, stream, &A) < 0)
+    if (bsq_k1h_op(ch.cfg, P.gosign, BSQ_OP_LAUNCH, grid, stream, &A) < 0)
       return fail(ctx, BSQ_ERR_ARG, "no kernel variant for this configuration");
     BSQ_CK(ctx, cudaGetLastError());
     BSQ_CK(ctx, cudaEventRecord(e1, stream));

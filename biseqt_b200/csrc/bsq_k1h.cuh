@@ -2,8 +2,8 @@
 // two pairs per lane in packed 16-bit arithmetic (sm_100a DPX .16x2 forms).
 //
 // Same mapping as K1 (a group of 8 lanes owns a table of up to 152 columns,
-// lane l owns 19 consecutive columns, walks the rows, lags its left neighbour by
-// one row) but every register holds the SAME cell of TWO problems of identical
+// lane l owns 19 consecutive columns -- or 16 lanes x 16 columns for up to 256 --
+// walks the rows, lags its left neighbour by one row) but every register holds the SAME cell of TWO problems of identical
 // shape -- problem A in the low halfword, problem B in the high one -- so that
 // one VIADD.16x2 / VIMNMX3.S16x2.RELU / VIADDMNMX.U16x2 instruction advances two
 // DP cells.  The recurrence is pwlib's (see bsq_kernels.cuh): candidates B, D, I,
@@ -22,15 +22,13 @@
 // Selected by the host only when it is exact: every score an integer,
 // (n + m + 4) * max|score| < 4000 (no 16-bit wrap with a -12000 "does not exist"
 // sentinel), go <= 0, ge <= 0 and ge + go <= 0 (padding columns can then never win
-// the end-cell search), alphabet <= 4 letters, m <= 151, all pairs of the batch of
+// the end-cell search), alphabet <= 4 letters, m <= 255, all pairs of the batch of
 // one shape.  Results are identical to K1's and to pwlib's.
 //   replaces: dptable_solve's fill loop pw.c:59-110 + _std_find_optimal (:339-355)
 #pragma once
 #include "bsq_kernels.cuh"
 #include "bsq_launch.h"
 
-#define BSQ_K1H_G 8
-#define BSQ_K1H_K 19
 #define BSQ_K1H_NINF (-12000)
 
 #ifdef BSQ_SIMT_EMU
@@ -66,9 +64,10 @@ __device__ __forceinline__ unsigned bsq_vminu2(unsigned a, unsigned b) { return 
 __device__ __forceinline__ unsigned bsq_vbmax2(unsigned a, unsigned b, bool* ph, bool* pl) { return __vibmax_s16x2(a, b, ph, pl); }
 #endif
 
-template <int GOS>
+// (G, K) is one of K1's single-pass geometries: (8, 19) for m <= 151, (16, 16) for m <= 255
+template <int G, int K, int GOS>
 __global__ void __launch_bounds__(128) bsq_k1h_fill(const BsqFillArgs A) {
-  constexpr int G = BSQ_K1H_G, K = BSQ_K1H_K, WPL = (K + 7) / 8, WST = BSQ_K1_WPL(K);
+  constexpr int WPL = (K + 7) / 8, WST = BSQ_K1_WPL(K);
   static_assert(GOS <= 0, "K1h handles go <= 0");
   // (origin letter of A, of B) x (mutant letter of A, of B; letter 4 = padding column):
   // subst - ge of both problems, packed

@@ -204,7 +204,7 @@ def run_duo_short_reads(make_engine, seed, npairs=37):
         try:
             rng = np.random.default_rng(seed)
             shapes = [(150, 150), (151, 151), (40, 151), (97, 33), (1, 1), (5, 0), (0, 7), (64, 152 - 1), (150, 120),
-                      (150, 150)]
+                      (250, 250), (100, 152), (255, 255), (200, 230), (150, 150)]
             for si, (n, m) in enumerate(shapes):
                 for gomode in (-1, 0):
                     L = int(rng.choice([2, 3, 4, 4]))
@@ -212,7 +212,7 @@ def run_duo_short_reads(make_engine, seed, npairs=37):
                     S = np.where(np.eye(L, dtype=bool), float(ma), float(mi))
                     ge = -float(rng.integers(0, 3))
                     go = 0.0 if gomode == 0 else -float(rng.integers(1, 6))
-                    if si == len(shapes) - 1:   # the largest scores the 16-bit kernel accepts: 304 * 13 < 4000
+                    if si == len(shapes) - 1:   # the largest scores the 16-bit kernel accepts: 304 * 13 < 4000; wider tables use the 16-lane geometry
                         S = np.where(np.eye(L, dtype=bool), 13.0, -13.0)
                         ge, go = -7.0, (0.0 if gomode == 0 else -6.0)
                     probs = []

@@ -64,6 +64,13 @@ struct BufSet {  // everything one batch needs in HBM
   DevBuf codes, pairs, ptr, slots, packed, score, ex, ey, sx, sy, status, txlen, txoff, tiles,
       subst, counters, colh, colf, total, k3pairs, k3sync, k3res, ooff, moff;
   PinBuf hpairs, hsmall;
+  size_t bytes() const {  // HBM currently held
+    const DevBuf* all[] = {&codes, &pairs, &ptr, &slots, &packed, &score, &ex, &ey, &sx, &sy, &status,
+                           &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff};
+    size_t n = 0;
+    for (const DevBuf* b : all) n += b->cap;
+    return n;
+  }
   void release() {
     DevBuf* all[] = {&codes, &pairs, &ptr, &slots, &packed, &score, &ex, &ey, &sx, &sy, &status,
                      &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff};
@@ -153,13 +160,18 @@ struct bsq_ctx {
   // cudaMemGetInfo costs 0.1 - 50 ms (measured on the bench box): the one-shot path remembers
   // "free bytes + our cached arena" and only asks again after a resident batch came or went or
   // an allocation failed
-  double mem_avail = -1.0;
+  double mem_avail = -1.0;         // HBM that would be free if this context held nothing; < 0: unknown
+  // buffer sets of released resident / two-phase batches, kept for the next one: an Aligner used
+  // one pair at a time (the reference's own calling pattern) must not pay ~15 cudaMalloc +
+  // cudaFree + a pinned allocation per pair (measured: 49 ms per 100 x 100 pair without this)
+  std::vector<BufSet*> pool;
+  std::vector<bsq_batch*> live;    // resident batches that own a buffer set right now
 };
 
 struct bsq_batch {
   bsq_ctx* ctx = nullptr;
   Plan plan;
-  BufSet bufs;          // used when own_bufs
+  BufSet* own = nullptr; // used when own_bufs (taken from / returned to the context's pool)
   BufSet* B = nullptr;  // the buffers in use (own or the context's cached set)
   bool own_bufs = false;
   bool single_chunk = false;  // all pointer tables resident at once
@@ -754,16 +766,34 @@ cudaEvent_t get_event(bsq_ctx* ctx, size_t i) {
   return ctx->events[i];
 }
 
-int64_t arena_budget_words(bsq_ctx* ctx, int64_t other_bytes, bool may_use_cached = false) {
-  if (!(may_use_cached && ctx->mem_avail >= 0.0)) {
+// HBM held by this context outside the buffer set `mine` (which the caller is about to reuse)
+size_t held_elsewhere(const bsq_ctx* ctx, const BufSet* mine) {
+  size_t n = 0;
+  if (&ctx->bufs != mine) n += ctx->bufs.bytes();
+  for (const BufSet* p : ctx->pool) if (p != mine) n += p->bytes();
+  for (const bsq_batch* b : ctx->live) if (b->own && b->own != mine) n += b->own->bytes();
+  return n;
+}
+
+// words the pointer arena of a plan may take: 85 % of what is free for the buffer set `mine`,
+// minus the plan's other buffers.  cudaMemGetInfo costs 0.1 - 50 ms (measured on the bench box),
+// so the context remembers "free + everything we hold" and asks again only after a failed
+// allocation (callers then retry once).
+int64_t arena_budget_words(bsq_ctx* ctx, int64_t other_bytes, const BufSet* mine) {
+  if (ctx->mem_avail < 0.0) {
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { fr = (size_t)1 << 30; cudaGetLastError(); }
-    ctx->mem_avail = (double)fr + (double)ctx->bufs.ptr.cap;  // our own cached arena counts as available
+    ctx->mem_avail = (double)fr + (double)held_elsewhere(ctx, nullptr);
   }
-  double budget = ctx->mem_avail * 0.85 - (double)other_bytes;
+  double budget = (ctx->mem_avail - (double)held_elsewhere(ctx, mine)) * 0.85 - (double)other_bytes;
   if (ctx->arena_cap_bytes && budget > (double)ctx->arena_cap_bytes) budget = (double)ctx->arena_cap_bytes;
   if (budget < (double)(1 << 16)) budget = (double)(1 << 16);
   return (int64_t)(budget / 4.0);
+}
+
+void drop_pool(bsq_ctx* ctx) {
+  for (BufSet* p : ctx->pool) { p->release(); delete p; }
+  ctx->pool.clear();
 }
 
 // pair records: a plain H2D copy, or (uniform batches) generated on the device from the
@@ -811,7 +841,7 @@ int stage_inputs(bsq_ctx* ctx, BufSet& B, Plan& P, const uint8_t* codes, int64_t
             B.txlen.ensure(4 * (size_t)N) && B.subst.ensure(8 * (size_t)L * L) &&
             B.counters.ensure(4 * (P.chunks.size() + 1)) && B.total.ensure(16) &&
             B.ptr.ensure(4 * (size_t)(single_chunk ? P.total_words : (P.half_words > 0 ? BSQ_ARENA_SLOTS * P.half_words : P.max_chunk_words)) + 64);
-  if (!ok) return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed");
+  if (!ok) { ctx->mem_avail = -1.0; return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed"); }
   cudaStream_t st = ctx->st;
   if (ncodes > 0) BSQ_CK(ctx, cudaMemcpyAsync(B.codes.p, codes, (size_t)ncodes, cudaMemcpyHostToDevice, st));
   ctx->tm.h2d_bytes += ncodes;
@@ -1107,6 +1137,7 @@ void bsq_destroy(bsq_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->st);
   ctx->bufs.release();
+  drop_pool(ctx);
   ctx->htotals.release();
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->st);
@@ -1178,13 +1209,18 @@ static int batch_upload(bsq_ctx* ctx, bsq_batch* b, bool own_bufs, bool single_c
                         const int32_t* dmin, const int32_t* dmax) {
   b->ctx = ctx;
   b->own_bufs = own_bufs;
-  b->B = own_bufs ? &b->bufs : &ctx->bufs;
+  if (own_bufs && !b->own) {
+    if (!ctx->pool.empty()) { b->own = ctx->pool.back(); ctx->pool.pop_back(); }
+    else b->own = new BufSet();
+    ctx->live.push_back(b);
+  }
+  b->B = own_bufs ? b->own : &ctx->bufs;
   b->plan.N = npairs;
   if (npairs == 0) return BSQ_SUCCESS;
   int64_t slot_guess = 0;
   for (int64_t i = 0; i < npairs; i++) slot_guess += (int64_t)o_len[i] + m_len[i];
   const int64_t other = ncodes + 2 * slot_guess + npairs * (int64_t)(sizeof(BsqPair) + 48) + (64 << 20);
-  const int64_t arena_words = arena_budget_words(ctx, other);
+  const int64_t arena_words = arena_budget_words(ctx, other, b->B);
   int rc = make_plan(ctx, b->plan, b->B->hpairs, params, npairs, ncodes, o_off, o_len, m_off, m_len, dmin, dmax,
                      single_chunk ? arena_words : arena_words / BSQ_ARENA_SLOTS, single_chunk,
                      single_chunk ? 0 : overlap_chunks(npairs, o_len, m_len));
@@ -1318,11 +1354,34 @@ static double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+static int align_batch_once(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, const uint8_t* codes,
+                            int64_t ncodes, const int64_t* o_off, const int32_t* o_len, const int64_t* m_off,
+                            const int32_t* m_len, const int32_t* dmin, const int32_t* dmax, double* score,
+                            int32_t* end_x, int32_t* end_y, int32_t* start_x, int32_t* start_y, int32_t* status,
+                            int64_t* tx_off, char* tx_buf, int64_t tx_cap, int64_t* tx_total);
+
 int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, const uint8_t* codes,
                     int64_t ncodes, const int64_t* o_off, const int32_t* o_len, const int64_t* m_off,
                     const int32_t* m_len, const int32_t* dmin, const int32_t* dmax, double* score,
                     int32_t* end_x, int32_t* end_y, int32_t* start_x, int32_t* start_y, int32_t* status,
                     int64_t* tx_off, char* tx_buf, int64_t tx_cap, int64_t* tx_total) {
+  if (!ctx) return BSQ_ERR_ARG;
+  int rc = align_batch_once(ctx, params, npairs, codes, ncodes, o_off, o_len, m_off, m_len, dmin, dmax, score, end_x,
+                            end_y, start_x, start_y, status, tx_off, tx_buf, tx_cap, tx_total);
+  if (rc == BSQ_ERR_NOMEM) {  // the remembered free-memory figure may be stale: ask the driver and try once more
+    drop_pool(ctx);
+    ctx->mem_avail = -1.0;
+    rc = align_batch_once(ctx, params, npairs, codes, ncodes, o_off, o_len, m_off, m_len, dmin, dmax, score, end_x,
+                          end_y, start_x, start_y, status, tx_off, tx_buf, tx_cap, tx_total);
+  }
+  return rc;
+}
+
+static int align_batch_once(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, const uint8_t* codes,
+                            int64_t ncodes, const int64_t* o_off, const int32_t* o_len, const int64_t* m_off,
+                            const int32_t* m_len, const int32_t* dmin, const int32_t* dmax, double* score,
+                            int32_t* end_x, int32_t* end_y, int32_t* start_x, int32_t* start_y, int32_t* status,
+                            int64_t* tx_off, char* tx_buf, int64_t tx_cap, int64_t* tx_total) {
   if (!ctx) return BSQ_ERR_ARG;
   const double t_call = now_ms();
   ctx->err.clear();
@@ -1384,7 +1443,7 @@ int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, cons
   }
   const int64_t other = ncodes + 2 * slot_guess + npairs * (int64_t)(sizeof(BsqPair) + 48) + (64 << 20);
   const double t_p1 = now_ms();
-  const int64_t budget = arena_budget_words(ctx, other, true);
+  const int64_t budget = arena_budget_words(ctx, other, &B);
   const double t_p2 = now_ms();
   rc = make_plan(ctx, P, B.hpairs, params, npairs, ncodes, o_off, o_len, m_off, m_len, dmin, dmax,
                  budget / BSQ_ARENA_SLOTS, false, overlap_chunks(npairs, o_len, m_len));
@@ -1573,13 +1632,18 @@ int bsq_batch_upload(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, con
   BSQ_CK(ctx, cudaSetDevice(ctx->device));
   memset(&ctx->tm, 0, sizeof ctx->tm);
   bsq_batch* b = new bsq_batch();
-  ctx->mem_avail = -1.0;  // a resident batch takes HBM of its own
   rc = batch_upload(ctx, b, true, keep_tables != 0, params, npairs, codes, ncodes, o_off, o_len, m_off, m_len, dmin, dmax);
+  if (rc == BSQ_ERR_NOMEM) {  // stale free-memory figure or hoarded buffer sets: ask the driver and try once more
+    cudaStreamSynchronize(ctx->st);
+    drop_pool(ctx);
+    ctx->mem_avail = -1.0;
+    rc = batch_upload(ctx, b, true, keep_tables != 0, params, npairs, codes, ncodes, o_off, o_len, m_off, m_len, dmin, dmax);
+  }
   if (rc == BSQ_SUCCESS) {
     cudaError_t e = cudaStreamSynchronize(ctx->st);
     if (e != cudaSuccess) { ctx->err = std::string("upload: ") + cudaGetErrorString(e); rc = BSQ_ERR_CUDA; }
   }
-  if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(ctx->st); b->bufs.release(); delete b; return rc; }
+  if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(ctx->st); bsq_release(b); return rc; }
   *batch = b;
   return BSQ_SUCCESS;
 }
@@ -1634,8 +1698,16 @@ int bsq_traceback_batch(bsq_batch* b, int32_t* start_x, int32_t* start_y, int32_
 
 void bsq_release(bsq_batch* b) {
   if (!b) return;
-  if (b->ctx) { cudaSetDevice(b->ctx->device); cudaStreamSynchronize(b->ctx->st); b->ctx->mem_avail = -1.0; }
-  if (b->own_bufs) b->bufs.release();
+  bsq_ctx* ctx = b->ctx;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->st); cudaStreamSynchronize(ctx->st_trace); }
+  if (b->own) {
+    if (ctx) {
+      for (size_t i = 0; i < ctx->live.size(); i++) if (ctx->live[i] == b) { ctx->live.erase(ctx->live.begin() + i); break; }
+      // keep up to two modest buffer sets for the next batch; big ones go back to the device
+      if (ctx->pool.size() < 2 && b->own->bytes() <= ((size_t)1 << 30)) { ctx->pool.push_back(b->own); b->own = nullptr; }
+    }
+    if (b->own) { b->own->release(); delete b->own; }
+  }
   delete b;
 }
 

@@ -51,6 +51,13 @@ class ClockSampler(object):
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def start(self):
         try:
@@ -65,7 +72,7 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
 
     def stop(self):
         if self.proc is None:
@@ -78,7 +85,14 @@ class ClockSampler(object):
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        # the sampler is started before the warm-up (nvidia-smi takes a while to come up on an
+        # 8-GPU box); keep the samples that arrived during the timed region, or, if the region was
+        # shorter than the sampling period, the ones around it
+        rows = [r for t, r in self.rows
+                if self.t_begin is None or (self.t_begin - 0.02 <= t <= (self.t_end or t) + 0.05)]
+        if not rows:
+            rows = [r for t, r in self.rows if self.t_begin is None or t >= self.t_begin - 1.0]
+        for r in rows:
             if len(r) < 9:
                 continue
             try:
@@ -213,10 +227,11 @@ def measure(eng, w, steps, warmup, sampler_gpu, do_e2e=True):
     args = (w['mode'], w['type'], w['subst'], w['go'], w['ge'])
     # ---- device-resident: upload once, run W + K times -----------------
     rb = eng.upload(w['codes'], w['o_off'], w['o_len'], w['m_off'], w['m_len'], *args, **kw)
+    sampler = ClockSampler(sampler_gpu).start()
     for _ in range(warmup):
         rb.run()
     barrier()
-    sampler = ClockSampler(sampler_gpu).start()
+    sampler.mark_begin()
     res_ms, fill_ms, launches = [], [], 0
     t = None
     for _ in range(steps):
@@ -224,6 +239,7 @@ def measure(eng, w, steps, warmup, sampler_gpu, do_e2e=True):
         res_ms.append(t['total_ms'])
         fill_ms.append(t['fill_ms'])
         launches += t['fill_launches']
+    sampler.mark_end()
     clocks = sampler.stop()
     barrier()
     cells = t['cells']

@@ -62,18 +62,18 @@ struct PinBuf {
 
 struct BufSet {  // everything one batch needs in HBM
   DevBuf codes, pairs, ptr, slots, packed, score, ex, ey, sx, sy, status, txlen, txoff, tiles,
-      subst, counters, colh, colf, total, k3pairs, k3sync, k3res, ooff, moff;
+      subst, counters, colh, colf, total, k3pairs, k3sync, k3res, ooff, moff, duos;
   PinBuf hpairs, hsmall;
   size_t bytes() const {  // HBM currently held
     const DevBuf* all[] = {&codes, &pairs, &ptr, &slots, &packed, &score, &ex, &ey, &sx, &sy, &status,
-                           &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff};
+                           &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff, &duos};
     size_t n = 0;
     for (const DevBuf* b : all) n += b->cap;
     return n;
   }
   void release() {
     DevBuf* all[] = {&codes, &pairs, &ptr, &slots, &packed, &score, &ex, &ey, &sx, &sy, &status,
-                     &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff};
+                     &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff, &duos};
     for (DevBuf* b : all) b->release();
     hpairs.release();
     hsmall.release();
@@ -88,7 +88,9 @@ struct Chunk {
   int max_n_multipass;   // K1: longest origin among pairs needing > 1 pass (0 if none)
   int64_t idx_lo, idx_hi; // caller indices [idx_lo, idx_hi) covered (identity order only)
   int64_t code_end;      // one past the last byte of codes[] this chunk reads
-  bool duo = false;      // K1h: pairs (2q, 2q+1) share a lane group, packed 16-bit arithmetic
+  bool duo = false;      // K1h: two equal-shape pairs share a lane group, packed 16-bit arithmetic
+  int64_t duo_first = -1; // first entry of Plan::duos (-1: pairs (2q, 2q+1) of the chunk, uniform batches)
+  int64_t nduos = 0;
   int64_t k3_strips = 0; // K3: strips in the chunk's work list
   int64_t k3_slab = 0;   // K3: boundary-column slab entries (sum of n+1)
   int64_t k3_active = 0; // K3: strips in flight when every pair's pipeline is full
@@ -135,6 +137,7 @@ struct Plan {
   BsqUniform uni;
   const int64_t* src_o_off = nullptr;
   const int64_t* src_m_off = nullptr;
+  std::vector<BsqDuo> duos;    // ragged batches: which two pairs of a K1h chunk share a lane group
   std::vector<BsqK3Pair> k3;  // per pair record (processing order); empty when no pair uses K3
   int64_t k3_max_strips = 0, k3_max_slab = 0, k3_max_pairs = 0;  // maxima over chunks
 };
@@ -320,6 +323,12 @@ int k3_op(int dtype, int cfg, int btype, int gos, int grid, cudaStream_t st, con
                                 : bsq_k3_f64_op(cfg, btype, gos, grid, st, A);
 }
 
+// batches of one shape take the planner's fast path, and K1h is used, from this many pairs on
+inline int64_t uniform_min_pairs() {
+  const char* e = getenv("BSQ_UNIFORM_MIN");  // test hook
+  return e ? atoll(e) : 4096;
+}
+
 // K3 geometry for bands no K2 geometry holds (or for every band: BSQ_FORCE_K3, a test hook)
 int pick_k3_cfg() {
   const char* e = getenv("BSQ_K3_CFG");  // tuning hook
@@ -463,6 +472,21 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   P.pairs = nullptr;
   const bool force_k3 = getenv("BSQ_FORCE_K3") != nullptr;  // test hook: K3 for every band
   const int k3_cfg = pick_k3_cfg();
+  // K1h (two equal-shape short problems per lane, packed 16-bit arithmetic): what the scores and
+  // the alignment type must satisfy; the shape conditions are per pair (PlanItem.lo for STD)
+  double duo_maxabs = std::fabs(prm->go) + std::fabs(prm->ge);
+  for (double v : P.subst) duo_maxabs = std::max(duo_maxabs, std::fabs(v));
+  bool duo_scores_ok = false;
+  {
+    bsq_params t1 = *prm;
+    t1.subst = P.subst.data();
+    const bool i32 = prm->dtype != BSQ_DTYPE_F64 && scores_int32_exact(&t1, scan_n, scan_m);
+    duo_scores_ok = family == 1 && i32 && P.bmode == BSQ_B_ALL && P.emode == BSQ_E_ALL && prm->go <= 0.0 &&
+                    prm->ge <= 0.0 && L <= 4 && getenv("BSQ_NO_DUO") == nullptr;
+  }
+  auto duo_shape_ok = [&](int cfg, int64_t passes, int n, int m) -> bool {
+    return duo_scores_ok && (cfg == 0 || cfg == 1) && passes == 1 && (double)(n + m + 4) * duo_maxabs < 4000.0;
+  };
   // what dptable_init would make of one problem shape, the kernel geometry, table size, cells
   auto classify = [&](int n, int m, int dlo, int dhi) -> PlanItem {
     PlanItem it{};
@@ -473,6 +497,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
       it.words = passes * (int64_t)(n + G) * G * WPL;  // rows t = x + lane, see bsq_kernels.cuh
       it.aux = passes > 1 ? n : 0;
       it.cells = (int64_t)(n + 1) * (m + 1);
+      it.lo = duo_shape_ok(it.cfg, passes, n, m) ? 1 : 0;   // STD has no band: lo flags K1h eligibility
     } else {
       int lo = dlo, hi = dhi;
       if (hi > n) hi = n;   // _pw_internals.c:29-36
@@ -512,9 +537,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
 
   // ---- fast path: one shape for the whole batch (fixed-length reads).  No per-pair host work:
   // chunk boundaries are arithmetic and the pair records are generated on the device.
-  const char* umin_env = getenv("BSQ_UNIFORM_MIN");  // test hook
-  const int64_t uniform_min = umin_env ? atoll(umin_env) : 4096;
-  if (all_uniform && N >= uniform_min && N < ((int64_t)1 << 31)) {
+  if (all_uniform && N >= uniform_min_pairs() && N < ((int64_t)1 << 31)) {
     const PlanItem it = classify(o_len[0], m_len[0], family == 2 ? dmin[0] : 0, family == 2 ? dmax[0] : 0);
     bsq_params tmp = *prm;
     tmp.subst = P.subst.data();
@@ -572,15 +595,9 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
         for (int64_t c = 0; c < NC; c++)
           for (int t = 0; t < 16; t++) P.chunks[(size_t)c].code_end = std::max(P.chunks[(size_t)c].code_end, ends[(size_t)c * 16 + t]);
       }
-      {  // K1h: short reads, small integer scores, STD LOCAL -> two problems per lane
-        double maxabs = std::fabs(prm->go) + std::fabs(prm->ge);
-        for (double v : P.subst) maxabs = std::max(maxabs, std::fabs(v));
-        const bool duo = family == 1 && (it.cfg == 0 || it.cfg == 1) && it.aux == 0 /* single pass */ &&
-                         dtype == BSQ_DTYPE_I32 && P.bmode == BSQ_B_ALL &&
-                         P.emode == BSQ_E_ALL && prm->go <= 0.0 && prm->ge <= 0.0 && L <= 4 &&
-                         (double)(scan_n + scan_m + 4) * maxabs < 4000.0 && getenv("BSQ_NO_DUO") == nullptr;
-        for (Chunk& ch : P.chunks) ch.duo = duo;
-      }
+      // K1h: short reads, small integer scores, STD LOCAL -> two problems per lane
+      for (Chunk& ch : P.chunks) { ch.duo = (family == 1 && it.lo == 1 && dtype == BSQ_DTYPE_I32); ch.duo_first = -1; ch.nduos = (ch.count + 1) / 2; }
+      P.duos.clear();
       P.max_chunk_words = std::min(ppc, N) * it.words;
       P.total_words = tot_words;
       P.slot_bytes = N * ((int64_t)o_len[0] + m_len[0]);
@@ -659,12 +676,13 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   order.clear();
   order.reserve((size_t)N);
   bool uniform = true;
-  int64_t first_words = -1, tot_words = 0, maxw = 0;
+  int64_t first_words = -1, tot_words = 0, maxw = 0, n_duo_ok = 0;
   int first_cfg = -1;
   for (int64_t i = 0; i < N; i++) {
     const PlanItem& it = items[i];
     if (!range_ok) { P.overrides.push_back({i, BSQ_UNSUPPORTED}); continue; }
     if (it.cfg < 0) { P.overrides.push_back({i, -1 - it.cfg}); continue; }
+    if (family == 1) n_duo_ok += it.lo;
     if (first_words < 0) { first_words = it.words; first_cfg = it.cfg; }
     else if (it.words != first_words || it.cfg != first_cfg) uniform = false;
     tot_words += it.words;
@@ -687,7 +705,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   P.pairs = hpairs.as<BsqPair>();
   BsqPair* out = P.pairs;
   // what the chunk-cutting scan below reads, in processing order
-  struct Gathered { int64_t words, code_end; int32_t len, cfg, aux, band_w; };
+  struct Gathered { int64_t words, code_end; int32_t len, cfg, aux, band_w, duo, pad_; };
   std::vector<char>& gbuf = ctx->plan_gather;
   if (gbuf.size() < sizeof(Gathered) * (size_t)std::max<int64_t>(E, 1)) gbuf.resize(sizeof(Gathered) * (size_t)std::max<int64_t>(E, 1));
   Gathered* gth = (Gathered*)gbuf.data();
@@ -698,21 +716,31 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   // scan assigns) straight to their final place in pinned memory: sequential reads of the caller's
   // arrays, one random 56-byte write per pair.  (A comparison sort plus gathers through the
   // permutation cost 110 ms per 10^6 ragged pairs, more than aligning them.)
+  // Ragged batches of short reads: K1h needs two problems of the SAME shape per lane group, so
+  // its candidates are ordered by exact shape (n, m <= 255: 2 x 65536 more keys) ahead of the rest;
+  // neighbours of one shape then become duos.  Worth it from a few thousand candidates on.
+  // Off unless BSQ_RAGGED_DUO is set: measured on 10^6 ragged 100-150 bp pairs the fill drops from
+  // 15.2 to 10.1 ms but the larger key space and the duo table cost the (serial) planner 7.7 ms
+  // more -- the planner, not the GPU, bounds ragged batches (21 ms vs 18 ms); see DESIGN.md section 8.
+  const bool use_duo = family == 1 && P.dtype == BSQ_DTYPE_I32 && n_duo_ok >= uniform_min_pairs() &&
+                       getenv("BSQ_RAGGED_DUO") != nullptr;
   constexpr int NCLS = 512;
-  const int nkeys = (BSQ_K2_NCFG + BSQ_K3_NCFG + 1) * NCLS;
+  const int nkeys_std = (BSQ_K2_NCFG + BSQ_K3_NCFG + 1) * NCLS;
+  const int nkeys = nkeys_std + (use_duo ? 2 * 65536 : 0);
   const int TMAX = parallel_threads(E);   // the ranges parallel_for(E, ..) hands out below
   std::vector<int64_t> hist;
-  auto key_of = [&](const PlanItem& it) -> int {
+  auto key_of = [&](const PlanItem& it, int n, int m) -> int {
+    if (use_duo && it.lo) return it.cfg * 65536 + (255 - n) * 256 + (255 - m);   // exact shape, bigger first
     const uint64_t w = (uint64_t)std::max<int64_t>(it.words, 1);
     const int lg = 63 - __builtin_clzll(w);
     const int frac = lg >= 3 ? (int)((w >> (lg - 3)) & 7) : 0;
-    return it.cfg * NCLS + (NCLS - 1 - (lg * 8 + frac));
+    return (use_duo ? 2 * 65536 : 0) + it.cfg * NCLS + (NCLS - 1 - (lg * 8 + frac));
   };
   if (!uniform) {
     hist.assign((size_t)TMAX * nkeys, 0);
     parallel_for(E, [&](int t, int64_t e0, int64_t e1) {
       int64_t* h = hist.data() + (size_t)t * nkeys;
-      for (int64_t e = e0; e < e1; e++) h[key_of(items[order[e]])]++;
+      for (int64_t e = e0; e < e1; e++) { const int64_t i = order[e]; h[key_of(items[i], o_len[i], m_len[i])]++; }
     });
     int64_t run = 0;  // exclusive prefix over (key, thread): thread t's pairs of a key go behind thread t-1's
     for (int k = 0; k < nkeys; k++)
@@ -723,7 +751,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
     for (int64_t e = e0; e < e1; e++) {
       const int64_t i = order[e];
       const PlanItem& it = items[i];
-      const int64_t pos = uniform ? e : h[key_of(it)]++;
+      const int64_t pos = uniform ? e : h[key_of(it, o_len[i], m_len[i])]++;
       BsqPair bp;
       bp.o_off = o_off[i];
       bp.m_off = m_off[i];
@@ -743,6 +771,8 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
       gq.cfg = it.cfg;
       gq.aux = it.aux;
       gq.band_w = it.hi - it.lo + 1;
+      gq.duo = (use_duo && it.lo) ? 1 : 0;
+      gq.pad_ = 0;
       gth[pos] = gq;
     }
   });
@@ -770,13 +800,14 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   lap("scan starts");
   for (int64_t e = 0; e < E; e++) {
     const Gathered& it = gth[e];
-    const bool new_chunk = cur.count > 0 && (it.cfg != cur.cfg || (!single_chunk && cur.ptr_words + it.words > arena_words));
+    const bool new_chunk = cur.count > 0 && (it.cfg != cur.cfg || (it.duo != 0) != cur.duo ||
+                                             (!single_chunk && cur.ptr_words + it.words > arena_words));
     if (new_chunk) {
       cur.idx_hi = out[e].pad;
       close_chunk(cur);
       cur = Chunk{e, 0, family, -1, 0, 0, out[e].pad, 0, 0};
     }
-    if (cur.count == 0) cur.cfg = it.cfg;
+    if (cur.count == 0) { cur.cfg = it.cfg; cur.duo = it.duo != 0; }
     out[e].ptr_off = single_chunk ? global_words : cur.ptr_words;
     out[e].tx_slot = slot;
     slot += it.len;
@@ -803,6 +834,18 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   P.total_words = global_words;
   P.slot_bytes = slot;
   P.half_words = (!single_chunk && P.chunks.size() >= 2) ? P.max_chunk_words : 0;
+  // K1h chunks: neighbours of one shape share a lane group
+  P.duos.clear();
+  for (Chunk& ch : P.chunks) {
+    if (!ch.duo) continue;
+    ch.duo_first = (int64_t)P.duos.size();
+    for (int64_t r = 0; r < ch.count;) {
+      const BsqPair& a = out[ch.first + r];
+      if (r + 1 < ch.count && out[ch.first + r + 1].n == a.n && out[ch.first + r + 1].m == a.m) { P.duos.push_back(BsqDuo{(int)r, (int)r + 1}); r += 2; }
+      else { P.duos.push_back(BsqDuo{(int)r, (int)r}); r += 1; }
+    }
+    ch.nduos = (int64_t)P.duos.size() - ch.duo_first;
+  }
   lap("chunked");
   return BSQ_SUCCESS;
 }
@@ -851,6 +894,11 @@ void drop_pool(bsq_ctx* ctx) {
 int upload_pairs(bsq_ctx* ctx, BufSet& B, const Plan& P, cudaStream_t st) {
   const int64_t E = P.E;
   if (E <= 0) return BSQ_SUCCESS;
+  if (!P.duos.empty()) {
+    if (!B.duos.ensure(sizeof(BsqDuo) * P.duos.size())) return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (duos)");
+    BSQ_CK(ctx, cudaMemcpyAsync(B.duos.p, P.duos.data(), sizeof(BsqDuo) * P.duos.size(), cudaMemcpyHostToDevice, st));
+    ctx->tm.h2d_bytes += (int64_t)(sizeof(BsqDuo) * P.duos.size());
+  }
   if (!P.uniform_dev) {
     BSQ_CK(ctx, cudaMemcpyAsync(B.pairs.p, P.pairs, sizeof(BsqPair) * (size_t)E, cudaMemcpyHostToDevice, st));
     ctx->tm.h2d_bytes += (int64_t)sizeof(BsqPair) * E;
@@ -958,7 +1006,9 @@ int launch_fill(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, size_t* evi, 
     int occ = bsq_k1h_op(ch.cfg, P.gosign, BSQ_OP_OCCUPANCY, 0, 0, nullptr);
     if (occ < 0) return fail(ctx, BSQ_ERR_ARG, "no kernel variant for this configuration");
     const int gpb = BSQ_FILL_THREADS / BSQ_K1_CFGS[ch.cfg].G;
-    const int64_t duos = (ch.count + 1) / 2;
+    const int64_t duos = ch.nduos;
+    A.duos = ch.duo_first >= 0 ? B.duos.as<BsqDuo>() + ch.duo_first : nullptr;
+    A.nduos = (int)ch.nduos;
     const int occ_use = (leave_room && occ >= 4) ? occ - 1 : occ;
     int grid = (int)std::min<int64_t>((duos + gpb - 1) / gpb, (int64_t)ctx->sms * occ_use);
     if (grid < 1) grid = 1;

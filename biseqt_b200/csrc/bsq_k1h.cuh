@@ -92,14 +92,16 @@ __global__ void __launch_bounds__(128) bsq_k1h_fill(const BsqFillArgs A) {
   const unsigned ONE2 = 0x00010001u;
   const unsigned ge2 = bsq_h2(ge, ge);
   const unsigned go16 = (unsigned)go & 0xffffu;  // halfword two's complement: (0/1) * go16 per halfword
-  const int nduos = (A.npairs + 1) / 2;
+  const int nduos = A.nduos;
 
   for (;;) {
     int q = 0;
     if (l == 0) q = atomicAdd(A.counter, 1);
     q = __shfl_sync(gmask, q, 0, G);
     if (q >= nduos) break;
-    const int pa = 2 * q, pb = (2 * q + 1 < A.npairs) ? 2 * q + 1 : 2 * q;  // an odd tail aligns itself twice
+    int pa, pb;   // a problem without a partner of its shape aligns itself twice
+    if (A.duos) { const BsqDuo d = A.duos[q]; pa = d.a; pb = d.b; }
+    else { pa = 2 * q; pb = (2 * q + 1 < A.npairs) ? 2 * q + 1 : 2 * q; }
     const BsqPair PA = A.pairs[pa];
     const BsqPair PB = A.pairs[pb];
     const int n = PA.n, m = PA.m;                  // PB has the same shape

@@ -236,7 +236,39 @@ def run_duo_short_reads(make_engine, seed, npairs=37):
                     assert eng.timing()['dtype'] == batch.DTYPE_I32
                     assert np.array_equal(r.score, r1.score) and np.array_equal(r.tx_off, r1.tx_off)
                     assert np.array_equal(r.tx_buf[:r.tx_off[-1]], r1.tx_buf[:r1.tx_off[-1]])
+            # ragged batches (opt-in, BSQ_RAGGED_DUO): a handful of shapes, repeated an odd or even
+            # number of times, plus pairs the packed kernel cannot take (two passes); neighbours of
+            # one shape share a lane group
+            os.environ['BSQ_RAGGED_DUO'] = '1'
+            for trial in range(3):
+                L = 4
+                S = np.where(np.eye(L, dtype=bool), 2.0, -3.0)
+                go, ge = (-4.0, -1.0) if trial != 1 else (0.0, -2.0)
+                shapes = [(int(rng.integers(20, 151)), int(rng.integers(20, 151))) for _ in range(5)]
+                shapes += [(30, 200), (60, 400)]      # 16-lane geometry / needs two passes: scalar kernel
+                probs = []
+                for (n, m) in shapes:
+                    for r in range(int(rng.integers(1, 6))):
+                        o = rng.integers(0, L, size=n).astype(np.uint8)
+                        t = rng.integers(0, L, size=m).astype(np.uint8)
+                        k = min(n, m)
+                        t[:k] = o[:k]
+                        t[rng.integers(0, m, size=max(1, m // 8))] = rng.integers(0, L, size=max(1, m // 8))
+                        probs.append(dict(origin=o, mutant=t, subst=S, go=go, ge=ge, mode=0, type=1, diag_range=None))
+                perm = rng.permutation(len(probs))
+                probs = [probs[i] for i in perm]
+                r = check_batch(eng, probs)
+                assert eng.timing()['dtype'] == batch.DTYPE_I16X2
+                assert eng.timing()['chunks'] >= 2     # packed chunks and scalar ones
+                os.environ['BSQ_NO_DUO'] = '1'
+                try:
+                    r1 = engine_batch(eng, probs)
+                finally:
+                    del os.environ['BSQ_NO_DUO']
+                assert np.array_equal(r.score, r1.score) and np.array_equal(r.tx_off, r1.tx_off)
+                assert np.array_equal(r.tx_buf[:r.tx_off[-1]], r1.tx_buf[:r1.tx_off[-1]])
         finally:
+            os.environ.pop('BSQ_RAGGED_DUO', None)
             eng.close()
     finally:
         del os.environ['BSQ_UNIFORM_MIN']

@@ -623,7 +623,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   // ---- phase 1 (parallel): classify every pair like dptable_init would ----------
   std::vector<PlanItem>& items = ctx->plan_items;
   if ((int64_t)items.size() < N) items.resize((size_t)N);
-  struct Part { int64_t max_n = 0, max_m = 0, cells = 0; int bad = 0; };
+  struct Part { int64_t max_n = 0, max_m = 0, cells = 0, tot_words = 0, maxw = 0, n_duo_ok = 0, n_invalid = 0; int bad = 0; };
   std::vector<Part> parts(16);
   parallel_for(N, [&](int t, int64_t i0, int64_t i1) {
     Part pt;
@@ -635,23 +635,30 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
       pt.max_n = std::max<int64_t>(pt.max_n, n);
       pt.max_m = std::max<int64_t>(pt.max_m, m);
       const int dlo = family == 2 ? dmin[i] : 0, dhi = family == 2 ? dmax[i] : 0;
-      if (n == pn && m == pm && dlo == plo && dhi == phi) {  // same shape as the previous pair
-        items[i] = prev;
-        if (prev.cfg >= 0) pt.cells += prev.cells;
-        continue;
+      if (!(n == pn && m == pm && dlo == plo && dhi == phi)) {  // else: same shape as the previous pair
+        prev = classify(n, m, dlo, dhi);
+        pn = n; pm = m; plo = dlo; phi = dhi;
       }
-      const PlanItem it = classify(n, m, dlo, dhi);
-      items[i] = it;
-      if (it.cfg >= 0) pt.cells += it.cells;
-      prev = it; pn = n; pm = m; plo = dlo; phi = dhi;
+      items[i] = prev;
+      if (prev.cfg >= 0) {
+        pt.cells += prev.cells;
+        pt.tot_words += prev.words;
+        pt.maxw = std::max(pt.maxw, prev.words);
+        if (family == 1) pt.n_duo_ok += prev.lo;
+      } else {
+        pt.n_invalid++;
+      }
     }
     parts[t] = pt;
   });
-  int64_t max_n = 0, max_m = 0;
+  int64_t max_n = 0, max_m = 0, n_invalid = 0;
+  Part all;
   P.cells = 0;
   for (const Part& pt : parts) {
     if (pt.bad) return fail(ctx, BSQ_ERR_ARG, "negative length or sequence range outside codes[]");
     max_n = std::max(max_n, pt.max_n); max_m = std::max(max_m, pt.max_m); P.cells += pt.cells;
+    all.tot_words += pt.tot_words; all.maxw = std::max(all.maxw, pt.maxw); all.n_duo_ok += pt.n_duo_ok;
+    n_invalid += pt.n_invalid;
   }
 
   bsq_params tmp = *prm;
@@ -672,22 +679,30 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   lap("classified");
   // ---- phase 2 (serial, O(N) light): order, chunk boundaries, prefix sums -----------
   P.overrides.clear();
-  std::vector<int64_t>& order = ctx->plan_order;  // processing order -> caller index
+  std::vector<int64_t>& order = ctx->plan_order;  // valid pairs in caller order (only built if some are not)
   order.clear();
-  order.reserve((size_t)N);
   bool uniform = true;
   int64_t first_words = -1, tot_words = 0, maxw = 0, n_duo_ok = 0;
   int first_cfg = -1;
-  for (int64_t i = 0; i < N; i++) {
-    const PlanItem& it = items[i];
-    if (!range_ok) { P.overrides.push_back({i, BSQ_UNSUPPORTED}); continue; }
-    if (it.cfg < 0) { P.overrides.push_back({i, -1 - it.cfg}); continue; }
-    if (family == 1) n_duo_ok += it.lo;
-    if (first_words < 0) { first_words = it.words; first_cfg = it.cfg; }
-    else if (it.words != first_words || it.cfg != first_cfg) uniform = false;
-    tot_words += it.words;
-    maxw = std::max(maxw, it.words);
-    order.push_back(i);
+  const bool have_order = !(range_ok && n_invalid == 0);   // every pair valid: position e IS caller index e
+  if (have_order) {
+    order.reserve((size_t)N);
+    for (int64_t i = 0; i < N; i++) {
+      const PlanItem& it = items[i];
+      if (!range_ok) { P.overrides.push_back({i, BSQ_UNSUPPORTED}); continue; }
+      if (it.cfg < 0) { P.overrides.push_back({i, -1 - it.cfg}); continue; }
+      if (family == 1) n_duo_ok += it.lo;
+      if (first_words < 0) { first_words = it.words; first_cfg = it.cfg; }
+      else if (it.words != first_words || it.cfg != first_cfg) uniform = false;
+      tot_words += it.words;
+      maxw = std::max(maxw, it.words);
+      order.push_back(i);
+    }
+  } else {
+    tot_words = all.tot_words; maxw = all.maxw; n_duo_ok = all.n_duo_ok;
+    // one table size and geometry for the whole batch <=> no reordering needed (ragged batches
+    // nearly never are; the test reads two fields per pair and stops at the first difference)
+    for (int64_t i = 1; i < N && uniform; i++) uniform = items[i].words == items[0].words && items[i].cfg == items[0].cfg;
   }
   if (!range_ok) P.cells = 0;
   P.identity = uniform;
@@ -699,7 +714,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   if (maxw > arena_words) return fail(ctx, BSQ_ERR_NOMEM, "a single pair's traceback table exceeds the device arena");
   if (single_chunk && tot_words > arena_words)
     return fail(ctx, BSQ_ERR_NOMEM, "batch does not fit the device arena in two-phase mode; use bsq_align_batch");
-  const int64_t E = (int64_t)order.size();
+  const int64_t E = have_order ? (int64_t)order.size() : N;
   P.E = E;
   if (!hpairs.ensure(sizeof(BsqPair) * (size_t)std::max<int64_t>(E, 1))) return fail(ctx, BSQ_ERR_NOMEM, "pinned host allocation failed");
   P.pairs = hpairs.as<BsqPair>();
@@ -740,7 +755,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
     hist.assign((size_t)TMAX * nkeys, 0);
     parallel_for(E, [&](int t, int64_t e0, int64_t e1) {
       int64_t* h = hist.data() + (size_t)t * nkeys;
-      for (int64_t e = e0; e < e1; e++) { const int64_t i = order[e]; h[key_of(items[i], o_len[i], m_len[i])]++; }
+      for (int64_t e = e0; e < e1; e++) { const int64_t i = have_order ? order[e] : e; h[key_of(items[i], o_len[i], m_len[i])]++; }
     });
     int64_t run = 0;  // exclusive prefix over (key, thread): thread t's pairs of a key go behind thread t-1's
     for (int k = 0; k < nkeys; k++)
@@ -749,7 +764,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   parallel_for(E, [&](int t, int64_t e0, int64_t e1) {
     int64_t* h = uniform ? nullptr : hist.data() + (size_t)t * nkeys;
     for (int64_t e = e0; e < e1; e++) {
-      const int64_t i = order[e];
+      const int64_t i = have_order ? order[e] : e;
       const PlanItem& it = items[i];
       const int64_t pos = uniform ? e : h[key_of(it, o_len[i], m_len[i])]++;
       BsqPair bp;

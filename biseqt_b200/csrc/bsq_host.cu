@@ -724,6 +724,11 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   std::vector<char>& gbuf = ctx->plan_gather;
   if (gbuf.size() < sizeof(Gathered) * (size_t)std::max<int64_t>(E, 1)) gbuf.resize(sizeof(Gathered) * (size_t)std::max<int64_t>(E, 1));
   Gathered* gth = (Gathered*)gbuf.data();
+  // (words, geometry, duo flag) of every pair in processing order, 8 bytes each: all the serial
+  // chunk-cutting scan has to read
+  std::vector<int64_t>& ckbuf = ctx->plan_sorted;
+  if ((int64_t)ckbuf.size() < E + 1) ckbuf.resize((size_t)E + 1);
+  uint64_t* ckey = (uint64_t*)ckbuf.data();
 
   // Processing order: by kernel geometry, heaviest first inside a geometry (LPT).  A stable counting
   // sort on (geometry, size class) -- 8 classes per octave of table size, so pairs of one class
@@ -789,6 +794,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
       gq.duo = (use_duo && it.lo) ? 1 : 0;
       gq.pad_ = 0;
       gth[pos] = gq;
+      ckey[pos] = (uint64_t)it.words | ((uint64_t)(it.cfg & 0xff) << 48) | ((uint64_t)gq.duo << 56);
     }
   });
   lap("ordered");
@@ -813,6 +819,8 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
     if (any_k3) P.k3.assign((size_t)E, BsqK3Pair{0, 0, 0});
   }
   lap("scan starts");
+  const bool serial_scan = !P.k3.empty() || E < 65536 || getenv("BSQ_SERIAL_SCAN") != nullptr;
+  if (serial_scan) {
   for (int64_t e = 0; e < E; e++) {
     const Gathered& it = gth[e];
     const bool new_chunk = cur.count > 0 && (it.cfg != cur.cfg || (it.duo != 0) != cur.duo ||
@@ -842,6 +850,67 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
     global_words += it.words;
     cur.count++;
     P.max_chunk_words = std::max(P.max_chunk_words, cur.ptr_words);
+  }
+  } else {
+    // (1) serial, over the 8-byte keys only: where the chunks begin
+    std::vector<int64_t> chunk_gw;   // pointer-table words of all pairs before the chunk
+    for (int64_t e = 0; e < E; e++) {
+      const uint64_t ck = ckey[e];
+      const int64_t words = (int64_t)(ck & 0xffffffffffffull);
+      const int cfg = (int)((ck >> 48) & 0xff);
+      const bool duo = (ck >> 56) != 0;
+      const bool new_chunk = cur.count > 0 && (cfg != cur.cfg || duo != cur.duo ||
+                                               (!single_chunk && cur.ptr_words + words > arena_words));
+      if (new_chunk) {
+        cur.idx_hi = out[e].pad;
+        close_chunk(cur);
+        cur = Chunk{e, 0, family, -1, 0, 0, out[e].pad, 0, 0};
+      }
+      if (cur.count == 0) { cur.cfg = cfg; cur.duo = duo; chunk_gw.push_back(global_words); }
+      cur.ptr_words += words;
+      global_words += words;
+      cur.count++;
+      P.max_chunk_words = std::max(P.max_chunk_words, cur.ptr_words);
+    }
+    std::vector<Chunk> done = P.chunks;   // closed so far; the open one is appended for the passes below
+    done.push_back(cur);
+    const int64_t NCH = (int64_t)done.size();
+    // (2) parallel: per-range sums, then every pair's offsets and the per-chunk maxima
+    const int TT = parallel_threads(E);
+    std::vector<int64_t> sumW((size_t)TT + 1, 0), sumL((size_t)TT + 1, 0);
+    parallel_for(E, [&](int t, int64_t e0, int64_t e1) {
+      int64_t w = 0, l = 0;
+      for (int64_t e = e0; e < e1; e++) { w += (int64_t)(ckey[e] & 0xffffffffffffull); l += gth[e].len; }
+      sumW[(size_t)t + 1] = w;
+      sumL[(size_t)t + 1] = l;
+    });
+    for (int t = 0; t < TT; t++) { sumW[(size_t)t + 1] += sumW[(size_t)t]; sumL[(size_t)t + 1] += sumL[(size_t)t]; }
+    std::vector<int64_t> mx_code((size_t)TT * NCH, 0);
+    std::vector<int> mx_aux((size_t)TT * NCH, 0);
+    parallel_for(E, [&](int t, int64_t e0, int64_t e1) {
+      int64_t gw = sumW[(size_t)t], gl = sumL[(size_t)t];
+      int64_t c = (int64_t)(std::upper_bound(done.begin(), done.end(), e0, [](int64_t e, const Chunk& ch) { return e < ch.first; }) - done.begin()) - 1;
+      int64_t* mc = mx_code.data() + (size_t)t * NCH;
+      int* ma = mx_aux.data() + (size_t)t * NCH;
+      for (int64_t e = e0; e < e1; e++) {
+        while (c + 1 < NCH && e >= done[(size_t)c + 1].first) c++;
+        const Gathered& it = gth[e];
+        out[e].ptr_off = single_chunk ? gw : gw - chunk_gw[(size_t)c];
+        out[e].tx_slot = gl;
+        gw += it.words;
+        gl += it.len;
+        mc[c] = std::max(mc[c], it.code_end);
+        if (family == 1) ma[c] = std::max(ma[c], it.aux);
+      }
+    });
+    slot = sumL[(size_t)TT];
+    for (int64_t c = 0; c < NCH; c++) {
+      Chunk& ch = (c + 1 < NCH) ? P.chunks[(size_t)c] : cur;
+      for (int t = 0; t < TT; t++) {
+        ch.code_end = std::max(ch.code_end, mx_code[(size_t)t * NCH + c]);
+        ch.max_n_multipass = std::max(ch.max_n_multipass, mx_aux[(size_t)t * NCH + c]);
+      }
+    }
   }
   cur.idx_hi = N;
   if (cur.count > 0) close_chunk(cur);

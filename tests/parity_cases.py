@@ -332,6 +332,45 @@ def run_stats(eng, seed, npairs=14, hi=70):
         rb.release()
 
 
+def run_big_ragged_plan(make_engine, seed, npairs=70000, all_modes=True):
+    """The planner's parallel passes (counting sort, chunk scan) need > 65536 pairs to run on several
+    threads: tiny ragged problems, several chunks, against the batch oracle and against the
+    serial scan."""
+    os.environ['BSQ_ARENA_CAP_BYTES'] = str(3 << 20)
+    try:
+        eng = make_engine()
+    finally:
+        del os.environ['BSQ_ARENA_CAP_BYTES']
+    try:
+        rng = np.random.default_rng(seed)
+        o_len = rng.integers(0, 7, size=npairs).astype(np.int32)
+        m_len = rng.integers(0, 7, size=npairs).astype(np.int32)
+        tot = (o_len.astype(np.int64) + m_len).cumsum()
+        o_off = np.concatenate([[0], tot[:-1]]).astype(np.int64)
+        m_off = o_off + o_len
+        codes = rng.integers(0, 4, size=int(tot[-1]) + 16, dtype=np.uint8)
+        S = np.where(np.eye(4, dtype=bool), 2.0, -1.0)
+        cases = ((0, 0, {}), (0, 1, {}), (1, 2, dict(dmin=np.full(npairs, -2, np.int32), dmax=np.full(npairs, 3, np.int32))))
+        for mode, typ, kw in (cases if all_modes else cases[1:2]):
+            r = eng.align(codes, o_off, o_len, m_off, m_len, mode, typ, S, -2.0, -1.0, **kw)
+            assert eng.timing()['chunks'] > 2
+            e = lean.align_batch(mode, typ, S, -2.0, -1.0, codes, o_off, o_len, m_off, m_len, kw.get('dmin'), kw.get('dmax'))
+            assert np.array_equal(r.status, e['status'])
+            ok = (e['status'] == 0) | (e['status'] == 4)
+            assert np.array_equal(r.score[ok], e['score'][ok])
+            assert np.array_equal(r.start_x[ok], e['start_x'][ok]) and np.array_equal(r.start_y[ok], e['start_y'][ok])
+            assert np.array_equal(r.tx_len, e['tx_len'])
+            os.environ['BSQ_SERIAL_SCAN'] = '1'
+            try:
+                r1 = eng.align(codes, o_off, o_len, m_off, m_len, mode, typ, S, -2.0, -1.0, **kw)
+            finally:
+                del os.environ['BSQ_SERIAL_SCAN']
+            assert np.array_equal(r.tx_off, r1.tx_off) and np.array_equal(r.tx_buf[:r.tx_off[-1]], r1.tx_buf[:r1.tx_off[-1]])
+            assert np.array_equal(r.status, r1.status) and np.array_equal(r.score, r1.score)
+    finally:
+        eng.close()
+
+
 def run_dtype_equivalence(eng, seed, npairs=12, lo=5, hi=60):
     """Integer scores: the I32 fast path and the F64 path give identical results."""
     rng = np.random.default_rng(seed)

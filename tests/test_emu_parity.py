@@ -93,3 +93,7 @@ def test_emu_duo_short_reads(emu_lib):
 
 def test_emu_stats(emu_engine):
     pc.run_stats(emu_engine, seed=97)
+
+
+def test_emu_big_ragged_plan(emu_lib):
+    pc.run_big_ragged_plan(lambda: batch.Engine(0, lib=emu_lib), seed=99, npairs=66000, all_modes=False)

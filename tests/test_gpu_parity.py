@@ -96,6 +96,10 @@ def test_gpu_stats(gpu_engine):
     pc.run_stats(gpu_engine, seed=97, npairs=200, hi=300)
 
 
+def test_gpu_big_ragged_plan():
+    pc.run_big_ragged_plan(lambda: batch.Engine(0), seed=99, npairs=300000)
+
+
 def test_gpu_uniform_batches():
     pc.run_uniform_batches(lambda: batch.Engine(0), seed=83)
 

@@ -740,8 +740,8 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   // its candidates are ordered by exact shape (n, m <= 255: 2 x 65536 more keys) ahead of the rest;
   // neighbours of one shape then become duos.  Worth it from a few thousand candidates on.
   // Off unless BSQ_RAGGED_DUO is set: measured on 10^6 ragged 100-150 bp pairs the fill drops from
-  // 15.2 to 10.1 ms but the larger key space and the duo table cost the (serial) planner 7.7 ms
-  // more -- the planner, not the GPU, bounds ragged batches (21 ms vs 18 ms); see DESIGN.md section 8.
+  // 15.2 to 10.1 ms but the larger key space and the (serially built) duo table cost the planner
+  // 13 ms more; see DESIGN.md section 8.
   const bool use_duo = family == 1 && P.dtype == BSQ_DTYPE_I32 && n_duo_ok >= uniform_min_pairs() &&
                        getenv("BSQ_RAGGED_DUO") != nullptr;
   constexpr int NCLS = 512;

@@ -57,7 +57,6 @@ struct BsqUniform {
 
 // K1h: the two problems (indices into the chunk's pair records, equal shapes; b == a for a
 // problem without a partner) that share a lane group
-struct BsqDuo { int a, b; };
 
 // K3 (strip-pipelined wide bands): what a pair needs beyond BsqPair
 struct BsqK3Pair {
@@ -95,8 +94,7 @@ struct BsqFillArgs {
   double* col_h;         // (also used for int scores, stored as double-sized slots)
   uint8_t* col_f;
   long long col_stride;  // entries per group
-  // K1h: nduos entries, or NULL: problems (2q, 2q+1) of the chunk (batches of one shape)
-  const BsqDuo* duos;
+  // K1h: lane groups to serve; group q takes problems (2q, 2q+1) of the chunk
   int nduos;
   // K3: strips of all pairs of the chunk form one ordered work list; col_h holds one
   // boundary-column slab per pair (BsqK3Pair.slab_off rows of 1 (I32) / 2 (F64) 64-bit

@@ -62,18 +62,18 @@ struct PinBuf {
 
 struct BufSet {  // everything one batch needs in HBM
   DevBuf codes, pairs, ptr, slots, packed, score, ex, ey, sx, sy, status, txlen, txoff, tiles,
-      subst, counters, colh, colf, total, k3pairs, k3sync, k3res, ooff, moff, duos;
+      subst, counters, colh, colf, total, k3pairs, k3sync, k3res, ooff, moff;
   PinBuf hpairs, hsmall;
   size_t bytes() const {  // HBM currently held
     const DevBuf* all[] = {&codes, &pairs, &ptr, &slots, &packed, &score, &ex, &ey, &sx, &sy, &status,
-                           &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff, &duos};
+                           &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff};
     size_t n = 0;
     for (const DevBuf* b : all) n += b->cap;
     return n;
   }
   void release() {
     DevBuf* all[] = {&codes, &pairs, &ptr, &slots, &packed, &score, &ex, &ey, &sx, &sy, &status,
-                     &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff, &duos};
+                     &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff};
     for (DevBuf* b : all) b->release();
     hpairs.release();
     hsmall.release();
@@ -88,9 +88,7 @@ struct Chunk {
   int max_n_multipass;   // K1: longest origin among pairs needing > 1 pass (0 if none)
   int64_t idx_lo, idx_hi; // caller indices [idx_lo, idx_hi) covered (identity order only)
   int64_t code_end;      // one past the last byte of codes[] this chunk reads
-  bool duo = false;      // K1h: two equal-shape pairs share a lane group, packed 16-bit arithmetic
-  int64_t duo_first = -1; // first entry of Plan::duos (-1: pairs (2q, 2q+1) of the chunk, uniform batches)
-  int64_t nduos = 0;
+  bool duo = false;      // K1h: pairs (2q, 2q+1) of the chunk share a lane group, packed 16-bit arithmetic
   int64_t k3_strips = 0; // K3: strips in the chunk's work list
   int64_t k3_slab = 0;   // K3: boundary-column slab entries (sum of n+1)
   int64_t k3_active = 0; // K3: strips in flight when every pair's pipeline is full
@@ -137,7 +135,6 @@ struct Plan {
   BsqUniform uni;
   const int64_t* src_o_off = nullptr;
   const int64_t* src_m_off = nullptr;
-  std::vector<BsqDuo> duos;    // ragged batches: which two pairs of a K1h chunk share a lane group
   std::vector<BsqK3Pair> k3;  // per pair record (processing order); empty when no pair uses K3
   int64_t k3_max_strips = 0, k3_max_slab = 0, k3_max_pairs = 0;  // maxima over chunks
 };
@@ -396,8 +393,15 @@ class WorkerPool {
   bool stop_ = false;
 };
 
+// pairs per planner thread before another one is worth waking (BSQ_PAR_GRAIN: test hook, so that
+// small batches exercise the multi-threaded passes)
+inline int64_t parallel_grain() {
+  const char* e = getenv("BSQ_PAR_GRAIN");
+  const int64_t g = e ? atoll(e) : 0;
+  return g > 0 ? g : 32768;
+}
 inline int parallel_threads(int64_t n) {
-  return (int)std::min<int64_t>(WorkerPool::get().size(), std::max<int64_t>(n / 32768, 1));
+  return (int)std::min<int64_t>(WorkerPool::get().size(), std::max<int64_t>(n / parallel_grain(), 1));
 }
 
 template <class F>
@@ -596,8 +600,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
           for (int t = 0; t < 16; t++) P.chunks[(size_t)c].code_end = std::max(P.chunks[(size_t)c].code_end, ends[(size_t)c * 16 + t]);
       }
       // K1h: short reads, small integer scores, STD LOCAL -> two problems per lane
-      for (Chunk& ch : P.chunks) { ch.duo = (family == 1 && it.lo == 1 && dtype == BSQ_DTYPE_I32); ch.duo_first = -1; ch.nduos = (ch.count + 1) / 2; }
-      P.duos.clear();
+      for (Chunk& ch : P.chunks) ch.duo = (family == 1 && it.lo == 1 && dtype == BSQ_DTYPE_I32);
       P.max_chunk_words = std::min(ppc, N) * it.words;
       P.total_words = tot_words;
       P.slot_bytes = N * ((int64_t)o_len[0] + m_len[0]);
@@ -620,10 +623,138 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
       fprintf(stderr, "[bsq] make_plan %s at %.3f ms\n", what,
               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count());
   };
+
+  // ---- fast path: ragged short reads (STD frame, one single-pass geometry for every pair, tables
+  // within 2x of each other).  Pairs keep the caller's order -- the fill kernels pull them from a
+  // queue, K1h pairs neighbours of any shape -- so there is no sort and results leave chunk by
+  // chunk.  Two light passes over blocks of 4096 pairs: (A) per-block sums and checks, read-only;
+  // a serial walk over the blocks cuts the chunks; (B) the pair records with their final offsets,
+  // written once, sequentially.  (The general path below costs 3x the memory traffic.)
+  const int64_t RB = getenv("BSQ_PLAN_BLOCK") ? std::max<int64_t>(1, atoll(getenv("BSQ_PLAN_BLOCK"))) : 4096;   // env: test hook
+  if (family == 1 && !all_uniform && N >= 4 * RB && N < ((int64_t)1 << 31) &&
+      getenv("BSQ_ALWAYS_SORT") == nullptr) {
+    bsq_params tmp = *prm;
+    tmp.subst = P.subst.data();
+    const bool i32ok = scores_int32_exact(&tmp, scan_n, scan_m);
+    if (prm->dtype == BSQ_DTYPE_I32 && !i32ok)
+      return fail(ctx, BSQ_ERR_ARG, "dtype I32 forced but scores are not int32-exact for these lengths");
+    const int dtype = (prm->dtype == BSQ_DTYPE_F64) ? BSQ_DTYPE_F64 : (i32ok ? BSQ_DTYPE_I32 : BSQ_DTYPE_F64);
+    bool range_ok = true;
+    if (dtype == BSQ_DTYPE_F64) {
+      double maxabs = std::fabs(prm->go) + std::fabs(prm->ge);
+      for (double v : P.subst) maxabs = std::max(maxabs, std::fabs(v));
+      range_ok = (double)(scan_n + scan_m + 4) * maxabs < 2147483647.0;
+    }
+    const int cfg = pick_k1_cfg((int)scan_n, (int)scan_m);   // geometry of the largest table
+    const int G = BSQ_K1_CFGS[cfg].G, K = BSQ_K1_CFGS[cfg].K, BW = G * K, WPL = BSQ_K1_WPL(K);
+    const int64_t NBLK = (N + RB - 1) / RB;
+    struct Blk { int64_t words, len, cells, code_end; int32_t min_n, flags; };   // flags: 1 other geometry / passes, 2 K1h-eligible seen, 4 not eligible seen
+    std::vector<Blk> blk((size_t)NBLK);
+    const int TT = parallel_threads(N);
+    auto over_blocks = [&](auto f) {
+      if (TT <= 1) { f((int64_t)0, NBLK); return; }
+      WorkerPool::get().run(TT, [&](int t) { f(NBLK * t / TT, NBLK * (t + 1) / TT); });
+    };
+    over_blocks([&](int64_t b0, int64_t b1) {
+      for (int64_t b = b0; b < b1; b++) {
+        Blk k{0, 0, 0, 0, INT32_MAX, 0};
+        const int64_t i1 = std::min(N, (b + 1) * RB);
+        for (int64_t i = b * RB; i < i1; i++) {
+          const int n = o_len[i], m = m_len[i];
+          if (m + BW >= 2 * BW || pick_k1_cfg(n, m) != cfg) k.flags |= 1;
+          k.flags |= duo_shape_ok(cfg, 1, n, m) ? 2 : 4;
+          k.words += (int64_t)(n + G) * G * WPL;
+          k.len += (int64_t)n + m;
+          k.cells += (int64_t)(n + 1) * (m + 1);
+          k.code_end = std::max(k.code_end, std::max(o_off[i] + n, m_off[i] + m));
+          k.min_n = std::min(k.min_n, n);
+        }
+        blk[(size_t)b] = k;
+      }
+    });
+    int flags = 0, min_n = INT32_MAX;
+    int64_t tot_words = 0, cells = 0, max_blk = 0;
+    for (const Blk& k : blk) { flags |= k.flags; min_n = std::min(min_n, k.min_n); tot_words += k.words; cells += k.cells; max_blk = std::max(max_blk, k.words); }
+    const int64_t maxw = (int64_t)(scan_n + G) * G * WPL, minw = (int64_t)(min_n + G) * G * WPL;
+    int64_t cap = arena_words;
+    if (target_chunks > 1 && !single_chunk)
+      cap = std::min(cap, std::max<int64_t>(std::max<int64_t>((tot_words + target_chunks - 1) / target_chunks, (int64_t)8 << 20), maxw));
+    const bool duo_all = (flags & 6) == 2, duo_none = (flags & 2) == 0 || dtype != BSQ_DTYPE_I32;
+    if (!(flags & 1) && range_ok && maxw <= 2 * minw && (duo_all || duo_none) && (single_chunk ? tot_words <= arena_words : max_blk <= cap)) {
+      P.dtype = dtype;
+      P.overrides.clear();
+      P.k3.clear();
+      P.k3_max_strips = P.k3_max_slab = P.k3_max_pairs = 0;
+      P.identity = true;
+      P.E = N;
+      P.cells = cells;
+      if (!hpairs.ensure(sizeof(BsqPair) * (size_t)N)) return fail(ctx, BSQ_ERR_NOMEM, "pinned host allocation failed");
+      P.pairs = hpairs.as<BsqPair>();
+      BsqPair* out = P.pairs;
+      // chunks: whole blocks, as many as fit `cap` words; remember where each block's tables and
+      // transcript slots start
+      std::vector<int64_t> blk_ptr((size_t)NBLK), blk_slot((size_t)NBLK);
+      P.chunks.clear();
+      P.max_chunk_words = 0;
+      Chunk cur{0, 0, family, cfg, 0, 0, 0, 0, 0};
+      int64_t gw = 0, gl = 0;
+      for (int64_t b = 0; b < NBLK; b++) {
+        const Blk& k = blk[(size_t)b];
+        if (!single_chunk && cur.count > 0 && cur.ptr_words + k.words > cap) {
+          cur.idx_hi = b * RB;
+          P.chunks.push_back(cur);
+          cur = Chunk{b * RB, 0, family, cfg, 0, 0, b * RB, 0, 0};
+        }
+        blk_ptr[(size_t)b] = single_chunk ? gw : cur.ptr_words;
+        blk_slot[(size_t)b] = gl;
+        cur.ptr_words += k.words;
+        cur.count += std::min(N, (b + 1) * RB) - b * RB;
+        cur.code_end = std::max(cur.code_end, k.code_end);
+        gw += k.words;
+        gl += k.len;
+        P.max_chunk_words = std::max(P.max_chunk_words, cur.ptr_words);
+      }
+      cur.idx_hi = N;
+      P.chunks.push_back(cur);
+      const bool duo = duo_all && dtype == BSQ_DTYPE_I32 && N >= uniform_min_pairs();
+      for (Chunk& ch : P.chunks) ch.duo = duo;
+      over_blocks([&](int64_t b0, int64_t b1) {
+        for (int64_t b = b0; b < b1; b++) {
+          int64_t pw = blk_ptr[(size_t)b], sl = blk_slot[(size_t)b];
+          const int64_t i1 = std::min(N, (b + 1) * RB);
+          for (int64_t i = b * RB; i < i1; i++) {
+            const int n = o_len[i], m = m_len[i];
+            BsqPair bp;
+            bp.o_off = o_off[i];
+            bp.m_off = m_off[i];
+            bp.ptr_off = pw;
+            bp.tx_slot = sl;
+            bp.n = n;
+            bp.m = m;
+            bp.dmin = bp.dmax = bp.s0 = 0;
+            bp.pad = (int)i;
+            out[i] = bp;
+            pw += (int64_t)(n + G) * G * WPL;
+            sl += (int64_t)n + m;
+          }
+        }
+      });
+      P.total_words = tot_words;
+      P.slot_bytes = gl;
+      P.half_words = (!single_chunk && P.chunks.size() >= 2) ? P.max_chunk_words : 0;
+      lap("in-order plan");
+      return BSQ_SUCCESS;
+    }
+  }
   // ---- phase 1 (parallel): classify every pair like dptable_init would ----------
   std::vector<PlanItem>& items = ctx->plan_items;
   if ((int64_t)items.size() < N) items.resize((size_t)N);
-  struct Part { int64_t max_n = 0, max_m = 0, cells = 0, tot_words = 0, maxw = 0, n_duo_ok = 0, n_invalid = 0; int bad = 0; };
+  struct Part {
+    int64_t max_n = 0, max_m = 0, cells = 0, tot_words = 0, maxw = 0, n_duo_ok = 0, n_invalid = 0;
+    int64_t minw = INT64_MAX;
+    int bad = 0;
+    int cfg0 = -1, mixed = 0;   // one kernel geometry (and K1h eligibility) for all valid pairs?
+  };
   std::vector<Part> parts(16);
   parallel_for(N, [&](int t, int64_t i0, int64_t i1) {
     Part pt;
@@ -644,7 +775,11 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
         pt.cells += prev.cells;
         pt.tot_words += prev.words;
         pt.maxw = std::max(pt.maxw, prev.words);
-        if (family == 1) pt.n_duo_ok += prev.lo;
+        pt.minw = std::min(pt.minw, prev.words);
+        const int tag = prev.cfg * 2 + ((family == 1 && prev.lo) ? 1 : 0);
+        if (pt.cfg0 < 0) pt.cfg0 = tag;
+        else if (pt.cfg0 != tag) pt.mixed = 1;
+        if (family == 1 && prev.lo) pt.n_duo_ok++;
       } else {
         pt.n_invalid++;
       }
@@ -658,6 +793,9 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
     if (pt.bad) return fail(ctx, BSQ_ERR_ARG, "negative length or sequence range outside codes[]");
     max_n = std::max(max_n, pt.max_n); max_m = std::max(max_m, pt.max_m); P.cells += pt.cells;
     all.tot_words += pt.tot_words; all.maxw = std::max(all.maxw, pt.maxw); all.n_duo_ok += pt.n_duo_ok;
+    all.minw = std::min(all.minw, pt.minw);
+    if (pt.cfg0 >= 0) { if (all.cfg0 < 0) all.cfg0 = pt.cfg0; else if (all.cfg0 != pt.cfg0) all.mixed = 1; }
+    all.mixed |= pt.mixed;
     n_invalid += pt.n_invalid;
   }
 
@@ -700,9 +838,12 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
     }
   } else {
     tot_words = all.tot_words; maxw = all.maxw; n_duo_ok = all.n_duo_ok;
-    // one table size and geometry for the whole batch <=> no reordering needed (ragged batches
-    // nearly never are; the test reads two fields per pair and stops at the first difference)
-    for (int64_t i = 1; i < N && uniform; i++) uniform = items[i].words == items[0].words && items[i].cfg == items[0].cfg;
+    // Caller order is kept (no sort, results leave chunk by chunk) when every pair runs on the
+    // same kernel geometry and the tables differ by less than 2x: the fill kernels pull pairs from
+    // a queue, so the order only matters for the tail, and K1h pairs neighbours of any shape.
+    // Typical case: ragged short reads.  Wide-band (K3) pairs are always ordered.
+    uniform = !all.mixed && all.cfg0 >= 0 && all.maxw <= 2 * all.minw &&
+              !(family == 2 && all.cfg0 / 2 >= BSQ_K2_NCFG) && getenv("BSQ_ALWAYS_SORT") == nullptr;
   }
   if (!range_ok) P.cells = 0;
   P.identity = uniform;
@@ -736,31 +877,29 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   // scan assigns) straight to their final place in pinned memory: sequential reads of the caller's
   // arrays, one random 56-byte write per pair.  (A comparison sort plus gathers through the
   // permutation cost 110 ms per 10^6 ragged pairs, more than aligning them.)
-  // Ragged batches of short reads: K1h needs two problems of the SAME shape per lane group, so
-  // its candidates are ordered by exact shape (n, m <= 255: 2 x 65536 more keys) ahead of the rest;
-  // neighbours of one shape then become duos.  Worth it from a few thousand candidates on.
-  // Off unless BSQ_RAGGED_DUO is set: measured on 10^6 ragged 100-150 bp pairs the fill drops from
-  // 15.2 to 10.1 ms but the larger key space and the (serially built) duo table cost the planner
-  // 13 ms more; see DESIGN.md section 8.
+  // Short reads that qualify for K1h (PlanItem.lo) are keyed ahead of the rest, so they form their
+  // own chunks, in which pairs (2q, 2q+1) share a lane group: neighbours of one size class, i.e.
+  // the longer problem of a duo has < 12.5 % more rows than the shorter.  Worth it from a few
+  // thousand candidates on.
   const bool use_duo = family == 1 && P.dtype == BSQ_DTYPE_I32 && n_duo_ok >= uniform_min_pairs() &&
-                       getenv("BSQ_RAGGED_DUO") != nullptr;
+                       getenv("BSQ_NO_DUO") == nullptr;
   constexpr int NCLS = 512;
   const int nkeys_std = (BSQ_K2_NCFG + BSQ_K3_NCFG + 1) * NCLS;
-  const int nkeys = nkeys_std + (use_duo ? 2 * 65536 : 0);
+  const int nkeys_duo = use_duo ? 2 * NCLS : 0;   // K1h runs on K1 geometries 0 and 1
+  const int nkeys = nkeys_std + nkeys_duo;
   const int TMAX = parallel_threads(E);   // the ranges parallel_for(E, ..) hands out below
   std::vector<int64_t> hist;
-  auto key_of = [&](const PlanItem& it, int n, int m) -> int {
-    if (use_duo && it.lo) return it.cfg * 65536 + (255 - n) * 256 + (255 - m);   // exact shape, bigger first
+  auto key_of = [&](const PlanItem& it) -> int {
     const uint64_t w = (uint64_t)std::max<int64_t>(it.words, 1);
     const int lg = 63 - __builtin_clzll(w);
     const int frac = lg >= 3 ? (int)((w >> (lg - 3)) & 7) : 0;
-    return (use_duo ? 2 * 65536 : 0) + it.cfg * NCLS + (NCLS - 1 - (lg * 8 + frac));
+    return ((use_duo && it.lo) ? 0 : nkeys_duo) + it.cfg * NCLS + (NCLS - 1 - (lg * 8 + frac));
   };
   if (!uniform) {
     hist.assign((size_t)TMAX * nkeys, 0);
     parallel_for(E, [&](int t, int64_t e0, int64_t e1) {
       int64_t* h = hist.data() + (size_t)t * nkeys;
-      for (int64_t e = e0; e < e1; e++) { const int64_t i = have_order ? order[e] : e; h[key_of(items[i], o_len[i], m_len[i])]++; }
+      for (int64_t e = e0; e < e1; e++) { const int64_t i = have_order ? order[e] : e; h[key_of(items[i])]++; }
     });
     int64_t run = 0;  // exclusive prefix over (key, thread): thread t's pairs of a key go behind thread t-1's
     for (int k = 0; k < nkeys; k++)
@@ -771,7 +910,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
     for (int64_t e = e0; e < e1; e++) {
       const int64_t i = have_order ? order[e] : e;
       const PlanItem& it = items[i];
-      const int64_t pos = uniform ? e : h[key_of(it, o_len[i], m_len[i])]++;
+      const int64_t pos = uniform ? e : h[key_of(it)]++;
       BsqPair bp;
       bp.o_off = o_off[i];
       bp.m_off = m_off[i];
@@ -819,7 +958,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
     if (any_k3) P.k3.assign((size_t)E, BsqK3Pair{0, 0, 0});
   }
   lap("scan starts");
-  const bool serial_scan = !P.k3.empty() || E < 65536 || getenv("BSQ_SERIAL_SCAN") != nullptr;
+  const bool serial_scan = !P.k3.empty() || E < 2 * parallel_grain() || getenv("BSQ_SERIAL_SCAN") != nullptr;
   if (serial_scan) {
   for (int64_t e = 0; e < E; e++) {
     const Gathered& it = gth[e];
@@ -918,18 +1057,6 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   P.total_words = global_words;
   P.slot_bytes = slot;
   P.half_words = (!single_chunk && P.chunks.size() >= 2) ? P.max_chunk_words : 0;
-  // K1h chunks: neighbours of one shape share a lane group
-  P.duos.clear();
-  for (Chunk& ch : P.chunks) {
-    if (!ch.duo) continue;
-    ch.duo_first = (int64_t)P.duos.size();
-    for (int64_t r = 0; r < ch.count;) {
-      const BsqPair& a = out[ch.first + r];
-      if (r + 1 < ch.count && out[ch.first + r + 1].n == a.n && out[ch.first + r + 1].m == a.m) { P.duos.push_back(BsqDuo{(int)r, (int)r + 1}); r += 2; }
-      else { P.duos.push_back(BsqDuo{(int)r, (int)r}); r += 1; }
-    }
-    ch.nduos = (int64_t)P.duos.size() - ch.duo_first;
-  }
   lap("chunked");
   return BSQ_SUCCESS;
 }
@@ -978,11 +1105,6 @@ void drop_pool(bsq_ctx* ctx) {
 int upload_pairs(bsq_ctx* ctx, BufSet& B, const Plan& P, cudaStream_t st) {
   const int64_t E = P.E;
   if (E <= 0) return BSQ_SUCCESS;
-  if (!P.duos.empty()) {
-    if (!B.duos.ensure(sizeof(BsqDuo) * P.duos.size())) return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (duos)");
-    BSQ_CK(ctx, cudaMemcpyAsync(B.duos.p, P.duos.data(), sizeof(BsqDuo) * P.duos.size(), cudaMemcpyHostToDevice, st));
-    ctx->tm.h2d_bytes += (int64_t)(sizeof(BsqDuo) * P.duos.size());
-  }
   if (!P.uniform_dev) {
     BSQ_CK(ctx, cudaMemcpyAsync(B.pairs.p, P.pairs, sizeof(BsqPair) * (size_t)E, cudaMemcpyHostToDevice, st));
     ctx->tm.h2d_bytes += (int64_t)sizeof(BsqPair) * E;
@@ -1090,9 +1212,8 @@ int launch_fill(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, size_t* evi, 
     int occ = bsq_k1h_op(ch.cfg, P.gosign, BSQ_OP_OCCUPANCY, 0, 0, nullptr);
     if (occ < 0) return fail(ctx, BSQ_ERR_ARG, "no kernel variant for this configuration");
     const int gpb = BSQ_FILL_THREADS / BSQ_K1_CFGS[ch.cfg].G;
-    const int64_t duos = ch.nduos;
-    A.duos = ch.duo_first >= 0 ? B.duos.as<BsqDuo>() + ch.duo_first : nullptr;
-    A.nduos = (int)ch.nduos;
+    const int64_t duos = (ch.count + 1) / 2;
+    A.nduos = (int)duos;
     const int occ_use = (leave_room && occ >= 4) ? occ - 1 : occ;
     int grid = (int)std::min<int64_t>((duos + gpb - 1) / gpb, (int64_t)ctx->sms * occ_use);
     if (grid < 1) grid = 1;

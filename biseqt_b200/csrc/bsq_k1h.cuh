@@ -3,8 +3,8 @@
 //
 // Same mapping as K1 (a group of 8 lanes owns a table of up to 152 columns,
 // lane l owns 19 consecutive columns -- or 16 lanes x 16 columns for up to 256 --
-// walks the rows, lags its left neighbour by one row) but every register holds the SAME cell of TWO problems of identical
-// shape -- problem A in the low halfword, problem B in the high one -- so that
+// walks the rows, lags its left neighbour by one row) but every register holds the SAME cell of TWO problems
+// -- problem A in the low halfword, problem B in the high one -- so that
 // one VIADD.16x2 / VIMNMX3.S16x2.RELU / VIADDMNMX.U16x2 instruction advances two
 // DP cells.  The recurrence is pwlib's (see bsq_kernels.cuh): candidates B, D, I,
 // M in that order, every candidate tying for the maximum kept, a gap extends for
@@ -22,8 +22,11 @@
 // Selected by the host only when it is exact: every score an integer,
 // (n + m + 4) * max|score| < 4000 (no 16-bit wrap with a -12000 "does not exist"
 // sentinel), go <= 0, ge <= 0 and ge + go <= 0 (padding columns can then never win
-// the end-cell search), alphabet <= 4 letters, m <= 255, all pairs of the batch of
-// one shape.  Results are identical to K1's and to pwlib's.
+// the end-cell search), alphabet <= 4 letters, m <= 255.  The two problems of a lane group
+// need the same geometry, not the same shape: the group walks max(nA, nB) rows and the
+// shorter problem sees padding rows / columns (letter 4, score "does not exist"), whose cells
+// can only decay (H <= the cell above / to the left) and therefore never become the first
+// maximum; their pointer words are not stored.  Results are identical to K1's and to pwlib's.
 //   replaces: dptable_solve's fill loop pw.c:59-110 + _std_find_optimal (:339-355)
 #pragma once
 #include "bsq_kernels.cuh"
@@ -69,14 +72,14 @@ template <int G, int K, int GOS>
 __global__ void __launch_bounds__(128) bsq_k1h_fill(const BsqFillArgs A) {
   constexpr int WPL = (K + 7) / 8, WST = BSQ_K1_WPL(K);
   static_assert(GOS <= 0, "K1h handles go <= 0");
-  // (origin letter of A, of B) x (mutant letter of A, of B; letter 4 = padding column):
+  // (origin letter of A, of B) x (mutant letter of A, of B); letter 4 = padding row / column:
   // subst - ge of both problems, packed
-  __shared__ unsigned s_sub2[16 * 25];
+  __shared__ unsigned s_sub2[25 * 25];
   const int L = A.L;
   const int ge = A.ge_i, go = A.go_i;
-  for (int i = threadIdx.x; i < 16 * 25; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 25 * 25; i += blockDim.x) {
     const int r = i / 25, c = i - r * 25;
-    const int oA = r >> 2, oB = r & 3, mA = c / 5, mB = c - mA * 5;
+    const int oA = r / 5, oB = r - oA * 5, mA = c / 5, mB = c - mA * 5;
     const int* sub = (const int*)A.subst;
     const int vA = (mA < L && oA < L) ? sub[oA * L + mA] - ge : BSQ_K1H_NINF;
     const int vB = (mB < L && oB < L) ? sub[oB * L + mB] - ge : BSQ_K1H_NINF;
@@ -99,19 +102,19 @@ __global__ void __launch_bounds__(128) bsq_k1h_fill(const BsqFillArgs A) {
     if (l == 0) q = atomicAdd(A.counter, 1);
     q = __shfl_sync(gmask, q, 0, G);
     if (q >= nduos) break;
-    int pa, pb;   // a problem without a partner of its shape aligns itself twice
-    if (A.duos) { const BsqDuo d = A.duos[q]; pa = d.a; pb = d.b; }
-    else { pa = 2 * q; pb = (2 * q + 1 < A.npairs) ? 2 * q + 1 : 2 * q; }
+    // problems (2q, 2q + 1) of the chunk; an odd one out aligns itself twice
+    const int pa = 2 * q, pb = (2 * q + 1 < A.npairs) ? 2 * q + 1 : 2 * q;
     const BsqPair PA = A.pairs[pa];
     const BsqPair PB = A.pairs[pb];
-    const int n = PA.n, m = PA.m;                  // PB has the same shape
+    const int nA = PA.n, mA = PA.m, nB = PB.n, mB = PB.m;
+    const int n = nA > nB ? nA : nB;               // rows the group walks
     const int y0 = l * K;
     int moff[K];                                   // column's letter pair -> index into a table row
 #pragma unroll
     for (int k = 0; k < K; k++) {
       const int y = y0 + k;
-      const int a = (y >= 1 && y <= m) ? (int)A.codes[PA.m_off + y - 1] : (y > m ? 4 : 0);
-      const int b = (y >= 1 && y <= m) ? (int)A.codes[PB.m_off + y - 1] : (y > m ? 4 : 0);
+      const int a = (y >= 1 && y <= mA) ? (int)A.codes[PA.m_off + y - 1] : (y > mA ? 4 : 0);
+      const int b = (y >= 1 && y <= mB) ? (int)A.codes[PB.m_off + y - 1] : (y > mB ? 4 : 0);
       moff[k] = a * 5 + b;
     }
     unsigned G2[K], nD2[K];
@@ -141,9 +144,10 @@ __global__ void __launch_bounds__(128) bsq_k1h_fill(const BsqFillArgs A) {
       unsigned inG2 = __shfl_up_sync(gmask, lastG2, 1, G);
       unsigned inN2 = __shfl_up_sync(gmask, lastN2, 1, G);
       if (l == 0) { inG2 = NINF2; inN2 = 0u; }
-      const int rowi = (la * 4 + lb) * 25;
-      int na = 0, nb_ = 0;                         // letters of row x + 1, used one iteration later
-      if (x >= 0 && x < n) { na = (int)oseqA[x]; nb_ = (int)oseqB[x]; }
+      const int rowi = (la * 5 + lb) * 25;
+      int na = 4, nb_ = 4;                         // letters of row x + 1, used one iteration later (4: past the end)
+      if (x < nA) na = (x >= 0) ? (int)oseqA[x] : 0;
+      if (x < nB) nb_ = (x >= 0) ? (int)oseqB[x] : 0;
       const bool active = (x >= 0 && x <= n);
       const unsigned* srow = s_sub2 + rowi;
       unsigned sq[4];
@@ -153,8 +157,8 @@ __global__ void __launch_bounds__(128) bsq_k1h_fill(const BsqFillArgs A) {
       asm volatile("" ::: "memory");
 #endif
       if (px >= 0) {
-        bsq_store_words<WPL, WST>(prowA + (long long)(px + l) * (G * WST), pwa);
-        if (pb != pa) bsq_store_words<WPL, WST>(prowB + (long long)(px + l) * (G * WST), pwb);
+        if (px <= nA) bsq_store_words<WPL, WST>(prowA + (long long)(px + l) * (G * WST), pwa);
+        if (pb != pa && px <= nB) bsq_store_words<WPL, WST>(prowB + (long long)(px + l) * (G * WST), pwb);
         px = -1;
       }
       if (active) {
@@ -215,8 +219,8 @@ __global__ void __launch_bounds__(128) bsq_k1h_fill(const BsqFillArgs A) {
       lb = nb_;
     }
     if (px >= 0) {
-      bsq_store_words<WPL, WST>(prowA + (long long)(px + l) * (G * WST), pwa);
-      if (pb != pa) bsq_store_words<WPL, WST>(prowB + (long long)(px + l) * (G * WST), pwb);
+      if (px <= nA) bsq_store_words<WPL, WST>(prowA + (long long)(px + l) * (G * WST), pwa);
+      if (pb != pa && px <= nB) bsq_store_words<WPL, WST>(prowB + (long long)(px + l) * (G * WST), pwb);
     }
 
     // group-wide first maximum of each problem: higher score, then smaller (x, y)

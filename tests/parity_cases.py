@@ -236,11 +236,12 @@ def run_duo_short_reads(make_engine, seed, npairs=37):
                     assert eng.timing()['dtype'] == batch.DTYPE_I32
                     assert np.array_equal(r.score, r1.score) and np.array_equal(r.tx_off, r1.tx_off)
                     assert np.array_equal(r.tx_buf[:r.tx_off[-1]], r1.tx_buf[:r1.tx_off[-1]])
-            # ragged batches (opt-in, BSQ_RAGGED_DUO): a handful of shapes, repeated an odd or even
-            # number of times, plus pairs the packed kernel cannot take (two passes); neighbours of
-            # one shape share a lane group
-            os.environ['BSQ_RAGGED_DUO'] = '1'
-            for trial in range(3):
+            # ragged batches: a handful of shapes, repeated an odd or even number of times, plus
+            # pairs the packed kernel cannot take (two passes); neighbours of one shape share a
+            # lane group.  Trials 3.. run the planner's multi-threaded passes (BSQ_PAR_GRAIN).
+            for trial in range(6):
+                if trial >= 3:
+                    os.environ['BSQ_PAR_GRAIN'] = str(trial - 1)
                 L = 4
                 S = np.where(np.eye(L, dtype=bool), 2.0, -3.0)
                 go, ge = (-4.0, -1.0) if trial != 1 else (0.0, -2.0)
@@ -248,7 +249,7 @@ def run_duo_short_reads(make_engine, seed, npairs=37):
                 shapes += [(30, 200), (60, 400)]      # 16-lane geometry / needs two passes: scalar kernel
                 probs = []
                 for (n, m) in shapes:
-                    for r in range(int(rng.integers(1, 6))):
+                    for r in range(int(rng.integers(1, 6 if trial < 3 else 12))):
                         o = rng.integers(0, L, size=n).astype(np.uint8)
                         t = rng.integers(0, L, size=m).astype(np.uint8)
                         k = min(n, m)
@@ -267,8 +268,48 @@ def run_duo_short_reads(make_engine, seed, npairs=37):
                     del os.environ['BSQ_NO_DUO']
                 assert np.array_equal(r.score, r1.score) and np.array_equal(r.tx_off, r1.tx_off)
                 assert np.array_equal(r.tx_buf[:r.tx_off[-1]], r1.tx_buf[:r1.tx_off[-1]])
+            os.environ.pop('BSQ_PAR_GRAIN', None)
+            # ragged batches that stay in caller order (one geometry, tables within 2x): every pair
+            # its own shape, neighbours (2q, 2q+1) share a lane group, the shorter one padded
+            for trial in range(8):
+                blocked = trial >= 4     # the block-wise in-order planner (BSQ_PLAN_BLOCK: small blocks)
+                trial %= 4
+                if blocked:
+                    os.environ['BSQ_PLAN_BLOCK'] = str(3 + trial)
+                    os.environ['BSQ_PAR_GRAIN'] = '7'
+                    os.environ['BSQ_ARENA_CAP_BYTES'] = '600000'   # several chunks (read when the engine is created)
+                    eng.close()
+                    eng = make_engine()
+                L = 4
+                S = np.where(np.eye(L, dtype=bool), 1.0, -3.0) if trial < 3 else np.where(np.eye(L, dtype=bool), 2.0, 0.0)
+                go, ge = [(-5.0, -2.0), (0.0, -1.0), (-1.0, 0.0), (0.0, 0.0)][trial]
+                lo, hi = [(90, 152), (160, 256), (90, 152), (100, 140)][trial]
+                probs = []
+                for i in range((2 * npairs if blocked else npairs) + trial):
+                    n, m = int(rng.integers(lo, hi)), int(rng.integers(lo, hi))
+                    o = rng.integers(0, L, size=n).astype(np.uint8)
+                    t = rng.integers(0, L, size=m).astype(np.uint8)
+                    k = min(n, m)
+                    if i % 3:
+                        t[:k] = o[:k]
+                        t[rng.integers(0, m, size=max(1, m // 8))] = rng.integers(0, L, size=max(1, m // 8))
+                    probs.append(dict(origin=o, mutant=t, subst=S, go=go, ge=ge, mode=0, type=1, diag_range=None))
+                r = check_batch(eng, probs)
+                assert eng.timing()['dtype'] == batch.DTYPE_I16X2
+                assert (eng.timing()['chunks'] > 1) if blocked else (eng.timing()['chunks'] == 1)
+                os.environ['BSQ_NO_DUO'] = '1'     # the scalar kernel on the same (in-order) plan
+                try:
+                    r1 = engine_batch(eng, probs)
+                finally:
+                    del os.environ['BSQ_NO_DUO']
+                assert eng.timing()['dtype'] == batch.DTYPE_I32
+                assert np.array_equal(r.score, r1.score) and np.array_equal(r.tx_off, r1.tx_off)
+                assert np.array_equal(r.tx_buf[:r.tx_off[-1]], r1.tx_buf[:r1.tx_off[-1]])
+                for k in ('BSQ_PLAN_BLOCK', 'BSQ_PAR_GRAIN', 'BSQ_ARENA_CAP_BYTES'):
+                    os.environ.pop(k, None)
         finally:
-            os.environ.pop('BSQ_RAGGED_DUO', None)
+            for k in ('BSQ_PLAN_BLOCK', 'BSQ_PAR_GRAIN', 'BSQ_ARENA_CAP_BYTES'):
+                os.environ.pop(k, None)
             eng.close()
     finally:
         del os.environ['BSQ_UNIFORM_MIN']

@@ -8,10 +8,10 @@ from biseqt_b200 import batch
 eng = batch.Engine(0)
 rng = np.random.default_rng(1)
 S = np.where(np.eye(4, dtype=bool), 1.0, -3.0)
-for ragged in (False, True):
+for ragged in (False, True, 2):   # 2: origin and mutant lengths drawn independently (51 x 51 shapes)
     for N in (1, 100, 10000, 100000, 1000000):
         lens = rng.integers(100, 151, size=N) if ragged else np.full(N, 150)
-        o_len = lens.astype(np.int32); m_len = lens.astype(np.int32)
+        o_len = lens.astype(np.int32); m_len = (rng.integers(100, 151, size=N) if ragged == 2 else lens).astype(np.int32)
         tot = (o_len.astype(np.int64) + m_len).cumsum()
         o_off = np.concatenate([[0], tot[:-1]]).astype(np.int64)
         m_off = o_off + o_len
@@ -35,6 +35,6 @@ for ragged in (False, True):
         t = eng.timing()
         cells = float(((o_len.astype(np.int64) + 1) * (m_len + 1)).sum())
         print('%-7s N=%-8d %9.3f ms  %8.1f GCUPS  plan %.3f ms  device %.3f ms (fill %.3f)  dtype %s chunks %d%s' % (
-            'ragged' if ragged else 'uniform', N, dt * 1e3, cells / dt / 1e9, t['plan_ms'], t['total_ms'], t['fill_ms'],
+            ('uniform', 'ragged', 'ragged2')[int(ragged)], N, dt * 1e3, cells / dt / 1e9, t['plan_ms'], t['total_ms'], t['fill_ms'],
             batch.DTYPE_NAMES[t['dtype']], t['chunks'], '  (pinned)' if out else ''))
 eng.close()

@@ -94,6 +94,10 @@ struct Chunk {
   int64_t k3_active = 0; // K3: strips in flight when every pair's pipeline is full
 };
 
+// largest pointer table (words) of a batch that is aligned in caller order instead of sorted:
+// short reads only (a 512 x 512 STD table has 34816 words)
+#define BSQ_INORDER_MAX_WORDS 65536
+
 // three slots: the fill of chunk c+2 need not wait for the traceback of chunk c, which shares
 // the SMs with fill c+1 and often takes longer than a fill
 #define BSQ_ARENA_SLOTS 3
@@ -680,7 +684,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
     if (target_chunks > 1 && !single_chunk)
       cap = std::min(cap, std::max<int64_t>(std::max<int64_t>((tot_words + target_chunks - 1) / target_chunks, (int64_t)8 << 20), maxw));
     const bool duo_all = (flags & 6) == 2, duo_none = (flags & 2) == 0 || dtype != BSQ_DTYPE_I32;
-    if (!(flags & 1) && range_ok && maxw <= 2 * minw && (duo_all || duo_none) && (single_chunk ? tot_words <= arena_words : max_blk <= cap)) {
+    if (!(flags & 1) && range_ok && maxw <= 2 * minw && maxw <= BSQ_INORDER_MAX_WORDS && (duo_all || duo_none) && (single_chunk ? tot_words <= arena_words : max_blk <= cap)) {
       P.dtype = dtype;
       P.overrides.clear();
       P.k3.clear();
@@ -838,12 +842,14 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
     }
   } else {
     tot_words = all.tot_words; maxw = all.maxw; n_duo_ok = all.n_duo_ok;
-    // Caller order is kept (no sort, results leave chunk by chunk) when every pair runs on the
-    // same kernel geometry and the tables differ by less than 2x: the fill kernels pull pairs from
-    // a queue, so the order only matters for the tail, and K1h pairs neighbours of any shape.
-    // Typical case: ragged short reads.  Wide-band (K3) pairs are always ordered.
-    uniform = !all.mixed && all.cfg0 >= 0 && all.maxw <= 2 * all.minw &&
-              !(family == 2 && all.cfg0 / 2 >= BSQ_K2_NCFG) && getenv("BSQ_ALWAYS_SORT") == nullptr;
+    // Caller order is kept (no sort, results leave chunk by chunk) for ragged SHORT reads: STD
+    // frame, one kernel geometry, tables within 2x of each other and small.  The fill kernels pull
+    // pairs from a queue and K1h pairs neighbours of any shape, so the order costs ~10 % of the fill
+    // (lane groups of one warp run different row counts) where the sort would cost more than that.
+    // Long pairs are always ordered: measured on config 3 (32768 banded pairs of ~10 kb) caller
+    // order made the fill 26 % slower, and their plan is < 3 % of the call either way.
+    uniform = family == 1 && !all.mixed && all.cfg0 >= 0 && all.maxw <= 2 * all.minw &&
+              all.maxw <= BSQ_INORDER_MAX_WORDS && getenv("BSQ_ALWAYS_SORT") == nullptr;
   }
   if (!range_ok) P.cells = 0;
   P.identity = uniform;
@@ -1209,7 +1215,7 @@ int launch_fill(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, size_t* evi, 
     return BSQ_SUCCESS;
   }
   if (ch.duo) {
-    int occ = bsq_k1h_op(ch.cfg, P.gosign, BSQ_OP_OCCUPANCY, 0, 0, nullptr);
+    int occ = bsq_k1h_op(ch.cfg, P.gosign, P.uniform_dev ? 1 : 0, BSQ_OP_OCCUPANCY, 0, 0, nullptr);
     if (occ < 0) return fail(ctx, BSQ_ERR_ARG, "no kernel variant for this configuration");
     const int gpb = BSQ_FILL_THREADS / BSQ_K1_CFGS[ch.cfg].G;
     const int64_t duos = (ch.count + 1) / 2;
@@ -1219,7 +1225,7 @@ int launch_fill(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, size_t* evi, 
     if (grid < 1) grid = 1;
     cudaEvent_t e0 = get_event(ctx, (*evi)++), e1 = get_event(ctx, (*evi)++);
     BSQ_CK(ctx, cudaEventRecord(e0, stream));
-    if (bsq_k1h_op(ch.cfg, P.gosign, BSQ_OP_LAUNCH, grid, stream, &A) < 0)
+    if (bsq_k1h_op(ch.cfg, P.gosign, P.uniform_dev ? 1 : 0, BSQ_OP_LAUNCH, grid, stream, &A) < 0)
       return fail(ctx, BSQ_ERR_ARG, "no kernel variant for this configuration");
     BSQ_CK(ctx, cudaGetLastError());
     BSQ_CK(ctx, cudaEventRecord(e1, stream));

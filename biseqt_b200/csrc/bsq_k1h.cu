@@ -13,10 +13,17 @@ static int bsq_k1h_do(KernelT kern, int op, int grid, cudaStream_t st, const Bsq
   return 0;
 }
 
-int bsq_k1h_op(int cfg, int gos, int op, int grid, cudaStream_t st, const BsqFillArgs* A) {
-  if (cfg == 0 && gos < 0) return bsq_k1h_do(bsq_k1h_fill<8, 19, -1>, op, grid, st, A);
-  if (cfg == 0 && gos == 0) return bsq_k1h_do(bsq_k1h_fill<8, 19, 0>, op, grid, st, A);
-  if (cfg == 1 && gos < 0) return bsq_k1h_do(bsq_k1h_fill<16, 16, -1>, op, grid, st, A);
-  if (cfg == 1 && gos == 0) return bsq_k1h_do(bsq_k1h_fill<16, 16, 0>, op, grid, st, A);
+int bsq_k1h_op(int cfg, int gos, int same, int op, int grid, cudaStream_t st, const BsqFillArgs* A) {
+  if (same) {
+    if (cfg == 0 && gos < 0) return bsq_k1h_do(bsq_k1h_fill<8, 19, -1, true>, op, grid, st, A);
+    if (cfg == 0 && gos == 0) return bsq_k1h_do(bsq_k1h_fill<8, 19, 0, true>, op, grid, st, A);
+    if (cfg == 1 && gos < 0) return bsq_k1h_do(bsq_k1h_fill<16, 16, -1, true>, op, grid, st, A);
+    if (cfg == 1 && gos == 0) return bsq_k1h_do(bsq_k1h_fill<16, 16, 0, true>, op, grid, st, A);
+  } else {
+    if (cfg == 0 && gos < 0) return bsq_k1h_do(bsq_k1h_fill<8, 19, -1, false>, op, grid, st, A);
+    if (cfg == 0 && gos == 0) return bsq_k1h_do(bsq_k1h_fill<8, 19, 0, false>, op, grid, st, A);
+    if (cfg == 1 && gos < 0) return bsq_k1h_do(bsq_k1h_fill<16, 16, -1, false>, op, grid, st, A);
+    if (cfg == 1 && gos == 0) return bsq_k1h_do(bsq_k1h_fill<16, 16, 0, false>, op, grid, st, A);
+  }
   return -1;
 }

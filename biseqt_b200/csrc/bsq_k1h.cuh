@@ -68,7 +68,9 @@ __device__ __forceinline__ unsigned bsq_vbmax2(unsigned a, unsigned b, bool* ph,
 #endif
 
 // (G, K) is one of K1's single-pass geometries: (8, 19) for m <= 151, (16, 16) for m <= 255
-template <int G, int K, int GOS>
+// SAME: every pair of the chunk has one shape (fixed-length reads): the per-problem row / column
+// bounds fold into one
+template <int G, int K, int GOS, bool SAME>
 __global__ void __launch_bounds__(128) bsq_k1h_fill(const BsqFillArgs A) {
   constexpr int WPL = (K + 7) / 8, WST = BSQ_K1_WPL(K);
   static_assert(GOS <= 0, "K1h handles go <= 0");
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(128) bsq_k1h_fill(const BsqFillArgs A) {
     const int pa = 2 * q, pb = (2 * q + 1 < A.npairs) ? 2 * q + 1 : 2 * q;
     const BsqPair PA = A.pairs[pa];
     const BsqPair PB = A.pairs[pb];
-    const int nA = PA.n, mA = PA.m, nB = PB.n, mB = PB.m;
+    const int nA = PA.n, mA = PA.m, nB = SAME ? nA : PB.n, mB = SAME ? mA : PB.m;
     const int n = nA > nB ? nA : nB;               // rows the group walks
     const int y0 = l * K;
     int moff[K];                                   // column's letter pair -> index into a table row
@@ -145,9 +147,15 @@ __global__ void __launch_bounds__(128) bsq_k1h_fill(const BsqFillArgs A) {
       unsigned inN2 = __shfl_up_sync(gmask, lastN2, 1, G);
       if (l == 0) { inG2 = NINF2; inN2 = 0u; }
       const int rowi = (la * 5 + lb) * 25;
-      int na = 4, nb_ = 4;                         // letters of row x + 1, used one iteration later (4: past the end)
-      if (x < nA) na = (x >= 0) ? (int)oseqA[x] : 0;
-      if (x < nB) nb_ = (x >= 0) ? (int)oseqB[x] : 0;
+      int na, nb_;                                 // letters of row x + 1, used one iteration later (4: past the end)
+      if (SAME) {
+        na = 0; nb_ = 0;
+        if (x >= 0 && x < n) { na = (int)oseqA[x]; nb_ = (int)oseqB[x]; }
+      } else {
+        na = 4; nb_ = 4;
+        if (x < nA) na = (x >= 0) ? (int)oseqA[x] : 0;
+        if (x < nB) nb_ = (x >= 0) ? (int)oseqB[x] : 0;
+      }
       const bool active = (x >= 0 && x <= n);
       const unsigned* srow = s_sub2 + rowi;
       unsigned sq[4];
@@ -157,8 +165,8 @@ __global__ void __launch_bounds__(128) bsq_k1h_fill(const BsqFillArgs A) {
       asm volatile("" ::: "memory");
 #endif
       if (px >= 0) {
-        if (px <= nA) bsq_store_words<WPL, WST>(prowA + (long long)(px + l) * (G * WST), pwa);
-        if (pb != pa && px <= nB) bsq_store_words<WPL, WST>(prowB + (long long)(px + l) * (G * WST), pwb);
+        if (SAME || px <= nA) bsq_store_words<WPL, WST>(prowA + (long long)(px + l) * (G * WST), pwa);
+        if (pb != pa && (SAME || px <= nB)) bsq_store_words<WPL, WST>(prowB + (long long)(px + l) * (G * WST), pwb);
         px = -1;
       }
       if (active) {
@@ -219,8 +227,8 @@ __global__ void __launch_bounds__(128) bsq_k1h_fill(const BsqFillArgs A) {
       lb = nb_;
     }
     if (px >= 0) {
-      if (px <= nA) bsq_store_words<WPL, WST>(prowA + (long long)(px + l) * (G * WST), pwa);
-      if (pb != pa && px <= nB) bsq_store_words<WPL, WST>(prowB + (long long)(px + l) * (G * WST), pwb);
+      if (SAME || px <= nA) bsq_store_words<WPL, WST>(prowA + (long long)(px + l) * (G * WST), pwa);
+      if (pb != pa && (SAME || px <= nB)) bsq_store_words<WPL, WST>(prowB + (long long)(px + l) * (G * WST), pwb);
     }
 
     // group-wide first maximum of each problem: higher score, then smaller (x, y)

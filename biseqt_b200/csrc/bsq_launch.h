@@ -33,6 +33,6 @@ int bsq_k2_i32_op(int cfg, int blocal, int gos, int op, int grid, cudaStream_t s
 // K3 (cfg = index into BSQ_K3_CFGS): launches on `grid` blocks of BSQ_K3_THREADS
 int bsq_k3_f64_op(int cfg, int btype, int gos, int grid, cudaStream_t st, const BsqFillArgs* A);
 int bsq_k3_i32_op(int cfg, int btype, int gos, int grid, cudaStream_t st, const BsqFillArgs* A);
-// K1h: STD LOCAL, two equal-shape short problems per lane in packed 16-bit arithmetic
-// (geometry of BSQ_K1_CFGS[cfg], cfg 0 or 1); gos <= 0
-int bsq_k1h_op(int cfg, int gos, int op, int grid, cudaStream_t st, const BsqFillArgs* A);
+// K1h: STD LOCAL, two short problems per lane in packed 16-bit arithmetic (geometry of
+// BSQ_K1_CFGS[cfg], cfg 0 or 1); gos <= 0; same != 0: all pairs of the chunk have one shape
+int bsq_k1h_op(int cfg, int gos, int same, int op, int grid, cudaStream_t st, const BsqFillArgs* A);

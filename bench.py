@@ -34,7 +34,7 @@ if ROOT not in sys.path:
 import bench_workloads as bw  # noqa: E402
 
 WORKLOAD_PAIRS = {'c2_int': 1000000, 'c2_logodds': 1000000, 'c3_int': 32768, 'c3_logodds': 32768,
-                  'c4_int': 1024, 'c1': 1, 'c2w_int': 400000, 'c5_int': 1, 'c5_logodds': 1, 'c5s_int': 1, 'c5s_logodds': 1}
+                  'c4_int': 4096, 'c1': 1, 'c2w_int': 400000, 'c5_int': 1, 'c5_logodds': 1, 'c5s_int': 1, 'c5s_logodds': 1}
 
 
 def ops_per_cell(go):

@@ -722,11 +722,21 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
       P.chunks.push_back(cur);
       const bool duo = duo_all && dtype == BSQ_DTYPE_I32 && N >= uniform_min_pairs();
       for (Chunk& ch : P.chunks) ch.duo = duo;
+      // Inside a block the pairs are ordered by origin length (a counting sort of <= RB cached
+      // entries): the lane groups of a warp -- and the two problems of a K1h duo -- then walk nearly
+      // the same number of rows.  A chunk still covers a contiguous range of caller indices.
+      const int nkeys = (int)scan_n - min_n + 1;
       over_blocks([&](int64_t b0, int64_t b1) {
+        std::vector<int> cnt((size_t)nkeys + 1), perm((size_t)RB);
         for (int64_t b = b0; b < b1; b++) {
           int64_t pw = blk_ptr[(size_t)b], sl = blk_slot[(size_t)b];
-          const int64_t i1 = std::min(N, (b + 1) * RB);
-          for (int64_t i = b * RB; i < i1; i++) {
+          const int64_t ib = b * RB, i1 = std::min(N, (b + 1) * RB);
+          std::fill(cnt.begin(), cnt.end(), 0);
+          for (int64_t i = ib; i < i1; i++) cnt[(size_t)((int)scan_n - o_len[i]) + 1]++;
+          for (int k = 0; k < nkeys; k++) cnt[(size_t)k + 1] += cnt[(size_t)k];
+          for (int64_t i = ib; i < i1; i++) perm[(size_t)cnt[(size_t)((int)scan_n - o_len[i])]++] = (int)(i - ib);
+          for (int64_t r = ib; r < i1; r++) {
+            const int64_t i = ib + perm[(size_t)(r - ib)];
             const int n = o_len[i], m = m_len[i];
             BsqPair bp;
             bp.o_off = o_off[i];
@@ -737,7 +747,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
             bp.m = m;
             bp.dmin = bp.dmax = bp.s0 = 0;
             bp.pad = (int)i;
-            out[i] = bp;
+            out[r] = bp;
             pw += (int64_t)(n + G) * G * WPL;
             sl += (int64_t)n + m;
           }

@@ -412,6 +412,50 @@ def run_big_ragged_plan(make_engine, seed, npairs=70000, all_modes=True):
         eng.close()
 
 
+def run_ragged_reads(make_engine, seed, npairs=30000, lo=100, hi=151):
+    """Ragged short reads through the caller-order planner (blocks of 4096 pairs, ordered by
+    origin length inside a block, K1h duos of unequal shapes) against the batch oracle, and the
+    same bytes from the sorting planner (BSQ_ALWAYS_SORT) and the scalar kernel (BSQ_NO_DUO)."""
+    os.environ['BSQ_ARENA_CAP_BYTES'] = str(200 << 20)    # several chunks
+    try:
+        eng = make_engine()
+    finally:
+        del os.environ['BSQ_ARENA_CAP_BYTES']
+    try:
+        rng = np.random.default_rng(seed)
+        o_len = rng.integers(lo, hi, size=npairs).astype(np.int32)
+        m_len = rng.integers(lo, hi, size=npairs).astype(np.int32)
+        tot = (o_len.astype(np.int64) + m_len).cumsum()
+        o_off = np.concatenate([[0], tot[:-1]]).astype(np.int64)
+        m_off = o_off + o_len
+        codes = rng.integers(0, 4, size=int(tot[-1]) + 16, dtype=np.uint8)
+        for i in range(0, npairs, 3):   # two thirds of the pairs are related reads
+            k = min(o_len[i], m_len[i])
+            codes[m_off[i]:m_off[i] + k] = codes[o_off[i]:o_off[i] + k]
+            hits = rng.integers(0, k, size=k // 12)
+            codes[m_off[i] + hits] = rng.integers(0, 4, size=len(hits))
+        S = np.where(np.eye(4, dtype=bool), 1.0, -3.0)
+        r = eng.align(codes, o_off, o_len, m_off, m_len, 0, 1, S, -5.0, -2.0)
+        t = eng.timing()
+        assert t['dtype'] == batch.DTYPE_I16X2 and t['chunks'] > 1
+        e = lean.align_batch(0, 1, S, -5.0, -2.0, codes, o_off, o_len, m_off, m_len, None, None)
+        assert np.array_equal(r.status, e['status'])
+        assert np.array_equal(r.score, e['score'])
+        assert np.array_equal(r.end_x, e['end_x']) and np.array_equal(r.end_y, e['end_y'])
+        assert np.array_equal(r.start_x, e['start_x']) and np.array_equal(r.start_y, e['start_y'])
+        assert r.transcripts() == lean.transcripts(e)
+        for var in ('BSQ_ALWAYS_SORT', 'BSQ_NO_DUO'):
+            os.environ[var] = '1'
+            try:
+                r1 = eng.align(codes, o_off, o_len, m_off, m_len, 0, 1, S, -5.0, -2.0)
+            finally:
+                del os.environ[var]
+            assert np.array_equal(r.tx_off, r1.tx_off) and np.array_equal(r.tx_buf[:r.tx_off[-1]], r1.tx_buf[:r1.tx_off[-1]])
+            assert np.array_equal(r.status, r1.status) and np.array_equal(r.score, r1.score)
+    finally:
+        eng.close()
+
+
 def run_dtype_equivalence(eng, seed, npairs=12, lo=5, hi=60):
     """Integer scores: the I32 fast path and the F64 path give identical results."""
     rng = np.random.default_rng(seed)

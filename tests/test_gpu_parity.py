@@ -100,6 +100,10 @@ def test_gpu_big_ragged_plan():
     pc.run_big_ragged_plan(lambda: batch.Engine(0), seed=99, npairs=300000)
 
 
+def test_gpu_ragged_reads():
+    pc.run_ragged_reads(lambda: batch.Engine(0), seed=101, npairs=30000)
+
+
 def test_gpu_uniform_batches():
     pc.run_uniform_batches(lambda: batch.Engine(0), seed=83)
 

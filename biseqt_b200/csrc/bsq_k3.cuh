@@ -38,6 +38,9 @@
 #define BSQ_BACKOFF(ns) __nanosleep(ns)
 #endif
 
+struct BsqFalse { static constexpr bool value = false; };
+struct BsqTrue { static constexpr bool value = true; };
+
 template <int K> struct BsqK3Unit;
 template <> struct BsqK3Unit<2> { typedef uint8_t type; };
 template <> struct BsqK3Unit<4> { typedef uint16_t type; };
@@ -207,7 +210,11 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3_fill(const BsqFillArgs 
       typename Slab::Raw nx = {};    // prefetched (raw) boundary entry of row x_lo + (next batch) + lane
       bool nx_have = false;
 
-      for (int t = 0; t < nsteps; t++) {
+      // One time step.  INT (interior): every lane's K cells lie inside band and table, no lane is
+      // on row 0 / row n / column m and the letter two rows ahead exists -- all gating, the B rule
+      // of the edges and the end-cell tests fold away (the same split as K2's three phases).
+      auto step = [&](const int t, auto interior_tag) {
+        constexpr bool INT = decltype(interior_tag)::value;
         const int x = x_lo + t - lane;
         if ((t & 31) == 0 && j > 0) {
           // boundary values of rows x_lo + t .. x_lo + t + 31: mine is row xr (fetched one batch
@@ -243,14 +250,14 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3_fill(const BsqFillArgs 
         }
         T inH = __shfl_up_sync(FULL, lastH, 1);
         int inG = __shfl_up_sync(FULL, lastG, 1);
-        const bool active = (t >= lane) && (x <= x_hi);
+        const bool active = INT || ((t >= lane) && (x <= x_hi));
         if (lane == 0) {
           inH = NINF;
           inG = 0;
           if (j > 0) { inH = s_inH[wib][t & 31]; inG = s_inG[wib][t & 31]; }
         }
         // loads for the next two rows, off the dependency chain
-        const int o2 = letter(x + 2);
+        const int o2 = INT ? (int)oseq[x + 1] : letter(x + 2);
         T sign[K];
         {
           const int ob = o1 * L;
@@ -261,9 +268,9 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3_fill(const BsqFillArgs 
           const int e = x - y0 - dmin;   // cell k is inside the band iff 0 <= e - k <= W - 1
           // B (_alnchoice_B, _pw_internals.c:182-197): B_LOCAL anywhere, B_OVERLAP on x==0 or y==0,
           // B_GLOBAL at (0,0) only
-          const bool rowb = (BT == BSQ_B_LOCAL) || (BT == BSQ_B_OVERLAP && x == 0);
+          const bool rowb = (BT == BSQ_B_LOCAL) || (!INT && BT == BSQ_B_OVERLAP && x == 0);
           const T brest = rowb ? ZERO : NINF;
-          const T bfirst = (rowb || (y0 == 0 && (BT == BSQ_B_OVERLAP || x == 0))) ? ZERO : NINF;
+          const T bfirst = (rowb || (!INT && y0 == 0 && (BT == BSQ_B_OVERLAP || x == 0))) ? ZERO : NINF;
           T left = inH;
           int gI = inG;
           T diag = prev_in;
@@ -271,7 +278,7 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3_fill(const BsqFillArgs 
           if (rowb) {
 #pragma unroll
             for (int k = 0; k < K; k++) {
-              const bool inb = ((unsigned)(e - k) <= (unsigned)Wm1) && (k < kv);
+              const bool inb = INT || (((unsigned)(e - k) <= (unsigned)Wm1) && (k < kv));
               const T up = Hup[k];
               T H;
               int fD, fI;
@@ -285,12 +292,12 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3_fill(const BsqFillArgs 
           } else {
 #pragma unroll
             for (int k = 0; k < K; k++) {
-              const bool inb = ((unsigned)(e - k) <= (unsigned)Wm1) && (k < kv);
+              const bool inb = INT || (((unsigned)(e - k) <= (unsigned)Wm1) && (k < kv));
               const T up = Hup[k];
               T H;
               int fD, fI;
               uint32_t nib;
-              if (k == 0) bsq_k3_cell<S, GOS, true>(up, gD[k], left, gI, diag, sig[k], bfirst, go, ge, inb, H, fD, fI, nib);
+              if (k == 0 && !INT) bsq_k3_cell<S, GOS, true>(up, gD[k], left, gI, diag, sig[k], bfirst, go, ge, inb, H, fD, fI, nib);
               else bsq_k3_cell<S, GOS, false>(up, gD[k], left, gI, diag, sig[k], ZERO, go, ge, inb, H, fD, fI, nib);
               cw |= nib << (4 * k);
               gD[k] = fD; gI = fI; diag = up; left = H; Hup[k] = H;
@@ -301,7 +308,8 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3_fill(const BsqFillArgs 
           prow[(long long)t * G] = (PU)cw;
           if (lane == G - 1 && has_succ) Slab::put(slab + (long long)x * Slab::EPR, left, gI != 0, tag_out);
           // end cell, _banded_find_optimal (_pw_internals.c:364-414)
-          if (BT == BSQ_B_GLOBAL) {
+          if (INT) {
+          } else if (BT == BSQ_B_GLOBAL) {
             if (x == n && km >= 0 && km < K) {
 #pragma unroll
               for (int k = 0; k < K; k++) if (k == km) { bs = Hup[k]; bk1 = n - m; bk2 = n; }
@@ -321,10 +329,30 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3_fill(const BsqFillArgs 
             }
           }
         }
-        if (t >= lane) prev_in = inH;
+        if (INT || t >= lane) prev_in = inH;
         o1 = o2;
 #pragma unroll
         for (int k = 0; k < K; k++) sig[k] = sign[k];
+      };
+      // interior steps [t_a, t_b]: with c0 = x_lo - (Y + dmin) >= 0, cell k of lane l sits at
+      // e - k = c0 + t - l (K + 1) - k in the band: >= 0 for lane 31, <= W - 1 for lane 0; lane 0
+      // (the lowest row) stays two rows clear of n, lane 31 is past row 0; the strip lies strictly
+      // left of column m; B_OVERLAP's column 0 (strip 0) is never interior
+      int t_a = nsteps, t_b = -1;
+      if (Y + BW - 1 < m && !(BT == BSQ_B_OVERLAP && j == 0)) {
+        const int c0 = x_lo - (Y + dmin);
+        t_a = 31 * (K + 1) + K - 1 - c0;
+        t_a = t_a < 32 ? 32 : t_a;
+        t_b = Wm1 - c0;
+        t_b = (n - 2 - x_lo < t_b) ? n - 2 - x_lo : t_b;
+        t_b = (x_hi - x_lo < t_b) ? x_hi - x_lo : t_b;
+        if (t_b < t_a) { t_a = nsteps; t_b = -1; }
+      }
+      {
+        int t = 0;
+        for (; t < t_a && t < nsteps; t++) step(t, BsqFalse{});
+        for (; t <= t_b; t++) step(t, BsqTrue{});
+        for (; t < nsteps; t++) step(t, BsqFalse{});
       }
       if (BT == BSQ_B_LOCAL) {  // every cell, (d, a) ascending; per column d ascends with x
 #pragma unroll

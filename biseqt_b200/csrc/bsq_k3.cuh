@@ -108,8 +108,9 @@ template <> struct BsqK3Slab<ScF64> {
 };
 
 // BT = banded_alntype (BSQ_B_GLOBAL 0 / BSQ_B_LOCAL 1 / BSQ_B_OVERLAP 2)
-template <class S, int K, int BT, int GOS>
+template <class S, int K, int R, int BT, int GOS>
 __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3_fill(const BsqFillArgs A) {
+  static_assert(R == 1 || R == 2 || R == 4 || R == 8, "R must divide the 32-row boundary batch");
   typedef typename S::T T;
   typedef typename BsqK3Unit<K>::type PU;
   typedef BsqK3Slab<S> Slab;
@@ -184,8 +185,10 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3_fill(const BsqFillArgs 
       for (int k = 0; k < K; k++) { Hup[k] = NINF; gD[k] = 0; }
 #pragma unroll
       for (int k = 0; k < NB; k++) { best[k] = NINF; bestx[k] = 0; }
-      T lastH = NINF;
-      int lastG = 0;
+      T lastH[R];                    // my rightmost column's cells of the rows of the last step
+      int lastG[R];
+#pragma unroll
+      for (int r = 0; r < R; r++) { lastH[r] = NINF; lastG[r] = 0; }
       T prev_in = NINF;
       if (lane == 0 && j > 0) {      // (x_lo - 1, Y - 1): the diagonal neighbour of my first cell
         const int xd = x_lo - 1;
@@ -195,31 +198,37 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3_fill(const BsqFillArgs 
           while (!Slab::decode(Slab::load(slab + (long long)xd * Slab::EPR), tag_in, prev_in, f)) { BSQ_BACKOFF(ns); if (ns < 1024) ns *= 2; }
         }
       }
-      const int nsteps = (x_hi - x_lo + 1) + G - 1;
+      // A time step is R rows: lane l does rows x_lo + (t - l) R + r, r < R, of its K columns, i.e.
+      // lags its left neighbour by R rows.  The pointer layout does not depend on R.
+      const int nsteps = (x_hi - x_lo + R) / R + G - 1;
       PU* prow = (PU*)(A.ptr + P.ptr_off) + (long long)j * P.s0 * G + lane;
       const uint8_t* oseq = A.codes + P.o_off;
       // software pipeline of the letter / score loads: row x uses o[x-1]
       auto letter = [&](int xr) -> int { return (xr >= 1 && xr <= n) ? (int)oseq[xr - 1] : 0; };
-      int o1 = letter(x_lo - lane + 1);  // letter of the row after the one being computed
-      T sig[K];
-      {
-        const int ob = letter(x_lo - lane) * L;
+      int o1[R];                     // letters of the rows of the next step
+      T sig[R][K];
 #pragma unroll
-        for (int k = 0; k < K; k++) sig[k] = s_sub[ob + moff[k]];
+      for (int r = 0; r < R; r++) {
+        o1[r] = letter(x_lo - lane * R + R + r);
+        const int ob = letter(x_lo - lane * R + r) * L;
+#pragma unroll
+        for (int k = 0; k < K; k++) sig[r][k] = s_sub[ob + moff[k]];
       }
       typename Slab::Raw nx = {};    // prefetched (raw) boundary entry of row x_lo + (next batch) + lane
       bool nx_have = false;
 
-      // One time step.  INT (interior): every lane's K cells lie inside band and table, no lane is
-      // on row 0 / row n / column m and the letter two rows ahead exists -- all gating, the B rule
-      // of the edges and the end-cell tests fold away (the same split as K2's three phases).
+      // One time step.  INT (interior): every cell of every lane lies inside band and table, no lane
+      // is on row 0 / row n / column m and the letters two steps ahead exist -- all gating, the B
+      // rule of the edges and the end-cell tests fold away (the same split as K2's three phases),
+      // and the R x K block is computed in anti-diagonal order: the cells of one anti-diagonal do
+      // not depend on each other, which is the only instruction-level parallelism a lone warp has.
       auto step = [&](const int t, auto interior_tag) {
         constexpr bool INT = decltype(interior_tag)::value;
-        const int x = x_lo + t - lane;
-        if ((t & 31) == 0 && j > 0) {
-          // boundary values of rows x_lo + t .. x_lo + t + 31: mine is row xr (fetched one batch
+        const int x0 = x_lo + (t - lane) * R;
+        if (((t * R) & 31) == 0 && j > 0) {
+          // boundary values of rows x_lo + tR .. x_lo + tR + 31: mine is row xr (fetched one batch
           // ahead); rows past pred_hi lie outside the band
-          const int xr = x_lo + t + lane;
+          const int xr = x_lo + t * R + lane;
           const bool need = (xr <= pred_hi);
           T bH = NINF;
           int bF = 0;
@@ -248,104 +257,153 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3_fill(const BsqFillArgs 
           nx_have = (xn <= pred_hi);
           if (nx_have) nx = Slab::load(slab + (long long)xn * Slab::EPR);
         }
-        T inH = __shfl_up_sync(FULL, lastH, 1);
-        int inG = __shfl_up_sync(FULL, lastG, 1);
-        const bool active = INT || ((t >= lane) && (x <= x_hi));
+        T inH[R];
+        int inG[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          inH[r] = __shfl_up_sync(FULL, lastH[r], 1);
+          inG[r] = __shfl_up_sync(FULL, lastG[r], 1);
+        }
         if (lane == 0) {
-          inH = NINF;
-          inG = 0;
-          if (j > 0) { inH = s_inH[wib][t & 31]; inG = s_inG[wib][t & 31]; }
-        }
-        // loads for the next two rows, off the dependency chain
-        const int o2 = INT ? (int)oseq[x + 1] : letter(x + 2);
-        T sign[K];
-        {
-          const int ob = o1 * L;
 #pragma unroll
-          for (int k = 0; k < K; k++) sign[k] = s_sub[ob + moff[k]];
-        }
-        if (active) {
-          const int e = x - y0 - dmin;   // cell k is inside the band iff 0 <= e - k <= W - 1
-          // B (_alnchoice_B, _pw_internals.c:182-197): B_LOCAL anywhere, B_OVERLAP on x==0 or y==0,
-          // B_GLOBAL at (0,0) only
-          const bool rowb = (BT == BSQ_B_LOCAL) || (!INT && BT == BSQ_B_OVERLAP && x == 0);
-          const T brest = rowb ? ZERO : NINF;
-          const T bfirst = (rowb || (!INT && y0 == 0 && (BT == BSQ_B_OVERLAP || x == 0))) ? ZERO : NINF;
-          T left = inH;
-          int gI = inG;
-          T diag = prev_in;
-          uint32_t cw = 0u;
-          if (rowb) {
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-              const bool inb = INT || (((unsigned)(e - k) <= (unsigned)Wm1) && (k < kv));
-              const T up = Hup[k];
-              T H;
-              int fD, fI;
-              uint32_t nib;
-              bsq_k3_cell<S, GOS, true>(up, gD[k], left, gI, diag, sig[k], k == 0 ? bfirst : brest, go, ge, inb,
-                                        H, fD, fI, nib);
-              cw |= nib << (4 * k);
-              gD[k] = fD; gI = fI; diag = up; left = H; Hup[k] = H;
-              if (BT == BSQ_B_LOCAL) { if (H > best[k < NB ? k : 0]) { best[k < NB ? k : 0] = H; bestx[k < NB ? k : 0] = x; } }
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-              const bool inb = INT || (((unsigned)(e - k) <= (unsigned)Wm1) && (k < kv));
-              const T up = Hup[k];
-              T H;
-              int fD, fI;
-              uint32_t nib;
-              if (k == 0 && !INT) bsq_k3_cell<S, GOS, true>(up, gD[k], left, gI, diag, sig[k], bfirst, go, ge, inb, H, fD, fI, nib);
-              else bsq_k3_cell<S, GOS, false>(up, gD[k], left, gI, diag, sig[k], ZERO, go, ge, inb, H, fD, fI, nib);
-              cw |= nib << (4 * k);
-              gD[k] = fD; gI = fI; diag = up; left = H; Hup[k] = H;
-            }
+          for (int r = 0; r < R; r++) {
+            inH[r] = NINF;
+            inG[r] = 0;
+            if (j > 0) { inH[r] = s_inH[wib][(t * R + r) & 31]; inG[r] = s_inG[wib][(t * R + r) & 31]; }
           }
-          lastH = left;
-          lastG = gI;
-          prow[(long long)t * G] = (PU)cw;
-          if (lane == G - 1 && has_succ) Slab::put(slab + (long long)x * Slab::EPR, left, gI != 0, tag_out);
-          // end cell, _banded_find_optimal (_pw_internals.c:364-414)
-          if (INT) {
-          } else if (BT == BSQ_B_GLOBAL) {
-            if (x == n && km >= 0 && km < K) {
+        }
+        // loads for the next two steps, off the dependency chain
+        int o2[R];
+        T sign[R][K];
 #pragma unroll
-              for (int k = 0; k < K; k++) if (k == km) { bs = Hup[k]; bk1 = n - m; bk2 = n; }
-            }
-          } else if (BT == BSQ_B_OVERLAP) {  // last cell of every diagonal, diagonals ascending, strict >
-            if (x == n) {
+        for (int r = 0; r < R; r++) {
+          o2[r] = INT ? (int)oseq[x0 + 2 * R + r - 1] : letter(x0 + 2 * R + r);
+          const int ob = o1[r] * L;
 #pragma unroll
-              for (int k = 0; k < K; k++) {
-                const T c = Hup[k];
-                if (c > NINF && bsq_better<T>(c, n - (y0 + k), 0, bs, bk1, bk2)) { bs = c; bk1 = n - (y0 + k); bk2 = 0; }
+          for (int k = 0; k < K; k++) sign[r][k] = s_sub[ob + moff[k]];
+        }
+        if (INT) {
+          constexpr bool HB = (BT == BSQ_B_LOCAL);
+          T left[R], diag[R];
+          int gI[R];
+          uint32_t cw[R];
+#pragma unroll
+          for (int r = 0; r < R; r++) { left[r] = inH[r]; gI[r] = inG[r]; diag[r] = r == 0 ? prev_in : inH[r - 1]; cw[r] = 0u; }
+#pragma unroll
+          for (int d = 0; d < R + K - 1; d++) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+              const int k = d - r;
+              if (k >= 0 && k < K) {
+                const T up = Hup[k];
+                T H;
+                int fD, fI;
+                uint32_t nib;
+                bsq_k3_cell<S, GOS, HB>(up, gD[k], left[r], gI[r], diag[r], sig[r][k], ZERO, go, ge, true, H, fD, fI, nib);
+                cw[r] |= nib << (4 * k);
+                gD[k] = fD; gI[r] = fI; diag[r] = up; left[r] = H; Hup[k] = H;
+                if (BT == BSQ_B_LOCAL) { if (H > best[k < NB ? k : 0]) { best[k < NB ? k : 0] = H; bestx[k < NB ? k : 0] = x0 + r; } }
               }
-            } else if (km >= 0 && km < K) {
-              T c = NINF;
+            }
+          }
 #pragma unroll
-              for (int k = 0; k < K; k++) if (k == km) c = Hup[k];
-              if (c > NINF && bsq_better<T>(c, x - m, 0, bs, bk1, bk2)) { bs = c; bk1 = x - m; bk2 = 0; }
+          for (int r = 0; r < R; r++) {
+            lastH[r] = left[r];
+            lastG[r] = gI[r];
+            prow[(long long)(t * R + r - lane * (R - 1)) * G] = (PU)cw[r];
+            if (lane == G - 1 && has_succ) Slab::put(slab + (long long)(x0 + r) * Slab::EPR, left[r], gI[r] != 0, tag_out);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            const int x = x0 + r;
+            const bool active = (t >= lane) && (x <= x_hi);
+            if (active) {
+              const int e = x - y0 - dmin;   // cell k is inside the band iff 0 <= e - k <= W - 1
+              // B (_alnchoice_B, _pw_internals.c:182-197): B_LOCAL anywhere, B_OVERLAP on x==0 or y==0,
+              // B_GLOBAL at (0,0) only
+              const bool rowb = (BT == BSQ_B_LOCAL) || (BT == BSQ_B_OVERLAP && x == 0);
+              const T brest = rowb ? ZERO : NINF;
+              const T bfirst = (rowb || (y0 == 0 && (BT == BSQ_B_OVERLAP || x == 0))) ? ZERO : NINF;
+              T left = inH[r];
+              int gI = inG[r];
+              T diag = r == 0 ? prev_in : inH[r - 1];
+              uint32_t cw = 0u;
+              if (rowb) {
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                  const bool inb = ((unsigned)(e - k) <= (unsigned)Wm1) && (k < kv);
+                  const T up = Hup[k];
+                  T H;
+                  int fD, fI;
+                  uint32_t nib;
+                  bsq_k3_cell<S, GOS, true>(up, gD[k], left, gI, diag, sig[r][k], k == 0 ? bfirst : brest, go, ge, inb,
+                                            H, fD, fI, nib);
+                  cw |= nib << (4 * k);
+                  gD[k] = fD; gI = fI; diag = up; left = H; Hup[k] = H;
+                  if (BT == BSQ_B_LOCAL) { if (H > best[k < NB ? k : 0]) { best[k < NB ? k : 0] = H; bestx[k < NB ? k : 0] = x; } }
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                  const bool inb = ((unsigned)(e - k) <= (unsigned)Wm1) && (k < kv);
+                  const T up = Hup[k];
+                  T H;
+                  int fD, fI;
+                  uint32_t nib;
+                  if (k == 0) bsq_k3_cell<S, GOS, true>(up, gD[k], left, gI, diag, sig[r][k], bfirst, go, ge, inb, H, fD, fI, nib);
+                  else bsq_k3_cell<S, GOS, false>(up, gD[k], left, gI, diag, sig[r][k], ZERO, go, ge, inb, H, fD, fI, nib);
+                  cw |= nib << (4 * k);
+                  gD[k] = fD; gI = fI; diag = up; left = H; Hup[k] = H;
+                }
+              }
+              lastH[r] = left;
+              lastG[r] = gI;
+              prow[(long long)(x - x_lo + lane) * G] = (PU)cw;
+              if (lane == G - 1 && has_succ) Slab::put(slab + (long long)x * Slab::EPR, left, gI != 0, tag_out);
+              // end cell, _banded_find_optimal (_pw_internals.c:364-414)
+              if (BT == BSQ_B_GLOBAL) {
+                if (x == n && km >= 0 && km < K) {
+#pragma unroll
+                  for (int k = 0; k < K; k++) if (k == km) { bs = Hup[k]; bk1 = n - m; bk2 = n; }
+                }
+              } else if (BT == BSQ_B_OVERLAP) {  // last cell of every diagonal, diagonals ascending, strict >
+                if (x == n) {
+#pragma unroll
+                  for (int k = 0; k < K; k++) {
+                    const T c = Hup[k];
+                    if (c > NINF && bsq_better<T>(c, n - (y0 + k), 0, bs, bk1, bk2)) { bs = c; bk1 = n - (y0 + k); bk2 = 0; }
+                  }
+                } else if (km >= 0 && km < K) {
+                  T c = NINF;
+#pragma unroll
+                  for (int k = 0; k < K; k++) if (k == km) c = Hup[k];
+                  if (c > NINF && bsq_better<T>(c, x - m, 0, bs, bk1, bk2)) { bs = c; bk1 = x - m; bk2 = 0; }
+                }
+              }
             }
           }
         }
-        if (INT || t >= lane) prev_in = inH;
-        o1 = o2;
+        if (INT || t >= lane) prev_in = inH[R - 1];
 #pragma unroll
-        for (int k = 0; k < K; k++) sig[k] = sign[k];
+        for (int r = 0; r < R; r++) {
+          o1[r] = o2[r];
+#pragma unroll
+          for (int k = 0; k < K; k++) sig[r][k] = sign[r][k];
+        }
       };
-      // interior steps [t_a, t_b]: with c0 = x_lo - (Y + dmin) >= 0, cell k of lane l sits at
-      // e - k = c0 + t - l (K + 1) - k in the band: >= 0 for lane 31, <= W - 1 for lane 0; lane 0
-      // (the lowest row) stays two rows clear of n, lane 31 is past row 0; the strip lies strictly
+      // interior steps [t_a, t_b]: with c0 = x_lo - (Y + dmin) >= 0, cell (r, k) of lane l sits at
+      // e - k = c0 + t R + r - l (R + K) - k in the band: >= 0 for lane 31, <= W - 1 for lane 0; lane 0
+      // (the lowest rows) stays two steps clear of n, lane 31 is past row 0; the strip lies strictly
       // left of column m; B_OVERLAP's column 0 (strip 0) is never interior
       int t_a = nsteps, t_b = -1;
       if (Y + BW - 1 < m && !(BT == BSQ_B_OVERLAP && j == 0)) {
         const int c0 = x_lo - (Y + dmin);
-        t_a = 31 * (K + 1) + K - 1 - c0;
+        t_a = (31 * (R + K) + K - 1 - c0 + R - 1) / R;
         t_a = t_a < 32 ? 32 : t_a;
-        t_b = Wm1 - c0;
-        t_b = (n - 2 - x_lo < t_b) ? n - 2 - x_lo : t_b;
-        t_b = (x_hi - x_lo < t_b) ? x_hi - x_lo : t_b;
+        t_b = (Wm1 - c0 - (R - 1)) / R;
+        t_b = ((n - 3 * R + 1 - x_lo) / R < t_b) ? (n - 3 * R + 1 - x_lo) / R : t_b;
+        t_b = ((x_hi - x_lo - (R - 1)) / R < t_b) ? (x_hi - x_lo - (R - 1)) / R : t_b;
         if (t_b < t_a) { t_a = nsteps; t_b = -1; }
       }
       {

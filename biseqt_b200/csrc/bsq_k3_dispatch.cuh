@@ -3,10 +3,17 @@
 #include "bsq_k3.cuh"
 #include "bsq_launch.h"
 
-template <class S, int K>
+// rows per time step of the three strip geometries (K = 2, 4, 8 columns per lane)
+#ifndef BSQ_K3_R0
+#define BSQ_K3_R0 1
+#define BSQ_K3_R1 4
+#define BSQ_K3_R2 2
+#endif
+
+template <class S, int K, int R>
 static int bsq_k3_variant(int btype, int gos, int grid, cudaStream_t st, const BsqFillArgs* A) {
 #define BSQ_K3_CASE(BT, GS) \
-  if (btype == BT && gos == GS) { BSQ_LAUNCH((bsq_k3_fill<S, K, BT, GS>), grid, BSQ_K3_THREADS, 0, st, *A); (void)st; return 0; }
+  if (btype == BT && gos == GS) { BSQ_LAUNCH((bsq_k3_fill<S, K, R, BT, GS>), grid, BSQ_K3_THREADS, 0, st, *A); (void)st; return 0; }
   BSQ_K3_CASE(0, -1) BSQ_K3_CASE(0, 0) BSQ_K3_CASE(0, 1)
   BSQ_K3_CASE(1, -1) BSQ_K3_CASE(1, 0) BSQ_K3_CASE(1, 1)
   BSQ_K3_CASE(2, -1) BSQ_K3_CASE(2, 0) BSQ_K3_CASE(2, 1)
@@ -17,9 +24,9 @@ static int bsq_k3_variant(int btype, int gos, int grid, cudaStream_t st, const B
 template <class S>
 static int bsq_k3_op_t(int cfg, int btype, int gos, int grid, cudaStream_t st, const BsqFillArgs* A) {
   switch (cfg) {
-    case 0: return bsq_k3_variant<S, 2>(btype, gos, grid, st, A);
-    case 1: return bsq_k3_variant<S, 4>(btype, gos, grid, st, A);
-    case 2: return bsq_k3_variant<S, 8>(btype, gos, grid, st, A);
+    case 0: return bsq_k3_variant<S, 2, BSQ_K3_R0>(btype, gos, grid, st, A);
+    case 1: return bsq_k3_variant<S, 4, BSQ_K3_R1>(btype, gos, grid, st, A);
+    case 2: return bsq_k3_variant<S, 8, BSQ_K3_R2>(btype, gos, grid, st, A);
   }
   return -1;
 }

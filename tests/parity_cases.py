@@ -148,8 +148,8 @@ def run_forced_k3(make_engine, seed, count=150, cfgs=(0, 1, 2), wide_len=700):
                 for typ in (0, 1, 2):
                     check_batch(eng, make_batch(rng, 9, 1, typ, 0, 150))
                 run_banded_interior(eng, seed=seed + 7 + cfg, length=330, npairs=2)
-                # bands wide enough (W = 341 >= 31 (K + 1) + K) for the strip kernel's ungated interior steps
-                run_very_wide_bands(eng, seed=seed + 11 + cfg, length=wide_len, radius=170, npairs=2)
+                # bands wide enough (W = 501 >= 31 (R + K) + R + K) for the strip kernel's ungated interior steps
+                run_very_wide_bands(eng, seed=seed + 11 + cfg, length=wide_len, radius=250, npairs=2)
             finally:
                 eng.close()
     finally:

@@ -334,7 +334,7 @@ inline int64_t uniform_min_pairs() {
 int pick_k3_cfg() {
   const char* e = getenv("BSQ_K3_CFG");  // tuning hook
   const int forced = e ? atoi(e) : -1;
-  return (forced >= 0 && forced < BSQ_K3_NCFG) ? forced : 1;  // K = 4 columns x R = 4 rows per lane and step: measured best on C5
+  return (forced >= 0 && forced < BSQ_K3_NCFG) ? forced : 1;  // K = 4 columns x R = 2 rows per lane and step: measured best on C5
 }
 
 // ---- planning -------------------------------------------------------------

@@ -6,7 +6,7 @@
 // rows per time step of the three strip geometries (K = 2, 4, 8 columns per lane)
 #ifndef BSQ_K3_R0
 #define BSQ_K3_R0 1
-#define BSQ_K3_R1 4
+#define BSQ_K3_R1 2
 #define BSQ_K3_R2 2
 #endif
 

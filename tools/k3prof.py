@@ -13,7 +13,7 @@ from biseqt_b200 import batch, _ffi  # noqa: E402
 def main():
     kind = sys.argv[1]
     _ffi.ffi.cdef('int bsq_debug_k3_res(bsq_batch* b, void* out, int64_t bytes);')
-    eng = batch.Engine(0, lib=_ffi.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'biseqt_b200', 'libbsqgpu_prof.so')))
+    eng = batch.Engine(0, lib=_ffi.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'biseqt_b200', os.environ.get('BSQ_PROF_LIB', 'libbsqgpu_prof.so'))))
     w = bw.make(kind, 1, seed=5)
     rb = eng.upload(w['codes'], w['o_off'], w['o_len'], w['m_off'], w['m_len'], w['mode'], w['type'],
                     w['subst'], w['go'], w['ge'], dmin=w.get('dmin'), dmax=w.get('dmax'))

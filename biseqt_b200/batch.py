@@ -19,6 +19,7 @@ OK, NO_ALIGNMENT, EMPTY, INIT_FAIL, REF_WOULD_ABORT, UNSUPPORTED = 0, 1, 2, 3, 4
 DTYPE_F64, DTYPE_I32, DTYPE_AUTO = 0, 1, -1
 DTYPE_I16X2 = 2
 DTYPE_NAMES = {0: 'f64', 1: 'i32', 2: 'i16x2'}
+ERR_CAPACITY = -4   # BSQ_ERR_CAPACITY (include/bsqgpu.h)
 
 
 def _ptr(a, ctype):
@@ -139,21 +140,35 @@ class Engine(object):
         status = arr('status', np.int32, N)
         tx_off = tx_buf = None
         cap = 0
+        def worst_case():   # a transcript has at most n + m ops
+            return int(o_len.sum(dtype=np.int64) + m_len.sum(dtype=np.int64))
         if transcripts:
-            cap = int(o_len.sum(dtype=np.int64) + m_len.sum(dtype=np.int64))
             tx_off = arr('tx_off', np.int64, N + 1)
             tx_buf = out.get('tx_buf')
-            if tx_buf is None or len(tx_buf) < cap:
+            if tx_buf is not None:
+                # the caller's buffer as it is: summing two million lengths costs a millisecond,
+                # and the library reports BSQ_ERR_CAPACITY if the transcripts do not fit
+                assert tx_buf.dtype == np.uint8
+                cap = len(tx_buf)
+            else:
+                cap = worst_case()
                 tx_buf = np.empty(max(cap, 1), dtype=np.uint8)
         total = ffi.new('int64_t*')
-        rc = self.lib.bsq_align_batch(
-            self.ctx, prm, N, _ptr(codes, 'uint8_t*'), len(codes),
-            _ptr(o_off, 'int64_t*'), _ptr(o_len, 'int32_t*'),
-            _ptr(m_off, 'int64_t*'), _ptr(m_len, 'int32_t*'),
-            _ptr(dmin, 'int32_t*'), _ptr(dmax, 'int32_t*'),
-            _ptr(score, 'double*'), _ptr(end_x, 'int32_t*'), _ptr(end_y, 'int32_t*'),
-            _ptr(start_x, 'int32_t*'), _ptr(start_y, 'int32_t*'), _ptr(status, 'int32_t*'),
-            _ptr(tx_off, 'int64_t*'), _ptr(tx_buf, 'char*'), cap, total)
+
+        def call():
+            return self.lib.bsq_align_batch(
+                self.ctx, prm, N, _ptr(codes, 'uint8_t*'), len(codes),
+                _ptr(o_off, 'int64_t*'), _ptr(o_len, 'int32_t*'),
+                _ptr(m_off, 'int64_t*'), _ptr(m_len, 'int32_t*'),
+                _ptr(dmin, 'int32_t*'), _ptr(dmax, 'int32_t*'),
+                _ptr(score, 'double*'), _ptr(end_x, 'int32_t*'), _ptr(end_y, 'int32_t*'),
+                _ptr(start_x, 'int32_t*'), _ptr(start_y, 'int32_t*'), _ptr(status, 'int32_t*'),
+                _ptr(tx_off, 'int64_t*'), _ptr(tx_buf, 'char*'), cap, total)
+        rc = call()
+        if rc == ERR_CAPACITY and transcripts and cap < worst_case():   # caller's buffer too small: use our own
+            cap = worst_case()
+            tx_buf = np.empty(max(cap, 1), dtype=np.uint8)
+            rc = call()
         if rc != 0:
             raise BsqError('bsq_align_batch failed (%d): %s' % (rc, self._err()))
         return BatchResult(score[:N], end_x[:N], end_y[:N], start_x[:N], start_y[:N],

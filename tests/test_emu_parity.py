@@ -3,6 +3,7 @@ against tests/simt_emu (fiber SIMT emulator) and driven through the real C ABI,
 checked against the oracle.  These are NOT the parity tests proper (those are
 tests/test_gpu_parity.py, -m gpu); they exist so that kernel bugs are found
 without spending GPU minutes."""
+import numpy as np
 import pytest
 
 from biseqt_b200 import batch
@@ -97,3 +98,26 @@ def test_emu_stats(emu_engine):
 
 def test_emu_big_ragged_plan(emu_lib):
     pc.run_big_ragged_plan(lambda: batch.Engine(0, lib=emu_lib), seed=99, npairs=66000, all_modes=False)
+
+
+def test_emu_caller_transcript_buffer(emu_engine):
+    """align(out={'tx_buf': ...}): the caller's buffer is used as it is when the transcripts fit;
+    one that is too small (BSQ_ERR_CAPACITY) is replaced by a worst-case buffer."""
+    rng = np.random.default_rng(5)
+    N = 6
+    o_len = np.full(N, 30, np.int32)
+    m_len = np.full(N, 30, np.int32)
+    tot = (o_len.astype(np.int64) + m_len).cumsum()
+    o_off = np.concatenate([[0], tot[:-1]]).astype(np.int64)
+    m_off = o_off + o_len
+    codes = rng.integers(0, 4, size=int(tot[-1]) + 16, dtype=np.uint8)
+    for i in range(N):
+        codes[m_off[i]:m_off[i] + 30] = codes[o_off[i]:o_off[i] + 30]
+    S = np.where(np.eye(4, dtype=bool), 1.0, -1.0)
+    args = (codes, o_off, o_len, m_off, m_len, 0, 0, S, -1.0, -1.0)
+    r0 = emu_engine.align(*args)
+    small, big = {'tx_buf': np.empty(10, np.uint8)}, {'tx_buf': np.empty(1000, np.uint8)}
+    r1 = emu_engine.align(*args, out=small)
+    r2 = emu_engine.align(*args, out=big)
+    assert r0.transcripts() == r1.transcripts() == r2.transcripts() == ['M' * 30] * N
+    assert r2.tx_buf is big['tx_buf'] and r1.tx_buf is not small['tx_buf']

@@ -511,6 +511,46 @@ def run_resident(eng, seed):
         rb.release()
 
 
+def run_block_plan_apis(make_engine, seed, npairs=14):
+    """The caller-order block planner behind the two-phase (solve / traceback) and the resident
+    (upload / run / fetch) entry points: ragged short reads, every table resident at once."""
+    os.environ['BSQ_PLAN_BLOCK'] = '3'
+    os.environ['BSQ_UNIFORM_MIN'] = '2'
+    try:
+        eng = make_engine()
+        try:
+            rng = np.random.default_rng(seed)
+            S = np.where(np.eye(4, dtype=bool), 2.0, -3.0)
+            probs = []
+            for i in range(npairs):
+                n, m = int(rng.integers(100, 141)), int(rng.integers(100, 141))
+                o = rng.integers(0, 4, size=n).astype(np.uint8)
+                t = rng.integers(0, 4, size=m).astype(np.uint8)
+                k = min(n, m)
+                t[:k] = o[:k]
+                t[rng.integers(0, m, size=m // 9)] = rng.integers(0, 4, size=m // 9)
+                probs.append(dict(origin=o, mutant=t, subst=S, go=-4.0, ge=-1.0, mode=0, type=1, diag_range=None))
+            codes, o_off, o_len, m_off, m_len = batch.pack_pairs([(p['origin'], p['mutant']) for p in probs])
+            sb = eng.solve(codes, o_off, o_len, m_off, m_len, 0, 1, S, -4.0, -1.0)
+            assert eng.timing()['dtype'] == batch.DTYPE_I16X2
+            r = sb.traceback()
+            for i, pr in enumerate(probs):
+                same_as(oracle_one(pr), r, i, what='two-phase, block plan %d' % i)
+            sb.release()
+            rb = eng.upload(codes, o_off, o_len, m_off, m_len, 0, 1, S, -4.0, -1.0)
+            rb.run()
+            rb.run()
+            r = rb.fetch()
+            for i, pr in enumerate(probs):
+                same_as(oracle_one(pr), r, i, what='resident, block plan %d' % i)
+            rb.release()
+        finally:
+            eng.close()
+    finally:
+        del os.environ['BSQ_PLAN_BLOCK']
+        del os.environ['BSQ_UNIFORM_MIN']
+
+
 def run_edge_cases(eng):
     E = np.zeros(0, np.uint8)
     A4 = np.array([0, 1, 2, 3, 0, 1], np.uint8)

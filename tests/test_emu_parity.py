@@ -121,3 +121,7 @@ def test_emu_caller_transcript_buffer(emu_engine):
     r2 = emu_engine.align(*args, out=big)
     assert r0.transcripts() == r1.transcripts() == r2.transcripts() == ['M' * 30] * N
     assert r2.tx_buf is big['tx_buf'] and r1.tx_buf is not small['tx_buf']
+
+
+def test_emu_block_plan_apis(emu_lib):
+    pc.run_block_plan_apis(lambda: batch.Engine(0, lib=emu_lib), seed=103)

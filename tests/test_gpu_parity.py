@@ -104,6 +104,10 @@ def test_gpu_ragged_reads():
     pc.run_ragged_reads(lambda: batch.Engine(0), seed=101, npairs=30000)
 
 
+def test_gpu_block_plan_apis():
+    pc.run_block_plan_apis(lambda: batch.Engine(0), seed=103, npairs=50)
+
+
 def test_gpu_uniform_batches():
     pc.run_uniform_batches(lambda: batch.Engine(0), seed=83)
 

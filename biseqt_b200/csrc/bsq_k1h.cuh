@@ -51,6 +51,12 @@ static inline unsigned bsq_vminu2(unsigned a, unsigned b) {
   auto f = [](unsigned x, unsigned y) { return x < y ? x : y; };
   return (f(a >> 16, b >> 16) << 16) | f(a & 0xffffu, b & 0xffffu);
 }
+static inline unsigned bsq_perm(unsigned a, unsigned b, unsigned sel) {   // __byte_perm
+  const unsigned long long v = ((unsigned long long)b << 32) | a;
+  unsigned r = 0;
+  for (int i = 0; i < 4; i++) r |= (unsigned)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xffu) << (8 * i);
+  return r;
+}
 static inline unsigned bsq_vbmax2(unsigned a, unsigned b, bool* ph, bool* pl) {  // max, pred = (a >= b)
   *pl = bsq_h2lo(a) >= bsq_h2lo(b);
   *ph = bsq_h2hi(a) >= bsq_h2hi(b);
@@ -65,6 +71,7 @@ __device__ __forceinline__ unsigned bsq_vmax3relu2(unsigned a, unsigned b, unsig
 __device__ __forceinline__ unsigned bsq_vaddminu2(unsigned a, unsigned b, unsigned c) { return __viaddmin_u16x2(a, b, c); }
 __device__ __forceinline__ unsigned bsq_vminu2(unsigned a, unsigned b) { return __vminu2(a, b); }
 __device__ __forceinline__ unsigned bsq_vbmax2(unsigned a, unsigned b, bool* ph, bool* pl) { return __vibmax_s16x2(a, b, ph, pl); }
+__device__ __forceinline__ unsigned bsq_perm(unsigned a, unsigned b, unsigned sel) { return __byte_perm(a, b, sel); }
 #endif
 
 // (G, K) is one of K1's single-pass geometries: (8, 19) for m <= 151, (16, 16) for m <= 255
@@ -173,9 +180,10 @@ __global__ void __launch_bounds__(128) bsq_k1h_fill(const BsqFillArgs A) {
         unsigned left = inG2, nI2 = inN2, diag = prev_in;
         const unsigned before = best2;
         uint32_t wa[WPL], wb[WPL];
+        constexpr int NACC = (K + 3) / 4;
+        unsigned acc[NACC];                        // 4 cells' not-in-tie-set nibbles per halfword (A low, B high)
 #pragma unroll
-        for (int w = 0; w < WPL; w++) { wa[w] = 0u; wb[w] = 0u; }
-        unsigned acc = 0u;                         // 4 cells' not-in-tie-set nibbles per halfword
+        for (int q = 0; q < NACC; q++) acc[q] = 0u;
 #pragma unroll
         for (int k = 0; k < K; k++) {
           const unsigned up = G2[k];
@@ -193,12 +201,14 @@ __global__ void __launch_bounds__(128) bsq_k1h_fill(const BsqFillArgs A) {
           const unsigned ni = bsq_vaddminu2(I2, mh2, ONE2);
           const unsigned nm = bsq_vaddminu2(M2, mh2, ONE2);
           const unsigned nb = bsq_vminu2(mh2, ONE2);            // B (score 0) ties iff h == 0
-          acc += (nb + 2u * nd + 4u * ni + 8u * nm) << (4 * (k & 3));
-          if ((k & 3) == 3 || k == K - 1) {                     // move 4 nibbles per problem into the row words
-            const int sh = 16 * ((k >> 2) & 1);
-            wa[k >> 3] |= (acc & 0xffffu) << sh;
-            wb[k >> 3] |= (acc >> 16) << sh;
-            acc = 0u;
+          // four multiply-adds into the accumulator (the sum first and one shift would be five
+          // instructions: the doubling of nd gets its own)
+          {
+            const unsigned sh = 4u * (unsigned)(k & 3);   // k is an unrolled loop index: a constant
+            acc[k >> 2] = nb * (1u << sh) + acc[k >> 2];
+            acc[k >> 2] = nd * (2u << sh) + acc[k >> 2];
+            acc[k >> 2] = ni * (4u << sh) + acc[k >> 2];
+            acc[k >> 2] = nm * (8u << sh) + acc[k >> 2];
           }
           nD2[k] = nd;
           nI2 = ni;
@@ -214,6 +224,14 @@ __global__ void __launch_bounds__(128) bsq_k1h_fill(const BsqFillArgs A) {
         lastN2 = nI2;
         if ((best2 ^ before) & 0xffffu) xA = x;
         if ((best2 ^ before) >> 16) xB = x;
+        // a row word holds 8 cells of ONE problem: the low halves of two accumulators for A, the
+        // high halves for B (one byte permute each)
+#pragma unroll
+        for (int w = 0; w < WPL; w++) {
+          const unsigned lo = acc[2 * w], hi = (2 * w + 1 < NACC) ? acc[2 * w + 1] : 0u;
+          wa[w] = bsq_perm(lo, hi, 0x5410u);
+          wb[w] = bsq_perm(lo, hi, 0x7632u);
+        }
 #pragma unroll
         for (int w = 0; w < WPL; w++) {
           const uint32_t full = (w == WPL - 1 && (K & 7)) ? ((1u << (4 * (K & 7))) - 1u) : 0xffffffffu;

@@ -380,7 +380,7 @@ def main():
             # DRAM bytes (read + write) of ONE fill launch, from the ncu --set full capture of this
             # kernel on this workload (profiles/r01_k1h_final_ncu.txt); algorithmic pointer bytes of
             # a launch (125k pairs x 0.5 B/cell) are 1.43e9
-            'traffic': 2.474e9 if (kind == 'c2_int' and npairs == 1000000 and m['dtype'] == 'i16x2') else None,
+            'traffic': 2.468e9 if (kind == 'c2_int' and npairs == 1000000 and m['dtype'] == 'i16x2') else None,
             'ops_per_cell': opc, 'pipe': which,
             'note': 'achieved = cells x algorithmic ops/cell / fill-kernel time (CUDA events on the library stream); '
                     'peak = %s issue rate measured in this run (bsq_microbench)' % {'IADD': 'add.s32', 'VADD2': 'packed 16-bit add (VIADD.16x2, two adds per instruction)', 'DADD': 'add.f64'}[which],

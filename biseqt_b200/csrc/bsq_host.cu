@@ -480,7 +480,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   P.pairs = nullptr;
   const bool force_k3 = getenv("BSQ_FORCE_K3") != nullptr;  // test hook: K3 for every band
   const int k3_cfg = pick_k3_cfg();
-  // K1h (two equal-shape short problems per lane, packed 16-bit arithmetic): what the scores and
+  // K1h (two short problems per lane group, packed 16-bit arithmetic): what the scores and
   // the alignment type must satisfy; the shape conditions are per pair (PlanItem.lo for STD)
   double duo_maxabs = std::fabs(prm->go) + std::fabs(prm->ge);
   for (double v : P.subst) duo_maxabs = std::max(duo_maxabs, std::fabs(v));

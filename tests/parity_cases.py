@@ -239,7 +239,7 @@ def run_duo_short_reads(make_engine, seed, npairs=37):
                     assert np.array_equal(r.score, r1.score) and np.array_equal(r.tx_off, r1.tx_off)
                     assert np.array_equal(r.tx_buf[:r.tx_off[-1]], r1.tx_buf[:r1.tx_off[-1]])
             # ragged batches: a handful of shapes, repeated an odd or even number of times, plus
-            # pairs the packed kernel cannot take (two passes); neighbours of one shape share a
+            # pairs the packed kernel cannot take (two passes); neighbours in processing order share a
             # lane group.  Trials 3.. run the planner's multi-threaded passes (BSQ_PAR_GRAIN).
             for trial in range(6):
                 if trial >= 3:

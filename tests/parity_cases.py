@@ -544,6 +544,19 @@ def run_block_plan_apis(make_engine, seed, npairs=14):
             for i, pr in enumerate(probs):
                 same_as(oracle_one(pr), r, i, what='resident, block plan %d' % i)
             rb.release()
+            # degenerate shapes (empty origin and / or mutant) next to ordinary ones in one lane group
+            probs = []
+            for i in range(3 * npairs):
+                n, m = int(rng.integers(0, 7)), int(rng.integers(0, 7))
+                o = rng.integers(0, 4, size=n).astype(np.uint8)
+                t = rng.integers(0, 4, size=m).astype(np.uint8)
+                if i % 2:
+                    k = min(n, m)
+                    t[:k] = o[:k]
+                probs.append(dict(origin=o, mutant=t, subst=S, go=-4.0 if i < npairs else 0.0, ge=-1.0, mode=0, type=1, diag_range=None))
+            for part in (probs[:npairs], probs[npairs:]):
+                check_batch(eng, part)
+                assert eng.timing()['dtype'] == batch.DTYPE_I16X2
         finally:
             eng.close()
     finally:

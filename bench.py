@@ -201,7 +201,10 @@ def run_reference_arm(args, rank, world, emit):
         'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * float(np.mean([t for t, _ in times])), 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': w['desc'], 'sample_pairs_per_step': int(len(w['o_len']))},
+        # the GPU arm's workload; each step of this arm times a bounded sample of it
+        'config': {'workload': w['desc'].replace('%d pairs' % len(w['o_len']), '%d pairs' % (args.pairs or WORKLOAD_PAIRS[kind]), 1),
+                   'pairs_per_gpu': int(args.pairs or WORKLOAD_PAIRS[kind]), 'seed': 2,
+                   'sample_pairs_per_step': int(len(w['o_len']))},
         'cpu_baseline': {'value': val, 'unit': 'GCUPS', 'cores': last['cores'], 'kind': last['kind'],
                          'sample': last['sample']},
         'pairs_per_s': last['pairs_per_s'],

@@ -34,7 +34,24 @@ if ROOT not in sys.path:
 import bench_workloads as bw  # noqa: E402
 
 WORKLOAD_PAIRS = {'c2_int': 1000000, 'c2_logodds': 1000000, 'c3_int': 32768, 'c3_logodds': 32768,
+                  'c3_blocal_int': 32768, 'c3_blocal_logodds': 32768,
                   'c4_int': 4096, 'c1': 1, 'c2w_int': 400000, 'c5_int': 1, 'c5_logodds': 1, 'c5s_int': 1, 'c5s_logodds': 1}
+
+
+# which SM pipes each microbenchmarked rate (bsq_microbench, csrc/bsq_microbench.cu) spans; the
+# rates themselves are measured in every run and stored in profiles/ALU_PEAKS.json
+PIPE_NOTES = {
+    'DADD': 'add.rn.f64 -> DADD, FP64 pipe only (64 lanes/clk/SM)',
+    'DMAX': 'setp.gt.f64 + selp.f64 -> DSETP (FP64 pipe) + 2 SEL (ALU pipe); counted as one op',
+    'DSETP': 'setp.eq.f64 + predicated LOP3 -> FP64 pipe + ALU pipe; counted as one op',
+    'IADD': 'add.s32 -> ptxas alternates IADD3 (ALU pipe) and IMAD (FMA pipe): a TWO-pipe rate; '
+            'the ALU pipe alone is the VIMAX3 figure',
+    'VIMAX3': 'VIMNMX3.S32 (DPX), ALU pipe only',
+    'VIADDMAX': 'VIADDMNMX.S32 (DPX), ALU pipe only',
+    'VADD2': 'VIADD.16x2, ALU pipe only; counted as two halfword adds per instruction',
+    'SHFL': 'shfl.sync.up.b32, one per warp instruction counted as 32 thread-ops',
+    'LDS64': 'ld.shared.b64, conflict free',
+}
 
 
 def ops_per_cell(go):
@@ -112,29 +129,47 @@ class ClockSampler(object):
 # CPU reference: the unmodified pwlib through oracle/pwref.py, one process per core
 # ---------------------------------------------------------------------------
 def _cpu_worker(task):
-    kind, w, idx = task
+    """Aligns pairs `idx` of workload w with the reference library (or the oracle port) and
+    returns (cells, busy seconds, pairs, results) -- results[i] = (status, score, end, start,
+    transcript) of every pair, for the per-pair parity verdict against the GPU arm."""
+    kind, w, idx, variant, keep = task
     from oracle import pwref, lean
     use_ref = (kind == 'reference')
     subst = w['subst'].tolist()
-    cells, busy = 0, 0.0
+    cells, busy, results = 0, 0.0, []
     for i in idx:
         o = w['codes'][w['o_off'][i]:w['o_off'][i] + w['o_len'][i]]
         t = w['codes'][w['m_off'][i]:w['m_off'][i] + w['m_len'][i]]
         dr = None if w['mode'] == 0 else (int(w['dmin'][i]), int(w['dmax'][i]))
         if use_ref:
-            P = pwref.Problem(o, t, subst, w['go'], w['ge'], w['mode'], w['type'], dr)
+            P = pwref.Problem(o, t, subst, w['go'], w['ge'], w['mode'], w['type'], dr, variant=variant)
+            res = [pwref.INIT_FAIL, None, None, None, None]
             t0 = time.perf_counter()     # init + solve + traceback + free (BASELINE.md section 3)
             if P.init() == 0:
-                if P.solve() is not None:
-                    P.traceback()
+                sc = P.solve()
+                tb = None
+                if sc is not None:
+                    # pw.c:132-134 exit(1)s when the path is all indels from (0,0); such a pair
+                    # (never produced by these generators) is classified, not run
+                    end = P.end_xy()
+                    if end == (0, 0) or 0 in (len(o), len(t)):
+                        res = [pwref.REF_WOULD_ABORT, sc, end, None, None]
+                    else:
+                        tb = P.traceback()
+                        res = [pwref.OK, sc, end, (tb[1], tb[2]), tb[3]] if tb is not None else [pwref.EMPTY, sc, end, None, None]
+                else:
+                    res = [pwref.NO_ALIGNMENT, None, None, None, None]
                 P.free()
             busy += time.perf_counter() - t0
         else:
             t0 = time.perf_counter()
-            lean.align(o, t, w['subst'], w['go'], w['ge'], w['mode'], w['type'], dr)
+            a = lean.align(o, t, w['subst'], w['go'], w['ge'], w['mode'], w['type'], dr)
             busy += time.perf_counter() - t0
+            res = [a['status'], a['score'], a['end'], a['start'], a['transcript']]
+        if keep:
+            results.append((int(i), res))
         cells += bw_cells_one(w, i)
-    return cells, busy, len(idx)
+    return cells, busy, len(idx), results
 
 
 def bw_cells_one(w, i):
@@ -145,11 +180,32 @@ def bw_cells_one(w, i):
     return lean.count_cells(1, n, m, int(w['dmin'][i]), int(w['dmax'][i]))
 
 
-def cpu_reference_run(w, pairs_per_core, cores=None, pool=None):
+def parity_verdict(w, results, r):
+    """the reference's (status, score, end, start, transcript) for the very
+    pairs the CPU leg just timed against the GPU arm's result r (BatchResult) on the same pairs."""
+    mism, worst = 0, []
+    for i, (st, sc, end, start, tx) in results:
+        ok = int(r.status[i]) == st
+        if ok and st in (0, 2, 4):
+            ok = float(r.score[i]) == sc and (int(r.end_x[i]), int(r.end_y[i])) == tuple(end)
+        if ok and st == 0:
+            ok = r.transcript(i) == tx and (int(r.start_x[i]), int(r.start_y[i])) == tuple(start)
+        if not ok:
+            mism += 1
+            if len(worst) < 5:
+                worst.append(int(i))
+    out = {'pairs': len(results), 'mismatches': mism,
+           'compared': 'status, score (bit-exact double), end cell, start cell, transcript'}
+    if worst:
+        out['first_mismatching_pairs'] = worst
+    return out
+
+
+def cpu_reference_run(w, pairs_per_core, cores=None, pool=None, variant='O2', keep=False):
     """Aligns a bounded sample on all host cores; returns dict(value GCUPS, ...)."""
     from oracle import pwref
     import multiprocessing as mp
-    kind = 'reference' if pwref.available() else 'port'
+    kind = 'reference' if pwref.available(variant) else 'port'
     cores = cores or (os.cpu_count() or 1)
     N = len(w['o_len'])
     total = min(N, pairs_per_core * cores)
@@ -159,7 +215,7 @@ def cpu_reference_run(w, pairs_per_core, cores=None, pool=None):
         slim['dmin'], slim['dmax'] = w['dmin'], w['dmax']
     hi = int(max(w['o_off'][total - 1] + w['o_len'][total - 1], w['m_off'][total - 1] + w['m_len'][total - 1]))
     slim['codes'] = w['codes'][:hi]
-    tasks = [(kind, slim, idx[c::cores]) for c in range(cores)]
+    tasks = [(kind, slim, idx[c::cores], variant, keep) for c in range(cores)]
     own = pool is None
     if own:
         pool = mp.get_context('fork').Pool(cores)
@@ -173,17 +229,29 @@ def cpu_reference_run(w, pairs_per_core, cores=None, pool=None):
     # the timed regions (struct construction in Python is excluded)
     rate = sum(r[0] / r[1] for r in res if r[1] > 0)
     return {'value': rate / 1e9, 'unit': 'GCUPS', 'cores': cores, 'kind': kind,
-            'sample': '%d of the workload\'s pairs (%d per core), init+solve+traceback+free per pair, -O2 build'
-                      % (total, pairs_per_core),
-            'pairs_per_s': sum(r[2] / r[1] for r in res if r[1] > 0), 'wall_s': wall, 'cells': cells}
+            'sample': '%d of the workload\'s pairs (%d per core), init+solve+traceback+free per pair, %s build'
+                      % (total, pairs_per_core, '-O2' if variant == 'O2' else 'reference-flags (-g, no -O: Makefile:1)'),
+            'pairs_per_s': sum(r[2] / r[1] for r in res if r[1] > 0), 'wall_s': wall, 'cells': cells,
+            'results': [x for r in res for x in r[3]]}
+
+
+def cpu_sample_per_core(kind, cores):
+    """Pairs per host core of the bounded CPU sample: C2 1250 per core (= BASELINE.md section 3's
+    2e4 pairs on a 16-core box, ~2.5 s per step), the long-pair configs one pair per core."""
+    return 1250 if kind.startswith('c2') else 1
+
+
+def bench_config(desc, pairs_per_gpu):
+    """`config` of the JSON line: identical (keys and values) for both arms."""
+    return {'workload': desc, 'pairs_per_gpu': int(pairs_per_gpu), 'seed': 2}
 
 
 def run_reference_arm(args, rank, world, emit):
     if rank != 0:
         return
     kind = args.workload
-    per_core = {'c2_int': 300, 'c2_logodds': 300}.get(kind, 1)
     cores = os.cpu_count() or 1
+    per_core = cpu_sample_per_core(kind, cores)
     npairs = max(per_core * cores, 64)
     w = bw.make(kind, min(npairs, WORKLOAD_PAIRS[kind]), seed=2)
     import multiprocessing as mp
@@ -201,10 +269,11 @@ def run_reference_arm(args, rank, world, emit):
         'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * float(np.mean([t for t, _ in times])), 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        # the GPU arm's workload; each step of this arm times a bounded sample of it
-        'config': {'workload': w['desc'].replace('%d pairs' % len(w['o_len']), '%d pairs' % (args.pairs or WORKLOAD_PAIRS[kind]), 1),
-                   'pairs_per_gpu': int(args.pairs or WORKLOAD_PAIRS[kind]), 'seed': 2,
-                   'sample_pairs_per_step': int(len(w['o_len']))},
+        # the GPU arm's workload (same keys and values as its `config`); each step of this arm times
+        # a bounded sample of it (`sample_pairs_per_step`)
+        'config': bench_config(w['desc'].replace('%d pairs' % len(w['o_len']), '%d pairs' % (args.pairs or WORKLOAD_PAIRS[kind]), 1),
+                               int(args.pairs or WORKLOAD_PAIRS[kind])),
+        'sample_pairs_per_step': int(len(w['o_len'])),
         'cpu_baseline': {'value': val, 'unit': 'GCUPS', 'cores': last['cores'], 'kind': last['kind'],
                          'sample': last['sample']},
         'pairs_per_s': last['pairs_per_s'],
@@ -279,6 +348,7 @@ def measure(eng, w, steps, warmup, sampler_gpu, do_e2e=True):
                                    'fill_kernels': tt['fill_ms'], 'chunks': tt['chunks']}
         out['h2d'], out['d2h'] = h2d, d2h
         out['ok_frac'] = float((r.status == 0).mean())
+        out['result'] = r          # the last timed call's output (pinned buffers), for the parity verdict
         out['launches'] = launches
         barrier()
     return out
@@ -368,6 +438,16 @@ def main():
             pipe = {k: eng.microbench(k) for k in ('DADD', 'DMAX', 'DSETP', 'IADD', 'VADD2', 'VIMAX3', 'VIADDMAX', 'SHFL', 'LDS64')}
         except Exception as e:   # never hide the bench line behind a microbenchmark problem
             pipe = {'error': str(e)}
+        if 'error' not in pipe:
+            try:   # stored next to the other measured peaks (gpurun_out/ travels back; copied to profiles/)
+                os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+                with open(os.path.join(ROOT, 'gpurun_out', 'ALU_PEAKS.json'), 'w') as f:
+                    json.dump({'unit': 'thread-ops/s, whole GPU', 'how': 'bsq_microbench: 8 independent chains per thread, '
+                               '8 x 256 threads per SM, best of 3 after a warm-up, CUDA events',
+                               'sm_clock_mhz_during_bench': m['clocks'].get('sm_mhz'),
+                               'rates': pipe, 'pipes': PIPE_NOTES}, f, indent=1)
+            except Exception:
+                pass
         fill_s = m['fill_ms'] * 1e-3
         achieved = m['cells'] * args.steps * opc / fill_s / 1e9
         peak = pipe.get(which, 0.0) / 1e9 if 'error' not in pipe else None
@@ -388,6 +468,7 @@ def main():
             'note': 'achieved = cells x algorithmic ops/cell / fill-kernel time (CUDA events on the library stream); '
                     'peak = %s issue rate measured in this run (bsq_microbench)' % {'IADD': 'add.s32', 'VADD2': 'packed 16-bit add (VIADD.16x2, two adds per instruction)', 'DADD': 'add.f64'}[which],
             'pipe_rates_gops': {k: v / 1e9 for k, v in pipe.items()} if 'error' not in pipe else pipe,
+            'pipe_notes': {which: PIPE_NOTES[which]},
             'hbm': {'achieved': m['ptr_bytes'] * args.steps / fill_s / 1e9, 'peak': hbm_peak,
                     'unit': 'GB/s', 'frac': m['ptr_bytes'] * args.steps / fill_s / 1e9 / hbm_peak,
                     'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback',
@@ -397,10 +478,10 @@ def main():
             'metric': 'GCUPS', 'value': value, 'unit': 'GCUPS', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': res_ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': m['dtype'], 'data': 'synthetic',
-            'config': {'workload': w['desc'], 'pairs_per_gpu': npairs, 'seed': 2,
-                       'l2': 'inputs larger than L2 (%.0f MB of sequences + %.1f GB of pointer tables per step)'
-                             % (len(w['codes']) / 1e6, m['ptr_bytes'] / 1e9),
-                       'timed': 'fill + traceback + transcript packing, inputs/outputs resident in HBM'},
+            'config': bench_config(w['desc'], npairs),
+            'l2': 'inputs larger than L2 (%.0f MB of sequences + %.1f GB of pointer tables per step)'
+                  % (len(w['codes']) / 1e6, m['ptr_bytes'] / 1e9),
+            'timed': 'fill + traceback + transcript packing, inputs/outputs resident in HBM',
             'pairs_per_s': pairs_all * args.steps / (res_ms * 1e-3),
             'fill_only_gcups': cells_all * args.steps / (allreduce(m['fill_ms'], 'MAX') * 1e-3) / 1e9 if world == 1 else None,
             'clocks': m['clocks'],
@@ -409,20 +490,27 @@ def main():
                     'note': 'bsq_align_batch from pinned host arrays: plan + H2D + fill + traceback + pack + D2H'},
             'gpu_launches': int(launches),
             'roofline': roofline,
-            'parity_spotcheck': {'status_ok_fraction': m['ok_frac']},
+            'roofline_frac_solve_plus_traceback': (m['cells'] * args.steps * opc / (m['resident_ms'] * 1e-3) / 1e9 / peak) if peak else None,
+            'status_ok_fraction': m['ok_frac'],
         }
 
     # secondary workloads (rank 0, single GPU): f64 path and the banded kernels
     if rank == 0 and world == 1 and not args.no_extras:
         extras = {}
         made = {}
-        for k2 in ('c2_logodds', 'c3_int', 'c3_logodds', 'c4_int', 'c5_int', 'c1'):
+        for k2 in ('c2_logodds', 'c3_int', 'c3_logodds', 'c3_blocal_int', 'c3_blocal_logodds', 'c4_int', 'c5_int', 'c1'):
             n2 = WORKLOAD_PAIRS[k2] if k2 != 'c2_logodds' else min(npairs, 250000)
             try:
-                if k2 == 'c3_logodds' and 'c3_int' in made:   # same pairs, log-odds scores
+                if k2 in ('c3_logodds', 'c3_blocal_int', 'c3_blocal_logodds') and 'c3_int' in made:
+                    # the same pairs and bands as c3_int; other scores and / or banded LOCAL
                     w2 = dict(made['c3_int'])
-                    S3, go3, ge3 = bw.st.log_odds_scores(4, 0.03, 0.06, 0.12)
-                    w2.update(kind=k2, subst=S3, go=go3, ge=ge3, desc=w2['desc'] + ' (log-odds scores)')
+                    if k2.endswith('logodds'):
+                        S3, go3, ge3 = bw.st.log_odds_scores(4, 0.03, 0.06, 0.12)
+                        w2.update(subst=S3, go=go3, ge=ge3)
+                    if 'blocal' in k2:
+                        w2.update(type=bw.B_LOCAL)
+                    w2.update(kind=k2, desc=w2['desc'].replace('B_OVERLAP', 'B_LOCAL' if 'blocal' in k2 else 'B_OVERLAP')
+                              .replace('int +2/-3 go0 ge-2', 'log-odds' if k2.endswith('logodds') else 'int +2/-3 go0 ge-2'))
                 else:
                     w2 = bw.make(k2, n2, seed=3)
                     made[k2] = w2
@@ -437,6 +525,10 @@ def main():
                               'fill_only_gcups': m2['cells'] * st2 / (m2['fill_ms'] * 1e-3) / 1e9,
                               'e2e_gcups': m2['cells'] * st2 / m2['e2e_s'] / 1e9,
                               'roofline_frac': ach / pk if pk else None, 'ops_per_cell': opc2,
+                              # SURVEY.md 8(d) defines the metric on solve + traceback time: the same
+                              # fraction with the whole resident step (fill + traceback + packing) as time
+                              'roofline_frac_solve_plus_traceback':
+                                  (m2['cells'] * st2 * opc2 / (m2['resident_ms'] * 1e-3) / 1e9) / pk if pk else None,
                               'status_ok_fraction': m2['ok_frac'], 'chunks': m2['chunks'],
                               'e2e_breakdown_ms': m2.get('e2e_breakdown_ms')}
             except Exception as e:
@@ -445,9 +537,17 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            per_core = 300 if kind.startswith('c2') else 1
-            line['cpu_baseline'] = {k: v for k, v in cpu_reference_run(w, per_core).items()
+            cores = os.cpu_count() or 1
+            per_core = cpu_sample_per_core(kind, cores)
+            cpu = cpu_reference_run(w, per_core, cores, keep=True)
+            line['cpu_baseline'] = {k: v for k, v in cpu.items()
                                     if k in ('value', 'unit', 'cores', 'kind', 'sample', 'pairs_per_s')}
+            # the reference's verdict on the very pairs it just timed vs the GPU arm's e2e output
+            line['parity_spotcheck'] = parity_verdict(w, cpu['results'], m['result'])
+            from oracle import pwref
+            if pwref.available('g'):   # the reference's own build flags (Makefile:1: -g, no -O), quarter sample
+                cg = cpu_reference_run(w, max(1, per_core // 4), cores, variant='g')
+                line['cpu_baseline']['reference_flags_build'] = {k: cg[k] for k in ('value', 'unit', 'cores', 'sample', 'pairs_per_s')}
         except Exception as e:
             line['cpu_baseline'] = {'error': str(e)}
     if rank == 0:

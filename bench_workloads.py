@@ -63,8 +63,9 @@ def make(kind, npairs, seed):
         return dict(kind=kind, mode=STD_MODE, type=LOCAL, subst=S, go=go, ge=ge, codes=codes,
                     o_off=o_off, o_len=o_len, m_off=m_off, m_len=m_len,
                     desc='%d pairs %dx%d bp, STD LOCAL, %s' % (npairs, n, n, 'int +1/-3 go-5 ge-2' if kind != 'c2_logodds' else 'log-odds'))
-    if kind in ('c3_int', 'c3_logodds', 'c4_int'):
-        # configs[2] / [3]: long noisy reads, banded overlap alignment
+    if kind in ('c3_int', 'c3_logodds', 'c4_int', 'c3_blocal_int', 'c3_blocal_logodds'):
+        # configs[2] / [3]: long noisy reads, banded overlap alignment (c3_blocal_*: the same pairs
+        # and bands as config 3 aligned B_LOCAL, the north star's "batched banded local alignment")
         if kind == 'c4_int':
             n, maxoff, gmax, sens = 50000, 25000, 0.15, 0.99
         else:
@@ -82,13 +83,17 @@ def make(kind, npairs, seed):
             r = np.full(npairs, 64)
         dmin = np.maximum(off - r, -mlen).astype(np.int32)
         dmax = np.minimum(off + r, n).astype(np.int32)
-        if kind == 'c3_logodds':
+        if kind.endswith('logodds'):
             S, go, ge = st.log_odds_scores(L, 0.03, 0.06, 0.12)
         else:
             S, go, ge = int_scores(2, -3), 0.0, -2.0
-        return dict(kind=kind, mode=BANDED_MODE, type=B_OVERLAP, subst=S, go=go, ge=ge, codes=codes,
+        btype = B_LOCAL if 'blocal' in kind else B_OVERLAP
+        return dict(kind=kind, mode=BANDED_MODE, type=btype, subst=S, go=go, ge=ge, codes=codes,
                     o_off=o_off, o_len=o_len, m_off=m_off, m_len=m_len, dmin=dmin, dmax=dmax,
-                    desc='%d pairs ~%d bp, B_OVERLAP, radius %s' % (npairs, n, '64' if kind != 'c4_int' else 'band_radius(K,.15,.99)~%d' % int(np.median(r))))
+                    desc='%d pairs ~%d bp, %s, radius %s, %s' % (
+                        npairs, n, 'B_LOCAL' if btype == B_LOCAL else 'B_OVERLAP',
+                        '64' if kind != 'c4_int' else 'band_radius(K,.15,.99)~%d' % int(np.median(r)),
+                        'log-odds' if kind.endswith('logodds') else 'int +2/-3 go0 ge-2'))
     if kind in ('c5_int', 'c5_logodds', 'c5s_int', 'c5s_logodds'):
         # configs[4]: `npairs` pairs of 1 Mb x ~1 Mb, B_GLOBAL, radius 2048 (c5s_*: 64 kb, the
         # size the CPU oracle finishes in seconds).  The mutant is made piecewise (1000-letter

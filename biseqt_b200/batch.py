@@ -89,7 +89,12 @@ class Engine(object):
         self.close()
 
     def _err(self):
-        return ffi.string(self.lib.bsq_last_error(self.ctx)).decode()
+        ctx = self.ctx if self.ctx is not None else ffi.NULL   # closed engine: the thread's last error
+        return ffi.string(self.lib.bsq_last_error(ctx)).decode() or 'engine is closed'
+
+    def reload_hooks(self):
+        """Re-read the BSQ_* environment hooks (they are read once, when the engine is created)."""
+        self.lib.bsq_reload_hooks(self.ctx)
 
     def pinned_empty(self, n, dtype):
         """1-D numpy array in page-locked host memory (full-speed H2D/D2H)."""

@@ -90,6 +90,7 @@ struct BsqFillArgs {
   int* out_ey;
   int* out_status;
   int* counter;          // dynamic work queue head
+  const int* bad;        // != 0: bsq_check_codes found a letter >= L; the kernel must not run
   // STD multi-pass boundary column scratch, one slab per resident group
   double* col_h;         // (also used for int scores, stored as double-sized slots)
   uint8_t* col_f;
@@ -121,4 +122,5 @@ struct BsqTraceArgs {
   int* txlen;
   char* slots;           // transcripts, right-aligned in [tx_slot, tx_slot+n+m)
   int family;            // 1 = K1, 2 = K2, 3 = K3 table layout
+  const int* bad;        // != 0: the fill did not run (see BsqFillArgs.bad)
 };

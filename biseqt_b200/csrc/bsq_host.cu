@@ -62,18 +62,18 @@ struct PinBuf {
 
 struct BufSet {  // everything one batch needs in HBM
   DevBuf codes, pairs, ptr, slots, packed, score, ex, ey, sx, sy, status, txlen, txoff, tiles,
-      subst, counters, colh, colf, total, k3pairs, k3sync, k3res, ooff, moff;
+      subst, counters, colh, colf, total, k3pairs, k3sync, k3res, ooff, moff, flags;
   PinBuf hpairs, hsmall;
   size_t bytes() const {  // HBM currently held
     const DevBuf* all[] = {&codes, &pairs, &ptr, &slots, &packed, &score, &ex, &ey, &sx, &sy, &status,
-                           &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff};
+                           &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff, &flags};
     size_t n = 0;
     for (const DevBuf* b : all) n += b->cap;
     return n;
   }
   void release() {
     DevBuf* all[] = {&codes, &pairs, &ptr, &slots, &packed, &score, &ex, &ey, &sx, &sy, &status,
-                     &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff};
+                     &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff, &flags};
     for (DevBuf* b : all) b->release();
     hpairs.release();
     hsmall.release();
@@ -105,6 +105,42 @@ struct Chunk {
 inline bool chunk_is_k3(const Chunk& ch) { return ch.family == 2 && ch.cfg >= BSQ_K2_NCFG; }
 
 struct Override { int64_t idx; int status; };
+
+// Test / tuning hooks.  Environment variables, read ONCE per context in bsq_create (listed in
+// tools/README.md); nothing on the call path reads the environment.
+struct Hooks {
+  bool force_k3 = false;        // BSQ_FORCE_K3: K3 for every band (test)
+  bool no_duo = false;          // BSQ_NO_DUO: never use K1h (test)
+  bool always_sort = false;     // BSQ_ALWAYS_SORT: no caller-order planners (test)
+  bool serial_scan = false;     // BSQ_SERIAL_SCAN: serial chunk-cutting scan (test)
+  bool plan_debug = false;      // BSQ_PLAN_DEBUG: planner / chunk timeline on stderr
+  int64_t uniform_min = 4096;   // BSQ_UNIFORM_MIN: pairs from which the uniform plan / K1h are used
+  int64_t plan_block = 4096;    // BSQ_PLAN_BLOCK: block size of the caller-order planner
+  int target_chunks = -1;       // BSQ_TARGET_CHUNKS: chunks to cut a batch into (< 0: automatic)
+  int k2_cfg = -1;              // BSQ_K2_CFG: forced K2 geometry
+  int k3_cfg = -1;              // BSQ_K3_CFG: forced K3 geometry
+  char trace_kernel = 0;        // BSQ_TRACE_KERNEL: 't'hread / 'w'arp / 'n'arrow
+  size_t arena_cap_bytes = 0;   // BSQ_ARENA_CAP_BYTES: upper bound for the pointer arena
+  void read_env() {
+    auto num = [](const char* name, long long dflt) { const char* e = getenv(name); return e ? atoll(e) : dflt; };
+    force_k3 = getenv("BSQ_FORCE_K3") != nullptr;
+    no_duo = getenv("BSQ_NO_DUO") != nullptr;
+    always_sort = getenv("BSQ_ALWAYS_SORT") != nullptr;
+    serial_scan = getenv("BSQ_SERIAL_SCAN") != nullptr;
+    plan_debug = getenv("BSQ_PLAN_DEBUG") != nullptr;
+    uniform_min = num("BSQ_UNIFORM_MIN", 4096);
+    plan_block = std::max<long long>(1, num("BSQ_PLAN_BLOCK", 4096));
+    target_chunks = (int)num("BSQ_TARGET_CHUNKS", -1);
+    k2_cfg = (int)num("BSQ_K2_CFG", -1);
+    k3_cfg = (int)num("BSQ_K3_CFG", -1);
+    const char* tk = getenv("BSQ_TRACE_KERNEL");
+    trace_kernel = tk ? tk[0] : 0;
+    arena_cap_bytes = (size_t)num("BSQ_ARENA_CAP_BYTES", 0);
+  }
+};
+// pairs per planner thread before another one is worth waking; process-wide like the worker pool
+// (BSQ_PAR_GRAIN, read in bsq_create: a test hook so that small batches exercise the threaded passes)
+int64_t g_par_grain = 32768;
 
 struct PlanItem {  // per-pair classification, filled in parallel
   int64_t words;   // pointer-table words
@@ -161,7 +197,7 @@ struct bsq_ctx {
   bsq_timing tm;
   BufSet bufs;
   std::vector<cudaEvent_t> events;
-  size_t arena_cap_bytes = 0;  // test hook / safety: upper bound for the pointer arena
+  Hooks hooks;                 // test / tuning hooks, read from the environment once in bsq_create
   // cudaMemGetInfo costs 0.1 - 50 ms (measured on the bench box): the one-shot path remembers
   // "free bytes + our cached arena" and only asks again after a resident batch came or went or
   // an allocation failed
@@ -186,8 +222,8 @@ struct bsq_batch {
 // How many chunks to cut a batch into so that traceback/copies of one chunk overlap the
 // fill of the next.  Only short pairs profit: their chunks still hold many waves of work,
 // and their thread-per-pair walk fits beside the fill; long pairs are cut by capacity only.
-static int overlap_chunks(int64_t npairs, const int32_t* o_len, const int32_t* m_len) {
-  if (const char* e = getenv("BSQ_TARGET_CHUNKS")) return atoi(e);  // tuning hook
+static int overlap_chunks(const bsq_ctx* ctx, int64_t npairs, const int32_t* o_len, const int32_t* m_len) {
+  if (ctx->hooks.target_chunks >= 0) return ctx->hooks.target_chunks;  // tuning hook
   if (npairs < 32768) return 1;
   int64_t tot = 0;
   const int64_t step = std::max<int64_t>(npairs / 1024, 1);
@@ -293,8 +329,7 @@ int pick_k1_cfg(int n, int m) {
 // speed.  Measured on B200 (profiles/r01_k2_geometry.txt): for doubles the
 // register footprint of C >= 16 diagonals per lane costs occupancy, so lanes with
 // fewer diagonals win even at lower lane efficiency; int32 prefers tight fits.
-int pick_k2_cfg(int W, bool f64) {
-  static const int forced = getenv("BSQ_K2_CFG") ? atoi(getenv("BSQ_K2_CFG")) : -1;  // tuning hook
+int pick_k2_cfg(int W, bool f64, int forced) {
   if (forced >= 0 && forced < BSQ_K2_NCFG && BSQ_K2_CFGS[forced].G * BSQ_K2_CFGS[forced].C >= W) return forced;
   int best = -1;
   double bestc = 1e300;
@@ -324,16 +359,8 @@ int k3_op(int dtype, int cfg, int btype, int gos, int grid, cudaStream_t st, con
                                 : bsq_k3_f64_op(cfg, btype, gos, grid, st, A);
 }
 
-// batches of one shape take the planner's fast path, and K1h is used, from this many pairs on
-inline int64_t uniform_min_pairs() {
-  const char* e = getenv("BSQ_UNIFORM_MIN");  // test hook
-  return e ? atoll(e) : 4096;
-}
-
-// K3 geometry for bands no K2 geometry holds (or for every band: BSQ_FORCE_K3, a test hook)
-int pick_k3_cfg() {
-  const char* e = getenv("BSQ_K3_CFG");  // tuning hook
-  const int forced = e ? atoi(e) : -1;
+// K3 geometry for bands no K2 geometry holds (or for every band: Hooks.force_k3)
+int pick_k3_cfg(int forced) {
   return (forced >= 0 && forced < BSQ_K3_NCFG) ? forced : 1;  // K = 4 columns x R = 2 rows per lane and step: measured best on C5
 }
 
@@ -397,13 +424,7 @@ class WorkerPool {
   bool stop_ = false;
 };
 
-// pairs per planner thread before another one is worth waking (BSQ_PAR_GRAIN: test hook, so that
-// small batches exercise the multi-threaded passes)
-inline int64_t parallel_grain() {
-  const char* e = getenv("BSQ_PAR_GRAIN");
-  const int64_t g = e ? atoll(e) : 0;
-  return g > 0 ? g : 32768;
-}
+inline int64_t parallel_grain() { return g_par_grain > 0 ? g_par_grain : 32768; }
 inline int parallel_threads(int64_t n) {
   return (int)std::min<int64_t>(WorkerPool::get().size(), std::max<int64_t>(n / parallel_grain(), 1));
 }
@@ -478,8 +499,9 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   }
   P.uniform_dev = false;
   P.pairs = nullptr;
-  const bool force_k3 = getenv("BSQ_FORCE_K3") != nullptr;  // test hook: K3 for every band
-  const int k3_cfg = pick_k3_cfg();
+  const Hooks& hk = ctx->hooks;
+  const bool force_k3 = hk.force_k3;
+  const int k3_cfg = pick_k3_cfg(hk.k3_cfg);
   // K1h (two short problems per lane group, packed 16-bit arithmetic): what the scores and
   // the alignment type must satisfy; the shape conditions are per pair (PlanItem.lo for STD)
   double duo_maxabs = std::fabs(prm->go) + std::fabs(prm->ge);
@@ -490,7 +512,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
     t1.subst = P.subst.data();
     const bool i32 = prm->dtype != BSQ_DTYPE_F64 && scores_int32_exact(&t1, scan_n, scan_m);
     duo_scores_ok = family == 1 && i32 && P.bmode == BSQ_B_ALL && P.emode == BSQ_E_ALL && prm->go <= 0.0 &&
-                    prm->ge <= 0.0 && L <= 4 && getenv("BSQ_NO_DUO") == nullptr;
+                    prm->ge <= 0.0 && L <= 4 && !hk.no_duo;
   }
   auto duo_shape_ok = [&](int cfg, int64_t passes, int n, int m) -> bool {
     return duo_scores_ok && (cfg == 0 || cfg == 1) && passes == 1 && (double)(n + m + 4) * duo_maxabs < 4000.0;
@@ -516,7 +538,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
       else if (W < 0) it.cfg = -1 - BSQ_INIT_FAIL;
       else if (W == 0) it.cfg = -1 - BSQ_NO_ALIGNMENT;
       else {
-        it.cfg = force_k3 ? -1 : pick_k2_cfg((int)std::min<int64_t>(W, 1 << 30), f64_geom);
+        it.cfg = force_k3 ? -1 : pick_k2_cfg((int)std::min<int64_t>(W, 1 << 30), f64_geom, ctx->hooks.k2_cfg);
         if (it.cfg < 0) it.cfg = BSQ_K2_NCFG + k3_cfg;
       }
       if (it.cfg >= BSQ_K2_NCFG) {  // K3: strips of G*K columns, tstride time steps each
@@ -545,7 +567,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
 
   // ---- fast path: one shape for the whole batch (fixed-length reads).  No per-pair host work:
   // chunk boundaries are arithmetic and the pair records are generated on the device.
-  if (all_uniform && N >= uniform_min_pairs() && N < ((int64_t)1 << 31)) {
+  if (all_uniform && N >= hk.uniform_min && N < ((int64_t)1 << 31)) {
     const PlanItem it = classify(o_len[0], m_len[0], family == 2 ? dmin[0] : 0, family == 2 ? dmax[0] : 0);
     bsq_params tmp = *prm;
     tmp.subst = P.subst.data();
@@ -620,7 +642,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
       return BSQ_SUCCESS;
     }
   }
-  const bool plan_dbg = getenv("BSQ_PLAN_DEBUG") != nullptr;
+  const bool plan_dbg = hk.plan_debug;
   const auto tp0 = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) {
     if (plan_dbg)
@@ -634,9 +656,9 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   // chunk.  Two light passes over blocks of 4096 pairs: (A) per-block sums and checks, read-only;
   // a serial walk over the blocks cuts the chunks; (B) the pair records with their final offsets,
   // written once, sequentially.  (The general path below costs 3x the memory traffic.)
-  const int64_t RB = getenv("BSQ_PLAN_BLOCK") ? std::max<int64_t>(1, atoll(getenv("BSQ_PLAN_BLOCK"))) : 4096;   // env: test hook
+  const int64_t RB = hk.plan_block;
   if (family == 1 && !all_uniform && N >= 4 * RB && N < ((int64_t)1 << 31) &&
-      getenv("BSQ_ALWAYS_SORT") == nullptr) {
+      !hk.always_sort) {
     bsq_params tmp = *prm;
     tmp.subst = P.subst.data();
     const bool i32ok = scores_int32_exact(&tmp, scan_n, scan_m);
@@ -720,7 +742,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
       }
       cur.idx_hi = N;
       P.chunks.push_back(cur);
-      const bool duo = duo_all && dtype == BSQ_DTYPE_I32 && N >= uniform_min_pairs();
+      const bool duo = duo_all && dtype == BSQ_DTYPE_I32 && N >= hk.uniform_min;
       for (Chunk& ch : P.chunks) ch.duo = duo;
       // Inside a block the pairs are ordered by origin length (a counting sort of <= RB cached
       // entries): the lane groups of a warp -- and the two problems of a K1h duo -- then walk nearly
@@ -859,7 +881,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
     // Long pairs are always ordered: measured on config 3 (32768 banded pairs of ~10 kb) caller
     // order made the fill 26 % slower, and their plan is < 3 % of the call either way.
     uniform = family == 1 && !all.mixed && all.cfg0 >= 0 && all.maxw <= 2 * all.minw &&
-              all.maxw <= BSQ_INORDER_MAX_WORDS && getenv("BSQ_ALWAYS_SORT") == nullptr;
+              all.maxw <= BSQ_INORDER_MAX_WORDS && !hk.always_sort;
   }
   if (!range_ok) P.cells = 0;
   P.identity = uniform;
@@ -897,8 +919,8 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   // own chunks, in which pairs (2q, 2q+1) share a lane group: neighbours of one size class, i.e.
   // the longer problem of a duo has < 12.5 % more rows than the shorter.  Worth it from a few
   // thousand candidates on.
-  const bool use_duo = family == 1 && P.dtype == BSQ_DTYPE_I32 && n_duo_ok >= uniform_min_pairs() &&
-                       getenv("BSQ_NO_DUO") == nullptr;
+  const bool use_duo = family == 1 && P.dtype == BSQ_DTYPE_I32 && n_duo_ok >= hk.uniform_min &&
+                       !hk.no_duo;
   constexpr int NCLS = 512;
   const int nkeys_std = (BSQ_K2_NCFG + BSQ_K3_NCFG + 1) * NCLS;
   const int nkeys_duo = use_duo ? 2 * NCLS : 0;   // K1h runs on K1 geometries 0 and 1
@@ -974,7 +996,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
     if (any_k3) P.k3.assign((size_t)E, BsqK3Pair{0, 0, 0});
   }
   lap("scan starts");
-  const bool serial_scan = !P.k3.empty() || E < 2 * parallel_grain() || getenv("BSQ_SERIAL_SCAN") != nullptr;
+  const bool serial_scan = !P.k3.empty() || E < 2 * parallel_grain() || hk.serial_scan;
   if (serial_scan) {
   for (int64_t e = 0; e < E; e++) {
     const Gathered& it = gth[e];
@@ -1106,7 +1128,7 @@ int64_t arena_budget_words(bsq_ctx* ctx, int64_t other_bytes, const BufSet* mine
     ctx->mem_avail = (double)fr + (double)held_elsewhere(ctx, nullptr);
   }
   double budget = (ctx->mem_avail - (double)held_elsewhere(ctx, mine)) * 0.85 - (double)other_bytes;
-  if (ctx->arena_cap_bytes && budget > (double)ctx->arena_cap_bytes) budget = (double)ctx->arena_cap_bytes;
+  if (ctx->hooks.arena_cap_bytes && budget > (double)ctx->hooks.arena_cap_bytes) budget = (double)ctx->hooks.arena_cap_bytes;
   if (budget < (double)(1 << 16)) budget = (double)(1 << 16);
   return (int64_t)(budget / 4.0);
 }
@@ -1138,6 +1160,18 @@ int upload_pairs(bsq_ctx* ctx, BufSet& B, const Plan& P, cudaStream_t st) {
   return BSQ_SUCCESS;
 }
 
+// every letter referenced by pair records [first, first + count) must be < alphabet_len; raises
+// B.flags[0] on the device (the fill / traceback kernels then return at once)
+int launch_check_codes(bsq_ctx* ctx, BufSet& B, const Plan& P, int64_t first, int64_t count, cudaStream_t st) {
+  if (count <= 0) return BSQ_SUCCESS;
+  const int grid = (int)((count * 32 + 127) / 128);
+  BSQ_LAUNCH(bsq_check_codes, grid, 128, 0, st, (const uint8_t*)B.codes.as<uint8_t>(),
+             (const BsqPair*)(B.pairs.as<BsqPair>() + first), (int)count, P.prm.alphabet_len, B.flags.as<int>());
+  BSQ_CK(ctx, cudaGetLastError());
+  ctx->tm.fill_launches++;
+  return BSQ_SUCCESS;
+}
+
 // K3 chunks: per-pair strip records, progress/done words, per-strip results, slabs
 int stage_k3(bsq_ctx* ctx, BufSet& B, const Plan& P, cudaStream_t st) {
   if (P.k3.empty()) return BSQ_SUCCESS;
@@ -1159,7 +1193,7 @@ int stage_inputs(bsq_ctx* ctx, BufSet& B, Plan& P, const uint8_t* codes, int64_t
             B.score.ensure(8 * (size_t)N) && B.ex.ensure(4 * (size_t)N) && B.ey.ensure(4 * (size_t)N) &&
             B.sx.ensure(4 * (size_t)N) && B.sy.ensure(4 * (size_t)N) && B.status.ensure(4 * (size_t)N) &&
             B.txlen.ensure(4 * (size_t)N) && B.subst.ensure(8 * (size_t)L * L) &&
-            B.counters.ensure(4 * (P.chunks.size() + 1)) && B.total.ensure(16) &&
+            B.counters.ensure(4 * (P.chunks.size() + 1)) && B.total.ensure(16) && B.flags.ensure(16) &&
             B.ptr.ensure(4 * (size_t)(single_chunk ? P.total_words : (P.half_words > 0 ? BSQ_ARENA_SLOTS * P.half_words : P.max_chunk_words)) + 64);
   if (!ok) { ctx->mem_avail = -1.0; return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed"); }
   cudaStream_t st = ctx->st;
@@ -1179,6 +1213,11 @@ int stage_inputs(bsq_ctx* ctx, BufSet& B, Plan& P, const uint8_t* codes, int64_t
   }
   BSQ_CK(ctx, cudaMemsetAsync(B.counters.p, 0, 4 * (P.chunks.size() + 1), st));
   BSQ_CK(ctx, cudaMemsetAsync(B.txlen.p, 0, 4 * (size_t)N, st));
+  BSQ_CK(ctx, cudaMemsetAsync(B.flags.p, 0, 16, st));
+  {
+    const int rck = launch_check_codes(ctx, B, P, 0, E, st);
+    if (rck != BSQ_SUCCESS) return rck;
+  }
   return stage_k3(ctx, B, P, st);
 }
 
@@ -1200,6 +1239,7 @@ int launch_fill(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, size_t* evi, 
   A.out_ey = B.ey.as<int>();
   A.out_status = B.status.as<int>();
   A.counter = B.counters.as<int>() + ci;
+  A.bad = B.flags.as<int>();
   if (chunk_is_k3(ch)) {
     A.k3 = B.k3pairs.as<BsqK3Pair>() + ch.first;
     A.k3_total = (int)ch.k3_strips;
@@ -1302,13 +1342,14 @@ int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, cudaStream_t
   T.sy = B.sy.as<int>();
   T.txlen = B.txlen.as<int>();
   T.slots = B.slots.as<char>();
+  T.bad = B.flags.as<int>();
   // long pairs: one warp per pair walking shared-memory tiles; short pairs: one
   // thread per pair (there are enough of them to hide the load latency)
   const long long avg_path = P.slot_bytes / std::max<long long>((long long)P.E, 1);
-  const char* force = getenv("BSQ_TRACE_KERNEL");  // test hook: "thread" / "warp" / "narrow"
+  const char force = ctx->hooks.trace_kernel;  // test hook: 't'hread / 'w'arp / 'n'arrow
   bool warp_walk = avg_path >= 1024;
-  if (force && force[0] == 't') warp_walk = false;
-  if (force && (force[0] == 'w' || force[0] == 'n')) warp_walk = true;  // "narrow": 8 lanes per pair
+  if (force == 't') warp_walk = false;
+  if (force == 'w' || force == 'n') warp_walk = true;  // "narrow": 8 lanes per pair
   if (k3) {  // one warp per pair over the [strip][t][lane] table
     const int grid = (int)ch.count;
 #define BSQ_WALK3(KK) { if (P.gosign < 0) BSQ_LAUNCH((bsq_k3_walk<KK, -1>), grid, 32, 0, stream, T); \
@@ -1318,7 +1359,7 @@ int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, cudaStream_t
 #undef BSQ_WALK3
   } else if (warp_walk) {
     // lanes per pair: 8 when there are enough pairs to fill the GPU four times over, else a warp
-    const bool narrow = (ch.count >= (int64_t)ctx->sms * 16 * 4 || (force && force[0] == 'n')) && !(force && force[0] == 'w');
+    const bool narrow = (ch.count >= (int64_t)ctx->sms * 16 * 4 || force == 'n') && force != 'w';
     const int ppb = BSQ_WALK_WARPS * (narrow ? 4 : 1);  // pairs per block
     const int grid = (int)((ch.count + ppb - 1) / ppb);
 #define BSQ_WALK(F, GS) { if (narrow) BSQ_LAUNCH((bsq_k4_walk<F, GS, 8>), grid, 32 * BSQ_WALK_WARPS, 0, stream, T); \
@@ -1448,8 +1489,7 @@ bsq_ctx* bsq_create(int device) {
     g_err = "cudaStreamCreate failed"; delete ctx; return nullptr;
   }
   memset(&ctx->tm, 0, sizeof ctx->tm);
-  const char* cap = getenv("BSQ_ARENA_CAP_BYTES");
-  if (cap) ctx->arena_cap_bytes = (size_t)atoll(cap);
+  bsq_reload_hooks(ctx);
   return ctx;
 }
 
@@ -1457,6 +1497,16 @@ void bsq_destroy(bsq_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->st);
+  cudaStreamSynchronize(ctx->st_trace);
+  // batches that outlive their context (Python: an Engine closed before its SolvedBatch /
+  // ResidentBatch objects are collected): give their buffers back now and orphan them, so that a
+  // later bsq_release / bsq_traceback_batch / bsq_batch_* on them touches nothing of this context
+  for (bsq_batch* b : ctx->live) {
+    if (b->own) { b->own->release(); delete b->own; b->own = nullptr; }
+    b->B = nullptr;
+    b->ctx = nullptr;
+  }
+  ctx->live.clear();
   ctx->bufs.release();
   drop_pool(ctx);
   ctx->htotals.release();
@@ -1467,6 +1517,13 @@ void bsq_destroy(bsq_ctx* ctx) {
   cudaStreamDestroy(ctx->st_d2h);
   cudaStreamDestroy(ctx->st_trace);
   delete ctx;
+}
+
+void bsq_reload_hooks(bsq_ctx* ctx) {
+  if (!ctx) return;
+  ctx->hooks.read_env();
+  const char* e = getenv("BSQ_PAR_GRAIN");
+  g_par_grain = e ? atoll(e) : 32768;
 }
 
 void* bsq_host_alloc(int64_t bytes) {
@@ -1544,7 +1601,7 @@ static int batch_upload(bsq_ctx* ctx, bsq_batch* b, bool own_bufs, bool single_c
   const int64_t arena_words = arena_budget_words(ctx, other, b->B);
   int rc = make_plan(ctx, b->plan, b->B->hpairs, params, npairs, ncodes, o_off, o_len, m_off, m_len, dmin, dmax,
                      single_chunk ? arena_words : arena_words / BSQ_ARENA_SLOTS, single_chunk,
-                     single_chunk ? 0 : overlap_chunks(npairs, o_len, m_len));
+                     single_chunk ? 0 : overlap_chunks(ctx, npairs, o_len, m_len));
   if (rc != BSQ_SUCCESS) return rc;
   b->single_chunk = single_chunk;
   return stage_inputs(ctx, *b->B, b->plan, codes, ncodes, single_chunk);
@@ -1767,10 +1824,10 @@ static int align_batch_once(bsq_ctx* ctx, const bsq_params* params, int64_t npai
   const int64_t budget = arena_budget_words(ctx, other, &B);
   const double t_p2 = now_ms();
   rc = make_plan(ctx, P, B.hpairs, params, npairs, ncodes, o_off, o_len, m_off, m_len, dmin, dmax,
-                 budget / BSQ_ARENA_SLOTS, false, overlap_chunks(npairs, o_len, m_len));
+                 budget / BSQ_ARENA_SLOTS, false, overlap_chunks(ctx, npairs, o_len, m_len));
   if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(sx); return rc; }
   ctx->tm.plan_ms = now_ms() - t_plan;
-  if (getenv("BSQ_PLAN_DEBUG"))
+  if (ctx->hooks.plan_debug)
     fprintf(stderr, "[bsq] plan: memgetinfo %.3f ms, make_plan %.3f ms, h2d enqueue before plan %.3f ms\n",
             t_p2 - t_p1, now_ms() - t_p2, t_plan - t_call);
   const int64_t E = (int64_t)P.E;
@@ -1780,7 +1837,7 @@ static int align_batch_once(bsq_ctx* ctx, const bsq_params* params, int64_t npai
   bool ok = B.pairs.ensure(sizeof(BsqPair) * (size_t)std::max<int64_t>(E, 1)) && B.score.ensure(8 * N) &&
             B.ex.ensure(4 * N) && B.ey.ensure(4 * N) && B.sx.ensure(4 * N) && B.sy.ensure(4 * N) &&
             B.status.ensure(4 * N) && B.txlen.ensure(4 * N) && B.subst.ensure(8 * (size_t)L * L + 64) &&
-            B.counters.ensure(4 * (NC + 1)) && B.total.ensure(8 * (NC + 2)) &&
+            B.counters.ensure(4 * (NC + 1)) && B.total.ensure(8 * (NC + 2)) && B.flags.ensure(16) &&
             B.ptr.ensure(4 * (size_t)(P.half_words > 0 ? BSQ_ARENA_SLOTS * P.half_words : P.max_chunk_words) + 64) &&
             ctx->htotals.ensure(8 * (NC + 2));
   if (ok && want_trace) ok = B.slots.ensure((size_t)std::max<int64_t>(P.slot_bytes, 1));
@@ -1814,6 +1871,7 @@ static int align_batch_once(bsq_ctx* ctx, const bsq_params* params, int64_t npai
   BSQ_CK(ctx, cudaMemsetAsync(B.counters.p, 0, 4 * (NC + 1), sc));
   BSQ_CK(ctx, cudaMemsetAsync(B.txlen.p, 0, 4 * N, sc));
   BSQ_CK(ctx, cudaMemsetAsync(B.total.p, 0, 8 * (NC + 2), sc));
+  BSQ_CK(ctx, cudaMemsetAsync(B.flags.p, 0, 16, sc));
   BSQ_CK(ctx, cudaStreamWaitEvent(sc, ev_pairs, 0));
   const bool per_chunk_out = P.identity;  // chunk c covers caller indices [idx_lo, idx_hi)
   std::vector<cudaEvent_t> ev_done;
@@ -1828,7 +1886,7 @@ static int align_batch_once(bsq_ctx* ctx, const bsq_params* params, int64_t npai
         while (need < nsl - 1 && slice_end[need] < ch.code_end) need++;
         for (int sidx = waited_slice + 1; sidx <= need && sidx < nsl; sidx++) BSQ_CK(ctx, cudaStreamWaitEvent(sc, ev_code[sidx], 0));
         waited_slice = std::max(waited_slice, need);
-        return BSQ_SUCCESS;
+        return launch_check_codes(ctx, B, P, ch.first, ch.count, sc);
       },
       [&](size_t ci, cudaStream_t ts) -> int {  // pack this chunk's transcripts behind its traceback
         if (!(want_tx && per_chunk_out)) return BSQ_SUCCESS;
@@ -1911,7 +1969,10 @@ static int align_batch_once(bsq_ctx* ctx, const bsq_params* params, int64_t npai
   BSQ_CK(ctx, cudaStreamSynchronize(sx));
   BSQ_CK(ctx, cudaStreamSynchronize(ctx->st_copy2));
   BSQ_CK(ctx, cudaStreamSynchronize(ctx->st_trace));
+  int bad_codes = 0;
+  BSQ_CK(ctx, cudaMemcpyAsync(&bad_codes, B.flags.p, 4, cudaMemcpyDeviceToHost, sc));
   BSQ_CK(ctx, cudaStreamSynchronize(sc));
+  if (bad_codes) return fail(ctx, BSQ_ERR_ARG, "a letter code is >= alphabet_len");
   collect_timing(ctx, 2, t0, t1);
   // only the (fill start, fill end) event pairs count as fill time
   {
@@ -1921,7 +1982,7 @@ static int align_batch_once(bsq_ctx* ctx, const bsq_params* params, int64_t npai
       if (cudaEventElapsedTime(&ms, ctx->events[fill_ev0[ci]], ctx->events[fill_ev0[ci] + 1]) == cudaSuccess) fill += ms;
     }
     ctx->tm.fill_ms = fill;
-    if (getenv("BSQ_PLAN_DEBUG")) {  // device timeline of the call, relative to its first event
+    if (ctx->hooks.plan_debug) {  // device timeline of the call, relative to its first event
       for (size_t ci = 0; ci < NC; ci++) {
         float a = 0, b = 0, c = 0;
         cudaEventElapsedTime(&a, t0, ctx->events[fill_ev0[ci]]);
@@ -1960,9 +2021,12 @@ int bsq_batch_upload(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, con
     ctx->mem_avail = -1.0;
     rc = batch_upload(ctx, b, true, keep_tables != 0, params, npairs, codes, ncodes, o_off, o_len, m_off, m_len, dmin, dmax);
   }
-  if (rc == BSQ_SUCCESS) {
-    cudaError_t e = cudaStreamSynchronize(ctx->st);
+  if (rc == BSQ_SUCCESS && npairs > 0) {
+    int bad = 0;
+    cudaError_t e = cudaMemcpyAsync(&bad, b->B->flags.p, 4, cudaMemcpyDeviceToHost, ctx->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->st);
     if (e != cudaSuccess) { ctx->err = std::string("upload: ") + cudaGetErrorString(e); rc = BSQ_ERR_CUDA; }
+    else if (bad) rc = fail(ctx, BSQ_ERR_ARG, "a letter code is >= alphabet_len");
   }
   if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(ctx->st); bsq_release(b); return rc; }
   *batch = b;

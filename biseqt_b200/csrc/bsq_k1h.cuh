@@ -81,6 +81,7 @@ template <int G, int K, int GOS, bool SAME>
 __global__ void __launch_bounds__(128) bsq_k1h_fill(const BsqFillArgs A) {
   constexpr int WPL = (K + 7) / 8, WST = BSQ_K1_WPL(K);
   static_assert(GOS <= 0, "K1h handles go <= 0");
+  BSQ_BAIL_IF_BAD(A);
   // (origin letter of A, of B) x (mutant letter of A, of B); letter 4 = padding row / column:
   // subst - ge of both problems, packed
   __shared__ unsigned s_sub2[25 * 25];

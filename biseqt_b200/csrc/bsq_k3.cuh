@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3_fill(const BsqFillArgs 
   typedef BsqK3Slab<S> Slab;
   constexpr int G = 32, BW = G * K;
   constexpr int NB = (BT == BSQ_B_LOCAL) ? K : 1;
+  BSQ_BAIL_IF_BAD(A);
   __shared__ T s_sub[BSQ_MAX_L * BSQ_MAX_L];
   __shared__ T s_inH[BSQ_K3_THREADS / 32][32];    // the batch of boundary values lane 0 consumes
   __shared__ int s_inG[BSQ_K3_THREADS / 32][32];

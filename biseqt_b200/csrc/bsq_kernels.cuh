@@ -27,6 +27,10 @@
 
 #define BSQ_INT_MAX 0x7fffffff
 
+// every fill / traceback kernel starts with this: a letter code >= alphabet_len would index the
+// shared-memory score table out of bounds, so after bsq_check_codes raised the flag nothing runs
+#define BSQ_BAIL_IF_BAD(A) do { if ((A).bad != nullptr && *(volatile const int*)(A).bad != 0) return; } while (0)
+
 // a lane's NW pointer words of one row / step -> ONE aligned vector store of STRIDE words
 template <int NW, int STRIDE>
 __device__ __forceinline__ void bsq_store_words(uint32_t* dst, const uint32_t (&w)[NW]) {
@@ -311,6 +315,7 @@ template <class S, int G, int K, bool BALL, int EALL, int GOS>
 __global__ void __launch_bounds__(128) bsq_k1_fill(const BsqFillArgs A) {
   typedef typename S::T T;
   static_assert(K <= 32, "end-cell positions are packed as x*32 + k");
+  BSQ_BAIL_IF_BAD(A);
   constexpr int WPL = (K + 7) / 8;          // words holding a lane's K nibbles
   constexpr int WST = BSQ_K1_WPL(K);        // words a lane's row occupies in the table
   constexpr int BW = G * K;
@@ -622,6 +627,7 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
   constexpr int HC = C / 2;
   constexpr int WPS = (HC + 7) / 8;
   constexpr int NB = BLOCAL ? C : 1;
+  BSQ_BAIL_IF_BAD(A);
   __shared__ T s_sub[BSQ_MAX_L * BSQ_MAX_L];
   const int L = A.L;
   // DNA-sized alphabets: the table is re-laid out 4 x 4 so that a nibble

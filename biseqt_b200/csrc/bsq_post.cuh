@@ -37,6 +37,7 @@ __device__ __forceinline__ uint32_t bsq_get_mask(const BsqTraceArgs& A, const Bs
 }
 
 __global__ void __launch_bounds__(128) bsq_k4_traceback(const BsqTraceArgs A) {
+  BSQ_BAIL_IF_BAD(A);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= A.npairs) return;
   const BsqPair P = A.pairs[p];
@@ -97,6 +98,7 @@ __device__ __forceinline__ uint32_t bsq_gap_base_t(uint32_t mk, uint32_t own) {
 template <int FAMILY, int GOS, int BSQ_WALK_GW>
 __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTraceArgs A) {
   constexpr int BSQ_WALK_PPW = 32 / BSQ_WALK_GW;
+  BSQ_BAIL_IF_BAD(A);
   __shared__ uint32_t s_tile[BSQ_WALK_WARPS * BSQ_WALK_PPW][BSQ_TILE_WORDS];
   __shared__ uint8_t s_let[BSQ_WALK_WARPS * BSQ_WALK_PPW][2][BSQ_LET_WIN];  // staged letters: origin, mutant
   const int wib = threadIdx.x >> 5;
@@ -350,6 +352,7 @@ __global__ void __launch_bounds__(32) bsq_k3_walk(const BsqTraceArgs A) {
   constexpr int LOGK = (K == 2) ? 1 : (K == 4 ? 2 : 3);
   constexpr int TSTEPS = BSQ_K3_TILE_BYTES / (G * (int)sizeof(PU));
   constexpr int BATCH = 8;       // diagonal moves examined per round out of preloaded nibbles
+  BSQ_BAIL_IF_BAD(A);
   __shared__ uint4 s_tile4[BSQ_K3_TILE_BYTES / 16];
   __shared__ uint8_t s_let[2][BSQ_K3_LET_WIN];
   PU* tile = (PU*)s_tile4;
@@ -471,6 +474,23 @@ __global__ void __launch_bounds__(32) bsq_k3_walk(const BsqTraceArgs A) {
     A.sy[oi] = y;
     A.status[oi] = (ex + ey - len <= 0) ? BSQ_REF_WOULD_ABORT : (len == 0 ? BSQ_EMPTY : BSQ_OK);
   }
+}
+
+// Input check dptable_init never needed (the reference indexes a double** the caller sized,
+// pwlib.h:72-77): every letter the batch references must be < alphabet_len, because the fill
+// kernels index a fixed-size shared-memory score table with it.  One warp per pair; raises *bad.
+__global__ void __launch_bounds__(128) bsq_check_codes(const uint8_t* codes, const BsqPair* pairs, int npairs,
+                                                       int L, int* bad) {
+  const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (warp >= npairs) return;
+  const BsqPair P = pairs[warp];
+  const uint8_t* o = codes + P.o_off;
+  const uint8_t* m = codes + P.m_off;
+  int worst = 0;
+  for (int i = lane; i < P.n; i += 32) worst = max(worst, (int)o[i]);
+  for (int i = lane; i < P.m; i += 32) worst = max(worst, (int)m[i]);
+  if (worst >= L) *bad = 1;
 }
 
 // exclusive scan of txlen (int32) into int64 offsets, three small kernels

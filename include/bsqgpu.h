@@ -112,6 +112,11 @@ void bsq_destroy(bsq_ctx* ctx);
 const char* bsq_last_error(const bsq_ctx* ctx);
 const char* bsq_version(void);
 
+/* Test / tuning hooks are BSQ_* environment variables (tools/README.md) read ONCE, in
+ * bsq_create; nothing on the call path reads the environment.  bsq_reload_hooks reads them
+ * again for this context (tests flip a hook between two calls on one context). */
+void bsq_reload_hooks(bsq_ctx* ctx);
+
 /* pinned host memory so that H2D/D2H run at link speed without a bounce copy */
 void* bsq_host_alloc(int64_t bytes);
 void bsq_host_free(void* p);

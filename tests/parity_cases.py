@@ -231,10 +231,12 @@ def run_duo_short_reads(make_engine, seed, npairs=37):
                     r = check_batch(eng, probs)
                     assert eng.timing()['dtype'] == batch.DTYPE_I16X2, (n, m, gomode)
                     os.environ['BSQ_NO_DUO'] = '1'
+                    eng.reload_hooks()
                     try:
                         r1 = engine_batch(eng, probs)
                     finally:
                         del os.environ['BSQ_NO_DUO']
+                        eng.reload_hooks()
                     assert eng.timing()['dtype'] == batch.DTYPE_I32
                     assert np.array_equal(r.score, r1.score) and np.array_equal(r.tx_off, r1.tx_off)
                     assert np.array_equal(r.tx_buf[:r.tx_off[-1]], r1.tx_buf[:r1.tx_off[-1]])
@@ -244,6 +246,7 @@ def run_duo_short_reads(make_engine, seed, npairs=37):
             for trial in range(6):
                 if trial >= 3:
                     os.environ['BSQ_PAR_GRAIN'] = str(trial - 1)
+                    eng.reload_hooks()
                 L = 4
                 S = np.where(np.eye(L, dtype=bool), 2.0, -3.0)
                 go, ge = (-4.0, -1.0) if trial != 1 else (0.0, -2.0)
@@ -264,13 +267,16 @@ def run_duo_short_reads(make_engine, seed, npairs=37):
                 assert eng.timing()['dtype'] == batch.DTYPE_I16X2
                 assert eng.timing()['chunks'] >= 2     # packed chunks and scalar ones
                 os.environ['BSQ_NO_DUO'] = '1'
+                eng.reload_hooks()
                 try:
                     r1 = engine_batch(eng, probs)
                 finally:
                     del os.environ['BSQ_NO_DUO']
+                    eng.reload_hooks()
                 assert np.array_equal(r.score, r1.score) and np.array_equal(r.tx_off, r1.tx_off)
                 assert np.array_equal(r.tx_buf[:r.tx_off[-1]], r1.tx_buf[:r1.tx_off[-1]])
             os.environ.pop('BSQ_PAR_GRAIN', None)
+            eng.reload_hooks()
             # ragged batches that stay in caller order (one geometry, tables within 2x): every pair
             # its own shape, neighbours (2q, 2q+1) share a lane group, the shorter one padded
             for trial in range(8):
@@ -300,15 +306,19 @@ def run_duo_short_reads(make_engine, seed, npairs=37):
                 assert eng.timing()['dtype'] == batch.DTYPE_I16X2
                 assert (eng.timing()['chunks'] > 1) if blocked else (eng.timing()['chunks'] == 1)
                 os.environ['BSQ_NO_DUO'] = '1'     # the scalar kernel on the same (in-order) plan
+                eng.reload_hooks()
                 try:
                     r1 = engine_batch(eng, probs)
                 finally:
                     del os.environ['BSQ_NO_DUO']
+                    eng.reload_hooks()
                 assert eng.timing()['dtype'] == batch.DTYPE_I32
                 assert np.array_equal(r.score, r1.score) and np.array_equal(r.tx_off, r1.tx_off)
                 assert np.array_equal(r.tx_buf[:r.tx_off[-1]], r1.tx_buf[:r1.tx_off[-1]])
                 for k in ('BSQ_PLAN_BLOCK', 'BSQ_PAR_GRAIN', 'BSQ_ARENA_CAP_BYTES'):
                     os.environ.pop(k, None)
+                if not blocked:
+                    eng.reload_hooks()
         finally:
             for k in ('BSQ_PLAN_BLOCK', 'BSQ_PAR_GRAIN', 'BSQ_ARENA_CAP_BYTES'):
                 os.environ.pop(k, None)
@@ -404,10 +414,12 @@ def run_big_ragged_plan(make_engine, seed, npairs=70000, all_modes=True):
             assert np.array_equal(r.start_x[ok], e['start_x'][ok]) and np.array_equal(r.start_y[ok], e['start_y'][ok])
             assert np.array_equal(r.tx_len, e['tx_len'])
             os.environ['BSQ_SERIAL_SCAN'] = '1'
+            eng.reload_hooks()
             try:
                 r1 = eng.align(codes, o_off, o_len, m_off, m_len, mode, typ, S, -2.0, -1.0, **kw)
             finally:
                 del os.environ['BSQ_SERIAL_SCAN']
+                eng.reload_hooks()
             assert np.array_equal(r.tx_off, r1.tx_off) and np.array_equal(r.tx_buf[:r.tx_off[-1]], r1.tx_buf[:r1.tx_off[-1]])
             assert np.array_equal(r.status, r1.status) and np.array_equal(r.score, r1.score)
     finally:
@@ -448,10 +460,12 @@ def run_ragged_reads(make_engine, seed, npairs=30000, lo=100, hi=151):
         assert r.transcripts() == lean.transcripts(e)
         for var in ('BSQ_ALWAYS_SORT', 'BSQ_NO_DUO'):
             os.environ[var] = '1'
+            eng.reload_hooks()
             try:
                 r1 = eng.align(codes, o_off, o_len, m_off, m_len, 0, 1, S, -5.0, -2.0)
             finally:
                 del os.environ[var]
+                eng.reload_hooks()
             assert np.array_equal(r.tx_off, r1.tx_off) and np.array_equal(r.tx_buf[:r.tx_off[-1]], r1.tx_buf[:r1.tx_off[-1]])
             assert np.array_equal(r.status, r1.status) and np.array_equal(r.score, r1.score)
     finally:
@@ -580,6 +594,64 @@ def run_edge_cases(eng):
     for L in (1, 20):
         for mode, typ in ((0, 1), (1, 2)):
             check_batch(eng, make_batch(rng, 5, mode, typ, 5, 40, L=L))
+    run_bad_codes(eng)
+
+
+def run_bad_codes(eng):
+    """A letter code >= alphabet_len is refused (BSQ_ERR_ARG) on every entry point instead of
+    indexing the shared-memory score table out of bounds; unreferenced bytes of codes[] may hold
+    anything (e.g. separators)."""
+    import pytest
+    from biseqt_b200._ffi import BsqError
+    o = np.array([0, 1, 2, 3, 250, 1, 2], np.uint8)
+    t = np.array([0, 1, 2, 3, 1, 2], np.uint8)
+    for mode, typ, dr in ((0, 1, None), (1, 2, (-3, 3))):
+        pr = dict(origin=o, mutant=t, subst=np.eye(4), go=-1.0, ge=-1.0, mode=mode, type=typ, diag_range=dr)
+        with pytest.raises(BsqError, match='alphabet_len'):
+            engine_batch(eng, [pr])
+    codes = np.concatenate([o, t])
+    args = ([0], [7], [7], [6], 0, 1, np.eye(4), -1.0, -1.0)
+    with pytest.raises(BsqError, match='alphabet_len'):
+        eng.solve(codes, *args)
+    with pytest.raises(BsqError, match='alphabet_len'):
+        eng.upload(codes, *args)
+    # the same bytes with the bad letter outside every frame: fine
+    sep = np.concatenate([o[:4], [255], t]).astype(np.uint8)
+    r = eng.align(sep, [0], [4], [5], [6], 0, 1, np.eye(4), -1.0, -1.0)
+    assert int(r.status[0]) == 0 and r.transcript(0) == 'MMMM'
+    # and the engine still works afterwards
+    check_batch(eng, [dict(origin=t, mutant=t, subst=np.eye(4), go=-1.0, ge=-1.0, mode=0, type=0, diag_range=None)])
+
+
+def run_lifetime(make_engine):
+    """Batches that outlive their engine (an Engine closed, or collected, before its SolvedBatch /
+    ResidentBatch): release and every other call on them must not touch the dead context."""
+    import pytest
+    from biseqt_b200._ffi import BsqError
+    rng = np.random.default_rng(8)
+    o = rng.integers(0, 4, 40).astype(np.uint8)
+    codes = np.concatenate([o, o])
+    args = ([0], [40], [40], [40], 0, 0, np.eye(4), -1.0, -1.0)
+    eng = make_engine()
+    sb = eng.solve(codes, *args)
+    rb = eng.upload(codes, *args)
+    rb.run()
+    eng.close()
+    with pytest.raises(BsqError):
+        sb.traceback()
+    with pytest.raises(BsqError):
+        rb.run()
+    with pytest.raises(BsqError):
+        rb.fetch()
+    sb.release()
+    rb.release()
+    eng2 = make_engine()      # a fresh context is unaffected
+    try:
+        sb2 = eng2.solve(codes, *args)
+        assert sb2.traceback().transcript(0) == 'M' * 40
+        sb2.release()
+    finally:
+        eng2.close()
 
 
 def run_table_scores(eng, seed):

@@ -76,6 +76,10 @@ def test_emu_edge_cases(emu_engine):
     pc.run_edge_cases(emu_engine)
 
 
+def test_emu_lifetime(emu_lib):
+    pc.run_lifetime(lambda: batch.Engine(0, lib=emu_lib))
+
+
 def test_emu_table_scores(emu_engine):
     pc.run_table_scores(emu_engine, seed=71)
 

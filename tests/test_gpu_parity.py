@@ -84,6 +84,10 @@ def test_gpu_edge_cases(gpu_engine):
     pc.run_edge_cases(gpu_engine)
 
 
+def test_gpu_lifetime():
+    pc.run_lifetime(lambda: batch.Engine(0))
+
+
 def test_gpu_table_scores(gpu_engine):
     pc.run_table_scores(gpu_engine, seed=71)
 
@@ -121,11 +125,12 @@ def _workload(kind, npairs, seed):
     return bw.make(kind, npairs, seed)
 
 
-@pytest.mark.parametrize('kind', ['c2_int', 'c2_logodds', 'c3_int', 'c3_logodds'])
+@pytest.mark.parametrize('kind', ['c1', 'c2_int', 'c2_logodds', 'c3_int', 'c3_logodds', 'c3_blocal_int',
+                                  'c3_blocal_logodds', 'c4_int'])
 def test_gpu_bench_shapes_vs_oracle(gpu_engine, kind):
-    """The bench's own workload generators (BASELINE.json configs[1] and [2]) at
-    a size the oracle finishes in seconds, every pair compared."""
-    npairs = 4000 if kind.startswith('c2') else 24
+    """The bench's own workload generators (BASELINE.json configs[0]..[3] and the banded
+    LOCAL variant of configs[2]) at a size the oracle finishes in seconds, every pair compared."""
+    npairs = {'c1': 1, 'c4_int': 4}.get(kind, 4000 if kind.startswith('c2') else 24)
     w = _workload(kind, npairs, seed=5)
     r = gpu_engine.align(w['codes'], w['o_off'], w['o_len'], w['m_off'], w['m_len'], w['mode'],
                          w['type'], w['subst'], w['go'], w['ge'], dmin=w.get('dmin'), dmax=w.get('dmax'))
@@ -140,6 +145,36 @@ def test_gpu_bench_shapes_vs_oracle(gpu_engine, kind):
     etx = lean.transcripts(e)
     for i in range(npairs):
         assert r.transcript(i) == etx[i], 'pair %d' % i
+
+
+def test_gpu_vs_compiled_reference_directly(gpu_engine, capfd):
+    """Engine output against the UNMODIFIED reference library itself (oracle/_ref/pwlib.so,
+    shipped to the GPU box prebuilt), not through the lean restatement: a shared misreading
+    in lean_oracle.c cannot mask a kernel bug here."""
+    from oracle import pwref
+    if not pwref.available():
+        pytest.skip('oracle/_ref/pwlib.so not present on this box')
+    from tests.gen import random_problem
+    from tests.util import engine_batch
+    rng = np.random.default_rng(2024)
+    n_ok = 0
+    for it in range(600):
+        pr = random_problem(rng, max_len=13 if it % 3 else 60)
+        a = lean.align(pr['origin'], pr['mutant'], pr['subst'], pr['go'], pr['ge'], pr['mode'],
+                       pr['type'], pr['diag_range'])
+        b = pwref.align(pr['origin'], pr['mutant'], pr['subst'].tolist(), pr['go'], pr['ge'],
+                        pr['mode'], pr['type'], pr['diag_range'], will_abort=(a['status'] == 4))
+        r = engine_batch(gpu_engine, [pr])
+        st = int(r.status[0])
+        assert st == b['status'], it
+        if st in (0, 2, 4):
+            assert float(r.score[0]) == b['score'] and (int(r.end_x[0]), int(r.end_y[0])) == tuple(b['end']), it
+        if st == 0:
+            assert r.transcript(0) == b['transcript'], it
+            assert (int(r.start_x[0]), int(r.start_y[0])) == tuple(b['start']), it
+            n_ok += 1
+    capfd.readouterr()
+    assert n_ok > 300
 
 
 def _rescore(w, r, i):

@@ -33,9 +33,9 @@ if ROOT not in sys.path:
 
 import bench_workloads as bw  # noqa: E402
 
-WORKLOAD_PAIRS = {'c2_int': 1000000, 'c2_logodds': 1000000, 'c3_int': 32768, 'c3_logodds': 32768,
-                  'c3_blocal_int': 32768, 'c3_blocal_logodds': 32768,
-                  'c4_int': 4096, 'c1': 1, 'c2w_int': 400000, 'c5_int': 1, 'c5_logodds': 1, 'c5s_int': 1, 'c5s_logodds': 1}
+WORKLOAD_PAIRS = {'c2_int': 1000000, 'c2_logodds': 1000000, 'c3_int': 100000, 'c3_logodds': 100000,
+                  'c3_blocal_int': 100000, 'c3_blocal_logodds': 100000,
+                  'c4_int': 10000, 'c1': 1, 'c2w_int': 400000, 'c5_int': 1, 'c5_logodds': 1, 'c5s_int': 1, 'c5s_logodds': 1}
 
 
 # which SM pipes each microbenchmarked rate (bsq_microbench, csrc/bsq_microbench.cu) spans; the
@@ -291,7 +291,7 @@ def pinned_copy(eng, a):
     return p
 
 
-def measure(eng, w, steps, warmup, sampler_gpu, do_e2e=True):
+def measure(eng, w, steps, warmup, sampler_gpu, do_e2e=True, compact=True):
     """Returns dict with resident + e2e timings for workload w on this rank."""
     from biseqt_b200 import batch
     N = len(w['o_len'])
@@ -321,36 +321,65 @@ def measure(eng, w, steps, warmup, sampler_gpu, do_e2e=True):
     rb.release()
     # ---- end to end: pinned host buffers in, pinned host buffers out ------
     if do_e2e:
-        pin = {k: pinned_copy(eng, np.ascontiguousarray(w[k])) for k in ('codes', 'o_off', 'o_len', 'm_off', 'm_len')}
-        if w['mode'] == 1:
-            kw = dict(dmin=pinned_copy(eng, w['dmin']), dmax=pinned_copy(eng, w['dmax']))
-        cap = int(w['o_len'].astype(np.int64).sum() + w['m_len'].astype(np.int64).sum())
-        outb = {'score': eng.pinned_empty(N, np.float64), 'tx_off': eng.pinned_empty(N + 1, np.int64),
-                'tx_buf': eng.pinned_empty(cap, np.uint8)}
-        for k in ('end_x', 'end_y', 'start_x', 'start_y', 'status'):
-            outb[k] = eng.pinned_empty(N, np.int32)
-        for _ in range(max(1, warmup - 1)):
-            eng.align(pin['codes'], pin['o_off'], pin['o_len'], pin['m_off'], pin['m_len'], *args, out=outb, **kw)
-        barrier()
-        t0 = time.perf_counter()
-        h2d = d2h = 0
-        plan_ms, call_ms = [], []
-        for _ in range(steps):
-            r = eng.align(pin['codes'], pin['o_off'], pin['o_len'], pin['m_off'], pin['m_len'], *args, out=outb, **kw)
-            tt = eng.timing()
-            h2d, d2h = tt['h2d_bytes'], tt['d2h_bytes']
-            launches += tt['fill_launches']
-            plan_ms.append(tt['plan_ms'])
-            call_ms.append(tt['call_ms'])
-        out['e2e_s'] = time.perf_counter() - t0
-        out['e2e_breakdown_ms'] = {'python_call': 1e3 * out['e2e_s'] / steps, 'c_call': float(np.mean(call_ms)),
-                                   'host_plan': float(np.mean(plan_ms)), 'device_span': tt['total_ms'],
-                                   'fill_kernels': tt['fill_ms'], 'chunks': tt['chunks']}
-        out['h2d'], out['d2h'] = h2d, d2h
-        out['ok_frac'] = float((r.status == 0).mean())
-        out['result'] = r          # the last timed call's output (pinned buffers), for the parity verdict
+        out.update(measure_e2e(eng, w, steps, warmup, compact=compact))
+        launches += out.pop('e2e_launches')
         out['launches'] = launches
-        barrier()
+    return out
+
+
+def measure_e2e(eng, w, steps, warmup, compact):
+    """The public batch call (Engine.align -> bsq_align_batch) from pinned HOST buffers to pinned
+    host buffers, H2D and D2H inside the timed region.  compact: the DNA forms of the two big
+    arrays -- sequences four letters per byte (BSQ_F_CODES_2BIT), transcripts four ops per byte
+    (BSQ_F_TX_2BIT), and no offset arrays when the pairs lie back to back in codes[]."""
+    from biseqt_b200 import batch
+    N = len(w['o_len'])
+    args = (w['mode'], w['type'], w['subst'], w['go'], w['ge'])
+    kw = {}
+    if w['mode'] == 1:
+        kw = dict(dmin=pinned_copy(eng, w['dmin']), dmax=pinned_copy(eng, w['dmax']))
+    cap = int(w['o_len'].astype(np.int64).sum() + w['m_len'].astype(np.int64).sum())
+    pin = {k: pinned_copy(eng, np.ascontiguousarray(w[k])) for k in ('o_len', 'm_len')}
+    if compact:
+        pin['codes'] = pinned_copy(eng, batch.pack_codes_2bit(w['codes']))
+        kw.update(codes_2bit=True, ncodes=len(w['codes']), tx_2bit=True)
+        cap = cap // 4 + 64
+    else:
+        pin['codes'] = pinned_copy(eng, np.ascontiguousarray(w['codes']))
+    if compact and w.get('back_to_back'):
+        pin['o_off'] = pin['m_off'] = None
+    else:
+        pin['o_off'], pin['m_off'] = pinned_copy(eng, w['o_off']), pinned_copy(eng, w['m_off'])
+    outb = {'score': eng.pinned_empty(N, np.float64), 'tx_off': eng.pinned_empty(N + 1, np.int64),
+            'tx_buf': eng.pinned_empty(cap, np.uint8)}
+    for k in ('end_x', 'end_y', 'start_x', 'start_y', 'status'):
+        outb[k] = eng.pinned_empty(N, np.int32)
+    call = lambda: eng.align(pin['codes'], pin['o_off'], pin['o_len'], pin['m_off'], pin['m_len'], *args, out=outb, **kw)   # noqa: E731
+    for _ in range(max(1, warmup - 1)):
+        call()
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = launches = 0
+    plan_ms, call_ms = [], []
+    for _ in range(steps):
+        r = call()
+        tt = eng.timing()
+        h2d, d2h = tt['h2d_bytes'], tt['d2h_bytes']
+        launches += tt['fill_launches']
+        plan_ms.append(tt['plan_ms'])
+        call_ms.append(tt['call_ms'])
+    out = {'e2e_s': time.perf_counter() - t0}
+    out['e2e_breakdown_ms'] = {'python_call': 1e3 * out['e2e_s'] / steps, 'c_call': float(np.mean(call_ms)),
+                               'host_plan': float(np.mean(plan_ms)), 'device_span': tt['total_ms'],
+                               'fill_kernels': tt['fill_ms'], 'chunks': tt['chunks']}
+    out['h2d'], out['d2h'] = h2d, d2h
+    out['ok_frac'] = float((r.status == 0).mean())
+    out['result'] = r          # the last timed call's output (pinned buffers), for the parity verdict
+    out['e2e_launches'] = launches
+    out['e2e_form'] = ('2-bit packed sequences in, 2-bit packed transcripts out' +
+                       (', pairs back to back (no offset arrays)' if pin['o_off'] is None else '')) if compact \
+        else 'one byte per letter in, one byte per op out, int64 offsets'
+    barrier()
     return out
 
 
@@ -384,6 +413,8 @@ def main():
     ap.add_argument('--pairs', type=int, default=0, help='pairs per GPU (default: the config\'s size)')
     ap.add_argument('--no-extras', action='store_true', help='skip the secondary workloads')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline')
+    ap.add_argument('--extras', default='c2_logodds,c3_int,c3_logodds,c3_blocal_int,c3_blocal_logodds,c4_int,c5_int,c1',
+                    help='comma-separated secondary workloads (single GPU only)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     rank = int(os.environ.get('RANK', '0'))
@@ -417,7 +448,7 @@ def main():
 
     kind = args.workload
     npairs = args.pairs or WORKLOAD_PAIRS[kind]
-    w = bw.make(kind, npairs, seed=2 + 1000 * rank)     # every rank aligns its own shard
+    w = bw.make_device(eng, kind, npairs, seed=2 + 1000 * rank)     # every rank aligns its own shard
     m = measure(eng, w, args.steps, args.warmup, local)
 
     # whole-job numbers: all ranks' cells over the slowest rank's time
@@ -487,6 +518,7 @@ def main():
             'clocks': m['clocks'],
             'e2e': {'value': e2e, 'unit': 'GCUPS', 'h2d_bytes_per_step': m['h2d'], 'd2h_bytes_per_step': m['d2h'],
                     'pairs_per_s': pairs_all * args.steps / e2e_s, 'breakdown_ms': m.get('e2e_breakdown_ms'),
+                    'form': m.get('e2e_form'),
                     'note': 'bsq_align_batch from pinned host arrays: plan + H2D + fill + traceback + pack + D2H'},
             'gpu_launches': int(launches),
             'roofline': roofline,
@@ -494,12 +526,22 @@ def main():
             'status_ok_fraction': m['ok_frac'],
         }
 
+    if rank == 0 and world == 1:   # the same call with the one-byte forms of both arrays, for comparison
+        try:
+            mb = measure_e2e(eng, w, max(2, args.steps // 4), 2, compact=False)
+            line['e2e_byte_forms'] = {'value': m['cells'] * max(2, args.steps // 4) / mb['e2e_s'] / 1e9, 'unit': 'GCUPS',
+                                      'h2d_bytes_per_step': mb['h2d'], 'd2h_bytes_per_step': mb['d2h'], 'form': mb['e2e_form']}
+        except Exception as e:
+            line['e2e_byte_forms'] = {'error': str(e)}
+
     # secondary workloads (rank 0, single GPU): f64 path and the banded kernels
     if rank == 0 and world == 1 and not args.no_extras:
         extras = {}
         made = {}
-        for k2 in ('c2_logodds', 'c3_int', 'c3_logodds', 'c3_blocal_int', 'c3_blocal_logodds', 'c4_int', 'c5_int', 'c1'):
-            n2 = WORKLOAD_PAIRS[k2] if k2 != 'c2_logodds' else min(npairs, 250000)
+        for k2 in [k for k in args.extras.split(',') if k]:
+            n2 = min(WORKLOAD_PAIRS[k2], npairs) if k2.startswith('c2') else WORKLOAD_PAIRS[k2]
+            if args.pairs and not k2.startswith('c2') and WORKLOAD_PAIRS[k2] > 1:
+                n2 = max(1, min(n2, args.pairs * WORKLOAD_PAIRS[k2] // WORKLOAD_PAIRS[kind]))   # --pairs scales every batch
             try:
                 if k2 in ('c3_logodds', 'c3_blocal_int', 'c3_blocal_logodds') and 'c3_int' in made:
                     # the same pairs and bands as c3_int; other scores and / or banded LOCAL
@@ -512,7 +554,7 @@ def main():
                     w2.update(kind=k2, desc=w2['desc'].replace('B_OVERLAP', 'B_LOCAL' if 'blocal' in k2 else 'B_OVERLAP')
                               .replace('int +2/-3 go0 ge-2', 'log-odds' if k2.endswith('logodds') else 'int +2/-3 go0 ge-2'))
                 else:
-                    w2 = bw.make(k2, n2, seed=3)
+                    w2 = bw.make_device(eng, k2, n2, seed=3)
                     made[k2] = w2
                 st2 = max(2, args.steps // 2)
                 m2 = measure(eng, w2, st2, 3 if not k2.startswith('c5') else 1, local, do_e2e=True)
@@ -520,7 +562,8 @@ def main():
                 which2 = {'i32': 'IADD', 'i16x2': 'VADD2'}.get(m2['dtype'], 'DADD')
                 pk = roofline['pipe_rates_gops'].get(which2) if isinstance(roofline['pipe_rates_gops'], dict) else None
                 ach = m2['cells'] * st2 * opc2 / (m2['fill_ms'] * 1e-3) / 1e9
-                extras[k2] = {'workload': w2['desc'], 'dtype': m2['dtype'],
+                extras[k2] = {'workload': w2['desc'], 'dtype': m2['dtype'], 'e2e_form': m2.get('e2e_form'),
+                              'h2d_bytes_per_step': m2.get('h2d'), 'd2h_bytes_per_step': m2.get('d2h'),
                               'gcups': m2['cells'] * st2 / (m2['resident_ms'] * 1e-3) / 1e9,
                               'fill_only_gcups': m2['cells'] * st2 / (m2['fill_ms'] * 1e-3) / 1e9,
                               'e2e_gcups': m2['cells'] * st2 / m2['e2e_s'] / 1e9,

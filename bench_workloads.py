@@ -130,6 +130,49 @@ def make(kind, npairs, seed):
     raise ValueError(kind)
 
 
+def make_device(eng, kind, npairs, seed):
+    """The same workloads as :func:`make` for the batched configs (c2_*, c3_*, c4_*), generated on
+    the device (``bsq_generate_pairs``: rand_seq + MutationProcess.mutate, csrc/bsq_gen.cuh) so
+    that BASELINE.json's full sizes (10^6 / 10^5 / 10^4 pairs) take milliseconds instead of
+    minutes.  Same distributions and layout, different random stream than the numpy generator."""
+    L = 4
+    if kind in ('c2_int', 'c2_logodds', 'c2w_int'):
+        n = 250 if kind == 'c2w_int' else 150
+        g = st.generate_pairs(eng, npairs, n, L, 0.02, 0.005, 0.01, seed=seed, fixed_mutant_len=n)
+        if kind == 'c2_logodds':
+            S, go, ge = st.log_odds_scores(L, 0.05, 0.05, 0.1)
+        else:
+            S, go, ge = int_scores(1, -3), -5.0, -2.0
+        return dict(kind=kind, mode=STD_MODE, type=LOCAL, subst=S, go=go, ge=ge, codes=g['codes'], o_off=g['o_off'],
+                    o_len=g['o_len'], m_off=g['m_off'], m_len=g['m_len'], back_to_back=True,
+                    desc='%d pairs %dx%d bp, STD LOCAL, %s' % (npairs, n, n, 'int +1/-3 go-5 ge-2' if kind != 'c2_logodds' else 'log-odds'))
+    if kind in ('c3_int', 'c3_logodds', 'c4_int', 'c3_blocal_int', 'c3_blocal_logodds'):
+        if kind == 'c4_int':
+            n, maxoff, gmax, sens = 50000, 25000, 0.15, 0.99
+        else:
+            n, maxoff = 10000, 5000
+        g = st.generate_pairs(eng, npairs, n, L, 0.03, 0.06, 0.12, seed=seed, max_offset=maxoff)
+        off, mlen = g['src_off'].astype(np.int64), g['m_len'].astype(np.int64)
+        if kind == 'c4_int':
+            r = band.band_radii(band.expected_overlap_len(n, mlen, off, gmax), gmax, sens)
+        else:
+            r = np.full(npairs, 64)
+        dmin = np.maximum(off - r, -mlen).astype(np.int32)
+        dmax = np.minimum(off + r, n).astype(np.int32)
+        if kind.endswith('logodds'):
+            S, go, ge = st.log_odds_scores(L, 0.03, 0.06, 0.12)
+        else:
+            S, go, ge = int_scores(2, -3), 0.0, -2.0
+        btype = B_LOCAL if 'blocal' in kind else B_OVERLAP
+        return dict(kind=kind, mode=BANDED_MODE, type=btype, subst=S, go=go, ge=ge, codes=g['codes'], o_off=g['o_off'],
+                    o_len=g['o_len'], m_off=g['m_off'], m_len=g['m_len'], dmin=dmin, dmax=dmax, back_to_back=True,
+                    desc='%d pairs ~%d bp, %s, radius %s, %s' % (
+                        npairs, n, 'B_LOCAL' if btype == B_LOCAL else 'B_OVERLAP',
+                        '64' if kind != 'c4_int' else 'band_radius(K,.15,.99)~%d' % int(np.median(r)),
+                        'log-odds' if kind.endswith('logodds') else 'int +2/-3 go0 ge-2'))
+    return make(kind, npairs, seed)
+
+
 def count_cells(w):
     """DP cells the reference would fill (pw.c:59-61), vectorised closed form."""
     n = w['o_len'].astype(np.int64)

@@ -35,13 +35,40 @@ def _c(a, dt):
     return a
 
 
-class BatchResult(object):
-    """Arrays of a finished batch; transcripts are packed in ``tx_buf``."""
+F_CODES_2BIT, F_TX_2BIT = CONST['BSQ_F_CODES_2BIT'], CONST['BSQ_F_TX_2BIT']
+_OPS = np.frombuffer(b'MSID', dtype=np.uint8)
 
-    def __init__(self, score, end_x, end_y, start_x, start_y, status, tx_off, tx_buf):
+
+def pack_codes_2bit(codes):
+    """One letter per byte -> four letters per byte (``BSQ_F_CODES_2BIT``): letter j in bits
+    2*(j&3).. of byte j>>2.  Alphabets of at most 4 letters."""
+    c = np.ascontiguousarray(codes, dtype=np.uint8)
+    pad = (-len(c)) % 4
+    if pad:
+        c = np.concatenate([c, np.zeros(pad, np.uint8)])
+    q = c.reshape(-1, 4)
+    return (q[:, 0] | (q[:, 1] << 2) | (q[:, 2] << 4) | (q[:, 3] << 6)).astype(np.uint8)
+
+
+def unpack_ops_2bit(buf, lo, hi):
+    """Ops [lo, hi) of a ``BSQ_F_TX_2BIT`` transcript buffer as b'MSID' bytes."""
+    if hi <= lo:
+        return b''
+    b = np.asarray(buf[lo >> 2:(hi + 3) >> 2], dtype=np.uint8)
+    q = np.empty((len(b), 4), np.uint8)
+    for k in range(4):
+        q[:, k] = (b >> (2 * k)) & 3
+    return _OPS[q.reshape(-1)[(lo & 3):(lo & 3) + (hi - lo)]].tobytes()
+
+
+class BatchResult(object):
+    """Arrays of a finished batch; transcripts are packed in ``tx_buf`` (one byte per op, or
+    four ops per byte when the batch was run with ``tx_2bit``; ``tx_off`` counts ops either way)."""
+
+    def __init__(self, score, end_x, end_y, start_x, start_y, status, tx_off, tx_buf, tx_2bit=False):
         self.score, self.end_x, self.end_y = score, end_x, end_y
         self.start_x, self.start_y, self.status = start_x, start_y, status
-        self.tx_off, self.tx_buf = tx_off, tx_buf
+        self.tx_off, self.tx_buf, self.tx_2bit = tx_off, tx_buf, tx_2bit
 
     def __len__(self):
         return len(self.score)
@@ -49,6 +76,8 @@ class BatchResult(object):
     def transcript(self, i):
         if self.tx_off is None:
             return None
+        if self.tx_2bit:
+            return unpack_ops_2bit(self.tx_buf, int(self.tx_off[i]), int(self.tx_off[i + 1])).decode()
         return bytes(self.tx_buf[self.tx_off[i]:self.tx_off[i + 1]]).decode()
 
     def transcripts(self):
@@ -107,7 +136,7 @@ class Engine(object):
         arr = np.frombuffer(ffi.buffer(p, max(nbytes, 1)), dtype=dtype, count=int(n))
         return arr
 
-    def _params(self, mode, type, subst, go, ge, dtype=DTYPE_AUTO, max_new_mins=-1):
+    def _params(self, mode, type, subst, go, ge, dtype=DTYPE_AUTO, max_new_mins=-1, flags=0):
         S = np.ascontiguousarray(np.asarray(subst, dtype=np.float64))
         assert S.ndim == 2 and S.shape[0] == S.shape[1], 'subst must be L x L'
         prm = ffi.new('bsq_params*')
@@ -117,20 +146,29 @@ class Engine(object):
         prm.go, prm.ge = float(go), float(ge)
         prm.subst = ffi.cast('double*', S.ctypes.data)
         prm.dtype = int(dtype)
+        prm.flags = int(flags)
         return prm, S
 
     def align(self, codes, o_off, o_len, m_off, m_len, mode, type, subst, go, ge,
               dmin=None, dmax=None, dtype=DTYPE_AUTO, transcripts=True, out=None,
-              max_new_mins=-1):
+              max_new_mins=-1, codes_2bit=False, ncodes=None, tx_2bit=False):
         """dptable_init + solve + traceback + free for a whole batch
         (``bsq_align_batch``).  Returns :class:`BatchResult`.  ``out`` may hold
-        preallocated (e.g. pinned) arrays under the result's field names."""
+        preallocated (e.g. pinned) arrays under the result's field names.
+
+        Compact forms of what crosses PCIe (alphabets of <= 4 letters): ``codes_2bit`` --
+        ``codes`` holds four letters per byte (:func:`pack_codes_2bit`; ``ncodes`` = number of
+        letters, default 4 * len(codes)); ``tx_2bit`` -- transcripts come back four ops per byte;
+        ``o_off = m_off = None`` -- the pairs lie back to back in ``codes``
+        (origin_0 | mutant_0 | origin_1 | ...), no offsets are uploaded."""
         codes = _c(codes, np.uint8)
         o_off, m_off = _c(o_off, np.int64), _c(m_off, np.int64)
         o_len, m_len = _c(o_len, np.int32), _c(m_len, np.int32)
         dmin, dmax = _c(dmin, np.int32), _c(dmax, np.int32)
         N = len(o_len)
-        prm, S = self._params(mode, type, subst, go, ge, dtype, max_new_mins)
+        flags = (F_CODES_2BIT if codes_2bit else 0) | (F_TX_2BIT if tx_2bit else 0)
+        prm, S = self._params(mode, type, subst, go, ge, dtype, max_new_mins, flags)
+        nletters = int(ncodes) if ncodes is not None else (4 * len(codes) if codes_2bit else len(codes))
         out = out or {}
 
         def arr(name, dt, n):
@@ -156,13 +194,13 @@ class Engine(object):
                 assert tx_buf.dtype == np.uint8
                 cap = len(tx_buf)
             else:
-                cap = worst_case()
+                cap = worst_case() // 4 + 64 if tx_2bit else worst_case()
                 tx_buf = np.empty(max(cap, 1), dtype=np.uint8)
         total = ffi.new('int64_t*')
 
         def call():
             return self.lib.bsq_align_batch(
-                self.ctx, prm, N, _ptr(codes, 'uint8_t*'), len(codes),
+                self.ctx, prm, N, _ptr(codes, 'uint8_t*'), nletters,
                 _ptr(o_off, 'int64_t*'), _ptr(o_len, 'int32_t*'),
                 _ptr(m_off, 'int64_t*'), _ptr(m_len, 'int32_t*'),
                 _ptr(dmin, 'int32_t*'), _ptr(dmax, 'int32_t*'),
@@ -170,30 +208,34 @@ class Engine(object):
                 _ptr(start_x, 'int32_t*'), _ptr(start_y, 'int32_t*'), _ptr(status, 'int32_t*'),
                 _ptr(tx_off, 'int64_t*'), _ptr(tx_buf, 'char*'), cap, total)
         rc = call()
-        if rc == ERR_CAPACITY and transcripts and cap < worst_case():   # caller's buffer too small: use our own
-            cap = worst_case()
+        full = worst_case() // 4 + 64 if tx_2bit else worst_case()
+        if rc == ERR_CAPACITY and transcripts and cap < full:   # caller's buffer too small: use our own
+            cap = full
             tx_buf = np.empty(max(cap, 1), dtype=np.uint8)
             rc = call()
         if rc != 0:
             raise BsqError('bsq_align_batch failed (%d): %s' % (rc, self._err()))
         return BatchResult(score[:N], end_x[:N], end_y[:N], start_x[:N], start_y[:N],
-                           status[:N], None if tx_off is None else tx_off[:N + 1], tx_buf)
+                           status[:N], None if tx_off is None else tx_off[:N + 1], tx_buf, tx_2bit=tx_2bit)
 
     def solve(self, codes, o_off, o_len, m_off, m_len, mode, type, subst, go, ge,
-              dmin=None, dmax=None, dtype=DTYPE_AUTO, max_new_mins=-1):
+              dmin=None, dmax=None, dtype=DTYPE_AUTO, max_new_mins=-1, codes_2bit=False, ncodes=None,
+              tx_2bit=False):
         """dptable_init + dptable_solve; tables stay in HBM (``bsq_solve_batch``)."""
         codes = _c(codes, np.uint8)
         o_off, m_off = _c(o_off, np.int64), _c(m_off, np.int64)
         o_len, m_len = _c(o_len, np.int32), _c(m_len, np.int32)
         dmin, dmax = _c(dmin, np.int32), _c(dmax, np.int32)
         N = len(o_len)
-        prm, S = self._params(mode, type, subst, go, ge, dtype, max_new_mins)
+        flags = (F_CODES_2BIT if codes_2bit else 0) | (F_TX_2BIT if tx_2bit else 0)
+        prm, S = self._params(mode, type, subst, go, ge, dtype, max_new_mins, flags)
+        nletters = int(ncodes) if ncodes is not None else (4 * len(codes) if codes_2bit else len(codes))
         score = np.empty(N, np.float64)
         end_x, end_y = np.empty(N, np.int32), np.empty(N, np.int32)
         status = np.empty(N, np.int32)
         hb = ffi.new('bsq_batch**')
         rc = self.lib.bsq_solve_batch(
-            self.ctx, prm, N, _ptr(codes, 'uint8_t*'), len(codes),
+            self.ctx, prm, N, _ptr(codes, 'uint8_t*'), nletters,
             _ptr(o_off, 'int64_t*'), _ptr(o_len, 'int32_t*'),
             _ptr(m_off, 'int64_t*'), _ptr(m_len, 'int32_t*'),
             _ptr(dmin, 'int32_t*'), _ptr(dmax, 'int32_t*'),
@@ -202,10 +244,11 @@ class Engine(object):
         if rc != 0:
             raise BsqError('bsq_solve_batch failed (%d): %s' % (rc, self._err()))
         cap = int(o_len.sum(dtype=np.int64) + m_len.sum(dtype=np.int64))
-        return SolvedBatch(self, hb[0], score, end_x, end_y, status, cap)
+        return SolvedBatch(self, hb[0], score, end_x, end_y, status, cap, tx_2bit)
 
     def upload(self, codes, o_off, o_len, m_off, m_len, mode, type, subst, go, ge,
-               dmin=None, dmax=None, dtype=DTYPE_AUTO, keep_tables=False, max_new_mins=-1):
+               dmin=None, dmax=None, dtype=DTYPE_AUTO, keep_tables=False, max_new_mins=-1,
+               codes_2bit=False, ncodes=None, tx_2bit=False):
         """Plan + H2D once (``bsq_batch_upload``); returns a :class:`ResidentBatch`
         whose ``run()`` executes with inputs and outputs resident in HBM."""
         codes = _c(codes, np.uint8)
@@ -213,17 +256,19 @@ class Engine(object):
         o_len, m_len = _c(o_len, np.int32), _c(m_len, np.int32)
         dmin, dmax = _c(dmin, np.int32), _c(dmax, np.int32)
         N = len(o_len)
-        prm, S = self._params(mode, type, subst, go, ge, dtype, max_new_mins)
+        flags = (F_CODES_2BIT if codes_2bit else 0) | (F_TX_2BIT if tx_2bit else 0)
+        prm, S = self._params(mode, type, subst, go, ge, dtype, max_new_mins, flags)
+        nletters = int(ncodes) if ncodes is not None else (4 * len(codes) if codes_2bit else len(codes))
         hb = ffi.new('bsq_batch**')
         rc = self.lib.bsq_batch_upload(
-            self.ctx, prm, N, _ptr(codes, 'uint8_t*'), len(codes),
+            self.ctx, prm, N, _ptr(codes, 'uint8_t*'), nletters,
             _ptr(o_off, 'int64_t*'), _ptr(o_len, 'int32_t*'),
             _ptr(m_off, 'int64_t*'), _ptr(m_len, 'int32_t*'),
             _ptr(dmin, 'int32_t*'), _ptr(dmax, 'int32_t*'), int(bool(keep_tables)), hb)
         if rc != 0:
             raise BsqError('bsq_batch_upload failed (%d): %s' % (rc, self._err()))
         cap = int(o_len.sum(dtype=np.int64) + m_len.sum(dtype=np.int64))
-        return ResidentBatch(self, hb[0], N, cap)
+        return ResidentBatch(self, hb[0], N, cap, tx_2bit)
 
     def microbench(self, which):
         """Measured issue rate (thread-ops/s, whole GPU) of one pipe; ``which`` is a
@@ -271,10 +316,10 @@ def _batch_stats(engine, handle, n):
 class SolvedBatch(object):
     """A solved batch whose pointer tables are still resident (``bsq_batch``)."""
 
-    def __init__(self, engine, handle, score, end_x, end_y, status, cap):
+    def __init__(self, engine, handle, score, end_x, end_y, status, cap, tx_2bit=False):
         self.engine, self.handle = engine, handle
         self.score, self.end_x, self.end_y, self.status = score, end_x, end_y, status
-        self._cap = cap
+        self._cap, self._tx_2bit = (cap // 4 + 64 if tx_2bit else cap), tx_2bit
 
     def traceback(self):
         N = len(self.score)
@@ -290,7 +335,7 @@ class SolvedBatch(object):
         if rc != 0:
             raise BsqError('bsq_traceback_batch failed (%d): %s' % (rc, self.engine._err()))
         return BatchResult(self.score, self.end_x, self.end_y, start_x, start_y, status,
-                           tx_off, tx_buf)
+                           tx_off, tx_buf, tx_2bit=self._tx_2bit)
 
     def stats(self):
         """Device-side Alignment post-processing (after :meth:`traceback`)."""
@@ -311,8 +356,9 @@ class SolvedBatch(object):
 class ResidentBatch(object):
     """Inputs uploaded once; ``run()`` = fill + traceback + packing on the device."""
 
-    def __init__(self, engine, handle, n, cap):
-        self.engine, self.handle, self.n, self._cap = engine, handle, n, cap
+    def __init__(self, engine, handle, n, cap, tx_2bit=False):
+        self.engine, self.handle, self.n = engine, handle, n
+        self._cap, self._tx_2bit = (cap // 4 + 64 if tx_2bit else cap), tx_2bit
 
     def run(self, traceback=True):
         rc = self.engine.lib.bsq_batch_run(self.handle, int(bool(traceback)))
@@ -332,7 +378,8 @@ class ResidentBatch(object):
             _ptr(tx_off, 'int64_t*'), _ptr(tx_buf, 'char*'), self._cap, total)
         if rc != 0:
             raise BsqError('bsq_batch_fetch failed (%d): %s' % (rc, self.engine._err()))
-        return BatchResult(score, ints[0], ints[1], ints[2], ints[3], ints[4], tx_off, tx_buf)
+        return BatchResult(score, ints[0], ints[1], ints[2], ints[3], ints[4], tx_off, tx_buf,
+                           tx_2bit=self._tx_2bit and transcripts)
 
     def stats(self):
         """Device-side Alignment post-processing (after ``run(traceback=True)``)."""

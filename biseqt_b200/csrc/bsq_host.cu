@@ -17,6 +17,7 @@
 
 #include "../../include/bsqgpu.h"
 #include "bsq_post.cuh"
+#include "bsq_gen.cuh"
 #include "bsq_launch.h"
 
 int bsq_microbench_impl(int sms, cudaStream_t st, int which, double* out, std::string* err);
@@ -62,18 +63,18 @@ struct PinBuf {
 
 struct BufSet {  // everything one batch needs in HBM
   DevBuf codes, pairs, ptr, slots, packed, score, ex, ey, sx, sy, status, txlen, txoff, tiles,
-      subst, counters, colh, colf, total, k3pairs, k3sync, k3res, ooff, moff, flags;
+      subst, counters, colh, colf, total, k3pairs, k3sync, k3res, ooff, moff, flags, codes2, packed2;
   PinBuf hpairs, hsmall;
   size_t bytes() const {  // HBM currently held
     const DevBuf* all[] = {&codes, &pairs, &ptr, &slots, &packed, &score, &ex, &ey, &sx, &sy, &status,
-                           &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff, &flags};
+                           &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff, &flags, &codes2, &packed2};
     size_t n = 0;
     for (const DevBuf* b : all) n += b->cap;
     return n;
   }
   void release() {
     DevBuf* all[] = {&codes, &pairs, &ptr, &slots, &packed, &score, &ex, &ey, &sx, &sy, &status,
-                     &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff, &flags};
+                     &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff, &flags, &codes2, &packed2};
     for (DevBuf* b : all) b->release();
     hpairs.release();
     hsmall.release();
@@ -192,6 +193,7 @@ struct bsq_ctx {
   PinBuf htotals;                  // pinned: running transcript totals per chunk
   std::vector<PlanItem> plan_items;  // planner scratch, kept across calls (no page faults)
   std::vector<int64_t> plan_order, plan_ptr_off, plan_slot_off, plan_sorted;
+  std::vector<int64_t> plan_ooff, plan_moff;   // offsets of a back-to-back batch given without o_off / m_off
   std::vector<char> plan_gather;
   std::string err;
   bsq_timing tm;
@@ -451,6 +453,8 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   if (prm->max_new_mins > 0)
     return fail(ctx, BSQ_ERR_ARG, "max_new_mins > 0 is undefined behaviour in the reference (_pw_internals.c:236-243); not supported");
   if (!std::isfinite(prm->go) || !std::isfinite(prm->ge)) return fail(ctx, BSQ_ERR_ARG, "go/ge must be finite");
+  if ((prm->flags & BSQ_F_CODES_2BIT) && L > 4) return fail(ctx, BSQ_ERR_ARG, "BSQ_F_CODES_2BIT needs an alphabet of at most 4 letters");
+  if (prm->flags & ~(BSQ_F_CODES_2BIT | BSQ_F_TX_2BIT)) return fail(ctx, BSQ_ERR_ARG, "unknown bits in params.flags");
   P.prm = *prm;
   P.subst.assign(prm->subst, prm->subst + L * L);
   for (double& v : P.subst) {
@@ -466,7 +470,19 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
 
   // one parallel pass over the lengths: maxima (for the arithmetic / overflow decisions), input
   // validation, and whether every pair has the same shape
-  struct Scan { int64_t max_n = 0, max_m = 0; int bad = 0, uniform = 1; };
+  // o_off == m_off == NULL: the pairs lie back to back in codes[].  A uniform batch never needs the
+  // offsets on the host (the device derives them); every other plan gets them materialised first.
+  const bool implicit = (o_off == nullptr);
+  auto materialize_offsets = [&]() {
+    std::vector<int64_t>& io = ctx->plan_ooff;
+    std::vector<int64_t>& im = ctx->plan_moff;
+    if ((int64_t)io.size() < N) { io.resize((size_t)N); im.resize((size_t)N); }
+    int64_t pos = 0;
+    for (int64_t i = 0; i < N; i++) { io[(size_t)i] = pos; pos += o_len[i]; im[(size_t)i] = pos; pos += m_len[i]; }
+    o_off = io.data();
+    m_off = im.data();
+  };
+  struct Scan { int64_t max_n = 0, max_m = 0, tot = 0; int bad = 0, uniform = 1; };
   std::vector<Scan> scans(16);
   {
     const int n0 = N ? o_len[0] : 0, m0 = N ? m_len[0] : 0;
@@ -475,21 +491,23 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
       Scan sc;
       for (int64_t i = i0; i < i1; i++) {
         const int n = o_len[i], m = m_len[i];
-        if (n < 0 || m < 0 || o_off[i] < 0 || m_off[i] < 0 || o_off[i] + n > ncodes || m_off[i] + m > ncodes) { sc.bad = 1; continue; }
+        if (n < 0 || m < 0 || (!implicit && (o_off[i] < 0 || m_off[i] < 0 || o_off[i] + n > ncodes || m_off[i] + m > ncodes))) { sc.bad = 1; continue; }
         sc.max_n = std::max<int64_t>(sc.max_n, n);
         sc.max_m = std::max<int64_t>(sc.max_m, m);
+        sc.tot += (int64_t)n + m;
         if (n != n0 || m != m0 || (family == 2 && (dmin[i] != lo0 || dmax[i] != hi0))) sc.uniform = 0;
       }
       scans[t] = sc;
     });
   }
-  int64_t scan_n = 0, scan_m = 0;
+  int64_t scan_n = 0, scan_m = 0, scan_tot = 0;
   bool all_uniform = N > 0;
   for (const Scan& sc : scans) {
     if (sc.bad) return fail(ctx, BSQ_ERR_ARG, "negative length or sequence range outside codes[]");
-    scan_n = std::max(scan_n, sc.max_n); scan_m = std::max(scan_m, sc.max_m);
+    scan_n = std::max(scan_n, sc.max_n); scan_m = std::max(scan_m, sc.max_m); scan_tot += sc.tot;
     if (!sc.uniform) all_uniform = false;
   }
+  if (implicit && scan_tot > ncodes) return fail(ctx, BSQ_ERR_ARG, "back-to-back pairs do not fit codes[]");
   // geometry depends on the arithmetic; decide it up front from the scores and maxima
   bool f64_geom = true;
   {
@@ -613,7 +631,9 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
         ch.idx_hi = ch.first + ch.count;
         ch.code_end = 0;
       }
-      {  // last byte of codes[] each chunk reads (pairs need not be laid out in order)
+      if (implicit) {
+        for (int64_t c = 0; c < NC; c++) P.chunks[(size_t)c].code_end = std::min<int64_t>(N, (c + 1) * ppc) * ((int64_t)o_len[0] + m_len[0]);
+      } else {  // last byte of codes[] each chunk reads (pairs need not be laid out in order)
         std::vector<int64_t> ends((size_t)NC * 16, 0);
         const int n = o_len[0], m = m_len[0];
         parallel_for(N, [&](int t, int64_t i0, int64_t i1) {
@@ -642,6 +662,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
       return BSQ_SUCCESS;
     }
   }
+  if (implicit) materialize_offsets();
   const bool plan_dbg = hk.plan_debug;
   const auto tp0 = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) {
@@ -1148,22 +1169,53 @@ int upload_pairs(bsq_ctx* ctx, BufSet& B, const Plan& P, cudaStream_t st) {
     ctx->tm.h2d_bytes += (int64_t)sizeof(BsqPair) * E;
     return BSQ_SUCCESS;
   }
-  if (!B.ooff.ensure(8 * (size_t)E) || !B.moff.ensure(8 * (size_t)E)) return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (offsets)");
-  BSQ_CK(ctx, cudaMemcpyAsync(B.ooff.p, P.src_o_off, 8 * (size_t)E, cudaMemcpyHostToDevice, st));
-  BSQ_CK(ctx, cudaMemcpyAsync(B.moff.p, P.src_m_off, 8 * (size_t)E, cudaMemcpyHostToDevice, st));
-  ctx->tm.h2d_bytes += 16 * E;
+  const bool have_off = P.src_o_off != nullptr;   // else: back-to-back pairs, offsets are arithmetic
+  if (have_off) {
+    if (!B.ooff.ensure(8 * (size_t)E) || !B.moff.ensure(8 * (size_t)E)) return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (offsets)");
+    BSQ_CK(ctx, cudaMemcpyAsync(B.ooff.p, P.src_o_off, 8 * (size_t)E, cudaMemcpyHostToDevice, st));
+    BSQ_CK(ctx, cudaMemcpyAsync(B.moff.p, P.src_m_off, 8 * (size_t)E, cudaMemcpyHostToDevice, st));
+    ctx->tm.h2d_bytes += 16 * E;
+  }
   const int grid = (int)((E + 255) / 256);
-  BSQ_LAUNCH(bsq_make_pairs_uniform, grid, 256, 0, st, (const long long*)B.ooff.as<long long>(),
-             (const long long*)B.moff.as<long long>(), (long long)E, P.uni, B.pairs.as<BsqPair>());
+  BSQ_LAUNCH(bsq_make_pairs_uniform, grid, 256, 0, st, have_off ? (const long long*)B.ooff.as<long long>() : (const long long*)nullptr,
+             have_off ? (const long long*)B.moff.as<long long>() : (const long long*)nullptr, (long long)E, P.uni, B.pairs.as<BsqPair>());
   BSQ_CK(ctx, cudaGetLastError());
   ctx->tm.fill_launches++;
   return BSQ_SUCCESS;
 }
 
+// bytes of codes[] as the caller holds them (one letter per byte, or four: BSQ_F_CODES_2BIT)
+inline int64_t codes_in_bytes(const bsq_params& prm, int64_t ncodes) {
+  return (prm.flags & BSQ_F_CODES_2BIT) ? (ncodes + 3) / 4 : ncodes;
+}
+
+// H2D of bytes [b0, b1) of the caller's codes[] on stream st; packed input is expanded to one byte
+// per letter right behind the copy (same stream), so that every kernel reads B.codes
+int upload_codes(bsq_ctx* ctx, BufSet& B, const bsq_params& prm, const uint8_t* codes, int64_t b0, int64_t b1, cudaStream_t st) {
+  if (b1 <= b0) return BSQ_SUCCESS;
+  if (!(prm.flags & BSQ_F_CODES_2BIT)) {
+    BSQ_CK(ctx, cudaMemcpyAsync((char*)B.codes.p + b0, codes + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st));
+    return BSQ_SUCCESS;
+  }
+  BSQ_CK(ctx, cudaMemcpyAsync((char*)B.codes2.p + b0, codes + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st));
+  const long long nb = b1 - b0;
+  const int grid = (int)((nb / 4 + 1 + 255) / 256);
+  BSQ_LAUNCH(bsq_unpack_2bit, grid, 256, 0, st, (const uint8_t*)(B.codes2.as<uint8_t>() + b0), nb, B.codes.as<uint8_t>() + 4 * b0);
+  BSQ_CK(ctx, cudaGetLastError());
+  ctx->tm.fill_launches++;
+  return BSQ_SUCCESS;
+}
+inline bool ensure_codes(BufSet& B, const bsq_params& prm, int64_t ncodes) {
+  if (!B.codes.ensure((size_t)ncodes + 64)) return false;
+  return !(prm.flags & BSQ_F_CODES_2BIT) || B.codes2.ensure((size_t)codes_in_bytes(prm, ncodes) + 16);
+}
+// packed input of a 4-letter alphabet cannot hold a letter >= alphabet_len
+inline bool codes_need_check(const bsq_params& prm) { return !((prm.flags & BSQ_F_CODES_2BIT) && prm.alphabet_len >= 4); }
+
 // every letter referenced by pair records [first, first + count) must be < alphabet_len; raises
 // B.flags[0] on the device (the fill / traceback kernels then return at once)
 int launch_check_codes(bsq_ctx* ctx, BufSet& B, const Plan& P, int64_t first, int64_t count, cudaStream_t st) {
-  if (count <= 0) return BSQ_SUCCESS;
+  if (count <= 0 || !codes_need_check(P.prm)) return BSQ_SUCCESS;
   const int grid = (int)((count * 32 + 127) / 128);
   BSQ_LAUNCH(bsq_check_codes, grid, 128, 0, st, (const uint8_t*)B.codes.as<uint8_t>(),
              (const BsqPair*)(B.pairs.as<BsqPair>() + first), (int)count, P.prm.alphabet_len, B.flags.as<int>());
@@ -1189,7 +1241,7 @@ int stage_k3(bsq_ctx* ctx, BufSet& B, const Plan& P, cudaStream_t st) {
 int stage_inputs(bsq_ctx* ctx, BufSet& B, Plan& P, const uint8_t* codes, int64_t ncodes, bool single_chunk) {
   const int64_t N = P.N, E = (int64_t)P.E;
   const int L = P.prm.alphabet_len;
-  bool ok = B.codes.ensure((size_t)ncodes + 16) && B.pairs.ensure(sizeof(BsqPair) * (size_t)std::max<int64_t>(E, 1)) &&
+  bool ok = ensure_codes(B, P.prm, ncodes) && B.pairs.ensure(sizeof(BsqPair) * (size_t)std::max<int64_t>(E, 1)) &&
             B.score.ensure(8 * (size_t)N) && B.ex.ensure(4 * (size_t)N) && B.ey.ensure(4 * (size_t)N) &&
             B.sx.ensure(4 * (size_t)N) && B.sy.ensure(4 * (size_t)N) && B.status.ensure(4 * (size_t)N) &&
             B.txlen.ensure(4 * (size_t)N) && B.subst.ensure(8 * (size_t)L * L) &&
@@ -1197,8 +1249,11 @@ int stage_inputs(bsq_ctx* ctx, BufSet& B, Plan& P, const uint8_t* codes, int64_t
             B.ptr.ensure(4 * (size_t)(single_chunk ? P.total_words : (P.half_words > 0 ? BSQ_ARENA_SLOTS * P.half_words : P.max_chunk_words)) + 64);
   if (!ok) { ctx->mem_avail = -1.0; return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed"); }
   cudaStream_t st = ctx->st;
-  if (ncodes > 0) BSQ_CK(ctx, cudaMemcpyAsync(B.codes.p, codes, (size_t)ncodes, cudaMemcpyHostToDevice, st));
-  ctx->tm.h2d_bytes += ncodes;
+  {
+    const int rcu = upload_codes(ctx, B, P.prm, codes, 0, codes_in_bytes(P.prm, ncodes), st);
+    if (rcu != BSQ_SUCCESS) return rcu;
+  }
+  ctx->tm.h2d_bytes += codes_in_bytes(P.prm, ncodes);
   {
     const int rcp = upload_pairs(ctx, B, P, st);
     if (rcp != BSQ_SUCCESS) return rcp;
@@ -1402,6 +1457,19 @@ int pack_transcripts(bsq_ctx* ctx, BufSet& B, const Plan& P) {
   return BSQ_SUCCESS;
 }
 
+// BSQ_F_TX_2BIT: words [w_lo, w_hi) of the 2-bit form of the packed byte transcripts (16 ops per
+// 32-bit word), converted on stream st and copied to tx_buf right behind
+int ship_tx_2bit(bsq_ctx* ctx, BufSet& B, long long nops, long long w_lo, long long w_hi, char* tx_buf, cudaStream_t st) {
+  if (w_hi <= w_lo) return BSQ_SUCCESS;
+  const int grid = (int)((w_hi - w_lo + 255) / 256);
+  BSQ_LAUNCH(bsq_tx_to_2bit, grid, 256, 0, st, (const char*)B.packed.as<char>(), nops, w_lo, w_hi, B.packed2.as<uint32_t>());
+  BSQ_CK(ctx, cudaGetLastError());
+  ctx->tm.fill_launches++;
+  BSQ_CK(ctx, cudaMemcpyAsync(tx_buf + 4 * w_lo, (const char*)B.packed2.p + 4 * w_lo, (size_t)(4 * (w_hi - w_lo)), cudaMemcpyDeviceToHost, st));
+  ctx->tm.d2h_bytes += 4 * (w_hi - w_lo);
+  return BSQ_SUCCESS;
+}
+
 int fetch_transcripts(bsq_ctx* ctx, BufSet& B, const Plan& P, int64_t* tx_off, char* tx_buf,
                       int64_t tx_cap, int64_t* tx_total) {
   const int64_t N = P.N;
@@ -1413,6 +1481,15 @@ int fetch_transcripts(bsq_ctx* ctx, BufSet& B, const Plan& P, int64_t* tx_off, c
   tx_off[N] = total;
   if (tx_total) *tx_total = total;
   ctx->tm.d2h_bytes += 8 * N + 8;
+  if (P.prm.flags & BSQ_F_TX_2BIT) {
+    const long long words = (total + 15) / 16;
+    if (4 * words > tx_cap) return fail(ctx, BSQ_ERR_CAPACITY, "tx_buf too small for the batch's transcripts");
+    if (!B.packed2.ensure((size_t)(4 * words + 16))) return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (2-bit transcripts)");
+    const int rc2 = ship_tx_2bit(ctx, B, total, 0, words, tx_buf, st);
+    if (rc2 != BSQ_SUCCESS) return rc2;
+    BSQ_CK(ctx, cudaStreamSynchronize(st));
+    return BSQ_SUCCESS;
+  }
   if (total > tx_cap) return fail(ctx, BSQ_ERR_CAPACITY, "tx_buf too small for the batch's transcripts");
   if (total > 0) {
     BSQ_CK(ctx, cudaMemcpyAsync(tx_buf, B.packed.p, (size_t)total, cudaMemcpyDeviceToHost, st));
@@ -1575,7 +1652,8 @@ int bsq_partition_pairs(int32_t mode, int64_t npairs, const int32_t* o_len, cons
 static int check_inputs(bsq_ctx* ctx, int64_t npairs, const uint8_t* codes, const int64_t* o_off,
                         const int32_t* o_len, const int64_t* m_off, const int32_t* m_len) {
   if (npairs < 0 || npairs >= ((int64_t)1 << 31)) return fail(ctx, BSQ_ERR_ARG, "npairs out of range");
-  if (npairs > 0 && (!codes || !o_off || !o_len || !m_off || !m_len)) return fail(ctx, BSQ_ERR_ARG, "NULL input array");
+  if (npairs > 0 && (!codes || !o_len || !m_len)) return fail(ctx, BSQ_ERR_ARG, "NULL input array");
+  if ((o_off == nullptr) != (m_off == nullptr)) return fail(ctx, BSQ_ERR_ARG, "o_off and m_off must both be given or both be NULL");
   return BSQ_SUCCESS;
 }
 
@@ -1782,27 +1860,34 @@ static int align_batch_once(bsq_ctx* ctx, const bsq_params* params, int64_t npai
   // started 7 ms late).  The other slices follow the pair records.
   const int NSL = 8;
   size_t evi = 2;  // events 0/1 bracket the call on the compute stream
-  if (!B.codes.ensure((size_t)ncodes + 16)) return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (codes)");
+  if (!params) return fail(ctx, BSQ_ERR_ARG, "params is NULL");
+  if ((params->flags & BSQ_F_CODES_2BIT) && params->alphabet_len > 4) return fail(ctx, BSQ_ERR_ARG, "BSQ_F_CODES_2BIT needs an alphabet of at most 4 letters");
+  if (!ensure_codes(B, *params, ncodes)) return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (codes)");
   cudaEvent_t ev_code[NSL];
-  int64_t slice_end[NSL];
-  const int64_t slice = ((ncodes + NSL - 1) / NSL + 255) / 256 * 256;
+  int64_t slice_end[NSL];      // in LETTERS (what Chunk.code_end counts)
+  int64_t slice_b0[NSL], slice_b1[NSL];   // in bytes of the caller's codes[]
+  const int64_t in_bytes = codes_in_bytes(*params, ncodes);
+  const int64_t lpb = (params->flags & BSQ_F_CODES_2BIT) ? 4 : 1;   // letters per input byte
+  const int64_t slice = ((in_bytes + NSL - 1) / NSL + 255) / 256 * 256;
   int nsl = 0;
-  for (int64_t off = 0; off < ncodes && nsl < NSL; off += slice, nsl++) {
-    const int64_t len = std::min<int64_t>(slice, ncodes - off);
+  for (int64_t off = 0; off < in_bytes && nsl < NSL; off += slice, nsl++) {
+    const int64_t len = std::min<int64_t>(slice, in_bytes - off);
     ev_code[nsl] = get_event(ctx, evi++);
-    slice_end[nsl] = off + len;
+    slice_b0[nsl] = off;
+    slice_b1[nsl] = off + len;
+    slice_end[nsl] = std::min<int64_t>(ncodes, (off + len) * lpb);
   }
   auto enqueue_slices = [&](int from, int to) -> int {
     for (int i = from; i < to && i < nsl; i++) {
-      const int64_t off = (int64_t)i * slice, len = slice_end[i] - off;
-      BSQ_CK(ctx, cudaMemcpyAsync((char*)B.codes.p + off, codes + off, (size_t)len, cudaMemcpyHostToDevice, sx));
+      const int rcu = upload_codes(ctx, B, *params, codes, slice_b0[i], slice_b1[i], sx);
+      if (rcu != BSQ_SUCCESS) return rcu;
       BSQ_CK(ctx, cudaEventRecord(ev_code[i], sx));
     }
     return BSQ_SUCCESS;
   };
   rc = enqueue_slices(0, 1);
   if (rc != BSQ_SUCCESS) return rc;
-  ctx->tm.h2d_bytes += ncodes;
+  ctx->tm.h2d_bytes += in_bytes;
 
   // ---- 1. plan on the host while the bytes fly
   const double t_plan = now_ms();
@@ -1843,6 +1928,8 @@ static int align_batch_once(bsq_ctx* ctx, const bsq_params* params, int64_t npai
   if (ok && want_trace) ok = B.slots.ensure((size_t)std::max<int64_t>(P.slot_bytes, 1));
   if (ok && want_tx) ok = B.txoff.ensure(8 * (N + 1)) && B.tiles.ensure(8 * (size_t)ntiles_max) &&
                           B.packed.ensure((size_t)std::max<int64_t>(P.slot_bytes, 1));
+  const bool tx2 = want_tx && (P.prm.flags & BSQ_F_TX_2BIT) != 0;
+  if (ok && tx2) ok = B.packed2.ensure((size_t)(P.slot_bytes / 4 + 64));
   if (!ok) { ctx->mem_avail = -1.0; cudaStreamSynchronize(sx); return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed"); }
 
   // ---- 2. pair records + score table right behind the first slice of sequence bytes, the rest of
@@ -1930,7 +2017,7 @@ static int align_batch_once(bsq_ctx* ctx, const bsq_params* params, int64_t npai
     return BSQ_SUCCESS;
   };
   if (per_chunk_out) {
-    long long shipped = 0;
+    long long shipped = 0, shipped_words = 0;
     for (size_t ci = 0; ci < NC; ci++) {
       const Chunk& ch = P.chunks[ci];
       const int64_t lo = ch.idx_lo, cnt = ch.idx_hi - ch.idx_lo;
@@ -1943,7 +2030,17 @@ static int align_batch_once(bsq_ctx* ctx, const bsq_params* params, int64_t npai
         BSQ_CK(ctx, cudaStreamSynchronize(sd));  // later chunks are already queued on the compute stream
         const long long upto = htot[ci + 1];
         ctx->tm.d2h_bytes += 8 * cnt + 8;
-        if (upto > tx_cap) { rc_cap = BSQ_ERR_CAPACITY; }
+        if (tx2) {
+          // whole 16-op words only; the word a chunk boundary cuts goes with the next chunk (its ops
+          // are packed by then: the chunks' pack kernels run in order on one stream)
+          const long long w_hi = (ci + 1 == NC) ? (upto + 15) / 16 : upto / 16;
+          if (4 * w_hi > tx_cap) { rc_cap = BSQ_ERR_CAPACITY; }
+          else if (rc_cap == BSQ_SUCCESS) {
+            rc = ship_tx_2bit(ctx, B, upto, shipped_words, w_hi, tx_buf, sd);
+            if (rc != BSQ_SUCCESS) return rc;
+            shipped_words = std::max(shipped_words, w_hi);
+          }
+        } else if (upto > tx_cap) { rc_cap = BSQ_ERR_CAPACITY; }
         else if (upto > shipped) {
           BSQ_CK(ctx, cudaMemcpyAsync(tx_buf + shipped, B.packed.as<char>() + shipped, (size_t)(upto - shipped), cudaMemcpyDeviceToHost, sd));
           ctx->tm.d2h_bytes += upto - shipped;
@@ -2110,6 +2207,84 @@ int bsq_microbench(bsq_ctx* ctx, int32_t which, double* ops_per_sec) {
   ctx->err.clear();
   BSQ_CK(ctx, cudaSetDevice(ctx->device));
   return bsq_microbench_impl(ctx->sms, ctx->st, which, ops_per_sec, &ctx->err);
+}
+
+int bsq_generate_pairs(bsq_ctx* ctx, const bsq_gen_params* gp, int64_t npairs, uint8_t* codes, int64_t codes_cap,
+                       int64_t* ncodes, int64_t* o_off, int32_t* o_len, int64_t* m_off, int32_t* m_len,
+                       int32_t* src_off, int64_t* tx_off, char* tx_buf, int64_t tx_cap) {
+  if (!ctx) return BSQ_ERR_ARG;
+  ctx->err.clear();
+  if (!gp || !ncodes || npairs < 0 || npairs >= ((int64_t)1 << 31)) return fail(ctx, BSQ_ERR_ARG, "bad argument");
+  if (npairs > 0 && (!codes || !o_off || !o_len || !m_off || !m_len)) return fail(ctx, BSQ_ERR_ARG, "NULL output array");
+  if ((tx_off == nullptr) != (tx_buf == nullptr)) return fail(ctx, BSQ_ERR_ARG, "tx_off and tx_buf go together");
+  if (gp->alphabet_len < 1 || gp->alphabet_len > 255 || gp->origin_len < 0 || gp->max_offset < 0 || gp->fixed_mutant_len < 0)
+    return fail(ctx, BSQ_ERR_ARG, "bad generator parameters");
+  if (!(gp->subst_prob >= 0 && gp->subst_prob < 1 && gp->go_prob >= 0 && gp->ge_prob < 1 && gp->go_prob <= gp->ge_prob))
+    return fail(ctx, BSQ_ERR_ARG, "need 0 <= subst_prob < 1 and 0 <= go_prob <= ge_prob < 1 (stochastics.py:128-141)");
+  *ncodes = 0;
+  if (tx_off) tx_off[0] = 0;
+  if (npairs == 0) return BSQ_SUCCESS;
+  BSQ_CK(ctx, cudaSetDevice(ctx->device));
+  BsqGenArgs G;
+  G.seed = gp->seed;
+  G.L = gp->alphabet_len; G.n = gp->origin_len; G.max_offset = gp->max_offset; G.fixed_mlen = gp->fixed_mutant_len;
+  G.subst_thr = (unsigned)std::floor(gp->subst_prob * 16777216.0);
+  G.go_thr = (unsigned)std::floor(gp->go_prob * 16777216.0);
+  G.ge_thr = (unsigned)std::floor(gp->ge_prob * 16777216.0);
+  G.npairs = npairs;
+  const size_t N = (size_t)npairs;
+  cudaStream_t st = ctx->st;
+  DevBuf dMlen, dTxlen, dOff, dBase, dTxbase, dCodes, dTx;
+  auto cleanup = [&] { dMlen.release(); dTxlen.release(); dOff.release(); dBase.release(); dTxbase.release(); dCodes.release(); dTx.release(); };
+  if (!dMlen.ensure(4 * N) || !dTxlen.ensure(4 * N) || !dOff.ensure(4 * N) || !dBase.ensure(8 * (N + 1)) || !dTxbase.ensure(8 * (N + 1))) {
+    cleanup();
+    return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (generator)");
+  }
+  const int gridp = (int)((npairs + 127) / 128);
+  BSQ_LAUNCH(bsq_gen_count, gridp, 128, 0, st, G, dMlen.as<int>(), dTxlen.as<int>(), dOff.as<int>());
+  std::vector<int32_t> txlen(N);
+  std::vector<int32_t> offs(N);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m_len, dMlen.p, 4 * N, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(txlen.data(), dTxlen.p, 4 * N, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(offs.data(), dOff.p, 4 * N, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { cleanup(); ctx->err = std::string("generator: ") + cudaGetErrorString(e); return BSQ_ERR_CUDA; }
+  std::vector<int64_t> base(N + 1), txbase(N + 1);
+  int64_t pos = 0, tpos = 0;
+  for (size_t i = 0; i < N; i++) {
+    base[i] = pos; txbase[i] = tpos;
+    o_off[i] = pos; o_len[i] = gp->origin_len;
+    m_off[i] = pos + gp->origin_len;
+    pos += (int64_t)gp->origin_len + m_len[i];
+    tpos += txlen[i];
+    if (src_off) src_off[i] = offs[i];
+    if (tx_off) tx_off[i + 1] = tpos;
+  }
+  base[N] = pos; txbase[N] = tpos;
+  *ncodes = pos + 16;
+  if (pos + 16 > codes_cap || (tx_buf && tpos > tx_cap)) { cleanup(); return fail(ctx, BSQ_ERR_CAPACITY, "codes / tx_buf too small for the generated pairs"); }
+  if (!dCodes.ensure((size_t)pos + 16) || (tx_buf && !dTx.ensure((size_t)std::max<int64_t>(tpos, 1)))) {
+    cleanup();
+    return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (generator output)");
+  }
+  e = cudaMemcpyAsync(dBase.p, base.data(), 8 * (N + 1), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dTxbase.p, txbase.data(), 8 * (N + 1), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync((char*)dCodes.p + pos, 0, 16, st);
+  if (e == cudaSuccess) {
+    const long long total = (long long)npairs * gp->origin_len;
+    const int grido = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)ctx->sms * 32));
+    BSQ_LAUNCH(bsq_gen_origins, grido, 256, 0, st, G, (const long long*)dBase.as<long long>(), dCodes.as<uint8_t>());
+    BSQ_LAUNCH(bsq_gen_write, gridp, 128, 0, st, G, (const long long*)dBase.as<long long>(), (const int*)dOff.as<int>(),
+               dCodes.as<uint8_t>(), (const long long*)dTxbase.as<long long>(), tx_buf ? dTx.as<char>() : (char*)nullptr);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(codes, dCodes.p, (size_t)pos + 16, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && tx_buf && tpos > 0) e = cudaMemcpyAsync(tx_buf, dTx.p, (size_t)tpos, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cleanup();
+  if (e != cudaSuccess) { ctx->err = std::string("generator: ") + cudaGetErrorString(e); return BSQ_ERR_CUDA; }
+  return BSQ_SUCCESS;
 }
 
 int bsq_batch_stats(bsq_batch* b, bsq_aln_stats* out) {

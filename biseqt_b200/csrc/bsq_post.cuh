@@ -493,6 +493,50 @@ __global__ void __launch_bounds__(128) bsq_check_codes(const uint8_t* codes, con
   if (worst >= L) *bad = 1;
 }
 
+// BSQ_F_CODES_2BIT: four letters per byte over PCIe, one byte per letter for the kernels (the
+// sequences are < 2 % of the bytes the fill moves, so the kernels keep their byte loads and the
+// link carries a quarter).  Thread t expands packed bytes [4t, 4t+4) into 16 letters.
+__global__ void __launch_bounds__(256) bsq_unpack_2bit(const uint8_t* packed, long long nbytes, uint8_t* out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long b0 = 4 * t;
+  if (b0 >= nbytes) return;
+  if (b0 + 4 <= nbytes && (((unsigned long long)packed | (unsigned long long)out) & 15ull) == 0ull) {
+    const uint32_t w = *(const uint32_t*)(packed + b0);
+    uint4 v;
+    v.x = (w & 3u) | ((w & 0xCu) << 6) | ((w & 0x30u) << 12) | ((w & 0xC0u) << 18);
+    const uint32_t w1 = w >> 8, w2 = w >> 16, w3 = w >> 24;
+    v.y = (w1 & 3u) | ((w1 & 0xCu) << 6) | ((w1 & 0x30u) << 12) | ((w1 & 0xC0u) << 18);
+    v.z = (w2 & 3u) | ((w2 & 0xCu) << 6) | ((w2 & 0x30u) << 12) | ((w2 & 0xC0u) << 18);
+    v.w = (w3 & 3u) | ((w3 & 0xCu) << 6) | ((w3 & 0x30u) << 12) | ((w3 & 0xC0u) << 18);
+    *(uint4*)(out + 4 * b0) = v;
+  } else {
+    for (long long b = b0; b < b0 + 4 && b < nbytes; b++) {
+      const uint32_t w = packed[b];
+      out[4 * b] = (uint8_t)(w & 3u); out[4 * b + 1] = (uint8_t)((w >> 2) & 3u);
+      out[4 * b + 2] = (uint8_t)((w >> 4) & 3u); out[4 * b + 3] = (uint8_t)(w >> 6);
+    }
+  }
+}
+
+// BSQ_F_TX_2BIT: ops [16 w, 16 w + 16) of the packed byte transcripts -> 32-bit word w, for words
+// [w_lo, w_hi); ops at or past `nops` read as 0.  M = 0, S = 1, I = 2, D = 3.
+__global__ void __launch_bounds__(256) bsq_tx_to_2bit(const char* ops, long long nops, long long w_lo, long long w_hi,
+                                                      uint32_t* out) {
+  const long long w = w_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= w_hi) return;
+  uint32_t acc = 0u;
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const long long q = 16 * w + k;
+    if (q < nops) {
+      const char c = ops[q];
+      const uint32_t code = (c == 'M') ? 0u : (c == 'S') ? 1u : (c == 'I') ? 2u : 3u;
+      acc |= code << (2 * k);
+    }
+  }
+  out[w] = acc;
+}
+
 // exclusive scan of txlen (int32) into int64 offsets, three small kernels
 #define BSQ_SCAN_TILE 2048
 __global__ void __launch_bounds__(256) bsq_scan_tile_sums(const int* in, int n, long long* tile_sums) {
@@ -565,8 +609,8 @@ __global__ void __launch_bounds__(256) bsq_make_pairs_uniform(const long long* o
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   BsqPair bp;
-  bp.o_off = o_off[e];
-  bp.m_off = m_off[e];
+  if (o_off) { bp.o_off = o_off[e]; bp.m_off = m_off[e]; }
+  else { bp.o_off = e * ((long long)U.n + U.m); bp.m_off = bp.o_off + U.n; }   // pairs back to back in codes[]
   bp.ptr_off = (e % U.ppc) * U.words;
   bp.tx_slot = e * ((long long)U.n + U.m);
   bp.n = U.n; bp.m = U.m;

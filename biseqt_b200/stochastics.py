@@ -1,8 +1,13 @@
 """Batched synthetic data with the reference's distributions
 (``biseqt/stochastics.py``): ``rand_seq`` (:28-41), ``MutationProcess.mutate``
 (:143-201) and ``log_odds_scores`` (:298-310), vectorised over pairs because
-the reference draws one ``np.random.choice`` per base.  Seeded
-``numpy.random.Generator``; the reference itself is unseeded."""
+the reference draws one ``np.random.choice`` per base.
+
+Two forms: :func:`generate_pairs` runs on the device (``bsq_generate_pairs``,
+csrc/bsq_gen.cuh; counter-based randomness, 10^5 pairs of 10 kb in milliseconds)
+and is what the bench uses at BASELINE.json's full sizes; :func:`rand_seqs` /
+:func:`mutate_batch` are the host (numpy, seeded ``Generator``) lock-step form
+used for small cases.  The reference itself is unseeded."""
 from math import log
 
 import numpy as np
@@ -86,3 +91,51 @@ def mutate_batch(rng, origins, L, subst_prob, go_prob, ge_prob, want_transcripts
         txs = [bytes(r[r != 0]).decode() for r in M]
         return out, olen, txs
     return out, olen
+
+
+def generate_pairs(engine, npairs, origin_len, L=4, subst_prob=0.0, go_prob=0.0, ge_prob=0.0, seed=0,
+                   max_offset=0, fixed_mutant_len=0, transcripts=False, pinned=False):
+    """``npairs`` synthetic (origin, mutant) pairs generated on the device
+    (``bsq_generate_pairs``): origin = uniform random letters (``rand_seq``), mutant =
+    ``MutationProcess(subst_probs=subst_prob, go_prob=, ge_prob=).mutate`` of the origin, or of
+    the chunk window ``off ~ U[0, max_offset]`` letters further on (overlapping long reads).
+    Returns a dict with ``codes, o_off, o_len, m_off, m_len, src_off`` in the layout
+    :meth:`biseqt_b200.batch.Engine.align` takes (+ ``transcripts``: list of planted edit
+    transcripts).  ``pinned``: ``codes`` lives in page-locked host memory."""
+    from ._ffi import ffi, BsqError
+    npairs = int(npairs)
+    gp = ffi.new('bsq_gen_params*')
+    gp.seed, gp.alphabet_len, gp.origin_len = int(seed), int(L), int(origin_len)
+    gp.max_offset, gp.fixed_mutant_len = int(max_offset), int(fixed_mutant_len)
+    gp.subst_prob, gp.go_prob, gp.ge_prob = float(subst_prob), float(go_prob), float(ge_prob)
+    o_off, m_off = np.empty(npairs, np.int64), np.empty(npairs, np.int64)
+    o_len, m_len = np.empty(npairs, np.int32), np.empty(npairs, np.int32)
+    src_off = np.empty(npairs, np.int32)
+    ncodes = ffi.new('int64_t*')
+    if fixed_mutant_len > 0:
+        est = origin_len + fixed_mutant_len
+    else:   # expected mutant length n (1 + go/(1-ge) / 2 ...) with slack; retried on BSQ_ERR_CAPACITY
+        est = origin_len * (2 + go_prob / max(1e-9, 1 - ge_prob)) + 8 * np.sqrt(origin_len + 1) + 64
+    cap = int(npairs * est) + 16
+    tx_off = np.empty(npairs + 1, np.int64) if transcripts else None
+    for attempt in range(2):
+        codes = engine.pinned_empty(cap, np.uint8) if pinned else np.empty(cap, np.uint8)
+        tx_cap = int(npairs * (2 * est)) if transcripts else 0
+        tx_buf = np.empty(max(tx_cap, 1), np.uint8) if transcripts else None
+        P = lambda a, t: ffi.NULL if a is None else ffi.cast(t, a.ctypes.data)   # noqa: E731
+        rc = engine.lib.bsq_generate_pairs(
+            engine.ctx, gp, npairs, P(codes, 'uint8_t*'), cap, ncodes, P(o_off, 'int64_t*'), P(o_len, 'int32_t*'),
+            P(m_off, 'int64_t*'), P(m_len, 'int32_t*'), P(src_off, 'int32_t*'), P(tx_off, 'int64_t*'),
+            P(tx_buf, 'char*'), tx_cap)
+        if rc == -4 and attempt == 0:     # BSQ_ERR_CAPACITY: *ncodes holds the size needed
+            cap = int(ncodes[0])
+            est = max(est, (cap / max(npairs, 1)))
+            continue
+        if rc != 0:
+            raise BsqError('bsq_generate_pairs failed (%d): %s' % (rc, engine._err()))
+        break
+    out = dict(codes=codes[:int(ncodes[0])] if npairs else codes[:0], o_off=o_off, o_len=o_len, m_off=m_off,
+               m_len=m_len, src_off=src_off)
+    if transcripts:
+        out['transcripts'] = [bytes(tx_buf[tx_off[i]:tx_off[i + 1]]).decode() for i in range(npairs)]
+    return out

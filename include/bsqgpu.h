@@ -85,8 +85,19 @@ typedef struct {
   double ge;             /* alnscores.gap_extend_score                                 */
   const double* subst;   /* L*L row-major, subst[o*L+m]            (alnscores.subst_scores) */
   int32_t dtype;         /* BSQ_DTYPE_AUTO (default), or force F64 / I32               */
-  int32_t reserved;
+  int32_t flags;         /* BSQ_F_* below, 0 = one byte per letter in, one byte per op out */
 } bsq_params;
+
+/* bsq_params.flags: compact forms of the two big arrays that cross PCIe (alphabets of <= 4
+ * letters; the reference passes int* at 4 bytes per letter, pwlib.h:85-86).
+ *   BSQ_F_CODES_2BIT  codes[] holds four letters per byte: letter j sits in bits 2*(j&3) .. +1 of
+ *                     byte j>>2.  o_off / m_off / ncodes count LETTERS, as always.
+ *   BSQ_F_TX_2BIT     tx_buf[] holds four ops per byte (M=0, S=1, I=2, D=3): op k of the batch sits
+ *                     in bits 2*(k&3) .. +1 of byte k>>2.  tx_off[] / *tx_total count OPS, as always
+ *                     (transcript i = ops tx_off[i] .. tx_off[i+1]); tx_cap stays in BYTES and
+ *                     must hold ceil(total ops / 16) * 4 of them. */
+#define BSQ_F_CODES_2BIT 1
+#define BSQ_F_TX_2BIT 2
 
 /* kernel-level timing of the last bsq_align_batch / bsq_solve_batch call,
  * measured with cudaEvents on the library's own streams */
@@ -125,8 +136,10 @@ void bsq_host_free(void* p);
  * dptable_init + dptable_solve + dptable_traceback + dptable_free for a whole
  * batch, pipelined over chunks that fit the pointer-table arena.
  *
- *  in : codes[]               all letters, uint8
- *       o_off/o_len, m_off/m_len   frame start + length of origin / mutant
+ *  in : codes[]               all letters, uint8 (or 2-bit packed: BSQ_F_CODES_2BIT)
+ *       o_off/o_len, m_off/m_len   frame start + length of origin / mutant.  o_off and m_off
+ *                             may both be NULL: the pairs then lie back to back in codes[],
+ *                             origin_0 | mutant_0 | origin_1 | ... (nothing to upload for them)
  *       dmin/dmax             BANDED only (NULL in STD); banded_alnparams.dmin/dmax,
  *                             clipped to [-m, n] like _pw_internals.c:29-36
  *  out: score[npairs]         choices[0].score of the end cell (pw.py:272)
@@ -217,6 +230,33 @@ int bsq_table_scores(bsq_ctx* ctx, const bsq_params* params,
                      const uint8_t* mutant, int32_t m, double* out);
 
 int bsq_get_timing(const bsq_ctx* ctx, bsq_timing* out);
+
+/*
+ * Batched synthetic pairs on the device: rand_seq (stochastics.py:28-41) and
+ * MutationProcess.mutate (stochastics.py:143-201) for npairs pairs at once.  Pair i is a
+ * random genome chunk; origin = chunk[0, origin_len); the mutant is mutate(chunk[off, off +
+ * origin_len)) with off ~ U[0, max_offset] (0: the mutant is mutated from the origin itself);
+ * fixed_mutant_len > 0 trims / pads (random letters) every mutant to that length (fixed-length
+ * reads).  Randomness is counter based on (seed, pair): a pair does not depend on its batch.
+ *  out: codes[] = origin_0 | mutant_0 | origin_1 | ... (+16 zero bytes), *ncodes bytes in all
+ *       (BSQ_ERR_CAPACITY with *ncodes set if codes_cap is too small); o_off/o_len/m_off/m_len
+ *       as bsq_align_batch takes them; src_off[i] = off (may be NULL); tx_off[npairs+1] /
+ *       tx_buf: the planted edit transcripts mutate() returns (both may be NULL).
+ */
+typedef struct {
+  uint64_t seed;
+  int32_t alphabet_len;
+  int32_t origin_len;
+  int32_t max_offset;
+  int32_t fixed_mutant_len;
+  double subst_prob;     /* probability of any substitution (MutationProcess(subst_probs=float)) */
+  double go_prob;        /* gap-open probability  */
+  double ge_prob;        /* gap-extend probability, >= go_prob (stochastics.py:140-141) */
+} bsq_gen_params;
+int bsq_generate_pairs(bsq_ctx* ctx, const bsq_gen_params* gen, int64_t npairs,
+                       uint8_t* codes, int64_t codes_cap, int64_t* ncodes,
+                       int64_t* o_off, int32_t* o_len, int64_t* m_off, int32_t* m_len,
+                       int32_t* src_off, int64_t* tx_off, char* tx_buf, int64_t tx_cap);
 
 /*
  * Pipe-rate microbenchmarks: the measured denominators of the ALU roofline

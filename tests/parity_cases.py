@@ -623,6 +623,84 @@ def run_bad_codes(eng):
     check_batch(eng, [dict(origin=t, mutant=t, subst=np.eye(4), go=-1.0, ge=-1.0, mode=0, type=0, diag_range=None)])
 
 
+def _same_results(r, q, what):
+    assert np.array_equal(r.status, q.status), what
+    assert np.array_equal(r.score, q.score), what
+    for k in ('end_x', 'end_y', 'start_x', 'start_y'):
+        ok = (r.status == 0)
+        assert np.array_equal(getattr(r, k)[ok], getattr(q, k)[ok]), (what, k)
+    assert np.array_equal(r.tx_off, q.tx_off), what
+    assert r.transcripts() == q.transcripts(), what
+
+
+def run_compact_io(make_engine, seed, npairs=41):
+    """BSQ_F_CODES_2BIT (four letters per byte in), BSQ_F_TX_2BIT (four ops per byte out) and
+    implicit back-to-back offsets against the plain one-byte forms of the same batches (which the
+    other tests pin to the oracle): ragged and uniform STD, banded, chunked (per-chunk shipping of
+    2-bit words), the two-phase and resident entry points."""
+    rng = np.random.default_rng(seed)
+    os.environ['BSQ_UNIFORM_MIN'] = '2'
+    os.environ['BSQ_ARENA_CAP_BYTES'] = str(1 << 17)
+    try:
+        engines = [make_engine()]
+    finally:
+        del os.environ['BSQ_ARENA_CAP_BYTES']
+    try:
+        engines.append(make_engine())
+    finally:
+        del os.environ['BSQ_UNIFORM_MIN']
+    engines.append(make_engine())
+    try:
+        for eng in engines:
+            for mode, typ, uniform in ((0, 1, True), (0, 1, False), (0, 0, False), (1, 2, False), (1, 1, True)):
+                S, go, ge = score_family(rng, 4, int(rng.integers(1, 3)), int(rng.integers(-1, 1)))
+                pairs, dmin, dmax = [], [], []
+                for i in range(npairs):
+                    n = 90 if uniform else int(rng.integers(0, 160))
+                    m = 90 if uniform else int(rng.integers(0, 160))
+                    o = rng.integers(0, 4, size=n).astype(np.uint8)
+                    t = rng.integers(0, 4, size=m).astype(np.uint8)
+                    k = min(n, m)
+                    if i % 4:
+                        t[:k] = o[:k]
+                        if m > 8:
+                            t[rng.integers(0, m, size=m // 8)] = rng.integers(0, 4, size=m // 8)
+                    pairs.append((o, t))
+                    dmin.append(-7)
+                    dmax.append(9)
+                codes, o_off, o_len, m_off, m_len = batch.pack_pairs(pairs)
+                kw = dict(dmin=dmin, dmax=dmax) if mode == 1 else {}
+                base = eng.align(codes, o_off, o_len, m_off, m_len, mode, typ, S, go, ge, **kw)
+                packed = batch.pack_codes_2bit(codes)
+                what = 'mode %d type %d uniform %s' % (mode, typ, uniform)
+                _same_results(base, eng.align(packed, o_off, o_len, m_off, m_len, mode, typ, S, go, ge, codes_2bit=True,
+                                              ncodes=len(codes), **kw), what + ' 2-bit in')
+                _same_results(base, eng.align(codes, o_off, o_len, m_off, m_len, mode, typ, S, go, ge, tx_2bit=True, **kw),
+                              what + ' 2-bit out')
+                _same_results(base, eng.align(packed, None, o_len, None, m_len, mode, typ, S, go, ge, codes_2bit=True,
+                                              ncodes=len(codes), tx_2bit=True, **kw), what + ' 2-bit in/out, no offsets')
+                _same_results(base, eng.align(codes, None, o_len, None, m_len, mode, typ, S, go, ge, **kw), what + ' no offsets')
+        eng = engines[-1]
+        sb = eng.solve(packed, None, o_len, None, m_len, mode, typ, S, go, ge, codes_2bit=True, ncodes=len(codes), tx_2bit=True, **kw)
+        _same_results(base, sb.traceback(), 'two-phase 2-bit')
+        sb.release()
+        rb = eng.upload(packed, o_off, o_len, m_off, m_len, mode, typ, S, go, ge, codes_2bit=True, ncodes=len(codes), tx_2bit=True, **kw)
+        rb.run()
+        _same_results(base, rb.fetch(), 'resident 2-bit')
+        rb.release()
+        # a 3-letter alphabet in 2-bit form: code 3 is out of range and must be refused
+        import pytest
+        from biseqt_b200._ffi import BsqError
+        with pytest.raises(BsqError, match='alphabet_len'):
+            eng.align(batch.pack_codes_2bit(np.array([0, 1, 3, 2, 1, 0, 1, 2], np.uint8)), [0], [4], [4], [4], 0, 1,
+                      np.eye(3), -1.0, -1.0, codes_2bit=True, ncodes=8)
+        with pytest.raises(BsqError, match='4 letters'):
+            eng.align(packed, o_off, o_len, m_off, m_len, 0, 1, np.eye(5), -1.0, -1.0, codes_2bit=True, ncodes=len(codes))
+    finally:
+        for eng in engines:
+            eng.close()
+
+
 def run_lifetime(make_engine):
     """Batches that outlive their engine (an Engine closed, or collected, before its SolvedBatch /
     ResidentBatch): release and every other call on them must not touch the dead context."""

@@ -76,6 +76,10 @@ def test_emu_edge_cases(emu_engine):
     pc.run_edge_cases(emu_engine)
 
 
+def test_emu_compact_io(emu_lib):
+    pc.run_compact_io(lambda: batch.Engine(0, lib=emu_lib), seed=111, npairs=13)
+
+
 def test_emu_lifetime(emu_lib):
     pc.run_lifetime(lambda: batch.Engine(0, lib=emu_lib))
 

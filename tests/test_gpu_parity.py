@@ -84,6 +84,10 @@ def test_gpu_edge_cases(gpu_engine):
     pc.run_edge_cases(gpu_engine)
 
 
+def test_gpu_compact_io():
+    pc.run_compact_io(lambda: batch.Engine(0), seed=111, npairs=301)
+
+
 def test_gpu_lifetime():
     pc.run_lifetime(lambda: batch.Engine(0))
 

@@ -65,10 +65,12 @@ class BatchResult(object):
     """Arrays of a finished batch; transcripts are packed in ``tx_buf`` (one byte per op, or
     four ops per byte when the batch was run with ``tx_2bit``; ``tx_off`` counts ops either way)."""
 
-    def __init__(self, score, end_x, end_y, start_x, start_y, status, tx_off, tx_buf, tx_2bit=False):
+    def __init__(self, score, end_x, end_y, start_x, start_y, status, tx_off, tx_buf, tx_2bit=False,
+                 tx_lens=None):
         self.score, self.end_x, self.end_y = score, end_x, end_y
         self.start_x, self.start_y, self.status = start_x, start_y, status
         self.tx_off, self.tx_buf, self.tx_2bit = tx_off, tx_buf, tx_2bit
+        self.tx_lens = tx_lens    # MultiEngine: transcript i = ops tx_off[i] .. tx_off[i] + tx_lens[i]
 
     def __len__(self):
         return len(self.score)
@@ -76,15 +78,19 @@ class BatchResult(object):
     def transcript(self, i):
         if self.tx_off is None:
             return None
+        lo = int(self.tx_off[i])
+        hi = lo + int(self.tx_lens[i]) if self.tx_lens is not None else int(self.tx_off[i + 1])
         if self.tx_2bit:
-            return unpack_ops_2bit(self.tx_buf, int(self.tx_off[i]), int(self.tx_off[i + 1])).decode()
-        return bytes(self.tx_buf[self.tx_off[i]:self.tx_off[i + 1]]).decode()
+            return unpack_ops_2bit(self.tx_buf, lo, hi).decode()
+        return bytes(self.tx_buf[lo:hi]).decode()
 
     def transcripts(self):
         return [self.transcript(i) for i in range(len(self))]
 
     @property
     def tx_len(self):
+        if self.tx_lens is not None:
+            return np.asarray(self.tx_lens, dtype=np.int32)
         return np.diff(self.tx_off).astype(np.int32)
 
 
@@ -296,6 +302,111 @@ class Engine(object):
         return {k: getattr(t, k) for k in ('fill_ms', 'traceback_ms', 'total_ms', 'cells',
                                            'fill_launches', 'h2d_bytes', 'd2h_bytes',
                                            'ptr_bytes', 'dtype', 'chunks', 'plan_ms', 'call_ms')}
+
+
+class MultiEngine(object):
+    """ONE batch over several GPUs of a box (``bsq_multi``): the batch is cut into contiguous
+    ranges of equal work, one host thread + context per GPU aligns its range and writes straight
+    into disjoint slices of the result arrays.  No collective, no peer traffic.
+    ``devices``: CUDA ordinals (an ordinal may repeat), or an int n for ordinals 0 .. n-1."""
+
+    def __init__(self, devices, lib=None):
+        self.lib = lib if lib is not None else _ffi.load()
+        devs = list(range(devices)) if isinstance(devices, int) else [int(d) for d in devices]
+        arr = ffi.new('int32_t[]', devs)
+        self.me = self.lib.bsq_multi_create(len(devs), arr)
+        if self.me == ffi.NULL:
+            raise BsqError('bsq_multi_create(%r) failed: %s' % (
+                devs, ffi.string(self.lib.bsq_multi_last_error(ffi.NULL)).decode()))
+        self.devices = devs
+
+    def close(self):
+        if self.me is not None and self.me != ffi.NULL:
+            self.lib.bsq_multi_destroy(self.me)
+        self.me = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def pinned_empty(self, n, dtype):
+        dtype = np.dtype(dtype)
+        nbytes = int(n) * dtype.itemsize
+        p = self.lib.bsq_host_alloc(max(nbytes, 1))
+        if p == ffi.NULL:
+            raise BsqError('bsq_host_alloc(%d) failed' % nbytes)
+        p = ffi.gc(p, self.lib.bsq_host_free, size=nbytes)
+        return np.frombuffer(ffi.buffer(p, max(nbytes, 1)), dtype=dtype, count=int(n))
+
+    def tx_capacity(self, o_len, m_len, tx_2bit=False):
+        """Bytes ``tx_buf`` must hold (the worst case, every GPU packs its own region)."""
+        ops = int(np.asarray(o_len, np.int64).sum() + np.asarray(m_len, np.int64).sum()) + 64 * len(self.devices)
+        return ops // 4 + 16 if tx_2bit else ops
+
+    def align(self, codes, o_off, o_len, m_off, m_len, mode, type, subst, go, ge, dmin=None, dmax=None,
+              dtype=DTYPE_AUTO, transcripts=True, out=None, codes_2bit=False, ncodes=None, tx_2bit=False):
+        """``Engine.align`` for one batch sharded over the engine's GPUs (``bsq_multi_align_batch``)."""
+        codes = _c(codes, np.uint8)
+        o_off, m_off = _c(o_off, np.int64), _c(m_off, np.int64)
+        o_len, m_len = _c(o_len, np.int32), _c(m_len, np.int32)
+        dmin, dmax = _c(dmin, np.int32), _c(dmax, np.int32)
+        N = len(o_len)
+        S = np.ascontiguousarray(np.asarray(subst, dtype=np.float64))
+        prm = ffi.new('bsq_params*')
+        prm.mode, prm.type, prm.alphabet_len, prm.max_new_mins = int(mode), int(type), S.shape[0], -1
+        prm.go, prm.ge, prm.subst, prm.dtype = float(go), float(ge), ffi.cast('double*', S.ctypes.data), int(dtype)
+        prm.flags = (F_CODES_2BIT if codes_2bit else 0) | (F_TX_2BIT if tx_2bit else 0)
+        nletters = int(ncodes) if ncodes is not None else (4 * len(codes) if codes_2bit else len(codes))
+        out = out or {}
+
+        def arr(name, dt, n):
+            a = out.get(name)
+            if a is None:
+                a = np.empty(n, dtype=dt)
+            assert a.dtype == dt and len(a) >= n
+            return a
+        score = arr('score', np.float64, N)
+        ints = {k: arr(k, np.int32, N) for k in ('end_x', 'end_y', 'start_x', 'start_y', 'status')}
+        tx_off = tx_len = tx_buf = None
+        cap = 0
+        if transcripts:
+            tx_off, tx_len = arr('tx_off', np.int64, N + 1), arr('tx_len', np.int32, N)
+            cap = self.tx_capacity(o_len, m_len, tx_2bit)
+            tx_buf = out.get('tx_buf')
+            if tx_buf is None or len(tx_buf) < cap:
+                tx_buf = np.empty(max(cap, 1), np.uint8)
+            cap = len(tx_buf)
+        rc = self.lib.bsq_multi_align_batch(
+            self.me, prm, N, _ptr(codes, 'uint8_t*'), nletters, _ptr(o_off, 'int64_t*'), _ptr(o_len, 'int32_t*'),
+            _ptr(m_off, 'int64_t*'), _ptr(m_len, 'int32_t*'), _ptr(dmin, 'int32_t*'), _ptr(dmax, 'int32_t*'),
+            _ptr(score, 'double*'), _ptr(ints['end_x'], 'int32_t*'), _ptr(ints['end_y'], 'int32_t*'),
+            _ptr(ints['start_x'], 'int32_t*'), _ptr(ints['start_y'], 'int32_t*'), _ptr(ints['status'], 'int32_t*'),
+            _ptr(tx_off, 'int64_t*'), _ptr(tx_len, 'int32_t*'), _ptr(tx_buf, 'char*'), cap)
+        if rc != 0:
+            raise BsqError('bsq_multi_align_batch failed (%d): %s' % (
+                rc, ffi.string(self.lib.bsq_multi_last_error(self.me)).decode()))
+        return BatchResult(score[:N], ints['end_x'][:N], ints['end_y'][:N], ints['start_x'][:N], ints['start_y'][:N],
+                           ints['status'][:N], None if tx_off is None else tx_off[:N + 1], tx_buf, tx_2bit=tx_2bit,
+                           tx_lens=None if tx_len is None else tx_len[:N])
+
+    def shards(self):
+        """[(first pair, count, device, timing dict)] of the last :meth:`align`."""
+        res = []
+        for k in range(len(self.devices)):
+            first, count, dev = ffi.new('int64_t*'), ffi.new('int64_t*'), ffi.new('int32_t*')
+            t = ffi.new('bsq_timing*')
+            self.lib.bsq_multi_get_shard(self.me, k, first, count, dev, t)
+            res.append((first[0], count[0], dev[0], {f: getattr(t, f) for f in (
+                'fill_ms', 'total_ms', 'cells', 'fill_launches', 'h2d_bytes', 'd2h_bytes', 'chunks', 'plan_ms', 'call_ms', 'dtype')}))
+        return res
 
 
 STATS_DTYPE = np.dtype([('n_match', 'i4'), ('n_subst', 'i4'), ('n_ins', 'i4'), ('n_del', 'i4'),

@@ -53,6 +53,8 @@ struct BsqUniform {
   int n, m, dmin, dmax, s0;
   long long words;       // pointer-table words per pair
   long long ppc;         // pairs per chunk (ptr_off restarts at every chunk)
+  long long off_base;    // added to every caller offset (a shard's window of codes[]); with implicit
+                         // back-to-back offsets: where the first pair starts
 };
 
 // K1h: the two problems (indices into the chunk's pair records, equal shapes; b == a for a

@@ -120,7 +120,7 @@ struct Hooks {
   int target_chunks = -1;       // BSQ_TARGET_CHUNKS: chunks to cut a batch into (< 0: automatic)
   int k2_cfg = -1;              // BSQ_K2_CFG: forced K2 geometry
   int k3_cfg = -1;              // BSQ_K3_CFG: forced K3 geometry
-  char trace_kernel = 0;        // BSQ_TRACE_KERNEL: 't'hread / 'w'arp / 'n'arrow
+  char trace_kernel = 0;        // BSQ_TRACE_KERNEL: 't'hread / 'w'arp / 'n'arrow / 'p'air-thread (banded)
   size_t arena_cap_bytes = 0;   // BSQ_ARENA_CAP_BYTES: upper bound for the pointer arena
   void read_env() {
     auto num = [](const char* name, long long dflt) { const char* e = getenv(name); return e ? atoll(e) : dflt; };
@@ -427,7 +427,11 @@ class WorkerPool {
 };
 
 inline int64_t parallel_grain() { return g_par_grain > 0 ? g_par_grain : 32768; }
+// bsq_multi runs one host thread per GPU, each planning its own shard: those plan single-threaded
+// (N planners x 8 pool threads would only queue up on the pool's lock)
+thread_local bool g_plan_serial = false;
 inline int parallel_threads(int64_t n) {
+  if (g_plan_serial) return 1;
   return (int)std::min<int64_t>(WorkerPool::get().size(), std::max<int64_t>(n / parallel_grain(), 1));
 }
 
@@ -442,7 +446,9 @@ void parallel_for(int64_t n, F f) {
 int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int64_t N, int64_t ncodes,
               const int64_t* o_off, const int32_t* o_len, const int64_t* m_off,
               const int32_t* m_len, const int32_t* dmin, const int32_t* dmax,
-              int64_t arena_words, bool single_chunk, int target_chunks = 0) {
+              int64_t arena_words, bool single_chunk, int target_chunks = 0, int64_t ob = 0) {
+  // ob: added to every caller offset (bsq_multi hands each GPU a window of the caller's codes[]);
+  // with implicit back-to-back offsets it is where the first pair starts
   if (!prm || !prm->subst) return fail(ctx, BSQ_ERR_ARG, "params/subst is NULL");
   const int L = prm->alphabet_len;
   if (L < 1 || L > BSQ_MAX_L) return fail(ctx, BSQ_ERR_ARG, "alphabet_len must be in [1,32]");
@@ -477,7 +483,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
     std::vector<int64_t>& io = ctx->plan_ooff;
     std::vector<int64_t>& im = ctx->plan_moff;
     if ((int64_t)io.size() < N) { io.resize((size_t)N); im.resize((size_t)N); }
-    int64_t pos = 0;
+    int64_t pos = 0;   // local offsets: ob is added wherever they are read, like for explicit ones
     for (int64_t i = 0; i < N; i++) { io[(size_t)i] = pos; pos += o_len[i]; im[(size_t)i] = pos; pos += m_len[i]; }
     o_off = io.data();
     m_off = im.data();
@@ -491,7 +497,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
       Scan sc;
       for (int64_t i = i0; i < i1; i++) {
         const int n = o_len[i], m = m_len[i];
-        if (n < 0 || m < 0 || (!implicit && (o_off[i] < 0 || m_off[i] < 0 || o_off[i] + n > ncodes || m_off[i] + m > ncodes))) { sc.bad = 1; continue; }
+        if (n < 0 || m < 0 || (!implicit && (o_off[i] + ob < 0 || m_off[i] + ob < 0 || o_off[i] + ob + n > ncodes || m_off[i] + ob + m > ncodes))) { sc.bad = 1; continue; }
         sc.max_n = std::max<int64_t>(sc.max_n, n);
         sc.max_m = std::max<int64_t>(sc.max_m, m);
         sc.tot += (int64_t)n + m;
@@ -507,7 +513,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
     scan_n = std::max(scan_n, sc.max_n); scan_m = std::max(scan_m, sc.max_m); scan_tot += sc.tot;
     if (!sc.uniform) all_uniform = false;
   }
-  if (implicit && scan_tot > ncodes) return fail(ctx, BSQ_ERR_ARG, "back-to-back pairs do not fit codes[]");
+  if (implicit && (ob < 0 || ob + scan_tot > ncodes)) return fail(ctx, BSQ_ERR_ARG, "back-to-back pairs do not fit codes[]");
   // geometry depends on the arithmetic; decide it up front from the scores and maxima
   bool f64_geom = true;
   {
@@ -632,14 +638,14 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
         ch.code_end = 0;
       }
       if (implicit) {
-        for (int64_t c = 0; c < NC; c++) P.chunks[(size_t)c].code_end = std::min<int64_t>(N, (c + 1) * ppc) * ((int64_t)o_len[0] + m_len[0]);
+        for (int64_t c = 0; c < NC; c++) P.chunks[(size_t)c].code_end = ob + std::min<int64_t>(N, (c + 1) * ppc) * ((int64_t)o_len[0] + m_len[0]);
       } else {  // last byte of codes[] each chunk reads (pairs need not be laid out in order)
         std::vector<int64_t> ends((size_t)NC * 16, 0);
         const int n = o_len[0], m = m_len[0];
         parallel_for(N, [&](int t, int64_t i0, int64_t i1) {
           for (int64_t i = i0; i < i1; i++) {
             int64_t& e = ends[(size_t)(i / ppc) * 16 + t];
-            e = std::max(e, std::max(o_off[i] + n, m_off[i] + m));
+            e = std::max(e, ob + std::max(o_off[i] + n, m_off[i] + m));
           }
         });
         for (int64_t c = 0; c < NC; c++)
@@ -659,6 +665,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
       P.uni.s0 = family == 2 ? it.aux : 0;
       P.uni.words = it.words;
       P.uni.ppc = single_chunk ? ((int64_t)1 << 62) : ppc;
+      P.uni.off_base = ob;
       return BSQ_SUCCESS;
     }
   }
@@ -713,7 +720,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
           k.words += (int64_t)(n + G) * G * WPL;
           k.len += (int64_t)n + m;
           k.cells += (int64_t)(n + 1) * (m + 1);
-          k.code_end = std::max(k.code_end, std::max(o_off[i] + n, m_off[i] + m));
+          k.code_end = std::max(k.code_end, ob + std::max(o_off[i] + n, m_off[i] + m));
           k.min_n = std::min(k.min_n, n);
         }
         blk[(size_t)b] = k;
@@ -782,8 +789,8 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
             const int64_t i = ib + perm[(size_t)(r - ib)];
             const int n = o_len[i], m = m_len[i];
             BsqPair bp;
-            bp.o_off = o_off[i];
-            bp.m_off = m_off[i];
+            bp.o_off = o_off[i] + ob;
+            bp.m_off = m_off[i] + ob;
             bp.ptr_off = pw;
             bp.tx_slot = sl;
             bp.n = n;
@@ -819,7 +826,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
     PlanItem prev{};
     for (int64_t i = i0; i < i1; i++) {
       const int n = o_len[i], m = m_len[i];
-      if (n < 0 || m < 0 || o_off[i] < 0 || m_off[i] < 0 || o_off[i] + n > ncodes || m_off[i] + m > ncodes) { pt.bad = 1; continue; }
+      if (n < 0 || m < 0 || o_off[i] + ob < 0 || m_off[i] + ob < 0 || o_off[i] + ob + n > ncodes || m_off[i] + ob + m > ncodes) { pt.bad = 1; continue; }
       pt.max_n = std::max<int64_t>(pt.max_n, n);
       pt.max_m = std::max<int64_t>(pt.max_m, m);
       const int dlo = family == 2 ? dmin[i] : 0, dhi = family == 2 ? dmax[i] : 0;
@@ -971,8 +978,8 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
       const PlanItem& it = items[i];
       const int64_t pos = uniform ? e : h[key_of(it)]++;
       BsqPair bp;
-      bp.o_off = o_off[i];
-      bp.m_off = m_off[i];
+      bp.o_off = o_off[i] + ob;
+      bp.m_off = m_off[i] + ob;
       bp.ptr_off = 0;
       bp.tx_slot = 0;
       bp.n = o_len[i];
@@ -984,7 +991,7 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
       out[pos] = bp;
       Gathered gq;
       gq.words = it.words;
-      gq.code_end = std::max(o_off[i] + o_len[i], m_off[i] + m_len[i]);
+      gq.code_end = ob + std::max(o_off[i] + o_len[i], m_off[i] + m_len[i]);
       gq.len = o_len[i] + m_len[i];
       gq.cfg = it.cfg;
       gq.aux = it.aux;
@@ -1412,6 +1419,12 @@ int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, cudaStream_t
                         else BSQ_LAUNCH((bsq_k3_walk<KK, 1>), grid, 32, 0, stream, T); }
     if (T.K == 2) BSQ_WALK3(2) else if (T.K == 4) BSQ_WALK3(4) else BSQ_WALK3(8)
 #undef BSQ_WALK3
+  } else if (ch.family == 2 && (force == 'p' || (warp_walk && !force && ch.count >= (int64_t)ctx->sms * 32))) {
+    // big batches of long banded pairs: a thread per pair, straight out of global memory
+    const int grid = (int)((ch.count + 127) / 128);
+    if (P.gosign < 0) BSQ_LAUNCH((bsq_k2_walk_thread<-1>), grid, 128, 0, stream, T);
+    else if (P.gosign == 0) BSQ_LAUNCH((bsq_k2_walk_thread<0>), grid, 128, 0, stream, T);
+    else BSQ_LAUNCH((bsq_k2_walk_thread<1>), grid, 128, 0, stream, T);
   } else if (warp_walk) {
     // lanes per pair: 8 when there are enough pairs to fill the GPU four times over, else a warp
     const bool narrow = (ch.count >= (int64_t)ctx->sms * 16 * 4 || force == 'n') && force != 'w';
@@ -1673,6 +1686,13 @@ static int batch_upload(bsq_ctx* ctx, bsq_batch* b, bool own_bufs, bool single_c
   b->B = own_bufs ? b->own : &ctx->bufs;
   b->plan.N = npairs;
   if (npairs == 0) return BSQ_SUCCESS;
+  // a resident batch must not be squeezed into what the one-shot path's cached arena leaves free
+  // (measured: config 3 cut into 34 small chunks instead of 2, fill 3x slower): give that back first
+  if (own_bufs && ctx->bufs.bytes() > ((size_t)1 << 30)) {
+    cudaStreamSynchronize(ctx->st);
+    cudaStreamSynchronize(ctx->st_trace);
+    ctx->bufs.release();
+  }
   int64_t slot_guess = 0;
   for (int64_t i = 0; i < npairs; i++) slot_guess += (int64_t)o_len[i] + m_len[i];
   const int64_t other = ncodes + 2 * slot_guess + npairs * (int64_t)(sizeof(BsqPair) + 48) + (64 << 20);
@@ -1814,30 +1834,39 @@ static int align_batch_once(bsq_ctx* ctx, const bsq_params* params, int64_t npai
                             int64_t ncodes, const int64_t* o_off, const int32_t* o_len, const int64_t* m_off,
                             const int32_t* m_len, const int32_t* dmin, const int32_t* dmax, double* score,
                             int32_t* end_x, int32_t* end_y, int32_t* start_x, int32_t* start_y, int32_t* status,
-                            int64_t* tx_off, char* tx_buf, int64_t tx_cap, int64_t* tx_total);
+                            int64_t* tx_off, char* tx_buf, int64_t tx_cap, int64_t* tx_total, int64_t off_base);
+
+static int align_batch_retry(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, const uint8_t* codes,
+                             int64_t ncodes, const int64_t* o_off, const int32_t* o_len, const int64_t* m_off,
+                             const int32_t* m_len, const int32_t* dmin, const int32_t* dmax, double* score,
+                             int32_t* end_x, int32_t* end_y, int32_t* start_x, int32_t* start_y, int32_t* status,
+                             int64_t* tx_off, char* tx_buf, int64_t tx_cap, int64_t* tx_total, int64_t off_base) {
+  if (!ctx) return BSQ_ERR_ARG;
+  int rc = align_batch_once(ctx, params, npairs, codes, ncodes, o_off, o_len, m_off, m_len, dmin, dmax, score, end_x,
+                            end_y, start_x, start_y, status, tx_off, tx_buf, tx_cap, tx_total, off_base);
+  if (rc == BSQ_ERR_NOMEM) {  // the remembered free-memory figure may be stale: ask the driver and try once more
+    drop_pool(ctx);
+    ctx->mem_avail = -1.0;
+    rc = align_batch_once(ctx, params, npairs, codes, ncodes, o_off, o_len, m_off, m_len, dmin, dmax, score, end_x,
+                          end_y, start_x, start_y, status, tx_off, tx_buf, tx_cap, tx_total, off_base);
+  }
+  return rc;
+}
 
 int bsq_align_batch(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, const uint8_t* codes,
                     int64_t ncodes, const int64_t* o_off, const int32_t* o_len, const int64_t* m_off,
                     const int32_t* m_len, const int32_t* dmin, const int32_t* dmax, double* score,
                     int32_t* end_x, int32_t* end_y, int32_t* start_x, int32_t* start_y, int32_t* status,
                     int64_t* tx_off, char* tx_buf, int64_t tx_cap, int64_t* tx_total) {
-  if (!ctx) return BSQ_ERR_ARG;
-  int rc = align_batch_once(ctx, params, npairs, codes, ncodes, o_off, o_len, m_off, m_len, dmin, dmax, score, end_x,
-                            end_y, start_x, start_y, status, tx_off, tx_buf, tx_cap, tx_total);
-  if (rc == BSQ_ERR_NOMEM) {  // the remembered free-memory figure may be stale: ask the driver and try once more
-    drop_pool(ctx);
-    ctx->mem_avail = -1.0;
-    rc = align_batch_once(ctx, params, npairs, codes, ncodes, o_off, o_len, m_off, m_len, dmin, dmax, score, end_x,
-                          end_y, start_x, start_y, status, tx_off, tx_buf, tx_cap, tx_total);
-  }
-  return rc;
+  return align_batch_retry(ctx, params, npairs, codes, ncodes, o_off, o_len, m_off, m_len, dmin, dmax, score, end_x,
+                           end_y, start_x, start_y, status, tx_off, tx_buf, tx_cap, tx_total, 0);
 }
 
 static int align_batch_once(bsq_ctx* ctx, const bsq_params* params, int64_t npairs, const uint8_t* codes,
                             int64_t ncodes, const int64_t* o_off, const int32_t* o_len, const int64_t* m_off,
                             const int32_t* m_len, const int32_t* dmin, const int32_t* dmax, double* score,
                             int32_t* end_x, int32_t* end_y, int32_t* start_x, int32_t* start_y, int32_t* status,
-                            int64_t* tx_off, char* tx_buf, int64_t tx_cap, int64_t* tx_total) {
+                            int64_t* tx_off, char* tx_buf, int64_t tx_cap, int64_t* tx_total, int64_t off_base) {
   if (!ctx) return BSQ_ERR_ARG;
   const double t_call = now_ms();
   ctx->err.clear();
@@ -1909,7 +1938,7 @@ static int align_batch_once(bsq_ctx* ctx, const bsq_params* params, int64_t npai
   const int64_t budget = arena_budget_words(ctx, other, &B);
   const double t_p2 = now_ms();
   rc = make_plan(ctx, P, B.hpairs, params, npairs, ncodes, o_off, o_len, m_off, m_len, dmin, dmax,
-                 budget / BSQ_ARENA_SLOTS, false, overlap_chunks(ctx, npairs, o_len, m_len));
+                 budget / BSQ_ARENA_SLOTS, false, overlap_chunks(ctx, npairs, o_len, m_len), off_base);
   if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(sx); return rc; }
   ctx->tm.plan_ms = now_ms() - t_plan;
   if (ctx->hooks.plan_debug)
@@ -2191,6 +2220,178 @@ void bsq_release(bsq_batch* b) {
     if (b->own) { b->own->release(); delete b->own; }
   }
   delete b;
+}
+
+// ---------------------------------------------------------------------------
+// bsq_multi: one batch over several GPUs
+// ---------------------------------------------------------------------------
+}  // extern "C"
+
+struct bsq_multi {
+  struct Shard {
+    bsq_ctx* ctx = nullptr;
+    int device = 0;
+    int64_t first = 0, count = 0;
+    PinBuf txoff;          // the shard's own tx_off (count + 1 entries), rebased into the caller's array afterwards
+    int rc = BSQ_SUCCESS;
+    bsq_timing tm;
+  };
+  std::vector<Shard> shards;
+  std::string err;
+};
+
+extern "C" {
+
+bsq_multi* bsq_multi_create(int32_t ndev, const int32_t* devices) {
+  if (ndev < 1 || ndev > 64) { g_err = "bsq_multi_create: need 1 <= ndev <= 64"; return nullptr; }
+  bsq_multi* me = new bsq_multi();
+  me->shards.resize((size_t)ndev);
+  for (int k = 0; k < ndev; k++) {
+    const int dev = devices ? devices[k] : k;
+    me->shards[(size_t)k].device = dev;
+    me->shards[(size_t)k].ctx = bsq_create(dev);
+    memset(&me->shards[(size_t)k].tm, 0, sizeof(bsq_timing));
+    if (!me->shards[(size_t)k].ctx) { bsq_multi_destroy(me); return nullptr; }   // g_err holds the reason
+  }
+  return me;
+}
+
+void bsq_multi_destroy(bsq_multi* me) {
+  if (!me) return;
+  for (auto& sh : me->shards) {
+    if (sh.ctx) { cudaSetDevice(sh.device); sh.txoff.release(); bsq_destroy(sh.ctx); }
+  }
+  delete me;
+}
+
+int32_t bsq_multi_size(const bsq_multi* me) { return me ? (int32_t)me->shards.size() : 0; }
+const char* bsq_multi_last_error(const bsq_multi* me) { return me ? me->err.c_str() : g_err.c_str(); }
+
+int bsq_multi_get_shard(const bsq_multi* me, int32_t k, int64_t* first, int64_t* count, int32_t* device, bsq_timing* timing) {
+  if (!me || k < 0 || k >= (int32_t)me->shards.size()) return BSQ_ERR_ARG;
+  const bsq_multi::Shard& sh = me->shards[(size_t)k];
+  if (first) *first = sh.first;
+  if (count) *count = sh.count;
+  if (device) *device = sh.device;
+  if (timing) *timing = sh.tm;
+  return BSQ_SUCCESS;
+}
+
+int bsq_multi_align_batch(bsq_multi* me, const bsq_params* params, int64_t npairs, const uint8_t* codes,
+                          int64_t ncodes, const int64_t* o_off, const int32_t* o_len, const int64_t* m_off,
+                          const int32_t* m_len, const int32_t* dmin, const int32_t* dmax, double* score,
+                          int32_t* end_x, int32_t* end_y, int32_t* start_x, int32_t* start_y, int32_t* status,
+                          int64_t* tx_off, int32_t* tx_len, char* tx_buf, int64_t tx_cap) {
+  if (!me) return BSQ_ERR_ARG;
+  me->err.clear();
+  auto bad = [&](int code, const std::string& msg) { me->err = msg; g_err = msg; return code; };
+  if (!params || npairs < 0 || npairs >= ((int64_t)1 << 31)) return bad(BSQ_ERR_ARG, "bad argument");
+  if (npairs > 0 && (!codes || !o_len || !m_len || !score || !status)) return bad(BSQ_ERR_ARG, "NULL array");
+  if ((o_off == nullptr) != (m_off == nullptr)) return bad(BSQ_ERR_ARG, "o_off and m_off must both be given or both be NULL");
+  if (params->mode == BSQ_BANDED_MODE && (!dmin || !dmax)) return bad(BSQ_ERR_ARG, "BANDED needs dmin/dmax");
+  const bool want_tx = tx_off && tx_buf;
+  if (want_tx && !tx_len) return bad(BSQ_ERR_ARG, "bsq_multi_align_batch needs tx_len next to tx_off/tx_buf");
+  const int K = (int)me->shards.size();
+  const bool tx2 = (params->flags & BSQ_F_TX_2BIT) != 0, c2 = (params->flags & BSQ_F_CODES_2BIT) != 0;
+  for (auto& sh : me->shards) { sh.first = sh.count = 0; sh.rc = BSQ_SUCCESS; memset(&sh.tm, 0, sizeof sh.tm); }
+  if (npairs == 0) return BSQ_SUCCESS;
+
+  // ---- cut [0, npairs) into K contiguous ranges of equal work.  Work of a pair ~ its DP cells
+  // ((n+1)(m+1), or band width x shorter side); letters[] = prefix of n + m (windows of codes[] for
+  // back-to-back batches, worst-case transcript room for every batch)
+  const int T = parallel_threads(npairs);
+  std::vector<double> pw((size_t)T + 1, 0.0);
+  std::vector<int64_t> pl((size_t)T + 1, 0);
+  auto weight = [&](int64_t i) -> double {
+    const double n = o_len[i], m = m_len[i];
+    if (params->mode == BSQ_STD_MODE) return (n + 1) * (m + 1);
+    const double w = std::max(1.0, std::min<double>(dmax[i], n) - std::max<double>(dmin[i], -m) + 1);
+    return w * (std::min(n, m) + 1);
+  };
+  parallel_for(npairs, [&](int t, int64_t i0, int64_t i1) {
+    double w = 0; int64_t l = 0;
+    for (int64_t i = i0; i < i1; i++) { w += weight(i); l += (int64_t)o_len[i] + m_len[i]; }
+    pw[(size_t)t + 1] = w; pl[(size_t)t + 1] = l;
+  });
+  for (int t = 0; t < T; t++) { pw[(size_t)t + 1] += pw[(size_t)t]; pl[(size_t)t + 1] += pl[(size_t)t]; }
+  const double total_w = pw[(size_t)T];
+  std::vector<int64_t> cut((size_t)K + 1, npairs), let_at((size_t)K + 1, pl[(size_t)T]);
+  cut[0] = 0; let_at[0] = 0;
+  {
+    int k = 1;
+    for (int t = 0; t < T && k < K; t++) {   // walk the thread ranges that hold a boundary
+      const int64_t i0 = npairs * t / T, i1 = npairs * (t + 1) / T;
+      if (pw[(size_t)t + 1] < total_w * k / K) continue;
+      double w = pw[(size_t)t]; int64_t l = pl[(size_t)t];
+      for (int64_t i = i0; i < i1 && k < K; i++) {
+        while (k < K && w >= total_w * k / K) { cut[(size_t)k] = i; let_at[(size_t)k] = l; k++; }
+        w += weight(i); l += (int64_t)o_len[i] + m_len[i];
+      }
+    }
+  }
+  // transcript regions (in ops): R_0 = 0, R_{k+1} = R_k + roundup64(worst case of shard k)
+  std::vector<int64_t> R((size_t)K + 1, 0);
+  for (int k = 0; k < K; k++) R[(size_t)k + 1] = R[(size_t)k] + ((let_at[(size_t)k + 1] - let_at[(size_t)k] + 63) / 64) * 64;
+  if (want_tx && (tx2 ? R[(size_t)K] / 4 : R[(size_t)K]) > tx_cap)
+    return bad(BSQ_ERR_CAPACITY, "tx_buf must hold the worst case: sum(o_len + m_len) + 64 * bsq_multi_size() ops");
+
+  auto run_shard = [&](int k) {
+    bsq_multi::Shard& sh = me->shards[(size_t)k];
+    const int64_t b = cut[(size_t)k], e = cut[(size_t)k + 1], n = e - b;
+    sh.first = b; sh.count = n;
+    if (n <= 0) return;
+    g_plan_serial = true;
+    cudaSetDevice(sh.device);
+    // the window of codes[] this shard's pairs reference, starting on a 4-letter boundary
+    int64_t lo, hi;
+    if (!o_off) { lo = let_at[(size_t)k]; hi = let_at[(size_t)k + 1]; }
+    else {
+      lo = INT64_MAX; hi = 0;
+      for (int64_t i = b; i < e; i++) {
+        lo = std::min(lo, std::min(o_off[i], m_off[i]));
+        hi = std::max(hi, std::max(o_off[i] + o_len[i], m_off[i] + m_len[i]));
+      }
+      if (lo < 0 || hi > ncodes) { sh.rc = BSQ_ERR_ARG; sh.ctx->err = "sequence range outside codes[]"; return; }
+    }
+    const int64_t ws = lo & ~(int64_t)3;
+    const uint8_t* cw = codes + (c2 ? ws / 4 : ws);
+    const int64_t base = o_off ? -ws : lo - ws;
+    int64_t* loc = nullptr;
+    if (want_tx) {
+      if (!sh.txoff.ensure(8 * (size_t)(n + 1))) { sh.rc = BSQ_ERR_NOMEM; sh.ctx->err = "pinned host allocation failed"; return; }
+      loc = sh.txoff.as<int64_t>();
+    }
+    const int64_t rcap = R[(size_t)k + 1] - R[(size_t)k];
+    int64_t total = 0;
+    sh.rc = align_batch_retry(sh.ctx, params, n, cw, hi - ws, o_off ? o_off + b : nullptr, o_len + b,
+                              m_off ? m_off + b : nullptr, m_len + b, dmin ? dmin + b : nullptr, dmax ? dmax + b : nullptr,
+                              score + b, end_x ? end_x + b : nullptr, end_y ? end_y + b : nullptr,
+                              start_x ? start_x + b : nullptr, start_y ? start_y + b : nullptr, status + b, loc,
+                              want_tx ? tx_buf + (tx2 ? R[(size_t)k] / 4 : R[(size_t)k]) : nullptr,
+                              tx2 ? rcap / 4 : rcap, &total, base);
+    sh.tm = sh.ctx->tm;
+    if (sh.rc == BSQ_SUCCESS && want_tx) {
+      for (int64_t i = 0; i < n; i++) { tx_off[b + i] = R[(size_t)k] + loc[i]; tx_len[b + i] = (int32_t)(loc[i + 1] - loc[i]); }
+    }
+    g_plan_serial = false;
+  };
+#ifdef BSQ_SIMT_EMU
+  for (int k = 0; k < K; k++) run_shard(k);      // the emulator's fibers are not thread safe
+#else
+  {
+    std::vector<std::thread> th;
+    for (int k = 1; k < K; k++) th.emplace_back(run_shard, k);
+    run_shard(0);
+    for (auto& t : th) t.join();
+  }
+#endif
+  if (want_tx) tx_off[npairs] = R[(size_t)K];
+  for (int k = 0; k < K; k++) {
+    const bsq_multi::Shard& sh = me->shards[(size_t)k];
+    if (sh.rc != BSQ_SUCCESS)
+      return bad(sh.rc, "shard " + std::to_string(k) + " (device " + std::to_string(sh.device) + "): " + sh.ctx->err);
+  }
+  return BSQ_SUCCESS;
 }
 
 #ifdef BSQ_K3_PROFILE

@@ -159,6 +159,11 @@ __device__ __forceinline__ int bsq_nz(int h, int x) {
 #endif
 }
 
+// 0 if x == h, else 1, given mh = -h (h >= x always): (x - h) mod 2^32 is 0 or >= 2^31, so one
+// unsigned add-min (VIADDMNMX.U32) per candidate and ONE negation per cell.  (bsq_nz above needs
+// a negation per candidate: measured 2-3 IMAD per cell in the issue-bound K2 loop.)
+__device__ __forceinline__ int bsq_nzu(unsigned mh, int x) { return (int)__viaddmin_u32((unsigned)x, mh, 1u); }
+
 // Integer cell without predicates: nX = min(h - X, 1) is 0 iff candidate X ties
 // for the maximum (h >= X always), so the tie set, the open/extend flags and the
 // pointer nibble are plain integer arithmetic -- subtractions and multiply-adds
@@ -181,10 +186,11 @@ __device__ __forceinline__ void bsq_cell_i32(int up, int gD, int left, int gI, i
     if (HASB) h = max(h, bval);
   }
   // differences in unsigned arithmetic: a -2^30 sentinel candidate may sit 2^31 below h
-  nD = bsq_nz(h, D);
-  nI = bsq_nz(h, I);
-  nM = bsq_nz(h, M);
-  nB = HASB ? bsq_nz(h, BZERO ? 0 : bval) : 1;
+  const unsigned mh = 0u - (unsigned)h;
+  nD = bsq_nzu(mh, D);
+  nI = bsq_nzu(mh, I);
+  nM = bsq_nzu(mh, M);
+  nB = HASB ? bsq_nzu(mh, BZERO ? 0 : bval) : 1;
   H = h;
 }
 
@@ -556,7 +562,14 @@ __device__ __forceinline__ void bsq_k2_step_fast(
   constexpr int SH = (sizeof(T) == 8) ? 3 : 2;  // log2 of the table entry size
   uint32_t cur[WPS];
 #pragma unroll
-  for (int w = 0; w < WPS; w++) cur[w] = 0u;
+  for (int w = 0; w < WPS; w++) {
+    cur[w] = 0u;
+    if (S::IS_INT) {   // every candidate of every cell ties (B only where it exists); the cells subtract
+      const int ncell = (HC - 8 * w) < 8 ? (HC - 8 * w) : 8;
+      const uint32_t each = BLOCAL ? 0xFFFFFFFFu : 0xEEEEEEEEu;
+      cur[w] = ncell >= 8 ? each : (each & ((1u << (4 * (ncell > 0 ? ncell : 0))) - 1u));
+    }
+  }
   const uint32_t comb_lo = (uint32_t)comb, comb_hi = (uint32_t)(comb >> 32);
 #pragma unroll
   for (int hc = 0; hc < HC; hc++) {
@@ -580,11 +593,26 @@ __device__ __forceinline__ void bsq_k2_step_fast(
       sig = s_sub[(int)oseq[x - 1] * L + (int)mseq[y - 1]];
     }
     if constexpr (S::IS_INT) {
-      int h, nB, nD, nI, nM;
-      bsq_cell_i32<GOS, BLOCAL, true>(up, gD, left, gI, diag, sig, 0, go, ge, h, nB, nD, nI, nM);
-      const int notmask = nB + 2 * nD + 4 * nI + 8 * nM;
-      cur[hc >> 3] += (uint32_t)(15 - notmask) << (4 * (hc & 7));
-      H[c] = h;
+      // Integer interior cell, the issue-bound inner loop of the banded fill.  In this phase the state
+      // array holds G = H + ge (the caller converts on entry and exit, like K1h) and the score table
+      // holds subst - ge, so the three candidates cost one add (two more multiply-adds for affine
+      // gaps); the tie flags nX = min((X - h) mod 2^32, 1) share one negation; the pointer word
+      // starts out as "every candidate ties" and each flag subtracts its bit with one multiply-add.
+      int D = up, I = left;
+      if (GOS != 0) { D = gD * go + D; I = gI * go + I; }
+      const int M = diag + sig;
+      const int h = BLOCAL ? __vimax3_s32_relu(D, I, M) : __vimax3_s32(D, I, M);
+      const unsigned mh = 0u - (unsigned)h;
+      const int nD = bsq_nzu(mh, D), nI = bsq_nzu(mh, I), nM = bsq_nzu(mh, M);
+      const int nB = BLOCAL ? (int)min((unsigned)h, 1u) : 1;   // B (score 0) ties iff h == 0
+      const uint32_t SHB = 4u * (uint32_t)(hc & 7);            // hc: an unrolled loop index, a constant
+      uint32_t w = cur[hc >> 3];
+      if (BLOCAL) w = (uint32_t)nB * (0u - (1u << SHB)) + w;
+      w = (uint32_t)nD * (0u - (2u << SHB)) + w;
+      w = (uint32_t)nI * (0u - (4u << SHB)) + w;
+      w = (uint32_t)nM * (0u - (8u << SHB)) + w;
+      cur[hc >> 3] = w;
+      H[c] = h + ge;
       fD[c] = bsq_gapflag_i32<GOS>(nD, nB, nI, nM);
       fI[c] = bsq_gapflag_i32<GOS>(nI, nB, nD, nM);
       if (BLOCAL) {
@@ -635,11 +663,18 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
   const bool packed = (L <= 4);
   for (int i = threadIdx.x; i < BSQ_MAX_L * BSQ_MAX_L; i += blockDim.x) s_sub[i] = (T)0;
   __syncthreads();
+  // the integer interior steps keep G = H + ge as their state and read subst - ge (see bsq_k2_step_fast)
+  __shared__ T s_subm[S::IS_INT ? BSQ_MAX_L * BSQ_MAX_L : 1];
   for (int i = threadIdx.x; i < L * L; i += blockDim.x) {
     const int o = i / L, mm = i - o * L;
     s_sub[packed ? (o * 4 + mm) : i] = ((const T*)A.subst)[i];
   }
   __syncthreads();
+  if (S::IS_INT) {
+    for (int i = threadIdx.x; i < BSQ_MAX_L * BSQ_MAX_L; i += blockDim.x) s_subm[i] = S::add(s_sub[i], (T)0 - S::ge(A));
+    __syncthreads();
+  }
+  const T* s_fast = S::IS_INT ? s_subm : s_sub;
   const int Lt = packed ? 4 : L;  // row stride of s_sub
 
   const int tid = threadIdx.x;
@@ -736,6 +771,10 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
           mw |= (unsigned long long)v << (4 * j);
         }
       }
+      if (S::IS_INT) {   // H -> G = H + ge for the interior phase
+#pragma unroll
+        for (int c = 0; c < C; c++) H[c] = S::add(H[c], ge);
+      }
       for (; s <= sB; s += 2) {
         unsigned no = 0u, nm = 0u;  // letters entering the windows after this pair
         if (packed) {
@@ -750,19 +789,19 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
         int eF = __shfl_up_sync(gmask, fD[C - 1], 1, G);
         if (l == 0) { eH = NINF; eF = 0; }
         if (packed)
-          bsq_k2_step_fast<S, C, BLOCAL, GOS, 0, true>(H, fD, fI, best, bests, eH, eF, s_sub, Lt, ow | mw, oseq,
+          bsq_k2_step_fast<S, C, BLOCAL, GOS, 0, true>(H, fD, fI, best, bests, eH, eF, s_fast, Lt, ow | mw, oseq,
                                                        mseq, s, d0, fixc, go, ge, pe);
         else
-          bsq_k2_step_fast<S, C, BLOCAL, GOS, 0, false>(H, fD, fI, best, bests, eH, eF, s_sub, Lt, 0ull, oseq,
+          bsq_k2_step_fast<S, C, BLOCAL, GOS, 0, false>(H, fD, fI, best, bests, eH, eF, s_fast, Lt, 0ull, oseq,
                                                         mseq, s, d0, fixc, go, ge, pe);
         eH = __shfl_down_sync(gmask, H[0], 1, G);
         eF = __shfl_down_sync(gmask, fI[0], 1, G);
         if (l == G - 1) { eH = NINF; eF = 0; }
         if (packed)
-          bsq_k2_step_fast<S, C, BLOCAL, GOS, 1, true>(H, fD, fI, best, bests, eH, eF, s_sub, Lt, ow_odd | mw,
+          bsq_k2_step_fast<S, C, BLOCAL, GOS, 1, true>(H, fD, fI, best, bests, eH, eF, s_fast, Lt, ow_odd | mw,
                                                        oseq, mseq, s + 1, d0, fixc, go, ge, po);
         else
-          bsq_k2_step_fast<S, C, BLOCAL, GOS, 1, false>(H, fD, fI, best, bests, eH, eF, s_sub, Lt, 0ull, oseq,
+          bsq_k2_step_fast<S, C, BLOCAL, GOS, 1, false>(H, fD, fI, best, bests, eH, eF, s_fast, Lt, 0ull, oseq,
                                                         mseq, s + 1, d0, fixc, go, ge, po);
         if (packed) {
           ow = ow_odd;
@@ -770,6 +809,10 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
           mw = (mw << 4) | (unsigned long long)nm;
           x0++; y0++;
         }
+      }
+      if (S::IS_INT) {   // back to H for the careful steps and the end-cell search
+#pragma unroll
+        for (int c = 0; c < C; c++) H[c] = S::add(H[c], (T)0 - ge);
       }
     }
     for (; s <= s_end; s += 2) BSQ_K2_CAREFUL_PAIR()

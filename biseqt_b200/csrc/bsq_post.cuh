@@ -338,6 +338,88 @@ __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTrac
 }
 
 // ---------------------------------------------------------------------------
+// K4t: the walk for BIG batches of long banded pairs (K2 tables), one THREAD per pair.
+// The tile walker above issues every instruction for 8 or 32 lanes that all do the same
+// walk and stages whole table rows (64 - 128 B per op) of which the path needs one nibble;
+// with tens of thousands of pairs in a chunk there is no need to spend a group on one pair:
+// a thread per pair walks straight out of global memory (one 4-byte load per op, incremental
+// addressing without divisions), prefetches the two rows it will reach PF rows further down into
+// L2 (a path stays on its diagonal or moves to a neighbour: the same 32-byte sector), and emits
+// four ops per 32-bit store.  ~8x fewer issued instructions and ~2x fewer DRAM bytes.
+//   table layout (bsq_k2_fill): [s - s0][lane][word], C/2 nibbles per lane and step
+// ---------------------------------------------------------------------------
+#define BSQ_WALKT_PF 24       // rows ahead that are prefetched (both parities of s)
+
+template <int GOS>
+__global__ void __launch_bounds__(128) bsq_k2_walk_thread(const BsqTraceArgs A) {
+  BSQ_BAIL_IF_BAD(A);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= A.npairs) return;
+  const BsqPair P = A.pairs[p];
+  const int oi = P.pad;
+  if (A.status[oi] != BSQ_OK) { A.txlen[oi] = 0; A.sx[oi] = -1; A.sy[oi] = -1; return; }
+  const int G = A.G, C = A.K, WPS = (C / 2 + 7) / 8, RB = G * WPS;
+  const int ex = A.ex[oi], ey = A.ey[oi];
+  int x = ex, y = ey, len = 0;
+  const int di = (x - y) - P.dmin;
+  int l = di / C, c = di - l * C;
+  long long row = (long long)(x + y) - P.s0;
+  const uint32_t* pw = A.ptr + P.ptr_off + row * RB + l * WPS;   // my lane's first word of the current row
+  const uint8_t* oseq = A.codes + P.o_off;
+  const uint8_t* mseq = A.codes + P.m_off;
+  char* wr_end = A.slots + P.tx_slot + (long long)P.n + P.m;      // one past the slot end
+  const int maxlen = P.n + P.m;
+  uint32_t arrive = BSQ_MM;     // how we got here: M (or the end cell) -> lowest bit
+  uint32_t acc = 0u;            // the last `filled` ops, latest in the low byte
+  int filled = 0;
+  for (;;) {
+    const int hc = c >> 1;
+    const uint32_t mk = (pw[hc >> 3] >> (4 * (hc & 7))) & 0xFu;
+    const uint32_t op = (arrive == BSQ_MM) ? bsq_lowest(mk) : bsq_gap_base_t<GOS>(mk, arrive);
+    if (op == BSQ_MB || op == 0u || len >= maxlen) break;
+    const bool isM = (op == BSQ_MM), isD = (op == BSQ_MD), isI = !(isM || isD);
+    const int xi = x > 0 ? x - 1 : 0, yi = y > 0 ? y - 1 : 0;       // only meaningful for a diagonal move
+    const char ms = (oseq[xi] == mseq[yi]) ? 'M' : 'S';
+    const uint32_t ch = (uint32_t)(unsigned char)(isM ? ms : (isD ? 'D' : 'I'));
+    acc = (acc << 8) | ch;
+    len++;
+    filled++;
+    {
+      char* a = wr_end - len;
+      if ((((unsigned long long)a) & 3ull) == 0ull) {     // a word boundary: flush
+        if (filled == 4) *(uint32_t*)a = acc;
+        else for (int j = 0; j < filled; j++) a[j] = (char)((acc >> (8 * j)) & 0xffu);
+        filled = 0;
+      }
+    }
+    arrive = op;
+    x -= isI ? 0 : 1;
+    y -= isD ? 0 : 1;
+    const int dr = isM ? 2 : 1;                  // s = x + y drops by 2 on a diagonal move
+    row -= dr;
+    pw -= dr * RB;
+    c += isI ? 1 : (isD ? -1 : 0);               // local diagonal moves with x - y
+    if (c < 0) { c = C - 1; l--; pw -= WPS; }
+    if (c == C) { c = 0; l++; pw += WPS; }
+#ifndef BSQ_SIMT_EMU
+    if (row > BSQ_WALKT_PF) {
+      const uint32_t* pf = pw - BSQ_WALKT_PF * RB + (hc >> 3);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pf - RB));
+    }
+#endif
+  }
+  if (filled > 0) {
+    char* a = wr_end - len;
+    for (int j = 0; j < filled; j++) a[j] = (char)((acc >> (8 * j)) & 0xffu);
+  }
+  A.txlen[oi] = len;
+  A.sx[oi] = x;
+  A.sy[oi] = y;
+  A.status[oi] = (ex + ey - len <= 0) ? BSQ_REF_WOULD_ABORT : (len == 0 ? BSQ_EMPTY : BSQ_OK);
+}
+
+// ---------------------------------------------------------------------------
 // K3 traceback (pw.c:116-151): one warp per pair walks the [strip][t][lane]
 // table out of shared-memory tiles (the rows at and below the current step of
 // the current strip), like bsq_k4_walk.
@@ -609,8 +691,8 @@ __global__ void __launch_bounds__(256) bsq_make_pairs_uniform(const long long* o
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   BsqPair bp;
-  if (o_off) { bp.o_off = o_off[e]; bp.m_off = m_off[e]; }
-  else { bp.o_off = e * ((long long)U.n + U.m); bp.m_off = bp.o_off + U.n; }   // pairs back to back in codes[]
+  if (o_off) { bp.o_off = o_off[e] + U.off_base; bp.m_off = m_off[e] + U.off_base; }
+  else { bp.o_off = U.off_base + e * ((long long)U.n + U.m); bp.m_off = bp.o_off + U.n; }   // pairs back to back in codes[]
   bp.ptr_off = (e % U.ppc) * U.words;
   bp.tx_slot = e * ((long long)U.n + U.m);
   bp.n = U.n; bp.m = U.m;

@@ -276,6 +276,36 @@ int bsq_generate_pairs(bsq_ctx* ctx, const bsq_gen_params* gen, int64_t npairs,
 #define BSQ_MB_COUNT 9
 int bsq_microbench(bsq_ctx* ctx, int32_t which, double* ops_per_sec);
 
+/*
+ * ONE caller batch over several GPUs of one box (pairs are independent: no collective, no peer
+ * traffic; the reference's callers hand one process a list of segment pairs, experiments/
+ * blot_stats.py:365-459).  The batch is cut into contiguous ranges of equal work (DP cells), one
+ * per GPU; one host thread + one context per GPU runs bsq_align_batch on its range and writes
+ * straight into disjoint slices of the caller's arrays (each GPU only receives the window of
+ * codes[] its pairs reference).  Same arguments and semantics as bsq_align_batch except for the
+ * transcripts: every GPU packs its own region of tx_buf, so transcript i is ops
+ * tx_off[i] .. tx_off[i] + tx_len[i] (tx_len is an extra output) and tx_cap must hold the worst
+ * case, sum(o_len + m_len) + 64 * bsq_multi_size() ops (a quarter of that in bytes with
+ * BSQ_F_TX_2BIT).  devices == NULL means ordinals 0 .. ndev-1; an ordinal may repeat (several
+ * contexts on one GPU).
+ */
+typedef struct bsq_multi bsq_multi;
+bsq_multi* bsq_multi_create(int32_t ndev, const int32_t* devices);
+void bsq_multi_destroy(bsq_multi* me);
+int32_t bsq_multi_size(const bsq_multi* me);
+const char* bsq_multi_last_error(const bsq_multi* me);
+int bsq_multi_align_batch(bsq_multi* me, const bsq_params* params, int64_t npairs,
+                          const uint8_t* codes, int64_t ncodes,
+                          const int64_t* o_off, const int32_t* o_len,
+                          const int64_t* m_off, const int32_t* m_len,
+                          const int32_t* dmin, const int32_t* dmax,
+                          double* score, int32_t* end_x, int32_t* end_y,
+                          int32_t* start_x, int32_t* start_y, int32_t* status,
+                          int64_t* tx_off, int32_t* tx_len, char* tx_buf, int64_t tx_cap);
+/* shard k of the last bsq_multi_align_batch: the range of pairs it took, its device, its timing */
+int bsq_multi_get_shard(const bsq_multi* me, int32_t k, int64_t* first, int64_t* count,
+                        int32_t* device, bsq_timing* timing);
+
 /* pure host helpers (usable without a GPU) ------------------------------- */
 
 /* cells the reference's fill loop visits for one problem (pw.c:59-61 over

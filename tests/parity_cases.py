@@ -701,6 +701,62 @@ def run_compact_io(make_engine, seed, npairs=41):
             eng.close()
 
 
+def run_multi(make_engine, make_multi, seed, npairs=60):
+    """bsq_multi: one batch cut over several contexts (on one GPU here: ordinals may repeat; the
+    8-GPU box runs the same code with distinct ordinals) equals the single-context result byte for
+    byte -- ragged and uniform batches, banded, explicit and back-to-back offsets, compact forms,
+    fewer pairs than shards."""
+    rng = np.random.default_rng(seed)
+    eng = make_engine()
+    try:
+        for nshards in (1, 2, 3):
+            me = make_multi(nshards)
+            try:
+                for mode, typ, uniform, n_pairs in ((0, 1, False, npairs), (0, 1, True, npairs), (1, 2, False, npairs),
+                                                    (1, 0, True, 7), (0, 0, False, 2), (0, 4, False, 1)):
+                    S, go, ge = score_family(rng, 4, int(rng.integers(1, 3)), int(rng.integers(-1, 1)))
+                    pairs, dmin, dmax = [], [], []
+                    for i in range(n_pairs):
+                        n = 70 if uniform else int(rng.integers(0, 200))
+                        m = 64 if uniform else int(rng.integers(0, 200))
+                        o = rng.integers(0, 4, size=n).astype(np.uint8)
+                        t = rng.integers(0, 4, size=m).astype(np.uint8)
+                        k = min(n, m)
+                        if i % 4:
+                            t[:k] = o[:k]
+                            if m > 8:
+                                t[rng.integers(0, m, size=m // 8)] = rng.integers(0, 4, size=m // 8)
+                        pairs.append((o, t))
+                        dmin.append(min(-5, n - m))
+                        dmax.append(max(6, n - m))
+                    codes, o_off, o_len, m_off, m_len = batch.pack_pairs(pairs)
+                    kw = dict(dmin=dmin, dmax=dmax) if mode == 1 else {}
+                    base = eng.align(codes, o_off, o_len, m_off, m_len, mode, typ, S, go, ge, **kw)
+                    packed = batch.pack_codes_2bit(codes)
+                    what = '%d shards, mode %d type %d uniform %s' % (nshards, mode, typ, uniform)
+                    for variant, r in (
+                            ('plain', me.align(codes, o_off, o_len, m_off, m_len, mode, typ, S, go, ge, **kw)),
+                            ('no offsets', me.align(codes, None, o_len, None, m_len, mode, typ, S, go, ge, **kw)),
+                            ('compact', me.align(packed, None, o_len, None, m_len, mode, typ, S, go, ge, codes_2bit=True,
+                                                 ncodes=len(codes), tx_2bit=True, **kw)),
+                            ('2-bit in, offsets', me.align(packed, o_off, o_len, m_off, m_len, mode, typ, S, go, ge,
+                                                           codes_2bit=True, ncodes=len(codes), **kw))):
+                        assert np.array_equal(base.status, r.status), (what, variant)
+                        assert np.array_equal(base.score, r.score), (what, variant)
+                        ok = base.status == 0
+                        for k in ('end_x', 'end_y', 'start_x', 'start_y'):
+                            assert np.array_equal(getattr(base, k)[ok], getattr(r, k)[ok]), (what, variant, k)
+                        assert np.array_equal(base.tx_len, r.tx_len), (what, variant)
+                        assert base.transcripts() == r.transcripts(), (what, variant)
+                    sh = me.shards()
+                    assert sum(c for _, c, _, _ in sh) == n_pairs and sh[0][0] == 0
+                    assert all(sh[k][0] + sh[k][1] == sh[k + 1][0] for k in range(nshards - 1))
+            finally:
+                me.close()
+    finally:
+        eng.close()
+
+
 def run_lifetime(make_engine):
     """Batches that outlive their engine (an Engine closed, or collected, before its SolvedBatch /
     ResidentBatch): release and every other call on them must not touch the dead context."""

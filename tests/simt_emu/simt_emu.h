@@ -267,6 +267,7 @@ inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __vimax3_s32(int a, int b, int c) { return std::max(a, std::max(b, c)); }
 inline int __vimax3_s32_relu(int a, int b, int c) { return std::max(0, std::max(a, std::max(b, c))); }
 inline int __viaddmax_s32(int a, int b, int c) { return std::max(a + b, c); }
+inline unsigned __viaddmin_u32(unsigned a, unsigned b, unsigned c) { return std::min(a + b, c); }
 inline int max(int a, int b) { return a > b ? a : b; }
 inline int min(int a, int b) { return a < b ? a : b; }
 inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }

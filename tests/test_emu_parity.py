@@ -38,7 +38,7 @@ def test_emu_wide_band_interior(emu_engine):
     pc.run_wide_bands(emu_engine, seed=45, length=520, radii=(460,))
 
 
-@pytest.mark.parametrize('which', ['warp', 'narrow'])
+@pytest.mark.parametrize('which', ['warp', 'narrow', 'pairthread'])
 def test_emu_warp_traceback(emu_lib, monkeypatch, which):
     """Force the tile walker (normally only used for long pairs): a warp, or 8 lanes, per pair."""
     monkeypatch.setenv('BSQ_TRACE_KERNEL', which)
@@ -78,6 +78,10 @@ def test_emu_edge_cases(emu_engine):
 
 def test_emu_compact_io(emu_lib):
     pc.run_compact_io(lambda: batch.Engine(0, lib=emu_lib), seed=111, npairs=13)
+
+
+def test_emu_multi(emu_lib):
+    pc.run_multi(lambda: batch.Engine(0, lib=emu_lib), lambda n: batch.MultiEngine([0] * n, lib=emu_lib), seed=121, npairs=17)
 
 
 def test_emu_lifetime(emu_lib):

@@ -48,7 +48,7 @@ def test_gpu_banded_interior(gpu_engine):
 
 
 def test_gpu_both_traceback_kernels(monkeypatch):
-    for which in ('warp', 'narrow', 'thread'):
+    for which in ('warp', 'narrow', 'thread', 'pairthread'):
         monkeypatch.setenv('BSQ_TRACE_KERNEL', which)
         eng = batch.Engine(0)
         try:
@@ -86,6 +86,13 @@ def test_gpu_edge_cases(gpu_engine):
 
 def test_gpu_compact_io():
     pc.run_compact_io(lambda: batch.Engine(0), seed=111, npairs=301)
+
+
+def test_gpu_multi():
+    """One batch over several contexts; distinct GPUs when the box has them, else repeated on cuda:0."""
+    from biseqt_b200 import _ffi
+    ndev = _ffi.load().bsq_device_count()
+    pc.run_multi(lambda: batch.Engine(0), lambda n: batch.MultiEngine([k % ndev for k in range(n)]), seed=121, npairs=400)
 
 
 def test_gpu_lifetime():

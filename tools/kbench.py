@@ -15,7 +15,7 @@ def main():
     trace = (len(sys.argv) <= 4) or sys.argv[4] != 'notrace'
     from biseqt_b200 import _ffi
     eng = batch.Engine(0, lib=_ffi.load(os.environ['BSQ_LIB']) if os.environ.get('BSQ_LIB') else None)   # A/B builds
-    w = bw.make(kind, npairs, seed=3)
+    w = bw.make_device(eng, kind, npairs, seed=3)
     rb = eng.upload(w['codes'], w['o_off'], w['o_len'], w['m_off'], w['m_len'], w['mode'], w['type'],
                     w['subst'], w['go'], w['ge'], dmin=w.get('dmin'), dmax=w.get('dmax'))
     fills, tots = [], []

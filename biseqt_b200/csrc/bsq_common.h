@@ -125,4 +125,5 @@ struct BsqTraceArgs {
   char* slots;           // transcripts, right-aligned in [tx_slot, tx_slot+n+m)
   int family;            // 1 = K1, 2 = K2, 3 = K3 table layout
   const int* bad;        // != 0: the fill did not run (see BsqFillArgs.bad)
+  const uint32_t* codes2; // the same letters, 16 per 32-bit word (alphabets <= 4), or NULL
 };

@@ -115,6 +115,7 @@ struct Hooks {
   bool always_sort = false;     // BSQ_ALWAYS_SORT: no caller-order planners (test)
   bool serial_scan = false;     // BSQ_SERIAL_SCAN: serial chunk-cutting scan (test)
   bool plan_debug = false;      // BSQ_PLAN_DEBUG: planner / chunk timeline on stderr
+  bool no_std_band = false;     // BSQ_NO_STD_BAND: big STD GLOBAL pairs stay on K1 (test)
   int64_t uniform_min = 4096;   // BSQ_UNIFORM_MIN: pairs from which the uniform plan / K1h are used
   int64_t plan_block = 4096;    // BSQ_PLAN_BLOCK: block size of the caller-order planner
   int target_chunks = -1;       // BSQ_TARGET_CHUNKS: chunks to cut a batch into (< 0: automatic)
@@ -129,6 +130,7 @@ struct Hooks {
     always_sort = getenv("BSQ_ALWAYS_SORT") != nullptr;
     serial_scan = getenv("BSQ_SERIAL_SCAN") != nullptr;
     plan_debug = getenv("BSQ_PLAN_DEBUG") != nullptr;
+    no_std_band = getenv("BSQ_NO_STD_BAND") != nullptr;
     uniform_min = num("BSQ_UNIFORM_MIN", 4096);
     plan_block = std::max<long long>(1, num("BSQ_PLAN_BLOCK", 4096));
     target_chunks = (int)num("BSQ_TARGET_CHUNKS", -1);
@@ -168,6 +170,7 @@ struct Plan {
   int64_t max_chunk_words = 0;
   int64_t total_words = 0;
   bool identity = false;  // processing order == caller order (no sort was needed)
+  bool codes2_ok = false; // BufSet.codes2 holds the 2-bit packed copy of this batch's letters
   int64_t half_words = 0; // > 0: BSQ_ARENA_SLOTS arena slots of this size, chunk c uses slot c % SLOTS so that
                           // trace(c) overlaps the fills of the following chunks
   // uniform batches (every pair the same shape, e.g. fixed-length reads): the pair records are
@@ -194,6 +197,7 @@ struct bsq_ctx {
   std::vector<PlanItem> plan_items;  // planner scratch, kept across calls (no page faults)
   std::vector<int64_t> plan_order, plan_ptr_off, plan_slot_off, plan_sorted;
   std::vector<int64_t> plan_ooff, plan_moff;   // offsets of a back-to-back batch given without o_off / m_off
+  std::vector<int32_t> plan_band_lo, plan_band_hi;   // full bands of STD GLOBAL pairs planned as wide bands
   std::vector<char> plan_gather;
   std::string err;
   bsq_timing tm;
@@ -361,10 +365,7 @@ int k3_op(int dtype, int cfg, int btype, int gos, int grid, cudaStream_t st, con
                                 : bsq_k3_f64_op(cfg, btype, gos, grid, st, A);
 }
 
-// K3 geometry for bands no K2 geometry holds (or for every band: Hooks.force_k3)
-int pick_k3_cfg(int forced) {
-  return (forced >= 0 && forced < BSQ_K3_NCFG) ? forced : 1;  // K = 4 columns x R = 2 rows per lane and step: measured best on C5
-}
+
 
 // ---- planning -------------------------------------------------------------
 
@@ -461,6 +462,27 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   if (!std::isfinite(prm->go) || !std::isfinite(prm->ge)) return fail(ctx, BSQ_ERR_ARG, "go/ge must be finite");
   if ((prm->flags & BSQ_F_CODES_2BIT) && L > 4) return fail(ctx, BSQ_ERR_ARG, "BSQ_F_CODES_2BIT needs an alphabet of at most 4 letters");
   if (prm->flags & ~(BSQ_F_CODES_2BIT | BSQ_F_TX_2BIT)) return fail(ctx, BSQ_ERR_ARG, "unknown bits in params.flags");
+  // One (or a handful of) big STD GLOBAL problems -- the reference's own calling pattern, config 1 --
+  // are latency bound on K1 (one warp walks the whole table, two passes for 1 kb).  GLOBAL is
+  // B_GLOBAL with the full band [-m, n] (same B rule, same end cell (n,m), same traceback:
+  // _pw_internals.c:165-181 vs :182-197, :309-315 vs :366-378), so they are planned as wide bands
+  // and take the strip pipeline (K3L): every 64 columns another warp.
+  bsq_params eff = *prm;
+  bool std_as_band = false;
+  if (prm->mode == BSQ_STD_MODE && prm->type == BSQ_GLOBAL && N >= 1 && N <= 8 && !ctx->hooks.no_std_band) {
+    std_as_band = true;
+    for (int64_t i = 0; i < N; i++) if (o_len[i] < 256 || m_len[i] < 256) std_as_band = false;
+  }
+  if (std_as_band) {
+    ctx->plan_band_lo.resize((size_t)N);
+    ctx->plan_band_hi.resize((size_t)N);
+    for (int64_t i = 0; i < N; i++) { ctx->plan_band_lo[(size_t)i] = -m_len[i]; ctx->plan_band_hi[(size_t)i] = o_len[i]; }
+    dmin = ctx->plan_band_lo.data();
+    dmax = ctx->plan_band_hi.data();
+    eff.mode = BSQ_BANDED_MODE;
+    eff.type = BSQ_B_GLOBAL;
+    prm = &eff;
+  }
   P.prm = *prm;
   P.subst.assign(prm->subst, prm->subst + L * L);
   for (double& v : P.subst) {
@@ -524,8 +546,11 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   P.uniform_dev = false;
   P.pairs = nullptr;
   const Hooks& hk = ctx->hooks;
-  const bool force_k3 = hk.force_k3;
-  const int k3_cfg = pick_k3_cfg(hk.k3_cfg);
+  const bool force_k3 = hk.force_k3 || std_as_band;
+  // strip geometry: cfg 1 (4 columns x 2 rows per lane and step) unless forced; full-width bands of
+  // STD GLOBAL pairs take the latency form (cfg 0, bsq_k3l_fill: measured 0.46 ms against 3.04 ms on
+  // K1 for config 1; on config 5's 4097-diagonal band cfg 1 is still ahead, 367 ms against 415 ms)
+  const int k3_cfg = (hk.k3_cfg >= 0 && hk.k3_cfg < BSQ_K3_NCFG) ? hk.k3_cfg : (std_as_band ? 0 : 1);
   // K1h (two short problems per lane group, packed 16-bit arithmetic): what the scores and
   // the alignment type must satisfy; the shape conditions are per pair (PlanItem.lo for STD)
   double duo_maxabs = std::fabs(prm->go) + std::fabs(prm->ge);
@@ -1196,12 +1221,22 @@ inline int64_t codes_in_bytes(const bsq_params& prm, int64_t ncodes) {
   return (prm.flags & BSQ_F_CODES_2BIT) ? (ncodes + 3) / 4 : ncodes;
 }
 
+// the thread-per-pair banded walker reads letters out of a 2-bit packed copy of codes[]
+inline bool want_packed_copy(const bsq_params& prm) { return prm.alphabet_len <= 4 && prm.mode == BSQ_BANDED_MODE; }
+
 // H2D of bytes [b0, b1) of the caller's codes[] on stream st; packed input is expanded to one byte
 // per letter right behind the copy (same stream), so that every kernel reads B.codes
 int upload_codes(bsq_ctx* ctx, BufSet& B, const bsq_params& prm, const uint8_t* codes, int64_t b0, int64_t b1, cudaStream_t st) {
   if (b1 <= b0) return BSQ_SUCCESS;
   if (!(prm.flags & BSQ_F_CODES_2BIT)) {
     BSQ_CK(ctx, cudaMemcpyAsync((char*)B.codes.p + b0, codes + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st));
+    if (want_packed_copy(prm)) {   // letters [b0, b1) -> words [b0 / 16, ceil(b1 / 16)); slices start on 256-byte boundaries
+      const long long w_lo = b0 / 16, w_hi = (b1 + 15) / 16;
+      const int grid = (int)((w_hi - w_lo + 255) / 256);
+      BSQ_LAUNCH(bsq_pack_2bit, grid, 256, 0, st, (const uint8_t*)B.codes.as<uint8_t>(), (long long)b1, w_lo, w_hi, B.codes2.as<uint32_t>());
+      BSQ_CK(ctx, cudaGetLastError());
+      ctx->tm.fill_launches++;
+    }
     return BSQ_SUCCESS;
   }
   BSQ_CK(ctx, cudaMemcpyAsync((char*)B.codes2.p + b0, codes + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st));
@@ -1214,7 +1249,8 @@ int upload_codes(bsq_ctx* ctx, BufSet& B, const bsq_params& prm, const uint8_t* 
 }
 inline bool ensure_codes(BufSet& B, const bsq_params& prm, int64_t ncodes) {
   if (!B.codes.ensure((size_t)ncodes + 64)) return false;
-  return !(prm.flags & BSQ_F_CODES_2BIT) || B.codes2.ensure((size_t)codes_in_bytes(prm, ncodes) + 16);
+  if (!(prm.flags & BSQ_F_CODES_2BIT) && !want_packed_copy(prm)) return true;
+  return B.codes2.ensure((size_t)(ncodes + 3) / 4 + 64);
 }
 // packed input of a 4-letter alphabet cannot hold a letter >= alphabet_len
 inline bool codes_need_check(const bsq_params& prm) { return !((prm.flags & BSQ_F_CODES_2BIT) && prm.alphabet_len >= 4); }
@@ -1259,6 +1295,7 @@ int stage_inputs(bsq_ctx* ctx, BufSet& B, Plan& P, const uint8_t* codes, int64_t
   {
     const int rcu = upload_codes(ctx, B, P.prm, codes, 0, codes_in_bytes(P.prm, ncodes), st);
     if (rcu != BSQ_SUCCESS) return rcu;
+    P.codes2_ok = (P.prm.flags & BSQ_F_CODES_2BIT) || want_packed_copy(P.prm);
   }
   ctx->tm.h2d_bytes += codes_in_bytes(P.prm, ncodes);
   {
@@ -1405,6 +1442,7 @@ int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, cudaStream_t
   T.txlen = B.txlen.as<int>();
   T.slots = B.slots.as<char>();
   T.bad = B.flags.as<int>();
+  T.codes2 = (P.codes2_ok && B.codes2.p) ? B.codes2.as<uint32_t>() : nullptr;
   // long pairs: one warp per pair walking shared-memory tiles; short pairs: one
   // thread per pair (there are enough of them to hide the load latency)
   const long long avg_path = P.slot_bytes / std::max<long long>((long long)P.E, 1);
@@ -1422,9 +1460,10 @@ int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, cudaStream_t
   } else if (ch.family == 2 && (force == 'p' || (warp_walk && !force && ch.count >= (int64_t)ctx->sms * 32))) {
     // big batches of long banded pairs: a thread per pair, straight out of global memory
     const int grid = (int)((ch.count + 127) / 128);
-    if (P.gosign < 0) BSQ_LAUNCH((bsq_k2_walk_thread<-1>), grid, 128, 0, stream, T);
-    else if (P.gosign == 0) BSQ_LAUNCH((bsq_k2_walk_thread<0>), grid, 128, 0, stream, T);
-    else BSQ_LAUNCH((bsq_k2_walk_thread<1>), grid, 128, 0, stream, T);
+#define BSQ_WALKT(GS) { if (T.codes2) BSQ_LAUNCH((bsq_k2_walk_thread<GS, true>), grid, 128, 0, stream, T); \
+                        else BSQ_LAUNCH((bsq_k2_walk_thread<GS, false>), grid, 128, 0, stream, T); }
+    if (P.gosign < 0) BSQ_WALKT(-1) else if (P.gosign == 0) BSQ_WALKT(0) else BSQ_WALKT(1)
+#undef BSQ_WALKT
   } else if (warp_walk) {
     // lanes per pair: 8 when there are enough pairs to fill the GPU four times over, else a warp
     const bool narrow = (ch.count >= (int64_t)ctx->sms * 16 * 4 || force == 'n') && force != 'w';
@@ -1941,6 +1980,7 @@ static int align_batch_once(bsq_ctx* ctx, const bsq_params* params, int64_t npai
                  budget / BSQ_ARENA_SLOTS, false, overlap_chunks(ctx, npairs, o_len, m_len), off_base);
   if (rc != BSQ_SUCCESS) { cudaStreamSynchronize(sx); return rc; }
   ctx->tm.plan_ms = now_ms() - t_plan;
+  P.codes2_ok = (params->flags & BSQ_F_CODES_2BIT) || want_packed_copy(*params);   // what enqueue_slices uploads
   if (ctx->hooks.plan_debug)
     fprintf(stderr, "[bsq] plan: memgetinfo %.3f ms, make_plan %.3f ms, h2d enqueue before plan %.3f ms\n",
             t_p2 - t_p1, now_ms() - t_p2, t_plan - t_call);

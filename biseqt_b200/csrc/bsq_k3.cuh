@@ -467,3 +467,274 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3_fill(const BsqFillArgs 
   }
 }
 
+
+// ===========================================================================
+// K3L: the strip pipeline tuned for LATENCY -- one (or a few) pairs, where the fill time is the
+// length of the dependency chain and not the cell count (config 5: one 1 Mb x 1 Mb pair; config 1:
+// one 1 kb x 1 kb STD GLOBAL pair, planned as a full-width band).  With strips of BW columns, rows
+// of lag R per lane and a boundary hand-over every B rows, strip j+1 starts
+//     (BW + B) / R + 31  steps
+// after strip j, and the whole fill takes m / BW of those lags.  bsq_k3_fill pays 71 "careful"
+// (gated, branchy) steps of ~1360 cycles per strip of 128 columns on config 5 -- 49 us per strip,
+// 366 ms in all, 33 warps busy.  Here: 64-column strips (K = 2), one row per step, hand-over every
+// 8 rows, and ONE uniform branch-free step (every cell gated by a precomputed step range, so there
+// are no phases and nothing diverges): ~100 steps of ~100 cycles per strip, twice the strips in
+// flight.  Origin letters are loaded by lane 0 only and travel down the lanes with the skew, one
+// step ahead of the row they belong to, so the score lookup never sits on the dependency chain.
+// Same pointer layout ([strip][t][lane], one byte = two nibbles) and slab protocol as bsq_k3_fill
+// with K = 2, so bsq_k3_walk<2> serves both.
+//   replaces: dptable_solve's fill loop pw.c:59-110 over _xlim/_ylim
+//   (_pw_internals.c:116-153) + _banded_find_optimal (:364-414)
+// ===========================================================================
+#define BSQ_K3L_BATCH 8
+
+template <class S, int BT, int GOS>
+__global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3l_fill(const BsqFillArgs A) {
+  typedef typename S::T T;
+  typedef uint8_t PU;
+  typedef BsqK3Slab<S> Slab;
+  constexpr int K = 2, G = 32, BW = G * K, NBT = BSQ_K3L_BATCH;
+  constexpr int NB = (BT == BSQ_B_LOCAL) ? K : 1;
+  BSQ_BAIL_IF_BAD(A);
+  __shared__ T s_sub[BSQ_MAX_L * BSQ_MAX_L];
+  __shared__ T s_inH[BSQ_K3_THREADS / 32][NBT];
+  __shared__ int s_inG[BSQ_K3_THREADS / 32][NBT];
+  const int L = A.L;
+  for (int i = threadIdx.x; i < L * L; i += blockDim.x) s_sub[i] = ((const T*)A.subst)[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const unsigned FULL = 0xffffffffu;
+  const T NINF = S::ninf();
+  const T ZERO = (T)0;
+  const T go = S::go(A), ge = S::ge(A);
+  unsigned long long* slab_all = (unsigned long long*)A.col_h;
+  int p = 0;
+
+  for (;;) {
+    int g = 0;
+    if (lane == 0) g = atomicAdd(A.counter, 1);
+    g = __shfl_sync(FULL, g, 0);
+    if (g >= A.k3_total) break;
+    while (g >= A.k3[p].strip_base + A.k3[p].nstrips) p++;  // claims only grow
+    const BsqPair P = A.pairs[p];
+    const BsqK3Pair Q = A.k3[p];
+    const int j = g - Q.strip_base;
+    const int n = P.n, m = P.m, dmin = P.dmin, dmax = P.dmax;
+    const int Y = j * BW;
+    const int ylast = (Y + BW - 1 < m) ? (Y + BW - 1) : m;
+    int x_lo = Y + dmin;
+    x_lo = x_lo < 0 ? 0 : x_lo;
+    int x_hi = ylast + dmax;
+    x_hi = x_hi > n ? n : x_hi;
+    const bool has_succ = (j + 1 < Q.nstrips);
+    int pred_hi = -1;                // rows the predecessor strip wrote to the slab: [pred_lo, pred_hi]
+    if (j > 0) { pred_hi = Y - 1 + dmax; pred_hi = pred_hi > n ? n : pred_hi; }
+    int pred_lo = Y - BW + dmin;
+    pred_lo = pred_lo < 0 ? 0 : pred_lo;
+    unsigned long long* slab = slab_all + Q.slab_off * Slab::EPR;
+    const unsigned tag_in = (unsigned)j, tag_out = (unsigned)j + 1u;
+
+    T bs = NINF;                     // lane's best end-cell candidate of this strip
+    int bk1 = BSQ_INT_MAX, bk2 = BSQ_INT_MAX;
+
+    if (x_lo <= x_hi) {
+      const int y0 = Y + lane * K;
+      int mlet[K];
+      int ta[K];                     // column k is inside band, table and strip rows for steps ta .. ta + span
+      unsigned span[K];
+      int xlast[K];                  // its last such row (or -1)
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const int y = y0 + k;
+        mlet[k] = (y >= 1 && y <= m) ? (int)A.codes[P.m_off + y - 1] : 0;
+        int xa = y + dmin, xb = y + dmax;
+        xa = xa < x_lo ? x_lo : xa;
+        xb = xb > x_hi ? x_hi : xb;
+        const bool any = (y <= m) && (xa <= xb);
+        ta[k] = any ? (xa - x_lo + lane) : 0x40000000;
+        span[k] = any ? (unsigned)(xb - xa) : 0u;
+        xlast[k] = any ? xb : -1;
+      }
+      const int km = m - y0;         // which of my columns is column m (if in [0,K))
+      T Hup[K], Hend[K];
+      int gD[K];
+      T best[NB];
+      int bestx[NB];
+#pragma unroll
+      for (int k = 0; k < K; k++) { Hup[k] = NINF; Hend[k] = NINF; gD[k] = 0; }
+#pragma unroll
+      for (int k = 0; k < NB; k++) { best[k] = NINF; bestx[k] = 0; }
+      T lastH = NINF;                // my right column's cell of the previous step
+      int mypay = 0;                 // its open/extend flag word | (letter of my NEXT row) << 8: what my right
+                                     // neighbour receives one step later is the letter of the row after that
+      T prev_in = NINF;
+      if (lane == 0 && j > 0) {      // (x_lo - 1, Y - 1): the diagonal neighbour of my first cell
+        const int xd = x_lo - 1;
+        if (xd >= pred_lo && xd <= pred_hi) {
+          unsigned ns = 32;
+          int f;
+          while (!Slab::decode(Slab::load(slab + (long long)xd * Slab::EPR), tag_in, prev_in, f)) { BSQ_BACKOFF(ns); if (ns < 256) ns *= 2; }
+        }
+      }
+      const int nsteps = (x_hi - x_lo + 1) + G - 1;
+      PU* prow = (PU*)(A.ptr + P.ptr_off) + (long long)j * P.s0 * G + lane;
+      const uint8_t* oseq = A.codes + P.o_off;
+      auto letter = [&](int xr) -> int { return (xr >= 1 && xr <= n) ? (int)oseq[xr - 1] : 0; };
+      // lane 0's letter pipeline: curlet = letter of its row at step t, l1 / l2 those of steps t+1, t+2
+      int curlet = (lane == 0) ? letter(x_lo) : 0;
+      if (lane == 0) mypay = curlet << 8;     // lane 1 starts one step later on the same row
+      int l1 = letter(x_lo + 1), l2 = letter(x_lo + 2);
+      T sig[K];
+#pragma unroll
+      for (int k = 0; k < K; k++) sig[k] = s_sub[curlet * L + mlet[k]];
+      typename Slab::Raw nx = {};    // prefetched (raw) boundary entry of row x_lo + (next batch) + lane
+      bool nx_have = false;
+
+      for (int t = 0; t < nsteps; t++) {
+        if ((t & (NBT - 1)) == 0 && j > 0) {
+          // boundary values of rows x_lo + t .. x_lo + t + NBT - 1 (lane i < NBT: row xr), fetched one
+          // batch ahead; rows past pred_hi lie outside the band
+          const int xr = x_lo + t + lane;
+          const bool mine = lane < NBT;
+          const bool need = mine && (xr <= pred_hi);
+          T bH = NINF;
+          int bF = 0;
+          bool ok = !need || (nx_have && Slab::decode(nx, tag_in, bH, bF));
+          unsigned ns = 32;
+          while (!__all_sync(FULL, ok)) {
+            if (!ok) {
+              ok = Slab::decode(Slab::load(slab + (long long)xr * Slab::EPR), tag_in, bH, bF);
+              if (!ok) { BSQ_BACKOFF(ns); if (ns < 256) ns *= 2; }
+            }
+          }
+          if (mine) {
+            s_inH[wib][lane] = need ? bH : NINF;
+            s_inG[wib][lane] = need ? S::flag(bF == 0) : 0;
+          }
+          __syncwarp();
+          const int xn = xr + NBT;
+          nx_have = mine && (xn <= pred_hi);
+          if (nx_have) nx = Slab::load(slab + (long long)xn * Slab::EPR);
+        }
+        T inH = __shfl_up_sync(FULL, lastH, 1);
+        const int pay = __shfl_up_sync(FULL, mypay, 1);
+        int inG = pay & ~0xFF00;
+        int nlet = (pay >> 8) & 0xFF;          // the letter of my NEXT row (sent one step ahead, see mypay)
+        if (lane == 0) {
+          inH = NINF;
+          inG = 0;
+          if (j > 0) { inH = s_inH[wib][t & (NBT - 1)]; inG = s_inG[wib][t & (NBT - 1)]; }
+          nlet = l1;
+        }
+        const int l3 = letter(x_lo + t + 3);   // lane 0's row three steps on (the other lanes load the same byte)
+        T sign[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) sign[k] = s_sub[nlet * L + mlet[k]];
+
+        const int x = x_lo + t - lane;
+        // B (_alnchoice_B, _pw_internals.c:182-197): B_LOCAL anywhere, B_OVERLAP on x==0 or y==0,
+        // B_GLOBAL at (0,0) only
+        const bool rowb = (BT == BSQ_B_LOCAL) || (BT == BSQ_B_OVERLAP && x == 0);
+        const T brest = rowb ? ZERO : NINF;
+        const T bfirst = (rowb || (y0 == 0 && (BT == BSQ_B_OVERLAP || x == 0))) ? ZERO : NINF;
+        T left = inH, diag = prev_in;
+        int gI = inG;
+        uint32_t cw = 0u;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          const bool inb = (unsigned)(t - ta[k]) <= span[k];
+          const T up = Hup[k];
+          T H;
+          int fD, fI;
+          uint32_t nib;
+          if (k == 0 || BT != BSQ_B_GLOBAL)
+            bsq_k3_cell<S, GOS, true>(up, gD[k], left, gI, diag, sig[k], k == 0 ? bfirst : brest, go, ge, inb, H, fD, fI, nib);
+          else
+            bsq_k3_cell<S, GOS, false>(up, gD[k], left, gI, diag, sig[k], ZERO, go, ge, inb, H, fD, fI, nib);
+          cw |= nib << (4 * k);
+          gD[k] = fD; gI = fI; diag = up; left = H; Hup[k] = H;
+          Hend[k] = inb ? H : Hend[k];
+          if (BT == BSQ_B_LOCAL) { if (H > best[k < NB ? k : 0]) { best[k < NB ? k : 0] = H; bestx[k < NB ? k : 0] = x; } }
+        }
+        const bool active = (t >= lane) && (x <= x_hi);
+        if (active) {
+          prow[(long long)t * G] = (PU)cw;
+          if (lane == G - 1 && has_succ) Slab::put(slab + (long long)x * Slab::EPR, left, gI != 0, tag_out);
+          if (BT == BSQ_B_OVERLAP && x < n && km >= 0 && km < K) {   // column m above the last row (:380-390)
+            T c = NINF;
+#pragma unroll
+            for (int k = 0; k < K; k++) if (k == km) c = Hup[k];
+            if (c > NINF && bsq_better<T>(c, x - m, 0, bs, bk1, bk2)) { bs = c; bk1 = x - m; bk2 = 0; }
+          }
+        }
+        lastH = left;
+        mypay = gI | (nlet << 8);
+        prev_in = inH;
+        curlet = nlet;
+        l1 = l2;
+        l2 = l3;
+#pragma unroll
+        for (int k = 0; k < K; k++) sig[k] = sign[k];
+      }
+      // end cell, _banded_find_optimal (_pw_internals.c:364-414)
+      if (BT == BSQ_B_GLOBAL) {
+#pragma unroll
+        for (int k = 0; k < K; k++) if (k == km && xlast[k] == n) { bs = Hend[k]; bk1 = n - m; bk2 = n; }
+      } else if (BT == BSQ_B_OVERLAP) {   // last cell of every diagonal, diagonals ascending, strict >
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          const T c = Hend[k];
+          if (xlast[k] == n && c > NINF && bsq_better<T>(c, n - (y0 + k), 0, bs, bk1, bk2)) { bs = c; bk1 = n - (y0 + k); bk2 = 0; }
+        }
+      } else {                            // every cell, (d, a) ascending; per column d ascends with x
+#pragma unroll
+        for (int k = 0; k < NB; k++) {
+          const T c = best[k];
+          const int d = bestx[k] - (y0 + k);
+          if (c > NINF && bsq_better<T>(c, d, bestx[k], bs, bk1, bk2)) { bs = c; bk1 = d; bk2 = bestx[k]; }
+        }
+      }
+    }
+
+    bsq_group_best<T, 32>(FULL, bs, bk1, bk2);
+    int last = 0;
+    if (lane == 0) {
+      BsqK3Res r;
+      r.score = S::to_f64(bs);
+      r.k1 = bk1;
+      r.k2 = bk2;
+#ifdef BSQ_K3_PROFILE
+      r.t_claim = r.t_ready = r.t_end = 0; r.wait_clk = 0; r.polls = 0; r.sm = 0;
+#endif
+      A.k3_res[g] = r;
+      __threadfence();
+      last = (atomicAdd(A.k3_done + p, 1) == Q.nstrips - 1);
+    }
+    last = __shfl_sync(FULL, last, 0);
+    if (last) {  // this warp finished the pair's last open strip: pick the end cell
+      __threadfence();
+      double fs = ScF64::ninf();
+      int f1 = BSQ_INT_MAX, f2 = BSQ_INT_MAX;
+      for (int i = lane; i < Q.nstrips; i += 32) {
+        const BsqK3Res* rp = A.k3_res + Q.strip_base + i;
+        const double sc = BSQ_LD_CG(&rp->score);
+        const int k1 = BSQ_LD_CG(&rp->k1), k2 = BSQ_LD_CG(&rp->k2);
+        if (k1 != BSQ_INT_MAX && (f1 == BSQ_INT_MAX || bsq_better<double>(sc, k1, k2, fs, f1, f2))) { fs = sc; f1 = k1; f2 = k2; }
+      }
+      bsq_group_best<double, 32>(FULL, fs, f1, f2);
+      if (lane == 0) {
+        int ex = -1, ey = -1, st = BSQ_OK;
+        if (f1 == BSQ_INT_MAX) { st = BSQ_NO_ALIGNMENT; fs = 0.0; }
+        else if (BT == BSQ_B_LOCAL) { ex = f2; ey = f2 - f1; }
+        else if (BT == BSQ_B_GLOBAL) { ex = n; ey = m; }
+        else { ex = n < m + f1 ? n : m + f1; ey = ex - f1; }
+        const int oi = P.pad;
+        A.out_score[oi] = fs;
+        A.out_ex[oi] = ex;
+        A.out_ey[oi] = ey;
+        A.out_status[oi] = st;
+      }
+    }
+  }
+}

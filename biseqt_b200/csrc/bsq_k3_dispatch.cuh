@@ -21,10 +21,22 @@ static int bsq_k3_variant(int btype, int gos, int grid, cudaStream_t st, const B
   return -1;
 }
 
+// cfg 0: the latency form (bsq_k3l_fill: 64-column strips, one row per step, uniform gated step)
+template <class S>
+static int bsq_k3l_variant(int btype, int gos, int grid, cudaStream_t st, const BsqFillArgs* A) {
+#define BSQ_K3L_CASE(BT, GS) \
+  if (btype == BT && gos == GS) { BSQ_LAUNCH((bsq_k3l_fill<S, BT, GS>), grid, BSQ_K3_THREADS, 0, st, *A); (void)st; return 0; }
+  BSQ_K3L_CASE(0, -1) BSQ_K3L_CASE(0, 0) BSQ_K3L_CASE(0, 1)
+  BSQ_K3L_CASE(1, -1) BSQ_K3L_CASE(1, 0) BSQ_K3L_CASE(1, 1)
+  BSQ_K3L_CASE(2, -1) BSQ_K3L_CASE(2, 0) BSQ_K3L_CASE(2, 1)
+#undef BSQ_K3L_CASE
+  return -1;
+}
+
 template <class S>
 static int bsq_k3_op_t(int cfg, int btype, int gos, int grid, cudaStream_t st, const BsqFillArgs* A) {
   switch (cfg) {
-    case 0: return bsq_k3_variant<S, 2, BSQ_K3_R0>(btype, gos, grid, st, A);
+    case 0: return bsq_k3l_variant<S>(btype, gos, grid, st, A);
     case 1: return bsq_k3_variant<S, 4, BSQ_K3_R1>(btype, gos, grid, st, A);
     case 2: return bsq_k3_variant<S, 8, BSQ_K3_R2>(btype, gos, grid, st, A);
   }

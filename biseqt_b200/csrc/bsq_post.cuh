@@ -348,9 +348,17 @@ __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTrac
 // four ops per 32-bit store.  ~8x fewer issued instructions and ~2x fewer DRAM bytes.
 //   table layout (bsq_k2_fill): [s - s0][lane][word], C/2 nibbles per lane and step
 // ---------------------------------------------------------------------------
-#define BSQ_WALKT_PF 24       // rows ahead that are prefetched (both parities of s)
+#define BSQ_WALKT_Q 4          // pointer words in flight along the current diagonal
 
-template <int GOS>
+// PACKED2: the M / S decision reads the letters out of two cached 32-bit words of the 2-bit packed
+// copy of codes[] (one load per 16 letters and sequence) instead of two byte loads per op.
+// Every memory instruction of this kernel is uncoalesced (32 pairs per warp), i.e. costs the
+// load/store unit ~32 cycles: the first version (two byte loads and two L2 prefetches per op)
+// was bound by exactly that (13.7 ms for config 3's 32768 pairs; profiles/r02_walk_thread.txt).
+// Now an op costs ONE pointer load: the words of the next BSQ_WALKT_Q cells down the current
+// diagonal are kept in flight (a run of diagonal moves -- 85-95 % of a path -- never waits for
+// DRAM), a gap move flushes that queue.
+template <int GOS, bool PACKED2>
 __global__ void __launch_bounds__(128) bsq_k2_walk_thread(const BsqTraceArgs A) {
   BSQ_BAIL_IF_BAD(A);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -364,7 +372,7 @@ __global__ void __launch_bounds__(128) bsq_k2_walk_thread(const BsqTraceArgs A) 
   const int di = (x - y) - P.dmin;
   int l = di / C, c = di - l * C;
   long long row = (long long)(x + y) - P.s0;
-  const uint32_t* pw = A.ptr + P.ptr_off + row * RB + l * WPS;   // my lane's first word of the current row
+  const uint32_t* pw = A.ptr + P.ptr_off + row * RB + l * WPS + ((c >> 1) >> 3);   // the word holding my nibble
   const uint8_t* oseq = A.codes + P.o_off;
   const uint8_t* mseq = A.codes + P.m_off;
   char* wr_end = A.slots + P.tx_slot + (long long)P.n + P.m;      // one past the slot end
@@ -372,15 +380,29 @@ __global__ void __launch_bounds__(128) bsq_k2_walk_thread(const BsqTraceArgs A) 
   uint32_t arrive = BSQ_MM;     // how we got here: M (or the end cell) -> lowest bit
   uint32_t acc = 0u;            // the last `filled` ops, latest in the low byte
   int filled = 0;
+  // q[i] = pointer word of the cell i diagonal moves further on (rows row - 2 i), if that row exists
+  uint32_t q[BSQ_WALKT_Q];
+#pragma unroll
+  for (int i = 0; i < BSQ_WALKT_Q; i++) q[i] = (row - 2 * i >= 0) ? pw[-(long long)(2 * i) * RB] : 0u;
+  uint32_t ow = 0u, mw = 0u;    // cached words of the packed letters
+  long long owi = -1, mwi = -1;
   for (;;) {
     const int hc = c >> 1;
-    const uint32_t mk = (pw[hc >> 3] >> (4 * (hc & 7))) & 0xFu;
+    const uint32_t mk = (q[0] >> (4 * (hc & 7))) & 0xFu;
     const uint32_t op = (arrive == BSQ_MM) ? bsq_lowest(mk) : bsq_gap_base_t<GOS>(mk, arrive);
     if (op == BSQ_MB || op == 0u || len >= maxlen) break;
     const bool isM = (op == BSQ_MM), isD = (op == BSQ_MD), isI = !(isM || isD);
     const int xi = x > 0 ? x - 1 : 0, yi = y > 0 ? y - 1 : 0;       // only meaningful for a diagonal move
-    const char ms = (oseq[xi] == mseq[yi]) ? 'M' : 'S';
-    const uint32_t ch = (uint32_t)(unsigned char)(isM ? ms : (isD ? 'D' : 'I'));
+    bool same;
+    if (PACKED2) {
+      const long long go_ = P.o_off + xi, gm_ = P.m_off + yi;
+      if ((go_ >> 4) != owi) { owi = go_ >> 4; ow = A.codes2[owi]; }
+      if ((gm_ >> 4) != mwi) { mwi = gm_ >> 4; mw = A.codes2[mwi]; }
+      same = (((ow >> (2 * (int)(go_ & 15))) ^ (mw >> (2 * (int)(gm_ & 15)))) & 3u) == 0u;
+    } else {
+      same = oseq[xi] == mseq[yi];
+    }
+    const uint32_t ch = (uint32_t)(unsigned char)(isM ? (same ? 'M' : 'S') : (isD ? 'D' : 'I'));
     acc = (acc << 8) | ch;
     len++;
     filled++;
@@ -397,17 +419,22 @@ __global__ void __launch_bounds__(128) bsq_k2_walk_thread(const BsqTraceArgs A) 
     y -= isD ? 0 : 1;
     const int dr = isM ? 2 : 1;                  // s = x + y drops by 2 on a diagonal move
     row -= dr;
-    pw -= dr * RB;
-    c += isI ? 1 : (isD ? -1 : 0);               // local diagonal moves with x - y
-    if (c < 0) { c = C - 1; l--; pw -= WPS; }
-    if (c == C) { c = 0; l++; pw += WPS; }
-#ifndef BSQ_SIMT_EMU
-    if (row > BSQ_WALKT_PF) {
-      const uint32_t* pf = pw - BSQ_WALKT_PF * RB + (hc >> 3);
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(pf - RB));
+    pw -= (long long)dr * RB;
+    if (!isM) {                                  // the local diagonal moves with x - y
+      const int w0 = (c >> 1) >> 3;              // word of my nibble inside the lane's row
+      c += isI ? 1 : -1;
+      if (c < 0) { c = C - 1; l--; pw -= WPS; }
+      if (c == C) { c = 0; l++; pw += WPS; }
+      pw += ((c >> 1) >> 3) - w0;
     }
-#endif
+    if (isM) {      // the queue moves up one cell; one new word enters at its end
+#pragma unroll
+      for (int i = 0; i + 1 < BSQ_WALKT_Q; i++) q[i] = q[i + 1];
+      q[BSQ_WALKT_Q - 1] = (row - 2 * (BSQ_WALKT_Q - 1) >= 0) ? pw[-(long long)(2 * (BSQ_WALKT_Q - 1)) * RB] : 0u;
+    } else {        // another diagonal (and the other parity of s): reload
+#pragma unroll
+      for (int i = 0; i < BSQ_WALKT_Q; i++) q[i] = (row - 2 * i >= 0) ? pw[-(long long)(2 * i) * RB] : 0u;
+    }
   }
   if (filled > 0) {
     char* a = wr_end - len;
@@ -420,25 +447,59 @@ __global__ void __launch_bounds__(128) bsq_k2_walk_thread(const BsqTraceArgs A) 
 }
 
 // ---------------------------------------------------------------------------
-// K3 traceback (pw.c:116-151): one warp per pair walks the [strip][t][lane]
-// table out of shared-memory tiles (the rows at and below the current step of
-// the current strip), like bsq_k4_walk.
+// K3 traceback (pw.c:116-151): one warp per pair walks the [strip][t][lane] table.
+//
+// A path is mostly runs of diagonal moves, so the warp examines 32 cells of the current diagonal
+// AT ONCE: lane q looks up the tied-max nibble of (x-q, y-q), a ballot finds how far the run of
+// "arrived by M, leaves by M" goes, those lanes emit their M / S in one coalesced store, and only
+// the op that ends the run (a gap, or B) is handled serially.  Config 5 (10^6 ops, ~2 10^4 gap
+// runs) takes ~5 10^4 rounds instead of 10^6 dependent steps.
+//
+// The pointer rows come through two shared-memory tiles filled by the bulk-copy engine
+// (cp.async.bulk + mbarrier, one elected lane issues): while one tile is walked, the steps below it
+// are already on their way, so the walk never waits for HBM inside a strip.
 // ---------------------------------------------------------------------------
 #define BSQ_K3_TILE_BYTES 8192
-#define BSQ_K3_LET_WIN 128
+#define BSQ_K3_LET_WIN 256
+
+#ifndef BSQ_SIMT_EMU
+__device__ __forceinline__ uint32_t bsq_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bsq_mbar_init(unsigned long long* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bsq_smem_addr(bar)));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// one lane: expect `bytes`, start the bulk copy global -> shared, completion counted on the barrier
+__device__ __forceinline__ void bsq_bulk_load(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bsq_smem_addr(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(bsq_smem_addr(dst)), "l"(src), "r"(bytes), "r"(bsq_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bsq_mbar_wait(unsigned long long* bar, uint32_t phase) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bsq_smem_addr(bar)), "r"(phase) : "memory");
+}
+#endif
 
 template <int K, int GOS>
 __global__ void __launch_bounds__(32) bsq_k3_walk(const BsqTraceArgs A) {
   typedef typename BsqK3Unit<K>::type PU;
   constexpr int G = 32, BW = G * K;
   constexpr int LOGK = (K == 2) ? 1 : (K == 4 ? 2 : 3);
-  constexpr int TSTEPS = BSQ_K3_TILE_BYTES / (G * (int)sizeof(PU));
-  constexpr int BATCH = 8;       // diagonal moves examined per round out of preloaded nibbles
+  constexpr int STEP_BYTES = G * (int)sizeof(PU);
+  constexpr int TSTEPS = BSQ_K3_TILE_BYTES / STEP_BYTES;
   BSQ_BAIL_IF_BAD(A);
-  __shared__ uint4 s_tile4[BSQ_K3_TILE_BYTES / 16];
+  alignas(128) __shared__ unsigned char s_tile[2][BSQ_K3_TILE_BYTES];
   __shared__ uint8_t s_let[2][BSQ_K3_LET_WIN];
-  PU* tile = (PU*)s_tile4;
+#ifndef BSQ_SIMT_EMU
+  alignas(8) __shared__ unsigned long long s_bar[2];
+#endif
   const int lane = threadIdx.x & 31;
+  const unsigned FULL = 0xffffffffu;
   const int p = blockIdx.x;
   if (p >= A.npairs) return;
   const BsqPair P = A.pairs[p];
@@ -447,6 +508,11 @@ __global__ void __launch_bounds__(32) bsq_k3_walk(const BsqTraceArgs A) {
     if (lane == 0) { A.txlen[oi] = 0; A.sx[oi] = -1; A.sy[oi] = -1; }
     return;
   }
+#ifndef BSQ_SIMT_EMU
+  if (lane == 0) { bsq_mbar_init(&s_bar[0]); bsq_mbar_init(&s_bar[1]); }
+  __syncwarp();
+  uint32_t phase[2] = {0u, 0u};
+#endif
   const int ex = A.ex[oi], ey = A.ey[oi];
   int x = ex, y = ey, len = 0;
   int j = y / BW;                // strip
@@ -454,74 +520,101 @@ __global__ void __launch_bounds__(32) bsq_k3_walk(const BsqTraceArgs A) {
   int xlo = j * BW + P.dmin;
   xlo = xlo < 0 ? 0 : xlo;
   const long long tstride = P.s0;
-  const PU* table = (const PU*)(A.ptr + P.ptr_off);
+  const unsigned char* table = (const unsigned char*)(A.ptr + P.ptr_off);
   const uint8_t* oseq = A.codes + P.o_off;
   const uint8_t* mseq = A.codes + P.m_off;
   char* wr = A.slots + P.tx_slot + (long long)P.n + P.m;
   const int maxlen = P.n + P.m;
-  int tlo = 1, thi = 0;          // staged steps [tlo, thi] of strip j (empty)
+  // tile `cur` holds steps [tlo, thi] of strip j (empty: tlo > thi); tile cur^1 may hold, or be
+  // receiving, steps [ntlo, nthi] of the same strip (nj == j)
+  int cur = 0, tlo = 1, thi = 0;
+  int nj = -1, ntlo = 1, nthi = 0;
   uint8_t* obuf = s_let[0];
   uint8_t* mbuf = s_let[1];
   int xb = x + 1, yb = y + 1;    // obuf holds o[xb .. xb+WIN), mbuf m[yb .. yb+WIN); empty
   uint32_t arrive = BSQ_MM;
+  // steps [lo, hi] of strip js -> tile b; asynchronous when the copy engine can take it
+  auto fetch = [&](int b, int js, int lo, int hi) {
+    const unsigned char* src = table + ((long long)js * tstride + lo) * STEP_BYTES;
+    const uint32_t bytes = (uint32_t)(hi - lo + 1) * STEP_BYTES;
+#ifndef BSQ_SIMT_EMU
+    if ((((unsigned long long)src) & 15ull) == 0ull) {
+      if (lane == 0) bsq_bulk_load(s_tile[b], src, bytes, &s_bar[b]);
+      return true;    // completion: wait on s_bar[b]
+    }
+#endif
+    for (uint32_t i = lane; i < bytes; i += 32) s_tile[b][i] = src[i];
+    __syncwarp();
+    return false;
+  };
+  bool npend = false;            // tile cur^1 is still in flight
   for (;;) {
     const int t = x - xlo + (c >> LOGK);
-    if (t < tlo || t > thi) {    // stage the steps at and below t
-      thi = t;
-      tlo = t - TSTEPS + 1;
-      tlo = tlo < 0 ? 0 : tlo;
-      const uint4* src = (const uint4*)(table + ((long long)j * tstride + tlo) * G);
-      const int n16 = (thi - tlo + 1) * G * (int)sizeof(PU) / 16;
+    if (t < tlo || t > thi) {    // the tile does not hold the current step
       __syncwarp();
-      for (int i = lane; i < n16; i += 32) s_tile4[i] = src[i];
+      if (nj == j && t >= ntlo && t <= nthi) {     // the prefetched one does
+        cur ^= 1;
+#ifndef BSQ_SIMT_EMU
+        if (npend) { bsq_mbar_wait(&s_bar[cur], phase[cur]); phase[cur] ^= 1u; }
+#endif
+        tlo = ntlo; thi = nthi;
+      } else {
+#ifndef BSQ_SIMT_EMU
+        if (npend) { bsq_mbar_wait(&s_bar[cur ^ 1], phase[cur ^ 1]); phase[cur ^ 1] ^= 1u; }   // drain before reuse
+#endif
+        thi = t;
+        tlo = t - TSTEPS + 1;
+        tlo = tlo < 0 ? 0 : tlo;
+        const bool pend = fetch(cur, j, tlo, thi);
+#ifndef BSQ_SIMT_EMU
+        if (pend) { bsq_mbar_wait(&s_bar[cur], phase[cur]); phase[cur] ^= 1u; }
+#else
+        (void)pend;
+#endif
+      }
+      npend = false;
+      nj = -1;
+      if (tlo > 0) {             // the walk goes on below: get those steps while this tile is walked
+        nj = j;
+        nthi = tlo - 1;
+        ntlo = nthi - TSTEPS + 1;
+        ntlo = ntlo < 0 ? 0 : ntlo;
+        npend = fetch(cur ^ 1, j, ntlo, nthi);
+      }
       __syncwarp();
     }
-    if (x - BATCH < xb && xb > 0) {  // the walk only moves towards smaller x and y
+    if (x - 32 < xb && xb > 0) {  // the walk only moves towards smaller x and y
       xb = x - BSQ_K3_LET_WIN; if (xb < 0) xb = 0;
       __syncwarp();
       for (int i = lane; i < BSQ_K3_LET_WIN; i += 32) if (xb + i < P.n) obuf[i] = oseq[xb + i];
       __syncwarp();
     }
-    if (y - BATCH < yb && yb > 0) {
+    if (y - 32 < yb && yb > 0) {
       yb = y - BSQ_K3_LET_WIN; if (yb < 0) yb = 0;
       __syncwarp();
       for (int i = lane; i < BSQ_K3_LET_WIN; i += 32) if (yb + i < P.m) mbuf[i] = mseq[yb + i];
       __syncwarp();
     }
-    // the q-th diagonal move from here visits (x-q, y-q): column c-q, step t-q-(lanes crossed).
-    // Those nibbles are loaded up front (independent loads), as far as strip and tile reach.
-    int jmax = c + 1;                                  // stay inside the strip
-    jmax = jmax > BATCH ? BATCH : jmax;
-    const int room = ((t - tlo) >> 1) + 1;             // a move lowers the step by at most 2
-    jmax = jmax > room ? room : jmax;
-    uint32_t nib[BATCH];
-#pragma unroll
-    for (int q = 0; q < BATCH; q++) {
-      nib[q] = 0u;
-      if (q < jmax) {
-        const int cq = c - q, lq = cq >> LOGK;
-        const int tq = x - q - xlo + lq;
-        nib[q] = ((uint32_t)tile[(tq - tlo) * G + lq] >> (4 * (cq & (K - 1)))) & 0xFu;
-      }
+    // lane q looks at (x-q, y-q): column c-q of this strip, step t-q-(lanes crossed)
+    const PU* tile = (const PU*)s_tile[cur];
+    const int cq = c - lane, lq = cq >> LOGK;
+    const int tq = x - lane - xlo + lq;
+    const bool valid = (cq >= 0) && (tq >= tlo) && (len + lane < maxlen);
+    uint32_t nib = 0u;
+    if (valid) nib = ((uint32_t)tile[(tq - tlo) * G + lq] >> (4 * (cq & (K - 1)))) & 0xFu;
+    const uint32_t opq = (lane == 0 && arrive != BSQ_MM) ? bsq_gap_base_t<GOS>(nib, arrive) : bsq_lowest(nib);
+    const unsigned vmask = __ballot_sync(FULL, valid);
+    const unsigned mmask = __ballot_sync(FULL, valid && opq == BSQ_MM);
+    const int nv = __popc(vmask);                       // valid cells form a prefix
+    int run = (~mmask == 0u) ? 32 : (__ffs((int)~mmask) - 1);
+    if (nv == 0) break;                                 // len == maxlen
+    if (lane < run) {
+      const char ch = (obuf[x - 1 - lane - xb] == mbuf[y - 1 - lane - yb]) ? 'M' : 'S';
+      wr[-(len + lane + 1)] = ch;
     }
-    int taken = 0;
-    uint32_t op = 0u;
-#pragma unroll
-    for (int q = 0; q < BATCH; q++) {
-      if (q < jmax && taken == q) {
-        const uint32_t mk = nib[q];
-        op = (q == 0 && arrive != BSQ_MM) ? bsq_gap_base_t<GOS>(mk, arrive) : bsq_lowest(mk);
-        if (op == BSQ_MM && len < maxlen) {
-          const char ch = (obuf[x - 1 - xb] == mbuf[y - 1 - yb]) ? 'M' : 'S';
-          x--; y--; len++;
-          if (lane == 0) wr[-len] = ch;
-          arrive = BSQ_MM;
-          taken = q + 1;
-        }
-      }
-    }
-    if (taken > 0) {
-      c -= taken;
+    if (run > 0) {
+      x -= run; y -= run; len += run; c -= run;
+      arrive = BSQ_MM;
       if (c < 0) {               // into the previous strip
         j--;
         c += BW;
@@ -529,10 +622,11 @@ __global__ void __launch_bounds__(32) bsq_k3_walk(const BsqTraceArgs A) {
         xlo = xlo < 0 ? 0 : xlo;
         tlo = 1; thi = 0;
       }
-      if (taken == jmax) continue;   // the run may go on
     }
-    // `op` is the op at the current cell and it is not a (possible) diagonal move
-    if (op == BSQ_MB || op == 0u || len >= maxlen || op == BSQ_MM) break;
+    if (run == nv) continue;     // the run reached the edge of what was staged (or of the strip)
+    // the cell that ended the run holds an op that is not a diagonal move
+    const uint32_t op = __shfl_sync(FULL, opq, run);
+    if (op == BSQ_MB || op == 0u || op == BSQ_MM || len >= maxlen) break;
     char ch;
     if (op == BSQ_MD) {
       ch = 'D'; x--;
@@ -550,6 +644,9 @@ __global__ void __launch_bounds__(32) bsq_k3_walk(const BsqTraceArgs A) {
     len++;
     if (lane == 0) wr[-len] = ch;
   }
+#ifndef BSQ_SIMT_EMU
+  if (npend) bsq_mbar_wait(&s_bar[cur ^ 1], phase[cur ^ 1]);   // nothing may still be landing in shared memory at exit
+#endif
   if (lane == 0) {
     A.txlen[oi] = len;
     A.sx[oi] = x;
@@ -598,6 +695,30 @@ __global__ void __launch_bounds__(256) bsq_unpack_2bit(const uint8_t* packed, lo
       out[4 * b + 2] = (uint8_t)((w >> 4) & 3u); out[4 * b + 3] = (uint8_t)(w >> 6);
     }
   }
+}
+
+// the reverse: letters [16 w, 16 w + 16) -> 32-bit word w of the 2-bit packed copy that the thread
+// walker reads (bsq_k2_walk_thread); `letters` bytes in all, words [w_lo, w_hi)
+__global__ void __launch_bounds__(256) bsq_pack_2bit(const uint8_t* codes, long long letters, long long w_lo, long long w_hi,
+                                                     uint32_t* out) {
+  const long long w = w_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= w_hi) return;
+  uint32_t acc = 0u;
+  if (16 * w + 16 <= letters && (((unsigned long long)codes) & 15ull) == 0ull) {
+    const uint4 v = *(const uint4*)(codes + 16 * w);
+    const uint32_t x4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t b = x4[k];
+      acc |= ((b & 3u) | ((b >> 6) & 0xCu) | ((b >> 12) & 0x30u) | ((b >> 18) & 0xC0u)) << (8 * k);
+    }
+  } else {
+    for (int k = 0; k < 16; k++) {
+      const long long q = 16 * w + k;
+      if (q < letters) acc |= ((uint32_t)codes[q] & 3u) << (2 * k);
+    }
+  }
+  out[w] = acc;
 }
 
 // BSQ_F_TX_2BIT: ops [16 w, 16 w + 16) of the packed byte transcripts -> 32-bit word w, for words

@@ -757,6 +757,43 @@ def run_multi(make_engine, make_multi, seed, npairs=60):
         eng.close()
 
 
+def run_std_as_band(make_engine, seed, sizes=((300, 280), (256, 700), (1000, 1040))):
+    """One to a few big STD GLOBAL pairs are planned as full-width B_GLOBAL bands and take the
+    strip pipeline (K3L) -- BASELINE.json configs[0]'s shape; same answer as the oracle's STD
+    GLOBAL and as K1 (BSQ_NO_STD_BAND), all score families and signs of go."""
+    rng = np.random.default_rng(seed)
+    eng = make_engine()
+    os.environ['BSQ_NO_STD_BAND'] = '1'
+    try:
+        eng_k1 = make_engine()
+    finally:
+        del os.environ['BSQ_NO_STD_BAND']
+    try:
+        for (n, m) in sizes:
+            for fam, gomode in ((1, -1), (2, 0), (1, 1), (2, -1)):
+                S, go, ge = score_family(rng, 4, fam, gomode)
+                probs = []
+                for i in range(1 + (n < 500)):
+                    o = rng.integers(0, 4, size=n).astype(np.uint8)
+                    t, _ = mutate(rng, o, 4, subst=0.1, go=0.05, ge=0.3)
+                    t = t[:m] if len(t) >= m else np.concatenate([t, rng.integers(0, 4, size=m - len(t)).astype(np.uint8)])
+                    probs.append(dict(origin=o, mutant=t, subst=S, go=go, ge=ge, mode=0, type=0, diag_range=None))
+                r = check_batch(eng, probs)
+                r1 = engine_batch(eng_k1, probs)
+                assert np.array_equal(r.score, r1.score) and r.transcripts() == r1.transcripts()
+        # two-phase form (what biseqt_b200.pw.Aligner issues) and a degenerate partner that keeps the batch on K1
+        pr = probs[0]
+        codes, o_off, o_len, m_off, m_len = batch.pack_pairs([(pr['origin'], pr['mutant'])])
+        sb = eng.solve(codes, o_off, o_len, m_off, m_len, 0, 0, pr['subst'], pr['go'], pr['ge'])
+        same_as(oracle_one(pr), sb.traceback(), 0, what='two-phase STD GLOBAL as band')
+        sb.release()
+        small = dict(pr, origin=pr['origin'][:40], mutant=pr['mutant'][:50])
+        check_batch(eng, [pr, small])
+    finally:
+        eng.close()
+        eng_k1.close()
+
+
 def run_lifetime(make_engine):
     """Batches that outlive their engine (an Engine closed, or collected, before its SolvedBatch /
     ResidentBatch): release and every other call on them must not touch the dead context."""

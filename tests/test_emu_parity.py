@@ -84,6 +84,10 @@ def test_emu_multi(emu_lib):
     pc.run_multi(lambda: batch.Engine(0, lib=emu_lib), lambda n: batch.MultiEngine([0] * n, lib=emu_lib), seed=121, npairs=17)
 
 
+def test_emu_std_as_band(emu_lib):
+    pc.run_std_as_band(lambda: batch.Engine(0, lib=emu_lib), seed=131, sizes=((300, 280), (256, 420)))
+
+
 def test_emu_lifetime(emu_lib):
     pc.run_lifetime(lambda: batch.Engine(0, lib=emu_lib))
 

@@ -95,6 +95,10 @@ def test_gpu_multi():
     pc.run_multi(lambda: batch.Engine(0), lambda n: batch.MultiEngine([k % ndev for k in range(n)]), seed=121, npairs=400)
 
 
+def test_gpu_std_as_band():
+    pc.run_std_as_band(lambda: batch.Engine(0), seed=131)
+
+
 def test_gpu_lifetime():
     pc.run_lifetime(lambda: batch.Engine(0))
 

@@ -383,6 +383,51 @@ def measure_e2e(eng, w, steps, warmup, compact):
     return out
 
 
+def sharded_batch_sweep(ndev, steps, npairs):
+    """SURVEY.md section 8(e)'s named sweep: ONE config-3 batch (long-read pairs, B_OVERLAP, radius 64)
+    handed to ONE process, which shards it over `ndev` GPUs (bsq_multi: contiguous ranges of equal
+    work, one host thread + context per GPU, results straight into slices of the caller's arrays;
+    no collective).  End to end from pinned host buffers, compact forms, wall clock around the call."""
+    from biseqt_b200 import batch
+    eng = batch.Engine(0)
+    w = bw.make_device(eng, 'c3_int', npairs, seed=11)
+    eng.close()
+    me = batch.MultiEngine(ndev)
+    try:
+        N = len(w['o_len'])
+        pin = {'codes': me.pinned_empty(0, np.uint8)}
+        packed = batch.pack_codes_2bit(w['codes'])
+        pin['codes'] = me.pinned_empty(len(packed), np.uint8)
+        pin['codes'][:] = packed
+        for k in ('o_len', 'm_len', 'dmin', 'dmax'):
+            pin[k] = me.pinned_empty(N, np.int32)
+            pin[k][:] = w[k]
+        outb = {'score': me.pinned_empty(N, np.float64), 'tx_off': me.pinned_empty(N + 1, np.int64),
+                'tx_len': me.pinned_empty(N, np.int32),
+                'tx_buf': me.pinned_empty(me.tx_capacity(w['o_len'], w['m_len'], tx_2bit=True), np.uint8)}
+        for k in ('end_x', 'end_y', 'start_x', 'start_y', 'status'):
+            outb[k] = me.pinned_empty(N, np.int32)
+        call = lambda: me.align(pin['codes'], None, pin['o_len'], None, pin['m_len'], w['mode'], w['type'], w['subst'],   # noqa: E731
+                                w['go'], w['ge'], dmin=pin['dmin'], dmax=pin['dmax'], out=outb, codes_2bit=True,
+                                ncodes=len(w['codes']), tx_2bit=True)
+        for _ in range(2):
+            r = call()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            r = call()
+        dt = (time.perf_counter() - t0) / steps
+        sh = me.shards()
+        cells = sum(t['cells'] for _, _, _, t in sh)
+        return {'workload': w['desc'], 'n_gpus': ndev, 'gcups_e2e': cells / dt / 1e9, 'ms_per_call': 1e3 * dt,
+                'pairs_per_s': N / dt, 'status_ok_fraction': float((r.status == 0).mean()),
+                'shards': [{'device': d, 'pairs': int(c), 'device_span_ms': t['total_ms'], 'fill_ms': t['fill_ms'],
+                            'h2d_bytes': int(t['h2d_bytes']), 'd2h_bytes': int(t['d2h_bytes'])} for _, c, d, t in sh],
+                'note': 'one process, one batch, bsq_multi_align_batch; wall clock around the call, pinned host '
+                        'buffers, 2-bit sequences in / 2-bit transcripts out'}
+    finally:
+        me.close()
+
+
 _dist = None
 
 
@@ -593,9 +638,17 @@ def main():
                 line['cpu_baseline']['reference_flags_build'] = {k: cg[k] for k in ('value', 'unit', 'cores', 'sample', 'pairs_per_s')}
         except Exception as e:
             line['cpu_baseline'] = {'error': str(e)}
+    eng.close()
+    if _dist is not None:
+        _dist.barrier()        # every rank has given its GPU memory back
+    if rank == 0 and not args.no_extras:
+        try:    # the one-batch-over-N-GPUs engine (section 8(e)); the other ranks wait at the barrier below
+            line['sharded_batch'] = sharded_batch_sweep(world, max(2, args.steps // 4),
+                                                        min(WORKLOAD_PAIRS['c3_int'], args.pairs or 10 ** 9))
+        except Exception as e:
+            line['sharded_batch'] = {'error': str(e)}
     if rank == 0:
         emit(line)
-    eng.close()
     if _dist is not None:
         _dist.barrier()
         _dist.destroy_process_group()

@@ -214,11 +214,12 @@ class Engine(object):
                 _ptr(start_x, 'int32_t*'), _ptr(start_y, 'int32_t*'), _ptr(status, 'int32_t*'),
                 _ptr(tx_off, 'int64_t*'), _ptr(tx_buf, 'char*'), cap, total)
         rc = call()
-        full = worst_case() // 4 + 64 if tx_2bit else worst_case()
-        if rc == ERR_CAPACITY and transcripts and cap < full:   # caller's buffer too small: use our own
-            cap = full
-            tx_buf = np.empty(max(cap, 1), dtype=np.uint8)
-            rc = call()
+        if rc == ERR_CAPACITY and transcripts:   # caller's buffer too small: use our own
+            full = worst_case() // 4 + 64 if tx_2bit else worst_case()   # (summing a million lengths costs 1 ms)
+            if cap < full:
+                cap = full
+                tx_buf = np.empty(max(cap, 1), dtype=np.uint8)
+                rc = call()
         if rc != 0:
             raise BsqError('bsq_align_batch failed (%d): %s' % (rc, self._err()))
         return BatchResult(score[:N], end_x[:N], end_y[:N], start_x[:N], start_y[:N],

@@ -30,6 +30,16 @@
 
 #define BSQ_MAX_L 32  // largest alphabet the kernels stage in shared memory
 
+// K2 pointer layout: [block of T steps][lane][32-byte unit].  A lane's nibbles of T consecutive
+// anti-diagonals (WPS = ceil(C/16) words per step, T = 8 / WPS steps) fill ONE 32-byte sector,
+// written with two 16-byte stores per block and read by the traceback as one sector per ~T/2 ops.
+// (One word per lane and step in step-major order -- the first layout -- made every op of every walk
+// a different DRAM sector: 14 ms of traceback behind a 24 ms fill on config 3, whether a thread or 8
+// lanes walked a pair.)  Nibble of cell hc at step i of the block: word i * WPS + hc / 8, bits 4 (hc % 8).
+#define BSQ_K2_UNIT_WORDS 8
+#define BSQ_K2_WPS(C) (((C) / 2 + 7) / 8)
+#define BSQ_K2_T(C) (BSQ_K2_UNIT_WORDS / BSQ_K2_WPS(C))
+
 // where B (start of alignment) is allowed: _alnchoice_B, _pw_internals.c:161-209
 enum { BSQ_B_ORIGIN = 0, BSQ_B_EDGE = 1, BSQ_B_ALL = 2 };
 // where an alignment may end: _std_find_optimal / _banded_find_optimal, :303-414

@@ -600,13 +600,13 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
         it.cells = count_cells(BSQ_BANDED_MODE, n, m, lo, hi);
       } else if (it.cfg >= 0) {
         it.lo = lo; it.hi = hi;
-        const int G = BSQ_K2_CFGS[it.cfg].G, C = BSQ_K2_CFGS[it.cfg].C, WPS = (C / 2 + 7) / 8;
+        const int G = BSQ_K2_CFGS[it.cfg].G, C = BSQ_K2_CFGS[it.cfg].C, TB = BSQ_K2_T(C);
         const int smin = (lo <= 0 && hi >= 0) ? 0 : std::min(std::abs(lo), std::abs(hi));
         const int sbase = smin - ((smin - lo) & 1);
         const int dstar = std::max(lo, std::min(hi, dend));
         const int s_end = 2 * std::min(n, m + dstar) - dstar;
         const int64_t steps = (int64_t)(s_end - sbase + 1 + 1) / 2 * 2 + 2;
-        it.words = steps * G * WPS;
+        it.words = ((steps + TB - 1) / TB) * G * BSQ_K2_UNIT_WORDS;   // [block of TB steps][lane][32-byte unit]
         it.aux = sbase;
         it.cells = count_cells(BSQ_BANDED_MODE, n, m, lo, hi);
       }
@@ -1457,13 +1457,23 @@ int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, cudaStream_t
                         else BSQ_LAUNCH((bsq_k3_walk<KK, 1>), grid, 32, 0, stream, T); }
     if (T.K == 2) BSQ_WALK3(2) else if (T.K == 4) BSQ_WALK3(4) else BSQ_WALK3(8)
 #undef BSQ_WALK3
-  } else if (ch.family == 2 && (force == 'p' || (warp_walk && !force && ch.count >= (int64_t)ctx->sms * 32))) {
-    // big batches of long banded pairs: a thread per pair, straight out of global memory
+  } else if (ch.family == 2 && force == 'p') {
+    // banded tables, a thread per pair straight out of global memory (hook: kept for comparison)
     const int grid = (int)((ch.count + 127) / 128);
 #define BSQ_WALKT(GS) { if (T.codes2) BSQ_LAUNCH((bsq_k2_walk_thread<GS, true>), grid, 128, 0, stream, T); \
                         else BSQ_LAUNCH((bsq_k2_walk_thread<GS, false>), grid, 128, 0, stream, T); }
     if (P.gosign < 0) BSQ_WALKT(-1) else if (P.gosign == 0) BSQ_WALKT(0) else BSQ_WALKT(1)
 #undef BSQ_WALKT
+  } else if (ch.family == 2 && force != 't') {
+    // banded tables ([block of steps][lane][unit]): a warp per pair; 8 lanes per pair ('n' hook) measured
+    // slower at every batch size (config 3, 32768 pairs: 9.3 ms against 6.7 ms; config 4: 17 against 4 ms)
+    const bool narrow = (force == 'n');
+    const int ppb = BSQ_WALKC_WARPS * (narrow ? 4 : 1);  // pairs per block
+    const int grid = (int)((ch.count + ppb - 1) / ppb);
+#define BSQ_WALKC(GS) { if (narrow) BSQ_LAUNCH((bsq_k2_walk_coop<GS, 8>), grid, 32 * BSQ_WALKC_WARPS, 0, stream, T); \
+                        else BSQ_LAUNCH((bsq_k2_walk_coop<GS, 32>), grid, 32 * BSQ_WALKC_WARPS, 0, stream, T); }
+    if (P.gosign < 0) BSQ_WALKC(-1) else if (P.gosign == 0) BSQ_WALKC(0) else BSQ_WALKC(1)
+#undef BSQ_WALKC
   } else if (warp_walk) {
     // lanes per pair: 8 when there are enough pairs to fill the GPU four times over, else a warp
     const bool narrow = (ch.count >= (int64_t)ctx->sms * 16 * 4 || force == 'n') && force != 'w';
@@ -1471,8 +1481,7 @@ int launch_trace(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, cudaStream_t
     const int grid = (int)((ch.count + ppb - 1) / ppb);
 #define BSQ_WALK(F, GS) { if (narrow) BSQ_LAUNCH((bsq_k4_walk<F, GS, 8>), grid, 32 * BSQ_WALK_WARPS, 0, stream, T); \
                           else BSQ_LAUNCH((bsq_k4_walk<F, GS, 32>), grid, 32 * BSQ_WALK_WARPS, 0, stream, T); }
-    if (ch.family == 1) { if (P.gosign < 0) BSQ_WALK(1, -1) else if (P.gosign == 0) BSQ_WALK(1, 0) else BSQ_WALK(1, 1) }
-    else { if (P.gosign < 0) BSQ_WALK(2, -1) else if (P.gosign == 0) BSQ_WALK(2, 0) else BSQ_WALK(2, 1) }
+    if (P.gosign < 0) BSQ_WALK(1, -1) else if (P.gosign == 0) BSQ_WALK(1, 0) else BSQ_WALK(1, 1)
 #undef BSQ_WALK
   } else {
     // small blocks so they fit beside a resident fill kernel's register allocation

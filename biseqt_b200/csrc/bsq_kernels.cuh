@@ -23,6 +23,7 @@
 // real one, which removes every boundary branch from the inner loops.
 #pragma once
 #include "bsq_common.h"
+#include "bsq_launch.h"
 #include "../../include/bsqgpu.h"
 
 #define BSQ_INT_MAX 0x7fffffff
@@ -497,12 +498,11 @@ __device__ __forceinline__ void bsq_k2_step_careful(
     int btype, typename S::T (&H)[C], int (&fD)[C], int (&fI)[C], typename S::T (&best)[BLOCAL ? C : 1],
     int (&bests)[BLOCAL ? C : 1], typename S::T edgeH, int edgeF, const typename S::T* s_sub, int L,
     const uint8_t* oseq, const uint8_t* mseq, int n, int m, int s, int d0, int nreal,
-    typename S::T go, typename S::T ge, uint32_t* pout) {
+    typename S::T go, typename S::T ge, uint32_t (&cur)[(C / 2 + 7) / 8]) {
   typedef typename S::T T;
   constexpr int HC = C / 2;
   constexpr int WPS = (HC + 7) / 8;
   const T NINF = S::ninf();
-  uint32_t cur[WPS];
 #pragma unroll
   for (int w = 0; w < WPS; w++) cur[w] = 0u;
   // Q == 0: cells c = 0,2,..; c = 0 takes (x-1,y) from the lane below (edge*)
@@ -542,7 +542,6 @@ __device__ __forceinline__ void bsq_k2_step_careful(
       }
     }
   }
-  bsq_store_words<WPS, WPS>(pout, cur);
 }
 
 // interior step: every band cell is a regular cell (x >= 1, y >= 1, in table).
@@ -556,6 +555,7 @@ __device__ __forceinline__ void bsq_k2_step_fast(
     const typename S::T* s_sub, int L, unsigned long long comb, const uint8_t* oseq,
     const uint8_t* mseq, int s, int d0, int fixc, typename S::T go, typename S::T ge,
     uint32_t* pout) {
+  // pout: the lane's staging slot of this step in shared memory (words BSQ_FILL_THREADS apart)
   typedef typename S::T T;
   constexpr int HC = C / 2;
   constexpr int WPS = (HC + 7) / 8;
@@ -645,7 +645,8 @@ __device__ __forceinline__ void bsq_k2_step_fast(
 #undef BSQ_FIX
     }
   }
-  bsq_store_words<WPS, WPS>(pout, cur);
+#pragma unroll
+  for (int w = 0; w < WPS; w++) pout[w * BSQ_FILL_THREADS] = cur[w];
 }
 
 template <class S, int G, int C, bool BLOCAL, int GOS>
@@ -655,7 +656,11 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
   constexpr int HC = C / 2;
   constexpr int WPS = (HC + 7) / 8;
   constexpr int NB = BLOCAL ? C : 1;
+  constexpr int TB = BSQ_K2_T(C);          // steps per 32-byte unit of the pointer table
+  constexpr int UW = BSQ_K2_UNIT_WORDS;
+  static_assert(TB >= 2 && TB % 2 == 0 && TB * WPS == UW, "a block of steps fills exactly one unit");
   BSQ_BAIL_IF_BAD(A);
+  __shared__ uint32_t s_unit[UW][BSQ_FILL_THREADS];   // careful steps stage their block here
   __shared__ T s_sub[BSQ_MAX_L * BSQ_MAX_L];
   const int L = A.L;
   // DNA-sized alphabets: the table is re-laid out 4 x 4 so that a nibble
@@ -707,6 +712,7 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
     dstar = dstar < dmin ? dmin : (dstar > dmax ? dmax : dstar);
     const int s_end = 2 * (n < m + dstar ? n : m + dstar) - dstar;
     const int s0 = P.s0;               // (s0 - dmin) is even: step parity == loop parity
+    const int s_last = s0 + 2 * ((s_end - s0) / 2) + 1;   // the last step the pair loops below execute
     // interior steps: all band diagonals have x >= 1, y >= 1 and have not ended
     const int admin = dmin < 0 ? -dmin : dmin, admax = dmax < 0 ? -dmax : dmax;
     const int si_lo = (admin > admax ? admin : admax) + 2;
@@ -725,27 +731,51 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
     for (int c = 0; c < C; c++) { H[c] = NINF; fD[c] = 0; fI[c] = 0; }
 #pragma unroll
     for (int c = 0; c < NB; c++) { best[c] = NINF; bests[c] = 0; }
-    uint32_t* prow = A.ptr + P.ptr_off + (long long)l * WPS;
+    // my 32-byte unit of block blk: unit0 + blk * (G * UW)
+    uint32_t* unit0 = A.ptr + P.ptr_off + (long long)l * UW;
 
     int s = s0;
+    // A careful step leaves its nibbles in cur[]; they go into the lane's staging unit in shared
+    // memory (word-major: no bank conflicts) at step (s - s0) mod TB of the block, and a full block
+    // (or the pair's last one) leaves with two 16-byte stores.
+    // Every step leaves its WPS words in the lane's staging unit in shared memory (word-major: no
+    // bank conflicts); a full block of TB steps (or the pair's last one) leaves with two 16-byte stores.
+    auto flush_unit = [&](const int blk) {
+      uint4 lo, hi;
+      lo.x = s_unit[0][tid]; lo.y = s_unit[1][tid]; lo.z = s_unit[2][tid]; lo.w = s_unit[3][tid];
+      hi.x = s_unit[4][tid]; hi.y = s_unit[5][tid]; hi.z = s_unit[6][tid]; hi.w = s_unit[7][tid];
+      uint4* dst = (uint4*)(unit0 + (long long)blk * (G * UW));
+      dst[0] = lo;
+      dst[1] = hi;
+    };
+    auto careful_put = [&](const uint32_t (&cur)[WPS], const int sc) {
+      const int rel = sc - s0, blk = rel / TB, i = rel - blk * TB;
+#pragma unroll
+      for (int w = 0; w < WPS; w++) s_unit[i * WPS + w][tid] = cur[w];
+      if (i == TB - 1 || sc >= s_last) flush_unit(blk);
+    };
 #define BSQ_K2_CAREFUL_PAIR()                                                                         \
     {                                                                                                 \
+      uint32_t cur[WPS];                                                                              \
       T eH = __shfl_up_sync(gmask, H[C - 1], 1, G);                                                   \
       int eF = __shfl_up_sync(gmask, fD[C - 1], 1, G);                                                \
       if (l == 0) { eH = NINF; eF = 0; }                                                              \
       bsq_k2_step_careful<S, C, BLOCAL, GOS, 0>(btype, H, fD, fI, best, bests, eH, eF, s_sub, Lt,     \
-                                                oseq, mseq, n, m, s, d0, nreal, go, ge,               \
-                                                prow + (long long)(s - s0) * (G * WPS));              \
+                                                oseq, mseq, n, m, s, d0, nreal, go, ge, cur);         \
+      careful_put(cur, s);                                                                            \
       eH = __shfl_down_sync(gmask, H[0], 1, G);                                                       \
       eF = __shfl_down_sync(gmask, fI[0], 1, G);                                                      \
       if (l == G - 1) { eH = NINF; eF = 0; }                                                          \
       bsq_k2_step_careful<S, C, BLOCAL, GOS, 1>(btype, H, fD, fI, best, bests, eH, eF, s_sub, Lt,     \
-                                                oseq, mseq, n, m, s + 1, d0, nreal, go, ge,           \
-                                                prow + (long long)(s + 1 - s0) * (G * WPS));          \
+                                                oseq, mseq, n, m, s + 1, d0, nreal, go, ge, cur);     \
+      careful_put(cur, s + 1);                                                                        \
     }
-    for (; s < sA && s <= s_end; s += 2) BSQ_K2_CAREFUL_PAIR()
+    // careful steps up to the first block boundary at or past sA
+    for (; (s < sA || ((s - s0) % TB) != 0) && s <= s_end; s += 2) BSQ_K2_CAREFUL_PAIR()
 
-    if (s <= sB) {
+    // interior steps in whole blocks: pair starts s .. sBB, the last block ending at or before sB + 1
+    const int sBB = (s + TB - 2 <= sB) ? s + ((sB + 2 - s) / TB) * TB - 2 : s - 2;
+    if (s <= sBB) {
       // letter windows for the pair of steps (s, s+1); cell hc of the even step is
       // (x0 + hc, y0 - hc), of the odd step (x0 + 1 + hc, y0 - hc).
       // nibble j of ow: 4*o[x0+j-1], of mw: m[y0-j-1] (j < HC); onx: 4*o[x0+HC-1],
@@ -775,7 +805,8 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
 #pragma unroll
         for (int c = 0; c < C; c++) H[c] = S::add(H[c], ge);
       }
-      for (; s <= sB; s += 2) {
+      int blk = (s - s0) / TB, ib = 0;     // block of steps, step inside it (0 here: blocks are entered whole)
+      for (; s <= sBB; s += 2) {
         unsigned no = 0u, nm = 0u;  // letters entering the windows after this pair
         if (packed) {
           const int xi = x0 + HC, yi = y0;
@@ -783,8 +814,8 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
           if ((unsigned)yi < (unsigned)m) nm = mseq[yi];
         }
         const unsigned long long ow_odd = (ow >> 4) | ((unsigned long long)onx << (4 * (HC - 1)));
-        uint32_t* pe = prow + (long long)(s - s0) * (G * WPS);
-        uint32_t* po = pe + G * WPS;
+        uint32_t* pe = &s_unit[ib * WPS][tid];
+        uint32_t* po = pe + WPS * BSQ_FILL_THREADS;
         T eH = __shfl_up_sync(gmask, H[C - 1], 1, G);
         int eF = __shfl_up_sync(gmask, fD[C - 1], 1, G);
         if (l == 0) { eH = NINF; eF = 0; }
@@ -809,6 +840,8 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
           mw = (mw << 4) | (unsigned long long)nm;
           x0++; y0++;
         }
+        ib += 2;
+        if (ib == TB) { flush_unit(blk); blk++; ib = 0; }
       }
       if (S::IS_INT) {   // back to H for the careful steps and the end-cell search
 #pragma unroll

@@ -27,10 +27,11 @@ __device__ __forceinline__ uint32_t bsq_get_mask(const BsqTraceArgs& A, const Bs
     const int pass = y / BW, r = y - pass * BW, l = r / K, k = r - l * K;
     idx = P.ptr_off + (((long long)pass * (P.n + G) + x + l) * G + l) * WPL + (k >> 3);
     sh = 4 * (k & 7);
-  } else {
-    const int G = A.G, C = A.K, WPS = (C / 2 + 7) / 8;
-    const int s = x + y, di = (x - y) - P.dmin, l = di / C, c = di - l * C, hc = c >> 1;
-    idx = P.ptr_off + ((long long)(s - P.s0) * G + l) * WPS + (hc >> 3);
+  } else {   // [block of TB steps][lane][32-byte unit], nibble (step in block) * C/2 + hc of the unit
+    const int G = A.G, C = A.K, WPS = BSQ_K2_WPS(C), TB = BSQ_K2_T(C);
+    const int rel = x + y - P.s0, blk = rel / TB, i = rel - blk * TB;
+    const int di = (x - y) - P.dmin, l = di / C, c = di - l * C, hc = c >> 1;
+    idx = P.ptr_off + ((long long)blk * G + l) * BSQ_K2_UNIT_WORDS + i * WPS + (hc >> 3);
     sh = 4 * (hc & 7);
   }
   return (A.ptr[idx] >> sh) & 0xFu;
@@ -338,26 +339,18 @@ __global__ void __launch_bounds__(32 * BSQ_WALK_WARPS) bsq_k4_walk(const BsqTrac
 }
 
 // ---------------------------------------------------------------------------
-// K4t: the walk for BIG batches of long banded pairs (K2 tables), one THREAD per pair.
-// The tile walker above issues every instruction for 8 or 32 lanes that all do the same
-// walk and stages whole table rows (64 - 128 B per op) of which the path needs one nibble;
-// with tens of thousands of pairs in a chunk there is no need to spend a group on one pair:
-// a thread per pair walks straight out of global memory (one 4-byte load per op, incremental
-// addressing without divisions), prefetches the two rows it will reach PF rows further down into
-// L2 (a path stays on its diagonal or moves to a neighbour: the same 32-byte sector), and emits
-// four ops per 32-bit store.  ~8x fewer issued instructions and ~2x fewer DRAM bytes.
-//   table layout (bsq_k2_fill): [s - s0][lane][word], C/2 nibbles per lane and step
+// K4t: the walk over K2 tables, one THREAD per pair.
+// The table is [block of TB steps][lane][32-byte unit] (bsq_common.h): the cells a path visits
+// while it crosses one block of anti-diagonals on one lane's diagonals share ONE sector, so a walk
+// costs a DRAM access per ~TB/2 ops (the first layout, a word per lane and step, cost one per op:
+// 14 ms for config 3's 32768 pairs whether a thread or 8 lanes walked a pair -- random 32-byte
+// reads out of 42 GB, or all 42 GB streamed through shared memory).  Addressing is incremental
+// (no divisions in the loop); the unit of the next block down is prefetched when a block is
+// entered; with PACKED2 the M / S decision reads the letters out of two cached words of the 2-bit
+// packed copy of codes[] (one load per 16 letters and sequence); four ops leave per 32-bit store.
 // ---------------------------------------------------------------------------
-#define BSQ_WALKT_Q 4          // pointer words in flight along the current diagonal
+#define BSQ_WALKT_PF 4
 
-// PACKED2: the M / S decision reads the letters out of two cached 32-bit words of the 2-bit packed
-// copy of codes[] (one load per 16 letters and sequence) instead of two byte loads per op.
-// Every memory instruction of this kernel is uncoalesced (32 pairs per warp), i.e. costs the
-// load/store unit ~32 cycles: the first version (two byte loads and two L2 prefetches per op)
-// was bound by exactly that (13.7 ms for config 3's 32768 pairs; profiles/r02_walk_thread.txt).
-// Now an op costs ONE pointer load: the words of the next BSQ_WALKT_Q cells down the current
-// diagonal are kept in flight (a run of diagonal moves -- 85-95 % of a path -- never waits for
-// DRAM), a gap move flushes that queue.
 template <int GOS, bool PACKED2>
 __global__ void __launch_bounds__(128) bsq_k2_walk_thread(const BsqTraceArgs A) {
   BSQ_BAIL_IF_BAD(A);
@@ -366,13 +359,16 @@ __global__ void __launch_bounds__(128) bsq_k2_walk_thread(const BsqTraceArgs A) 
   const BsqPair P = A.pairs[p];
   const int oi = P.pad;
   if (A.status[oi] != BSQ_OK) { A.txlen[oi] = 0; A.sx[oi] = -1; A.sy[oi] = -1; return; }
-  const int G = A.G, C = A.K, WPS = (C / 2 + 7) / 8, RB = G * WPS;
+  const int G = A.G, C = A.K, WPS = BSQ_K2_WPS(C), TB = BSQ_K2_T(C);
+  constexpr int UW = BSQ_K2_UNIT_WORDS;
   const int ex = A.ex[oi], ey = A.ey[oi];
   int x = ex, y = ey, len = 0;
   const int di = (x - y) - P.dmin;
   int l = di / C, c = di - l * C;
-  long long row = (long long)(x + y) - P.s0;
-  const uint32_t* pw = A.ptr + P.ptr_off + row * RB + l * WPS + ((c >> 1) >> 3);   // the word holding my nibble
+  const int rel = x + y - P.s0;
+  int blk = rel / TB, i = rel - blk * TB;          // block of steps, step inside it
+  const uint32_t* pu = A.ptr + P.ptr_off + ((long long)blk * G + l) * UW;   // my lane's unit of that block
+  const long long bstride = (long long)G * UW;
   const uint8_t* oseq = A.codes + P.o_off;
   const uint8_t* mseq = A.codes + P.m_off;
   char* wr_end = A.slots + P.tx_slot + (long long)P.n + P.m;      // one past the slot end
@@ -380,15 +376,17 @@ __global__ void __launch_bounds__(128) bsq_k2_walk_thread(const BsqTraceArgs A) 
   uint32_t arrive = BSQ_MM;     // how we got here: M (or the end cell) -> lowest bit
   uint32_t acc = 0u;            // the last `filled` ops, latest in the low byte
   int filled = 0;
-  // q[i] = pointer word of the cell i diagonal moves further on (rows row - 2 i), if that row exists
-  uint32_t q[BSQ_WALKT_Q];
-#pragma unroll
-  for (int i = 0; i < BSQ_WALKT_Q; i++) q[i] = (row - 2 * i >= 0) ? pw[-(long long)(2 * i) * RB] : 0u;
   uint32_t ow = 0u, mw = 0u;    // cached words of the packed letters
   long long owi = -1, mwi = -1;
+  // the units of the next BSQ_WALKT_PF blocks down (same lane: a path drifts by a diagonal or two per
+  // block) are requested ahead: a block is crossed in a few hundred cycles, DRAM answers in ~a thousand
+#ifndef BSQ_SIMT_EMU
+#pragma unroll
+  for (int k = 1; k <= BSQ_WALKT_PF; k++) if (blk >= k) asm volatile("prefetch.global.L2 [%0];" ::"l"(pu - k * bstride));
+#endif
   for (;;) {
     const int hc = c >> 1;
-    const uint32_t mk = (q[0] >> (4 * (hc & 7))) & 0xFu;
+    const uint32_t mk = (pu[i * WPS + (hc >> 3)] >> (4 * (hc & 7))) & 0xFu;
     const uint32_t op = (arrive == BSQ_MM) ? bsq_lowest(mk) : bsq_gap_base_t<GOS>(mk, arrive);
     if (op == BSQ_MB || op == 0u || len >= maxlen) break;
     const bool isM = (op == BSQ_MM), isD = (op == BSQ_MD), isI = !(isM || isD);
@@ -417,23 +415,19 @@ __global__ void __launch_bounds__(128) bsq_k2_walk_thread(const BsqTraceArgs A) 
     arrive = op;
     x -= isI ? 0 : 1;
     y -= isD ? 0 : 1;
-    const int dr = isM ? 2 : 1;                  // s = x + y drops by 2 on a diagonal move
-    row -= dr;
-    pw -= (long long)dr * RB;
-    if (!isM) {                                  // the local diagonal moves with x - y
-      const int w0 = (c >> 1) >> 3;              // word of my nibble inside the lane's row
-      c += isI ? 1 : -1;
-      if (c < 0) { c = C - 1; l--; pw -= WPS; }
-      if (c == C) { c = 0; l++; pw += WPS; }
-      pw += ((c >> 1) >> 3) - w0;
+    i -= isM ? 2 : 1;                            // s = x + y drops by 2 on a diagonal move
+    if (i < 0) {                                 // into the block below
+      i += TB;
+      blk--;
+      pu -= bstride;
+#ifndef BSQ_SIMT_EMU
+      if (blk >= BSQ_WALKT_PF) asm volatile("prefetch.global.L2 [%0];" ::"l"(pu - BSQ_WALKT_PF * bstride));
+#endif
     }
-    if (isM) {      // the queue moves up one cell; one new word enters at its end
-#pragma unroll
-      for (int i = 0; i + 1 < BSQ_WALKT_Q; i++) q[i] = q[i + 1];
-      q[BSQ_WALKT_Q - 1] = (row - 2 * (BSQ_WALKT_Q - 1) >= 0) ? pw[-(long long)(2 * (BSQ_WALKT_Q - 1)) * RB] : 0u;
-    } else {        // another diagonal (and the other parity of s): reload
-#pragma unroll
-      for (int i = 0; i < BSQ_WALKT_Q; i++) q[i] = (row - 2 * i >= 0) ? pw[-(long long)(2 * i) * RB] : 0u;
+    if (!isM) {                                  // the local diagonal moves with x - y
+      c += isI ? 1 : -1;
+      if (c < 0) { c = C - 1; l--; pu -= UW; }
+      if (c == C) { c = 0; l++; pu += UW; }
     }
   }
   if (filled > 0) {
@@ -444,6 +438,108 @@ __global__ void __launch_bounds__(128) bsq_k2_walk_thread(const BsqTraceArgs A) 
   A.sx[oi] = x;
   A.sy[oi] = y;
   A.status[oi] = (ex + ey - len <= 0) ? BSQ_REF_WOULD_ABORT : (len == 0 ? BSQ_EMPTY : BSQ_OK);
+}
+
+// ---------------------------------------------------------------------------
+// K4c: the walk over K2 tables by a GROUP of GW lanes per pair (8: four pairs per warp, big
+// batches; 32: small batches).  The group stages a WINDOW of the table around the path -- the
+// units of BSQ_WALKC_NBLK blocks of steps below the current one, for the path's lane and its two
+// neighbours (a path drifts by a diagonal or two per block, a lane owns C of them) -- with
+// independent 16-byte loads (GW requests in flight instead of one: the thread-per-pair walker is
+// bound by the latency of a DRAM access per block on long pairs, 41 ms on config 4), ~100 bytes per
+// block instead of the whole 256 - 1024-byte row of blocks.  Then lane q examines cell (x-q, y-q) of the
+// current diagonal, a ballot finds how far the run of diagonal moves goes, those lanes emit
+// their M / S together, and only the op that ends the run is handled serially.
+// ---------------------------------------------------------------------------
+#define BSQ_WALKC_NBLK 16
+#define BSQ_WALKC_WARPS 4
+
+template <int GOS, int GW>
+__global__ void __launch_bounds__(32 * BSQ_WALKC_WARPS) bsq_k2_walk_coop(const BsqTraceArgs A) {
+  constexpr int PPW = 32 / GW;                               // pairs per warp
+  constexpr int UW = BSQ_K2_UNIT_WORDS;
+  BSQ_BAIL_IF_BAD(A);
+  __shared__ uint4 s_win[BSQ_WALKC_WARPS * PPW][BSQ_WALKC_NBLK * 3 * 2];   // [block][lane - wl0][half unit]
+  const int wib = threadIdx.x >> 5;
+  const int lane = threadIdx.x & (GW - 1);
+  const int grp = (threadIdx.x & 31) / GW;
+  const unsigned gmask = (GW == 32) ? 0xffffffffu : (((1u << GW) - 1u) << (grp * GW));
+  const int slot = wib * PPW + grp;
+  const int p = blockIdx.x * (BSQ_WALKC_WARPS * PPW) + slot;
+  if (p >= A.npairs) return;  // the whole group
+  const BsqPair P = A.pairs[p];
+  const int oi = P.pad;
+  if (A.status[oi] != BSQ_OK) {
+    if (lane == 0) { A.txlen[oi] = 0; A.sx[oi] = -1; A.sy[oi] = -1; }
+    return;
+  }
+  const int G = A.G, C = A.K, WPS = BSQ_K2_WPS(C), TB = BSQ_K2_T(C);
+  const int ex = A.ex[oi], ey = A.ey[oi];
+  int x = ex, y = ey, len = 0;
+  const int di0 = (x - y) - P.dmin;
+  int l = di0 / C, c = di0 - l * C;                          // lane / local diagonal of (x, y)
+  int rel = x + y - P.s0;                                    // step of (x, y)
+  const uint32_t* table = A.ptr + P.ptr_off;
+  const uint8_t* oseq = A.codes + P.o_off;
+  const uint8_t* mseq = A.codes + P.m_off;
+  char* wr = A.slots + P.tx_slot + (long long)P.n + P.m;
+  const int maxlen = P.n + P.m;
+  const uint32_t* win = (const uint32_t*)s_win[slot];
+  int wlo = 1, whi = 0, wl0 = 0;                             // window: blocks [wlo, whi], lanes [wl0, wl0 + 2]
+  uint32_t arrive = BSQ_MM;
+  for (;;) {
+    const int blk = rel / TB;
+    if (blk < wlo || blk > whi || l < wl0 || l > wl0 + 2) {  // stage the window below and around (blk, l)
+      whi = blk;
+      wlo = blk - BSQ_WALKC_NBLK + 1;
+      wlo = wlo < 0 ? 0 : wlo;
+      wl0 = l - 1;
+      wl0 = wl0 < 0 ? 0 : (wl0 + 2 > G - 1 ? (G - 3 < 0 ? 0 : G - 3) : wl0);
+      const int nl = G < 3 ? G : 3;
+      const int nq = (whi - wlo + 1) * nl * 2;               // 16-byte quantities to fetch
+      __syncwarp(gmask);
+      for (int k = lane; k < nq; k += GW) {
+        const int b = k / (nl * 2), r = k - b * (nl * 2), ll = r >> 1, h = r & 1;
+        s_win[slot][(b * 3 + ll) * 2 + h] =
+            *(const uint4*)(table + ((long long)(wlo + b) * G + wl0 + ll) * UW + 4 * h);
+      }
+      __syncwarp(gmask);
+    }
+    // lane q looks at (x-q, y-q): the same diagonal (lane l, nibble c/2), step rel - 2q
+    const int relq = rel - 2 * lane, blkq = relq >= 0 ? relq / TB : -1, iq = relq - blkq * TB;
+    const bool valid = (relq >= 0) && (blkq >= wlo) && (x - lane >= 0) && (y - lane >= 0) && (len + lane < maxlen);
+    const int hc = c >> 1;
+    uint32_t nib = 0u;
+    if (valid) nib = (win[((blkq - wlo) * 3 + (l - wl0)) * UW + iq * WPS + (hc >> 3)] >> (4 * (hc & 7))) & 0xFu;
+    const uint32_t opq = (lane == 0 && arrive != BSQ_MM) ? bsq_gap_base_t<GOS>(nib, arrive) : bsq_lowest(nib);
+    const unsigned vmask = __ballot_sync(gmask, valid) >> (grp * GW);
+    const unsigned mmask = (__ballot_sync(gmask, valid && opq == BSQ_MM) >> (grp * GW)) & (GW == 32 ? 0xffffffffu : ((1u << GW) - 1u));
+    const int nv = __popc(vmask & (GW == 32 ? 0xffffffffu : ((1u << GW) - 1u)));   // valid cells form a prefix
+    const unsigned inv = ~mmask & (GW == 32 ? 0xffffffffu : ((1u << GW) - 1u));
+    const int run = inv == 0u ? GW : (__ffs((int)inv) - 1);
+    if (nv == 0) break;                                      // len == maxlen (or nothing left)
+    if (lane < run) {
+      const char ch = (oseq[x - 1 - lane] == mseq[y - 1 - lane]) ? 'M' : 'S';
+      wr[-(len + lane + 1)] = ch;
+    }
+    if (run > 0) { x -= run; y -= run; len += run; rel -= 2 * run; arrive = BSQ_MM; }
+    if (run == nv) continue;                                 // the run reached the edge of the window
+    const uint32_t op = __shfl_sync(gmask, opq, run, GW);    // the cell that ended the run: not a diagonal move
+    if (op == BSQ_MB || op == 0u || op == BSQ_MM || len >= maxlen) break;
+    char ch;
+    if (op == BSQ_MD) { ch = 'D'; x--; if (--c < 0) { c = C - 1; l--; } }
+    else { ch = 'I'; y--; if (++c == C) { c = 0; l++; } }
+    rel -= 1;
+    arrive = op;
+    len++;
+    if (lane == 0) wr[-len] = ch;
+  }
+  if (lane == 0) {
+    A.txlen[oi] = len;
+    A.sx[oi] = x;
+    A.sy[oi] = y;
+    A.status[oi] = (ex + ey - len <= 0) ? BSQ_REF_WOULD_ABORT : (len == 0 ? BSQ_EMPTY : BSQ_OK);
+  }
 }
 
 // ---------------------------------------------------------------------------

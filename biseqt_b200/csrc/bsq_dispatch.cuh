@@ -42,9 +42,12 @@ static int bsq_k1_op_t(int cfg, int ball, int eall, int gos, int op, int grid, c
 template <class S, int G, int C>
 static int bsq_k2_variant(int blocal, int gos, int op, int grid, cudaStream_t st, const BsqFillArgs* A) {
 #define BSQ_K2_CASE(B, GS) \
-  if (blocal == B && gos == GS) return bsq_do_op(bsq_k2_fill<S, G, C, B != 0, GS>, op, grid, st, A);
+  if (blocal == B && gos == GS) return bsq_do_op(bsq_k2_fill<S, G, C, B, GS>, op, grid, st, A);
   BSQ_K2_CASE(0, -1) BSQ_K2_CASE(0, 0) BSQ_K2_CASE(0, 1)
   BSQ_K2_CASE(1, -1) BSQ_K2_CASE(1, 0) BSQ_K2_CASE(1, 1)
+  if constexpr (S::IS_INT) {   // blocal == 2: B_LOCAL with packed end-cell keys (see bsq_k2_fill)
+    BSQ_K2_CASE(2, -1) BSQ_K2_CASE(2, 0) BSQ_K2_CASE(2, 1)
+  }
 #undef BSQ_K2_CASE
   return -1;
 }

@@ -171,6 +171,8 @@ struct Plan {
   int64_t total_words = 0;
   bool identity = false;  // processing order == caller order (no sort was needed)
   bool codes2_ok = false; // BufSet.codes2 holds the 2-bit packed copy of this batch's letters
+  int64_t max_nm = 0;     // largest n + m of the batch
+  double score_bound = 0; // (max n + max m + 4) * largest |score|: no partial sum leaves it
   int64_t half_words = 0; // > 0: BSQ_ARENA_SLOTS arena slots of this size, chunk c uses slot c % SLOTS so that
                           // trace(c) overlaps the fills of the following chunks
   // uniform batches (every pair the same shape, e.g. fixed-length reads): the pair records are
@@ -536,6 +538,12 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
     if (!sc.uniform) all_uniform = false;
   }
   if (implicit && (ob < 0 || ob + scan_tot > ncodes)) return fail(ctx, BSQ_ERR_ARG, "back-to-back pairs do not fit codes[]");
+  P.max_nm = scan_n + scan_m;
+  {
+    double maxabs = std::fabs(prm->go) + std::fabs(prm->ge);
+    for (double v : P.subst) maxabs = std::max(maxabs, std::fabs(v));
+    P.score_bound = (double)(scan_n + scan_m + 4) * maxabs;
+  }
   // geometry depends on the arithmetic; decide it up front from the scores and maxima
   bool f64_geom = true;
   {
@@ -1388,7 +1396,9 @@ int launch_fill(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, size_t* evi, 
   // the -inf padding columns can never beat a real cell; explicitly gated otherwise
   const bool monotone = (P.prm.ge <= 0.0) && (P.prm.ge + P.prm.go <= 0.0);
   const int ball = P.bmode == BSQ_B_ALL, eall = (P.emode == BSQ_E_ALL) ? (monotone ? 1 : 2) : 0;
-  const int blocal = P.prm.type == BSQ_B_LOCAL;
+  // B_LOCAL: 2 = packed end-cell keys (integer scores below 2^16, n + m below 2^16), 1 = general
+  int blocal = P.prm.type == BSQ_B_LOCAL;
+  if (blocal && ch.family == 2 && P.dtype == BSQ_DTYPE_I32 && P.max_nm < 65000 && P.score_bound < 65000.0) blocal = 2;
   int occ = ch.family == 1 ? k1_op(P.dtype, ch.cfg, ball, eall, P.gosign, BSQ_OP_OCCUPANCY, 0, 0, nullptr)
                            : k2_op(P.dtype, ch.cfg, blocal, P.gosign, BSQ_OP_OCCUPANCY, 0, 0, nullptr);
   if (occ < 0) return fail(ctx, BSQ_ERR_ARG, "no kernel variant for this configuration");

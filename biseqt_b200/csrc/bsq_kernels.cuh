@@ -27,6 +27,9 @@
 #include "../../include/bsqgpu.h"
 
 #define BSQ_INT_MAX 0x7fffffff
+// B_LOCAL end-cell keys of the integer K2 kernel (BLOCAL == 2)
+#define BSQ_K2_KEYBITS 15
+#define BSQ_K2_KSTEP(s, s0) (((1 << BSQ_K2_KEYBITS) - 1) - (((s) - (s0)) >> 1))
 
 // every fill / traceback kernel starts with this: a letter code >= alphabet_len would index the
 // shared-memory score table out of bounds, so after bsq_check_codes raised the flag nothing runs
@@ -493,12 +496,12 @@ __global__ void __launch_bounds__(128) bsq_k1_fill(const BsqFillArgs A) {
 // cell right of it -- i.e. what diagonals c+1 and c-1 will need one step later.
 
 // careful step: any cell may be off-table, on an edge, or a padding diagonal
-template <class S, int C, bool BLOCAL, int GOS, int Q>
+template <class S, int C, int BLOCAL, int GOS, int Q>
 __device__ __forceinline__ void bsq_k2_step_careful(
     int btype, typename S::T (&H)[C], int (&fD)[C], int (&fI)[C], typename S::T (&best)[BLOCAL ? C : 1],
-    int (&bests)[BLOCAL ? C : 1], typename S::T edgeH, int edgeF, const typename S::T* s_sub, int L,
+    int (&bests)[BLOCAL == 1 ? C : 1], typename S::T edgeH, int edgeF, const typename S::T* s_sub, int L,
     const uint8_t* oseq, const uint8_t* mseq, int n, int m, int s, int d0, int nreal,
-    typename S::T go, typename S::T ge, uint32_t (&cur)[(C / 2 + 7) / 8]) {
+    typename S::T go, typename S::T ge, uint32_t (&cur)[(C / 2 + 7) / 8], const int kstep) {
   typedef typename S::T T;
   constexpr int HC = C / 2;
   constexpr int WPS = (HC + 7) / 8;
@@ -537,9 +540,13 @@ __device__ __forceinline__ void bsq_k2_step_careful(
       H[c] = h;
       fD[c] = bsq_gapflag<S, GOS>(eD, eB, eI, eM);
       fI[c] = bsq_gapflag<S, GOS>(eI, eB, eD, eM);
-      if (BLOCAL) {  // :397-406 restricted to one diagonal (a ascends with s)
+      if (BLOCAL == 1) {  // :397-406 restricted to one diagonal (a ascends with s)
         if (h > best[c]) { best[c] = h; bests[c] = s; }
       }
+    }
+    if constexpr (BLOCAL == 2) {   // the same record as ONE packed key (see bsq_k2_fill), kept only for table cells
+      const int key = (int)h * (1 << BSQ_K2_KEYBITS) + kstep;
+      best[c] = (intab && key > (int)best[c]) ? key : best[c];
     }
   }
 }
@@ -548,13 +555,13 @@ __device__ __forceinline__ void bsq_k2_step_careful(
 // comb: nibble hc = 4*origin letter + mutant letter of cell hc (PACKED), else
 // the letters are read per cell.  fixc: local index of the first diagonal past
 // the band in this lane (or -1): it is reset to -inf so the band edge stays shut.
-template <class S, int C, bool BLOCAL, int GOS, int Q, bool PACKED>
+template <class S, int C, int BLOCAL, int GOS, int Q, bool PACKED>
 __device__ __forceinline__ void bsq_k2_step_fast(
     typename S::T (&H)[C], int (&fD)[C], int (&fI)[C], typename S::T (&best)[BLOCAL ? C : 1],
-    int (&bests)[BLOCAL ? C : 1], typename S::T edgeH, int edgeF,
+    int (&bests)[BLOCAL == 1 ? C : 1], typename S::T edgeH, int edgeF,
     const typename S::T* s_sub, int L, unsigned long long comb, const uint8_t* oseq,
     const uint8_t* mseq, int s, int d0, int fixc, typename S::T go, typename S::T ge,
-    uint32_t* pout) {
+    uint32_t* pout, const int kstep) {
   // pout: the lane's staging slot of this step in shared memory (words BSQ_FILL_THREADS apart)
   typedef typename S::T T;
   constexpr int HC = C / 2;
@@ -615,13 +622,15 @@ __device__ __forceinline__ void bsq_k2_step_fast(
       H[c] = h + ge;
       fD[c] = bsq_gapflag_i32<GOS>(nD, nB, nI, nM);
       fI[c] = bsq_gapflag_i32<GOS>(nI, nB, nD, nM);
-      if (BLOCAL) {
+      if (BLOCAL == 1) {
         if (h > best[c]) { best[c] = h; bests[c] = s; }
+      } else if (BLOCAL == 2) {   // (score, earliest step) as one key: a multiply-add and a max
+        best[c] = max(best[c], h * (1 << BSQ_K2_KEYBITS) + kstep);
       }
     } else {
     T h;
     bool eB, eD, eI, eM;
-    bsq_cell2<S, GOS, BLOCAL>(up, gD, left, gI, diag, sig, (T)0, go, ge, h, eB, eD, eI, eM);
+    bsq_cell2<S, GOS, BLOCAL != 0>(up, gD, left, gI, diag, sig, (T)0, go, ge, h, eB, eD, eI, eM);
     uint32_t w = cur[hc >> 3];
     if (BLOCAL) { if (eB) w += BSQ_MB << (4 * (hc & 7)); }
     if (eD) w += BSQ_MD << (4 * (hc & 7));
@@ -631,7 +640,7 @@ __device__ __forceinline__ void bsq_k2_step_fast(
     H[c] = h;
     fD[c] = bsq_gapflag<S, GOS>(eD, eB, eI, eM);
     fI[c] = bsq_gapflag<S, GOS>(eI, eB, eD, eM);
-    if (BLOCAL) {
+    if (BLOCAL == 1) {
       if (h > best[c]) { best[c] = h; bests[c] = s; }
     }
     }
@@ -649,13 +658,15 @@ __device__ __forceinline__ void bsq_k2_step_fast(
   for (int w = 0; w < WPS; w++) pout[w * BSQ_FILL_THREADS] = cur[w];
 }
 
-template <class S, int G, int C, bool BLOCAL, int GOS>
+template <class S, int G, int C, int BLOCAL, int GOS>
 __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
   typedef typename S::T T;
   static_assert(C % 2 == 0 && C <= 32, "lanes own an even number of diagonals, at most 32");
   constexpr int HC = C / 2;
   constexpr int WPS = (HC + 7) / 8;
   constexpr int NB = BLOCAL ? C : 1;
+  constexpr int NBS = BLOCAL == 1 ? C : 1;
+  static_assert(BLOCAL != 2 || S::IS_INT, "packed end-cell keys are an integer form");
   constexpr int TB = BSQ_K2_T(C);          // steps per 32-byte unit of the pointer table
   constexpr int UW = BSQ_K2_UNIT_WORDS;
   static_assert(TB >= 2 && TB % 2 == 0 && TB * WPS == UW, "a block of steps fills exactly one unit");
@@ -725,12 +736,20 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
 
     T H[C];
     int fD[C], fI[C];
+    // B_LOCAL's end cell (_banded_find_optimal :395-408: every cell, diagonals ascending, first strict
+    // maximum) needs, per diagonal, its best score and the earliest step that reached it.  BLOCAL == 1:
+    // two registers per diagonal and compare + two selects per cell.  BLOCAL == 2 (host: integer scores
+    // below 2^(31 - KEYBITS), n + m below 2^(KEYBITS + 1)): ONE key score * 2^KEYBITS + (2^KEYBITS - 1 -
+    // (s - s0) / 2) per diagonal, one multiply-add and one max per cell -- its maximum is the highest
+    // score at the earliest step.
     T best[NB];
-    int bests[NB];
+    int bests[NBS];
 #pragma unroll
     for (int c = 0; c < C; c++) { H[c] = NINF; fD[c] = 0; fI[c] = 0; }
 #pragma unroll
-    for (int c = 0; c < NB; c++) { best[c] = NINF; bests[c] = 0; }
+    for (int c = 0; c < NB; c++) best[c] = (BLOCAL == 2) ? (T)-1 : NINF;
+#pragma unroll
+    for (int c = 0; c < NBS; c++) bests[c] = 0;
     // my 32-byte unit of block blk: unit0 + blk * (G * UW)
     uint32_t* unit0 = A.ptr + P.ptr_off + (long long)l * UW;
 
@@ -761,13 +780,15 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
       int eF = __shfl_up_sync(gmask, fD[C - 1], 1, G);                                                \
       if (l == 0) { eH = NINF; eF = 0; }                                                              \
       bsq_k2_step_careful<S, C, BLOCAL, GOS, 0>(btype, H, fD, fI, best, bests, eH, eF, s_sub, Lt,     \
-                                                oseq, mseq, n, m, s, d0, nreal, go, ge, cur);         \
+                                                oseq, mseq, n, m, s, d0, nreal, go, ge, cur,          \
+                                                BSQ_K2_KSTEP(s, s0));                                 \
       careful_put(cur, s);                                                                            \
       eH = __shfl_down_sync(gmask, H[0], 1, G);                                                       \
       eF = __shfl_down_sync(gmask, fI[0], 1, G);                                                      \
       if (l == G - 1) { eH = NINF; eF = 0; }                                                          \
       bsq_k2_step_careful<S, C, BLOCAL, GOS, 1>(btype, H, fD, fI, best, bests, eH, eF, s_sub, Lt,     \
-                                                oseq, mseq, n, m, s + 1, d0, nreal, go, ge, cur);     \
+                                                oseq, mseq, n, m, s + 1, d0, nreal, go, ge, cur,      \
+                                                BSQ_K2_KSTEP(s + 1, s0));                             \
       careful_put(cur, s + 1);                                                                        \
     }
     // careful steps up to the first block boundary at or past sA
@@ -821,19 +842,19 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
         if (l == 0) { eH = NINF; eF = 0; }
         if (packed)
           bsq_k2_step_fast<S, C, BLOCAL, GOS, 0, true>(H, fD, fI, best, bests, eH, eF, s_fast, Lt, ow | mw, oseq,
-                                                       mseq, s, d0, fixc, go, ge, pe);
+                                                       mseq, s, d0, fixc, go, ge, pe, BSQ_K2_KSTEP(s, s0));
         else
           bsq_k2_step_fast<S, C, BLOCAL, GOS, 0, false>(H, fD, fI, best, bests, eH, eF, s_fast, Lt, 0ull, oseq,
-                                                        mseq, s, d0, fixc, go, ge, pe);
+                                                        mseq, s, d0, fixc, go, ge, pe, BSQ_K2_KSTEP(s, s0));
         eH = __shfl_down_sync(gmask, H[0], 1, G);
         eF = __shfl_down_sync(gmask, fI[0], 1, G);
         if (l == G - 1) { eH = NINF; eF = 0; }
         if (packed)
           bsq_k2_step_fast<S, C, BLOCAL, GOS, 1, true>(H, fD, fI, best, bests, eH, eF, s_fast, Lt, ow_odd | mw,
-                                                       oseq, mseq, s + 1, d0, fixc, go, ge, po);
+                                                       oseq, mseq, s + 1, d0, fixc, go, ge, po, BSQ_K2_KSTEP(s + 1, s0));
         else
           bsq_k2_step_fast<S, C, BLOCAL, GOS, 1, false>(H, fD, fI, best, bests, eH, eF, s_fast, Lt, 0ull, oseq,
-                                                        mseq, s + 1, d0, fixc, go, ge, po);
+                                                        mseq, s + 1, d0, fixc, go, ge, po, BSQ_K2_KSTEP(s + 1, s0));
         if (packed) {
           ow = ow_odd;
           onx = no << 2;
@@ -862,8 +883,14 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
 #pragma unroll
       for (int c = 0; c < C; c++) {
         if (c < nreal) {
-          const T cand = BLOCAL ? best[c < NB ? c : 0] : H[c];
-          if (cand > bs) { bs = cand; bdi = l * C + c; ba = BLOCAL ? bests[c < NB ? c : 0] : 0; }
+          T cand = BLOCAL ? best[c < NB ? c : 0] : H[c];
+          int step = BLOCAL == 1 ? bests[c < NBS ? c : 0] : 0;
+          if (BLOCAL == 2) {   // unpack (score, step); no key: no cell of this diagonal in the table
+            const int key = (int)cand;
+            step = s0 + 2 * ((1 << BSQ_K2_KEYBITS) - 1 - (key & ((1 << BSQ_K2_KEYBITS) - 1))) + (c & 1);
+            cand = key < 0 ? NINF : (T)(key >> BSQ_K2_KEYBITS);
+          }
+          if (cand > bs) { bs = cand; bdi = l * C + c; ba = step; }
         }
       }
     }

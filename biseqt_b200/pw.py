@@ -78,6 +78,22 @@ class Aligner(object):
     ``Exception('Failed to initialize the DP table.')`` where the reference
     returns -1); ``solve()`` fills the table on the GPU and keeps the
     traceback pointers in HBM; ``traceback()`` walks them; ``__exit__`` frees.
+
+    Deviations from the reference, all where its behaviour is undefined or fatal
+    (INTEGRATION.md section 3):
+
+    * ``max_new_mins > 0`` raises ``NotImplementedError`` (the reference reads
+      uninitialised fields there, ``_pw_internals.c:236-243``);
+    * alphabets of more than 32 letters raise ``ValueError`` here (the kernels stage the
+      score table in shared memory; the reference has no limit);
+    * ``|score| * (n + m) >= 2**31`` raises ``NotImplementedError`` from ``solve()`` (the
+      reference's ``-INT_MAX`` clamp of gap candidates could bind there);
+    * ``traceback()`` returns ``None`` for an empty optimal alignment where the reference
+      fails ``assert alignment != ffi.NULL`` (``pw.py:299``), and returns the transcript
+      where the reference ``exit(1)``s (a path of indels only from (0,0), ``pw.c:132-134``);
+    * ``table_scores()`` re-solves the problem instead of reading the solved table and raises
+      ``IndexError`` for ranges beyond the frame (the reference reads out of bounds); banded
+      tables are refused like in the reference (``pw.py:280-281``).
     """
 
     def __init__(self, origin, mutant, **kw):
@@ -91,6 +107,9 @@ class Aligner(object):
         assert origin.alphabet == mutant.alphabet
         self.origin, self.mutant = origin, mutant
         self.alphabet = origin.alphabet
+        if len(self.alphabet) > 32:
+            raise ValueError('alphabets of more than 32 letters are not supported by the GPU kernels '
+                             '(got %d letters)' % len(self.alphabet))
 
         origin_range = kw.get('origin_range', (0, len(self.origin)))
         mutant_range = kw.get('mutant_range', (0, len(self.mutant)))

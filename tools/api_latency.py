@@ -4,7 +4,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from biseqt_b200.sequence import Alphabet, Sequence
-from biseqt_b200.pw import Aligner, LOCAL, STD_MODE
+from biseqt_b200.pw import Aligner, LOCAL, GLOBAL, STD_MODE
 
 A = Alphabet('ACGT')
 rng = np.random.default_rng(1)
@@ -19,4 +19,13 @@ for n in (100, 1000):
     for _ in range(K):
         with Aligner(S, T, alntype=LOCAL, match_score=1, mismatch_score=-1, go_score=-2, ge_score=-1) as al:
             al.solve(); al.traceback()
-    print('%d x %d: %.3f ms per Aligner (solve + traceback)' % (n, n, 1e3 * (time.perf_counter() - t0) / K))
+    print('%d x %d LOCAL: %.3f ms per Aligner (solve + traceback)' % (n, n, 1e3 * (time.perf_counter() - t0) / K))
+    # the reference's default alignment type (configs[0]): big GLOBAL pairs take the strip pipeline (K3L)
+    for _ in range(3):
+        with Aligner(S, T, alntype=GLOBAL, match_score=1, mismatch_score=-1, go_score=-2, ge_score=-1) as al:
+            al.solve(); al.traceback()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        with Aligner(S, T, alntype=GLOBAL, match_score=1, mismatch_score=-1, go_score=-2, ge_score=-1) as al:
+            al.solve(); al.traceback()
+    print('%d x %d GLOBAL: %.3f ms per Aligner (solve + traceback)' % (n, n, 1e3 * (time.perf_counter() - t0) / K))

@@ -54,6 +54,14 @@ PIPE_NOTES = {
 }
 
 
+def k1h_traffic():
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r02_k1h_traffic.json')) as f:
+            return json.load(f)['traffic']
+    except Exception:
+        return None
+
+
 def ops_per_cell(go):
     """Algorithmic ALU ops per cell: 5 adds + 3 max + 4 equality
     tests; the two '+go' adds vanish when go == 0."""
@@ -518,7 +526,7 @@ def main():
             pipe = {k: eng.microbench(k) for k in ('DADD', 'DMAX', 'DSETP', 'IADD', 'VADD2', 'VIMAX3', 'VIADDMAX', 'SHFL', 'LDS64')}
         except Exception as e:   # never hide the bench line behind a microbenchmark problem
             pipe = {'error': str(e)}
-        if 'error' not in pipe:
+        if 'error' not in pipe and pipe.get('DADD', 0) > 5e12:   # (a run under ncu measures nonsense: do not store it)
             try:   # stored next to the other measured peaks (gpurun_out/ travels back; copied to profiles/)
                 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
                 with open(os.path.join(ROOT, 'gpurun_out', 'ALU_PEAKS.json'), 'w') as f:
@@ -540,10 +548,11 @@ def main():
         roofline = {
             'bound': 'alu', 'achieved': achieved, 'peak': peak, 'unit': 'Gop/s',
             'frac': (achieved / peak) if peak else None,
-            # DRAM bytes (read + write) of ONE fill launch, from the ncu --set full capture of this
-            # kernel on this workload (profiles/r01_k1h_final_ncu.txt); algorithmic pointer bytes of
-            # a launch (125k pairs x 0.5 B/cell) are 1.43e9
-            'traffic': 2.468e9 if (kind == 'c2_int' and npairs == 1000000 and m['dtype'] == 'i16x2') else None,
+            # DRAM bytes (read + write) of ONE fill launch: read from the file the round's ncu --set full
+            # capture of this kernel on this workload was summarised into (profiles/r02_k1h_traffic.json,
+            # made from profiles/r02_k1h_ncu.txt); algorithmic pointer bytes of a launch (125k pairs x
+            # 0.5 B/cell) are 1.43e9
+            'traffic': k1h_traffic() if (kind == 'c2_int' and npairs == 1000000 and m['dtype'] == 'i16x2') else None,
             'ops_per_cell': opc, 'pipe': which,
             'note': 'achieved = cells x algorithmic ops/cell / fill-kernel time (CUDA events on the library stream); '
                     'peak = %s issue rate measured in this run (bsq_microbench)' % {'IADD': 'add.s32', 'VADD2': 'packed 16-bit add (VIADD.16x2, two adds per instruction)', 'DADD': 'add.f64'}[which],

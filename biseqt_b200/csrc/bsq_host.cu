@@ -555,10 +555,11 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   P.pairs = nullptr;
   const Hooks& hk = ctx->hooks;
   const bool force_k3 = hk.force_k3 || std_as_band;
-  // strip geometry: cfg 1 (4 columns x 2 rows per lane and step) unless forced; full-width bands of
-  // STD GLOBAL pairs take the latency form (cfg 0, bsq_k3l_fill: measured 0.46 ms against 3.04 ms on
-  // K1 for config 1; on config 5's 4097-diagonal band cfg 1 is still ahead, 367 ms against 415 ms)
-  const int k3_cfg = (hk.k3_cfg >= 0 && hk.k3_cfg < BSQ_K3_NCFG) ? hk.k3_cfg : (std_as_band ? 0 : 1);
+  // strip geometry: a few wide-band pairs are bound by the dependency chain and take the latency form
+  // (cfg 0, bsq_k3l_fill: config 5 fills in 274 ms against 367 ms, config 1 -- a full-width band -- in
+  // 0.32 ms against 3.04 ms on K1); many of them are bound by throughput: cfg 1, 4 columns x 2 rows
+  // per lane and step
+  const int k3_cfg = (hk.k3_cfg >= 0 && hk.k3_cfg < BSQ_K3_NCFG) ? hk.k3_cfg : (N <= 8 ? 0 : 1);
   // K1h (two short problems per lane group, packed 16-bit arithmetic): what the scores and
   // the alignment type must satisfy; the shape conditions are per pair (PlanItem.lo for STD)
   double duo_maxabs = std::fabs(prm->go) + std::fabs(prm->ge);

@@ -591,11 +591,31 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3l_fill(const BsqFillArgs
       typename Slab::Raw nx = {};    // prefetched (raw) boundary entry of row x_lo + (next batch) + lane
       bool nx_have = false;
 
-      for (int t = 0; t < nsteps; t++) {
-        if ((t & (NBT - 1)) == 0 && j > 0) {
-          // boundary values of rows x_lo + t .. x_lo + t + NBT - 1 (lane i < NBT: row xr), fetched one
+      // The step body is straight-line code: a lone warp pays 25 - 50 cycles for every branch it has to
+      // resolve (ncu source view of the first version: 5 branches, ~200 of a step's ~450 cycles), so
+      // stores are predicated instead of guarded, the boundary batch sits at the top of a group of NBT
+      // unrolled steps instead of behind a per-step test, pointers advance instead of being recomputed,
+      // and the kernel parameters the loop needs live in registers (the compiler would re-read the
+      // constant bank every step to save registers nobody else wants: one warp per scheduler).
+      const uint8_t* letp = oseq + (x_lo + 2);             // &o[(x_lo + t + 3) - 1] at t = 0
+      PU* pst = prow;                                      // prow + t * G
+      unsigned long long* pslab = slab + (long long)(x_lo - lane) * Slab::EPR;   // slab + x * EPR
+      const bool put31 = (lane == G - 1) && has_succ;
+      const bool lane0 = (lane == 0), lane0in = lane0 && (j > 0);
+      const T* sbase = s_sub;
+      int Lr = L, nr = n;
+      T gor = go, ger = ge;
+#ifndef BSQ_SIMT_EMU
+      asm volatile("" : "+r"(Lr), "+r"(nr));
+      if constexpr (S::IS_INT) asm volatile("" : "+r"(gor), "+r"(ger));
+      else asm volatile("" : "+d"(gor), "+d"(ger));
+      asm volatile("" : "+l"(letp), "+l"(pst), "+l"(pslab), "+l"(sbase));
+#endif
+      for (int t0 = 0; t0 < nsteps; t0 += NBT) {
+        if (j > 0) {
+          // boundary values of rows x_lo + t0 .. x_lo + t0 + NBT - 1 (lane i < NBT: row xr), fetched one
           // batch ahead; rows past pred_hi lie outside the band
-          const int xr = x_lo + t + lane;
+          const int xr = x_lo + t0 + lane;
           const bool mine = lane < NBT;
           const bool need = mine && (xr <= pred_hi);
           T bH = NINF;
@@ -617,65 +637,76 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3l_fill(const BsqFillArgs
           nx_have = mine && (xn <= pred_hi);
           if (nx_have) nx = Slab::load(slab + (long long)xn * Slab::EPR);
         }
-        T inH = __shfl_up_sync(FULL, lastH, 1);
-        const int pay = __shfl_up_sync(FULL, mypay, 1);
-        int inG = pay & ~0xFF00;
-        int nlet = (pay >> 8) & 0xFF;          // the letter of my NEXT row (sent one step ahead, see mypay)
-        if (lane == 0) {
-          inH = NINF;
-          inG = 0;
-          if (j > 0) { inH = s_inH[wib][t & (NBT - 1)]; inG = s_inG[wib][t & (NBT - 1)]; }
-          nlet = l1;
-        }
-        const int l3 = letter(x_lo + t + 3);   // lane 0's row three steps on (the other lanes load the same byte)
-        T sign[K];
 #pragma unroll
-        for (int k = 0; k < K; k++) sign[k] = s_sub[nlet * L + mlet[k]];
-
-        const int x = x_lo + t - lane;
-        // B (_alnchoice_B, _pw_internals.c:182-197): B_LOCAL anywhere, B_OVERLAP on x==0 or y==0,
-        // B_GLOBAL at (0,0) only
-        const bool rowb = (BT == BSQ_B_LOCAL) || (BT == BSQ_B_OVERLAP && x == 0);
-        const T brest = rowb ? ZERO : NINF;
-        const T bfirst = (rowb || (y0 == 0 && (BT == BSQ_B_OVERLAP || x == 0))) ? ZERO : NINF;
-        T left = inH, diag = prev_in;
-        int gI = inG;
-        uint32_t cw = 0u;
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-          const bool inb = (unsigned)(t - ta[k]) <= span[k];
-          const T up = Hup[k];
-          T H;
-          int fD, fI;
-          uint32_t nib;
-          if (k == 0 || BT != BSQ_B_GLOBAL)
-            bsq_k3_cell<S, GOS, true>(up, gD[k], left, gI, diag, sig[k], k == 0 ? bfirst : brest, go, ge, inb, H, fD, fI, nib);
-          else
-            bsq_k3_cell<S, GOS, false>(up, gD[k], left, gI, diag, sig[k], ZERO, go, ge, inb, H, fD, fI, nib);
-          cw |= nib << (4 * k);
-          gD[k] = fD; gI = fI; diag = up; left = H; Hup[k] = H;
-          Hend[k] = inb ? H : Hend[k];
-          if (BT == BSQ_B_LOCAL) { if (H > best[k < NB ? k : 0]) { best[k < NB ? k : 0] = H; bestx[k < NB ? k : 0] = x; } }
-        }
-        const bool active = (t >= lane) && (x <= x_hi);
-        if (active) {
-          prow[(long long)t * G] = (PU)cw;
-          if (lane == G - 1 && has_succ) Slab::put(slab + (long long)x * Slab::EPR, left, gI != 0, tag_out);
-          if (BT == BSQ_B_OVERLAP && x < n && km >= 0 && km < K) {   // column m above the last row (:380-390)
-            T c = NINF;
-#pragma unroll
-            for (int k = 0; k < K; k++) if (k == km) c = Hup[k];
-            if (c > NINF && bsq_better<T>(c, x - m, 0, bs, bk1, bk2)) { bs = c; bk1 = x - m; bk2 = 0; }
+        for (int ti = 0; ti < NBT; ti++) {
+          const int t = t0 + ti;           // steps past nsteps - 1 (the last group) are inactive for every lane
+          T inH = __shfl_up_sync(FULL, lastH, 1);
+          const int pay = __shfl_up_sync(FULL, mypay, 1);
+          int inG = pay & ~0xFF00;
+          int nlet = (pay >> 8) & 0xFF;        // the letter of my NEXT row (sent one step ahead, see mypay)
+          {
+            const T bh = s_inH[wib][ti];
+            const int bg = s_inG[wib][ti];
+            inH = lane0 ? (lane0in ? bh : NINF) : inH;
+            inG = lane0 ? (lane0in ? bg : 0) : inG;
+            nlet = lane0 ? l1 : nlet;
           }
-        }
-        lastH = left;
-        mypay = gI | (nlet << 8);
-        prev_in = inH;
-        curlet = nlet;
-        l1 = l2;
-        l2 = l3;
+          // lane 0's row three steps on (the other lanes load the same byte; only lane 0 uses it)
+          const int xr3 = x_lo + t + 3;
+          int l3 = 0;
+          if (xr3 <= nr) l3 = (int)*letp;          // xr3 >= 3
+          letp++;
+          T sign[K];
 #pragma unroll
-        for (int k = 0; k < K; k++) sig[k] = sign[k];
+          for (int k = 0; k < K; k++) sign[k] = sbase[nlet * Lr + mlet[k]];
+
+          const int x = x_lo + t - lane;
+          // B (_alnchoice_B, _pw_internals.c:182-197): B_LOCAL anywhere, B_OVERLAP on x==0 or y==0,
+          // B_GLOBAL at (0,0) only
+          const bool rowb = (BT == BSQ_B_LOCAL) || (BT == BSQ_B_OVERLAP && x == 0);
+          const T brest = rowb ? ZERO : NINF;
+          const T bfirst = (rowb || (y0 == 0 && (BT == BSQ_B_OVERLAP || x == 0))) ? ZERO : NINF;
+          T left = inH, diag = prev_in;
+          int gI = inG;
+          uint32_t cw = 0u;
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            const bool inb = (unsigned)(t - ta[k]) <= span[k];
+            const T up = Hup[k];
+            T H;
+            int fD, fI;
+            uint32_t nib;
+            if (k == 0 || BT != BSQ_B_GLOBAL)
+              bsq_k3_cell<S, GOS, true>(up, gD[k], left, gI, diag, sig[k], k == 0 ? bfirst : brest, gor, ger, inb, H, fD, fI, nib);
+            else
+              bsq_k3_cell<S, GOS, false>(up, gD[k], left, gI, diag, sig[k], ZERO, gor, ger, inb, H, fD, fI, nib);
+            cw |= nib << (4 * k);
+            gD[k] = fD; gI = fI; diag = up; left = H; Hup[k] = H;
+            Hend[k] = inb ? H : Hend[k];
+            if (BT == BSQ_B_LOCAL) { if (H > best[k < NB ? k : 0]) { best[k < NB ? k : 0] = H; bestx[k < NB ? k : 0] = x; } }
+          }
+          const bool active = (unsigned)(t - lane) <= (unsigned)(x_hi - x_lo);   // t >= lane and x <= x_hi
+          if (active) *pst = (PU)cw;                                   // a predicated store, no branch
+          if (active && put31) Slab::put(pslab, left, gI != 0, tag_out);
+          pst += G;
+          pslab += Slab::EPR;
+          if (BT == BSQ_B_OVERLAP) {
+            if (active && x < n && km >= 0 && km < K) {   // column m above the last row (:380-390)
+              T c = NINF;
+#pragma unroll
+              for (int k = 0; k < K; k++) if (k == km) c = Hup[k];
+              if (c > NINF && bsq_better<T>(c, x - m, 0, bs, bk1, bk2)) { bs = c; bk1 = x - m; bk2 = 0; }
+            }
+          }
+          lastH = left;
+          mypay = gI | (nlet << 8);
+          prev_in = inH;
+          curlet = nlet;
+          l1 = l2;
+          l2 = l3;
+#pragma unroll
+          for (int k = 0; k < K; k++) sig[k] = sign[k];
+        }
       }
       // end cell, _banded_find_optimal (_pw_internals.c:364-414)
       if (BT == BSQ_B_GLOBAL) {

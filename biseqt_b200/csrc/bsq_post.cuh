@@ -441,17 +441,18 @@ __global__ void __launch_bounds__(128) bsq_k2_walk_thread(const BsqTraceArgs A) 
 }
 
 // ---------------------------------------------------------------------------
-// K4c: the walk over K2 tables by a GROUP of GW lanes per pair (8: four pairs per warp, big
-// batches; 32: small batches).  The group stages a WINDOW of the table around the path -- the
-// units of BSQ_WALKC_NBLK blocks of steps below the current one, for the path's lane and its two
-// neighbours (a path drifts by a diagonal or two per block, a lane owns C of them) -- with
-// independent 16-byte loads (GW requests in flight instead of one: the thread-per-pair walker is
-// bound by the latency of a DRAM access per block on long pairs, 41 ms on config 4), ~100 bytes per
-// block instead of the whole 256 - 1024-byte row of blocks.  Then lane q examines cell (x-q, y-q) of the
-// current diagonal, a ballot finds how far the run of diagonal moves goes, those lanes emit
-// their M / S together, and only the op that ends the run is handled serially.
+// K4c: the walk over K2 tables by a GROUP of GW lanes per pair (32: a warp per pair, the default;
+// 8: four pairs per warp, measured slower).  The group stages a WINDOW of the table along the path
+// -- the units of the path's own lane for the BSQ_WALKC_NBLK blocks of steps at and below the
+// current one, 32 bytes per block instead of the 256 - 1024-byte row of blocks -- with independent
+// 16-byte loads (GW requests in flight instead of one: a thread-per-pair walker is bound by the
+// latency of a DRAM access per block on long pairs, 41 ms on config 4).  Then lane q examines cell
+// (x-q, y-q) of the current diagonal (same lane of the table, two steps further down each), a ballot
+// finds how far the run of diagonal moves goes, those lanes emit their M / S together, and only the
+// op that ends the run is handled serially.  A gap moves the path to the next diagonal; when that
+// belongs to the neighbouring lane the window is staged again (every few hundred ops).
 // ---------------------------------------------------------------------------
-#define BSQ_WALKC_NBLK 16
+#define BSQ_WALKC_NBLK 32
 #define BSQ_WALKC_WARPS 4
 
 template <int GOS, int GW>
@@ -459,11 +460,12 @@ __global__ void __launch_bounds__(32 * BSQ_WALKC_WARPS) bsq_k2_walk_coop(const B
   constexpr int PPW = 32 / GW;                               // pairs per warp
   constexpr int UW = BSQ_K2_UNIT_WORDS;
   BSQ_BAIL_IF_BAD(A);
-  __shared__ uint4 s_win[BSQ_WALKC_WARPS * PPW][BSQ_WALKC_NBLK * 3 * 2];   // [block][lane - wl0][half unit]
+  __shared__ uint4 s_win[BSQ_WALKC_WARPS * PPW][BSQ_WALKC_NBLK * 2];   // [block][half unit] of ONE lane
   const int wib = threadIdx.x >> 5;
   const int lane = threadIdx.x & (GW - 1);
   const int grp = (threadIdx.x & 31) / GW;
   const unsigned gmask = (GW == 32) ? 0xffffffffu : (((1u << GW) - 1u) << (grp * GW));
+  const unsigned lmask = (GW == 32) ? 0xffffffffu : ((1u << GW) - 1u);
   const int slot = wib * PPW + grp;
   const int p = blockIdx.x * (BSQ_WALKC_WARPS * PPW) + slot;
   if (p >= A.npairs) return;  // the whole group
@@ -485,24 +487,19 @@ __global__ void __launch_bounds__(32 * BSQ_WALKC_WARPS) bsq_k2_walk_coop(const B
   char* wr = A.slots + P.tx_slot + (long long)P.n + P.m;
   const int maxlen = P.n + P.m;
   const uint32_t* win = (const uint32_t*)s_win[slot];
-  int wlo = 1, whi = 0, wl0 = 0;                             // window: blocks [wlo, whi], lanes [wl0, wl0 + 2]
+  int wlo = 1, whi = 0, wl = -1;                             // window: blocks [wlo, whi] of lane wl
   uint32_t arrive = BSQ_MM;
   for (;;) {
     const int blk = rel / TB;
-    if (blk < wlo || blk > whi || l < wl0 || l > wl0 + 2) {  // stage the window below and around (blk, l)
+    if (blk < wlo || blk > whi || l != wl) {                 // stage the window at and below (blk, l)
       whi = blk;
       wlo = blk - BSQ_WALKC_NBLK + 1;
       wlo = wlo < 0 ? 0 : wlo;
-      wl0 = l - 1;
-      wl0 = wl0 < 0 ? 0 : (wl0 + 2 > G - 1 ? (G - 3 < 0 ? 0 : G - 3) : wl0);
-      const int nl = G < 3 ? G : 3;
-      const int nq = (whi - wlo + 1) * nl * 2;               // 16-byte quantities to fetch
+      wl = l;
+      const int nq = (whi - wlo + 1) * 2;                    // 16-byte quantities to fetch
       __syncwarp(gmask);
-      for (int k = lane; k < nq; k += GW) {
-        const int b = k / (nl * 2), r = k - b * (nl * 2), ll = r >> 1, h = r & 1;
-        s_win[slot][(b * 3 + ll) * 2 + h] =
-            *(const uint4*)(table + ((long long)(wlo + b) * G + wl0 + ll) * UW + 4 * h);
-      }
+      for (int k = lane; k < nq; k += GW)
+        s_win[slot][k] = *(const uint4*)(table + ((long long)(wlo + (k >> 1)) * G + wl) * UW + 4 * (k & 1));
       __syncwarp(gmask);
     }
     // lane q looks at (x-q, y-q): the same diagonal (lane l, nibble c/2), step rel - 2q
@@ -510,12 +507,12 @@ __global__ void __launch_bounds__(32 * BSQ_WALKC_WARPS) bsq_k2_walk_coop(const B
     const bool valid = (relq >= 0) && (blkq >= wlo) && (x - lane >= 0) && (y - lane >= 0) && (len + lane < maxlen);
     const int hc = c >> 1;
     uint32_t nib = 0u;
-    if (valid) nib = (win[((blkq - wlo) * 3 + (l - wl0)) * UW + iq * WPS + (hc >> 3)] >> (4 * (hc & 7))) & 0xFu;
+    if (valid) nib = (win[(blkq - wlo) * UW + iq * WPS + (hc >> 3)] >> (4 * (hc & 7))) & 0xFu;
     const uint32_t opq = (lane == 0 && arrive != BSQ_MM) ? bsq_gap_base_t<GOS>(nib, arrive) : bsq_lowest(nib);
-    const unsigned vmask = __ballot_sync(gmask, valid) >> (grp * GW);
-    const unsigned mmask = (__ballot_sync(gmask, valid && opq == BSQ_MM) >> (grp * GW)) & (GW == 32 ? 0xffffffffu : ((1u << GW) - 1u));
-    const int nv = __popc(vmask & (GW == 32 ? 0xffffffffu : ((1u << GW) - 1u)));   // valid cells form a prefix
-    const unsigned inv = ~mmask & (GW == 32 ? 0xffffffffu : ((1u << GW) - 1u));
+    const unsigned vmask = (__ballot_sync(gmask, valid) >> (grp * GW)) & lmask;
+    const unsigned mmask = (__ballot_sync(gmask, valid && opq == BSQ_MM) >> (grp * GW)) & lmask;
+    const int nv = __popc(vmask);                            // valid cells form a prefix
+    const unsigned inv = ~mmask & lmask;
     const int run = inv == 0u ? GW : (__ffs((int)inv) - 1);
     if (nv == 0) break;                                      // len == maxlen (or nothing left)
     if (lane < run) {

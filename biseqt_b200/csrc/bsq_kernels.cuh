@@ -561,7 +561,7 @@ __device__ __forceinline__ void bsq_k2_step_fast(
     int (&bests)[BLOCAL == 1 ? C : 1], typename S::T edgeH, int edgeF,
     const typename S::T* s_sub, int L, unsigned long long comb, const uint8_t* oseq,
     const uint8_t* mseq, int s, int d0, int fixc, typename S::T go, typename S::T ge,
-    uint32_t* pout, const int kstep) {
+    uint32_t* pout, const int kstep, const int n, const int m) {
   // pout: the lane's staging slot of this step in shared memory (words BSQ_FILL_THREADS apart)
   typedef typename S::T T;
   constexpr int HC = C / 2;
@@ -595,9 +595,14 @@ __device__ __forceinline__ void bsq_k2_step_fast(
       const uint32_t off = (sh >= 0 ? (cw >> (sh >= 0 ? sh : 0)) : (cw << (sh < 0 ? -sh : 0))) & (0xFu << SH);
       sig = *(const T*)((const char*)s_sub + off);
     } else {
+      // (a lane's diagonals past the band are computed and thrown away: their cells may lie outside
+      // the table, so the letter indices are clamped -- found by the AddressSanitizer run of the
+      // emulator build, tools/asan_cases.py)
       const int d = d0 + c;
-      const int x = (s + d) >> 1, y = (s - d) >> 1;
-      sig = s_sub[(int)oseq[x - 1] * L + (int)mseq[y - 1]];
+      int xi = ((s + d) >> 1) - 1, yi = ((s - d) >> 1) - 1;
+      xi = xi < 0 ? 0 : (xi > n - 1 ? n - 1 : xi);
+      yi = yi < 0 ? 0 : (yi > m - 1 ? m - 1 : yi);
+      sig = s_sub[(int)oseq[xi] * L + (int)mseq[yi]];
     }
     if constexpr (S::IS_INT) {
       // Integer interior cell, the issue-bound inner loop of the banded fill.  In this phase the state
@@ -842,19 +847,19 @@ __global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
         if (l == 0) { eH = NINF; eF = 0; }
         if (packed)
           bsq_k2_step_fast<S, C, BLOCAL, GOS, 0, true>(H, fD, fI, best, bests, eH, eF, s_fast, Lt, ow | mw, oseq,
-                                                       mseq, s, d0, fixc, go, ge, pe, BSQ_K2_KSTEP(s, s0));
+                                                       mseq, s, d0, fixc, go, ge, pe, BSQ_K2_KSTEP(s, s0), n, m);
         else
           bsq_k2_step_fast<S, C, BLOCAL, GOS, 0, false>(H, fD, fI, best, bests, eH, eF, s_fast, Lt, 0ull, oseq,
-                                                        mseq, s, d0, fixc, go, ge, pe, BSQ_K2_KSTEP(s, s0));
+                                                        mseq, s, d0, fixc, go, ge, pe, BSQ_K2_KSTEP(s, s0), n, m);
         eH = __shfl_down_sync(gmask, H[0], 1, G);
         eF = __shfl_down_sync(gmask, fI[0], 1, G);
         if (l == G - 1) { eH = NINF; eF = 0; }
         if (packed)
           bsq_k2_step_fast<S, C, BLOCAL, GOS, 1, true>(H, fD, fI, best, bests, eH, eF, s_fast, Lt, ow_odd | mw,
-                                                       oseq, mseq, s + 1, d0, fixc, go, ge, po, BSQ_K2_KSTEP(s + 1, s0));
+                                                       oseq, mseq, s + 1, d0, fixc, go, ge, po, BSQ_K2_KSTEP(s + 1, s0), n, m);
         else
           bsq_k2_step_fast<S, C, BLOCAL, GOS, 1, false>(H, fD, fI, best, bests, eH, eF, s_fast, Lt, 0ull, oseq,
-                                                        mseq, s + 1, d0, fixc, go, ge, po, BSQ_K2_KSTEP(s + 1, s0));
+                                                        mseq, s + 1, d0, fixc, go, ge, po, BSQ_K2_KSTEP(s + 1, s0), n, m);
         if (packed) {
           ow = ow_odd;
           onx = no << 2;

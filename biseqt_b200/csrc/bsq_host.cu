@@ -603,7 +603,9 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
         it.lo = lo; it.hi = hi;
         const int K = BSQ_K3_CFGS[it.cfg - BSQ_K2_NCFG].K, G = 32, BW = G * K;
         const int64_t nstrips = ((int64_t)m + BW) / BW;
-        const int64_t tstride = std::min<int64_t>((int64_t)n + 1, W + BW - 1) + G - 1;
+        // time steps per strip, padded to whole groups of 8: K3L stores every step of a group
+        // unconditionally (slots of idle lanes and of the padding are never read)
+        const int64_t tstride = (std::min<int64_t>((int64_t)n + 1, W + BW - 1) + G - 1 + 7) / 8 * 8;
         it.words = nstrips * tstride * G * (K / 2) / 4;
         it.aux = (int32_t)tstride;
         it.cells = count_cells(BSQ_BANDED_MODE, n, m, lo, hi);
@@ -1358,7 +1360,8 @@ int launch_fill(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, size_t* evi, 
     BSQ_CK(ctx, cudaMemsetAsync(B.colh.p, 0, (P.dtype == BSQ_DTYPE_I32 ? 8 : 16) * (size_t)ch.k3_slab, stream));
     // workers: twice the strips in flight with full pipelines (the rest would only poll), at
     // most 16 warps per SM; any number is deadlock-free because strips are claimed in order
-    const int wpb = BSQ_K3_THREADS / 32;
+    // K3 blocks hold two independent strip workers, K3L blocks one worker and its feeder warp
+    const int wpb = (ch.cfg - BSQ_K2_NCFG == 0) ? 1 : BSQ_K3_THREADS / 32;
     int64_t workers = std::min<int64_t>(ch.k3_strips, std::max<int64_t>(2 * ch.k3_active, 64));
     workers = std::min<int64_t>(workers, (int64_t)ctx->sms * 16);
     const int grid = (int)std::max<int64_t>((workers + wpb - 1) / wpb, 1);

@@ -82,6 +82,10 @@ template <> struct BsqK3Slab<ScI32> {
     BSQ_ST_CG(row, (unsigned long long)(unsigned)H | ((unsigned long long)(opens ? 1u : 0u) << 32) |
                        ((unsigned long long)tag << 33));
   }
+  // the same entry from the flag word the kernels carry (S::flag(): 0 / 1) and tag2 = 2 * tag
+  static __device__ __forceinline__ void put_g(unsigned long long* row, int H, int g, unsigned tag2) {
+    BSQ_ST_CG((uint2*)row, make_uint2((unsigned)H, tag2 + (unsigned)g));
+  }
   static __device__ __forceinline__ Raw load(const unsigned long long* row) { Raw r; r.e0 = BSQ_LD_CG(row); return r; }
   static __device__ __forceinline__ bool decode(const Raw& r, unsigned tag, int& H, int& opens) {
     H = (int)(unsigned)r.e0;
@@ -96,6 +100,10 @@ template <> struct BsqK3Slab<ScF64> {
     const unsigned long long b = (unsigned long long)__double_as_longlong(H);
     BSQ_ST_CG(row, (b & 0xffffffffull) | ((unsigned long long)tag << 32));
     BSQ_ST_CG(row + 1, (b >> 32) | ((unsigned long long)(2u * tag + (opens ? 1u : 0u)) << 32));
+  }
+  static __device__ __forceinline__ void put_g(unsigned long long* row, double H, int g, unsigned tag2) {  // g: 0 / 0x3FF00000
+    BSQ_ST_CG((uint2*)row, make_uint2((unsigned)__double2loint(H), tag2 >> 1));
+    BSQ_ST_CG((uint2*)(row + 1), make_uint2((unsigned)__double2hiint(H), tag2 + ((unsigned)g >> 29)));
   }
   static __device__ __forceinline__ Raw load(const unsigned long long* row) {
     Raw r; r.e0 = BSQ_LD_CG(row); r.e1 = BSQ_LD_CG(row + 1); return r;
@@ -474,19 +482,76 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3_fill(const BsqFillArgs 
 // one 1 kb x 1 kb STD GLOBAL pair, planned as a full-width band).  With strips of BW columns, rows
 // of lag R per lane and a boundary hand-over every B rows, strip j+1 starts
 //     (BW + B) / R + 31  steps
-// after strip j, and the whole fill takes m / BW of those lags.  bsq_k3_fill pays 71 "careful"
-// (gated, branchy) steps of ~1360 cycles per strip of 128 columns on config 5 -- 49 us per strip,
-// 366 ms in all, 33 warps busy.  Here: 64-column strips (K = 2), one row per step, hand-over every
-// 8 rows, and ONE uniform branch-free step (every cell gated by a precomputed step range, so there
-// are no phases and nothing diverges): ~100 steps of ~100 cycles per strip, twice the strips in
-// flight.  Origin letters are loaded by lane 0 only and travel down the lanes with the skew, one
-// step ahead of the row they belong to, so the score lookup never sits on the dependency chain.
+// after strip j, and the whole fill takes m / BW of those lags: only the FIRST ~100 steps of every
+// strip (its ramp: lanes entering the band one after the other) are on the critical path, each run
+// by a lone warp that issues in order.  So the step is built for instruction count and has no
+// branch (a lone warp pays 25 - 50 cycles to resolve one):
+//   * 64-column strips (K = 2), one row per step, hand-over every 8 rows;
+//   * groups of 8 unrolled steps in two flavours picked by one uniform test per group -- LEAN
+//     (every lane is above the lower end of its columns for the whole group and the group holds
+//     no cell where an alignment may begin: cells are gated by "t >= first step" alone, pointer
+//     bytes are stored unconditionally -- slots of idle lanes exist in the layout and are never
+//     read --, no end-cell bookkeeping) and FULL (everything gated; first group of a GLOBAL pair,
+//     the first rows of OVERLAP, the tail of every strip);
+//   * the shuffle is a rotation: lane 31 sends the NEXT boundary value (staged in shared memory by
+//     the batch) instead of its own, so lane 0 needs no special case;
+//   * the origin letter of a row enters with the boundary batch and rides the skew one step
+//     ahead of its row, pre-shifted into a byte offset that is OR-ed with the lane's column base
+//     in a transposed, power-of-two-padded score table: one LOP3 + one LDS per cell, off the chain.
 // Same pointer layout ([strip][t][lane], one byte = two nibbles) and slab protocol as bsq_k3_fill
 // with K = 2, so bsq_k3_walk<2> serves both.
 //   replaces: dptable_solve's fill loop pw.c:59-110 over _xlim/_ylim
 //   (_pw_internals.c:116-153) + _banded_find_optimal (:364-414)
 // ===========================================================================
 #define BSQ_K3L_BATCH 8
+// flavours of a group of BSQ_K3L_BATCH steps
+#define BSQ_K3L_FULL 0    // everything gated and tracked
+#define BSQ_K3L_RAMP 1    // columns still beginning: gated by their first step
+#define BSQ_K3L_INNER 2   // every column inside: nothing gated
+#define BSQ_K3L_TAIL 3    // columns ending: gated by their last step, last values kept
+template <int V> struct BsqInt { static constexpr int value = V; };
+
+#ifdef BSQ_SIMT_EMU
+#define BSQ_SH_ALIGN(n)
+#else
+#define BSQ_SH_ALIGN(n) __align__(n)
+#endif
+
+// score table entry at byte offset `a` (device: `a` already holds the table's shared-window address)
+template <class T>
+__device__ __forceinline__ T bsq_lds_off(const T* table, uint32_t a) {
+#ifdef BSQ_SIMT_EMU
+  return *(const T*)((const char*)table + a);
+#else
+  (void)table;
+  T v;
+  if constexpr (sizeof(T) == 8) asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  else asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+#endif
+}
+
+// one cell, ungated.  HB: 0 = no B candidate, 1 = bval (0 or -inf), 2 = B allowed everywhere
+template <class S, int GOS, int HB>
+__device__ __forceinline__ void bsq_k3l_cell(typename S::T up, int gD, typename S::T left, int gI,
+                                             typename S::T diag, typename S::T sig, typename S::T bval,
+                                             typename S::T go, typename S::T ge, typename S::T& h,
+                                             int& fD, int& fI, uint32_t& nib) {
+  typedef typename S::T T;
+  if constexpr (S::IS_INT) {
+    int nB, nD, nI, nM;
+    bsq_cell_i32<GOS, HB != 0, HB == 2>(up, gD, left, gI, diag, sig, bval, go, ge, h, nB, nD, nI, nM);
+    nib = (uint32_t)(15 - (nB + 2 * nD + 4 * nI + 8 * nM));
+    fD = bsq_gapflag_i32<GOS>(nD, nB, nI, nM);
+    fI = bsq_gapflag_i32<GOS>(nI, nB, nD, nM);
+  } else {
+    bool eB, eD, eI, eM;
+    bsq_cell2<S, GOS, HB != 0>(up, gD, left, gI, diag, sig, HB == 2 ? (T)0 : bval, go, ge, h, eB, eD, eI, eM);
+    nib = (eB ? BSQ_MB : 0u) | (eD ? BSQ_MD : 0u) | (eI ? BSQ_MI : 0u) | (eM ? BSQ_MM : 0u);
+    fD = bsq_gapflag<S, GOS>(eD, eB, eI, eM);
+    fI = bsq_gapflag<S, GOS>(eI, eB, eD, eM);
+  }
+}
 
 template <class S, int BT, int GOS>
 __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3l_fill(const BsqFillArgs A) {
@@ -495,15 +560,34 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3l_fill(const BsqFillArgs
   typedef BsqK3Slab<S> Slab;
   constexpr int K = 2, G = 32, BW = G * K, NBT = BSQ_K3L_BATCH;
   constexpr int NB = (BT == BSQ_B_LOCAL) ? K : 1;
+  // the word lanes pass along: open/extend flag of the sender's right cell | (origin letter of
+  // the receiver's NEXT row) << LSH, i.e. the letter as a byte offset into a score-table column
+  constexpr int LSH = (sizeof(T) == 8) ? 3 : 2;
+  constexpr int LETMASK = (BSQ_MAX_L - 1) << LSH;
   BSQ_BAIL_IF_BAD(A);
-  __shared__ T s_sub[BSQ_MAX_L * BSQ_MAX_L];
-  __shared__ T s_inH[BSQ_K3_THREADS / 32][NBT];
-  __shared__ int s_inG[BSQ_K3_THREADS / 32][NBT];
+  // transposed and padded: entry (origin letter o, mutant letter c) at [(c << lp) | o], 2^lp >= L
+  __shared__ BSQ_SH_ALIGN(BSQ_MAX_L * BSQ_MAX_L * sizeof(T)) T s_subT[BSQ_MAX_L * BSQ_MAX_L];
+  // boundary ring, filled by the feeder warp: slot (r mod RING) holds row x_lo + r of the strip's
+  // left boundary column: H of (row, Y - 1) and its flag | the letter of row + 1
+  constexpr int RING = 8 * NBT;
+  __shared__ T s_rH[RING];
+  __shared__ int s_rP[RING];
+  __shared__ int s_ctl[4];        // [0] claimed strip, [1] rows staged (feeder), [2] groups consumed (worker)
+  volatile int* ctl = s_ctl;
   const int L = A.L;
-  for (int i = threadIdx.x; i < L * L; i += blockDim.x) s_sub[i] = ((const T*)A.subst)[i];
+  int lp = 0;
+  while ((1 << lp) < L) lp++;
+  for (int i = threadIdx.x; i < L * L; i += blockDim.x) s_subT[((i % L) << lp) | (i / L)] = ((const T*)A.subst)[i];
   __syncthreads();
+#ifdef BSQ_SIMT_EMU
+  const uint32_t tbase = 0u;
+#else
+  const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(s_subT);
+#endif
 
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int srcl = (lane + G - 1) & (G - 1);
+  const bool lane31 = (lane == G - 1);
   const unsigned FULL = 0xffffffffu;
   const T NINF = S::ninf();
   const T ZERO = (T)0;
@@ -512,10 +596,16 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3l_fill(const BsqFillArgs
   int p = 0;
 
   for (;;) {
-    int g = 0;
-    if (lane == 0) g = atomicAdd(A.counter, 1);
-    g = __shfl_sync(FULL, g, 0);
+    __syncthreads();                 // both warps are done with the previous strip and its ring
+    if (threadIdx.x == 0) { s_ctl[0] = atomicAdd(A.counter, 1); s_ctl[1] = 0; s_ctl[2] = 0; }
+    __syncthreads();
+    const int g = s_ctl[0];
     if (g >= A.k3_total) break;
+#ifdef BSQ_K3_PROFILE
+    long long pf_claim, pf_ready = 0, pf_wait = 0;
+    int pf_polls = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pf_claim));
+#endif
     while (g >= A.k3[p].strip_base + A.k3[p].nstrips) p++;  // claims only grow
     const BsqPair P = A.pairs[p];
     const BsqK3Pair Q = A.k3[p];
@@ -533,7 +623,55 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3l_fill(const BsqFillArgs
     int pred_lo = Y - BW + dmin;
     pred_lo = pred_lo < 0 ? 0 : pred_lo;
     unsigned long long* slab = slab_all + Q.slab_off * Slab::EPR;
-    const unsigned tag_in = (unsigned)j, tag_out = (unsigned)j + 1u;
+    const unsigned tag_in = (unsigned)j, tag2_out = 2u * ((unsigned)j + 1u);
+
+    if (wib != 0) {
+      // The feeder warp: polls the predecessor's boundary column in the slab (32 rows per round,
+      // rows past pred_hi lie outside the band; strip 0 has no predecessor: pred_hi = -1), stages
+      // the contiguous valid prefix with the origin letters into the ring and publishes the count.
+      // The worker warp never touches global memory for its inputs.
+      if (x_lo <= x_hi) {
+        const int nsteps = (x_hi - x_lo + 1) + G - 1;
+        const int nrows = ((nsteps + NBT - 1) / NBT) * NBT;
+        const uint8_t* oseq = A.codes + P.o_off;
+        const int nm1 = n > 0 ? n - 1 : 0;
+        int r0 = 0;
+        int idle = 0;
+        while (r0 < nrows) {
+          const int r = r0 + lane;
+          const int xr = x_lo + r;
+          const bool need = (r < nrows) && (xr <= pred_hi);
+          const int let = (int)oseq[xr < nm1 ? xr : nm1];        // the letter of row xr + 1 (rows past n: unused)
+          T bH = NINF;
+          int bF = 0;
+          bool ok = true;
+          if (need) ok = Slab::decode(Slab::load(slab + (long long)xr * Slab::EPR), tag_in, bH, bF);
+          const unsigned okm = __ballot_sync(FULL, ok);
+          int c = (okm == FULL) ? 32 : (__ffs((int)~okm) - 1);
+          const int room = __shfl_sync(FULL, ctl[2], 0) * NBT + RING - r0;   // slots the worker has released (one read: uniform)
+          c = c < room ? c : room;
+          c = c < nrows - r0 ? c : nrows - r0;
+          if (c > 0) {
+            if (lane < c) {
+              s_rH[r & (RING - 1)] = need ? bH : NINF;
+              s_rP[r & (RING - 1)] = (need ? S::flag(bF == 0) : 0) | (let << LSH);
+            }
+            __threadfence_block();
+            __syncwarp();
+            r0 += c;
+            if (lane == 0) ctl[1] = r0;
+            idle = 0;
+          } else {
+#ifdef BSQ_SIMT_EMU
+            emu::yield();
+#else
+            if (++idle > 64) __nanosleep(100);
+#endif
+          }
+        }
+      }
+      continue;
+    }
 
     T bs = NINF;                     // lane's best end-cell candidate of this strip
     int bk1 = BSQ_INT_MAX, bk2 = BSQ_INT_MAX;
@@ -544,10 +682,16 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3l_fill(const BsqFillArgs
       int ta[K];                     // column k is inside band, table and strip rows for steps ta .. ta + span
       unsigned span[K];
       int xlast[K];                  // its last such row (or -1)
+      uint32_t colb[K];              // byte address of its score-table column
+      int tend[K];                   // ta + span (or -1)
+      int thi = 0x7fffffff;          // the last step at which every existing column of the strip is still inside
+      int tmax_a = 0;                // the first step at which every existing column has begun
+      bool allcols = true;           // all 64 columns exist
 #pragma unroll
       for (int k = 0; k < K; k++) {
         const int y = y0 + k;
         mlet[k] = (y >= 1 && y <= m) ? (int)A.codes[P.m_off + y - 1] : 0;
+        colb[k] = tbase + ((uint32_t)mlet[k] << (lp + LSH));
         int xa = y + dmin, xb = y + dmax;
         xa = xa < x_lo ? x_lo : xa;
         xb = xb > x_hi ? x_hi : xb;
@@ -555,19 +699,33 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3l_fill(const BsqFillArgs
         ta[k] = any ? (xa - x_lo + lane) : 0x40000000;
         span[k] = any ? (unsigned)(xb - xa) : 0u;
         xlast[k] = any ? xb : -1;
+        tend[k] = any ? ta[k] + (xb - xa) : -1;
+        if (any) { thi = min(thi, tend[k]); tmax_a = max(tmax_a, ta[k]); }
+        allcols = allcols && any;
       }
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) {
+        thi = min(thi, __shfl_xor_sync(FULL, thi, d));
+        tmax_a = max(tmax_a, __shfl_xor_sync(FULL, tmax_a, d));
+      }
+      allcols = __all_sync(FULL, allcols);
+      // LEAN groups: no cell where an alignment may begin other than "everywhere" (B_LOCAL), no
+      // column m above the last row (B_OVERLAP's other end), every cell below its column's last step
+      bool lean_strip = true;
+      int tlo_lean = 0;
+      if (BT == BSQ_B_GLOBAL) tlo_lean = (j == 0) ? NBT : 0;                       // (0, 0)
+      if (BT == BSQ_B_OVERLAP) { lean_strip = (j > 0) && (Y + BW - 1 < m); tlo_lean = (x_lo == 0) ? G : 0; }  // y == 0, x == 0
       const int km = m - y0;         // which of my columns is column m (if in [0,K))
       T Hup[K], Hend[K];
       int gD[K];
       T best[NB];
-      int bestx[NB];
+      int bestt[NB];
 #pragma unroll
       for (int k = 0; k < K; k++) { Hup[k] = NINF; Hend[k] = NINF; gD[k] = 0; }
 #pragma unroll
-      for (int k = 0; k < NB; k++) { best[k] = NINF; bestx[k] = 0; }
-      T lastH = NINF;                // my right column's cell of the previous step
-      int mypay = 0;                 // its open/extend flag word | (letter of my NEXT row) << 8: what my right
-                                     // neighbour receives one step later is the letter of the row after that
+      for (int k = 0; k < NB; k++) { best[k] = NINF; bestt[k] = 0; }
+      T lastH = NINF;                // what I send: my right column's cell of the previous step (lane 31: the
+      int mypay = 0;                 // next boundary value), and its flag | letter word
       T prev_in = NINF;
       if (lane == 0 && j > 0) {      // (x_lo - 1, Y - 1): the diagonal neighbour of my first cell
         const int xd = x_lo - 1;
@@ -578,135 +736,133 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3l_fill(const BsqFillArgs
         }
       }
       const int nsteps = (x_hi - x_lo + 1) + G - 1;
-      PU* prow = (PU*)(A.ptr + P.ptr_off) + (long long)j * P.s0 * G + lane;
       const uint8_t* oseq = A.codes + P.o_off;
-      auto letter = [&](int xr) -> int { return (xr >= 1 && xr <= n) ? (int)oseq[xr - 1] : 0; };
-      // lane 0's letter pipeline: curlet = letter of its row at step t, l1 / l2 those of steps t+1, t+2
-      int curlet = (lane == 0) ? letter(x_lo) : 0;
-      if (lane == 0) mypay = curlet << 8;     // lane 1 starts one step later on the same row
-      int l1 = letter(x_lo + 1), l2 = letter(x_lo + 2);
       T sig[K];
+      {
+        const int curlet = (lane == 0 && x_lo >= 1) ? (int)oseq[x_lo - 1] : 0;   // x_lo <= n
 #pragma unroll
-      for (int k = 0; k < K; k++) sig[k] = s_sub[curlet * L + mlet[k]];
-      typename Slab::Raw nx = {};    // prefetched (raw) boundary entry of row x_lo + (next batch) + lane
-      bool nx_have = false;
+        for (int k = 0; k < K; k++) sig[k] = s_subT[(mlet[k] << lp) | curlet];
+      }
+      T* rH = s_rH;                  // ring slots of the current group
+      int* rP = s_rP;
 
-      // The step body is straight-line code: a lone warp pays 25 - 50 cycles for every branch it has to
-      // resolve (ncu source view of the first version: 5 branches, ~200 of a step's ~450 cycles), so
-      // stores are predicated instead of guarded, the boundary batch sits at the top of a group of NBT
-      // unrolled steps instead of behind a per-step test, pointers advance instead of being recomputed,
-      // and the kernel parameters the loop needs live in registers (the compiler would re-read the
-      // constant bank every step to save registers nobody else wants: one warp per scheduler).
-      const uint8_t* letp = oseq + (x_lo + 2);             // &o[(x_lo + t + 3) - 1] at t = 0
-      PU* pst = prow;                                      // prow + t * G
-      unsigned long long* pslab = slab + (long long)(x_lo - lane) * Slab::EPR;   // slab + x * EPR
-      const bool put31 = (lane == G - 1) && has_succ;
-      const bool lane0 = (lane == 0), lane0in = lane0 && (j > 0);
-      const T* sbase = s_sub;
-      int Lr = L, nr = n;
+      PU* pst = (PU*)(A.ptr + P.ptr_off) + (long long)j * P.s0 * G + lane;       // + t * G
+      unsigned long long* pslab = slab + (long long)(x_lo - lane) * Slab::EPR;     // slab + x * EPR
+      const bool put31 = lane31 && has_succ;
       T gor = go, ger = ge;
 #ifndef BSQ_SIMT_EMU
-      asm volatile("" : "+r"(Lr), "+r"(nr));
+      // keep the loop's scalars in registers (the compiler would re-read the constant bank every
+      // step to save registers nobody else wants: one warp per scheduler)
       if constexpr (S::IS_INT) asm volatile("" : "+r"(gor), "+r"(ger));
       else asm volatile("" : "+d"(gor), "+d"(ger));
-      asm volatile("" : "+l"(letp), "+l"(pst), "+l"(pslab), "+l"(sbase));
 #endif
-      for (int t0 = 0; t0 < nsteps; t0 += NBT) {
-        if (j > 0) {
-          // boundary values of rows x_lo + t0 .. x_lo + t0 + NBT - 1 (lane i < NBT: row xr), fetched one
-          // batch ahead; rows past pred_hi lie outside the band
-          const int xr = x_lo + t0 + lane;
-          const bool mine = lane < NBT;
-          const bool need = mine && (xr <= pred_hi);
-          T bH = NINF;
-          int bF = 0;
-          bool ok = !need || (nx_have && Slab::decode(nx, tag_in, bH, bF));
-          unsigned ns = 32;
-          while (!__all_sync(FULL, ok)) {
-            if (!ok) {
-              ok = Slab::decode(Slab::load(slab + (long long)xr * Slab::EPR), tag_in, bH, bF);
-              if (!ok) { BSQ_BACKOFF(ns); if (ns < 256) ns *= 2; }
-            }
-          }
-          if (mine) {
-            s_inH[wib][lane] = need ? bH : NINF;
-            s_inG[wib][lane] = need ? S::flag(bF == 0) : 0;
-          }
-          __syncwarp();
-          const int xn = xr + NBT;
-          nx_have = mine && (xn <= pred_hi);
-          if (nx_have) nx = Slab::load(slab + (long long)xn * Slab::EPR);
-        }
+
+      auto group = [&](const int t0, auto flavour) {
+        constexpr int FL = decltype(flavour)::value;
+        constexpr bool FULLG = (FL == BSQ_K3L_FULL);
 #pragma unroll
         for (int ti = 0; ti < NBT; ti++) {
           const int t = t0 + ti;           // steps past nsteps - 1 (the last group) are inactive for every lane
-          T inH = __shfl_up_sync(FULL, lastH, 1);
-          const int pay = __shfl_up_sync(FULL, mypay, 1);
-          int inG = pay & ~0xFF00;
-          int nlet = (pay >> 8) & 0xFF;        // the letter of my NEXT row (sent one step ahead, see mypay)
-          {
-            const T bh = s_inH[wib][ti];
-            const int bg = s_inG[wib][ti];
-            inH = lane0 ? (lane0in ? bh : NINF) : inH;
-            inG = lane0 ? (lane0in ? bg : 0) : inG;
-            nlet = lane0 ? l1 : nlet;
-          }
-          // lane 0's row three steps on (the other lanes load the same byte; only lane 0 uses it)
-          const int xr3 = x_lo + t + 3;
-          int l3 = 0;
-          if (xr3 <= nr) l3 = (int)*letp;          // xr3 >= 3
-          letp++;
+          const T inH = __shfl_sync(FULL, lastH, srcl);
+          const int pay = __shfl_sync(FULL, mypay, srcl);
+          const uint32_t lo = (uint32_t)(pay & LETMASK);
+          int gI = pay & ~LETMASK;
           T sign[K];
 #pragma unroll
-          for (int k = 0; k < K; k++) sign[k] = sbase[nlet * Lr + mlet[k]];
-
-          const int x = x_lo + t - lane;
+          for (int k = 0; k < K; k++) sign[k] = bsq_lds_off<T>(s_subT, lo | colb[k]);
           // B (_alnchoice_B, _pw_internals.c:182-197): B_LOCAL anywhere, B_OVERLAP on x==0 or y==0,
           // B_GLOBAL at (0,0) only
-          const bool rowb = (BT == BSQ_B_LOCAL) || (BT == BSQ_B_OVERLAP && x == 0);
-          const T brest = rowb ? ZERO : NINF;
-          const T bfirst = (rowb || (y0 == 0 && (BT == BSQ_B_OVERLAP || x == 0))) ? ZERO : NINF;
+          const int x = x_lo + t - lane;
+          T bfirst = NINF, brest = NINF;
+          if (FULLG) {
+            const bool rowb = (BT == BSQ_B_LOCAL) || (BT == BSQ_B_OVERLAP && x == 0);
+            brest = rowb ? ZERO : NINF;
+            bfirst = (rowb || (y0 == 0 && (BT == BSQ_B_OVERLAP || x == 0))) ? ZERO : NINF;
+          }
           T left = inH, diag = prev_in;
-          int gI = inG;
           uint32_t cw = 0u;
 #pragma unroll
           for (int k = 0; k < K; k++) {
-            const bool inb = (unsigned)(t - ta[k]) <= span[k];
+            const bool inb = FL == BSQ_K3L_RAMP ? (t >= ta[k]) : FL == BSQ_K3L_TAIL ? (t <= tend[k])
+                           : FL == BSQ_K3L_INNER ? true : ((unsigned)(t - ta[k]) <= span[k]);
             const T up = Hup[k];
-            T H;
+            T h;
             int fD, fI;
             uint32_t nib;
-            if (k == 0 || BT != BSQ_B_GLOBAL)
-              bsq_k3_cell<S, GOS, true>(up, gD[k], left, gI, diag, sig[k], k == 0 ? bfirst : brest, gor, ger, inb, H, fD, fI, nib);
+            if (!FULLG)
+              bsq_k3l_cell<S, GOS, (BT == BSQ_B_LOCAL) ? 2 : 0>(up, gD[k], left, gI, diag, sig[k], ZERO, gor, ger, h, fD, fI, nib);
+            else if (k == 0 || BT != BSQ_B_GLOBAL)
+              bsq_k3l_cell<S, GOS, 1>(up, gD[k], left, gI, diag, sig[k], k == 0 ? bfirst : brest, gor, ger, h, fD, fI, nib);
             else
-              bsq_k3_cell<S, GOS, false>(up, gD[k], left, gI, diag, sig[k], ZERO, gor, ger, inb, H, fD, fI, nib);
+              bsq_k3l_cell<S, GOS, 0>(up, gD[k], left, gI, diag, sig[k], ZERO, gor, ger, h, fD, fI, nib);
+            const T H = (FL == BSQ_K3L_INNER) ? h : (inb ? h : NINF);
             cw |= nib << (4 * k);
             gD[k] = fD; gI = fI; diag = up; left = H; Hup[k] = H;
-            Hend[k] = inb ? H : Hend[k];
-            if (BT == BSQ_B_LOCAL) { if (H > best[k < NB ? k : 0]) { best[k < NB ? k : 0] = H; bestx[k < NB ? k : 0] = x; } }
+            if (FULLG || FL == BSQ_K3L_TAIL) Hend[k] = inb ? H : Hend[k];
+            if (BT == BSQ_B_LOCAL) { if (H > best[k < NB ? k : 0]) { best[k < NB ? k : 0] = H; bestt[k < NB ? k : 0] = t; } }
           }
-          const bool active = (unsigned)(t - lane) <= (unsigned)(x_hi - x_lo);   // t >= lane and x <= x_hi
-          if (active) *pst = (PU)cw;                                   // a predicated store, no branch
-          if (active && put31) Slab::put(pslab, left, gI != 0, tag_out);
-          pst += G;
-          pslab += Slab::EPR;
-          if (BT == BSQ_B_OVERLAP) {
-            if (active && x < n && km >= 0 && km < K) {   // column m above the last row (:380-390)
-              T c = NINF;
+          pst[ti * G] = (PU)cw;        // idle lanes write slots nobody reads (the stride is padded to whole groups)
+          bool pput;                   // lane 31 is on a row of the strip: t >= 31 and x <= x_hi
+          if (FL == BSQ_K3L_RAMP) pput = put31 && (t >= G - 1);
+          else if (FL == BSQ_K3L_INNER) pput = put31;
+          else if (FL == BSQ_K3L_TAIL) pput = put31 && (t < nsteps);
+          else {
+            const bool active = (unsigned)(t - lane) <= (unsigned)(x_hi - x_lo);   // t >= lane and x <= x_hi
+            pput = put31 && active;
+            if (BT == BSQ_B_OVERLAP) {
+              if (active && x < n && km >= 0 && km < K) {   // column m above the last row (:380-390)
+                T c = NINF;
 #pragma unroll
-              for (int k = 0; k < K; k++) if (k == km) c = Hup[k];
-              if (c > NINF && bsq_better<T>(c, x - m, 0, bs, bk1, bk2)) { bs = c; bk1 = x - m; bk2 = 0; }
+                for (int k = 0; k < K; k++) if (k == km) c = Hup[k];
+                if (c > NINF && bsq_better<T>(c, x - m, 0, bs, bk1, bk2)) { bs = c; bk1 = x - m; bk2 = 0; }
+              }
             }
           }
+          if (pput) Slab::put_g(pslab + ti * Slab::EPR, left, gI, tag2_out);
           lastH = left;
-          mypay = gI | (nlet << 8);
+          mypay = (int)lo | gI;
+          if (ti + 1 < NBT) {
+            if (lane31) { lastH = rH[ti + 1]; mypay = rP[ti + 1]; }
+          }
           prev_in = inH;
-          curlet = nlet;
-          l1 = l2;
-          l2 = l3;
 #pragma unroll
           for (int k = 0; k < K; k++) sig[k] = sign[k];
         }
+      };
+
+      for (int t0 = 0; t0 < nsteps; t0 += NBT) {
+        {
+          // boundary values of rows x_lo + t0 .. x_lo + t0 + NBT - 1: wait for the feeder
+          const int want = t0 + NBT;
+#ifdef BSQ_K3_PROFILE
+          const long long pf_c0 = clock64();
+#endif
+          while (ctl[1] < want) {
+#ifdef BSQ_SIMT_EMU
+            emu::yield();
+#endif
+#ifdef BSQ_K3_PROFILE
+            pf_polls++;
+#endif
+          }
+#ifdef BSQ_K3_PROFILE
+          pf_wait += clock64() - pf_c0;
+          if (t0 == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pf_ready));
+#endif
+          rH = s_rH + (t0 & (RING - 1));
+          rP = s_rP + (t0 & (RING - 1));
+          if (lane31) { lastH = rH[0]; mypay = rP[0]; }
+        }
+        const bool early = t0 + NBT - 1 < thi;      // every column still above its last step
+        const bool begun = allcols && t0 >= tmax_a; // every column past its first
+        if (!(lean_strip && t0 >= tlo_lean) || !(early || begun)) group(t0, BsqInt<BSQ_K3L_FULL>{});
+        else if (!begun) group(t0, BsqInt<BSQ_K3L_RAMP>{});
+        else if (early) group(t0, BsqInt<BSQ_K3L_INNER>{});
+        else group(t0, BsqInt<BSQ_K3L_TAIL>{});
+        pst += NBT * G;
+        pslab += NBT * Slab::EPR;
+        __syncwarp();                          // lane 31 has read the group's slots
+        if (lane == 0) ctl[2] = t0 / NBT + 1;
       }
       // end cell, _banded_find_optimal (_pw_internals.c:364-414)
       if (BT == BSQ_B_GLOBAL) {
@@ -722,8 +878,9 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3l_fill(const BsqFillArgs
 #pragma unroll
         for (int k = 0; k < NB; k++) {
           const T c = best[k];
-          const int d = bestx[k] - (y0 + k);
-          if (c > NINF && bsq_better<T>(c, d, bestx[k], bs, bk1, bk2)) { bs = c; bk1 = d; bk2 = bestx[k]; }
+          const int bx = x_lo + bestt[k] - lane;
+          const int d = bx - (y0 + k);
+          if (c > NINF && bsq_better<T>(c, d, bx, bs, bk1, bk2)) { bs = c; bk1 = d; bk2 = bx; }
         }
       }
     }
@@ -736,7 +893,9 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3l_fill(const BsqFillArgs
       r.k1 = bk1;
       r.k2 = bk2;
 #ifdef BSQ_K3_PROFILE
-      r.t_claim = r.t_ready = r.t_end = 0; r.wait_clk = 0; r.polls = 0; r.sm = 0;
+      r.t_claim = pf_claim; r.t_ready = pf_ready; r.wait_clk = pf_wait; r.polls = pf_polls;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(r.t_end));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(r.sm));
 #endif
       A.k3_res[g] = r;
       __threadfence();

@@ -18,8 +18,6 @@ constants, but the DP fill and traceback run in ``libbsqgpu.so``.
 One ``Aligner`` is a GPU batch of one pair; for throughput use
 :class:`biseqt_b200.batch.Engine` directly.
 """
-import re
-from collections import namedtuple
 
 import numpy as np
 
@@ -242,175 +240,145 @@ class Aligner(object):
                                          self.ge_score)
 
 
-_ANSI = {'green': '\033[32m', 'red': '\033[31m'}
-_ANSI_RESET = '\033[0m'
-
-
-def _colored(text, color=None):
-    # the reference uses termcolor.colored (pw.py:523-524); same escape codes
-    if color is None:
-        return text
-    return _ANSI[color] + text + _ANSI_RESET
+_PAINT = {'M': '\033[32m', 'S': '\033[31m'}    # matches green, substitutions red
+_RESET = '\033[0m'
 
 
 class Alignment(object):
-    """A pairwise alignment (``biseqt/pw.py:322-572``): transcript over
-    ``MSID`` plus start positions; pure host-side value object."""
+    """What ``Aligner.traceback()`` returns: a transcript over ``MSID`` anchored at a start position
+    on each sequence.  A host-side value object with the interface of the reference's
+    (``biseqt/pw.py:322-572``: same constructor, same assertions, same text output -- checked against
+    outputs recorded from the reference, ``tests/test_alignment_golden.py``); the batched
+    equivalents of its three computations run on the device (``BatchResult.stats``).
+
+    One rendering detail is kept on purpose: with ``colored=True`` EVERY column ends in the reset
+    sequence, coloured or not, as termcolor 1.1 (the reference's dependency) emits it.
+    """
+
+    _ADVANCES = {'origin': 'MSD', 'mutant': 'MSI'}
 
     def __init__(self, origin, mutant, transcript, score=None,
                  origin_start=0, mutant_start=0):
         assert isinstance(origin, Sequence) and isinstance(mutant, Sequence)
         assert origin.alphabet == mutant.alphabet
+        transcript = str(transcript)
+        assert len(transcript) > 0 and not transcript.strip('MSID')
+        assert origin_start >= 0 and mutant_start >= 0
+        assert origin_start + self.projected_len(transcript, on='origin') <= len(origin)
+        assert mutant_start + self.projected_len(transcript, on='mutant') <= len(mutant)
         self.alphabet = origin.alphabet
-        assert all(c in 'MSID' for c in transcript)
-        assert len(transcript) > 0
-        origin_end = origin_start + self.projected_len(transcript, on='origin')
-        mutant_end = mutant_start + self.projected_len(transcript, on='mutant')
-        assert 0 <= origin_start and origin_end <= len(origin)
-        assert 0 <= mutant_start and mutant_end <= len(mutant)
-        self.transcript = str(transcript)
         self.origin, self.mutant = origin, mutant
         self.origin_start, self.mutant_start = origin_start, mutant_start
+        self.transcript = transcript
         self.score = score
 
-    def __str__(self):
-        return self.render_term(term_width=float('+inf'), margin=0, colored=0)
+    def _key(self):
+        return (self.origin, self.mutant, self.transcript, self.origin_start, self.mutant_start)
 
     def __eq__(self, other):
         assert isinstance(other, Alignment)
-        return other.origin == self.origin and \
-            other.mutant == self.mutant and \
-            other.transcript == self.transcript and \
-            other.origin_start == self.origin_start and \
-            other.mutant_start == self.mutant_start
+        return self._key() == other._key()
 
     def __ne__(self, other):
-        return not self.__eq__(other)
+        return not self == other
 
     __hash__ = None
 
+    def __str__(self):
+        return self.render_term(term_width=float('inf'), margin=0, colored=False)
+
     @classmethod
     def projected_len(cls, transcript, on='origin'):
-        assert on in ['origin', 'mutant']
-        ops = 'MSD' if on == 'origin' else 'MSI'
-        return sum(int(op in ops) for op in transcript)
+        """Letters of ``origin`` (``mutant``) the transcript consumes (pw.py:367-389)."""
+        assert on in cls._ADVANCES
+        return sum(transcript.count(op) for op in cls._ADVANCES[on])
 
     def calculate_score(self, subst_scores, go_score, ge_score):
-        score = 0.
-        i, j = self.origin_start, self.mutant_start
-        for match in re.finditer(r'(.)\1*', self.transcript):
-            run = match.group(0)
-            op, num = run[0], len(run)
-            if op in 'MS':
-                score += sum(
-                    subst_scores[self.origin[i + k]][self.mutant[j + k]]
-                    for k in range(num)
-                )
-                i, j = i + num, j + num
+        """Score of the transcript under the given scores (pw.py:391-428): substitution scores
+        letter by letter, ``go_score + len * ge_score`` per maximal run of one gap kind; runs are
+        accumulated in transcript order, each summed on its own, like the reference does."""
+        ops = np.frombuffer(self.transcript.encode('ascii'), dtype=np.uint8)
+        on_o = (ops != ord('I')).astype(np.int64)
+        on_m = (ops != ord('D')).astype(np.int64)
+        at_o = self.origin_start + np.cumsum(on_o) - on_o      # position on origin BEFORE each op
+        at_m = self.mutant_start + np.cumsum(on_m) - on_m
+        cuts = np.flatnonzero(np.diff(ops)) + 1                 # run boundaries
+        total = 0.
+        for a, b in zip(np.concatenate(([0], cuts)), np.concatenate((cuts, [len(ops)]))):
+            if chr(ops[a]) in 'MS':
+                run = 0
+                for k in range(a, b):
+                    run += subst_scores[self.origin[int(at_o[k])]][self.mutant[int(at_m[k])]]
+                total += run
             else:
-                assert op in 'ID'
-                score += go_score + ge_score * num
-                if op == 'I':
-                    j = j + num
-                else:
-                    i = i + num
-        return score
+                total += go_score + ge_score * int(b - a)
+        return total
 
     def truncate_to_match(self):
-        tx_start = 0
-        origin_start, mutant_start = self.origin_start, self.mutant_start
-        tx_end = len(self.transcript) - 1
-        while self.transcript[tx_start] != 'M':
-            if self.transcript[tx_start] in 'DS':
-                origin_start += 1
-            if self.transcript[tx_start] in 'IS':
-                mutant_start += 1
-            tx_start += 1
-        while self.transcript[tx_end] != 'M':
-            tx_end -= 1
-        if tx_start < tx_end:
-            tx = self.transcript[tx_start:tx_end + 1]
-            return Alignment(self.origin, self.mutant, tx,
-                             origin_start=origin_start,
-                             mutant_start=mutant_start)
-        else:
+        """The alignment between its first and its last match (pw.py:430-448); ``None`` when fewer
+        than two matches are left.  (No match at all: ``IndexError``, as in the reference.)"""
+        first, last = self.transcript.find('M'), self.transcript.rfind('M')
+        if first < 0:
+            raise IndexError('no match in transcript')
+        if first >= last:
             return None
+        skipped = self.transcript[:first]
+        return Alignment(self.origin, self.mutant, self.transcript[first:last + 1],
+                         origin_start=self.origin_start + self.projected_len(skipped, on='origin'),
+                         mutant_start=self.mutant_start + self.projected_len(skipped, on='mutant'))
+
+    def _columns(self, margin):
+        """The rendered columns in order: ``(op or None, position on origin, position on mutant)``;
+        ``None`` columns are the context shown around the alignment."""
+        width = self.alphabet._letlen
+        i, j = self.origin_start, self.mutant_start
+        lead = min(margin, max(i, j) * width)
+        for k in range(lead):
+            yield None, i - lead + k, j - lead + k
+        for op in self.transcript:
+            yield op, i, j
+            i += op != 'I'
+            j += op != 'D'
+        trail = min(margin, max(len(self.origin) - i, len(self.mutant) - j) * width)
+        for k in range(trail):
+            yield None, i + k, j + k
 
     def render_term(self, term_width=120, margin=0, colored=True):
+        """Two-line text rendering, wrapped at ``term_width`` (pw.py:450-572): every line pair
+        opens with the positions it starts at, gaps show as ``-``, context beyond either sequence
+        as ``.``; a column is only ever broken off BEFORE it is written, when the pair already
+        reaches ``term_width``."""
         assert term_width >= 30
         assert margin >= 0
-        letlen = self.alphabet._letlen
-        Carriage = namedtuple('carriage',
-                              ['pos', 'o_idx', 'm_idx', 'o_line', 'm_line'])
-        term_color = {'M': 'green', 'S': 'red'}
+        width = self.alphabet._letlen
+        seqs = (self.origin, self.mutant)
+        shown = ('MSD', 'MSI')
+        pairs = []                   # finished line pairs
+        rows, used = None, 0         # the open pair: two lists of pieces, visible length so far
 
-        def start_line(o_idx, m_idx):
-            o_line = 'origin[%d]: ' % o_idx
-            m_line = 'mutant[%d]: ' % m_idx
-            pos = max(len(o_line), len(m_line))
-            assert pos <= term_width, \
-                'Alignment preamble does not fit in width %d' % term_width
-            return Carriage(pos=pos, o_idx=o_idx, m_idx=m_idx,
-                            o_line=o_line, m_line=m_line)
+        def close():
+            texts = [''.join(r) for r in rows]
+            size = max(len(t) for t in texts)
+            pairs.append('%s\n%s\n' % tuple(t.rjust(size) for t in texts))
 
-        def carriage_flush(carriage):
-            line_len = max(len(carriage.o_line), len(carriage.m_line))
-            return '%s\n%s\n' % (carriage.o_line.rjust(line_len),
-                                 carriage.m_line.rjust(line_len))
-
-        def carriage_fwd(carriage, op=None):
-            gap = '.' * letlen if op is None else '-' * letlen
-            o_contents, m_contents = gap, gap
-            if op is None:
-                if 0 <= carriage.o_idx < len(self.origin):
-                    o_contents = self.alphabet[self.origin[carriage.o_idx]]
-                if 0 <= carriage.m_idx < len(self.mutant):
-                    m_contents = self.alphabet[self.mutant[carriage.m_idx]]
-            else:
-                assert op in 'MSID'
-                if op in 'MSD':
-                    o_contents = self.alphabet[self.origin[carriage.o_idx]]
-                if op in 'MSI':
-                    m_contents = self.alphabet[self.mutant[carriage.m_idx]]
-            length = len(o_contents)
-            assert length == len(m_contents)
-            color = term_color.get(op) if colored else None
-            o_contents = _colored(o_contents, color)
-            m_contents = _colored(m_contents, color)
-            output = ''
-            if carriage.pos >= term_width:
-                output += carriage_flush(carriage)
-                carriage = start_line(carriage.o_idx, carriage.m_idx)
-            return output, Carriage(
-                pos=carriage.pos + length,
-                o_idx=carriage.o_idx + int(op is None or op in 'MSD'),
-                m_idx=carriage.m_idx + int(op is None or op in 'MSI'),
-                o_line=carriage.o_line + o_contents,
-                m_line=carriage.m_line + m_contents
-            )
-
-        def pre_margin(o_idx, m_idx):
-            margin_len = min(margin, max(o_idx, m_idx) * letlen)
-            carriage = start_line(o_idx - margin_len, m_idx - margin_len)
-            output = ''
-            for i in range(margin_len):
-                out, carriage = carriage_fwd(carriage, op=None)
-                output += out
-            return output, carriage
-
-        def post_margin(carriage):
-            output = ''
-            margin_len = min(margin,
-                             max((len(self.origin) - carriage.o_idx) * letlen,
-                                 (len(self.mutant) - carriage.m_idx) * letlen))
-            for i in range(margin_len):
-                out, carriage = carriage_fwd(carriage, op=None)
-                output += out
-            return output + carriage_flush(carriage)
-
-        output, carriage = pre_margin(self.origin_start, self.mutant_start)
-        for op in self.transcript:
-            out, carriage = carriage_fwd(carriage, op=op)
-            output += out
-        output += post_margin(carriage)
-        return output
+        for op, i, j in self._columns(margin):
+            if rows is None or used >= term_width:
+                if rows is not None:
+                    close()
+                rows = [['origin[%d]: ' % i], ['mutant[%d]: ' % j]]
+                used = max(len(rows[0][0]), len(rows[1][0]))
+                assert used <= term_width, \
+                    'Alignment preamble does not fit in width %d' % term_width
+            for row, seq, at, ops in zip(rows, seqs, (i, j), shown):
+                if op is None:
+                    text = self.alphabet[seq[at]] if 0 <= at < len(seq) else '.' * width
+                else:
+                    text = self.alphabet[seq[at]] if op in ops else '-' * width
+                if colored:
+                    text = _PAINT.get(op, '') + text + _RESET
+                row.append(text)
+            used += width
+        if rows is None:             # cannot happen: a transcript is never empty
+            rows = [['origin[%d]: ' % self.origin_start], ['mutant[%d]: ' % self.mutant_start]]
+        close()
+        return ''.join(pairs)

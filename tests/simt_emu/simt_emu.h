@@ -14,6 +14,7 @@
 // the biseqt_b200 package on its own, and is ~10^4x slower than a GPU.
 #pragma once
 #include <ucontext.h>
+#include <dlfcn.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -31,6 +32,7 @@ struct dim3 {
 
 struct uint4 { unsigned x, y, z, w; };
 struct uint2 { unsigned x, y; };
+inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }
 
 namespace emu {
 
@@ -49,6 +51,7 @@ struct Lane {
   ucontext_t ctx;
   char* stack = nullptr;
   bool done = false;
+  void* site = nullptr;     // return address of the last yield (deadlock report)
 };
 
 struct Block {
@@ -67,8 +70,9 @@ struct Block {
 
 inline Block*& cur_block() { static Block* b = nullptr; return b; }
 
-inline void yield() {
+__attribute__((noinline)) inline void yield() {
   Block* b = cur_block();
+  b->lanes[b->cur].site = __builtin_return_address(0);
   swapcontext(&b->lanes[b->cur].ctx, &b->sched);
 }
 
@@ -138,6 +142,7 @@ inline void run_block(Block& B) {
     makecontext(&L.ctx, (void (*)())trampoline, 0);
   }
   int ndone = 0;
+  int stalled = 0;
   while (ndone < B.nthreads) {
     uint64_t before = B.progress;
     ndone = 0;
@@ -147,10 +152,20 @@ inline void run_block(Block& B) {
       swapcontext(&B.sched, &B.lanes[i].ctx);
       if (B.lanes[i].done) ndone++;
     }
-    if (ndone < B.nthreads && B.progress == before) {
+    // a pass without a completed collective is not yet a deadlock: lanes may be polling memory
+    // another warp of the block writes between its own collectives (emu::yield() in a spin loop)
+    if (ndone < B.nthreads && B.progress == before) stalled++; else stalled = 0;
+    if (stalled > 20000) {
       fprintf(stderr, "simt_emu: deadlock in block (%u): %d/%d lanes done, no progress "
               "(divergent collective or exited lane inside a full-mask shuffle)\n",
               B.bidx.x, ndone, B.nthreads);
+      for (int i = 0; i < B.nthreads; i++) {      // where every parked lane sits (addr2line -e <lib> <offset>)
+        if (B.lanes[i].done || (i > 0 && B.lanes[i].site == B.lanes[i - 1].site)) continue;
+        Dl_info di;
+        if (dladdr(B.lanes[i].site, &di) && di.dli_fbase)
+          fprintf(stderr, "  lane %d.. parked at %s+0x%lx\n", i, di.dli_fname,
+                  (unsigned long)((char*)B.lanes[i].site - (char*)di.dli_fbase));
+      }
       abort();
     }
   }

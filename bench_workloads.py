@@ -118,15 +118,17 @@ def make(kind, npairs, seed):
                     o_off=o_off, o_len=o_len, m_off=m_off, m_len=m_len, dmin=dmin, dmax=dmax,
                     desc='%d pair(s) %d x ~%d bp, B_GLOBAL, radius 2048, %s' % (
                         npairs, n, n, 'log-odds' if kind.endswith('logodds') else 'int +2/-3 go-4 ge-2'))
-    if kind == 'c1':
-        # configs[0]: one 1 kb x 1 kb STD GLOBAL pair, log-odds scores (go_score = 0)
+    if kind in ('c1', 'c1n'):
+        # configs[0]: one 1 kb x 1 kb STD GLOBAL pair, log-odds scores (go_score = 0); c1n: npairs of them
         n = 1000
-        o = st.rand_seqs(rng, 1, n, L)
+        count = npairs if kind == 'c1n' else 1
+        o = st.rand_seqs(rng, count, n, L)
         mut, mlen = st.mutate_batch(rng, o, L, 0.1, 0.1, 0.1)
-        codes, o_off, o_len, m_off, m_len = _pack_rows(o, [n], mut, mlen)
+        codes, o_off, o_len, m_off, m_len = _pack_rows(o, [n] * count, mut, mlen)
         S, go, ge = st.log_odds_scores(L, 0.1, 0.1, 0.1)
         return dict(kind=kind, mode=STD_MODE, type=GLOBAL, subst=S, go=go, ge=ge, codes=codes,
-                    o_off=o_off, o_len=o_len, m_off=m_off, m_len=m_len, desc='1 pair 1 kb x ~1 kb STD GLOBAL log-odds')
+                    o_off=o_off, o_len=o_len, m_off=m_off, m_len=m_len,
+                    desc='%d pair(s) 1 kb x ~1 kb STD GLOBAL log-odds' % count)
     raise ValueError(kind)
 
 

@@ -73,8 +73,11 @@ struct BsqUniform {
 // K3 (strip-pipelined wide bands): what a pair needs beyond BsqPair
 struct BsqK3Pair {
   long long slab_off;    // first entry of this pair's boundary-column slab (n+1 entries)
-  int strip_base;        // index of this pair's strip 0 in the chunk's strip list
+  int strip_base;        // index of this pair's strip 0 in the chunk's per-strip result array
   int nstrips;           // ceil((m+1) / (32*K))
+};
+struct BsqK3Item {       // one entry of a chunk's strip work list: strip `strip` of the chunk's pair `pair`
+  int pair, strip;
 };
 struct BsqK3Res {        // best end-cell candidate found inside one strip
   double score;
@@ -113,6 +116,8 @@ struct BsqFillArgs {
   // boundary-column slab per pair (BsqK3Pair.slab_off rows of 1 (I32) / 2 (F64) 64-bit
   // self-validating entries), zeroed before the launch
   const BsqK3Pair* k3;
+  const BsqK3Item* k3_order;  // [k3_total] the work list: strips of all pairs interleaved (strip j of every
+                              // pair before strip j+1 of any), so that all pairs' pipelines run at once
   int k3_total;          // strips in the chunk
   int* k3_done;          // [npairs] strips finished per pair, zeroed before the launch
   BsqK3Res* k3_res;      // [k3_total]

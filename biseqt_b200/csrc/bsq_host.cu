@@ -63,18 +63,18 @@ struct PinBuf {
 
 struct BufSet {  // everything one batch needs in HBM
   DevBuf codes, pairs, ptr, slots, packed, score, ex, ey, sx, sy, status, txlen, txoff, tiles,
-      subst, counters, colh, colf, total, k3pairs, k3sync, k3res, ooff, moff, flags, codes2, packed2;
+      subst, counters, colh, colf, total, k3pairs, k3sync, k3res, k3order, ooff, moff, flags, codes2, packed2;
   PinBuf hpairs, hsmall;
   size_t bytes() const {  // HBM currently held
     const DevBuf* all[] = {&codes, &pairs, &ptr, &slots, &packed, &score, &ex, &ey, &sx, &sy, &status,
-                           &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff, &flags, &codes2, &packed2};
+                           &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &k3order, &ooff, &moff, &flags, &codes2, &packed2};
     size_t n = 0;
     for (const DevBuf* b : all) n += b->cap;
     return n;
   }
   void release() {
     DevBuf* all[] = {&codes, &pairs, &ptr, &slots, &packed, &score, &ex, &ey, &sx, &sy, &status,
-                     &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &ooff, &moff, &flags, &codes2, &packed2};
+                     &txlen, &txoff, &tiles, &subst, &counters, &colh, &colf, &total, &k3pairs, &k3sync, &k3res, &k3order, &ooff, &moff, &flags, &codes2, &packed2};
     for (DevBuf* b : all) b->release();
     hpairs.release();
     hsmall.release();
@@ -93,6 +93,7 @@ struct Chunk {
   int64_t k3_strips = 0; // K3: strips in the chunk's work list
   int64_t k3_slab = 0;   // K3: boundary-column slab entries (sum of n+1)
   int64_t k3_active = 0; // K3: strips in flight when every pair's pipeline is full
+  int64_t k3_order_off = 0;  // K3: where the chunk's strip work list starts in Plan::k3order
 };
 
 // largest pointer table (words) of a batch that is aligned in caller order instead of sorted:
@@ -121,6 +122,7 @@ struct Hooks {
   int target_chunks = -1;       // BSQ_TARGET_CHUNKS: chunks to cut a batch into (< 0: automatic)
   int k2_cfg = -1;              // BSQ_K2_CFG: forced K2 geometry
   int k3_cfg = -1;              // BSQ_K3_CFG: forced K3 geometry
+  int std_band_max = 4096;      // BSQ_STD_BAND_MAX: most STD GLOBAL pairs of a batch planned as full-width bands
   char trace_kernel = 0;        // BSQ_TRACE_KERNEL: 't'hread / 'w'arp / 'n'arrow / 'p'air-thread (banded)
   size_t arena_cap_bytes = 0;   // BSQ_ARENA_CAP_BYTES: upper bound for the pointer arena
   void read_env() {
@@ -136,6 +138,7 @@ struct Hooks {
     target_chunks = (int)num("BSQ_TARGET_CHUNKS", -1);
     k2_cfg = (int)num("BSQ_K2_CFG", -1);
     k3_cfg = (int)num("BSQ_K3_CFG", -1);
+    std_band_max = (int)num("BSQ_STD_BAND_MAX", 4096);
     const char* tk = getenv("BSQ_TRACE_KERNEL");
     trace_kernel = tk ? tk[0] : 0;
     arena_cap_bytes = (size_t)num("BSQ_ARENA_CAP_BYTES", 0);
@@ -182,6 +185,7 @@ struct Plan {
   const int64_t* src_o_off = nullptr;
   const int64_t* src_m_off = nullptr;
   std::vector<BsqK3Pair> k3;  // per pair record (processing order); empty when no pair uses K3
+  std::vector<BsqK3Item> k3order;  // the strip work lists of the K3 chunks, one after the other
   int64_t k3_max_strips = 0, k3_max_slab = 0, k3_max_pairs = 0;  // maxima over chunks
 };
 
@@ -464,14 +468,16 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   if (!std::isfinite(prm->go) || !std::isfinite(prm->ge)) return fail(ctx, BSQ_ERR_ARG, "go/ge must be finite");
   if ((prm->flags & BSQ_F_CODES_2BIT) && L > 4) return fail(ctx, BSQ_ERR_ARG, "BSQ_F_CODES_2BIT needs an alphabet of at most 4 letters");
   if (prm->flags & ~(BSQ_F_CODES_2BIT | BSQ_F_TX_2BIT)) return fail(ctx, BSQ_ERR_ARG, "unknown bits in params.flags");
-  // One (or a handful of) big STD GLOBAL problems -- the reference's own calling pattern, config 1 --
-  // are latency bound on K1 (one warp walks the whole table, two passes for 1 kb).  GLOBAL is
-  // B_GLOBAL with the full band [-m, n] (same B rule, same end cell (n,m), same traceback:
-  // _pw_internals.c:165-181 vs :182-197, :309-315 vs :366-378), so they are planned as wide bands
-  // and take the strip pipeline (K3L): every 64 columns another warp.
+  // One big STD GLOBAL problem -- the reference's own calling pattern, config 1 -- or a few thousand
+  // of them are latency bound on K1 (one warp walks the whole table, two passes for 1 kb: 3.3 ms for
+  // 16 pairs, 10 ms for 1024).  GLOBAL is B_GLOBAL with the full band [-m, n] (same B rule, same end
+  // cell (n,m), same traceback: _pw_internals.c:165-181 vs :182-197, :309-315 vs :366-378), so they
+  // are planned as wide bands and take the strip pipeline (K3L): every 64 columns another warp,
+  // the pipelines of all pairs side by side (0.19 ms for 16 pairs, 2.6 ms for 1024).  Beyond a few
+  // thousand pairs K1 has enough warps of its own.
   bsq_params eff = *prm;
   bool std_as_band = false;
-  if (prm->mode == BSQ_STD_MODE && prm->type == BSQ_GLOBAL && N >= 1 && N <= 8 && !ctx->hooks.no_std_band) {
+  if (prm->mode == BSQ_STD_MODE && prm->type == BSQ_GLOBAL && N >= 1 && N <= ctx->hooks.std_band_max && !ctx->hooks.no_std_band) {
     std_as_band = true;
     for (int64_t i = 0; i < N; i++) if (o_len[i] < 256 || m_len[i] < 256) std_as_band = false;
   }
@@ -555,11 +561,11 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   P.pairs = nullptr;
   const Hooks& hk = ctx->hooks;
   const bool force_k3 = hk.force_k3 || std_as_band;
-  // strip geometry: a few wide-band pairs are bound by the dependency chain and take the latency form
-  // (cfg 0, bsq_k3l_fill: config 5 fills in 274 ms against 367 ms, config 1 -- a full-width band -- in
-  // 0.32 ms against 3.04 ms on K1); many of them are bound by throughput: cfg 1, 4 columns x 2 rows
-  // per lane and step
-  const int k3_cfg = (hk.k3_cfg >= 0 && hk.k3_cfg < BSQ_K3_NCFG) ? hk.k3_cfg : (N <= 8 ? 0 : 1);
+  // strip geometry: cfg 0 (bsq_k3l_fill, 64-column strips, a worker and a feeder warp per strip) for
+  // every plan -- config 5 fills in 118 ms against 367 ms with cfg 1, config 1 (a full-width band) in
+  // 0.2 ms against 3.04 ms on K1, and it also wins on throughput (10 pairs of config 5: 1.35 s against
+  // 3.39 s).  cfg 1 / 2 (bsq_k3_fill, 4 / 8 columns x 2 rows per lane and step) stay selectable.
+  const int k3_cfg = (hk.k3_cfg >= 0 && hk.k3_cfg < BSQ_K3_NCFG) ? hk.k3_cfg : 0;
   // K1h (two short problems per lane group, packed 16-bit arithmetic): what the scores and
   // the alignment type must satisfy; the shape conditions are per pair (PlanItem.lo for STD)
   double duo_maxabs = std::fabs(prm->go) + std::fabs(prm->ge);
@@ -1155,6 +1161,26 @@ int make_plan(bsq_ctx* ctx, Plan& P, PinBuf& hpairs, const bsq_params* prm, int6
   }
   cur.idx_hi = N;
   if (cur.count > 0) close_chunk(cur);
+  // K3 work lists: strip j of every pair of the chunk before strip j+1 of any, so that the strip
+  // pipelines of all its pairs run side by side (claimed in list order: a strip's predecessor is
+  // always taken before it).  Pairs by falling strip count: level j is a prefix of that order.
+  P.k3order.clear();
+  if (!P.k3.empty()) {
+    std::vector<int> by_strips;
+    for (Chunk& ch : P.chunks) {
+      if (!chunk_is_k3(ch)) continue;
+      ch.k3_order_off = (int64_t)P.k3order.size();
+      by_strips.resize((size_t)ch.count);
+      for (int64_t i = 0; i < ch.count; i++) by_strips[(size_t)i] = (int)i;
+      const BsqK3Pair* kp = P.k3.data() + ch.first;
+      std::stable_sort(by_strips.begin(), by_strips.end(), [&](int a, int b) { return kp[a].nstrips > kp[b].nstrips; });
+      size_t live = by_strips.size();
+      for (int j = 0; live > 0; j++) {
+        while (live > 0 && kp[by_strips[live - 1]].nstrips <= j) live--;
+        for (size_t i = 0; i < live; i++) P.k3order.push_back(BsqK3Item{by_strips[i], j});
+      }
+    }
+  }
   if (!P.chunks.empty()) P.chunks.front().idx_lo = 0;
   P.total_words = global_words;
   P.slot_bytes = slot;
@@ -1284,10 +1310,12 @@ int stage_k3(bsq_ctx* ctx, BufSet& B, const Plan& P, cudaStream_t st) {
   const bool ok = B.k3pairs.ensure(sizeof(BsqK3Pair) * P.k3.size()) &&
                   B.k3sync.ensure(4 * (size_t)(P.k3_max_pairs + 1)) &&
                   B.k3res.ensure(sizeof(BsqK3Res) * (size_t)(P.k3_max_strips + 1)) &&
+                  B.k3order.ensure(sizeof(BsqK3Item) * (P.k3order.size() + 1)) &&
                   B.colh.ensure(16 * (size_t)(P.k3_max_slab + 1));
   if (!ok) return fail(ctx, BSQ_ERR_NOMEM, "device allocation failed (wide-band strips)");
   BSQ_CK(ctx, cudaMemcpyAsync(B.k3pairs.p, P.k3.data(), sizeof(BsqK3Pair) * P.k3.size(), cudaMemcpyHostToDevice, st));
-  ctx->tm.h2d_bytes += (int64_t)(sizeof(BsqK3Pair) * P.k3.size());
+  BSQ_CK(ctx, cudaMemcpyAsync(B.k3order.p, P.k3order.data(), sizeof(BsqK3Item) * P.k3order.size(), cudaMemcpyHostToDevice, st));
+  ctx->tm.h2d_bytes += (int64_t)(sizeof(BsqK3Pair) * P.k3.size() + sizeof(BsqK3Item) * P.k3order.size());
   return BSQ_SUCCESS;
 }
 
@@ -1352,6 +1380,7 @@ int launch_fill(bsq_ctx* ctx, BufSet& B, const Plan& P, size_t ci, size_t* evi, 
   A.bad = B.flags.as<int>();
   if (chunk_is_k3(ch)) {
     A.k3 = B.k3pairs.as<BsqK3Pair>() + ch.first;
+    A.k3_order = B.k3order.as<BsqK3Item>() + ch.k3_order_off;
     A.k3_total = (int)ch.k3_strips;
     A.k3_done = B.k3sync.as<int>();
     A.k3_res = B.k3res.as<BsqK3Res>();

@@ -12,9 +12,9 @@
 // word is needed: an entry is either the old one or completely the new one), and
 // fetches them 32 rows at a time, one batch ahead.  Successive strips thus run as
 // a software pipeline across the SMs: about (W + 32K) / 32K strips are in flight.  Strips of all pairs of a
-// chunk form ONE ordered work list claimed with an atomic counter -- a strip's
-// predecessor is therefore always held by a resident warp (no deadlock) and
-// several wide pairs overlap without a drain in between.
+// chunk form ONE ordered work list claimed with an atomic counter, strip j of every pair before
+// strip j+1 of any (BsqFillArgs::k3_order) -- a strip's predecessor is therefore always held by a
+// resident warp (no deadlock) and the pipelines of all pairs run side by side.
 //
 // The single-pair case is bound by the dependency chain, not by ALU issue: the
 // last strip cannot finish before ~m * (1 + 1/K) row steps have elapsed.
@@ -138,7 +138,6 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3_fill(const BsqFillArgs 
   const T ZERO = (T)0;
   const T go = S::go(A), ge = S::ge(A);
   unsigned long long* slab_all = (unsigned long long*)A.col_h;
-  int p = 0;
 
   for (;;) {
     int g = 0;
@@ -150,10 +149,10 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3_fill(const BsqFillArgs 
     int pf_polls = 0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pf_claim));
 #endif
-    while (g >= A.k3[p].strip_base + A.k3[p].nstrips) p++;  // claims only grow
+    const BsqK3Item item = A.k3_order[g];   // a strip's predecessor is always earlier in the list
+    const int p = item.pair, j = item.strip;
     const BsqPair P = A.pairs[p];
     const BsqK3Pair Q = A.k3[p];
-    const int j = g - Q.strip_base;
     const int n = P.n, m = P.m, dmin = P.dmin, dmax = P.dmax;
     const int Wm1 = dmax - dmin;
     const int Y = j * BW;
@@ -443,7 +442,7 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3_fill(const BsqFillArgs 
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(r.t_end));
       asm volatile("mov.u32 %0, %%smid;" : "=r"(r.sm));
 #endif
-      A.k3_res[g] = r;
+      A.k3_res[Q.strip_base + j] = r;
       __threadfence();
       last = (atomicAdd(A.k3_done + p, 1) == Q.nstrips - 1);
     }
@@ -553,8 +552,13 @@ __device__ __forceinline__ void bsq_k3l_cell(typename S::T up, int gD, typename 
   }
 }
 
+// (minBlocks = 1 in the launch bounds is a scheduling hint with a measured effect: without it ptxas
+// keeps the kernel at 56 - 64 registers and puts the consumers of the two shuffles 4 - 6 instructions
+// behind them; with it, it spends ~100 registers and 10 - 20 instructions of independent work in
+// between -- config 5 fills in 119 ms instead of 139.  tools/shfl_distance.py reads that distance
+// off the SASS.)
 template <class S, int BT, int GOS>
-__global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3l_fill(const BsqFillArgs A) {
+__global__ void __launch_bounds__(BSQ_K3_THREADS, 1) bsq_k3l_fill(const BsqFillArgs A) {
   typedef typename S::T T;
   typedef uint8_t PU;
   typedef BsqK3Slab<S> Slab;
@@ -593,7 +597,6 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3l_fill(const BsqFillArgs
   const T ZERO = (T)0;
   const T go = S::go(A), ge = S::ge(A);
   unsigned long long* slab_all = (unsigned long long*)A.col_h;
-  int p = 0;
 
   for (;;) {
     __syncthreads();                 // both warps are done with the previous strip and its ring
@@ -606,10 +609,10 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3l_fill(const BsqFillArgs
     int pf_polls = 0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pf_claim));
 #endif
-    while (g >= A.k3[p].strip_base + A.k3[p].nstrips) p++;  // claims only grow
+    const BsqK3Item item = A.k3_order[g];   // a strip's predecessor is always earlier in the list
+    const int p = item.pair, j = item.strip;
     const BsqPair P = A.pairs[p];
     const BsqK3Pair Q = A.k3[p];
-    const int j = g - Q.strip_base;
     const int n = P.n, m = P.m, dmin = P.dmin, dmax = P.dmax;
     const int Y = j * BW;
     const int ylast = (Y + BW - 1 < m) ? (Y + BW - 1) : m;
@@ -760,11 +763,14 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3l_fill(const BsqFillArgs
       auto group = [&](const int t0, auto flavour) {
         constexpr int FL = decltype(flavour)::value;
         constexpr bool FULLG = (FL == BSQ_K3L_FULL);
+        // The two shuffles of a step are issued as soon as the values they send are final -- before
+        // the pointer byte, the slab entry and the end-cell bookkeeping of the step they follow -- so
+        // that this off-chain work runs while they are in flight (the lone warp issues in order).
+        T inH = __shfl_sync(FULL, lastH, srcl);
+        int pay = __shfl_sync(FULL, mypay, srcl);
 #pragma unroll
         for (int ti = 0; ti < NBT; ti++) {
           const int t = t0 + ti;           // steps past nsteps - 1 (the last group) are inactive for every lane
-          const T inH = __shfl_sync(FULL, lastH, srcl);
-          const int pay = __shfl_sync(FULL, mypay, srcl);
           const uint32_t lo = (uint32_t)(pay & LETMASK);
           int gI = pay & ~LETMASK;
           T sign[K];
@@ -801,6 +807,14 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3l_fill(const BsqFillArgs
             if (FULLG || FL == BSQ_K3L_TAIL) Hend[k] = inb ? H : Hend[k];
             if (BT == BSQ_B_LOCAL) { if (H > best[k < NB ? k : 0]) { best[k < NB ? k : 0] = H; bestt[k < NB ? k : 0] = t; } }
           }
+          const T sentH = inH;         // (x, y0 - 1): next step's diagonal neighbour
+          lastH = left;
+          mypay = (int)lo | gI;
+          if (ti + 1 < NBT) {
+            if (lane31) { lastH = rH[ti + 1]; mypay = rP[ti + 1]; }
+            inH = __shfl_sync(FULL, lastH, srcl);
+            pay = __shfl_sync(FULL, mypay, srcl);
+          }
           pst[ti * G] = (PU)cw;        // idle lanes write slots nobody reads (the stride is padded to whole groups)
           bool pput;                   // lane 31 is on a row of the strip: t >= 31 and x <= x_hi
           if (FL == BSQ_K3L_RAMP) pput = put31 && (t >= G - 1);
@@ -819,12 +833,7 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3l_fill(const BsqFillArgs
             }
           }
           if (pput) Slab::put_g(pslab + ti * Slab::EPR, left, gI, tag2_out);
-          lastH = left;
-          mypay = (int)lo | gI;
-          if (ti + 1 < NBT) {
-            if (lane31) { lastH = rH[ti + 1]; mypay = rP[ti + 1]; }
-          }
-          prev_in = inH;
+          prev_in = sentH;
 #pragma unroll
           for (int k = 0; k < K; k++) sig[k] = sign[k];
         }
@@ -897,7 +906,7 @@ __global__ void __launch_bounds__(BSQ_K3_THREADS) bsq_k3l_fill(const BsqFillArgs
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(r.t_end));
       asm volatile("mov.u32 %0, %%smid;" : "=r"(r.sm));
 #endif
-      A.k3_res[g] = r;
+      A.k3_res[Q.strip_base + j] = r;
       __threadfence();
       last = (atomicAdd(A.k3_done + p, 1) == Q.nstrips - 1);
     }

@@ -189,6 +189,12 @@ struct Plan {
   int64_t k3_max_strips = 0, k3_max_slab = 0, k3_max_pairs = 0;  // maxima over chunks
 };
 
+// grid.y of bsq_pack_transcripts: segments of the longest possible transcript (n + m ops)
+inline unsigned pack_segments(const Plan& P) {
+  const int64_t seg = (P.max_nm + BSQ_PACK_SEG - 1) / BSQ_PACK_SEG;
+  return (unsigned)std::min<int64_t>(std::max<int64_t>(seg, 1), 65535);
+}
+
 }  // namespace
 
 struct bsq_ctx {
@@ -1551,7 +1557,7 @@ int pack_transcripts(bsq_ctx* ctx, BufSet& B, const Plan& P) {
              (const long long*)B.tiles.as<long long>(), B.txoff.as<long long>());
   ctx->tm.fill_launches += 3;
   if (E > 0) {
-    const int grid = (int)((E * 32 + 255) / 256);
+    const dim3 grid((unsigned)((E * 32 + 255) / 256), pack_segments(P));
     BSQ_LAUNCH(bsq_pack_transcripts, grid, 256, 0, st, (const BsqPair*)B.pairs.as<BsqPair>(), (int)E,
                (const int*)B.txlen.as<int>(), (const long long*)B.txoff.as<long long>(),
                (const char*)B.slots.as<char>(), B.packed.as<char>());
@@ -2106,7 +2112,7 @@ static int align_batch_once(bsq_ctx* ctx, const bsq_params* params, int64_t npai
         BSQ_LAUNCH(bsq_scan_tiles, 1, 256, 0, ts, tiles, nt, (const long long*)(totals + ci), totals + ci + 1);
         BSQ_LAUNCH(bsq_scan_apply, nt, 256, 0, ts, (const int*)(B.txlen.as<int>() + lo), (int)cnt,
                    (const long long*)tiles, B.txoff.as<long long>() + lo);
-        const int grid = (int)((ch.count * 32 + 255) / 256);
+        const dim3 grid((unsigned)((ch.count * 32 + 255) / 256), pack_segments(P));
         BSQ_LAUNCH(bsq_pack_transcripts, grid, 256, 0, ts, (const BsqPair*)(B.pairs.as<BsqPair>() + ch.first),
                    (int)ch.count, (const int*)B.txlen.as<int>(), (const long long*)B.txoff.as<long long>(),
                    (const char*)B.slots.as<char>(), B.packed.as<char>());

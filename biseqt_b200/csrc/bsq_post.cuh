@@ -548,12 +548,17 @@ __global__ void __launch_bounds__(32 * BSQ_WALKC_WARPS) bsq_k2_walk_coop(const B
 // the op that ends the run (a gap, or B) is handled serially.  Config 5 (10^6 ops, ~2 10^4 gap
 // runs) takes ~5 10^4 rounds instead of 10^6 dependent steps.
 //
-// The pointer rows come through two shared-memory tiles filled by the bulk-copy engine
-// (cp.async.bulk + mbarrier, one elected lane issues): while one tile is walked, the steps below it
-// are already on their way, so the walk never waits for HBM inside a strip.
+// The pointer rows come through a small cache of shared-memory tiles filled by the bulk-copy engine
+// (cp.async.bulk + mbarrier, one elected lane issues).  A walk crosses a strip in (K + 1) * 32 steps
+// and then continues in the strip to its left, ~BW rows further up: on entering a strip the tiles
+// of the next two strips are requested around the step where a diagonal path would enter them
+// (gaps move that by a few steps; the tile has room), and the steps below the current tile when
+// the walk gets near its lower edge.  Config 5 crosses 15 625 strips: without the look-ahead each
+// crossing waited for HBM (~1 us: 23 of the 40 ms its traceback took).
 // ---------------------------------------------------------------------------
 #define BSQ_K3_TILE_BYTES 8192
-#define BSQ_K3_LET_WIN 256
+#define BSQ_K3_NTILES 4
+#define BSQ_K3_LET_WIN 1024
 
 #ifndef BSQ_SIMT_EMU
 __device__ __forceinline__ uint32_t bsq_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -581,15 +586,16 @@ __device__ __forceinline__ void bsq_mbar_wait(unsigned long long* bar, uint32_t 
 template <int K, int GOS>
 __global__ void __launch_bounds__(32) bsq_k3_walk(const BsqTraceArgs A) {
   typedef typename BsqK3Unit<K>::type PU;
-  constexpr int G = 32, BW = G * K;
+  constexpr int G = 32, BW = G * K, NT = BSQ_K3_NTILES;
   constexpr int LOGK = (K == 2) ? 1 : (K == 4 ? 2 : 3);
   constexpr int STEP_BYTES = G * (int)sizeof(PU);
   constexpr int TSTEPS = BSQ_K3_TILE_BYTES / STEP_BYTES;
+  constexpr int SLACK = TSTEPS / 8;   // steps above the predicted entry step a look-ahead tile covers
   BSQ_BAIL_IF_BAD(A);
-  alignas(128) __shared__ unsigned char s_tile[2][BSQ_K3_TILE_BYTES];
-  __shared__ uint8_t s_let[2][BSQ_K3_LET_WIN];
+  alignas(128) __shared__ unsigned char s_tile[NT][BSQ_K3_TILE_BYTES];
+  alignas(16) __shared__ uint8_t s_let[2][BSQ_K3_LET_WIN];
 #ifndef BSQ_SIMT_EMU
-  alignas(8) __shared__ unsigned long long s_bar[2];
+  alignas(8) __shared__ unsigned long long s_bar[NT];
 #endif
   const int lane = threadIdx.x & 31;
   const unsigned FULL = 0xffffffffu;
@@ -602,9 +608,11 @@ __global__ void __launch_bounds__(32) bsq_k3_walk(const BsqTraceArgs A) {
     return;
   }
 #ifndef BSQ_SIMT_EMU
-  if (lane == 0) { bsq_mbar_init(&s_bar[0]); bsq_mbar_init(&s_bar[1]); }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NT; i++) bsq_mbar_init(&s_bar[i]);
+  }
   __syncwarp();
-  uint32_t phase[2] = {0u, 0u};
 #endif
   const int ex = A.ex[oi], ey = A.ey[oi];
   int x = ex, y = ey, len = 0;
@@ -612,81 +620,147 @@ __global__ void __launch_bounds__(32) bsq_k3_walk(const BsqTraceArgs A) {
   int c = y - j * BW;            // column inside the strip: lane = c >> LOGK, nibble = c & (K-1)
   int xlo = j * BW + P.dmin;
   xlo = xlo < 0 ? 0 : xlo;
-  const long long tstride = P.s0;
+  const int tstride = P.s0;
   const unsigned char* table = (const unsigned char*)(A.ptr + P.ptr_off);
   const uint8_t* oseq = A.codes + P.o_off;
   const uint8_t* mseq = A.codes + P.m_off;
   char* wr = A.slots + P.tx_slot + (long long)P.n + P.m;
   const int maxlen = P.n + P.m;
-  // tile `cur` holds steps [tlo, thi] of strip j (empty: tlo > thi); tile cur^1 may hold, or be
-  // receiving, steps [ntlo, nthi] of the same strip (nj == j)
-  int cur = 0, tlo = 1, thi = 0;
-  int nj = -1, ntlo = 1, nthi = 0;
+  // the tile cache: slot i holds (or is receiving: spend) steps [slo, shi] of strip sj; all uniform
+  int sj[NT], slo[NT], shi[NT];
+  bool spend[NT];
+  uint32_t sphase[NT];
+#pragma unroll
+  for (int i = 0; i < NT; i++) { sj[i] = -1; slo[i] = 1; shi[i] = 0; spend[i] = false; sphase[i] = 0u; }
+  int cur = 0, tlo = 1, thi = 0; // the slot being walked and its step range (empty: look one up)
+  int rr = 0;                    // next slot to overwrite (round robin, never `cur`)
+  int ahead_for = -1;            // strip whose look-ahead requests have been issued
+  int ahead_lo = 0x7fffffff;     // lowest strip a look-ahead tile has been requested for
   uint8_t* obuf = s_let[0];
   uint8_t* mbuf = s_let[1];
   int xb = x + 1, yb = y + 1;    // obuf holds o[xb .. xb+WIN), mbuf m[yb .. yb+WIN); empty
   uint32_t arrive = BSQ_MM;
-  // steps [lo, hi] of strip js -> tile b; asynchronous when the copy engine can take it
+  auto wait_slot = [&](int b) {  // b: a compile-time index after unrolling
+#ifndef BSQ_SIMT_EMU
+    if (spend[b]) { bsq_mbar_wait(&s_bar[b], sphase[b]); sphase[b] ^= 1u; }
+#endif
+    spend[b] = false;
+  };
+  // steps [lo, hi] of strip js -> slot b; asynchronous when the copy engine can take it
   auto fetch = [&](int b, int js, int lo, int hi) {
+    wait_slot(b);                // nothing may still be landing in a slot that is reused
+    sj[b] = js; slo[b] = lo; shi[b] = hi;
     const unsigned char* src = table + ((long long)js * tstride + lo) * STEP_BYTES;
     const uint32_t bytes = (uint32_t)(hi - lo + 1) * STEP_BYTES;
 #ifndef BSQ_SIMT_EMU
     if ((((unsigned long long)src) & 15ull) == 0ull) {
       if (lane == 0) bsq_bulk_load(s_tile[b], src, bytes, &s_bar[b]);
-      return true;    // completion: wait on s_bar[b]
+      spend[b] = true;
+      return;
     }
 #endif
+    __syncwarp();
     for (uint32_t i = lane; i < bytes; i += 32) s_tile[b][i] = src[i];
     __syncwarp();
-    return false;
   };
-  bool npend = false;            // tile cur^1 is still in flight
+  auto find = [&](int js, int t) {
+    int f = -1;
+#pragma unroll
+    for (int i = 0; i < NT; i++) if (sj[i] == js && t >= slo[i] && t <= shi[i]) f = i;
+    return f;
+  };
+  // request steps [.., hi] of strip js unless a slot already covers step `t`
+  auto want = [&](int js, int t, int hi) {
+    if (js < 0 || find(js, t) >= 0) return;
+    hi = hi > tstride - 1 ? tstride - 1 : hi;
+    int lo = hi - TSTEPS + 1;
+    lo = lo < 0 ? 0 : lo;
+    if (t < lo || t > hi) return;
+    if (rr == cur) rr = (rr + 1) % NT;
+    const int b = rr;
+    rr = (rr + 1) % NT;
+#pragma unroll
+    for (int i = 0; i < NT; i++) if (i == b) fetch(i, js, lo, hi);
+  };
+  // letters [b, b + WIN) of a sequence of `len` into a window, b <= pos - (WIN - 16) chosen so that the
+  // source is 16-byte aligned: every lane has all its loads in flight before it stores (a byte loop
+  // waits for HBM once per iteration: 14 us per refill, a quarter of config 5's walk)
+  auto refill = [&](uint8_t* buf, const uint8_t* seq, int pos, int len) {
+    int b = pos - (BSQ_K3_LET_WIN - 16);
+    b -= (int)((unsigned long long)(seq + b) & 15ull);
+    __syncwarp();
+    if (b >= 0) {
+      uint4 v[BSQ_K3_LET_WIN / 512];
+#pragma unroll
+      for (int q = 0; q < BSQ_K3_LET_WIN / 512; q++) {
+        const int o = q * 512 + lane * 16;
+        v[q] = make_uint4(0u, 0u, 0u, 0u);
+        if (b + o < len) v[q] = *(const uint4*)(seq + b + o);   // may read up to 15 bytes past `len`: codes[] is padded
+      }
+#pragma unroll
+      for (int q = 0; q < BSQ_K3_LET_WIN / 512; q++) *(uint4*)(buf + q * 512 + lane * 16) = v[q];
+    } else {                     // the window reaches the start of the sequence
+      b = 0;
+      for (int i = lane; i < BSQ_K3_LET_WIN; i += 32) if (i < len) buf[i] = seq[i];
+    }
+    __syncwarp();
+    return b;
+  };
+  // The round is written for a lone warp that issues in order and pays 25 - 50 cycles for every
+  // branch it resolves: all the rare upkeep (tile lookup, look-ahead requests, letter windows) sits
+  // behind ONE test, and moves are applied with selects instead of branches.
+  auto cross = [&]() {           // c < 0: into the strip on the left (select form, no branch)
+    const bool over = c < 0;
+    j -= over ? 1 : 0;
+    c += over ? BW : 0;
+    int xl = j * BW + P.dmin;
+    xl = xl < 0 ? 0 : xl;
+    xlo = over ? xl : xlo;
+    tlo = over ? 1 : tlo;
+    thi = over ? 0 : thi;
+  };
   for (;;) {
     const int t = x - xlo + (c >> LOGK);
-    if (t < tlo || t > thi) {    // the tile does not hold the current step
-      __syncwarp();
-      if (nj == j && t >= ntlo && t <= nthi) {     // the prefetched one does
-        cur ^= 1;
-#ifndef BSQ_SIMT_EMU
-        if (npend) { bsq_mbar_wait(&s_bar[cur], phase[cur]); phase[cur] ^= 1u; }
-#endif
-        tlo = ntlo; thi = nthi;
-      } else {
-#ifndef BSQ_SIMT_EMU
-        if (npend) { bsq_mbar_wait(&s_bar[cur ^ 1], phase[cur ^ 1]); phase[cur ^ 1] ^= 1u; }   // drain before reuse
-#endif
-        thi = t;
-        tlo = t - TSTEPS + 1;
-        tlo = tlo < 0 ? 0 : tlo;
-        const bool pend = fetch(cur, j, tlo, thi);
-#ifndef BSQ_SIMT_EMU
-        if (pend) { bsq_mbar_wait(&s_bar[cur], phase[cur]); phase[cur] ^= 1u; }
-#else
-        (void)pend;
-#endif
+    const bool upkeep = (t < tlo) | (t > thi) | (ahead_for != j) | ((t - tlo < 40) & (tlo > 0)) |
+                        ((x - 32 < xb) & (xb > 0)) | ((y - 32 < yb) & (yb > 0));
+    if (upkeep) {
+      if (t < tlo || t > thi) {  // the current tile does not hold this step
+        __syncwarp();
+        int f = find(j, t);
+        if (f < 0) {             // nor does any other: fetch it now (no room above: the walk goes up)
+          if (rr == cur && thi >= tlo) rr = (rr + 1) % NT;
+          f = rr;
+          rr = (rr + 1) % NT;
+          int lo = t - TSTEPS + 1;
+          lo = lo < 0 ? 0 : lo;
+#pragma unroll
+          for (int i = 0; i < NT; i++) if (i == f) fetch(i, j, lo, t);
+        }
+#pragma unroll
+        for (int i = 0; i < NT; i++) if (i == f) { wait_slot(i); tlo = slo[i]; thi = shi[i]; }
+        cur = f;
+        __syncwarp();
       }
-      npend = false;
-      nj = -1;
-      if (tlo > 0) {             // the walk goes on below: get those steps while this tile is walked
-        nj = j;
-        nthi = tlo - 1;
-        ntlo = nthi - TSTEPS + 1;
-        ntlo = ntlo < 0 ? 0 : ntlo;
-        npend = fetch(cur ^ 1, j, ntlo, nthi);
+      if (ahead_for != j) {      // entered a strip: where a diagonal path enters the next two
+        ahead_for = j;
+        int xe = x - (c + 1);    // row at which column -1 of this strip = column BW-1 of strip j-1 is reached
+#pragma unroll
+        for (int a = 1; a <= 2; a++) {
+          const int js = j - a;
+          if (js >= 0 && js < ahead_lo && xe >= 0) {   // (strip j-1 was asked for one crossing ago)
+            ahead_lo = js;
+            int xl = js * BW + P.dmin;
+            xl = xl < 0 ? 0 : xl;
+            const int te = xe - xl + (G - 1);
+            if (te >= 0) want(js, te < tstride - 1 ? te : tstride - 1, te + SLACK);
+          }
+          xe -= BW;
+        }
+      } else if (t - tlo < 40 && tlo > 0) {
+        want(j, tlo - 1, tlo - 1);  // the walk is heading for the steps below this tile
       }
-      __syncwarp();
-    }
-    if (x - 32 < xb && xb > 0) {  // the walk only moves towards smaller x and y
-      xb = x - BSQ_K3_LET_WIN; if (xb < 0) xb = 0;
-      __syncwarp();
-      for (int i = lane; i < BSQ_K3_LET_WIN; i += 32) if (xb + i < P.n) obuf[i] = oseq[xb + i];
-      __syncwarp();
-    }
-    if (y - 32 < yb && yb > 0) {
-      yb = y - BSQ_K3_LET_WIN; if (yb < 0) yb = 0;
-      __syncwarp();
-      for (int i = lane; i < BSQ_K3_LET_WIN; i += 32) if (yb + i < P.m) mbuf[i] = mseq[yb + i];
-      __syncwarp();
+      if (x - 32 < xb && xb > 0) xb = refill(obuf, oseq, x, P.n);   // the walk only moves towards smaller x and y
+      if (y - 32 < yb && yb > 0) yb = refill(mbuf, mseq, y, P.m);
     }
     // lane q looks at (x-q, y-q): column c-q of this strip, step t-q-(lanes crossed)
     const PU* tile = (const PU*)s_tile[cur];
@@ -699,47 +773,33 @@ __global__ void __launch_bounds__(32) bsq_k3_walk(const BsqTraceArgs A) {
     const unsigned vmask = __ballot_sync(FULL, valid);
     const unsigned mmask = __ballot_sync(FULL, valid && opq == BSQ_MM);
     const int nv = __popc(vmask);                       // valid cells form a prefix
-    int run = (~mmask == 0u) ? 32 : (__ffs((int)~mmask) - 1);
-    if (nv == 0) break;                                 // len == maxlen
+    const int run = (~mmask == 0u) ? 32 : (__ffs((int)~mmask) - 1);
     if (lane < run) {
       const char ch = (obuf[x - 1 - lane - xb] == mbuf[y - 1 - lane - yb]) ? 'M' : 'S';
       wr[-(len + lane + 1)] = ch;
     }
-    if (run > 0) {
-      x -= run; y -= run; len += run; c -= run;
-      arrive = BSQ_MM;
-      if (c < 0) {               // into the previous strip
-        j--;
-        c += BW;
-        xlo = j * BW + P.dmin;
-        xlo = xlo < 0 ? 0 : xlo;
-        tlo = 1; thi = 0;
-      }
+    x -= run; y -= run; len += run; c -= run;           // run == 0: nothing moves
+    arrive = run > 0 ? BSQ_MM : arrive;
+    cross();
+    // the cell that ended the run (if it was staged: run < nv) holds an op that is not a diagonal move
+    const uint32_t op = __shfl_sync(FULL, opq, run & 31);
+    if (run == nv) {
+      if (nv == 0) break;                               // len == maxlen
+      continue;                                         // the run reached the edge of what was staged (or of the strip)
     }
-    if (run == nv) continue;     // the run reached the edge of what was staged (or of the strip)
-    // the cell that ended the run holds an op that is not a diagonal move
-    const uint32_t op = __shfl_sync(FULL, opq, run);
     if (op == BSQ_MB || op == 0u || op == BSQ_MM || len >= maxlen) break;
-    char ch;
-    if (op == BSQ_MD) {
-      ch = 'D'; x--;
-    } else {
-      ch = 'I'; y--;
-      if (--c < 0) {
-        j--;
-        c += BW;
-        xlo = j * BW + P.dmin;
-        xlo = xlo < 0 ? 0 : xlo;
-        tlo = 1; thi = 0;
-      }
-    }
+    const bool del = (op == BSQ_MD);
+    x -= del ? 1 : 0;
+    y -= del ? 0 : 1;
+    c -= del ? 0 : 1;
+    cross();
     arrive = op;
     len++;
-    if (lane == 0) wr[-len] = ch;
+    if (lane == 0) wr[-len] = del ? 'D' : 'I';
   }
-#ifndef BSQ_SIMT_EMU
-  if (npend) bsq_mbar_wait(&s_bar[cur ^ 1], phase[cur ^ 1]);   // nothing may still be landing in shared memory at exit
-#endif
+  // nothing may still be landing in shared memory at exit
+#pragma unroll
+  for (int i = 0; i < NT; i++) wait_slot(i);
   if (lane == 0) {
     A.txlen[oi] = len;
     A.sx[oi] = x;
@@ -916,7 +976,9 @@ __global__ void __launch_bounds__(256) bsq_make_pairs_uniform(const long long* o
   out[e] = bp;
 }
 
-// pack transcripts: one warp per pair copies slot tail -> packed[off]
+// pack transcripts: slot tail -> packed[off]; one warp per pair and segment of BSQ_PACK_SEG ops
+// (blockIdx.y = segment: config 5's single 2 10^6-op transcript took one warp 7 ms)
+#define BSQ_PACK_SEG 8192
 __global__ void __launch_bounds__(256) bsq_pack_transcripts(const BsqPair* pairs, int npairs,
                                                             const int* txlen, const long long* off,
                                                             const char* slots, char* packed) {
@@ -925,9 +987,12 @@ __global__ void __launch_bounds__(256) bsq_pack_transcripts(const BsqPair* pairs
   if (warp >= npairs) return;
   const int oi = pairs[warp].pad;
   const int len = txlen[oi];
+  const long long lo = (long long)blockIdx.y * BSQ_PACK_SEG;
+  if (lo >= len) return;
+  const int hi = (int)(lo + BSQ_PACK_SEG < len ? lo + BSQ_PACK_SEG : len);
   const char* src = slots + pairs[warp].tx_slot + (long long)pairs[warp].n + pairs[warp].m - len;
   char* dst = packed + off[oi];
-  for (int i = lane; i < len; i += 32) dst[i] = src[i];
+  for (int i = (int)lo + lane; i < hi; i += 32) dst[i] = src[i];
 }
 
 // ===========================================================================

@@ -35,7 +35,7 @@ import bench_workloads as bw  # noqa: E402
 
 WORKLOAD_PAIRS = {'c2_int': 1000000, 'c2_logodds': 1000000, 'c3_int': 100000, 'c3_logodds': 100000,
                   'c3_blocal_int': 100000, 'c3_blocal_logodds': 100000,
-                  'c4_int': 10000, 'c1': 1, 'c2w_int': 400000, 'c5_int': 1, 'c5_logodds': 1, 'c5s_int': 1, 'c5s_logodds': 1}
+                  'c4_int': 10000, 'c1': 1, 'c2w_int': 400000, 'c5_int': 1, 'c5_logodds': 1, 'c5s_int': 64, 'c5s_logodds': 64}
 
 
 # which SM pipes each microbenchmarked rate (bsq_microbench, csrc/bsq_microbench.cu) spans; the
@@ -467,7 +467,7 @@ def main():
     ap.add_argument('--no-extras', action='store_true', help='skip the secondary workloads')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline')
     host_group = None
-    ap.add_argument('--extras', default='c2_logodds,c3_int,c3_logodds,c3_blocal_int,c3_blocal_logodds,c4_int,c5_int,c1',
+    ap.add_argument('--extras', default='c2_logodds,c3_int,c3_logodds,c3_blocal_int,c3_blocal_logodds,c4_int,c5_int,c5_logodds,c5s_int,c1',
                     help='comma-separated secondary workloads (single GPU only)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup

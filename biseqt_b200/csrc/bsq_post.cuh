@@ -584,7 +584,7 @@ __device__ __forceinline__ void bsq_mbar_wait(unsigned long long* bar, uint32_t 
 #endif
 
 template <int K, int GOS>
-__global__ void __launch_bounds__(32) bsq_k3_walk(const BsqTraceArgs A) {
+__global__ void __launch_bounds__(32, 1) bsq_k3_walk(const BsqTraceArgs A) {
   typedef typename BsqK3Unit<K>::type PU;
   constexpr int G = 32, BW = G * K, NT = BSQ_K3_NTILES;
   constexpr int LOGK = (K == 2) ? 1 : (K == 4 ? 2 : 3);

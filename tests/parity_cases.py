@@ -130,6 +130,25 @@ def run_very_wide_bands(eng, seed, length=1300, radius=560, npairs=1):
         check_batch(eng, probs)
 
 
+def run_wide_band_batch(eng, seed, lens=(3000, 9000, 5200, 12000, 700, 8000), radius=600):
+    """Several wide-band pairs of different lengths in one batch: their strips are claimed from ONE
+    strip-major work list (strip j of every pair before strip j+1 of any; pairs run out of strips at
+    different levels), every pair against the oracle."""
+    rng = np.random.default_rng(seed)
+    for typ, fam, gomode in ((0, 1, -1), (1, 2, 0), (2, 1, 1)):
+        S, go, ge = score_family(rng, 4, fam, gomode)
+        probs = []
+        for n in lens:
+            o = rng.integers(0, 4, size=n).astype(np.uint8)
+            t, _ = mutate(rng, o, 4, subst=0.08, go=0.02, ge=0.3)
+            c = int(rng.integers(-5, 6))
+            dr = (c - radius, c + radius)
+            if typ == 0:
+                dr = (min(dr[0], 0, n - len(t)), max(dr[1], 0, n - len(t)))
+            probs.append(dict(origin=o, mutant=t, subst=S, go=go, ge=ge, mode=1, type=typ, diag_range=dr, L=4))
+        check_batch(eng, probs)
+
+
 def run_forced_k3(make_engine, seed, count=150, cfgs=(0, 1, 2), wide_len=700):
     """The strip kernel on every banded problem, all three strip geometries."""
     os.environ['BSQ_FORCE_K3'] = '1'

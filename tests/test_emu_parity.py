@@ -56,6 +56,10 @@ def test_emu_very_wide_band(emu_engine):
     pc.run_very_wide_bands(emu_engine, seed=91, length=1100, radius=530)
 
 
+def test_emu_wide_band_batch(emu_engine):
+    pc.run_wide_band_batch(emu_engine, seed=141, lens=(300, 900, 520, 1200, 70, 800), radius=530)
+
+
 def test_emu_forced_k3(emu_lib):
     pc.run_forced_k3(lambda: batch.Engine(0, lib=emu_lib), seed=95, count=120)
 

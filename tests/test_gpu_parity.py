@@ -64,6 +64,12 @@ def test_gpu_very_wide_bands(gpu_engine):
     pc.run_very_wide_bands(gpu_engine, seed=92, length=5000, radius=1500, npairs=2)
 
 
+@pytest.mark.gpu
+def test_gpu_wide_band_batch(gpu_engine):
+    pc.run_wide_band_batch(gpu_engine, seed=141)
+    pc.run_wide_band_batch(gpu_engine, seed=142, lens=(20000, 2600, 15000, 9000, 1100, 4000, 12000, 6100, 300), radius=1100)
+
+
 def test_gpu_forced_k3():
     pc.run_forced_k3(lambda: batch.Engine(0), seed=95, count=400)
 

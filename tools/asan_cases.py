@@ -28,6 +28,7 @@ def main():
     pc.run_banded_interior(eng, seed=43, length=200, npairs=2)
     pc.run_wide_bands(eng, seed=41, length=120, radii=(40, 100, 300))
     pc.run_very_wide_bands(eng, seed=91, length=1100, radius=530)
+    pc.run_wide_band_batch(eng, seed=141, lens=(300, 900, 520, 1200, 70, 800), radius=530)
     pc.run_edge_cases(eng)
     pc.run_stats(eng, seed=97, npairs=10, hi=60)
     pc.run_two_phase(eng, seed=61)

@@ -169,9 +169,9 @@ def run_forced_k3(make_engine, seed, count=150, cfgs=(0, 1, 2), wide_len=700):
                 run_banded_interior(eng, seed=seed + 7 + cfg, length=330, npairs=2)
                 # bands wide enough (W = 501 >= 31 (R + K) + R + K) for the strip kernel's ungated interior steps
                 run_very_wide_bands(eng, seed=seed + 11 + cfg, length=wide_len, radius=250, npairs=2)
-                # a narrow band long enough for the traceback's vector-loaded 1024-letter windows and for
-                # tiles requested ahead across dozens of strips
-                run_very_wide_bands(eng, seed=seed + 17 + cfg, length=2600, radius=24, npairs=2)
+                # a narrow band long enough for the traceback's vector-loaded 1024-letter windows, for tiles
+                # requested ahead across dozens of strips, and for a transcript packed in two segments
+                run_very_wide_bands(eng, seed=seed + 17 + cfg, length=4300, radius=24, npairs=2)
             finally:
                 eng.close()
     finally:

@@ -140,22 +140,9 @@ __device__ __forceinline__ void bsq_cell2(typename S::T up, int gD, typename S::
     I = S::open(I, gI, go);
   }
   const T M = S::add(diag, sig);  // :234
-#if defined(BSQ_F64_PMOV) && !defined(BSQ_SIMT_EMU)
-  T h = I;
-  if constexpr (!S::IS_INT) {
-    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %0;\n\t@p mov.f64 %0, %1;\n\t}" : "+d"(h) : "d"(D));
-    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %0;\n\t@p mov.f64 %0, %1;\n\t}" : "+d"(h) : "d"(M));
-    if (HASB) asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %0;\n\t@p mov.f64 %0, %1;\n\t}" : "+d"(h) : "d"(bval));
-  } else {
-    h = D > I ? D : I;
-    h = M > h ? M : h;
-    if (HASB) h = bval > h ? bval : h;
-  }
-#else
   T h = D > I ? D : I;
   h = M > h ? M : h;
   if (HASB) h = bval > h ? bval : h;
-#endif
   eD = (D == h);
   eI = (I == h);
   eM = (M == h);

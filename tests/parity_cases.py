@@ -816,6 +816,38 @@ def run_std_as_band(make_engine, seed, sizes=((300, 280), (256, 700), (1000, 104
         eng_k1.close()
 
 
+def run_std_as_band_many(make_engine, seed, npairs=300, n=1000):
+    """Hundreds of big STD GLOBAL pairs in one batch, planned as full-width bands (16 strips each,
+    one strip-major work list) against the same batch on K1 (which the other tests pin to the oracle)."""
+    rng = np.random.default_rng(seed)
+    S, go, ge = score_family(rng, 4, 2, -1)
+    probs = []
+    for i in range(npairs):
+        o = rng.integers(0, 4, size=int(rng.integers(n // 2, n + 1))).astype(np.uint8)
+        t, _ = mutate(rng, o, 4, subst=0.1, go=0.05, ge=0.3)
+        if len(t) < 256:
+            t = np.concatenate([t, rng.integers(0, 4, size=256 - len(t)).astype(np.uint8)])
+        probs.append(dict(origin=o, mutant=t, subst=S, go=go, ge=ge, mode=0, type=0, diag_range=None))
+    eng = make_engine()
+    os.environ['BSQ_NO_STD_BAND'] = '1'
+    try:
+        eng_k1 = make_engine()
+    finally:
+        del os.environ['BSQ_NO_STD_BAND']
+    try:
+        r = engine_batch(eng, probs)
+        r1 = engine_batch(eng_k1, probs)
+        assert np.array_equal(r.status, r1.status) and np.array_equal(r.score, r1.score)
+        assert np.array_equal(r.end_x, r1.end_x) and np.array_equal(r.end_y, r1.end_y)
+        assert np.array_equal(r.start_x, r1.start_x) and np.array_equal(r.start_y, r1.start_y)
+        assert r.transcripts() == r1.transcripts()
+        for i in (0, npairs // 2, npairs - 1):
+            same_as(oracle_one(probs[i]), r, i, what='pair %d of a big STD GLOBAL batch' % i)
+    finally:
+        eng.close()
+        eng_k1.close()
+
+
 def run_lifetime(make_engine):
     """Batches that outlive their engine (an Engine closed, or collected, before its SolvedBatch /
     ResidentBatch): release and every other call on them must not touch the dead context."""

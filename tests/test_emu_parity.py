@@ -90,6 +90,7 @@ def test_emu_multi(emu_lib):
 
 def test_emu_std_as_band(emu_lib):
     pc.run_std_as_band(lambda: batch.Engine(0, lib=emu_lib), seed=131, sizes=((300, 280), (256, 420)))
+    pc.run_std_as_band_many(lambda: batch.Engine(0, lib=emu_lib), seed=133, npairs=12, n=520)
 
 
 def test_emu_lifetime(emu_lib):

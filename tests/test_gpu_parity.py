@@ -103,6 +103,7 @@ def test_gpu_multi():
 
 def test_gpu_std_as_band():
     pc.run_std_as_band(lambda: batch.Engine(0), seed=131)
+    pc.run_std_as_band_many(lambda: batch.Engine(0), seed=133)
 
 
 def test_gpu_lifetime():

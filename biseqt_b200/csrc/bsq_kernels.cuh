@@ -322,7 +322,10 @@ __device__ __forceinline__ void bsq_k1_row(
 }
 
 template <class S, int G, int K, bool BALL, int EALL, int GOS>
-__global__ void __launch_bounds__(128) bsq_k1_fill(const BsqFillArgs A) {
+// (minBlocks = 3 for the F64 instantiations is a scheduling hint: ptxas keeps ~160 registers either way,
+// but orders the row loop better with it -- 586 -> 625 GCUPS on 150 bp log-odds pairs; 2 gives 619, none 586.
+// The integer ones and K1h are fastest without a hint: profiles/r02_launch_bounds_sweep.txt.)
+__global__ void __launch_bounds__(128, S::IS_INT ? 0 : 3) bsq_k1_fill(const BsqFillArgs A) {
   typedef typename S::T T;
   static_assert(K <= 32, "end-cell positions are packed as x*32 + k");
   BSQ_BAIL_IF_BAD(A);
@@ -663,8 +666,16 @@ __device__ __forceinline__ void bsq_k2_step_fast(
   for (int w = 0; w < WPS; w++) pout[w * BSQ_FILL_THREADS] = cur[w];
 }
 
+// minBlocks hint of bsq_k2_fill (0 = none): the 32 x 16 integer geometry (bands of 257 - 512 diagonals,
+// config 4) lands at 128 registers = 4 blocks per SM on its own; capped at 96 it runs 5 and fills 9 %
+// faster (1171 -> 1278 GCUPS on 4096 config-4 pairs).  Every hint tried on the 8 x 18 integer and the
+// 16 x 10 F64 geometries (config 3) cost 0 - 20 %, so it is set per instantiation
+// (profiles/r02_launch_bounds_sweep.txt).
+template <class S, int G, int C, int BLOCAL>
+constexpr int bsq_k2_minblocks() { return (S::IS_INT && G == 32 && C == 16 && BLOCAL == 0) ? 5 : 0; }
+
 template <class S, int G, int C, int BLOCAL, int GOS>
-__global__ void __launch_bounds__(128) bsq_k2_fill(const BsqFillArgs A) {
+__global__ void __launch_bounds__(128, bsq_k2_minblocks<S, G, C, BLOCAL>()) bsq_k2_fill(const BsqFillArgs A) {
   typedef typename S::T T;
   static_assert(C % 2 == 0 && C <= 32, "lanes own an even number of diagonals, at most 32");
   constexpr int HC = C / 2;

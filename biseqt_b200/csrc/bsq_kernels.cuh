@@ -671,11 +671,15 @@ __device__ __forceinline__ void bsq_k2_step_fast(
 // faster (1171 -> 1278 GCUPS on 4096 config-4 pairs).  Every hint tried on the 8 x 18 integer and the
 // 16 x 10 F64 geometries (config 3) cost 0 - 20 %, so it is set per instantiation
 // (profiles/r02_launch_bounds_sweep.txt).
-template <class S, int G, int C, int BLOCAL>
-constexpr int bsq_k2_minblocks() { return (S::IS_INT && G == 32 && C == 16 && BLOCAL == 0) ? 5 : 0; }
+template <class S, int G, int C, int BLOCAL, int GOS>
+constexpr int bsq_k2_minblocks() {
+  if (S::IS_INT && G == 32 && C == 16 && BLOCAL == 0) return 5;
+  if (S::IS_INT && G == 8 && C == 18 && BLOCAL == 2 && GOS == 0) return 5;   // banded LOCAL, packed keys: 1006 -> 1025 GCUPS
+  return 0;
+}
 
 template <class S, int G, int C, int BLOCAL, int GOS>
-__global__ void __launch_bounds__(128, bsq_k2_minblocks<S, G, C, BLOCAL>()) bsq_k2_fill(const BsqFillArgs A) {
+__global__ void __launch_bounds__(128, bsq_k2_minblocks<S, G, C, BLOCAL, GOS>()) bsq_k2_fill(const BsqFillArgs A) {
   typedef typename S::T T;
   static_assert(C % 2 == 0 && C <= 32, "lanes own an even number of diagonals, at most 32");
   constexpr int HC = C / 2;
